@@ -1,0 +1,183 @@
+"""TEST INFRASTRUCTURE ONLY — generates tests/golden/*.npz by running the UNMODIFIED reference
+(/root/reference, imported through oracle/ref_import.py).  Run in the build container:
+
+    python -m oracle.make_golden
+
+What runs reference code here:
+  * code/ddm_inversion/inversion_utils.py  inversion_forward_process / inversion_reverse_process   (unmodified)
+  * code/models.py                         PipelineWrapper.{sample_xts_from_x0,get_zs_from_xts,
+                                           reverse_step_with_custom_noise}, AudioLDMWrapper.{get_variance,
+                                           get_alpha_prod_t_prev}                                   (unmodified)
+  * code/audioldm/latent_diffusion/openaimodel.py  UNetModel (the only in-tree U-Net)               (unmodified)
+  * code/audioldm/audio/stft.py            TacotronSTFT.mel_spectrogram                             (unmodified)
+  * code/audioldm/variational_autoencoder/modules.py Encoder / Decoder, code/audioldm/hifigan/models.py Generator
+What is substituted (absent third-party code): the diffusers scheduler object -> oracle.ddpm_oracle.MiniDDIM,
+the diffusers U-Net module tree -> the vendored UNetModel called from an overridden `unet_forward`,
+text encoders -> fixed seeded embedding vectors.
+"""
+from __future__ import annotations
+
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, ROOT)
+
+from oracle import ref_import, unet_torch as U          # noqa: E402
+from oracle.ddpm_oracle import MiniDDIM                  # noqa: E402
+from audioeditingcode_b200 import unet_config as C      # noqa: E402
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def prompt_vector(prompt: str, dim: int = 512) -> torch.Tensor:
+    """Deterministic stand-in for the CLAP text projection: L2-normalised N(0,1) seeded by the prompt."""
+    seed = sum((i + 1) * ord(c) for i, c in enumerate(prompt)) % (2 ** 31)
+    g = torch.Generator().manual_seed(1000 + seed)
+    return torch.nn.functional.normalize(torch.randn(1, dim, generator=g), dim=-1)
+
+
+def build_ldm_unet(ref, cfg, weights):
+    assert cfg.transformer_specs == (None,)
+    ch = cfg.block_out_channels
+    mult = [c // ch[0] for c in ch]
+    att = [2 ** i for i, a in enumerate(cfg.attn_levels) if a]
+    m = ref.openaimodel.UNetModel(
+        image_size=64, extra_film_condition_dim=cfg.class_embed_dim, extra_film_use_concat=True,
+        in_channels=cfg.in_channels, out_channels=cfg.out_channels, model_channels=ch[0],
+        attention_resolutions=att, num_res_blocks=cfg.layers_per_block, channel_mult=mult,
+        num_head_channels=ch[-1] // cfg.num_heads[-1], use_spatial_transformer=True).eval()
+    m.load_state_dict(U.canonical_to_ldm(cfg, weights))
+    return m
+
+
+def make_fake_wrapper(ref, cfg, weights, n_steps, prediction_type="epsilon"):
+    """Reference AudioLDMWrapper with __init__ bypassed: the loop/scheduler math is the
+    reference's own; only the absent diffusers objects are substituted."""
+    unet = build_ldm_unet(ref, cfg, weights)
+
+    class Fake(ref.models.AudioLDMWrapper):
+        def __init__(self):
+            torch.nn.Module.__init__(self)
+            self.model_id = "fake/audioldm"
+            self.device = torch.device("cpu")
+            self.double_precision = False
+            sched = MiniDDIM(cfg.beta_start, cfg.beta_end, prediction_type=prediction_type)
+            sched.set_timesteps(n_steps)
+            self.model = types.SimpleNamespace(
+                unet=types.SimpleNamespace(config=types.SimpleNamespace(in_channels=cfg.in_channels)),
+                scheduler=sched)
+            self.calls = 0
+
+        def encode_text(self, prompts, **kw):
+            return None, torch.cat([prompt_vector(p) for p in prompts], 0), None
+
+        def unet_forward(self, sample, timestep, encoder_hidden_states=None, class_labels=None, **kw):
+            self.calls += 1
+            t = timestep if torch.is_tensor(timestep) else torch.tensor(timestep)
+            t = t.reshape(-1).expand(sample.shape[0])
+            with torch.no_grad():
+                out = unet(sample, t, y=class_labels)
+            return ref_import.UNet2DConditionOutput(sample=out), None, None
+
+    return Fake()
+
+
+def run_loops(ref, cfg, weights, n_steps, H, W, src, tgt, cfg_src, cfg_tar, tstart, pred, seed, cutoff=None):
+    model = make_fake_wrapper(ref, cfg, weights, n_steps, pred)
+    g = torch.Generator().manual_seed(seed)
+    x0 = 0.5 * torch.randn(1, cfg.in_channels, H, W, generator=g)
+    # replicate the reference's N randn_like draws (models.py:79-81) to hand them to the port explicitly
+    torch.manual_seed(seed + 1)
+    noise = torch.stack([torch.randn_like(x0)[0] for _ in range(n_steps)])
+    torch.manual_seed(seed + 1)
+    with torch.no_grad():
+        xt, zs, xts, _ = ref.inversion_utils.inversion_forward_process(
+            model, x0, etas=1.0, prompts=list(src), cfg_scales=list(cfg_src), num_inference_steps=n_steps,
+            numerical_fix=True, cutoff_points=cutoff)
+        raw_xts = xts.clone()
+        ts = torch.tensor(tstart, dtype=torch.int)
+        skip = n_steps - ts
+        w_edit, _ = ref.inversion_utils.inversion_reverse_process(
+            model, xT=xts, tstart=ts, etas=1.0, prompts=list(tgt), neg_prompts=[""], cfg_scales=list(cfg_tar),
+            zs=zs[:int(n_steps - min(skip))], cutoff_points=cutoff)
+    return dict(x0=x0, noise=noise, zs=zs, xts=xts, w_edit=w_edit,
+                uncond=prompt_vector(""), src=torch.cat([prompt_vector(p) for p in src]),
+                tgt=torch.cat([prompt_vector(p) for p in tgt]))
+
+
+def save(name, **arrs):
+    os.makedirs(GOLD, exist_ok=True)
+    out = {}
+    for k, v in arrs.items():
+        out[k] = v.detach().cpu().numpy() if torch.is_tensor(v) else np.asarray(v)
+    np.savez_compressed(os.path.join(GOLD, name), **out)
+    print("wrote", name, {k: tuple(v.shape) for k, v in out.items()})
+
+
+def main():
+    ref = ref_import.load()
+    torch.set_num_threads(8)
+    cfg = C.preset("tiny-audioldm")
+    w = U.synthetic_weights(cfg, seed=0)
+    H, W, N = 16, 16, 10
+
+    # (1) single U-Net evaluation by the vendored UNetModel
+    unet = build_ldm_unet(ref, cfg, w)
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(3, 8, H, W, generator=g)
+    t = torch.tensor([981, 501, 1])
+    y = torch.cat([prompt_vector(p) for p in ("", "a dog barking", "piano")])
+    with torch.no_grad():
+        eps = unet(x, t, y=y)
+    save("unet_tiny_audioldm.npz", x=x, t=t, y=y, eps=eps, weight_seed=0)
+
+    # (2) loops, eps-prediction, single prompt
+    r = run_loops(ref, cfg, w, N, H, W, ["a recording of a dog"], ["a recording of a cat"], [3.0], [12.0],
+                  [N // 2 + 2], "epsilon", seed=21)
+    save("loop_eps_single.npz", n_steps=N, tstart=[N // 2 + 2], cfg_src=[3.0], cfg_tar=[12.0], **r)
+
+    # (3) loops, v-prediction (TANGO scheduler branch of models.py:92-93,104-105,133-134,144-145)
+    r = run_loops(ref, cfg, w, N, H, W, ["rain"], ["thunder"], [1.0], [3.0], [N], "v_prediction", seed=31)
+    save("loop_vpred_single.npz", n_steps=N, tstart=[N], cfg_src=[1.0], cfg_tar=[3.0], **r)
+
+    # (4) multi-prompt with per-prompt tstart (mask-fix branch inversion_utils.py:308-315) — H=32 so the
+    #     15-tap blur's reflect padding (needs H, W > 7) is legal
+    r = run_loops(ref, cfg, w, N, 32, W, ["speech", "music"], ["a choir", "a violin"], [3.0, 2.0], [5.0, 8.0],
+                  [8, 6], "epsilon", seed=41)
+    save("loop_eps_multi.npz", n_steps=N, tstart=[8, 6], cfg_src=[3.0, 2.0], cfg_tar=[5.0, 8.0], **r)
+
+    # (5) uncond-only forward (prompts == [""], inversion_utils.py:86,110-111)
+    model = make_fake_wrapper(ref, cfg, w, N)
+    g = torch.Generator().manual_seed(51)
+    x0 = 0.5 * torch.randn(1, 8, H, W, generator=g)
+    torch.manual_seed(52)
+    noise = torch.stack([torch.randn_like(x0)[0] for _ in range(N)])
+    torch.manual_seed(52)
+    with torch.no_grad():
+        _, zs, xts, _ = ref.inversion_utils.inversion_forward_process(
+            model, x0, etas=1.0, prompts=[""], cfg_scales=[3.5], num_inference_steps=N, numerical_fix=True)
+    assert model.calls == N
+    save("loop_eps_uncond_only.npz", n_steps=N, x0=x0, noise=noise, zs=zs, xts=xts, uncond=prompt_vector(""))
+
+    # (6) scheduler scalars through the reference's own get_variance / get_alpha_prod_t_prev
+    for n in (50, 100, 200):
+        model = make_fake_wrapper(ref, cfg, w, n)
+        ts = model.model.scheduler.timesteps
+        var, ap = [], []
+        for tt in ts:
+            prev = tt - 1000 // n
+            var.append(float(model.get_variance(tt, prev)))
+            ap.append(float(model.get_alpha_prod_t_prev(prev)))
+        save(f"sched_{n}.npz", timesteps=ts, variance=np.asarray(var, np.float32),
+             alpha_prod_t_prev=np.asarray(ap, np.float32),
+             alphas_cumprod=model.model.scheduler.alphas_cumprod)
+
+
+if __name__ == "__main__":
+    main()

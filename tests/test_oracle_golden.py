@@ -1,0 +1,86 @@
+"""The oracle (oracle/ddpm_oracle.py, oracle/unet_torch.py) pinned against golden vectors produced by the
+UNMODIFIED reference (oracle/make_golden.py).  CPU only."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import ddpm_oracle as D
+from oracle import unet_torch as U
+from tests.helpers import load_golden, tiny_cfg_and_weights, oracle_unet_fn, make_sched
+
+
+def test_unet_restatement_matches_vendored_unetmodel_bitexact():
+    g = load_golden("unet_tiny_audioldm.npz")
+    cfg, w = tiny_cfg_and_weights()
+    with torch.no_grad():
+        eps = U.unet_forward(cfg, w, g["x"], g["t"], class_labels=g["y"])[0]
+    assert torch.equal(eps, g["eps"])
+
+
+@pytest.mark.parametrize("name,pred", [("loop_eps_single.npz", "epsilon"), ("loop_vpred_single.npz", "v_prediction"),
+                                       ("loop_eps_multi.npz", "epsilon")])
+def test_loops_match_reference_bitexact(name, pred):
+    g = load_golden(name)
+    cfg, w = tiny_cfg_and_weights()
+    N = int(g["n_steps"])
+    sched = make_sched(cfg, N, pred)
+    P = g["src"].shape[0]
+    fn_src = oracle_unet_fn(cfg, w, g["uncond"], g["src"])
+    xt, zs, xts = D.inversion_forward_process(sched, fn_src, g["x0"], g["noise"], 1.0, P,
+                                              [float(v) for v in g["cfg_src"]], prompts=["x"] * P)
+    assert torch.equal(zs, g["zs"])
+    assert torch.equal(xts, g["xts"])
+    tstart = g["tstart"].to(torch.int)
+    fn_tgt = oracle_unet_fn(cfg, w, g["uncond"], g["tgt"])
+    skip = N - tstart
+    w_edit = D.inversion_reverse_process(sched, fn_tgt, xts, zs[:int(N - min(skip))], tstart, 1.0, P,
+                                         [float(v) for v in g["cfg_tar"]])
+    assert torch.equal(w_edit, g["w_edit"])
+
+
+def test_uncond_only_forward():
+    g = load_golden("loop_eps_uncond_only.npz")
+    cfg, w = tiny_cfg_and_weights()
+    N = int(g["n_steps"])
+    sched = make_sched(cfg, N)
+    calls = []
+    base = oracle_unet_fn(cfg, w, g["uncond"], None)
+
+    def fn(x, t, which):
+        calls.append(which)
+        return base(x, t, which)
+    _, zs, xts = D.inversion_forward_process(sched, fn, g["x0"], g["noise"], 1.0, 1, [3.5], uncond_only=True)
+    assert calls == ["uncond"] * N                      # inversion_utils.py:86,110-111
+    assert torch.equal(zs, g["zs"]) and torch.equal(xts, g["xts"])
+    assert torch.count_nonzero(zs[0]) == 0              # inversion_utils.py:133
+
+
+@pytest.mark.parametrize("n", [50, 100, 200])
+def test_scheduler_kats(n):
+    g = load_golden(f"sched_{n}.npz")
+    cfg, _ = tiny_cfg_and_weights()
+    s = make_sched(cfg, n)
+    assert torch.equal(s.timesteps, g["timesteps"])
+    assert torch.equal(s.timesteps, torch.arange(n).flip(0) * (1000 // n) + 1)   # leading spacing, offset 1
+    assert torch.equal(s.alphas_cumprod, g["alphas_cumprod"])
+    for i, t in enumerate(s.timesteps):
+        prev = int(t) - 1000 // n
+        assert float(D.get_variance(s, int(t), prev)) == pytest.approx(float(g["variance"][i]), rel=0, abs=0)
+        assert float(D.alpha_prod_t_prev(s, prev)) == float(g["alpha_prod_t_prev"][i])
+
+
+def test_replay_invariant_F9():
+    """same prompt/cfg replays wts[k] bit-exactly for k>=1; final miss = sigma*z of the dropped noise."""
+    g = load_golden("loop_eps_single.npz")
+    cfg, w = tiny_cfg_and_weights()
+    N = int(g["n_steps"])
+    sched = make_sched(cfg, N)
+    fn = oracle_unet_fn(cfg, w, g["uncond"], g["src"])
+    xt = g["xts"][N][None]
+    cfgm, _ = D.build_cfg_maps(1, g["x0"].shape[1:], [float(g["cfg_src"][0])], None)
+    for it, t in enumerate(sched.timesteps):
+        idx = N - it - 1
+        eps = D.cfg_combine(fn(xt, int(t), "uncond"), fn(xt, int(t), "cond"), cfgm)
+        xt = D.reverse_step_with_custom_noise(sched, eps, t, xt, g["zs"][idx][None], 1.0)
+        if idx >= 1:
+            assert torch.equal(xt[0], g["xts"][idx])
