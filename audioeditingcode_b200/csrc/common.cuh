@@ -1,0 +1,53 @@
+// Shared host-side helpers for libaedit: error reporting, launch accounting, small device utilities.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include <atomic>
+
+#include "../../include/aedit.h"
+
+namespace aedit {
+
+extern thread_local char g_err[512];
+extern std::atomic<long long> g_launches;
+
+inline int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define AE_CHECK_ARG(cond, ...)                     \
+  do {                                              \
+    if (!(cond)) return ::aedit::fail(AE_EINVAL, __VA_ARGS__); \
+  } while (0)
+
+// call after every kernel launch
+inline int launched(const char* what) {
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  cudaError_t e = cudaPeekAtLastError();
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return fail(AE_ECUDA, "%s: %s", what, cudaGetErrorString(e));
+  }
+  return AE_OK;
+}
+
+inline cudaStream_t as_stream(ae_stream s) { return reinterpret_cast<cudaStream_t>(s); }
+
+inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
+
+__device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+
+struct __align__(16) bf16x8 {
+  __nv_bfloat162 v[4];
+};
+
+}  // namespace aedit

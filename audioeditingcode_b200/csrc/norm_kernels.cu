@@ -1,0 +1,255 @@
+// GroupNorm(+SiLU) and LayerNorm producers of the tensor-core operands (K3 of SURVEY.md §2.2).
+//   ae_groupnorm : diffusers ResnetBlock2D.norm1/norm2, Transformer2DModel.norm, conv_norm_out
+//                  (in-tree: openaimodel.py:213-216,238-239 with util.py:240-242; attention.py:75-78)
+//   ae_layernorm : BasicTransformerBlock.norm1/2/3 (attention.py:393-395)
+// Both read the fp32 residual stream (channels-last) and write the bf16 operand the next GEMM loads by TMA.
+// Statistics are accumulated per sample in a fixed order (no atomics on data) so a sample's result does not
+// depend on what else is in the batch.
+#include "common.cuh"
+
+namespace aedit {
+namespace {
+
+constexpr int kGNThreads = 256;
+constexpr int kMaxSplits = 32;
+
+struct GNArgs {
+  const float* x1;
+  const float* x2;
+  int C1, C2, C, G, cpg;
+  int B;
+  long long HW;
+  int S;            // position splits per sample
+  long long chunk;  // positions per split
+  float eps;
+  const float* gamma;
+  const float* beta;
+  int silu;
+  __nv_bfloat16* out;
+  __nv_bfloat16* raw_out;
+  float* cat_out;
+  double* partial;     // [B, S, G, 2]
+  float* stats;        // [B, G, 2] mean, rstd
+  unsigned int* counters;  // [B]
+};
+
+__device__ __forceinline__ float load_cat(const GNArgs& a, long long row, int c) {
+  return c < a.C1 ? a.x1[row * a.C1 + c] : a.x2[row * a.C2 + (c - a.C1)];
+}
+
+// grid (S, B).  Each CTA reduces `chunk` positions x all channels, then the last CTA of a sample finalises.
+__global__ void __launch_bounds__(kGNThreads) gn_stats_kernel(GNArgs a) {
+  extern __shared__ float sm[];  // [2*C] per-channel sum / sumsq
+  __shared__ bool is_last;
+  const int s = blockIdx.x, b = blockIdx.y;
+  const long long p0 = (long long)s * a.chunk;
+  const long long p1 = min(a.HW, p0 + a.chunk);
+  float* ssum = sm;
+  float* ssq = sm + a.C;
+  for (int c = threadIdx.x; c < a.C; c += kGNThreads) {
+    float su = 0.f, sq = 0.f;
+    for (long long p = p0; p < p1; ++p) {
+      const float v = load_cat(a, (long long)b * a.HW + p, c);
+      su += v;
+      sq += v * v;
+    }
+    ssum[c] = su;
+    ssq[c] = sq;
+  }
+  __syncthreads();
+  for (int g = threadIdx.x; g < a.G; g += kGNThreads) {
+    double su = 0.0, sq = 0.0;
+    for (int c = g * a.cpg; c < (g + 1) * a.cpg; ++c) {
+      su += (double)ssum[c];
+      sq += (double)ssq[c];
+    }
+    double* dst = a.partial + (((long long)b * a.S + s) * a.G + g) * 2;
+    dst[0] = su;
+    dst[1] = sq;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int prev = atomicAdd(&a.counters[b], 1u);
+    is_last = (prev == (unsigned int)(a.S - 1));
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  for (int g = threadIdx.x; g < a.G; g += kGNThreads) {
+    double su = 0.0, sq = 0.0;
+    for (int k = 0; k < a.S; ++k) {  // fixed order -> deterministic
+      const double* src = a.partial + (((long long)b * a.S + k) * a.G + g) * 2;
+      su += __ldcg(src);
+      sq += __ldcg(src + 1);
+    }
+    const double n = (double)a.HW * a.cpg;
+    const double mean = su / n;
+    double var = sq / n - mean * mean;
+    if (var < 0.0) var = 0.0;
+    a.stats[((long long)b * a.G + g) * 2 + 0] = (float)mean;
+    a.stats[((long long)b * a.G + g) * 2 + 1] = (float)(1.0 / sqrt(var + (double)a.eps));
+  }
+  if (threadIdx.x == 0) a.counters[b] = 0;  // re-arm for the next call
+}
+
+// grid (ceil(HW / rows_per_cta), B): thread handles 4 consecutive channels
+__global__ void __launch_bounds__(kGNThreads) gn_apply_kernel(GNArgs a, int rows_per_cta) {
+  extern __shared__ float sm[];  // mean[G], rstd[G]
+  const int b = blockIdx.y;
+  for (int g = threadIdx.x; g < a.G; g += kGNThreads) {
+    sm[g] = a.stats[((long long)b * a.G + g) * 2];
+    sm[a.G + g] = a.stats[((long long)b * a.G + g) * 2 + 1];
+  }
+  __syncthreads();
+  const int vec_per_row = a.C >> 2;
+  const long long p0 = (long long)blockIdx.x * rows_per_cta;
+  const long long p1 = min(a.HW, p0 + rows_per_cta);
+  const long long total = (p1 - p0) * vec_per_row;
+  for (long long i = threadIdx.x; i < total; i += kGNThreads) {
+    const long long p = p0 + i / vec_per_row;
+    const int c = (int)(i % vec_per_row) << 2;
+    const long long row = (long long)b * a.HW + p;
+    float4 v;
+    if (c < a.C1)
+      v = *reinterpret_cast<const float4*>(a.x1 + row * a.C1 + c);
+    else
+      v = *reinterpret_cast<const float4*>(a.x2 + row * a.C2 + (c - a.C1));
+    const float in[4] = {v.x, v.y, v.z, v.w};
+    float o[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int g = (c + k) / a.cpg;
+      float y = (in[k] - sm[g]) * sm[a.G + g];
+      y = y * __ldg(a.gamma + c + k) + __ldg(a.beta + c + k);
+      if (a.silu) y = silu_f(y);
+      o[k] = y;
+    }
+    const long long off = row * a.C + c;
+    __nv_bfloat162 h0 = __floats2bfloat162_rn(o[0], o[1]);
+    __nv_bfloat162 h1 = __floats2bfloat162_rn(o[2], o[3]);
+    uint2 pk;
+    pk.x = *reinterpret_cast<uint32_t*>(&h0);
+    pk.y = *reinterpret_cast<uint32_t*>(&h1);
+    *reinterpret_cast<uint2*>(a.out + off) = pk;
+    if (a.raw_out) {
+      __nv_bfloat162 r0 = __floats2bfloat162_rn(in[0], in[1]);
+      __nv_bfloat162 r1 = __floats2bfloat162_rn(in[2], in[3]);
+      uint2 rk;
+      rk.x = *reinterpret_cast<uint32_t*>(&r0);
+      rk.y = *reinterpret_cast<uint32_t*>(&r1);
+      *reinterpret_cast<uint2*>(a.raw_out + off) = rk;
+    }
+    if (a.cat_out) *reinterpret_cast<float4*>(a.cat_out + off) = v;
+  }
+}
+
+// one warp per row
+__global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, long long rows, int C, float eps,
+                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                        __nv_bfloat16* __restrict__ out) {
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  const float* xr = x + row * C;
+  float su = 0.f;
+  for (int c = lane * 4; c < C; c += 128) {
+    const float4 v = *reinterpret_cast<const float4*>(xr + c);
+    su += (v.x + v.y) + (v.z + v.w);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) su += __shfl_xor_sync(0xffffffffu, su, o);
+  const float mean = su / (float)C;
+  float sq = 0.f;
+  for (int c = lane * 4; c < C; c += 128) {
+    const float4 v = *reinterpret_cast<const float4*>(xr + c);
+    const float d0 = v.x - mean, d1 = v.y - mean, d2 = v.z - mean, d3 = v.w - mean;
+    sq += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+  const float rstd = rsqrtf(sq / (float)C + eps);
+  __nv_bfloat16* orow = out + row * C;
+  for (int c = lane * 4; c < C; c += 128) {
+    const float4 v = *reinterpret_cast<const float4*>(xr + c);
+    const float4 g = *reinterpret_cast<const float4*>(gamma + c);
+    const float4 bb = *reinterpret_cast<const float4*>(beta + c);
+    __nv_bfloat162 h0 = __floats2bfloat162_rn((v.x - mean) * rstd * g.x + bb.x, (v.y - mean) * rstd * g.y + bb.y);
+    __nv_bfloat162 h1 = __floats2bfloat162_rn((v.z - mean) * rstd * g.z + bb.z, (v.w - mean) * rstd * g.w + bb.w);
+    uint2 pk;
+    pk.x = *reinterpret_cast<uint32_t*>(&h0);
+    pk.y = *reinterpret_cast<uint32_t*>(&h1);
+    *reinterpret_cast<uint2*>(orow + c) = pk;
+  }
+}
+
+}  // namespace
+}  // namespace aedit
+
+using namespace aedit;
+
+extern "C" int64_t ae_groupnorm_workspace_bytes(int B, int groups) {
+  // partial sums [B, kMaxSplits, G, 2] double + stats [B, G, 2] float + counters [B] u32 (must start zeroed)
+  return (int64_t)B * kMaxSplits * groups * 2 * 8 + (int64_t)B * groups * 2 * 4 + (int64_t)B * 4 + 64;
+}
+
+extern "C" int ae_groupnorm(const float* x1, int C1, const float* x2, int C2, int B, int64_t HW, int groups, float eps,
+                            const float* gamma, const float* beta, int silu, void* out_bf16, void* raw_out_bf16,
+                            float* cat_out_f32, float* workspace, ae_stream stream) {
+  AE_CHECK_ARG(x1 && C1 > 0 && B > 0 && HW > 0 && groups > 0, "ae_groupnorm: bad argument");
+  AE_CHECK_ARG((x2 != nullptr) == (C2 > 0), "ae_groupnorm: x2/C2 mismatch");
+  const int C = C1 + C2;
+  AE_CHECK_ARG(C % groups == 0, "ae_groupnorm: C=%d not divisible by groups=%d", C, groups);
+  AE_CHECK_ARG(C1 % 4 == 0 && C2 % 4 == 0, "ae_groupnorm: channel counts must be multiples of 4 (C1=%d C2=%d)", C1, C2);
+  AE_CHECK_ARG(gamma && beta && out_bf16 && workspace, "ae_groupnorm: null pointer");
+  GNArgs a;
+  a.x1 = x1;
+  a.x2 = x2;
+  a.C1 = C1;
+  a.C2 = C2;
+  a.C = C;
+  a.G = groups;
+  a.cpg = C / groups;
+  a.B = B;
+  a.HW = HW;
+  int S = (int)ceil_div64(HW, 16);
+  if (S > kMaxSplits) S = kMaxSplits;
+  a.S = S;
+  a.chunk = ceil_div64(HW, S);
+  a.S = (int)ceil_div64(HW, a.chunk);
+  a.eps = eps;
+  a.gamma = gamma;
+  a.beta = beta;
+  a.silu = silu;
+  a.out = reinterpret_cast<__nv_bfloat16*>(out_bf16);
+  a.raw_out = reinterpret_cast<__nv_bfloat16*>(raw_out_bf16);
+  a.cat_out = cat_out_f32;
+  char* ws = reinterpret_cast<char*>(workspace);
+  a.partial = reinterpret_cast<double*>(ws);
+  ws += (size_t)B * kMaxSplits * groups * 2 * 8;
+  a.stats = reinterpret_cast<float*>(ws);
+  ws += (size_t)B * groups * 2 * 4;
+  a.counters = reinterpret_cast<unsigned int*>(ws);
+  cudaStream_t st = as_stream(stream);
+  gn_stats_kernel<<<dim3(a.S, B), kGNThreads, 2 * C * sizeof(float), st>>>(a);
+  int rc = launched("ae_groupnorm(stats)");
+  if (rc) return rc;
+  // ~8 KiB of fp32 per CTA pass keeps the grid >= 2 waves at the U-Net's top level
+  int rows_per_cta = (int)(2048 / C);
+  if (rows_per_cta < 1) rows_per_cta = 1;
+  if (rows_per_cta > 64) rows_per_cta = 64;
+  rows_per_cta *= 4;
+  gn_apply_kernel<<<dim3((unsigned)ceil_div64(HW, rows_per_cta), B), kGNThreads, 2 * groups * sizeof(float), st>>>(
+      a, rows_per_cta);
+  return launched("ae_groupnorm(apply)");
+}
+
+extern "C" int ae_layernorm(const float* x, int64_t rows, int C, float eps, const float* gamma, const float* beta,
+                            void* out_bf16, ae_stream stream) {
+  AE_CHECK_ARG(x && gamma && beta && out_bf16 && rows > 0 && C > 0, "ae_layernorm: bad argument");
+  AE_CHECK_ARG(C % 4 == 0, "ae_layernorm: C=%d must be a multiple of 4", C);
+  const int warps = 8;
+  layernorm_kernel<<<(unsigned)ceil_div64(rows, warps), warps * 32, 0, as_stream(stream)>>>(
+      x, rows, C, eps, gamma, beta, reinterpret_cast<__nv_bfloat16*>(out_bf16));
+  return launched("ae_layernorm");
+}

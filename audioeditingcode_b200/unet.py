@@ -1,0 +1,400 @@
+"""U-Net evaluation engine: the device-side replacement of what `PipelineWrapper.unet_forward`
+(reference code/models.py:160-393, AudioLDM2 variant :691-899) reaches through `self.model.unet.*`.
+
+Host logic (this file) is Python; every FLOP is issued through libaedit.so (ops.CudaOps):
+  * convolutions / linears  -> tcgen05 GEMM (implicit conv by TMA where the geometry allows, else patch gather)
+  * GroupNorm+SiLU, LayerNorm, GEGLU, attention, resize, layout -> dedicated kernels
+Data layout: channels-last.  The residual stream between blocks is fp32; every tensor-core operand is bf16
+(produced by the norm / activation kernel in front of each GEMM); accumulation is fp32.
+
+Top-level op order and tap points follow models.py:216-393:
+  time embedding -> class embedding (concat) -> conv_in -> down blocks (skip stack) -> mid -> h-space tap /
+  replace -> + mid_block_additional_residual -> up blocks (skip replace / zero) -> GN, SiLU, conv_out.
+Block internals follow the in-tree statement of the same math (openaimodel.py:175-286 ResBlock,
+attention.py:370-469 transformer) — see oracle/unet_torch.py, which this engine is tested against.
+
+Weights arrive under diffusers state-dict names (what the reference's checkpoints contain).
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence
+
+import torch
+
+from .unet_config import UNetConfig
+
+F32 = torch.float32
+NEG_PAD = -1.0e30  # additive bias for key slots that exist only as padding (never present in the reference)
+
+
+class TextCache:
+    """Frozen text conditioning of a run: per cross-attention layer the projected K|V of every text row
+    (computed once per prompt set — the reference recomputes to_k/to_v(text) at every step,
+    attention.py:234-235), plus the additive key biases (models.py:204-210, :745-755)."""
+
+    def __init__(self, n_rows: int):
+        self.n_rows = n_rows
+        self.kv: Dict[str, torch.Tensor] = {}       # layer prefix -> bf16 [n_rows, L, 2C]
+        self.bias: List[Optional[torch.Tensor]] = []  # per stream: fp32 [n_rows, L] or None
+        self.lens: List[int] = []
+
+
+class UNetEngine:
+    def __init__(self, cfg: UNetConfig, weights: Dict[str, torch.Tensor], device, ops=None):
+        if ops is None:
+            from .ops import CudaOps
+            ops = CudaOps()
+        self.cfg = cfg
+        self.ops = ops
+        self.device = torch.device(device)
+        self.adt = ops.act_dtype            # bf16 on the device path
+        self.w: Dict[str, torch.Tensor] = {}
+        self._pack(weights)
+
+    # ------------------------------------------------------------------------------------------ weights
+    def _to(self, t, dtype):
+        return t.detach().to(device=self.device, dtype=dtype).contiguous()
+
+    def _pack(self, w):
+        cfg = self.cfg
+        P = self.w
+        temb_w, temb_b, self.temb_off = [], [], {}
+        off = 0
+        for name, t in w.items():
+            if name.endswith(".time_emb_proj.weight"):
+                continue
+            if name.endswith(".time_emb_proj.bias"):
+                continue
+            if name.endswith(".weight") and t.dim() == 4:          # conv: [O,I,kh,kw] -> [O, kh*kw*I]
+                P[name] = self._to(t.permute(0, 2, 3, 1).reshape(t.shape[0], -1), self.adt)
+            elif name.endswith(".weight") and t.dim() == 2:        # linear
+                P[name] = self._to(t, self.adt)
+            else:                                                  # biases, norm affine
+                P[name] = self._to(t, F32)
+        # all ResBlock time-embedding projections as ONE GEMM (K4 of SURVEY.md §2.2)
+        for name in sorted(k for k in w if k.endswith(".time_emb_proj.weight")):
+            p = name[: -len(".time_emb_proj.weight")]
+            temb_w.append(w[name])
+            temb_b.append(w[p + ".time_emb_proj.bias"])
+            self.temb_off[p] = off
+            off += w[name].shape[0]
+        self.temb_total = off
+        P["__temb_all.weight"] = self._to(torch.cat(temb_w, 0), self.adt)
+        P["__temb_all.bias"] = self._to(torch.cat(temb_b, 0), F32)
+        # fused q|k|v (self) and k|v (cross) projections
+        for name in [k for k in w if k.endswith(".to_q.weight")]:
+            p = name[: -len(".to_q.weight")]
+            q, k, v = w[name], w[p + ".to_k.weight"], w[p + ".to_v.weight"]
+            if k.shape[1] == q.shape[1] and self._is_self(p):
+                P[p + ".qkv.weight"] = self._to(torch.cat([q, k, v], 0), self.adt)
+            else:
+                P[p + ".kv.weight"] = self._to(torch.cat([k, v], 0), self.adt)
+
+    def _is_self(self, attn_prefix: str) -> bool:
+        if attn_prefix.endswith(".attn1"):
+            return True
+        return self._spec_of(attn_prefix) is None
+
+    def _spec_of(self, attn_prefix: str):
+        # ...attentions.{idx}.transformer_blocks.{l}.attn2  -> spec = transformer_specs[idx % n_specs]
+        parts = attn_prefix.split(".")
+        idx = int(parts[parts.index("attentions") + 1])
+        return self.cfg.transformer_specs[idx % len(self.cfg.transformer_specs)]
+
+    # ------------------------------------------------------------------------------------------ text
+    def prepare_text(self, streams: Sequence[Optional[torch.Tensor]] = (),
+                     masks: Sequence[Optional[torch.Tensor]] = ()) -> TextCache:
+        """streams[i]: [R, L_i, D_i] (any float dtype), masks[i]: [R, L_i] (1 keep / 0 discard) or None."""
+        cfg = self.cfg
+        R = 0
+        for s in streams:
+            if s is not None:
+                R = s.shape[0]
+        tc = TextCache(R)
+        st_bf = []
+        for i, s in enumerate(streams):
+            if s is None:
+                st_bf.append(None)
+                tc.bias.append(None)
+                tc.lens.append(0)
+                continue
+            st_bf.append(self._to(s, self.adt))
+            m = masks[i] if i < len(masks) else None
+            tc.bias.append(None if m is None else ((1 - m.to(device=self.device, dtype=F32)) * -10000.0).contiguous())
+            tc.lens.append(s.shape[1])
+        for name in [k for k in self.w if k.endswith(".attn2.kv.weight")]:
+            p = name[: -len(".kv.weight")]
+            spec = self._spec_of(p)
+            s = st_bf[spec[1]]
+            Wkv = self.w[name]
+            out = self.ops.empty((R, s.shape[1], Wkv.shape[0]), self.adt, self.device)
+            self.ops.gemm(s.reshape(-1, s.shape[-1]), Wkv, out_bf16=out.reshape(-1, Wkv.shape[0]))
+            tc.kv[p] = out
+        return tc
+
+    # ------------------------------------------------------------------------------------------ blocks
+    def _conv3x3(self, a_bf16, B, H, W, Cin, name, out, rowbias=None, rows_per_group=1, residual=None):
+        """a_bf16: [B,H,W,Cin] channels-last operand; out fp32 [B*H*W, Cout]."""
+        ops = self.ops
+        Wt, bias = self.w[name + ".weight"], self.w[name + ".bias"]
+        if ops.conv_supported(B, H, W, Cin):
+            ops.gemm(a_bf16, Wt, out_f32=out, bias=bias, rowbias=rowbias, rows_per_group=rows_per_group,
+                     residual=residual, conv=(B, H, W, Cin, 3, 3, 1, 1))
+        else:
+            K = 9 * Cin
+            ld = (K + 7) // 8 * 8
+            col = ops.empty((B * H * W, ld), self.adt, self.device)
+            ops.im2col(a_bf16, B, H, W, Cin, 3, 3, 1, 1, 1, 1, H, W, col)
+            ops.gemm(col, Wt, out_f32=out, bias=bias, rowbias=rowbias, rows_per_group=rows_per_group,
+                     residual=residual, K=K)
+
+    def _resnet(self, x1, x2, B, H, W, p, temb_all):
+        ops, cfg = self.ops, self.cfg
+        C1 = x1.shape[-1]
+        C2 = 0 if x2 is None else x2.shape[-1]
+        Cin = C1 + C2
+        Cout = self.w[p + ".conv1.bias"].shape[0]
+        M = B * H * W
+        has_sc = (p + ".conv_shortcut.weight") in self.w
+        a1 = ops.empty((B, H, W, Cin), self.adt, self.device)
+        raw = ops.empty((M, Cin), self.adt, self.device) if has_sc else None
+        ops.groupnorm(x1, x2, self.w[p + ".norm1.weight"], self.w[p + ".norm1.bias"], cfg.norm_eps,
+                      cfg.norm_num_groups, True, a1, raw_out=raw)
+        h = ops.empty((M, Cout), F32, self.device)
+        off = self.temb_off[p]
+        self._conv3x3(a1, B, H, W, Cin, p + ".conv1", h, rowbias=temb_all[:, off:off + Cout], rows_per_group=H * W)
+        a2 = ops.empty((B, H, W, Cout), self.adt, self.device)
+        ops.groupnorm(h.view(B, H * W, Cout), None, self.w[p + ".norm2.weight"], self.w[p + ".norm2.bias"],
+                      cfg.norm_eps, cfg.norm_num_groups, True, a2)
+        if has_sc:
+            res = ops.empty((M, Cout), F32, self.device)
+            ops.gemm(raw, self.w[p + ".conv_shortcut.weight"], out_f32=res, bias=self.w[p + ".conv_shortcut.bias"])
+        else:
+            res = x1.reshape(M, Cout)
+        out = ops.empty((M, Cout), F32, self.device)
+        self._conv3x3(a2, B, H, W, Cout, p + ".conv2", out, residual=res)
+        return out.view(B, H * W, Cout)
+
+    def _attention(self, q, k, v, out, heads, B, Tq, Tk, ld_q, bs_q, ld_k, bs_k, ld_v, bs_v, kv_map=None, bias=None):
+        d = out.shape[-1] // heads
+        self.ops.attention(q, k, v, out, heads, d, float(d) ** -0.5, Tq, Tk, B, ld_q, bs_q, ld_k, bs_k, ld_v, bs_v,
+                           kv_map=kv_map, bias=bias)
+
+    def _transformer(self, x, B, H, W, p, heads, spec, text: Optional[TextCache], slot_map):
+        ops, cfg = self.ops, self.cfg
+        C = x.shape[-1]
+        T = H * W
+        M = B * T
+        g = ops.empty((M, C), self.adt, self.device)
+        ops.groupnorm(x, None, self.w[p + ".norm.weight"], self.w[p + ".norm.bias"], 1e-6, cfg.norm_num_groups, False, g)
+        hs = ops.empty((M, C), F32, self.device)
+        ops.gemm(g, self.w[p + ".proj_in.weight"], out_f32=hs, bias=self.w[p + ".proj_in.bias"])
+        hs_b = None
+        nl = cfg.transformer_layers_per_block
+        for l in range(nl):
+            q = f"{p}.transformer_blocks.{l}"
+            # --- attn1 (self)
+            n = ops.empty((M, C), self.adt, self.device)
+            ops.layernorm(hs, self.w[q + ".norm1.weight"], self.w[q + ".norm1.bias"], n)
+            qkv = ops.empty((M, 3 * C), self.adt, self.device)
+            ops.gemm(n, self.w[q + ".attn1.qkv.weight"], out_bf16=qkv)
+            a = ops.empty((M, C), self.adt, self.device)
+            self._attention(qkv, qkv[:, C:], qkv[:, 2 * C:], a, heads, B, T, T, 3 * C, T * 3 * C, 3 * C, T * 3 * C,
+                            3 * C, T * 3 * C)
+            ops.gemm(a, self.w[q + ".attn1.to_out.0.weight"], out_f32=hs, bias=self.w[q + ".attn1.to_out.0.bias"],
+                     residual=hs)
+            # --- attn2 (self or cross)
+            ops.layernorm(hs, self.w[q + ".norm2.weight"], self.w[q + ".norm2.bias"], n)
+            if spec is None:
+                ops.gemm(n, self.w[q + ".attn2.qkv.weight"], out_bf16=qkv)
+                self._attention(qkv, qkv[:, C:], qkv[:, 2 * C:], a, heads, B, T, T, 3 * C, T * 3 * C, 3 * C,
+                                T * 3 * C, 3 * C, T * 3 * C)
+            else:
+                if text is None or (q + ".attn2") not in text.kv:
+                    raise ValueError("cross-attention layer needs prepared text (UNetEngine.prepare_text)")
+                qq = qkv[:, :C]
+                ops.gemm(n, self.w[q + ".attn2.to_q.weight"], out_bf16=qq)
+                kv = text.kv[q + ".attn2"]
+                L = kv.shape[1]
+                self._attention(qq, kv, kv[:, :, C:], a, heads, B, T, L, 3 * C, T * 3 * C, 2 * C, L * 2 * C, 2 * C,
+                                L * 2 * C, kv_map=slot_map, bias=text.bias[spec[1]])
+            ops.gemm(a, self.w[q + ".attn2.to_out.0.weight"], out_f32=hs, bias=self.w[q + ".attn2.to_out.0.bias"],
+                     residual=hs)
+            # --- GEGLU feed-forward
+            ops.layernorm(hs, self.w[q + ".norm3.weight"], self.w[q + ".norm3.bias"], n)
+            ff = ops.empty((M, 8 * C), self.adt, self.device)
+            ops.gemm(n, self.w[q + ".ff.net.0.proj.weight"], out_bf16=ff, bias=self.w[q + ".ff.net.0.proj.bias"])
+            gg = ops.empty((M, 4 * C), self.adt, self.device)
+            ops.geglu(ff, gg)
+            if l == nl - 1:
+                hs_b = ops.empty((M, C), self.adt, self.device)
+            ops.gemm(gg, self.w[q + ".ff.net.2.weight"], out_f32=hs, out_bf16=hs_b if l == nl - 1 else None,
+                     bias=self.w[q + ".ff.net.2.bias"], residual=hs)
+        out = ops.empty((M, C), F32, self.device)
+        ops.gemm(hs_b, self.w[p + ".proj_out.weight"], out_f32=out, bias=self.w[p + ".proj_out.bias"],
+                 residual=x.reshape(M, C))
+        return out.view(B, T, C)
+
+    def _site(self, x, B, H, W, base, idx0, level, text, slot_map):
+        cfg = self.cfg
+        ns = len(cfg.transformer_specs)
+        for j, spec in enumerate(cfg.transformer_specs):
+            x = self._transformer(x, B, H, W, f"{base}.{idx0 * ns + j}", cfg.num_heads[level], spec, text, slot_map)
+        return x
+
+    # ------------------------------------------------------------------------------------------ forward
+    def forward(self, sample: torch.Tensor, timesteps: torch.Tensor, text: Optional[TextCache] = None,
+                slot_map: Optional[torch.Tensor] = None, class_labels: Optional[torch.Tensor] = None,
+                mid_block_additional_residual=None, replace_h_space=None, replace_skip_conns=None,
+                zero_out_resconns=None, want_taps: bool = False, out: Optional[torch.Tensor] = None):
+        """sample: fp32 NCHW [B,Cin,H,W]; timesteps: int64 [B]; slot_map: int32 [B] rows of `text`;
+        class_labels: [B, class_embed_dim].  Returns eps (fp32 NCHW) and, if want_taps, (eps, h_space, skips)
+        in the reference's NCHW convention (models.py:336-361,393)."""
+        ops, cfg = self.ops, self.cfg
+        dev = self.device
+        sample = sample.to(dev, F32).contiguous()
+        B, Cin, H, W = sample.shape
+        timesteps = torch.as_tensor(timesteps).to(dev, torch.int64).reshape(-1)
+        if timesteps.numel() == 1 and B > 1:
+            timesteps = timesteps.expand(B)
+        timesteps = timesteps.contiguous()
+        if slot_map is not None:
+            slot_map = slot_map.to(dev, torch.int32).contiguous()
+        ch = cfg.block_out_channels
+        nlev = len(ch)
+        ted = 4 * ch[0]
+        temb_ch = self.w["__temb_all.weight"].shape[1]
+
+        # ---- time / class embedding (models.py:231-256); silu(emb) is the only consumer of emb
+        tproj = ops.empty((B, ch[0]), self.adt, dev)
+        ops.timestep_embedding(timesteps, ch[0], tproj)
+        e1 = ops.empty((B, ted), self.adt, dev)
+        ops.gemm(tproj, self.w["time_embedding.linear_1.weight"], out_bf16=e1,
+                 bias=self.w["time_embedding.linear_1.bias"], act=1)
+        emb_act = ops.empty((B, temb_ch), self.adt, dev)
+        ops.gemm(e1, self.w["time_embedding.linear_2.weight"], out_bf16=emb_act[:, :ted],
+                 bias=self.w["time_embedding.linear_2.bias"], act=1)
+        if cfg.class_embed_dim is not None:
+            if class_labels is None:
+                raise ValueError("class_labels should be provided when num_class_embeds > 0")  # models.py:241-242
+            cl = ops.empty((B, cfg.class_embed_dim), self.adt, dev)
+            ops.cast_bf16(class_labels.to(dev, F32).contiguous(), cl)
+            if not cfg.class_embeddings_concat:
+                raise NotImplementedError("additive class embedding is not used by the audio models")
+            ops.gemm(cl, self.w["class_embedding.weight"], out_bf16=emb_act[:, ted:],
+                     bias=self.w["class_embedding.bias"], act=1)
+        temb_all = ops.empty((B, self.temb_total), F32, dev)
+        ops.gemm(emb_act, self.w["__temb_all.weight"], out_f32=temb_all, bias=self.w["__temb_all.bias"])
+
+        # ---- conv_in (Cin = 8: explicit patch gather, K = 72)
+        x_nhwc = ops.empty((B, H, W, Cin), F32, dev)
+        ops.nchw_to_nhwc(sample, out_f32=x_nhwc)
+        K0 = 9 * Cin
+        col = ops.empty((B * H * W, (K0 + 7) // 8 * 8), self.adt, dev)
+        ops.im2col(x_nhwc, B, H, W, Cin, 3, 3, 1, 1, 1, 1, H, W, col)
+        h = ops.empty((B * H * W, ch[0]), F32, dev)
+        ops.gemm(col, self.w["conv_in.weight"], out_f32=h, bias=self.w["conv_in.bias"], K=K0)
+        h = h.view(B, H * W, ch[0])
+
+        sizes = [(H, W)]
+        skips = [h]
+        hh, ww = H, W
+        for i in range(nlev):
+            for j in range(cfg.layers_per_block):
+                h = self._resnet(h, None, B, hh, ww, f"down_blocks.{i}.resnets.{j}", temb_all)
+                if cfg.attn_levels[i]:
+                    h = self._site(h, B, hh, ww, f"down_blocks.{i}.attentions", j, i, text, slot_map)
+                skips.append(h)
+            if i != nlev - 1:
+                C = ch[i]
+                ho, wo = (hh - 1) // 2 + 1, (ww - 1) // 2 + 1
+                col = ops.empty((B * ho * wo, 9 * C), self.adt, dev)
+                ops.im2col(h, B, hh, ww, C, 3, 3, 2, 1, 1, 1, ho, wo, col)
+                d = ops.empty((B * ho * wo, C), F32, dev)
+                p = f"down_blocks.{i}.downsamplers.0.conv"
+                ops.gemm(col, self.w[p + ".weight"], out_f32=d, bias=self.w[p + ".bias"])
+                hh, ww = ho, wo
+                sizes.append((hh, ww))
+                h = d.view(B, hh * ww, C)
+                skips.append(h)
+
+        h = self._resnet(h, None, B, hh, ww, "mid_block.resnets.0", temb_all)
+        h = self._site(h, B, hh, ww, "mid_block.attentions", 0, nlev - 1, text, slot_map)
+        h = self._resnet(h, None, B, hh, ww, "mid_block.resnets.1", temb_all)
+
+        # ---- h-space tap / replace, additive residual (models.py:336-343)
+        Cm = ch[-1]
+        h_space = None
+        if replace_h_space is not None:
+            h_space = replace_h_space
+            rep = ops.empty((B, hh, ww, Cm), F32, dev)
+            ops.nchw_to_nhwc(replace_h_space.to(dev, F32).expand(B, -1, -1, -1).contiguous(), out_f32=rep)
+            h = rep.view(B, hh * ww, Cm)
+        elif want_taps:
+            h_space = ops.empty((B, Cm, hh, ww), F32, dev)
+            ops.nhwc_to_nchw(h, B, Cm, hh, ww, h_space)
+        if mid_block_additional_residual is not None:
+            add = ops.empty((B, hh, ww, Cm), F32, dev)
+            ops.nchw_to_nhwc(mid_block_additional_residual.to(dev, F32).expand(B, -1, -1, -1).contiguous(), out_f32=add)
+            h2 = ops.empty((B, hh * ww, Cm), F32, dev)
+            ops.add(h, add.view(B, hh * ww, Cm), h2)
+            h = h2
+
+        extracted = {}
+        n_up = cfg.layers_per_block + 1
+        for i in range(nlev):
+            level = nlev - 1 - i
+            hh, ww = sizes[level]
+            res = skips[-n_up:]
+            skips = skips[:-n_up]
+            if replace_skip_conns is not None and replace_skip_conns.get(i):
+                res = [self._from_nchw(t, B) for t in replace_skip_conns.get(i)]
+            if zero_out_resconns is not None:
+                if (type(zero_out_resconns) is int and i >= (zero_out_resconns - 1)) or \
+                        (type(zero_out_resconns) is list and i in zero_out_resconns):
+                    res = [torch.zeros_like(t) for t in res]
+            if want_taps:
+                extracted[i] = [self._to_nchw(t, B, hh, ww) for t in res]
+            res = list(res)
+            for j in range(n_up):
+                h = self._resnet(h, res.pop(), B, hh, ww, f"up_blocks.{i}.resnets.{j}", temb_all)
+                if cfg.attn_levels[level]:
+                    h = self._site(h, B, hh, ww, f"up_blocks.{i}.attentions", j, level, text, slot_map)
+            if i != nlev - 1:
+                C = ch[level]
+                ho, wo = sizes[level - 1]
+                up = ops.empty((B, ho, wo, C), self.adt, dev)
+                ops.upsample_nearest(h, B, hh, ww, C, ho, wo, up)
+                u = ops.empty((B * ho * wo, C), F32, dev)
+                self._conv3x3(up, B, ho, wo, C, f"up_blocks.{i}.upsamplers.0.conv", u)
+                h = u.view(B, ho * wo, C)
+
+        # ---- conv_norm_out -> SiLU -> conv_out (models.py:385-388)
+        a = ops.empty((B, H, W, ch[0]), self.adt, dev)
+        ops.groupnorm(h, None, self.w["conv_norm_out.weight"], self.w["conv_norm_out.bias"], cfg.norm_eps,
+                      cfg.norm_num_groups, True, a)
+        Co = cfg.out_channels
+        o = ops.empty((B * H * W, Co), F32, dev)
+        self._conv3x3(a, B, H, W, ch[0], "conv_out", o)
+        if out is None:
+            out = ops.empty((B, Co, H, W), F32, dev)
+        ops.nhwc_to_nchw(o, B, Co, H, W, out)
+        if want_taps:
+            return out, h_space, extracted
+        return out
+
+    def _to_nchw(self, t, B, H, W):
+        C = t.shape[-1]
+        o = self.ops.empty((B, C, H, W), F32, self.device)
+        self.ops.nhwc_to_nchw(t.contiguous(), B, C, H, W, o)
+        return o
+
+    def _from_nchw(self, t, B):
+        t = t.to(self.device, F32)
+        if t.shape[0] != B:
+            t = t.expand(B, -1, -1, -1)
+        t = t.contiguous()
+        _, C, H, W = t.shape
+        o = self.ops.empty((B, H, W, C), F32, self.device)
+        self.ops.nchw_to_nhwc(t, out_f32=o)
+        return o.view(B, H * W, C)

@@ -1,0 +1,204 @@
+/* libaedit.so — C ABI of the B200-native DDPM-inversion / CFG-denoising hot path.
+ *
+ * The reference (HilaManor/AudioEditingCode) has no FFI: its "plugin" boundary is the Python duck-typed
+ * `PipelineWrapper` protocol of code/models.py:14-158 that the loops in
+ * code/ddm_inversion/inversion_utils.py and code/pc_drift.py call.  The Python package
+ * `audioeditingcode_b200` mirrors that protocol; every piece of device math it performs goes through the
+ * entry points below (plain pointers and sizes, no torch types).  Each entry point cites the reference
+ * lines whose arithmetic it replaces.
+ *
+ * Conventions
+ *   - all pointers are DEVICE pointers unless suffixed _h (host)
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*), never synchronises, never
+ *     allocates device memory (the only allocations are in *_create), and is CUDA-graph capturable
+ *   - return 0 on success, negative AE_E* otherwise; ae_last_error() returns a thread-local message
+ *   - activations are channels-last: images [B,H,W,C], token sequences [B,T,C]; "f32" = float, "bf16" =
+ *     __nv_bfloat16.  Latents / noise maps of the scheduler kernels are plain contiguous fp32 of any layout.
+ */
+#ifndef AEDIT_H_
+#define AEDIT_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AE_OK 0
+#define AE_EINVAL (-1)   /* bad argument / unsupported shape */
+#define AE_ECUDA (-2)    /* CUDA runtime / driver error */
+#define AE_EUNSUPPORTED (-3)
+
+typedef void* ae_stream; /* cudaStream_t */
+
+const char* ae_last_error(void);
+int ae_version(void);
+/* number of kernels this library has launched since load (bench.py's gpu_launches) */
+int64_t ae_launch_count(void);
+/* 1 if the current device is compute capability 10.x */
+int ae_device_ok(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Scheduler table  (code/models.py:85-158, :539-549; integer index math of
+ * code/ddm_inversion/inversion_utils.py:75,222-224 and models.py:76-80,96-97,123-124)
+ *
+ * Built on the host from alphas_cumprod [T] (fp32, exactly the scheduler's tensor), final_alpha_cumprod and
+ * the descending `timesteps` [N].  Row k (k = position in `timesteps`) holds, in the reference's fp32
+ * operation order:  t, prev_t, alpha_bar_t, alpha_prod_t_prev, variance,
+ *   sqrt_ab = ab**0.5, sqrt_1mab = (1-ab)**0.5, sqrt_ap = ap**0.5, sqrt_var = var**0.5
+ * `eta` dependent terms are formed at call time (eta is per call in the reference).
+ * pred_type: 0 = epsilon, 1 = v_prediction.
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct ae_sched ae_sched;
+
+typedef struct {
+  int32_t t, prev_t;
+  float alpha_bar_t, alpha_prod_t_prev, variance;
+  float sqrt_ab, sqrt_1mab, sqrt_ap, sqrt_var;
+} ae_sched_row;
+
+int ae_sched_create(const float* alphas_cumprod_h, int T, float final_alpha_cumprod, const int64_t* timesteps_h, int N,
+                    int pred_type, ae_sched** out);
+void ae_sched_destroy(ae_sched*);
+int ae_sched_num_steps(const ae_sched*);
+/* host copy of row `pos` (pos indexes `timesteps`) */
+int ae_sched_row_h(const ae_sched*, int pos, ae_sched_row* out);
+/* position of timestep value t in `timesteps`, or -1   (t_to_idx of inversion_utils.py:68) */
+int ae_sched_pos_of_t(const ae_sched*, int64_t t);
+
+/* models.py:67-83 sample_xts_from_x0:  xts[0] = x0;  xts[N - pos] = x0*sqrt(ab[t_pos]) + noise[k]*sqrt(1-ab[t_pos])
+ * where k = N-1-pos is the draw order of the reference (ascending t).  noise: [N, n_el], xts: [N+1, n_el]. */
+int ae_sample_xts(const ae_sched*, const float* x0, const float* noise, float* xts, int64_t n_el, ae_stream stream);
+
+/* Fused CFG combine (inversion_utils.py:97-102) + get_zs_from_xts (models.py:85-117) for `count` consecutive
+ * loop positions pos0 .. pos0+count-1 (count > 1 = the timestep-batched forward process).  For position pos,
+ * idx = N - pos - 1 (inversion_utils.py:75):
+ *      xt    = xts_in[idx+1]           (read from `xt_src`, usually == xts)
+ *      eps   = eps_u[j] + sum_p cfg_map[p] * (eps_c[j,p] - eps_u[j])      j = pos - pos0;  P == 0: eps = eps_u[j]
+ *      z     = (xts[idx] - mu) / (eta*sqrt(var));   zs[idx] = z;
+ *      numerical_fix: xts[idx] = mu + eta*sqrt(var)*z
+ * eps_u: [count, n_el] with row stride ld_eps_u; eps_c: [count, P, n_el] (row stride ld_eps_c per (j,p) row);
+ * cfg_map: [P, n_el].  xt_src and xts may alias (sequential semantics are then the caller's business). */
+int ae_cfg_inv_step(const ae_sched*, int pos0, int count, float eta, const float* eps_u, int64_t ld_eps_u,
+                    const float* eps_c, int64_t ld_eps_c, int P, const float* cfg_map, const float* xt_src, float* xts,
+                    float* zs, int numerical_fix, int64_t n_el, ae_stream stream);
+
+/* Fused CFG combine (inversion_utils.py:276-281) + reverse_step_with_custom_noise (models.py:119-158) +
+ * optional multi-prompt mask "fix" (inversion_utils.py:308-315) for ONE loop position `pos`.
+ * If d_pos != NULL the position is read from device memory instead (graph replay).
+ *      xt_out = mu(xt, eps) + eta*sqrt(var)*z            (eta > 0; z may be NULL when eta == 0)
+ * fix (n_fix_p > 0): xt_out = sum_p mask[p] * (xt_out*(1-a_p) + a_p*xT_fix), a_p = fix_alpha[p] (0 = no fix for p) */
+int ae_cfg_rev_step(const ae_sched*, int pos, const int32_t* d_pos, float eta, const float* eps_u, const float* eps_c,
+                    int P, const float* cfg_map, const float* xt, const float* z, float* xt_out, const float* masks,
+                    const float* fix_alpha_h, const float* xT_fix, int64_t n_el, ae_stream stream);
+
+/* [UPSTREAM] DDIMScheduler.step as used by code/pc_drift.py:89 (std = eta*sqrt(var), direction uses std**2):
+ * writes prev_sample and pred_original_sample for `B` rows sharing timestep position pos. cfg: scalar guidance. */
+int ae_ddim_step(const ae_sched*, int pos, float eta, float cfg_scale, const float* eps_u, const float* eps_c,
+                 const float* sample, const float* variance_noise, float* prev_sample, float* pred_x0, int64_t n_el,
+                 ae_stream stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * U-Net building blocks (the math of `self.model.unet.*` called from models.py:231-388 / :772-894; in-tree
+ * statement: code/audioldm/latent_diffusion/openaimodel.py, attention.py, util.py)
+ * ------------------------------------------------------------------------------------------------ */
+
+/* D[M,N] = alpha * A[M,K] · W[N,K]^T  (+bias[n]) (+rowbias[m / rows_per_group, n]) (+residual[m,n])  -> act -> out
+ * A, W: bf16, K contiguous.  tcgen05 tensor-core tiles (128 x BN x 64) fed by TMA, fp32 accumulation in TMEM.
+ * conv != 0: A is a channels-last image [B,H,W,C] and the K dimension is gathered on the fly by TMA
+ *            (implicit GEMM, zero padding by out-of-bounds fill): K = kh*kw*C ordered (kh,kw,c), stride 1,
+ *            output positions = input positions ("same" size: pad = dil*(k-1)/2).  M = B*H*W.
+ * batch > 1: independent problems z = 0..batch-1 with element strides (A, W, outputs, residual). */
+typedef struct {
+  const void* A;
+  int64_t lda;
+  const void* W;
+  int64_t ldw;
+  int32_t M, N, K;
+  int32_t batch;
+  int64_t strideA, strideW, stride_out, stride_res;
+  const float* bias;
+  const float* rowbias;
+  int64_t ld_rowbias;
+  int32_t rows_per_group;
+  const float* residual;
+  int64_t ld_res;
+  float* out_f32;
+  int64_t ld_out_f32;
+  void* out_bf16;
+  int64_t ld_out_bf16;
+  int32_t act; /* 0 none, 1 SiLU */
+  float alpha;
+  /* implicit convolution */
+  int32_t conv;
+  int32_t B, H, W_, C, kh, kw, dil_h, dil_w;
+  int32_t force_bn; /* 0 = auto tile width, else 32/64/128 */
+} ae_gemm_args;
+int ae_gemm(const ae_gemm_args*, ae_stream stream);
+/* 1 if the implicit-conv fast path supports this geometry (else use ae_im2col + plain GEMM) */
+int ae_gemm_conv_supported(int B, int H, int W, int C);
+
+/* Explicit patch gather for the convolutions the TMA path does not cover (stride 2, asymmetric padding, C%64!=0):
+ * out[m, (i*kw + j)*C + c] = in[b, ho*stride - pad_t + i*dil, wo*stride - pad_l + j*dil, c]  (0 outside), bf16 out.
+ * in: f32 or bf16 [B,H,W,C];  out: [B*Ho*Wo, ld_out] with ld_out >= kh*kw*C (tail columns zeroed). */
+int ae_im2col(const void* in, int in_is_bf16, int B, int H, int W, int C, int kh, int kw, int stride, int dil,
+              int pad_t, int pad_l, int Ho, int Wo, void* out_bf16, int64_t ld_out, ae_stream stream);
+
+/* GroupNorm (+ optional SiLU) over channels-last fp32 input, bf16 output (openaimodel.py:213-216,238-239; util.py:240).
+ * The input may be a virtual channel concatenation of two tensors (up-block skip concat, openaimodel.py:845):
+ * x = cat([x1 (C1 ch), x2 (C2 ch)], channel).  HW = spatial positions per sample.  raw_out (optional): bf16 copy of x.
+ * workspace: ae_groupnorm_workspace_bytes(B, groups) bytes, ZERO-initialised once by the caller (it holds the
+ * per-sample arrival counters, which the kernel re-arms itself). */
+int64_t ae_groupnorm_workspace_bytes(int B, int groups);
+int ae_groupnorm(const float* x1, int C1, const float* x2, int C2, int B, int64_t HW, int groups, float eps,
+                 const float* gamma, const float* beta, int silu, void* out_bf16, void* raw_out_bf16,
+                 float* cat_out_f32, float* workspace, ae_stream stream);
+
+/* LayerNorm over the last dim of fp32 [rows, C] -> bf16 (attention.py:393-395, eps 1e-5) */
+int ae_layernorm(const float* x, int64_t rows, int C, float eps, const float* gamma, const float* beta, void* out_bf16,
+                 ae_stream stream);
+
+/* GEGLU: out[m, j] = h[m, j] * gelu(h[m, inner + j])   (attention.py:37-44), bf16 in/out */
+int ae_geglu(const void* h_bf16, int64_t rows, int inner, void* out_bf16, ae_stream stream);
+
+/* Fused multi-head attention, online softmax (attention.py:285-323): O = softmax(Q K^T * scale + bias) V.
+ * q: [B, Tq, heads*d] rows with stride ld_q (elements); k, v: [Bkv, Tk, heads*d] with strides ld_k, ld_v;
+ * kv_batch_map[b] (optional, device) selects the K/V batch of query batch b (shared text K/V);
+ * key_bias (optional): additive fp32 [Bkv, Tk] (models.py:204-210: 0 keep / -10000 discard).  bf16 in/out. */
+int ae_attention(const void* q, int64_t ld_q, int64_t q_batch_stride, const void* k, int64_t ld_k,
+                 int64_t k_batch_stride, const void* v, int64_t ld_v, int64_t v_batch_stride, const int32_t* kv_batch_map,
+                 const float* key_bias, int64_t ld_bias, int B, int heads, int d, int Tq, int Tk, float scale, void* out,
+                 int64_t ld_o, int64_t o_batch_stride, ae_stream stream);
+
+/* Sinusoidal timestep embedding [cos | sin] (util.py:173-197), bf16 out [B, dim]; t: int64 [B] */
+int ae_timestep_embedding(const int64_t* t, int B, int dim, void* out_bf16, ae_stream stream);
+
+/* nearest-neighbour resize of channels-last fp32 [B,H,W,C] to [B,Ho,Wo,C] bf16 (openaimodel.py:113-121) */
+int ae_upsample_nearest(const float* x, int B, int H, int W, int C, int Ho, int Wo, void* out_bf16, ae_stream stream);
+
+/* layout / dtype movers */
+int ae_nchw_to_nhwc(const float* x, int B, int C, int H, int W, float* out_f32, void* out_bf16, ae_stream stream);
+int ae_nhwc_to_nchw(const float* x, int B, int C, int H, int W, float* out_f32, ae_stream stream);
+int ae_cast_f32_bf16(const float* x, int64_t n, void* out_bf16, int silu, ae_stream stream);
+int ae_add_f32(const float* a, const float* b, float scale_b, int64_t n, float* out, ae_stream stream);
+/* row-wise softmax of fp32 [rows, n] (+ optional per-column bias) -> bf16, used by the unfused attention path (VAE) */
+int ae_softmax_rows(const float* x, int64_t rows, int n, int64_t ld, void* out_bf16, int64_t ld_out, ae_stream stream);
+/* bf16 [rows, cols] -> bf16 [cols, rows] per batch */
+int ae_transpose_bf16(const void* x, int batch, int rows, int cols, void* out, ae_stream stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Audio front end (code/audioldm/audio/stft.py:52-81,159-180; tools.py:18-31):
+ * log-mel of a mono waveform: reflect pad n_fft/2, frames of n_fft with hop, window, |DFT|, mel matmul,
+ * log(clamp(.,1e-5)).  wav [n_samples] f32; window [n_fft]; mel_basis [n_mels, n_fft/2+1]; out [n_frames, n_mels]
+ * workspace: >= n_frames * (n_fft/2+1) floats (magnitudes). */
+int ae_stft_mel(const float* wav, int n_samples, int n_fft, int hop, const float* window, const float* mel_basis,
+                int n_mels, int n_frames, float* mag_workspace, float* out_logmel, ae_stream stream);
+
+/* 1-D ops of the HiFi-GAN vocoder (code/audioldm/hifigan/models.py:20-165), channels-last [B,T,C] fp32 */
+int ae_leaky_relu_bf16(const float* x, int64_t n, float slope, void* out_bf16, ae_stream stream);
+int ae_tanh_f32(const float* x, int64_t n, float* out, ae_stream stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AEDIT_H_ */
