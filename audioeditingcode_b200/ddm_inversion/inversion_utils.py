@@ -1,0 +1,412 @@
+"""Edit-friendly DDPM inversion loops — drop-in for code/ddm_inversion/inversion_utils.py (same names,
+signatures, return tuples, error behaviour):
+
+    inversion_forward_process(model, x0, etas, prog_bar, prompts, cfg_scales, num_inference_steps, cutoff_points,
+                              numerical_fix, extract_h_space, extract_skipconns, duration, first_order)
+        -> (xt, zs, xts, extra_info[, hspaces[, skipconns]])                     reference :8-144
+    inversion_reverse_process(model, xT, tstart, fix_alpha, etas, prompts, neg_prompts, cfg_scales, prog_bar, zs,
+                              cutoff_points, hspace_add, hspace_replace, skipconns_replace, zero_out_resconns,
+                              extract_h_space, extract_skipconns, duration, first_order, extra_info)
+        -> (xt, zs[, hspaces[, skipconns]])                                      reference :147-323
+
+Two execution paths, both on the libaedit kernels:
+  * fused path (default; no h-space / skip taps requested): one batched U-Net launch per step for the
+    uncond+cond CFG rows, CFG combine + scheduler update fused in one kernel (ae_cfg_inv_step / ae_cfg_rev_step),
+    no per-step host synchronisation.  The forward process can additionally batch `forward_batch` timesteps per
+    launch (every U-Net input of the forward process is sampled directly from x0); with
+    forward_batch=1 the loop is step-sequential and reproduces the reference's data flow exactly, including the
+    bit-exact replay invariant.
+  * general path (taps requested): the reference's per-step structure through the wrapper methods.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Dict, List, Optional, Tuple, Union
+
+import torch
+from tqdm import tqdm
+
+from .. import _lib
+from ..models import PipelineWrapper, _ptr, _stream
+
+DEFAULT_FORWARD_BATCH = int(os.environ.get("AEDIT_FORWARD_BATCH", "8"))
+
+
+def _gaussian_blur_k15_s1(x: torch.Tensor) -> torch.Tensor:
+    """torchvision.transforms.functional.gaussian_blur(x, kernel_size=15, sigma=1) (reflect padding, separable
+    kernel) — used once per run on the multi-prompt cfg / mask maps (inversion_utils.py:49,197-198)."""
+    from torchvision.transforms import functional as TF
+    return TF.gaussian_blur(x, kernel_size=15, sigma=1)
+
+
+def _build_cfg_maps(batch_size, shape, cfg_scales, cutoff_points, device, dtype, prompts=None, masks_too=False):
+    """inversion_utils.py:29-51 (forward) / :177-200 (reverse).  Mutates cfg_scales in place like the reference
+    (`cfg_scales *= batch_size`)."""
+    cfg_scales_tensor = torch.ones((batch_size, *shape), device=device, dtype=dtype)
+    masks = torch.ones((batch_size, *shape), device=device, dtype=dtype) if masks_too else None
+    if batch_size > 1:
+        if cutoff_points is None:
+            cutoff_points = [i * 1 / batch_size for i in range(1, batch_size)]
+        if len(cfg_scales) == 1:
+            cfg_scales *= batch_size
+        elif len(cfg_scales) < batch_size:
+            raise ValueError("Not enough target CFG scales")
+        cutoff_points = [int(x * cfg_scales_tensor.shape[2]) for x in cutoff_points]
+        cutoff_points = [0, *cutoff_points, cfg_scales_tensor.shape[2]]
+        for i, (start, end) in enumerate(zip(cutoff_points[:-1], cutoff_points[1:])):
+            cfg_scales_tensor[i, :, end:] = 0
+            cfg_scales_tensor[i, :, :start] = 0
+            if masks_too:
+                masks[i, :, end:] = 0
+                masks[i, :, :start] = 0
+            cfg_scales_tensor[i] *= cfg_scales[i]
+            if (not masks_too) and prompts is not None and prompts[i] == "":
+                cfg_scales_tensor[i] = 0
+        cfg_scales_tensor = _gaussian_blur_k15_s1(cfg_scales_tensor)
+        if masks_too:
+            masks = _gaussian_blur_k15_s1(masks)
+    else:
+        cfg_scales_tensor *= cfg_scales[0]
+    return cfg_scales_tensor.contiguous(), (masks.contiguous() if masks_too else None)
+
+
+def _cat_text(model: PipelineWrapper, uncond, cond):
+    """Stack the uncond row(s) and the P cond rows of (hidden_states, class_labels, mask) into one text batch,
+    right-padding the token axis (padding keys get a large negative bias, i.e. exactly zero softmax weight)."""
+    streams_u, masks_u, cl_u = model._text_for(*uncond)
+    if cond is None:
+        return streams_u, masks_u, cl_u
+    streams_c, masks_c, cl_c = model._text_for(*cond)
+    streams, masks = [], []
+    for su, sc, mu, mc in zip(streams_u, streams_c, masks_u, masks_c):
+        L = max(su.shape[1], sc.shape[1])
+        need_mask = (mu is not None) or (mc is not None) or su.shape[1] != sc.shape[1]
+
+        def pad(s, m):
+            n, l = s.shape[0], s.shape[1]
+            if m is None:
+                m = torch.ones(n, l, device=s.device)
+            m = m.to(torch.float32)
+            if l < L:
+                s = torch.cat([s, s.new_zeros(n, L - l, s.shape[2])], 1)
+                # padded slots: mask value chosen so that (1-m)*-10000 becomes a huge negative bias
+                m = torch.cat([m, m.new_full((n, L - l), -1.0e26)], 1)
+            return s, m
+        su2, mu2 = pad(su, mu)
+        sc2, mc2 = pad(sc, mc)
+        streams.append(torch.cat([su2, sc2], 0))
+        masks.append(torch.cat([mu2, mc2], 0) if need_mask else None)
+    cl = None if cl_u is None else torch.cat([cl_u, cl_c], 0)
+    return streams, masks, cl
+
+
+def _t_to_idx(timesteps):
+    if timesteps[0].dtype == torch.int64:
+        return {int(v): k for k, v in enumerate(timesteps)}
+    return {float(v): k for k, v in enumerate(timesteps)}
+
+
+def inversion_forward_process(model: PipelineWrapper,
+                              x0: torch.Tensor,
+                              etas: Optional[float] = None,
+                              prog_bar: bool = False,
+                              prompts: List[str] = [""],
+                              cfg_scales: List[float] = [3.5],
+                              num_inference_steps: int = 50,
+                              cutoff_points: Optional[List[float]] = None,
+                              numerical_fix: bool = False,
+                              extract_h_space: bool = False,
+                              extract_skipconns: bool = False,
+                              duration: Optional[float] = None,
+                              first_order: bool = False,
+                              forward_batch: Optional[int] = None,
+                              noise: Optional[torch.Tensor] = None) -> Tuple:
+    if len(prompts) > 1 and extract_h_space:
+        raise NotImplementedError("How do you split cfg_scales for hspace? TODO")
+    if extract_h_space or extract_skipconns:
+        return _forward_general(model, x0, etas, prog_bar, prompts, cfg_scales, num_inference_steps, cutoff_points,
+                                numerical_fix, extract_h_space, extract_skipconns, duration, first_order)
+
+    have_cond = len(prompts) > 1 or prompts[0] != ""
+    P = len(prompts) if have_cond else 0
+    cond = None
+    cfg_map = None
+    if have_cond:
+        cond = model.encode_text(prompts)
+        cfg_map, _ = _build_cfg_maps(P, x0.shape[1:], cfg_scales, cutoff_points, model.device, x0.dtype, prompts)
+    uncond = model.encode_text([""], negative=True)
+    sched = model.model.scheduler
+    timesteps = sched.timesteps.to(model.device)
+    N = num_inference_steps
+    if type(etas) in [int, float]:
+        etas = [etas] * sched.num_inference_steps
+    xts = model.sample_xts_from_x0(x0, num_inference_steps=N, noise=noise)
+    zs = torch.zeros(size=model.get_noise_shape(x0, N), device=model.device)
+    extra_info = [None] * len(zs)
+    model.setup_extra_inputs(x0, init_timestep=timesteps[0], audio_end_in_s=duration)
+
+    tb = forward_batch if forward_batch is not None else DEFAULT_FORWARD_BATCH
+    tb = max(1, min(int(tb), N))
+    streams, masks, cl = _cat_text(model, uncond, cond)
+    text = model._cached_text(streams, masks) if streams else None
+    tab = model.sched_table
+    n_el = x0[0].numel()
+    rows = 1 + P
+    xt_src = xts.clone() if tb > 1 else xts      # batched: every U-Net input is the directly sampled x_t (F8)
+    ts_cpu = sched.timesteps_cpu
+    eta0 = float(etas[0])
+    if any(float(e) != eta0 for e in etas):
+        tb = 1
+    it = range(0, N, tb)
+    if prog_bar:
+        it = tqdm(it)
+    for pos0 in it:
+        count = min(tb, N - pos0)
+        # loop position pos <-> idx = N - pos - 1 (inversion_utils.py:75); U-Net input xts[idx+1] = xts[N - pos]
+        src_rows = torch.arange(N - pos0, N - pos0 - count, -1, device=model.device)
+        xt_b = xt_src.index_select(0, src_rows)                                    # [count, C, H, W]
+        t_b = ts_cpu[pos0:pos0 + count].to(model.device)
+        if P > 0:
+            x_in = torch.cat([xt_b, xt_b.repeat_interleave(P, 0)], 0)
+            t_in = torch.cat([t_b, t_b.repeat_interleave(P)], 0)
+            slot = torch.cat([torch.zeros(count, dtype=torch.int32),
+                              (1 + torch.arange(P, dtype=torch.int32)).repeat(count)]).to(model.device)
+        else:
+            x_in, t_in = xt_b, t_b
+            slot = torch.zeros(count, dtype=torch.int32, device=model.device)
+        cl_b = None if cl is None else cl.index_select(0, slot.long())
+        eps = model.engine.forward(x_in, t_in, text=text, slot_map=slot if text is not None else None, class_labels=cl_b)
+        eta = float(etas[N - pos0 - 1])
+        _lib.check(tab.lib.ae_cfg_inv_step(tab.h, pos0, count, eta, _ptr(eps), n_el,
+                                           _ptr(eps[count:]) if P > 0 else None, n_el, P, _ptr(cfg_map), _ptr(xt_src),
+                                           _ptr(xts), _ptr(zs), int(bool(numerical_fix)), n_el, _stream()),
+                   "ae_cfg_inv_step")
+    xt = xts[1][None] if N >= 1 else x0                 # the reference returns the last loop's xt = xts[1]
+    zs[0] = torch.zeros_like(zs[0])                     # inversion_utils.py:133
+    return xt, zs, xts, extra_info
+
+
+def inversion_reverse_process(model: PipelineWrapper,
+                              xT: torch.Tensor,
+                              tstart: torch.Tensor,
+                              fix_alpha: float = 0.1,
+                              etas: float = 0,
+                              prompts: List[str] = [""],
+                              neg_prompts: List[str] = [""],
+                              cfg_scales: Optional[List[float]] = None,
+                              prog_bar: bool = False,
+                              zs: Optional[List[torch.Tensor]] = None,
+                              cutoff_points: Optional[List[float]] = None,
+                              hspace_add: Optional[torch.Tensor] = None,
+                              hspace_replace: Optional[torch.Tensor] = None,
+                              skipconns_replace: Optional[Dict[int, torch.Tensor]] = None,
+                              zero_out_resconns: Optional[Union[int, List]] = None,
+                              extract_h_space: bool = False,
+                              extract_skipconns: bool = False,
+                              duration: Optional[float] = None,
+                              first_order: bool = False,
+                              extra_info: Optional[List] = None,
+                              trace: Optional[List] = None) -> Tuple:
+    """`trace` (optional list) receives a clone of x_t after every step — a debugging / test hook that the
+    reference does not have."""
+    taps = (hspace_add is not None or hspace_replace is not None or skipconns_replace is not None
+            or zero_out_resconns is not None or extract_h_space or extract_skipconns)
+    if taps or not prompts:
+        return _reverse_general(model, xT, tstart, fix_alpha, etas, prompts, neg_prompts, cfg_scales, prog_bar, zs,
+                                cutoff_points, hspace_add, hspace_replace, skipconns_replace, zero_out_resconns,
+                                extract_h_space, extract_skipconns, duration, first_order, extra_info)
+    P = len(prompts)
+    cond = model.encode_text(prompts)
+    uncond = model.encode_text(neg_prompts, negative=True)
+    cfg_map, masks = _build_cfg_maps(P, xT.shape[1:], cfg_scales, cutoff_points, model.device, xT.dtype, masks_too=True)
+    sched = model.model.scheduler
+    N = sched.num_inference_steps
+    xt = xT[int(tstart.max())].unsqueeze(0).to(torch.float32).contiguous().clone()
+    if etas is None:
+        etas = 0
+    if type(etas) in [int, float]:
+        etas = [etas] * N
+    assert len(etas) == N
+    n = zs.shape[0]
+    ts_cpu = sched.timesteps_cpu[-n:]
+    model.setup_extra_inputs(xt, extra_info=extra_info, init_timestep=ts_cpu[0], audio_end_in_s=duration)
+    streams, masks_t, cl = _cat_text(model, uncond, cond)
+    text = model._cached_text(streams, masks_t) if streams else None
+    tab = model.sched_table
+    n_el = xt.numel()
+    rows = 1 + P
+    slot = torch.arange(rows, dtype=torch.int32, device=model.device)
+    zs = zs.contiguous()
+    tmax = int(tstart.max())
+    it = range(n)
+    if prog_bar:
+        it = tqdm(it)
+    x_in = torch.empty((rows, *xt.shape[1:]), device=model.device, dtype=torch.float32)
+    for k in it:
+        t = int(ts_cpu[k])
+        pos = N - n + k
+        idx = n - k - 1                                                      # inversion_utils.py:222-224
+        x_in.copy_(xt.expand(rows, -1, -1, -1))
+        t_in = torch.full((rows,), t, dtype=torch.int64, device=model.device)
+        eps = model.engine.forward(x_in, t_in, text=text, slot_map=slot if text is not None else None, class_labels=cl)
+        apply_fix = ((tstart.max() - tstart) > k)
+        fix_h = None
+        xT_fix = None
+        if apply_fix.any():                                                  # inversion_utils.py:308-315
+            fa = (apply_fix * fix_alpha).to(torch.float32)
+            fix_h = (C.c_float * 8)(*([float(v) for v in fa] + [0.0] * (8 - P)))
+            xT_fix = xT[tmax - k - 1].to(torch.float32).contiguous()
+        out = torch.empty_like(xt)
+        _lib.check(tab.lib.ae_cfg_rev_step(tab.h, pos, None, float(etas[idx]), _ptr(eps), _ptr(eps[1:]), P,
+                                           _ptr(cfg_map), _ptr(xt), _ptr(zs[idx]), _ptr(out),
+                                           _ptr(masks) if fix_h is not None else None,
+                                           C.cast(fix_h, C.c_void_p) if fix_h is not None else None, _ptr(xT_fix),
+                                           n_el, _stream()), "ae_cfg_rev_step")
+        xt = out
+        if trace is not None:
+            trace.append(xt.clone())
+    return xt, zs
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# General path: the reference's per-step structure (needed when h-space / skip-connection taps are requested).
+# ------------------------------------------------------------------------------------------------------------------
+def _forward_general(model, x0, etas, prog_bar, prompts, cfg_scales, num_inference_steps, cutoff_points,
+                     numerical_fix, extract_h_space, extract_skipconns, duration, first_order):
+    have_cond = len(prompts) > 1 or prompts[0] != ""
+    if have_cond:
+        text_hs, text_cl, text_mask = model.encode_text(prompts)
+        batch_size = len(prompts)
+        cfg_scales_tensor, _ = _build_cfg_maps(batch_size, x0.shape[1:], cfg_scales, cutoff_points, model.device,
+                                               x0.dtype, prompts)
+    un_hs, un_cl, un_mask = model.encode_text([""], negative=True)
+    timesteps = model.model.scheduler.timesteps.to(model.device)
+    variance_noise_shape = model.get_noise_shape(x0, num_inference_steps)
+    if type(etas) in [int, float]:
+        etas = [etas] * model.model.scheduler.num_inference_steps
+    xts = model.sample_xts_from_x0(x0, num_inference_steps=num_inference_steps)
+    zs = torch.zeros(size=variance_noise_shape, device=model.device)
+    extra_info = [None] * len(zs)
+    hspaces, skipconns = [], []
+    t_to_idx = _t_to_idx(timesteps)
+    xt = x0
+    op = tqdm(timesteps) if prog_bar else timesteps
+    model.setup_extra_inputs(xt, init_timestep=timesteps[0], audio_end_in_s=duration)
+    for t in op:
+        idx = num_inference_steps - t_to_idx[int(t)] - 1
+        xt = xts[idx + 1][None]
+        xt_inp = model.model.scheduler.scale_model_input(xt, t)
+        with torch.no_grad():
+            out, out_hspace, out_skipconns = model.unet_forward(
+                xt_inp, timestep=t, encoder_hidden_states=un_hs, class_labels=un_cl, encoder_attention_mask=un_mask)
+            if have_cond:
+                cond_out, cond_out_hspace, cond_out_skipconns = model.unet_forward(
+                    xt_inp.expand(len(prompts), -1, -1, -1), timestep=t, encoder_hidden_states=text_hs,
+                    class_labels=text_cl, encoder_attention_mask=text_mask)
+        if have_cond:
+            noise_pred = out.sample + (cfg_scales_tensor * (cond_out.sample - out.sample.expand(batch_size, -1, -1, -1))
+                                       ).sum(axis=0).unsqueeze(0)
+            noise_h_space = out_hspace + cfg_scales[0] * (cond_out_hspace - out_hspace)
+            if extract_skipconns:
+                noise_skipconns = {k: [out_skipconns[k][j] + cfg_scales[0] * (cond_out_skipconns[k][j] - out_skipconns[k][j])
+                                       for j in range(len(out_skipconns[k]))] for k in out_skipconns}
+        else:
+            noise_pred = out.sample
+            noise_h_space = out_hspace
+            if extract_skipconns:
+                noise_skipconns = out_skipconns
+        hspaces.append(noise_h_space)
+        if extract_skipconns:
+            skipconns.append(noise_skipconns)
+        xtm1 = xts[idx][None]
+        z, xtm1, extra = model.get_zs_from_xts(xt, xtm1, noise_pred, t, eta=etas[idx], numerical_fix=numerical_fix,
+                                               first_order=first_order)
+        zs[idx] = z
+        xts[idx] = xtm1
+        extra_info[idx] = extra
+    if zs is not None:
+        zs[0] = torch.zeros_like(zs[0])
+    if extract_h_space:
+        return xt, zs, xts, extra_info, torch.concat(hspaces, axis=0)
+    return xt, zs, xts, extra_info, torch.concat(hspaces, axis=0), skipconns
+
+
+def _reverse_general(model, xT, tstart, fix_alpha, etas, prompts, neg_prompts, cfg_scales, prog_bar, zs, cutoff_points,
+                     hspace_add, hspace_replace, skipconns_replace, zero_out_resconns, extract_h_space,
+                     extract_skipconns, duration, first_order, extra_info):
+    batch_size = len(prompts)
+    text_hs, text_cl, text_mask = model.encode_text(prompts)
+    un_hs, un_cl, un_mask = model.encode_text(neg_prompts, negative=True)
+    cfg_scales_tensor, masks = _build_cfg_maps(batch_size, xT.shape[1:], cfg_scales, cutoff_points, model.device,
+                                               xT.dtype, masks_too=True)
+    xt = xT[tstart.max()].unsqueeze(0)
+    if etas is None:
+        etas = 0
+    if type(etas) in [int, float]:
+        etas = [etas] * model.model.scheduler.num_inference_steps
+    assert len(etas) == model.model.scheduler.num_inference_steps
+    timesteps = model.model.scheduler.timesteps.to(model.device)
+    op = tqdm(timesteps[-zs.shape[0]:]) if prog_bar else timesteps[-zs.shape[0]:]
+    t_to_idx = _t_to_idx(timesteps[-zs.shape[0]:])
+    hspaces, skipconns = [], []
+    model.setup_extra_inputs(xt, extra_info=extra_info, init_timestep=timesteps[-zs.shape[0]], audio_end_in_s=duration)
+    N = model.model.scheduler.num_inference_steps
+    for it, t in enumerate(op):
+        idx = N - t_to_idx[int(t)] - (N - zs.shape[0] + 1)
+        xt_inp = model.model.scheduler.scale_model_input(xt, t)
+
+        def tap_args(weight):
+            return dict(
+                mid_block_additional_residual=(None if hspace_add is None else weight *
+                                               (hspace_add[-zs.shape[0]:][it] if hspace_add.shape[0] > 1 else hspace_add)),
+                replace_h_space=(None if hspace_replace is None else
+                                 (hspace_replace[-zs.shape[0]:][it].unsqueeze(0) if hspace_replace.shape[0] > 1
+                                  else hspace_replace)),
+                zero_out_resconns=zero_out_resconns,
+                replace_skip_conns=(None if skipconns_replace is None else
+                                    (skipconns_replace[-zs.shape[0]:][it] if len(skipconns_replace) > 1
+                                     else skipconns_replace)))
+        with torch.no_grad():
+            uncond_out, out_hspace, out_skipconns = model.unet_forward(
+                xt_inp, timestep=t, encoder_hidden_states=un_hs, class_labels=un_cl, encoder_attention_mask=un_mask,
+                **tap_args(None if hspace_add is None else 1 / (cfg_scales[0] + 1)))
+        if prompts:
+            with torch.no_grad():
+                cond_out, cond_out_hspace, cond_out_skipconns = model.unet_forward(
+                    xt_inp.expand(batch_size, -1, -1, -1), timestep=t, encoder_hidden_states=text_hs,
+                    class_labels=text_cl, encoder_attention_mask=text_mask,
+                    **tap_args(None if hspace_add is None else cfg_scales[0] / (cfg_scales[0] + 1)))
+        z = zs[idx] if zs is not None else None
+        z = z.unsqueeze(0)
+        if prompts:
+            noise_pred = uncond_out.sample + (cfg_scales_tensor * (cond_out.sample -
+                                                                   uncond_out.sample.expand(batch_size, -1, -1, -1))
+                                              ).sum(axis=0).unsqueeze(0)
+            if extract_h_space or extract_skipconns:
+                noise_h_space = out_hspace + cfg_scales[0] * (cond_out_hspace - out_hspace)
+            if extract_skipconns:
+                noise_skipconns = {k: [out_skipconns[k][j] + cfg_scales[0] * (cond_out_skipconns[k][j] - out_skipconns[k][j])
+                                       for j in range(len(out_skipconns[k]))] for k in out_skipconns}
+        else:
+            noise_pred = uncond_out.sample
+            if extract_h_space or extract_skipconns:
+                noise_h_space = out_hspace
+            if extract_skipconns:
+                noise_skipconns = out_skipconns
+        if extract_h_space or extract_skipconns:
+            hspaces.append(noise_h_space)
+        if extract_skipconns:
+            skipconns.append(noise_skipconns)
+        xt = model.reverse_step_with_custom_noise(noise_pred, t, xt, variance_noise=z, eta=etas[idx],
+                                                  first_order=first_order)
+        apply_fix = ((tstart.max() - tstart) > it)
+        if apply_fix.any():
+            apply_fix = (apply_fix * fix_alpha).unsqueeze(1).unsqueeze(2).unsqueeze(3).to(xT.device)
+            xt = (masks * (xt.expand(batch_size, -1, -1, -1) * (1 - apply_fix) +
+                           apply_fix * (xT[tstart.max() - it - 1].expand(batch_size, -1, -1, -1)))).sum(axis=0).unsqueeze(0)
+    if extract_h_space:
+        return xt, zs, torch.concat(hspaces, axis=0)
+    if extract_skipconns:
+        return xt, zs, torch.concat(hspaces, axis=0), skipconns
+    return xt, zs

@@ -1,0 +1,384 @@
+"""Drop-in replacement of the reference's model-wrapper boundary (code/models.py): same class names, method
+names, argument meaning and error behaviour for the audio path — `PipelineWrapper`, `AudioLDMWrapper`,
+`AudioLDM2Wrapper`, `TangoWrapper`, `load_model` — so the loops in ddm_inversion/inversion_utils.py and
+pc_drift.py (and the reference's own main_run*.py) run unchanged on top of it.
+
+What is different underneath: there is no diffusers pipeline object.  `self.model` is a light namespace exposing
+exactly the attributes the callers touch (`.unet.config.in_channels`, `.scheduler`,
+`.vocoder.config`, `.vae_scale_factor`), and every device computation goes to libaedit.so:
+    unet_forward                       -> UNetEngine (tcgen05 GEMM/conv, fused norms, attention)      models.py:160-393
+    sample_xts_from_x0                 -> ae_sample_xts                                                models.py:67-83
+    get_zs_from_xts                    -> ae_cfg_inv_step (P = 0)                                      models.py:85-117
+    reverse_step_with_custom_noise     -> ae_cfg_rev_step (P = 0)                                      models.py:119-158
+Image / StableAudio wrappers of the reference (models.py:902-1354) are out of scope.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import types
+from typing import Any, Dict, List, Optional, Tuple, Union
+
+import torch
+
+from . import _lib
+from .scheduler import DDIMScheduler
+from .unet import UNetEngine, TextCache
+from .unet_config import UNetConfig, from_model_id
+from . import weights as W
+
+
+class UNet2DConditionOutput:
+    """Stand-in for diffusers' output dataclass: the loops only read `.sample` (models.py:7,393)."""
+
+    def __init__(self, sample: torch.Tensor):
+        self.sample = sample
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class SchedTable:
+    """libaedit scheduler table bound to a DDIMScheduler state (rebuilt when set_timesteps changes)."""
+
+    def __init__(self, scheduler: DDIMScheduler):
+        lib = _lib.load()
+        self.lib = lib
+        ac = scheduler.alphas_cumprod.contiguous()
+        ts = scheduler.timesteps_cpu.contiguous()
+        h = C.c_void_p()
+        pred = {"epsilon": 0, "v_prediction": 1}[scheduler.config.prediction_type]
+        _lib.check(lib.ae_sched_create(C.c_void_p(ac.data_ptr()), ac.numel(), float(scheduler.final_alpha_cumprod),
+                                       C.c_void_p(ts.data_ptr()), ts.numel(), pred, C.byref(h)), "ae_sched_create")
+        self.h = h
+        self.N = ts.numel()
+        self._keep = (ac, ts)
+
+    def pos_of_t(self, t: int) -> int:
+        pos = self.lib.ae_sched_pos_of_t(self.h, int(t))
+        if pos < 0:
+            raise KeyError(f"timestep {int(t)} is not in the scheduler's timesteps")   # dict KeyError in the reference
+        return pos
+
+    def row(self, pos: int) -> _lib.AeSchedRow:
+        r = _lib.AeSchedRow()
+        _lib.check(self.lib.ae_sched_row_h(self.h, pos, C.byref(r)), "ae_sched_row_h")
+        return r
+
+    def __del__(self):
+        try:
+            self.lib.ae_sched_destroy(self.h)
+        except Exception:
+            pass
+
+
+class PipelineWrapper(torch.nn.Module):
+    def __init__(self, model_id: str, device: torch.device, double_precision: bool = False,
+                 token: Optional[str] = None, *args, weights: Optional[Dict[str, torch.Tensor]] = None,
+                 config: Optional[UNetConfig] = None, weight_seed: int = 0, **kwargs) -> None:
+        super().__init__()
+        self.model_id = model_id
+        self.device = torch.device(device)
+        self.double_precision = double_precision
+        self.token = token
+        if double_precision:
+            raise NotImplementedError("double_precision: the B200 path computes U-Net internals in bf16/fp32")
+        cfg = config
+        ckpt_dir = model_id if os.path.isdir(model_id) else None
+        if cfg is None:
+            if ckpt_dir and os.path.exists(os.path.join(ckpt_dir, "unet", "config.json")):
+                cfg = W.unet_config_from_json(os.path.join(ckpt_dir, "unet", "config.json"), os.path.basename(ckpt_dir))
+            else:
+                cfg = from_model_id(model_id)
+        self.unet_config = cfg
+        if weights is None:
+            if ckpt_dir:
+                weights = W.load_unet_checkpoint(os.path.join(ckpt_dir, "unet"), cfg)
+                self.weights_source = f"checkpoint:{ckpt_dir}"
+            else:
+                # no network / no weights on disk: seeded synthetic weights of the named architecture
+                weights = W.synthetic_weights(cfg, seed=weight_seed)
+                self.weights_source = f"synthetic(seed={weight_seed})"
+        else:
+            self.weights_source = "caller"
+        self.engine = UNetEngine(cfg, weights, self.device)
+        unet_ns = types.SimpleNamespace(config=types.SimpleNamespace(in_channels=cfg.in_channels,
+                                                                     sample_size=256, out_channels=cfg.out_channels),
+                                        num_upsamplers=len(cfg.block_out_channels) - 1)
+        vocoder_ns = types.SimpleNamespace(config=types.SimpleNamespace(model_in_dim=64, upsample_rates=[5, 4, 2, 2, 2],
+                                                                        sampling_rate=16000))
+        self.model = types.SimpleNamespace(unet=unet_ns, scheduler=None, vocoder=vocoder_ns, vae_scale_factor=4)
+        self._text_cache: Dict[Any, TextCache] = {}
+        self._sched_table: Optional[SchedTable] = None
+
+    # ---------------------------------------------------------------- scheduler plumbing
+    @property
+    def sched_table(self) -> SchedTable:
+        s = self.model.scheduler
+        if s._table is None:
+            s._table = SchedTable(s)
+        return s._table
+
+    def get_sigma(self, timestep: int) -> float:                      # models.py:25-27
+        sqrt_recipm1_alphas_cumprod = torch.sqrt(1.0 / self.model.scheduler.alphas_cumprod - 1)
+        return sqrt_recipm1_alphas_cumprod[timestep]
+
+    def load_scheduler(self) -> None:
+        cfg = self.unet_config
+        self.model.scheduler = DDIMScheduler(cfg.beta_start, cfg.beta_end, prediction_type=cfg.prediction_type)
+
+    def get_fn_STFT(self) -> torch.nn.Module:
+        from .audio import TacotronSTFT
+        return TacotronSTFT(filter_length=1024, hop_length=160, win_length=1024, n_mel_channels=64,
+                            sampling_rate=16000, mel_fmin=0, mel_fmax=8000, device=self.device)
+
+    def get_sr(self) -> int:
+        return 16000
+
+    def setup_extra_inputs(self, *args, **kwargs) -> None:           # models.py:47-48 (StableAudio only)
+        pass
+
+    def get_variance(self, timestep: torch.Tensor, prev_timestep: torch.Tensor) -> torch.Tensor:   # models.py:539-545
+        alpha_prod_t = self.model.scheduler.alphas_cumprod[int(timestep)]
+        alpha_prod_t_prev = self.get_alpha_prod_t_prev(prev_timestep)
+        beta_prod_t = 1 - alpha_prod_t
+        beta_prod_t_prev = 1 - alpha_prod_t_prev
+        return (beta_prod_t_prev / beta_prod_t) * (1 - alpha_prod_t / alpha_prod_t_prev)
+
+    def get_alpha_prod_t_prev(self, prev_timestep: torch.Tensor) -> torch.Tensor:                 # models.py:547-549
+        return self.model.scheduler.alphas_cumprod[int(prev_timestep)] if prev_timestep >= 0 \
+            else self.model.scheduler.final_alpha_cumprod
+
+    def get_noise_shape(self, x0: torch.Tensor, num_steps: int) -> Tuple[int, ...]:                # models.py:60-65
+        return (num_steps, self.model.unet.config.in_channels, x0.shape[-2], x0.shape[-1])
+
+    # ---------------------------------------------------------------- a3: models.py:67-83
+    def sample_xts_from_x0(self, x0: torch.Tensor, num_inference_steps: int = 50,
+                           noise: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Samples from P(x_1:T|x_0).  `noise` ([N, C, H, W], draw order = ascending t like the reference's loop)
+        may be passed explicitly; otherwise it is drawn with N torch.randn_like calls in the reference's order so
+        a seeded run consumes the generator identically."""
+        tab = self.sched_table
+        N = tab.N
+        assert N == num_inference_steps
+        x0 = x0.to(self.device, torch.float32).contiguous()
+        if noise is None:
+            noise = torch.stack([torch.randn_like(x0[0]) for _ in range(N)])
+        noise = noise.to(self.device, torch.float32).contiguous()
+        xts = torch.empty(self.get_noise_shape(x0, N + 1), device=self.device, dtype=torch.float32)
+        n_el = x0[0].numel()
+        _lib.check(tab.lib.ae_sample_xts(tab.h, _ptr(x0), _ptr(noise), _ptr(xts), n_el, _stream()), "ae_sample_xts")
+        return xts
+
+    # ---------------------------------------------------------------- a4: models.py:85-117
+    def get_zs_from_xts(self, xt: torch.Tensor, xtm1: torch.Tensor, noise_pred: torch.Tensor, t: torch.Tensor,
+                        eta: float = 0, numerical_fix: bool = True, **kwargs
+                        ) -> Tuple[torch.Tensor, torch.Tensor, Optional[torch.Tensor]]:
+        tab = self.sched_table
+        pos = tab.pos_of_t(int(t))
+        n_el = xt.numel()
+        # the kernel addresses xt as xt_src[idx+1] and xtm1 as xts[idx]: hand it 2-row scratch views
+        idx = tab.N - pos - 1
+        xt = xt.to(torch.float32).contiguous()
+        xtm1_out = xtm1.to(torch.float32).clone().contiguous()
+        z = torch.empty_like(xtm1_out)
+        base_src = xt.data_ptr() - (idx + 1) * n_el * 4
+        base_xts = xtm1_out.data_ptr() - idx * n_el * 4
+        base_zs = z.data_ptr() - idx * n_el * 4
+        _lib.check(tab.lib.ae_cfg_inv_step(tab.h, pos, 1, float(eta), _ptr(noise_pred.to(torch.float32).contiguous()),
+                                           n_el, None, 0, 0, None, C.c_void_p(base_src), C.c_void_p(base_xts),
+                                           C.c_void_p(base_zs), int(bool(numerical_fix)), n_el, _stream()),
+                   "ae_cfg_inv_step")
+        return z, xtm1_out, None
+
+    # ---------------------------------------------------------------- a5: models.py:119-158
+    def reverse_step_with_custom_noise(self, model_output: torch.Tensor, timestep: torch.Tensor, sample: torch.Tensor,
+                                       variance_noise: Optional[torch.Tensor] = None, eta: float = 0, **kwargs
+                                       ) -> torch.Tensor:
+        tab = self.sched_table
+        pos = tab.pos_of_t(int(timestep))
+        if eta > 0 and variance_noise is None:
+            variance_noise = torch.randn(model_output.shape, device=self.device)          # models.py:153-154
+        out = torch.empty_like(sample, dtype=torch.float32)
+        _lib.check(tab.lib.ae_cfg_rev_step(tab.h, pos, None, float(eta), _ptr(model_output.to(torch.float32).contiguous()),
+                                           None, 0, None, _ptr(sample.to(torch.float32).contiguous()),
+                                           _ptr(None if variance_noise is None else
+                                                variance_noise.to(torch.float32).contiguous()),
+                                           _ptr(out), None, None, None, sample.numel(), _stream()), "ae_cfg_rev_step")
+        return out
+
+    # ---------------------------------------------------------------- a7/a8: models.py:160-393, :691-899
+    def _text_for(self, encoder_hidden_states, class_labels, encoder_attention_mask):
+        """Maps the reference's (encoder_hidden_states, class_labels, encoder_attention_mask) triple onto the
+        engine's text streams.  Overridden per family."""
+        raise NotImplementedError
+
+    def _cached_text(self, streams, masks) -> TextCache:
+        key = tuple((None if s is None else (s.data_ptr(), tuple(s.shape), s._version)) for s in list(streams) + list(masks))
+        tc = self._text_cache.get(key)
+        if tc is None:
+            if len(self._text_cache) > 16:
+                self._text_cache.clear()
+            tc = self.engine.prepare_text(streams, masks)
+            tc._keep = (streams, masks)
+            self._text_cache[key] = tc
+        return tc
+
+    def unet_forward(self,
+                     sample: torch.FloatTensor,
+                     timestep: Union[torch.Tensor, float, int],
+                     encoder_hidden_states: torch.Tensor,
+                     class_labels: Optional[torch.Tensor] = None,
+                     timestep_cond: Optional[torch.Tensor] = None,
+                     attention_mask: Optional[torch.Tensor] = None,
+                     cross_attention_kwargs: Optional[Dict[str, Any]] = None,
+                     added_cond_kwargs: Optional[Dict[str, torch.Tensor]] = None,
+                     down_block_additional_residuals: Optional[Tuple[torch.Tensor]] = None,
+                     mid_block_additional_residual: Optional[torch.Tensor] = None,
+                     encoder_attention_mask: Optional[torch.Tensor] = None,
+                     replace_h_space: Optional[torch.Tensor] = None,
+                     replace_skip_conns: Optional[Dict[int, torch.Tensor]] = None,
+                     return_dict: bool = True,
+                     zero_out_resconns: Optional[Union[int, List]] = None) -> Tuple:
+        if timestep_cond is not None or attention_mask is not None or down_block_additional_residuals is not None \
+                or added_cond_kwargs is not None:
+            raise NotImplementedError("timestep_cond / attention_mask / down_block_additional_residuals / "
+                                      "added_cond_kwargs are never passed on the audio editing path")
+        B = sample.shape[0]
+        if not torch.is_tensor(timestep):
+            timestep = torch.tensor([timestep], dtype=torch.int64)
+        t = timestep.reshape(-1).to(torch.int64)
+        if t.numel() == 1:
+            t = t.expand(B)
+        streams, masks, cl = self._text_for(encoder_hidden_states, class_labels, encoder_attention_mask)
+        text = slot = None
+        if streams:
+            text = self._cached_text(streams, masks)
+            if text.n_rows == B:
+                slot = torch.arange(B, dtype=torch.int32, device=self.device)
+            elif text.n_rows == 1:
+                slot = torch.zeros(B, dtype=torch.int32, device=self.device)
+            else:
+                raise ValueError(f"text batch {text.n_rows} does not match sample batch {B}")
+        if cl is not None and cl.shape[0] != B:
+            cl = cl.expand(B, -1)
+        out, h_space, extracted = self.engine.forward(
+            sample, t, text=text, slot_map=slot, class_labels=cl,
+            mid_block_additional_residual=mid_block_additional_residual, replace_h_space=replace_h_space,
+            replace_skip_conns=replace_skip_conns, zero_out_resconns=zero_out_resconns, want_taps=True)
+        if not return_dict:
+            return (out,)
+        return UNet2DConditionOutput(sample=out), h_space, extracted
+
+    # ---------------------------------------------------------------- text (a13) — synthetic fallback
+    def _synthetic_text(self, prompts: List[str], dim: int, L: Optional[int], normalize: bool, salt: int):
+        """Deterministic stand-in embeddings when no text-encoder checkpoint is on disk (no network here):
+        N(0,1) seeded by the prompt string."""
+        rows = []
+        for p in prompts:
+            seed = (sum((i + 1) * ord(c) for i, c in enumerate(p)) + 7919 * salt) % (2 ** 31)
+            g = torch.Generator().manual_seed(1000 + seed)
+            n = 1 if L is None else L
+            e = torch.randn(n, dim, generator=g)
+            if normalize:
+                e = torch.nn.functional.normalize(e, dim=-1)
+            rows.append(e)
+        return torch.stack(rows).to(self.device)
+
+    # ---------------------------------------------------------------- ends (a10-a12), filled by ends.py
+    def _ends(self):
+        if getattr(self, "_ends_obj", None) is None:
+            from .ends import AudioEnds
+            self._ends_obj = AudioEnds(self.device, self.model_id if os.path.isdir(self.model_id) else None)
+        return self._ends_obj
+
+    def vae_encode(self, x: torch.Tensor) -> torch.Tensor:                                    # models.py:495-499
+        if x.shape[2] % 4:
+            x = torch.nn.functional.pad(x, (0, 0, 4 - (x.shape[2] % 4), 0))
+        return self._ends().vae_encode_mode(x).float()
+
+    def vae_decode(self, x: torch.Tensor) -> torch.Tensor:                                    # models.py:502-503
+        return self._ends().vae_decode(x)
+
+    def decode_to_mel(self, x: torch.Tensor) -> torch.Tensor:                                 # models.py:505-509
+        return self._ends().vocoder(x[0, 0].detach().float()).detach().unsqueeze(0)
+
+
+class AudioLDMWrapper(PipelineWrapper):
+    """models.py:475-549.  Conditioning = L2-normalised 512-d CLAP text embedding passed as `class_labels`."""
+
+    def _text_for(self, encoder_hidden_states, class_labels, encoder_attention_mask):
+        return [], [], class_labels
+
+    def encode_text(self, prompts: List[str], **kwargs) -> Tuple[None, Optional[torch.Tensor], None]:
+        enc = self._ends().clap_text_encoder()
+        if enc is not None:
+            return None, enc(prompts), None
+        return None, self._synthetic_text(prompts, 512, None, True, 0)[:, 0], None
+
+
+class AudioLDM2Wrapper(PipelineWrapper):
+    """models.py:552-899.  encode_text returns (GPT-2 generated [P,8,768], T5 [P,L,1024], T5 mask [P,L]);
+    unet_forward routes them as stream 0 (unmasked) and stream 1 (masked) — the translation of models.py:706-710."""
+
+    def _text_for(self, encoder_hidden_states, class_labels, encoder_attention_mask):
+        return [encoder_hidden_states, class_labels], [None, encoder_attention_mask], None
+
+    def encode_text(self, prompts: List[str], **kwargs) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+        L = max(1, max(len(p.split()) for p in prompts) + (1 if any(p for p in prompts) else 0))
+        gen = self._synthetic_text(prompts, 768, 8, False, 1)
+        t5 = self._synthetic_text(prompts, 1024, L, False, 2)
+        mask = torch.zeros(len(prompts), L, dtype=torch.long, device=self.device)
+        for i, p in enumerate(prompts):
+            mask[i, : max(1, len(p.split()) + (1 if p else 0))] = 1
+        return gen, t5, mask
+
+    def decode_to_mel(self, x: torch.Tensor) -> torch.Tensor:                                 # models.py:591-597
+        tmp = self._ends().vocoder(x[:, 0].detach().float()).detach()
+        if len(tmp.shape) == 1:
+            tmp = tmp.unsqueeze(0)
+        return tmp
+
+
+class TangoWrapper(PipelineWrapper):
+    """models.py:396-472.  Conditioning = T5 hidden states + boolean mask; v-prediction scheduler (SD-2.1 betas)."""
+
+    def _text_for(self, encoder_hidden_states, class_labels, encoder_attention_mask):
+        return [encoder_hidden_states], [encoder_attention_mask], None
+
+    def vae_encode(self, x: torch.Tensor) -> torch.Tensor:                                    # models.py:439-447
+        if x.shape[2] % 4:
+            x = torch.nn.functional.pad(x, (0, 0, 4 - (x.shape[2] % 4), 0))
+        if x.shape[2] > 1700:
+            raise RuntimeWarning("This model dies at this point")
+        return self._ends().vae_encode_sample(x).float()
+
+    def encode_text(self, prompts: List[str], **kwargs) -> Tuple[Optional[torch.Tensor], None, Optional[torch.Tensor]]:
+        L = max(1, max(len(p.split()) for p in prompts) + 1)
+        t5 = self._synthetic_text(prompts, 1024, L, False, 3)
+        mask = torch.zeros(len(prompts), L, dtype=torch.bool, device=self.device)
+        for i, p in enumerate(prompts):
+            mask[i, : len(p.split()) + 1] = True
+        return t5, None, mask
+
+
+def load_model(model_id: str, device: torch.device, num_diffusion_steps: int,
+               double_precision: bool = False, token: Optional[str] = None, **kwargs) -> PipelineWrapper:
+    """models.py:1357-1374: substring dispatch, load_scheduler(), scheduler.set_timesteps(N)."""
+    if 'tango' in model_id:
+        ldm_stable = TangoWrapper(model_id=model_id, device=device, double_precision=double_precision, token=token, **kwargs)
+    elif 'audioldm2' in model_id:
+        ldm_stable = AudioLDM2Wrapper(model_id=model_id, device=device, double_precision=double_precision, token=token, **kwargs)
+    elif 'audioldm' in model_id:
+        ldm_stable = AudioLDMWrapper(model_id=model_id, device=device, double_precision=double_precision, token=token, **kwargs)
+    else:
+        raise ValueError(f"{model_id}: only the AudioLDM / AudioLDM2 / TANGO audio path is implemented "
+                         "(image and Stable Audio wrappers of the reference are out of scope)")
+    ldm_stable.load_scheduler()
+    ldm_stable.model.scheduler.set_timesteps(num_diffusion_steps, device=device)
+    return ldm_stable

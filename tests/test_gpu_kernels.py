@@ -1,0 +1,197 @@
+"""GPU parity tests of the individual libaedit kernels (run with `-m gpu` on a B200).  Each kernel is compared
+with a plain PyTorch fp32 computation of the same op on the same seeded inputs; bf16-operand kernels use inputs
+already rounded to bf16 so the only differences are accumulation order and the final rounding."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+BF = torch.bfloat16
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from audioeditingcode_b200.ops import CudaOps
+    o = CudaOps()
+    assert o.lib.ae_device_ok() == 1, "these tests need an sm_100 device"
+    return o
+
+
+def rnd(shape, seed, scale=1.0, dtype=torch.float32):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(shape, generator=g) * scale).to(dtype).cuda()
+
+
+def relerr(a, b):
+    return ((a.float() - b.float()).norm() / (b.float().norm() + 1e-12)).item()
+
+
+@pytest.mark.parametrize("M,N,K,bn", [(128, 128, 64, 0), (256, 256, 512, 128), (300, 200, 200, 64), (64, 40, 72, 32),
+                                      (4096, 128, 1152, 0), (128, 640, 5760, 0), (2, 8320, 1024, 0)])
+def test_gemm_plain(ops, M, N, K, bn):
+    A = rnd((M, K), 1, dtype=BF)
+    W = rnd((N, K), 2, 1 / math.sqrt(K), dtype=BF)
+    bias = rnd((N,), 3)
+    res = rnd((M, N), 4)
+    rowbias = rnd(((M + 15) // 16, N), 5)
+    o32 = torch.empty(M, N, device="cuda")
+    o16 = torch.empty(M, N, device="cuda", dtype=BF)
+    ops.gemm(A, W, out_f32=o32, out_bf16=o16, bias=bias, rowbias=rowbias, rows_per_group=16, residual=res, force_bn=bn)
+    ref = A.float() @ W.float().t() + bias + res + rowbias.repeat_interleave(16, 0)[:M]
+    torch.cuda.synchronize()
+    assert relerr(o32, ref) < 2e-5
+    assert relerr(o16, ref) < 4e-3
+    # SiLU epilogue, no extras
+    ops.gemm(A, W, out_f32=o32, act=1, force_bn=bn)
+    assert relerr(o32, F.silu(A.float() @ W.float().t())) < 2e-5
+
+
+def test_gemm_batched(ops):
+    Bz, M, N, K = 3, 200, 96, 160
+    A = rnd((Bz, M, K), 1, dtype=BF)
+    W = rnd((Bz, N, K), 2, 0.1, dtype=BF)
+    o = torch.empty(Bz, M, N, device="cuda")
+    ops.gemm(A, W, out_f32=o, batch=Bz, strideA=M * K, strideW=N * K, stride_out=M * N, alpha=0.5)
+    ref = 0.5 * torch.einsum("bmk,bnk->bmn", A.float(), W.float())
+    assert relerr(o, ref) < 2e-5
+
+
+@pytest.mark.parametrize("B,H,W,C,Co,kh,kw,dh,dw", [(2, 16, 16, 64, 128, 3, 3, 1, 1), (1, 256, 16, 128, 128, 3, 3, 1, 1),
+                                                    (2, 32, 2, 640, 640, 3, 3, 1, 1), (3, 64, 4, 384, 384, 3, 3, 1, 1),
+                                                    (1, 1, 1024, 64, 64, 1, 7, 1, 3), (2, 8, 8, 192, 8, 3, 3, 1, 1),
+                                                    (2, 128, 8, 256, 256, 1, 1, 1, 1)])
+def test_gemm_implicit_conv(ops, B, H, W, C, Co, kh, kw, dh, dw):
+    assert ops.conv_supported(B, H, W, C)
+    x = rnd((B, H, W, C), 1, dtype=BF)
+    wt = rnd((Co, C, kh, kw), 2, 1 / math.sqrt(C * kh * kw), dtype=BF)
+    bias = rnd((Co,), 3)
+    temb = rnd((B, Co), 4)
+    res = rnd((B * H * W, Co), 5)
+    Wp = wt.permute(0, 2, 3, 1).reshape(Co, -1).contiguous()
+    out = torch.empty(B * H * W, Co, device="cuda")
+    ops.gemm(x, Wp, out_f32=out, bias=bias, rowbias=temb, rows_per_group=H * W, residual=res,
+             conv=(B, H, W, C, kh, kw, dh, dw))
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), wt.float(), bias, padding=(dh * (kh - 1) // 2, dw * (kw - 1) // 2),
+                   dilation=(dh, dw))
+    ref = ref + temb[:, :, None, None]
+    ref = ref.permute(0, 2, 3, 1).reshape(B * H * W, Co) + res
+    assert relerr(out, ref) < 2e-5
+
+
+@pytest.mark.parametrize("stride,pad,H,W,C", [(2, 1, 16, 16, 64), (1, 1, 20, 16, 8), (2, 0, 17, 9, 32)])
+def test_im2col(ops, stride, pad, H, W, C):
+    B, kh, kw = 2, 3, 3
+    x = rnd((B, H, W, C), 1)
+    Ho = (H + 2 * pad - 3) // stride + 1
+    Wo = (W + 2 * pad - 3) // stride + 1
+    K = 9 * C
+    ld = (K + 7) // 8 * 8
+    col = torch.empty(B * Ho * Wo, ld, device="cuda", dtype=BF)
+    ops.im2col(x, B, H, W, C, kh, kw, stride, 1, pad, pad, Ho, Wo, col)
+    cols = F.unfold(x.permute(0, 3, 1, 2), 3, padding=pad, stride=stride)
+    cols = cols.reshape(B, C, 9, -1).permute(0, 3, 2, 1).reshape(B * Ho * Wo, K)
+    assert torch.equal(col[:, :K], cols.to(BF))
+
+
+@pytest.mark.parametrize("B,HW,C1,C2,G,silu", [(2, 4096, 128, 0, 32, True), (3, 64, 640, 640, 32, True),
+                                               (2, 256, 192, 96, 32, False), (1, 1000, 576, 384, 32, True)])
+def test_groupnorm(ops, B, HW, C1, C2, G, silu):
+    x1 = rnd((B, HW, C1), 1) + 0.5
+    x2 = rnd((B, HW, C2), 2, 2.0) if C2 else None
+    C = C1 + C2
+    gamma, beta = rnd((C,), 3) * 0.1 + 1, rnd((C,), 4) * 0.1
+    out = torch.empty(B, HW, C, device="cuda", dtype=BF)
+    raw = torch.empty(B, HW, C, device="cuda", dtype=BF)
+    ops.groupnorm(x1, x2, gamma, beta, 1e-5, G, silu, out, raw_out=raw)
+    x = x1 if x2 is None else torch.cat([x1, x2], -1)
+    ref = F.group_norm(x.permute(0, 2, 1), G, gamma, beta, 1e-5).permute(0, 2, 1)
+    if silu:
+        ref = F.silu(ref)
+    assert (out.float() - ref).abs().max().item() < 3e-2
+    assert relerr(out, ref) < 4e-3
+    assert torch.equal(raw, x.to(BF))
+    # second call reuses the self-re-arming workspace
+    ops.groupnorm(x1, x2, gamma, beta, 1e-5, G, silu, out)
+    assert relerr(out, ref) < 4e-3
+
+
+def test_layernorm_geglu(ops):
+    x = rnd((300, 384), 1) * 2 + 0.3
+    g, b = rnd((384,), 2) * 0.1 + 1, rnd((384,), 3) * 0.1
+    out = torch.empty(300, 384, device="cuda", dtype=BF)
+    ops.layernorm(x, g, b, out)
+    assert relerr(out, F.layer_norm(x, (384,), g, b)) < 4e-3
+    h = rnd((100, 2 * 256), 4, dtype=BF)
+    o = torch.empty(100, 256, device="cuda", dtype=BF)
+    ops.geglu(h, o)
+    a, gt = h.float().chunk(2, -1)
+    assert relerr(o, a * F.gelu(gt)) < 4e-3
+
+
+@pytest.mark.parametrize("d,heads,Tq,Tk", [(32, 4, 64, 64), (32, 8, 1024, 1024), (64, 5, 200, 200), (48, 8, 256, 256),
+                                           (72, 8, 64, 64), (120, 8, 64, 64), (160, 8, 64, 64), (96, 8, 130, 77)])
+def test_attention_self(ops, d, heads, Tq, Tk):
+    B, C = 2, heads * d
+    q = rnd((B, Tq, C), 1, dtype=BF)
+    k = rnd((B, Tk, C), 2, dtype=BF)
+    v = rnd((B, Tk, C), 3, dtype=BF)
+    out = torch.empty(B * Tq, C, device="cuda", dtype=BF)
+    ops.attention(q, k, v, out, heads, d, d ** -0.5, Tq, Tk, B, C, Tq * C, C, Tk * C, C, Tk * C)
+    qh, kh, vh = (t.float().view(B, -1, heads, d).transpose(1, 2) for t in (q, k, v))
+    ref = (qh @ kh.transpose(-1, -2) * d ** -0.5).softmax(-1) @ vh
+    ref = ref.transpose(1, 2).reshape(B * Tq, C)
+    assert relerr(out, ref) < 1e-2
+
+
+def test_attention_cross_masked(ops):
+    B, heads, d, Tq, R, L = 4, 8, 48, 256, 2, 13
+    C = heads * d
+    q = rnd((B, Tq, C), 1, dtype=BF)
+    kv = rnd((R, L, 2 * C), 2, dtype=BF)
+    slot = torch.tensor([0, 1, 1, 0], dtype=torch.int32, device="cuda")
+    mask = torch.ones(R, L, device="cuda")
+    mask[1, 9:] = 0
+    bias = (1 - mask) * -10000.0
+    out = torch.empty(B * Tq, C, device="cuda", dtype=BF)
+    ops.attention(q, kv, kv[:, :, C:], out, heads, d, d ** -0.5, Tq, L, B, C, Tq * C, 2 * C, L * 2 * C, 2 * C, L * 2 * C,
+                  kv_map=slot, bias=bias)
+    k = kv[:, :, :C][slot.long()].float().view(B, L, heads, d).transpose(1, 2)
+    v = kv[:, :, C:][slot.long()].float().view(B, L, heads, d).transpose(1, 2)
+    qh = q.float().view(B, Tq, heads, d).transpose(1, 2)
+    s = qh @ k.transpose(-1, -2) * d ** -0.5 + bias[slot.long()][:, None, None, :]
+    ref = (s.softmax(-1) @ v).transpose(1, 2).reshape(B * Tq, C)
+    assert relerr(out, ref) < 1e-2
+
+
+def test_small_movers(ops):
+    t = torch.tensor([981, 501, 1, 0], device="cuda")
+    out = torch.empty(4, 128, device="cuda", dtype=BF)
+    ops.timestep_embedding(t, 128, out)
+    half = 64
+    freqs = torch.exp(-math.log(10000.0) * torch.arange(half, dtype=torch.float32, device="cuda") / half)
+    args = t[:, None].float() * freqs[None]
+    ref = torch.cat([torch.cos(args), torch.sin(args)], -1)
+    assert (out.float() - ref).abs().max().item() < 1e-2
+    x = rnd((2, 5, 7, 64), 1)
+    up = torch.empty(2, 10, 13, 64, device="cuda", dtype=BF)
+    ops.upsample_nearest(x, 2, 5, 7, 64, 10, 13, up)
+    ref = F.interpolate(x.permute(0, 3, 1, 2), size=(10, 13), mode="nearest").permute(0, 2, 3, 1)
+    assert torch.equal(up, ref.to(BF))
+    y = rnd((3, 8, 20, 16), 2)
+    nhwc = torch.empty(3, 20, 16, 8, device="cuda")
+    ops.nchw_to_nhwc(y, out_f32=nhwc)
+    assert torch.equal(nhwc, y.permute(0, 2, 3, 1).contiguous())
+    back = torch.empty_like(y)
+    ops.nhwc_to_nchw(nhwc, 3, 8, 20, 16, back)
+    assert torch.equal(back, y)
+    s = rnd((70, 333), 3)
+    so = torch.empty(70, 333, device="cuda", dtype=BF)
+    ops.softmax_rows(s, so)
+    assert relerr(so, s.softmax(-1)) < 4e-3
+    tb = rnd((2, 50, 70), 4, dtype=BF)
+    to = torch.empty(2, 70, 50, device="cuda", dtype=BF)
+    ops.transpose_bf16(tb, to)
+    assert torch.equal(to, tb.transpose(1, 2).contiguous())
