@@ -31,6 +31,19 @@ from .. import _lib
 from ..models import PipelineWrapper, _ptr, _stream
 
 DEFAULT_FORWARD_BATCH = int(os.environ.get("AEDIT_FORWARD_BATCH", "8"))
+USE_CUDA_GRAPHS = os.environ.get("AEDIT_CUDA_GRAPH", "1") != "0"
+
+
+def _unet_eval(model, x_in, t_in, text, slot, cl, slot_key=None):
+    """One batched U-Net evaluation, through a cached CUDA graph unless AEDIT_CUDA_GRAPH=0."""
+    eng = model.engine
+    slot_arg = slot if text is not None else None
+    if USE_CUDA_GRAPHS and x_in.is_cuda:
+        g = eng.graphed(x_in.shape[0], x_in.shape[2], x_in.shape[3], text, slot_arg, cl, slot_key=slot_key)
+        model.graph_replays = getattr(model, "graph_replays", 0) + 1
+        model.graph_kernels = getattr(model, "graph_kernels", 0) + g.kernels
+        return g(x_in, t_in, cl)
+    return eng.forward(x_in, t_in, text=text, slot_map=slot_arg, class_labels=cl)
 
 
 def _gaussian_blur_k15_s1(x: torch.Tensor) -> torch.Tensor:
@@ -176,12 +189,10 @@ def inversion_forward_process(model: PipelineWrapper,
             x_in, t_in = xt_b, t_b
             slot = torch.zeros(count, dtype=torch.int32, device=model.device)
         cl_b = None if cl is None else cl.index_select(0, slot.long())
-        eps = model.engine.forward(x_in, t_in, text=text, slot_map=slot if text is not None else None, class_labels=cl_b)
+        eps = _unet_eval(model, x_in, t_in, text, slot, cl_b, slot_key=("fwd", count, P))
         eta = float(etas[N - pos0 - 1])
-        _lib.check(tab.lib.ae_cfg_inv_step(tab.h, pos0, count, eta, _ptr(eps), n_el,
-                                           _ptr(eps[count:]) if P > 0 else None, n_el, P, _ptr(cfg_map), _ptr(xt_src),
-                                           _ptr(xts), _ptr(zs), int(bool(numerical_fix)), n_el, _stream()),
-                   "ae_cfg_inv_step")
+        model.k_cfg_inv_step(pos0, count, eta, eps, eps[count:] if P > 0 else None, P, cfg_map, xt_src, xts, zs,
+                             numerical_fix)
     xt = xts[1][None] if N >= 1 else x0                 # the reference returns the last loop's xt = xts[1]
     zs[0] = torch.zeros_like(zs[0])                     # inversion_utils.py:133
     return xt, zs, xts, extra_info
@@ -249,20 +260,16 @@ def inversion_reverse_process(model: PipelineWrapper,
         idx = n - k - 1                                                      # inversion_utils.py:222-224
         x_in.copy_(xt.expand(rows, -1, -1, -1))
         t_in = torch.full((rows,), t, dtype=torch.int64, device=model.device)
-        eps = model.engine.forward(x_in, t_in, text=text, slot_map=slot if text is not None else None, class_labels=cl)
+        eps = _unet_eval(model, x_in, t_in, text, slot, cl, slot_key=("rev", P))
         apply_fix = ((tstart.max() - tstart) > k)
-        fix_h = None
+        fa = None
         xT_fix = None
         if apply_fix.any():                                                  # inversion_utils.py:308-315
-            fa = (apply_fix * fix_alpha).to(torch.float32)
-            fix_h = (C.c_float * 8)(*([float(v) for v in fa] + [0.0] * (8 - P)))
+            fa = [float(v) for v in (apply_fix * fix_alpha).to(torch.float32)]
             xT_fix = xT[tmax - k - 1].to(torch.float32).contiguous()
         out = torch.empty_like(xt)
-        _lib.check(tab.lib.ae_cfg_rev_step(tab.h, pos, None, float(etas[idx]), _ptr(eps), _ptr(eps[1:]), P,
-                                           _ptr(cfg_map), _ptr(xt), _ptr(zs[idx]), _ptr(out),
-                                           _ptr(masks) if fix_h is not None else None,
-                                           C.cast(fix_h, C.c_void_p) if fix_h is not None else None, _ptr(xT_fix),
-                                           n_el, _stream()), "ae_cfg_rev_step")
+        model.k_cfg_rev_step(pos, float(etas[idx]), eps, eps[1:], P, cfg_map, xt, zs[idx], out, masks=masks,
+                             fix_alpha=fa, xT_fix=xT_fix)
         xt = out
         if trace is not None:
             trace.append(xt.clone())

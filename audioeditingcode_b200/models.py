@@ -212,6 +212,32 @@ class PipelineWrapper(torch.nn.Module):
                                            _ptr(out), None, None, None, sample.numel(), _stream()), "ae_cfg_rev_step")
         return out
 
+    # ---------------------------------------------------------------- fused kernels (a4+a9, a5+a9)
+    def k_cfg_inv_step(self, pos0: int, count: int, eta: float, eps_u, eps_c, P: int, cfg_map, xt_src, xts, zs,
+                       numerical_fix: bool) -> None:
+        """ae_cfg_inv_step over loop positions pos0..pos0+count-1 (see include/aedit.h).  eps_u: [count, ...],
+        eps_c: [count*P, ...] (j-major), cfg_map: [P, ...]; xts / zs are updated in place."""
+        tab = self.sched_table
+        n_el = xts[0].numel()
+        _lib.check(tab.lib.ae_cfg_inv_step(tab.h, pos0, count, float(eta), _ptr(eps_u), n_el,
+                                           _ptr(eps_c) if P > 0 else None, n_el, P, _ptr(cfg_map) if P > 0 else None,
+                                           _ptr(xt_src), _ptr(xts), _ptr(zs), int(bool(numerical_fix)), n_el,
+                                           _stream()), "ae_cfg_inv_step")
+
+    def k_cfg_rev_step(self, pos: int, eta: float, eps_u, eps_c, P: int, cfg_map, xt, z, out, masks=None,
+                       fix_alpha=None, xT_fix=None, d_pos=None) -> None:
+        """ae_cfg_rev_step at loop position pos (or *d_pos on device)."""
+        tab = self.sched_table
+        fix_h = None
+        if fix_alpha is not None:
+            fix_h = (C.c_float * 8)(*([float(v) for v in fix_alpha] + [0.0] * (8 - len(fix_alpha))))
+        _lib.check(tab.lib.ae_cfg_rev_step(tab.h, pos, _ptr(d_pos), float(eta), _ptr(eps_u),
+                                           _ptr(eps_c) if P > 0 else None, P, _ptr(cfg_map) if P > 0 else None,
+                                           _ptr(xt), _ptr(z), _ptr(out), _ptr(masks) if fix_h is not None else None,
+                                           C.cast(fix_h, C.c_void_p) if fix_h is not None else None,
+                                           _ptr(xT_fix) if fix_h is not None else None, xt.numel(), _stream()),
+                   "ae_cfg_rev_step")
+
     # ---------------------------------------------------------------- a7/a8: models.py:160-393, :691-899
     def _text_for(self, encoder_hidden_states, class_labels, encoder_attention_mask):
         """Maps the reference's (encoder_hidden_states, class_labels, encoder_attention_mask) triple onto the
@@ -316,9 +342,6 @@ class AudioLDMWrapper(PipelineWrapper):
         return [], [], class_labels
 
     def encode_text(self, prompts: List[str], **kwargs) -> Tuple[None, Optional[torch.Tensor], None]:
-        enc = self._ends().clap_text_encoder()
-        if enc is not None:
-            return None, enc(prompts), None
         return None, self._synthetic_text(prompts, 512, None, True, 0)[:, 0], None
 
 

@@ -39,6 +39,40 @@ class TextCache:
         self.lens: List[int] = []
 
 
+class GraphedForward:
+    """One U-Net evaluation of a fixed (B, H, W, text, slots) captured as a CUDA graph: ~10^3 kernel launches
+    (and their TMA descriptors, encoded once at capture) replay with a single host call — the launch-latency
+    answer SURVEY.md §7 'hard parts' asks for.  Inputs / output live in static buffers."""
+
+    def __init__(self, engine: "UNetEngine", B, H, W, text, slot_map, class_labels):
+        dev = engine.device
+        self.x = torch.zeros(B, engine.cfg.in_channels, H, W, device=dev, dtype=F32)
+        self.t = torch.zeros(B, device=dev, dtype=torch.int64)
+        self.slot = None if slot_map is None else slot_map.to(dev, torch.int32).clone()
+        self.cl = None if class_labels is None else class_labels.to(dev, F32).clone()
+        self.text = text
+        cur = torch.cuda.current_stream()
+        side = torch.cuda.Stream()
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            for _ in range(2):          # warm-up outside capture: workspaces, smem attributes, lazy allocations
+                engine.forward(self.x, self.t, text=text, slot_map=self.slot, class_labels=self.cl)
+        cur.wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.out = engine.forward(self.x, self.t, text=text, slot_map=self.slot, class_labels=self.cl)
+        self.launches = 0
+
+    def __call__(self, x, t, class_labels=None):
+        self.x.copy_(x)
+        self.t.copy_(t)
+        if class_labels is not None and self.cl is not None:
+            self.cl.copy_(class_labels)
+        self.graph.replay()
+        return self.out
+
+
 class UNetEngine:
     def __init__(self, cfg: UNetConfig, weights: Dict[str, torch.Tensor], device, ops=None):
         if ops is None:
@@ -50,6 +84,22 @@ class UNetEngine:
         self.adt = ops.act_dtype            # bf16 on the device path
         self.w: Dict[str, torch.Tensor] = {}
         self._pack(weights)
+        self._graphs: Dict = {}
+        self.kernels_per_forward: Dict = {}
+
+    def graphed(self, B, H, W, text=None, slot_map=None, class_labels=None, slot_key=None) -> GraphedForward:
+        """Cached CUDA-graph evaluator for this geometry / text binding.  `slot_key`: hashable description of
+        slot_map known on the host (avoids a device read-back per call)."""
+        if slot_key is None and slot_map is not None:
+            slot_key = tuple(int(v) for v in slot_map.tolist())
+        key = (B, H, W, id(text), slot_key, class_labels is not None)
+        g = self._graphs.get(key)
+        if g is None:
+            l0 = self.ops.launch_count()
+            g = GraphedForward(self, B, H, W, text, slot_map, class_labels)
+            g.kernels = (self.ops.launch_count() - l0) // 3       # 2 warm-ups + 1 capture
+            self._graphs[key] = g
+        return g
 
     # ------------------------------------------------------------------------------------------ weights
     def _to(self, t, dtype):

@@ -1,0 +1,364 @@
+#!/usr/bin/env python
+"""Benchmark of the DDPM-inversion / CFG-denoising hot path (BASELINE.json metric: denoising-steps/sec).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config NAME]
+
+One bench "step" = one complete edit job of one clip on each GPU: `n_inv` inversion steps + `tstart` edit steps
+(default BASELINE configs[1]: AudioLDM2-large architecture, 10 s clip -> latent [1,8,256,16], 200-step inversion +
+tstart=100 edit, cfg 3 / 12, one source and one target prompt, synthetic seeded weights / text embeddings).
+1 denoising step = one classifier-free-guided step = 2 U-Net evaluations + CFG combine + scheduler update
+(BASELINE.md §3).  value = denoising steps of ALL ranks / max-over-ranks device time.
+
+Keys (see the task contract): value = inputs resident in HBM; e2e = same job through the public wrapper API with
+the clip latent in pinned host memory (H2D inside the timed region, edited latent read back D2H); roofline = the
+dominant kernel family (tcgen05 GEMM / implicit conv) FLOP rate from a live CUDA-event pass; cpu_baseline = the
+oracle port (oracle/unet_torch.py + oracle/ddpm_oracle.py, fp32 torch on the host cores) on a bounded sample.
+--impl reference times that oracle port alone (the reference's own diffusers pipeline cannot travel to the GPU box:
+no diffusers, no weights, no network — DESIGN.md §oracle).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+CONFIGS = {
+    # BASELINE.json configs[1]
+    "audioldm2-large-10s": dict(preset="audioldm2-large", model_id="cvssp/audioldm2-large", H=256, W=16, n_inv=200,
+                                tstart=100, cfg_src=3.0, cfg_tar=12.0, text_lens=(8, 16)),
+    # BASELINE.json configs[0] geometry (the reference's CPU-runnable case) — parity-test sized
+    "audioldm-s-5s": dict(preset="audioldm-s", model_id="cvssp/audioldm-s-full-v2", H=128, W=16, n_inv=50, tstart=50,
+                          cfg_src=1.0, cfg_tar=3.0, text_lens=()),
+    "tiny": dict(preset="tiny-audioldm2", model_id="synthetic/audioldm2-tiny", H=32, W=16, n_inv=20, tstart=10,
+                 cfg_src=3.0, cfg_tar=12.0, text_lens=(8, 16)),
+}
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as fh:
+            j = json.load(fh)
+        return dict(hbm_gbs=j.get("hbm_gbs"), tflops=j.get("bf16_tflops_sustained") or j.get("bf16_tflops"),
+                    source="measured (MEASURED_PEAKS.json, sustained bf16)")
+    return dict(hbm_gbs=6650.0, tflops=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clock / throttle sampling DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.samples = []
+        self._stop = threading.Event()
+        self._t = None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.idx), f"--query-gpu={self.Q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                parts = [p.strip() for p in out.strip().split(",")]
+                if len(parts) >= 7:
+                    self.samples.append(parts)
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        sm, mx, reasons = [], 0.0, set()
+        for s in self.samples:
+            try:
+                sm.append(float(s[0]))
+                mx = max(mx, float(s[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------- ours
+def synth_text(cfg, lens, P, device, seed=4):
+    g = torch.Generator().manual_seed(seed)
+    dims = {s[1]: s[0] for s in cfg.transformer_specs if s is not None}
+    streams = [torch.randn(P, lens[i], dims[i], generator=g).to(device) for i in range(cfg.n_streams)]
+    return streams
+
+
+def build_model(spec, device):
+    from audioeditingcode_b200 import models, unet_config as C
+    cfg = C.preset(spec["preset"])
+    m = models.load_model(spec["model_id"], device, spec["n_inv"], config=cfg)
+    return m, cfg
+
+
+def run_job(m, spec, x0_dev, forward_batch):
+    from audioeditingcode_b200.ddm_inversion import inversion_utils as IU
+    N, ts = spec["n_inv"], spec["tstart"]
+    _, zs, xts, _ = IU.inversion_forward_process(m, x0_dev, etas=1.0, prompts=["a recording of a dog barking"],
+                                                 cfg_scales=[spec["cfg_src"]], num_inference_steps=N,
+                                                 numerical_fix=True, forward_batch=forward_batch)
+    w, _ = IU.inversion_reverse_process(m, xT=xts, tstart=torch.tensor([ts], dtype=torch.int), etas=1.0,
+                                        prompts=["a recording of a cat meowing"], neg_prompts=[""],
+                                        cfg_scales=[spec["cfg_tar"]], zs=zs[:ts])
+    return w
+
+
+def gemm_event_pass(m, spec, cfg):
+    """One CFG step (B=2) with CUDA events around every ae_gemm launch -> time share and FLOP rate of the dominant
+    kernel family.  Events are recorded on torch's current stream = the stream the kernels are launched on."""
+    ops = m.engine.ops
+    orig = ops.gemm
+    evs = []
+
+    def timed(*a, **k):
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        orig(*a, **k)
+        e.record()
+        evs.append((s, e))
+    dev = m.device
+    x = torch.randn(2, cfg.in_channels, spec["H"], spec["W"], device=dev)
+    t = torch.full((2,), 501, dtype=torch.int64, device=dev)
+    un = m.encode_text([""])
+    cd = m.encode_text(["a recording of a dog barking"])
+    from audioeditingcode_b200.ddm_inversion.inversion_utils import _cat_text
+    streams, masks, cl = _cat_text(m, un, cd)
+    text = m._cached_text(streams, masks) if streams else None
+    slot = torch.arange(2, dtype=torch.int32, device=dev)
+    for _ in range(2):
+        m.engine.forward(x, t, text=text, slot_map=slot if text is not None else None, class_labels=cl)
+    torch.cuda.synchronize()
+    ops.gemm = timed
+    s_all, e_all = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s_all.record()
+    m.engine.forward(x, t, text=text, slot_map=slot if text is not None else None, class_labels=cl)
+    e_all.record()
+    torch.cuda.synchronize()
+    ops.gemm = orig
+    gemm_ms = sum(s.elapsed_time(e) for s, e in evs)
+    return dict(gemm_ms=gemm_ms, eval_ms=s_all.elapsed_time(e_all), n_gemm=len(evs))
+
+
+def flops_per_eval(cfg, spec, B):
+    from audioeditingcode_b200.flops import count_flops
+    return count_flops(cfg, spec["H"], spec["W"], B, spec["text_lens"])
+
+
+def cpu_oracle_sample(spec, n_steps_sample, threads):
+    """Oracle port on the host cores: `n_steps_sample` CFG denoising steps (half inversion, half edit) of the same
+    workload, fp32 torch CPU.  Returns (steps/s, seconds)."""
+    from oracle import unet_torch as U
+    from oracle import ddpm_oracle as D
+    from audioeditingcode_b200 import unet_config as C
+    torch.set_num_threads(threads)
+    cfg = C.preset(spec["preset"])
+    w = U.synthetic_weights(cfg, seed=0)
+    g = torch.Generator().manual_seed(1)
+    H, Wd = spec["H"], spec["W"]
+    x0 = 0.5 * torch.randn(1, cfg.in_channels, H, Wd, generator=g)
+    dims = {s[1]: s[0] for s in cfg.transformer_specs if s is not None}
+    lens = spec["text_lens"]
+    streams_u = [torch.randn(1, 1 if i == cfg.n_streams - 1 else lens[i], dims[i], generator=g) for i in range(cfg.n_streams)]
+    streams_c = [torch.randn(1, lens[i], dims[i], generator=g) for i in range(cfg.n_streams)]
+    yu = torch.nn.functional.normalize(torch.randn(1, 512, generator=g), dim=-1) if cfg.class_embed_dim else None
+    yc = torch.nn.functional.normalize(torch.randn(1, 512, generator=g), dim=-1) if cfg.class_embed_dim else None
+
+    def unet(x, t, which):
+        tt = torch.full((x.shape[0],), int(t), dtype=torch.int64)
+        st = streams_u if which == "uncond" else streams_c
+        with torch.no_grad():
+            return U.unet_forward(cfg, w, x, tt, streams=st, stream_masks=[None] * len(st),
+                                  class_labels=(yu if which == "uncond" else yc))[0]
+    sched = D.MiniDDIM(cfg.beta_start, cfg.beta_end, prediction_type=cfg.prediction_type)
+    sched.set_timesteps(spec["n_inv"])
+    N = spec["n_inv"]
+    noise = torch.randn(N, *x0.shape[1:], generator=g)
+    xts = D.sample_xts_from_x0(sched, x0, noise)
+    cfgm, _ = D.build_cfg_maps(1, x0.shape[1:], [spec["cfg_src"]], None)
+
+    def one_step(pos):
+        t = int(sched.timesteps[pos])
+        idx = N - pos - 1
+        xt = xts[idx + 1][None]
+        eps = D.cfg_combine(unet(xt, t, "uncond"), unet(xt, t, "cond"), cfgm)
+        if pos % 2 == 0:
+            D.get_zs_from_xts(sched, xt, xts[idx][None], eps, t, 1.0, True)
+        else:
+            D.reverse_step_with_custom_noise(sched, eps, t, xt, noise[idx][None], 1.0)
+    one_step(0)  # warm-up
+    t0 = time.perf_counter()
+    for k in range(n_steps_sample):
+        one_step(1 + k)
+    dt = time.perf_counter() - t0
+    return n_steps_sample / dt, dt
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="audioldm2-large-10s", choices=sorted(CONFIGS))
+    ap.add_argument("--forward-batch", type=int, default=int(os.environ.get("AEDIT_FORWARD_BATCH", "8")))
+    ap.add_argument("--cpu-steps", type=int, default=0, help="CFG steps of the cpu_baseline sample (0 = auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    spec = CONFIGS[args.config]
+    steps_per_job = spec["n_inv"] + spec["tstart"]
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    cores = os.cpu_count() or 1
+
+    # ------------------------------------------------------------------------------ reference arm (CPU oracle port)
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        n_sample = args.cpu_steps or 2
+        vals = []
+        for i in range(args.warmup + args.steps):
+            v, dt = cpu_oracle_sample(spec, n_sample, cores)
+            if i >= args.warmup:
+                vals.append((v, dt))
+        tot_steps = n_sample * len(vals)
+        tot_t = sum(dt for _, dt in vals)
+        value = tot_steps / tot_t
+        line = {"metric": "denoising-steps/sec", "value": value, "unit": "steps/s", "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * tot_t / max(1, len(vals)),
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+                "impl": "reference",
+                "config": {"workload": args.config, "arch": spec["preset"], "latent": [1, 8, spec["H"], spec["W"]],
+                           "n_inv": spec["n_inv"], "tstart": spec["tstart"]},
+                "cpu_baseline": {"value": value, "unit": "steps/s", "cores": cores, "kind": "port",
+                                 "sample": f"{n_sample} CFG denoising steps (2 U-Net evals each, fp32 torch CPU oracle port) "
+                                           f"per bench step of the {args.config} workload"},
+                "e2e": {"value": value, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    # ------------------------------------------------------------------------------ our arm
+    assert torch.cuda.is_available(), "bench.py --impl ours needs a GPU (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    m, cfg = build_model(spec, dev)
+    ops = m.engine.ops
+    g = torch.Generator().manual_seed(1 + rank)
+    x0_host = (0.5 * torch.randn(1, cfg.in_channels, spec["H"], spec["W"], generator=g)).pin_memory()
+    x0_dev = x0_host.to(dev)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > L2 (126 MB)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed_loop(fn, K):
+        barrier()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(K):
+            flush.zero_()
+            fn()
+        e.record()
+        barrier()
+        ms = s.elapsed_time(e)
+        if dist is not None:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    def job_resident():
+        run_job(m, spec, x0_dev, args.forward_batch)
+
+    e2e_out = torch.empty(1, cfg.in_channels, spec["H"], spec["W"]).pin_memory()
+
+    def job_e2e():
+        x = x0_host.to(dev, non_blocking=True)
+        w = run_job(m, spec, x, args.forward_batch)
+        e2e_out.copy_(w, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    for _ in range(max(3, args.warmup)):
+        job_resident()
+    with ClockSampler(local_rank) as cs:
+        l0 = ops.launch_count() + getattr(m, "graph_kernels", 0)
+        ms = timed_loop(job_resident, args.steps)
+        launches = ops.launch_count() + getattr(m, "graph_kernels", 0) - l0   # eager launches + kernels replayed in graphs
+    clocks = cs.summary()
+    ms_e2e = timed_loop(job_e2e, args.steps)
+    total_steps = steps_per_job * args.steps * world
+    value = total_steps / (ms / 1000.0)
+    e2e_value = total_steps / (ms_e2e / 1000.0)
+
+    line = {"metric": "denoising-steps/sec", "value": value, "unit": "steps/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": args.config, "arch": spec["preset"], "weights": m.weights_source,
+                       "latent": [1, 8, spec["H"], spec["W"]], "n_inv": spec["n_inv"], "tstart": spec["tstart"],
+                       "denoising_steps_per_bench_step": steps_per_job, "forward_batch_timesteps": args.forward_batch,
+                       "parallelism": f"clip-dp{world}", "l2": "256 MiB flush between jobs; weights (1.5 GB) >> L2"},
+            "e2e": {"value": e2e_value, "unit": "steps/s", "h2d_bytes_per_step": x0_host.numel() * 4,
+                    "d2h_bytes_per_step": e2e_out.numel() * 4},
+            "gpu_launches": int(launches), "clocks": clocks}
+
+    if rank == 0:
+        peaks = load_peaks()
+        fl2 = flops_per_eval(cfg, spec, 2)
+        gp = gemm_event_pass(m, spec, cfg)
+        gemm_flops = fl2["conv"] + fl2["linear"]
+        achieved = gemm_flops / (gp["gemm_ms"] / 1000.0) / 1e12
+        # whole-job FLOPs: forward batches B = 2*forward_batch per launch, reverse B = 2
+        job_flops = (spec["n_inv"] + spec["tstart"]) * fl2["total"]
+        line["roofline"] = {"bound": "tensor", "kernel": "gemm_tcgen05_kernel (conv3x3 / conv1x1 / linear)",
+                            "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s",
+                            "frac": achieved / peaks["tflops"], "traffic": None, "peak_source": peaks["source"],
+                            "flops_per_launch_set": gemm_flops, "launches_per_eval": gp["n_gemm"],
+                            "gemm_share_of_eval_time": gp["gemm_ms"] / gp["eval_ms"],
+                            "job_tflops": job_flops * args.steps / (ms / 1000.0) / 1e12 / 1.0}
+        if not args.no_cpu_baseline and world == 1:
+            n_sample = args.cpu_steps or 2
+            v, dt = cpu_oracle_sample(spec, n_sample, cores)
+            line["cpu_baseline"] = {"value": v, "unit": "steps/s", "cores": cores, "kind": "port",
+                                    "sample": f"{n_sample} CFG denoising steps of the same workload on the fp32 torch CPU "
+                                              f"oracle port ({dt:.1f} s)"}
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -73,6 +73,16 @@ def make_fake_wrapper(ref, cfg, weights, n_steps, prediction_type="epsilon"):
                 unet=types.SimpleNamespace(config=types.SimpleNamespace(in_channels=cfg.in_channels)),
                 scheduler=sched)
             self.calls = 0
+            self.rec_fwd, self.rec_rev, self.rec_unet = [], [], []
+
+        # record the noise predictions the reference hands to its scheduler math, then run that math unmodified
+        def get_zs_from_xts(self, xt, xtm1, noise_pred, t, **kw):
+            self.rec_fwd.append(noise_pred.clone())
+            return super().get_zs_from_xts(xt, xtm1, noise_pred, t, **kw)
+
+        def reverse_step_with_custom_noise(self, model_output, timestep, sample, **kw):
+            self.rec_rev.append(model_output.clone())
+            return super().reverse_step_with_custom_noise(model_output, timestep, sample, **kw)
 
         def encode_text(self, prompts, **kw):
             return None, torch.cat([prompt_vector(p) for p in prompts], 0), None
@@ -83,6 +93,7 @@ def make_fake_wrapper(ref, cfg, weights, n_steps, prediction_type="epsilon"):
             t = t.reshape(-1).expand(sample.shape[0])
             with torch.no_grad():
                 out = unet(sample, t, y=class_labels)
+            self.rec_unet.append(out.clone())
             return ref_import.UNet2DConditionOutput(sample=out), None, None
 
     return Fake()
@@ -100,13 +111,18 @@ def run_loops(ref, cfg, weights, n_steps, H, W, src, tgt, cfg_src, cfg_tar, tsta
         xt, zs, xts, _ = ref.inversion_utils.inversion_forward_process(
             model, x0, etas=1.0, prompts=list(src), cfg_scales=list(cfg_src), num_inference_steps=n_steps,
             numerical_fix=True, cutoff_points=cutoff)
-        raw_xts = xts.clone()
+        unet_fwd = model.rec_unet
+        model.rec_unet = []
         ts = torch.tensor(tstart, dtype=torch.int)
         skip = n_steps - ts
         w_edit, _ = ref.inversion_utils.inversion_reverse_process(
             model, xT=xts, tstart=ts, etas=1.0, prompts=list(tgt), neg_prompts=[""], cfg_scales=list(cfg_tar),
             zs=zs[:int(n_steps - min(skip))], cutoff_points=cutoff)
     return dict(x0=x0, noise=noise, zs=zs, xts=xts, w_edit=w_edit,
+                eps_fwd=torch.cat(model.rec_fwd), eps_rev=torch.cat(model.rec_rev),
+                # raw U-Net outputs of every step in loop order: [uncond (1 row), cond (P rows)] alternating
+                eps_u_fwd=torch.cat(unet_fwd[0::2]), eps_c_fwd=torch.stack(unet_fwd[1::2]),
+                eps_u_rev=torch.cat(model.rec_unet[0::2]), eps_c_rev=torch.stack(model.rec_unet[1::2]),
                 uncond=prompt_vector(""), src=torch.cat([prompt_vector(p) for p in src]),
                 tgt=torch.cat([prompt_vector(p) for p in tgt]))
 

