@@ -114,6 +114,27 @@ def _cat_text(model: PipelineWrapper, uncond, cond):
     return streams, masks, cl
 
 
+def _loop_text(model: PipelineWrapper, neg_prompts, prompts):
+    """Text conditioning of one loop call: (TextCache or None, class-label rows or None) for the rows
+    [uncond, cond_1..cond_P].  Cached per prompt strings — the text encoders are deterministic, so re-encoding the
+    same prompts for every call (as the reference does) would only rebuild identical K/V tensors (and force the
+    CUDA graphs bound to them to be re-captured)."""
+    enc = model.encode_text
+    key = (tuple(neg_prompts), None if prompts is None else tuple(prompts), id(getattr(enc, "__self__", enc)))
+    cache = model.__dict__.setdefault("_loop_text_cache", {})
+    hit = cache.get(key)
+    if hit is None:
+        if len(cache) > 8:
+            cache.clear()
+        uncond = model.encode_text(list(neg_prompts), negative=True)
+        cond = None if prompts is None else model.encode_text(list(prompts))
+        streams, masks, cl = _cat_text(model, uncond, cond)
+        text = model.engine.prepare_text(streams, masks) if streams else None
+        hit = (text, cl, (streams, masks))
+        cache[key] = hit
+    return hit[0], hit[1]
+
+
 def _t_to_idx(timesteps):
     if timesteps[0].dtype == torch.int64:
         return {int(v): k for k, v in enumerate(timesteps)}
@@ -143,12 +164,10 @@ def inversion_forward_process(model: PipelineWrapper,
 
     have_cond = len(prompts) > 1 or prompts[0] != ""
     P = len(prompts) if have_cond else 0
-    cond = None
     cfg_map = None
     if have_cond:
-        cond = model.encode_text(prompts)
         cfg_map, _ = _build_cfg_maps(P, x0.shape[1:], cfg_scales, cutoff_points, model.device, x0.dtype, prompts)
-    uncond = model.encode_text([""], negative=True)
+    text, cl = _loop_text(model, [""], prompts if have_cond else None)
     sched = model.model.scheduler
     timesteps = sched.timesteps.to(model.device)
     N = num_inference_steps
@@ -161,11 +180,7 @@ def inversion_forward_process(model: PipelineWrapper,
 
     tb = forward_batch if forward_batch is not None else DEFAULT_FORWARD_BATCH
     tb = max(1, min(int(tb), N))
-    streams, masks, cl = _cat_text(model, uncond, cond)
-    text = model._cached_text(streams, masks) if streams else None
-    tab = model.sched_table
     n_el = x0[0].numel()
-    rows = 1 + P
     xt_src = xts.clone() if tb > 1 else xts      # batched: every U-Net input is the directly sampled x_t (F8)
     ts_cpu = sched.timesteps_cpu
     eta0 = float(etas[0])
@@ -228,8 +243,7 @@ def inversion_reverse_process(model: PipelineWrapper,
                                 cutoff_points, hspace_add, hspace_replace, skipconns_replace, zero_out_resconns,
                                 extract_h_space, extract_skipconns, duration, first_order, extra_info)
     P = len(prompts)
-    cond = model.encode_text(prompts)
-    uncond = model.encode_text(neg_prompts, negative=True)
+    text, cl = _loop_text(model, neg_prompts, prompts)
     cfg_map, masks = _build_cfg_maps(P, xT.shape[1:], cfg_scales, cutoff_points, model.device, xT.dtype, masks_too=True)
     sched = model.model.scheduler
     N = sched.num_inference_steps
@@ -242,10 +256,6 @@ def inversion_reverse_process(model: PipelineWrapper,
     n = zs.shape[0]
     ts_cpu = sched.timesteps_cpu[-n:]
     model.setup_extra_inputs(xt, extra_info=extra_info, init_timestep=ts_cpu[0], audio_end_in_s=duration)
-    streams, masks_t, cl = _cat_text(model, uncond, cond)
-    text = model._cached_text(streams, masks_t) if streams else None
-    tab = model.sched_table
-    n_el = xt.numel()
     rows = 1 + P
     slot = torch.arange(rows, dtype=torch.int32, device=model.device)
     zs = zs.contiguous()

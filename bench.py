@@ -147,11 +147,8 @@ def gemm_event_pass(m, spec, cfg):
     dev = m.device
     x = torch.randn(2, cfg.in_channels, spec["H"], spec["W"], device=dev)
     t = torch.full((2,), 501, dtype=torch.int64, device=dev)
-    un = m.encode_text([""])
-    cd = m.encode_text(["a recording of a dog barking"])
-    from audioeditingcode_b200.ddm_inversion.inversion_utils import _cat_text
-    streams, masks, cl = _cat_text(m, un, cd)
-    text = m._cached_text(streams, masks) if streams else None
+    from audioeditingcode_b200.ddm_inversion.inversion_utils import _loop_text
+    text, cl = _loop_text(m, [""], ["a recording of a dog barking"])
     slot = torch.arange(2, dtype=torch.int32, device=dev)
     for _ in range(2):
         m.engine.forward(x, t, text=text, slot_map=slot if text is not None else None, class_labels=cl)
