@@ -35,6 +35,8 @@ _SIGS = {
     "ae_launch_count": (i64, []),
     "ae_device_ok": (i32, []),
     "ae_sched_create": (i32, [vp, i32, f32, vp, i32, i32, C.POINTER(vp)]),
+    "ae_sched_create_from_rows": (i32, [C.POINTER(AeSchedRow), i32, i32, i32, C.POINTER(vp)]),
+    "ae_sched_set_eta": (i32, [vp, vp, vp]),
     "ae_sched_destroy": (None, [vp]),
     "ae_sched_num_steps": (i32, [vp]),
     "ae_sched_row_h": (i32, [vp, i32, C.POINTER(AeSchedRow)]),

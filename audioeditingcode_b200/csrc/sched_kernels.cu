@@ -23,6 +23,8 @@ struct ae_sched {
   std::vector<ae_sched_row> rows;
   std::unordered_map<long long, int> pos_of_t;
   ae_sched_row* d_rows = nullptr;
+  float* d_eta = nullptr;  // [2*N]: c_dir[pos], sig[pos] supplied by the host (ae_sched_set_eta), or null
+  bool has_eta = false;
 };
 
 using namespace aedit;
@@ -86,9 +88,53 @@ extern "C" int ae_sched_create(const float* ac, int T, float final_alpha, const 
   *out = s;
   return AE_OK;
 }
+extern "C" int ae_sched_create_from_rows(const ae_sched_row* rows_h, int N, int pred_type, int num_train_timesteps,
+                                         ae_sched** out) {
+  AE_CHECK_ARG(rows_h && out && N > 0, "ae_sched_create_from_rows: null/empty argument");
+  AE_CHECK_ARG(pred_type == 0 || pred_type == 1, "ae_sched_create_from_rows: bad pred_type");
+  ae_sched* s = new ae_sched();
+  s->N = N;
+  s->pred_type = pred_type;
+  s->num_train = num_train_timesteps;
+  s->rows.assign(rows_h, rows_h + N);
+  for (int k = 0; k < N; ++k) s->pos_of_t[rows_h[k].t] = k;
+  cudaError_t e = cudaMalloc(&s->d_rows, sizeof(ae_sched_row) * N);
+  if (e == cudaSuccess) e = cudaMemcpy(s->d_rows, s->rows.data(), sizeof(ae_sched_row) * N, cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    s->d_rows = nullptr;
+  }
+  *out = s;
+  return AE_OK;
+}
+
+extern "C" int ae_sched_set_eta(ae_sched* s, const float* c_dir_h, const float* sig_h) {
+  AE_CHECK_ARG(s, "ae_sched_set_eta: null scheduler");
+  if (!c_dir_h || !sig_h) {
+    s->has_eta = false;
+    return AE_OK;
+  }
+  if (!s->d_rows) return AE_OK;  // host-only table (no GPU)
+  if (!s->d_eta) {
+    cudaError_t e = cudaMalloc(&s->d_eta, sizeof(float) * 2 * s->N);
+    if (e != cudaSuccess) return fail(AE_ECUDA, "ae_sched_set_eta: %s", cudaGetErrorString(e));
+  }
+  std::vector<float> tmp(2 * s->N);
+  for (int k = 0; k < s->N; ++k) {
+    tmp[k] = c_dir_h[k];
+    tmp[s->N + k] = sig_h[k];
+  }
+  // synchronous copy: the table may be replaced between runs while kernels of the previous run are in flight
+  cudaError_t e = cudaMemcpy(s->d_eta, tmp.data(), sizeof(float) * 2 * s->N, cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) return fail(AE_ECUDA, "ae_sched_set_eta: %s", cudaGetErrorString(e));
+  s->has_eta = true;
+  return AE_OK;
+}
+
 extern "C" void ae_sched_destroy(ae_sched* s) {
   if (!s) return;
   if (s->d_rows) cudaFree(s->d_rows);
+  if (s->d_eta) cudaFree(s->d_eta);
   delete s;
 }
 extern "C" int ae_sched_num_steps(const ae_sched* s) { return s ? s->N : 0; }
@@ -148,6 +194,7 @@ __global__ void sample_xts_kernel(const ae_sched_row* __restrict__ rows, int N, 
 }
 
 struct InvArgs {
+  const float* eta_tab;  // [2N] c_dir | sig, or null (computed in-kernel with IEEE ops)
   const ae_sched_row* rows;
   int N, pos0, pred_type, P, numerical_fix;
   float eta;
@@ -167,8 +214,8 @@ __global__ void cfg_inv_step_kernel(InvArgs a) {
   const int pos = a.pos0 + j;
   const int idx = a.N - pos - 1;  // inversion_utils.py:75
   const ae_sched_row r = a.rows[pos];
-  const float c_dir = dir_coeff(r, a.eta);
-  const float sig = __fmul_rn(a.eta, r.sqrt_var);
+  const float c_dir = a.eta_tab ? a.eta_tab[pos] : dir_coeff(r, a.eta);
+  const float sig = a.eta_tab ? a.eta_tab[a.N + pos] : __fmul_rn(a.eta, r.sqrt_var);
   const float* eu = a.eps_u + (int64_t)j * a.ld_eps_u;
   const float* xt_p = a.xt_src + (int64_t)(idx + 1) * a.n_el;
   float* xtm1_p = a.xts + (int64_t)idx * a.n_el;
@@ -194,6 +241,8 @@ __global__ void cfg_inv_step_kernel(InvArgs a) {
 }
 
 struct RevArgs {
+  const float* eta_tab;
+  int N;
   const ae_sched_row* rows;
   int pos;
   const int32_t* d_pos;
@@ -215,8 +264,8 @@ struct RevArgs {
 __global__ void cfg_rev_step_kernel(RevArgs a) {
   const int pos = a.d_pos ? *a.d_pos : a.pos;
   const ae_sched_row r = a.rows[pos];
-  const float c_dir = dir_coeff(r, a.eta);
-  const float sig = __fmul_rn(a.eta, r.sqrt_var);
+  const float c_dir = a.eta_tab ? a.eta_tab[pos] : dir_coeff(r, a.eta);
+  const float sig = a.eta_tab ? a.eta_tab[a.N + pos] : __fmul_rn(a.eta, r.sqrt_var);
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n_el; i += (int64_t)gridDim.x * blockDim.x) {
     const float u = a.eps_u[i];
     float eps = u;
@@ -300,7 +349,7 @@ extern "C" int ae_cfg_inv_step(const ae_sched* s, int pos0, int count, float eta
   AE_CHECK_ARG(eps_u && xt_src && xts && zs && n_el > 0, "ae_cfg_inv_step: null pointer");
   AE_CHECK_ARG(P >= 0 && P <= kMaxP && (P == 0 || (eps_c && cfg_map)), "ae_cfg_inv_step: bad P=%d", P);
   AE_CHECK_ARG(eta > 0.0f, "ae_cfg_inv_step: eta must be > 0 (z is divided by eta*sqrt(var))");
-  InvArgs a{s->d_rows, s->N, pos0, s->pred_type, P, numerical_fix, eta, eps_u, ld_eps_u, eps_c, ld_eps_c,
+  InvArgs a{s->has_eta ? s->d_eta : nullptr, s->d_rows, s->N, pos0, s->pred_type, P, numerical_fix, eta, eps_u, ld_eps_u, eps_c, ld_eps_c,
             cfg_map, xt_src, xts, zs, n_el};
   dim3 grid(grid_for(n_el, 256, count), count);
   cfg_inv_step_kernel<<<grid, 256, 0, as_stream(stream)>>>(a);
@@ -317,6 +366,8 @@ extern "C" int ae_cfg_rev_step(const ae_sched* s, int pos, const int32_t* d_pos,
   AE_CHECK_ARG(P >= 0 && P <= kMaxP && (P == 0 || (eps_c && cfg_map)), "ae_cfg_rev_step: bad P=%d", P);
   AE_CHECK_ARG(eta == 0.0f || z, "ae_cfg_rev_step: eta > 0 needs the noise map z");
   RevArgs a;
+  a.eta_tab = s->has_eta ? s->d_eta : nullptr;
+  a.N = s->N;
   a.rows = s->d_rows;
   a.pos = pos;
   a.d_pos = d_pos;

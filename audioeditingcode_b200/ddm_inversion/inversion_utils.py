@@ -183,9 +183,7 @@ def inversion_forward_process(model: PipelineWrapper,
     n_el = x0[0].numel()
     xt_src = xts.clone() if tb > 1 else xts      # batched: every U-Net input is the directly sampled x_t (F8)
     ts_cpu = sched.timesteps_cpu
-    eta0 = float(etas[0])
-    if any(float(e) != eta0 for e in etas):
-        tb = 1
+    model.sched_table.set_etas(etas)
     it = range(0, N, tb)
     if prog_bar:
         it = tqdm(it)
@@ -257,6 +255,7 @@ def inversion_reverse_process(model: PipelineWrapper,
     ts_cpu = sched.timesteps_cpu[-n:]
     model.setup_extra_inputs(xt, extra_info=extra_info, init_timestep=ts_cpu[0], audio_end_in_s=duration)
     rows = 1 + P
+    model.sched_table.set_etas(etas)
     slot = torch.arange(rows, dtype=torch.int32, device=model.device)
     zs = zs.contiguous()
     tmax = int(tstart.max())

@@ -22,7 +22,7 @@ from typing import Any, Dict, List, Optional, Tuple, Union
 import torch
 
 from . import _lib
-from .scheduler import DDIMScheduler
+from .scheduler import DDIMScheduler, SchedTable
 from .unet import UNetEngine, TextCache
 from .unet_config import UNetConfig, from_model_id
 from . import weights as W
@@ -41,40 +41,6 @@ def _ptr(t: Optional[torch.Tensor]):
 
 def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
-
-
-class SchedTable:
-    """libaedit scheduler table bound to a DDIMScheduler state (rebuilt when set_timesteps changes)."""
-
-    def __init__(self, scheduler: DDIMScheduler):
-        lib = _lib.load()
-        self.lib = lib
-        ac = scheduler.alphas_cumprod.contiguous()
-        ts = scheduler.timesteps_cpu.contiguous()
-        h = C.c_void_p()
-        pred = {"epsilon": 0, "v_prediction": 1}[scheduler.config.prediction_type]
-        _lib.check(lib.ae_sched_create(C.c_void_p(ac.data_ptr()), ac.numel(), float(scheduler.final_alpha_cumprod),
-                                       C.c_void_p(ts.data_ptr()), ts.numel(), pred, C.byref(h)), "ae_sched_create")
-        self.h = h
-        self.N = ts.numel()
-        self._keep = (ac, ts)
-
-    def pos_of_t(self, t: int) -> int:
-        pos = self.lib.ae_sched_pos_of_t(self.h, int(t))
-        if pos < 0:
-            raise KeyError(f"timestep {int(t)} is not in the scheduler's timesteps")   # dict KeyError in the reference
-        return pos
-
-    def row(self, pos: int) -> _lib.AeSchedRow:
-        r = _lib.AeSchedRow()
-        _lib.check(self.lib.ae_sched_row_h(self.h, pos, C.byref(r)), "ae_sched_row_h")
-        return r
-
-    def __del__(self):
-        try:
-            self.lib.ae_sched_destroy(self.h)
-        except Exception:
-            pass
 
 
 class PipelineWrapper(torch.nn.Module):
@@ -119,10 +85,7 @@ class PipelineWrapper(torch.nn.Module):
     # ---------------------------------------------------------------- scheduler plumbing
     @property
     def sched_table(self) -> SchedTable:
-        s = self.model.scheduler
-        if s._table is None:
-            s._table = SchedTable(s)
-        return s._table
+        return self.model.scheduler.table
 
     def get_sigma(self, timestep: int) -> float:                      # models.py:25-27
         sqrt_recipm1_alphas_cumprod = torch.sqrt(1.0 / self.model.scheduler.alphas_cumprod - 1)
@@ -181,6 +144,7 @@ class PipelineWrapper(torch.nn.Module):
                         ) -> Tuple[torch.Tensor, torch.Tensor, Optional[torch.Tensor]]:
         tab = self.sched_table
         pos = tab.pos_of_t(int(t))
+        tab.set_etas([eta] * tab.N)
         n_el = xt.numel()
         # the kernel addresses xt as xt_src[idx+1] and xtm1 as xts[idx]: hand it 2-row scratch views
         idx = tab.N - pos - 1
@@ -202,6 +166,7 @@ class PipelineWrapper(torch.nn.Module):
                                        ) -> torch.Tensor:
         tab = self.sched_table
         pos = tab.pos_of_t(int(timestep))
+        tab.set_etas([eta] * tab.N)
         if eta > 0 and variance_noise is None:
             variance_noise = torch.randn(model_output.shape, device=self.device)          # models.py:153-154
         out = torch.empty_like(sample, dtype=torch.float32)

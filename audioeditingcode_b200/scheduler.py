@@ -10,10 +10,98 @@ runs in libaedit (ae_ddim_step).
 """
 from __future__ import annotations
 
+import ctypes as C
 import types
 from typing import Optional
 
 import torch
+
+from . import _lib
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class SchedTable:
+    """libaedit scheduler table bound to a DDIMScheduler state (rebuilt when set_timesteps changes).
+
+    The per-step scalars are computed HERE with the reference's own expressions on 0-dim fp32 CPU tensors
+    (code/models.py:89-111,126-150, :539-549) and handed to the library (ae_sched_create_from_rows /
+    ae_sched_set_eta): torch's CPU `**0.5` is not always the correctly rounded square root, and the reference
+    evaluates these scalars on the host even when the latents live on the GPU (alphas_cumprod stays on the CPU)."""
+
+    def __init__(self, scheduler: "DDIMScheduler"):
+        lib = _lib.load()
+        self.lib = lib
+        ac = scheduler.alphas_cumprod
+        ts = scheduler.timesteps_cpu
+        N = ts.numel()
+        step = scheduler.config.num_train_timesteps // N                       # models.py:96-97
+        rows = (_lib.AeSchedRow * N)()
+        self._ap, self._var = [], []
+        for k in range(N):
+            t = int(ts[k])
+            prev = t - step
+            ab = ac[t]
+            ap = ac[prev] if prev >= 0 else scheduler.final_alpha_cumprod      # models.py:547-549
+            var = ((1 - ap) / (1 - ab)) * (1 - ab / ap)                        # models.py:539-545
+            r = rows[k]
+            r.t, r.prev_t = t, prev
+            r.alpha_bar_t, r.alpha_prod_t_prev, r.variance = float(ab), float(ap), float(var)
+            r.sqrt_ab = float(ab ** 0.5)
+            r.sqrt_1mab = float((1 - ab) ** 0.5)
+            r.sqrt_ap = float(ap ** 0.5)
+            r.sqrt_var = float(var ** 0.5)
+            self._ap.append(ap)
+            self._var.append(var)
+        h = C.c_void_p()
+        pred = {"epsilon": 0, "v_prediction": 1}[scheduler.config.prediction_type]
+        _lib.check(lib.ae_sched_create_from_rows(rows, N, pred, scheduler.config.num_train_timesteps, C.byref(h)),
+                   "ae_sched_create_from_rows")
+        self.h = h
+        self.N = N
+        self._eta_key = None
+
+    def set_etas(self, etas) -> None:
+        """etas: list of length N indexed like the reference's `etas[idx]`, idx = N - pos - 1."""
+        key = tuple(float(e) for e in etas)
+        if key == self._eta_key:
+            return
+        N = self.N
+        cdir = (C.c_float * N)()
+        sig = (C.c_float * N)()
+        for pos in range(N):
+            eta = key[N - pos - 1]
+            ap, var = self._ap[pos], self._var[pos]
+            cdir[pos] = float((1 - ap - eta * var) ** 0.5)                      # models.py:107 / :148
+            sig[pos] = float(eta * var ** 0.5)                                   # models.py:111 / :155
+        _lib.check(self.lib.ae_sched_set_eta(self.h, C.cast(cdir, C.c_void_p), C.cast(sig, C.c_void_p)),
+                   "ae_sched_set_eta")
+        self._eta_key = key
+
+    def pos_of_t(self, t: int) -> int:
+        pos = self.lib.ae_sched_pos_of_t(self.h, int(t))
+        if pos < 0:
+            raise KeyError(f"timestep {int(t)} is not in the scheduler's timesteps")   # dict KeyError in the reference
+        return pos
+
+    def row(self, pos: int) -> _lib.AeSchedRow:
+        r = _lib.AeSchedRow()
+        _lib.check(self.lib.ae_sched_row_h(self.h, pos, C.byref(r)), "ae_sched_row_h")
+        return r
+
+    def __del__(self):
+        try:
+            self.lib.ae_sched_destroy(self.h)
+        except Exception:
+            pass
+
+
 
 
 class DDIMScheduler:
@@ -39,6 +127,29 @@ class DDIMScheduler:
         self.timesteps_cpu = ts
         self.timesteps = ts.to(device) if device is not None else ts
         self._table = None
+
+    @property
+    def table(self) -> SchedTable:
+        if self._table is None:
+            self._table = SchedTable(self)
+        return self._table
+
+    def step(self, model_output, timestep, sample, eta: float = 0.0, use_clipped_model_output: bool = False,
+             generator=None, variance_noise=None, return_dict: bool = True):
+        """[UPSTREAM] DDIMScheduler.step (std = eta*sqrt(var); direction uses std**2) on the device (ae_ddim_step).
+        Returns an object with .prev_sample and .pred_original_sample (what pc_drift.py:89-93 reads)."""
+        tab = self.table
+        pos = tab.pos_of_t(int(timestep))
+        mo = model_output.to(torch.float32).contiguous()
+        x = sample.to(torch.float32).contiguous()
+        if eta > 0 and variance_noise is None:
+            variance_noise = torch.randn(mo.shape, generator=generator, device=mo.device, dtype=mo.dtype)
+        vn = None if variance_noise is None else variance_noise.to(torch.float32).expand_as(mo).contiguous()
+        prev = torch.empty_like(x)
+        x0 = torch.empty_like(x)
+        _lib.check(tab.lib.ae_ddim_step(tab.h, pos, float(eta), 0.0, _ptr(mo), None, _ptr(x), _ptr(vn), _ptr(prev),
+                                        _ptr(x0), x.numel(), _stream()), "ae_ddim_step")
+        return types.SimpleNamespace(prev_sample=prev, pred_original_sample=x0)
 
     def scale_model_input(self, sample, timestep=None):
         return sample

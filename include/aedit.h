@@ -59,6 +59,13 @@ typedef struct {
 
 int ae_sched_create(const float* alphas_cumprod_h, int T, float final_alpha_cumprod, const int64_t* timesteps_h, int N,
                     int pred_type, ae_sched** out);
+/* Same table from rows computed by the caller.  The Python host computes the scalars with the SAME torch CPU ops the
+ * reference uses (torch's CPU `x ** 0.5` is not always the IEEE-rounded sqrtf ae_sched_create uses: 1 scalar in
+ * ~500 differs by an ulp), so that results stay bit-identical to the reference's. */
+int ae_sched_create_from_rows(const ae_sched_row* rows_h, int N, int pred_type, int num_train_timesteps, ae_sched** out);
+/* Optional per-position eta terms from the host (same motivation): c_dir[pos] = (1 - alpha_prod_t_prev - eta*var)**0.5
+ * and sig[pos] = eta*var**0.5 (models.py:107,111,155).  NULL pointers revert to in-kernel IEEE evaluation from `eta`. */
+int ae_sched_set_eta(ae_sched*, const float* c_dir_h, const float* sig_h);
 void ae_sched_destroy(ae_sched*);
 int ae_sched_num_steps(const ae_sched*);
 /* host copy of row `pos` (pos indexes `timesteps`) */

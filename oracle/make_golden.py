@@ -195,5 +195,33 @@ def main():
              alphas_cumprod=model.model.scheduler.alphas_cumprod)
 
 
+def synthetic_wave(n, seed=3):
+    """5 sines + noise, peak-normalised to 0.5 like tools.py:46-64 (SURVEY.md §8d synthetic audio)."""
+    g = torch.Generator().manual_seed(seed)
+    t = torch.arange(n, dtype=torch.float64) / 16000.0
+    freqs = [110.0, 440.0, 1250.0, 3100.0, 6400.0]
+    w = sum((0.6 ** i) * torch.sin(2 * np.pi * f * t + i) for i, f in enumerate(freqs))
+    w = w + 0.05 * torch.randn(n, generator=g, dtype=torch.float64)
+    w = w - w.mean()
+    w = 0.5 * w / w.abs().max()
+    return w.float()
+
+
+def golden_stft():
+    """Reference TacotronSTFT (audioldm/audio/stft.py, unmodified; librosa.filters.mel stubbed by the slaney
+    restatement in oracle/ref_import.py) on a synthetic clip."""
+    ref = ref_import.load()
+    fn = ref.stft.TacotronSTFT(1024, 160, 1024, 64, 16000, 0, 8000)
+    wav = synthetic_wave(16000 * 2 + 37)
+    with torch.no_grad():
+        mel, logmag, energy = fn.mel_spectrogram(wav[None])
+    save("stft_mel.npz", wav=wav, mel=mel[0], logmag=logmag[0], energy=energy[0], mel_basis=fn.mel_basis,
+         window=torch.from_numpy(np.asarray(__import__("scipy.signal").signal.get_window("hann", 1024, fftbins=True))).float())
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "stft":
+        golden_stft()
+    else:
+        main()
+        golden_stft()

@@ -52,6 +52,7 @@ def test_sched_kernels_bitexact_vs_reference(name, pred):
     xts_seq = xts.clone()
     zs2 = torch.zeros_like(zs)
     xts2 = xts.clone()
+    m.sched_table.set_etas([1.0] * N)
     for pos in range(N):                                   # step-sequential, one fused launch per step
         idx = N - pos - 1
         eu, ec = g["eps_u_fwd"][pos:pos + 1].cuda(), g["eps_c_fwd"][pos].cuda()
@@ -97,6 +98,7 @@ def test_sched_kernels_multi_prompt_vs_reference():
     cfg_map, _ = IU._build_cfg_maps(P, shape, [float(v) for v in g["cfg_src"]], None, dev, torch.float32, ["a", "b"])
     xts = m.sample_xts_from_x0(g["x0"].cuda(), N, noise=g["noise"].cuda())
     zs = torch.zeros(N, *shape, device=dev)
+    m.sched_table.set_etas([1.0] * N)
     for pos in range(N):
         m.k_cfg_inv_step(pos, 1, 1.0, g["eps_u_fwd"][pos:pos + 1].cuda(), g["eps_c_fwd"][pos].cuda(), P, cfg_map, xts,
                          xts, zs, True)

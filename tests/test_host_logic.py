@@ -1,0 +1,88 @@
+"""CPU-only tests of the host side: C-ABI surface, scheduler table (integer index math + fp32 scalars, bit-exact
+against the reference's own get_variance / get_alpha_prod_t_prev golden values), FLOP accounting, weight
+inventory, model-id dispatch."""
+import ctypes as C
+import os
+import re
+
+import pytest
+import torch
+
+from tests.helpers import load_golden
+from audioeditingcode_b200 import _lib, unet_config as UC, weights as W
+from audioeditingcode_b200.flops import count_flops
+from audioeditingcode_b200.scheduler import DDIMScheduler
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "aedit.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(ae_[a-z0-9_]+)\s*\(", hdr))
+    assert declared, "no declarations parsed"
+    lib = _lib.load()
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"libaedit.so does not export {name}"
+    assert declared == set(_lib.EXPORTS), (declared ^ set(_lib.EXPORTS))
+    assert lib.ae_version() >= 100
+
+
+@pytest.mark.parametrize("n", [50, 100, 200])
+def test_sched_table_bitexact_vs_reference_scalars(n):
+    g = load_golden(f"sched_{n}.npz")
+    s = DDIMScheduler()
+    s.set_timesteps(n)
+    assert torch.equal(s.timesteps, g["timesteps"])
+    assert torch.equal(s.alphas_cumprod, g["alphas_cumprod"])
+    tab = s.table
+    for pos in range(n):
+        r = tab.row(pos)
+        t = int(g["timesteps"][pos])
+        assert r.t == t and r.prev_t == t - 1000 // n                 # models.py:96-97 integer math
+        assert tab.pos_of_t(t) == pos                                 # t_to_idx, inversion_utils.py:68
+        assert r.variance == float(g["variance"][pos])               # models.py:539-545, fp32 op order
+        assert r.alpha_prod_t_prev == float(g["alpha_prod_t_prev"][pos])   # models.py:547-549 (final_alpha at prev<0)
+        ab = float(g["alphas_cumprod"][t])
+        assert r.alpha_bar_t == ab
+        assert r.sqrt_ab == float(torch.tensor(ab) ** 0.5)
+        assert r.sqrt_1mab == float((1 - torch.tensor(ab)) ** 0.5)
+        assert r.sqrt_var == float(torch.tensor(r.variance) ** 0.5)
+    assert tab.lib.ae_sched_pos_of_t(tab.h, 2) == -1
+    with pytest.raises(KeyError):
+        tab.pos_of_t(2)
+
+
+def test_flop_accounting_matches_survey():
+    f = count_flops(UC.preset("audioldm-s"), 256, 16, 1, ())
+    assert round(f["conv"] / 1e9, 1) == 64.2 and round(f["linear"] / 1e9, 1) == 27.3 and round(f["attn"] / 1e9, 1) == 11.9
+    assert round(f["total"] / 1e9, 1) == 103.4
+
+
+def test_weight_inventory_and_param_counts():
+    from oracle import unet_torch as U
+    for name, millions in [("audioldm-s", 185.0), ("audioldm-l", 739.1), ("audioldm2", 346.9), ("tango", 865.9)]:
+        cfg = UC.preset(name)
+        assert W.weight_shapes(cfg) == U.weight_shapes(cfg)
+        assert round(W.count_params(cfg) / 1e6, 1) == millions
+    cfg = UC.preset("tiny-audioldm2")
+    a, b = W.synthetic_weights(cfg, 0), U.synthetic_weights(cfg, 0)
+    assert a.keys() == b.keys() and all(torch.equal(a[k], b[k]) for k in a)
+
+
+def test_model_id_dispatch_and_errors():
+    assert UC.from_model_id("cvssp/audioldm-s-full-v2").name == "audioldm-s"
+    assert UC.from_model_id("cvssp/audioldm-l-full").name == "audioldm-l"
+    assert UC.from_model_id("cvssp/audioldm2-large").name == "audioldm2-large"
+    assert UC.from_model_id("cvssp/audioldm2-music").name == "audioldm2"
+    assert UC.from_model_id("declare-lab/tango-full-ft-audiocaps").prediction_type == "v_prediction"
+    with pytest.raises(ValueError):
+        UC.from_model_id("CompVis/stable-diffusion-v1-4")
+
+
+def test_conv_fast_path_geometry():
+    lib = _lib.load()
+    ok = lambda B, H, W_, C_: bool(lib.ae_gemm_conv_supported(B, H, W_, C_))
+    assert ok(2, 256, 16, 128) and ok(2, 128, 8, 256) and ok(2, 64, 4, 384) and ok(2, 32, 2, 640)   # AudioLDM-S levels
+    assert ok(1, 1, 1024, 64) and ok(1, 1024, 64, 128)                                             # vocoder / VAE
+    assert not ok(2, 256, 16, 8) and not ok(1, 141, 16, 128) and not ok(1, 20, 16, 128)
