@@ -118,13 +118,45 @@ def run_loops(ref, cfg, weights, n_steps, H, W, src, tgt, cfg_src, cfg_tar, tsta
         w_edit, _ = ref.inversion_utils.inversion_reverse_process(
             model, xT=xts, tstart=ts, etas=1.0, prompts=list(tgt), neg_prompts=[""], cfg_scales=list(cfg_tar),
             zs=zs[:int(n_steps - min(skip))], cutoff_points=cutoff)
-    return dict(x0=x0, noise=noise, zs=zs, xts=xts, w_edit=w_edit,
+    bf16_zs, bf16_edit = bf16_autocast_errors(cfg, weights, n_steps, pred, x0, noise, zs, xts, w_edit, src, tgt,
+                                              cfg_src, cfg_tar, tstart, cutoff)
+    return dict(x0=x0, noise=noise, zs=zs, xts=xts, w_edit=w_edit, bf16_autocast_err_zs=bf16_zs,
+                bf16_autocast_err_edit=bf16_edit,
                 eps_fwd=torch.cat(model.rec_fwd), eps_rev=torch.cat(model.rec_rev),
                 # raw U-Net outputs of every step in loop order: [uncond (1 row), cond (P rows)] alternating
                 eps_u_fwd=torch.cat(unet_fwd[0::2]), eps_c_fwd=torch.stack(unet_fwd[1::2]),
                 eps_u_rev=torch.cat(model.rec_unet[0::2]), eps_c_rev=torch.stack(model.rec_unet[1::2]),
                 uncond=prompt_vector(""), src=torch.cat([prompt_vector(p) for p in src]),
                 tgt=torch.cat([prompt_vector(p) for p in tgt]))
+
+
+def bf16_autocast_errors(cfg, weights, n_steps, pred, x0, noise, zs_ref, xts_ref, w_ref, src, tgt, cfg_src, cfg_tar,
+                         tstart, cutoff):
+    """Error level of STOCK PyTorch bf16 autocast on the same loops (oracle loop code, U-Net under
+    torch.autocast(bfloat16)) relative to the fp32 reference: the yardstick for the bf16 tensor-core path's
+    end-to-end tolerance (a bf16 path cannot be expected to beat it by much; ours keeps an fp32 residual stream)."""
+    from oracle import ddpm_oracle as D
+    sched = MiniDDIM(cfg.beta_start, cfg.beta_end, prediction_type=pred)
+    sched.set_timesteps(n_steps)
+    un = prompt_vector("")
+
+    def mk(prompts):
+        y_c = torch.cat([prompt_vector(p) for p in prompts])
+
+        def fn(x, t, which):
+            y = un if which == "uncond" else y_c
+            tt = torch.full((x.shape[0],), int(t), dtype=torch.int64)
+            with torch.no_grad(), torch.autocast("cpu", dtype=torch.bfloat16):
+                return U.unet_forward(cfg, weights, x, tt, class_labels=y)[0].float()
+        return fn
+    P = len(src)
+    _, zs, xts = D.inversion_forward_process(sched, mk(src), x0, noise, 1.0, P, list(cfg_src), cutoff_points=cutoff,
+                                             prompts=list(src))
+    ts = torch.tensor(tstart, dtype=torch.int)
+    w = D.inversion_reverse_process(sched, mk(tgt), xts, zs[:int(ts.max())], ts, 1.0, P, list(cfg_tar),
+                                    cutoff_points=cutoff)
+    rel = lambda a, b: float((a - b).norm() / b.norm())
+    return rel(zs, zs_ref), rel(w, w_ref)
 
 
 def save(name, **arrs):
@@ -219,9 +251,43 @@ def golden_stft():
          window=torch.from_numpy(np.asarray(__import__("scipy.signal").signal.get_window("hann", 1024, fftbins=True))).float())
 
 
+def golden_ends():
+    """Vendored VAE Encoder/Decoder (variational_autoencoder/modules.py) and HiFi-GAN Generator (hifigan/models.py),
+    unmodified, on seeded synthetic weights (oracle/ends_torch.py naming converted by vae_to_ldm / hifigan_to_ldm)."""
+    from oracle import ends_torch as E
+    ref = ref_import.load()
+    dd = dict(double_z=True, z_channels=8, resolution=256, downsample_time=False, in_channels=1, out_ch=1, ch=128,
+              ch_mult=[1, 2, 4], num_res_blocks=2, attn_resolutions=[], dropout=0.0)
+    enc, dec = ref.vae_modules.Encoder(**dd).eval(), ref.vae_modules.Decoder(**dd).eval()
+    w = E.vae_synthetic_weights(0)
+    ld = E.vae_to_ldm(w)
+    enc.load_state_dict({k[8:]: v for k, v in ld.items() if k.startswith("encoder.")})
+    dec.load_state_dict({k[8:]: v for k, v in ld.items() if k.startswith("decoder.")})
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(1, 1, 128, 64, generator=g) * 2 - 4          # log-mel-like
+    with torch.no_grad():
+        mom = torch.nn.functional.conv2d(enc(x), ld["quant_conv.weight"], ld["quant_conv.bias"])
+        z = mom[:, :8] * E.VAE_SCALING
+        dx = dec(torch.nn.functional.conv2d(z / E.VAE_SCALING, ld["post_quant_conv.weight"], ld["post_quant_conv.bias"]))
+    save("vae_ends.npz", x=x, moments=mom, z=z, decoded=dx, weight_seed=0)
+    h = types.SimpleNamespace(resblock="1", upsample_rates=[5, 4, 2, 2, 2], upsample_kernel_sizes=[16, 16, 8, 4, 4],
+                              upsample_initial_channel=1024, resblock_kernel_sizes=[3, 7, 11],
+                              resblock_dilation_sizes=[[1, 3, 5]] * 3, num_mels=64)
+    gen = ref.hifigan.Generator(h).eval()
+    gen.remove_weight_norm()
+    hw = E.hifigan_synthetic_weights(0)
+    gen.load_state_dict(E.hifigan_to_ldm(hw))
+    mel = torch.randn(1, 32, 64, generator=g) * 2 - 4
+    with torch.no_grad():
+        wav = gen(mel.transpose(1, 2)).squeeze(1)
+    save("hifigan_ends.npz", mel=mel, wav=wav, weight_seed=0)
+
+
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "stft":
-        golden_stft()
-    else:
+    what = sys.argv[1] if len(sys.argv) > 1 else "all"
+    if what in ("all", "loops"):
         main()
+    if what in ("all", "stft"):
         golden_stft()
+    if what in ("all", "ends"):
+        golden_ends()

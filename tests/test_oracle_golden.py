@@ -121,3 +121,20 @@ def test_replay_invariant_F9():
         xt = D.reverse_step_with_custom_noise(sched, eps, t, xt, g["zs"][idx][None], 1.0)
         if idx >= 1:
             assert _same(xt[0], g["xts"][idx], 2e-5)
+
+
+def test_ends_restatements_vs_vendored_modules():
+    """oracle/ends_torch.py vs golden outputs of the vendored VAE Encoder/Decoder and HiFi-GAN Generator."""
+    from oracle import ends_torch as E
+    g = load_golden("vae_ends.npz")
+    w = E.vae_synthetic_weights(0)
+    with torch.no_grad():
+        mom = E.vae_encode_moments(w, g["x"])
+        dec = E.vae_decode(w, g["z"])
+    assert torch.allclose(mom, g["moments"], atol=2e-5, rtol=1e-5)
+    assert torch.allclose(dec, g["decoded"], atol=5e-5, rtol=1e-5)
+    h = load_golden("hifigan_ends.npz")
+    hw = E.hifigan_synthetic_weights(0)
+    with torch.no_grad():
+        wav = E.hifigan_forward(hw, h["mel"])
+    assert _same(wav, h["wav"], 1e-6)
