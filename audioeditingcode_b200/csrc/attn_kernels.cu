@@ -56,6 +56,8 @@ __device__ __forceinline__ void load_tile(__nv_bfloat16* dst, const __nv_bfloat1
 
 template <int D>
 __global__ void __launch_bounds__(kAttnThreads) attention_kernel(AttnArgs a) {
+  pdl_trigger();
+  pdl_wait();
   using C = AttnCfg<D>;
   constexpr int DP = C::DP;
   constexpr int LDS = C::LDS;
@@ -234,7 +236,7 @@ int launch_attn(const AttnArgs& a, int B, int heads, cudaStream_t st) {
     attr_set = true;
   }
   dim3 grid((a.Tq + BQ - 1) / BQ, heads, B);
-  attention_kernel<D><<<grid, kAttnThreads, C::kSmemBytes, st>>>(a);
+  launch_kernel(attention_kernel<D>, dim3(grid), dim3(kAttnThreads), (size_t)(C::kSmemBytes), st, a);
   return launched("ae_attention");
 }
 

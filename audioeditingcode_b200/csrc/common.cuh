@@ -40,6 +40,29 @@ inline int launched(const char* what) {
 
 inline cudaStream_t as_stream(ae_stream s) { return reinterpret_cast<cudaStream_t>(s); }
 
+// Programmatic dependent launch (PDL): every kernel of the library starts with pdl_trigger() (lets the next kernel
+// in the stream be scheduled early so its prologue overlaps this kernel) and calls pdl_wait() before its first
+// global-memory access (blocks until the previous kernel has completed and its writes are visible).
+extern int g_use_pdl;
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                 Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = g_use_pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }

@@ -7,16 +7,19 @@
 // code/audioldm/latent_diffusion/openaimodel.py:213-244, attention.py:220-323).
 //
 // Tile: 128 (M) x BN (N) x 64 (K) bf16, fp32 accumulators in TMEM.  One CTA per output tile, 6 warps:
-//   warp 0  TMA producer   (cp.async.bulk.tensor, 128B-swizzled K-major tiles, STAGES-deep mbarrier ring)
+//   warp 0  TMA producer   (cp.async.bulk.tensor, 128B-swizzled K-major tiles, 3-stage mbarrier ring; the ring is
+//           kept short so 2-3 CTAs are resident per SM and one CTA's epilogue overlaps another's main loop)
 //   warp 1  TMEM allocator + single-thread tcgen05.mma issuer (4 UMMAs of K=16 per stage) + tcgen05.commit
 //   warps 2-5  epilogue: tcgen05.ld 32 lanes x 32 columns per warp, fused bias / time-embedding row bias /
-//              residual / SiLU, direct vectorised global stores (each thread owns one output row segment)
+//              residual / SiLU / GEGLU, direct vectorised global stores (each thread owns one output row segment)
 // Implicit convolution: the A operand is a channels-last image [B,H,W,C]; K-block kb = (tap, 64-channel slab);
 // the producer issues a 4-D TMA box {64 ch, Wb, Hb, Bb} at (c0, w0+dw, h0+dh, b0) — out-of-bounds rows/cols are
 // zero-filled by TMA, which is exactly the convolution's zero padding.  The 128 tile rows are the flattened
 // (b,h,w) positions m0..m0+127, so the epilogue is identical to the plain GEMM.
-// Determinism / batch invariance: no split-K, no atomics — a sample's reduction order never depends on the
-// batch it is launched with (needed for the bit-exact replay invariant).
+// Small-M layers (deep U-Net levels at batch 2: one or two M tiles, K up to 8640): split-K over blockIdx.z, fp32
+// partial tiles to a workspace, then a fully parallel fixed-order reduce + epilogue kernel (no atomics).
+// Determinism / batch invariance: the split factor depends only on (tiles, K), never on data; a sample's reduction
+// order never depends on what else is in the batch except through the tile count (documented in DESIGN.md §4).
 #include <cuda.h>
 #include <mutex>
 
@@ -24,16 +27,20 @@
 #include "ptx.cuh"
 
 namespace aedit {
+int g_use_pdl = 1;
 namespace {
 
 constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int kThreads = 192;
 constexpr int kATileBytes = BM * BK * 2;  // 16 KiB
+constexpr int kStages = 3;
 
 struct GemmDev {
   int M, N;
   int num_kblocks;
+  int kb_per_split;  // == num_kblocks when not split
+  int split;         // 1: blockIdx.z is a K split (partials to out_f32 + z*stride_out), else a batch index
   // implicit conv
   int conv, H, W, HW, cblocks, kw, dil_h, dil_w, pad_h, pad_w;
   // epilogue
@@ -48,7 +55,7 @@ struct GemmDev {
   __nv_bfloat16* out_bf16;
   long long ld_out_bf16;
   long long stride_out, stride_res;
-  int act;
+  int act;  // 0 none, 1 SiLU, 2 GEGLU (output width N/2: out[16q+i] = acc[32q+i] * gelu(acc[32q+16+i]))
   float alpha;
 };
 
@@ -56,18 +63,20 @@ template <int BN>
 struct SmemLayout {
   static constexpr int kBTileBytes = BN * BK * 2;
   static constexpr int kStageBytes = kATileBytes + kBTileBytes;
-  static constexpr int kStages = (BN <= 32) ? 8 : (BN <= 64 ? 8 : 6);
-  static constexpr int kBarBytes = 256;
+  static constexpr int kBarBytes = 128;
   static constexpr int kTotal = kStages * kStageBytes + kBarBytes + 1024;  // +1024 manual alignment slack
 };
 
+__device__ __forceinline__ float gelu_erf_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+
 template <int BN>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreads)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmDev p) {
   using L = SmemLayout<BN>;
-  constexpr int STAGES = L::kStages;
+  constexpr int STAGES = kStages;
   constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
   extern __shared__ uint8_t smem_raw[];
+  pdl_trigger();
   // 1024-byte alignment is required by the 128B swizzle atoms (TMA and UMMA both derive the XOR from address bits)
   const uint32_t raw_addr = ptx::smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
@@ -85,6 +94,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const int z = blockIdx.z;
   const int m0 = tile_m * BM;
   const int n0 = tile_n * BN;
+  const int zb = p.split ? 0 : z;  // batch coordinate of the tensor maps
+  const int kb0 = p.split ? z * p.kb_per_split : 0;
+  const int kb1 = p.split ? min(p.num_kblocks, kb0 + p.kb_per_split) : p.num_kblocks;
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&tmA);
@@ -101,6 +113,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   __syncthreads();
   ptx::tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();  // everything above overlapped the previous kernel; from here on we touch global memory
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -114,7 +127,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
       int stage = 0;
       uint32_t phase = 0;
-      for (int kb = 0; kb < p.num_kblocks; ++kb) {
+      for (int kb = kb0; kb < kb1; ++kb) {
         ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
         ptx::mbar_expect_tx(&full_bar[stage], L::kStageBytes);
         if (p.conv) {
@@ -125,9 +138,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           ptx::tma_load_4d(&tmA, &full_bar[stage], sA + stage * kATileBytes, cb * BK, w0 + j * p.dil_w - p.pad_w,
                            h0 + i * p.dil_h - p.pad_h, b0);
         } else {
-          ptx::tma_load_3d(&tmA, &full_bar[stage], sA + stage * kATileBytes, kb * BK, m0, z);
+          ptx::tma_load_3d(&tmA, &full_bar[stage], sA + stage * kATileBytes, kb * BK, m0, zb);
         }
-        ptx::tma_load_3d(&tmB, &full_bar[stage], sB + stage * L::kBTileBytes, kb * BK, n0, z);
+        ptx::tma_load_3d(&tmB, &full_bar[stage], sB + stage * L::kBTileBytes, kb * BK, n0, zb);
         if (++stage == STAGES) {
           stage = 0;
           phase ^= 1;
@@ -140,7 +153,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       constexpr uint32_t idesc = ptx::umma_idesc_bf16_f32(BM, BN);
       int stage = 0;
       uint32_t phase = 0;
-      for (int kb = 0; kb < p.num_kblocks; ++kb) {
+      for (int kb = kb0; kb < kb1; ++kb) {
         ptx::mbar_wait(&full_bar[stage], phase);
         ptx::tcgen05_fence_after();
         const uint32_t a_addr = ptx::smem_u32(sA + stage * kATileBytes);
@@ -150,7 +163,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           // advance 16 bf16 = 32 B along K inside the 128 B swizzle atom
           const uint64_t da = ptx::umma_desc_k_sw128(a_addr + k * 32);
           const uint64_t db = ptx::umma_desc_k_sw128(b_addr + k * 32);
-          ptx::umma_bf16_ss(tmem_base, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          ptx::umma_bf16_ss(tmem_base, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
         }
         ptx::umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
         if (++stage == STAGES) {
@@ -185,9 +198,21 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
       for (int j = 0; j < 32; ++j) acc[j] = __uint_as_float(v[j]) * p.alpha;
       if (p.bias) {
+        if (nvalid == 32) {
+          const float4* b4 = reinterpret_cast<const float4*>(p.bias + nbase);
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (j < nvalid) acc[j] += __ldg(p.bias + nbase + j);
+          for (int j = 0; j < 8; ++j) {
+            const float4 t = __ldg(b4 + j);
+            acc[4 * j + 0] += t.x;
+            acc[4 * j + 1] += t.y;
+            acc[4 * j + 2] += t.z;
+            acc[4 * j + 3] += t.w;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (j < nvalid) acc[j] += __ldg(p.bias + nbase + j);
+        }
       }
       if (rb) {
 #pragma unroll
@@ -211,41 +236,50 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             if (j < nvalid) acc[j] += res[nbase + j];
         }
       }
+      int obase = nbase, ovalid = nvalid;
       if (p.act == 1) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) acc[j] = silu_f(acc[j]);
+      } else if (p.act == 2) {
+        // weight rows were interleaved host-side: columns [32q, 32q+16) = value, [32q+16, 32q+32) = gate
+#pragma unroll
+        for (int j = 0; j < 16; ++j) acc[j] = acc[j] * gelu_erf_f(acc[16 + j]);
+        obase = nbase >> 1;
+        ovalid = nvalid >> 1;
       }
       if (of) {
-        if (nvalid == 32 && ((reinterpret_cast<uintptr_t>(of + nbase) & 15) == 0)) {
-          float4* o4 = reinterpret_cast<float4*>(of + nbase);
+        if (ovalid == 32 && ((reinterpret_cast<uintptr_t>(of + obase) & 15) == 0)) {
+          float4* o4 = reinterpret_cast<float4*>(of + obase);
 #pragma unroll
           for (int j = 0; j < 8; ++j) o4[j] = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
         } else {
 #pragma unroll
           for (int j = 0; j < 32; ++j)
-            if (j < nvalid) of[nbase + j] = acc[j];
+            if (j < ovalid) of[obase + j] = acc[j];
         }
       }
       if (ob) {
-        if (nvalid == 32 && ((reinterpret_cast<uintptr_t>(ob + nbase) & 15) == 0)) {
-          uint4* o4 = reinterpret_cast<uint4*>(ob + nbase);
+        if ((ovalid == 32 || ovalid == 16) && ((reinterpret_cast<uintptr_t>(ob + obase) & 15) == 0)) {
+          uint4* o4 = reinterpret_cast<uint4*>(ob + obase);
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            __nv_bfloat162 h0 = __floats2bfloat162_rn(acc[8 * j + 0], acc[8 * j + 1]);
-            __nv_bfloat162 h1 = __floats2bfloat162_rn(acc[8 * j + 2], acc[8 * j + 3]);
-            __nv_bfloat162 h2 = __floats2bfloat162_rn(acc[8 * j + 4], acc[8 * j + 5]);
-            __nv_bfloat162 h3 = __floats2bfloat162_rn(acc[8 * j + 6], acc[8 * j + 7]);
-            uint4 pk;
-            pk.x = *reinterpret_cast<uint32_t*>(&h0);
-            pk.y = *reinterpret_cast<uint32_t*>(&h1);
-            pk.z = *reinterpret_cast<uint32_t*>(&h2);
-            pk.w = *reinterpret_cast<uint32_t*>(&h3);
-            o4[j] = pk;
+            if (8 * j < ovalid) {
+              __nv_bfloat162 h0 = __floats2bfloat162_rn(acc[8 * j + 0], acc[8 * j + 1]);
+              __nv_bfloat162 h1 = __floats2bfloat162_rn(acc[8 * j + 2], acc[8 * j + 3]);
+              __nv_bfloat162 h2 = __floats2bfloat162_rn(acc[8 * j + 4], acc[8 * j + 5]);
+              __nv_bfloat162 h3 = __floats2bfloat162_rn(acc[8 * j + 6], acc[8 * j + 7]);
+              uint4 pk;
+              pk.x = *reinterpret_cast<uint32_t*>(&h0);
+              pk.y = *reinterpret_cast<uint32_t*>(&h1);
+              pk.z = *reinterpret_cast<uint32_t*>(&h2);
+              pk.w = *reinterpret_cast<uint32_t*>(&h3);
+              o4[j] = pk;
+            }
           }
         } else {
 #pragma unroll
           for (int j = 0; j < 32; ++j)
-            if (j < nvalid) ob[nbase + j] = __float2bfloat16_rn(acc[j]);
+            if (j < ovalid) ob[obase + j] = __float2bfloat16_rn(acc[j]);
         }
       }
     }
@@ -255,6 +289,75 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if (warp == 1) {
     ptx::tcgen05_fence_after();
     ptx::tmem_dealloc<TMEM_COLS>(tmem_base);
+  }
+}
+
+// out = act(alpha * sum_s ws[s] + bias + rowbias + residual): fixed summation order s = 0..S-1 (deterministic)
+struct ReduceArgs {
+  const float* ws;
+  int S;
+  long long MN;
+  int M, N;
+  const float* bias;
+  const float* rowbias;
+  long long ld_rowbias;
+  int rows_per_group;
+  const float* residual;
+  long long ld_res;
+  float* out_f32;
+  long long ld_out_f32;
+  __nv_bfloat16* out_bf16;
+  long long ld_out_bf16;
+  int act;
+  float alpha;
+};
+
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(ReduceArgs a) {
+  pdl_trigger();
+  pdl_wait();
+  const int n4 = a.N >> 2;
+  const long long total = (long long)a.M * n4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long m = i / n4;
+    const int n = (int)(i - m * n4) << 2;
+    const float* w = a.ws + m * a.N + n;
+    float4 acc = *reinterpret_cast<const float4*>(w);
+    for (int s = 1; s < a.S; ++s) {
+      const float4 t = *reinterpret_cast<const float4*>(w + (long long)s * a.MN);
+      acc.x += t.x;
+      acc.y += t.y;
+      acc.z += t.z;
+      acc.w += t.w;
+    }
+    float v[4] = {acc.x * a.alpha, acc.y * a.alpha, acc.z * a.alpha, acc.w * a.alpha};
+    if (a.bias) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) v[k] += __ldg(a.bias + n + k);
+    }
+    if (a.rowbias) {
+      const float* rb = a.rowbias + (m / a.rows_per_group) * a.ld_rowbias + n;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) v[k] += __ldg(rb + k);
+    }
+    if (a.residual) {
+      const float* r = a.residual + m * a.ld_res + n;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) v[k] += r[k];
+    }
+    if (a.act == 1) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) v[k] = silu_f(v[k]);
+    }
+    if (a.out_f32) {
+      float* o = a.out_f32 + m * a.ld_out_f32 + n;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) o[k] = v[k];
+    }
+    if (a.out_bf16) {
+      __nv_bfloat16* o = a.out_bf16 + m * a.ld_out_bf16 + n;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) o[k] = __float2bfloat16_rn(v[k]);
+    }
   }
 }
 
@@ -325,7 +428,7 @@ bool conv_box(int B, int H, int W, ConvBox* bx) {
 }
 
 template <int BN>
-int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmDev& p, int batch, cudaStream_t st) {
+int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmDev& p, int gz, cudaStream_t st) {
   using L = SmemLayout<BN>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -333,8 +436,9 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmDev& p, int
     if (e != cudaSuccess) return fail(AE_ECUDA, "cudaFuncSetAttribute(smem=%d): %s", L::kTotal, cudaGetErrorString(e));
     attr_set = true;
   }
-  dim3 grid((p.M + BM - 1) / BM, (p.N + BN - 1) / BN, batch);
-  gemm_tcgen05_kernel<BN><<<grid, kThreads, L::kTotal, st>>>(tmA, tmB, p);
+  dim3 grid((p.M + BM - 1) / BM, (p.N + BN - 1) / BN, gz);
+  cudaError_t e = launch_kernel(gemm_tcgen05_kernel<BN>, grid, dim3(kThreads), (size_t)L::kTotal, st, tmA, tmB, p);
+  if (e != cudaSuccess) return fail(AE_ECUDA, "ae_gemm launch: %s", cudaGetErrorString(e));
   return launched("ae_gemm");
 }
 
@@ -342,6 +446,8 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmDev& p, int
 }  // namespace aedit
 
 using namespace aedit;
+
+extern "C" void ae_set_pdl(int enable) { g_use_pdl = enable ? 1 : 0; }
 
 extern "C" int ae_gemm_conv_supported(int B, int H, int W, int C) {
   ConvBox bx;
@@ -352,6 +458,8 @@ extern "C" int ae_gemm(const ae_gemm_args* a, ae_stream stream) {
   AE_CHECK_ARG(a && a->A && a->W, "ae_gemm: null operand");
   AE_CHECK_ARG(a->M > 0 && a->N > 0 && a->K > 0, "ae_gemm: bad shape M=%d N=%d K=%d", a->M, a->N, a->K);
   AE_CHECK_ARG(a->out_f32 || a->out_bf16, "ae_gemm: no output");
+  AE_CHECK_ARG(a->act >= 0 && a->act <= 2, "ae_gemm: act must be 0 (none), 1 (SiLU) or 2 (GEGLU)");
+  AE_CHECK_ARG(a->act != 2 || a->N % 32 == 0, "ae_gemm: GEGLU epilogue needs N %% 32 == 0 (N=%d)", a->N);
   const int batch = a->batch > 0 ? a->batch : 1;
   GemmDev p;
   p.M = a->M;
@@ -374,6 +482,7 @@ extern "C" int ae_gemm(const ae_gemm_args* a, ae_stream stream) {
   p.H = p.W = p.HW = p.cblocks = p.kw = 1;
   p.dil_h = p.dil_w = 1;
   p.pad_h = p.pad_w = 0;
+  p.split = 0;
 
   CUtensorMap tmA, tmB;
   int rc;
@@ -412,23 +521,38 @@ extern "C" int ae_gemm(const ae_gemm_args* a, ae_stream stream) {
     if (rc) return rc;
   }
   AE_CHECK_ARG(a->ldw >= a->K, "ae_gemm: ldw < K");
+  p.kb_per_split = p.num_kblocks;
 
-  // tile width: wide tiles when the grid already fills the machine, narrower ones to spread weight streaming
+  // ---- tile width.  Wide tiles minimise shared-memory traffic per FLOP; parallelism for small grids comes from
+  //      split-K (below), not from narrow tiles.
+  const long long tiles_m = (a->M + BM - 1) / BM;
   int bn = a->force_bn;
   if (bn == 0) {
-    const long long tiles_m = (a->M + BM - 1) / BM;
-    bn = 128;
     if (a->N <= 32)
       bn = 32;
-    else if (a->N <= 64)
+    else if (a->N <= 64 || (a->N % 128 != 0 && a->N % 128 <= 64 && a->N < 512))
       bn = 64;
-    else {
-      const long long t128 = tiles_m * ((a->N + 127) / 128) * batch;
-      const long long t64 = tiles_m * ((a->N + 63) / 64) * batch;
-      if (t128 < 120) bn = (t64 < 120) ? 32 : 64;
-    }
+    else
+      bn = 128;
   }
   AE_CHECK_ARG(bn == 32 || bn == 64 || bn == 128, "ae_gemm: force_bn must be 32, 64 or 128");
+  const long long tiles = tiles_m * ((a->N + bn - 1) / bn);
+
+  // ---- split-K: only un-batched problems whose tile grid leaves most SMs idle and whose K is deep enough
+  int S = 1;
+  if (batch == 1 && a->act != 2 && a->splitk_ws && a->N % 4 == 0 && a->force_split != 1) {
+    if (a->force_split > 1)
+      S = a->force_split;
+    else if (tiles <= 48 && p.num_kblocks >= 8) {
+      S = (int)(148 / tiles);
+      const int max_by_k = p.num_kblocks / 4;
+      if (S > max_by_k) S = max_by_k;
+      if (S > 32) S = 32;
+    }
+    if (S > p.num_kblocks) S = p.num_kblocks;
+    while (S > 1 && (long long)S * a->M * a->N * 4 > a->splitk_ws_bytes) --S;
+    if (S < 2) S = 1;
+  }
   {
     uint64_t dims[3] = {(uint64_t)a->K, (uint64_t)a->N, (uint64_t)batch};
     uint64_t str[2] = {(uint64_t)a->ldw * 2, (uint64_t)(batch > 1 ? a->strideW : (int64_t)a->N * a->ldw) * 2};
@@ -437,12 +561,56 @@ extern "C" int ae_gemm(const ae_gemm_args* a, ae_stream stream) {
     if (rc) return rc;
   }
   cudaStream_t st = as_stream(stream);
+  int gz = batch;
+  GemmDev q = p;
+  if (S > 1) {
+    q.split = 1;
+    q.kb_per_split = (p.num_kblocks + S - 1) / S;
+    S = (p.num_kblocks + q.kb_per_split - 1) / q.kb_per_split;  // no empty splits
+    gz = S;
+    q.bias = nullptr;
+    q.rowbias = nullptr;
+    q.residual = nullptr;
+    q.out_bf16 = nullptr;
+    q.out_f32 = a->splitk_ws;
+    q.ld_out_f32 = a->N;
+    q.stride_out = (long long)a->M * a->N;
+    q.act = 0;
+    q.alpha = 1.0f;
+  }
   switch (bn) {
     case 32:
-      return launch<32>(tmA, tmB, p, batch, st);
+      rc = launch<32>(tmA, tmB, q, gz, st);
+      break;
     case 64:
-      return launch<64>(tmA, tmB, p, batch, st);
+      rc = launch<64>(tmA, tmB, q, gz, st);
+      break;
     default:
-      return launch<128>(tmA, tmB, p, batch, st);
+      rc = launch<128>(tmA, tmB, q, gz, st);
+      break;
   }
+  if (rc || S == 1) return rc;
+  ReduceArgs r;
+  r.ws = a->splitk_ws;
+  r.S = S;
+  r.MN = (long long)a->M * a->N;
+  r.M = a->M;
+  r.N = a->N;
+  r.bias = p.bias;
+  r.rowbias = p.rowbias;
+  r.ld_rowbias = p.ld_rowbias;
+  r.rows_per_group = p.rows_per_group;
+  r.residual = p.residual;
+  r.ld_res = p.ld_res;
+  r.out_f32 = p.out_f32;
+  r.ld_out_f32 = p.ld_out_f32;
+  r.out_bf16 = p.out_bf16;
+  r.ld_out_bf16 = p.ld_out_bf16;
+  r.act = p.act;
+  r.alpha = p.alpha;
+  long long blocks = ceil_div64(r.MN / 4, 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  cudaError_t e = launch_kernel(splitk_reduce_kernel, dim3((unsigned)blocks), dim3(256), (size_t)0, st, r);
+  if (e != cudaSuccess) return fail(AE_ECUDA, "splitk_reduce launch: %s", cudaGetErrorString(e));
+  return launched("ae_gemm(splitk_reduce)");
 }

@@ -11,6 +11,8 @@ namespace {
 template <typename T>
 __global__ void im2col_kernel(const T* __restrict__ in, int B, int H, int W, int C, int kh, int kw, int stride, int dil,
                               int pad_t, int pad_l, int Ho, int Wo, __nv_bfloat16* __restrict__ out, long long ld_out) {
+  pdl_trigger();
+  pdl_wait();
   // one CTA row of threads walks the K dimension of one output position (coalesced over channels)
   const long long m = blockIdx.x;
   const int wo = (int)(m % Wo);
@@ -37,6 +39,8 @@ __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + e
 
 __global__ void geglu_kernel(const __nv_bfloat16* __restrict__ h, long long rows, int inner,
                              __nv_bfloat16* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
   const int vec = inner >> 3;
   const long long total = rows * vec;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -61,6 +65,8 @@ __global__ void geglu_kernel(const __nv_bfloat16* __restrict__ h, long long rows
 // ------------------------------------------------------------------ timestep embedding  [cos | sin]
 __global__ void timestep_embedding_kernel(const long long* __restrict__ t, int B, int dim,
                                           __nv_bfloat16* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
   const int half = dim >> 1;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * half) return;
@@ -75,6 +81,8 @@ __global__ void timestep_embedding_kernel(const long long* __restrict__ t, int B
 // ------------------------------------------------------------------ nearest resize (f32 NHWC -> bf16 NHWC)
 __global__ void upsample_nearest_kernel(const float* __restrict__ x, int B, int H, int W, int C, int Ho, int Wo,
                                         __nv_bfloat16* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
   const int vec = C >> 2;
   const long long total = (long long)B * Ho * Wo * vec;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -100,6 +108,8 @@ __global__ void upsample_nearest_kernel(const float* __restrict__ x, int B, int 
 // ------------------------------------------------------------------ NCHW <-> NHWC (tiled transpose per sample)
 __global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, int C, long long HW, float* __restrict__ of,
                                     __nv_bfloat16* __restrict__ ob) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float tile[32][33];
   const int b = blockIdx.z;
   const long long p0 = (long long)blockIdx.x * 32;
@@ -122,6 +132,8 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, int C, long lon
   }
 }
 __global__ void nhwc_to_nchw_kernel(const float* __restrict__ x, int C, long long HW, float* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float tile[32][33];
   const int b = blockIdx.z;
   const long long p0 = (long long)blockIdx.x * 32;
@@ -141,6 +153,8 @@ __global__ void nhwc_to_nchw_kernel(const float* __restrict__ x, int C, long lon
 
 // ------------------------------------------------------------------ elementwise
 __global__ void cast_f32_bf16_kernel(const float* __restrict__ x, long long n, __nv_bfloat16* __restrict__ out, int silu) {
+  pdl_trigger();
+  pdl_wait();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     float v = x[i];
     if (silu) v = silu_f(v);
@@ -149,17 +163,23 @@ __global__ void cast_f32_bf16_kernel(const float* __restrict__ x, long long n, _
 }
 __global__ void add_f32_kernel(const float* __restrict__ a, const float* __restrict__ b, float sb, long long n,
                                float* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     out[i] = a[i] + sb * b[i];
 }
 __global__ void leaky_relu_bf16_kernel(const float* __restrict__ x, long long n, float slope,
                                        __nv_bfloat16* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const float v = x[i];
     out[i] = __float2bfloat16_rn(v > 0.f ? v : v * slope);
   }
 }
 __global__ void tanh_f32_kernel(const float* __restrict__ x, long long n, float* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     out[i] = tanhf(x[i]);
 }
@@ -167,6 +187,8 @@ __global__ void tanh_f32_kernel(const float* __restrict__ x, long long n, float*
 // ------------------------------------------------------------------ row softmax (fp32 -> bf16), one CTA per row
 __global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restrict__ x, int n, long long ld,
                                                            __nv_bfloat16* __restrict__ out, long long ld_out) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float red[8];
   const float* xr = x + (long long)blockIdx.x * ld;
   __nv_bfloat16* orow = out + (long long)blockIdx.x * ld_out;
@@ -196,6 +218,8 @@ __global__ void __launch_bounds__(256) softmax_rows_kernel(const float* __restri
 
 __global__ void transpose_bf16_kernel(const __nv_bfloat16* __restrict__ x, int rows, int cols,
                                       __nv_bfloat16* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ __nv_bfloat16 tile[32][34];
   const long long boff = (long long)blockIdx.z * rows * cols;
   const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
@@ -230,28 +254,24 @@ extern "C" int ae_im2col(const void* in, int in_is_bf16, int B, int H, int W, in
   AE_CHECK_ARG(M > 0 && M < 2147483647LL, "ae_im2col: bad output size");
   const int threads = ld_out >= 256 ? 256 : 128;
   if (in_is_bf16)
-    im2col_kernel<__nv_bfloat16><<<(unsigned)M, threads, 0, as_stream(stream)>>>(
-        reinterpret_cast<const __nv_bfloat16*>(in), B, H, W, C, kh, kw, stride, dil, pad_t, pad_l, Ho, Wo,
+    launch_kernel(im2col_kernel<__nv_bfloat16>, dim3((unsigned)M), dim3(threads), (size_t)(0), as_stream(stream), reinterpret_cast<const __nv_bfloat16*>(in), B, H, W, C, kh, kw, stride, dil, pad_t, pad_l, Ho, Wo,
         reinterpret_cast<__nv_bfloat16*>(out_bf16), ld_out);
   else
-    im2col_kernel<float><<<(unsigned)M, threads, 0, as_stream(stream)>>>(
-        reinterpret_cast<const float*>(in), B, H, W, C, kh, kw, stride, dil, pad_t, pad_l, Ho, Wo,
+    launch_kernel(im2col_kernel<float>, dim3((unsigned)M), dim3(threads), (size_t)(0), as_stream(stream), reinterpret_cast<const float*>(in), B, H, W, C, kh, kw, stride, dil, pad_t, pad_l, Ho, Wo,
         reinterpret_cast<__nv_bfloat16*>(out_bf16), ld_out);
   return launched("ae_im2col");
 }
 
 extern "C" int ae_geglu(const void* h, int64_t rows, int inner, void* out, ae_stream stream) {
   AE_CHECK_ARG(h && out && rows > 0 && inner > 0 && inner % 8 == 0, "ae_geglu: bad argument (inner %% 8 == 0 required)");
-  geglu_kernel<<<ew_grid(rows * (inner / 8), 256), 256, 0, as_stream(stream)>>>(
-      reinterpret_cast<const __nv_bfloat16*>(h), rows, inner, reinterpret_cast<__nv_bfloat16*>(out));
+  launch_kernel(geglu_kernel, dim3(ew_grid(rows * (inner / 8), 256)), dim3(256), (size_t)(0), as_stream(stream), reinterpret_cast<const __nv_bfloat16*>(h), rows, inner, reinterpret_cast<__nv_bfloat16*>(out));
   return launched("ae_geglu");
 }
 
 extern "C" int ae_timestep_embedding(const int64_t* t, int B, int dim, void* out_bf16, ae_stream stream) {
   AE_CHECK_ARG(t && out_bf16 && B > 0 && dim > 0 && dim % 2 == 0, "ae_timestep_embedding: bad argument");
   const int n = B * (dim / 2);
-  timestep_embedding_kernel<<<(n + 127) / 128, 128, 0, as_stream(stream)>>>(
-      reinterpret_cast<const long long*>(t), B, dim, reinterpret_cast<__nv_bfloat16*>(out_bf16));
+  launch_kernel(timestep_embedding_kernel, dim3((n + 127) / 128), dim3(128), (size_t)(0), as_stream(stream), reinterpret_cast<const long long*>(t), B, dim, reinterpret_cast<__nv_bfloat16*>(out_bf16));
   return launched("ae_timestep_embedding");
 }
 
@@ -259,8 +279,7 @@ extern "C" int ae_upsample_nearest(const float* x, int B, int H, int W, int C, i
                                    ae_stream stream) {
   AE_CHECK_ARG(x && out_bf16 && B > 0 && H > 0 && W > 0 && C > 0 && C % 4 == 0 && Ho > 0 && Wo > 0,
                "ae_upsample_nearest: bad argument");
-  upsample_nearest_kernel<<<ew_grid((long long)B * Ho * Wo * (C / 4), 256), 256, 0, as_stream(stream)>>>(
-      x, B, H, W, C, Ho, Wo, reinterpret_cast<__nv_bfloat16*>(out_bf16));
+  launch_kernel(upsample_nearest_kernel, dim3(ew_grid((long long)B * Ho * Wo * (C / 4), 256)), dim3(256), (size_t)(0), as_stream(stream), x, B, H, W, C, Ho, Wo, reinterpret_cast<__nv_bfloat16*>(out_bf16));
   return launched("ae_upsample_nearest");
 }
 
@@ -269,7 +288,7 @@ extern "C" int ae_nchw_to_nhwc(const float* x, int B, int C, int H, int W, float
   AE_CHECK_ARG(x && (out_f32 || out_bf16) && B > 0 && C > 0 && H > 0 && W > 0, "ae_nchw_to_nhwc: bad argument");
   const long long HW = (long long)H * W;
   dim3 grid((unsigned)ceil_div64(HW, 32), (C + 31) / 32, B);
-  nchw_to_nhwc_kernel<<<grid, dim3(32, 8), 0, as_stream(stream)>>>(x, C, HW, out_f32,
+  launch_kernel(nchw_to_nhwc_kernel, dim3(grid), dim3(dim3(32, 8)), (size_t)(0), as_stream(stream), x, C, HW, out_f32,
                                                                    reinterpret_cast<__nv_bfloat16*>(out_bf16));
   return launched("ae_nchw_to_nhwc");
 }
@@ -278,40 +297,40 @@ extern "C" int ae_nhwc_to_nchw(const float* x, int B, int C, int H, int W, float
   AE_CHECK_ARG(x && out_f32 && B > 0 && C > 0 && H > 0 && W > 0, "ae_nhwc_to_nchw: bad argument");
   const long long HW = (long long)H * W;
   dim3 grid((unsigned)ceil_div64(HW, 32), (C + 31) / 32, B);
-  nhwc_to_nchw_kernel<<<grid, dim3(32, 8), 0, as_stream(stream)>>>(x, C, HW, out_f32);
+  launch_kernel(nhwc_to_nchw_kernel, dim3(grid), dim3(dim3(32, 8)), (size_t)(0), as_stream(stream), x, C, HW, out_f32);
   return launched("ae_nhwc_to_nchw");
 }
 
 extern "C" int ae_cast_f32_bf16(const float* x, int64_t n, void* out_bf16, int silu, ae_stream stream) {
   AE_CHECK_ARG(x && out_bf16 && n > 0, "ae_cast_f32_bf16: bad argument");
-  cast_f32_bf16_kernel<<<ew_grid(n, 256), 256, 0, as_stream(stream)>>>(x, n, reinterpret_cast<__nv_bfloat16*>(out_bf16),
+  launch_kernel(cast_f32_bf16_kernel, dim3(ew_grid(n, 256)), dim3(256), (size_t)(0), as_stream(stream), x, n, reinterpret_cast<__nv_bfloat16*>(out_bf16),
                                                                        silu);
   return launched("ae_cast_f32_bf16");
 }
 
 extern "C" int ae_add_f32(const float* a, const float* b, float scale_b, int64_t n, float* out, ae_stream stream) {
   AE_CHECK_ARG(a && b && out && n > 0, "ae_add_f32: bad argument");
-  add_f32_kernel<<<ew_grid(n, 256), 256, 0, as_stream(stream)>>>(a, b, scale_b, n, out);
+  launch_kernel(add_f32_kernel, dim3(ew_grid(n, 256)), dim3(256), (size_t)(0), as_stream(stream), a, b, scale_b, n, out);
   return launched("ae_add_f32");
 }
 
 extern "C" int ae_leaky_relu_bf16(const float* x, int64_t n, float slope, void* out_bf16, ae_stream stream) {
   AE_CHECK_ARG(x && out_bf16 && n > 0, "ae_leaky_relu_bf16: bad argument");
-  leaky_relu_bf16_kernel<<<ew_grid(n, 256), 256, 0, as_stream(stream)>>>(x, n, slope,
+  launch_kernel(leaky_relu_bf16_kernel, dim3(ew_grid(n, 256)), dim3(256), (size_t)(0), as_stream(stream), x, n, slope,
                                                                          reinterpret_cast<__nv_bfloat16*>(out_bf16));
   return launched("ae_leaky_relu_bf16");
 }
 
 extern "C" int ae_tanh_f32(const float* x, int64_t n, float* out, ae_stream stream) {
   AE_CHECK_ARG(x && out && n > 0, "ae_tanh_f32: bad argument");
-  tanh_f32_kernel<<<ew_grid(n, 256), 256, 0, as_stream(stream)>>>(x, n, out);
+  launch_kernel(tanh_f32_kernel, dim3(ew_grid(n, 256)), dim3(256), (size_t)(0), as_stream(stream), x, n, out);
   return launched("ae_tanh_f32");
 }
 
 extern "C" int ae_softmax_rows(const float* x, int64_t rows, int n, int64_t ld, void* out_bf16, int64_t ld_out,
                                ae_stream stream) {
   AE_CHECK_ARG(x && out_bf16 && rows > 0 && n > 0 && rows < 2147483647LL, "ae_softmax_rows: bad argument");
-  softmax_rows_kernel<<<(unsigned)rows, 256, 0, as_stream(stream)>>>(x, n, ld, reinterpret_cast<__nv_bfloat16*>(out_bf16),
+  launch_kernel(softmax_rows_kernel, dim3((unsigned)rows), dim3(256), (size_t)(0), as_stream(stream), x, n, ld, reinterpret_cast<__nv_bfloat16*>(out_bf16),
                                                                      ld_out);
   return launched("ae_softmax_rows");
 }
@@ -319,7 +338,7 @@ extern "C" int ae_softmax_rows(const float* x, int64_t rows, int n, int64_t ld, 
 extern "C" int ae_transpose_bf16(const void* x, int batch, int rows, int cols, void* out, ae_stream stream) {
   AE_CHECK_ARG(x && out && batch > 0 && rows > 0 && cols > 0, "ae_transpose_bf16: bad argument");
   dim3 grid((cols + 31) / 32, (rows + 31) / 32, batch);
-  transpose_bf16_kernel<<<grid, dim3(32, 8), 0, as_stream(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(x), rows, cols,
+  launch_kernel(transpose_bf16_kernel, dim3(grid), dim3(dim3(32, 8)), (size_t)(0), as_stream(stream), reinterpret_cast<const __nv_bfloat16*>(x), rows, cols,
                                                                      reinterpret_cast<__nv_bfloat16*>(out));
   return launched("ae_transpose_bf16");
 }

@@ -11,7 +11,7 @@ namespace aedit {
 namespace {
 
 constexpr int kGNThreads = 256;
-constexpr int kMaxSplits = 32;
+constexpr int kMaxSplits = 64;
 
 struct GNArgs {
   const float* x1;
@@ -37,64 +37,100 @@ __device__ __forceinline__ float load_cat(const GNArgs& a, long long row, int c)
   return c < a.C1 ? a.x1[row * a.C1 + c] : a.x2[row * a.C2 + (c - a.C1)];
 }
 
-// grid (S, B).  Each CTA reduces `chunk` positions x all channels, then the last CTA of a sample finalises.
-__global__ void __launch_bounds__(kGNThreads) gn_stats_kernel(GNArgs a) {
-  extern __shared__ float sm[];  // [2*C] per-channel sum / sumsq
+// grid (S, B), block (TX, TY): thread (tx, ty) owns the channel quads tx, tx+TX, ... (<= 4 of them) and walks the
+// positions p0+ty, p0+ty+TY, ... of this CTA's chunk with independent float4 loads (coalesced along channels,
+// TY loads in flight per quad).  Per-channel partials are combined over ty in shared memory in a fixed order, then
+// per group in double; the last CTA of a sample (arrival counter) finalises mean / rstd for all groups.
+constexpr int kGNMaxQuadsPerThread = 4;
+__global__ void __launch_bounds__(512) gn_stats_kernel(GNArgs a) {
+  pdl_trigger();
+  pdl_wait();
+  extern __shared__ float sm[];  // [TY][2*C] per-channel sum / sumsq per ty
   __shared__ bool is_last;
   const int s = blockIdx.x, b = blockIdx.y;
+  const int TX = blockDim.x, TY = blockDim.y;
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int tid = ty * TX + tx, nthr = TX * TY;
   const long long p0 = (long long)s * a.chunk;
   const long long p1 = min(a.HW, p0 + a.chunk);
-  float* ssum = sm;
-  float* ssq = sm + a.C;
-  for (int c = threadIdx.x; c < a.C; c += kGNThreads) {
-    float su = 0.f, sq = 0.f;
-    for (long long p = p0; p < p1; ++p) {
-      const float v = load_cat(a, (long long)b * a.HW + p, c);
-      su += v;
-      sq += v * v;
+  const int nq = a.C >> 2;
+  float su[kGNMaxQuadsPerThread][4], sq[kGNMaxQuadsPerThread][4];
+#pragma unroll
+  for (int k = 0; k < kGNMaxQuadsPerThread; ++k)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) su[k][e] = sq[k][e] = 0.f;
+  for (long long p = p0 + ty; p < p1; p += TY) {
+    const long long row = (long long)b * a.HW + p;
+#pragma unroll
+    for (int k = 0; k < kGNMaxQuadsPerThread; ++k) {
+      const int qd = tx + k * TX;
+      if (qd < nq) {
+        const int c = qd << 2;
+        const float4 v = c < a.C1 ? *reinterpret_cast<const float4*>(a.x1 + row * a.C1 + c)
+                                  : *reinterpret_cast<const float4*>(a.x2 + row * a.C2 + (c - a.C1));
+        su[k][0] += v.x; sq[k][0] += v.x * v.x;
+        su[k][1] += v.y; sq[k][1] += v.y * v.y;
+        su[k][2] += v.z; sq[k][2] += v.z * v.z;
+        su[k][3] += v.w; sq[k][3] += v.w * v.w;
+      }
     }
-    ssum[c] = su;
-    ssq[c] = sq;
+  }
+  float* mysum = sm + (size_t)ty * 2 * a.C;
+#pragma unroll
+  for (int k = 0; k < kGNMaxQuadsPerThread; ++k) {
+    const int qd = tx + k * TX;
+    if (qd < nq) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        mysum[(qd << 2) + e] = su[k][e];
+        mysum[a.C + (qd << 2) + e] = sq[k][e];
+      }
+    }
   }
   __syncthreads();
-  for (int g = threadIdx.x; g < a.G; g += kGNThreads) {
-    double su = 0.0, sq = 0.0;
-    for (int c = g * a.cpg; c < (g + 1) * a.cpg; ++c) {
-      su += (double)ssum[c];
-      sq += (double)ssq[c];
+  for (int g = tid; g < a.G; g += nthr) {
+    double dsu = 0.0, dsq = 0.0;
+    for (int y = 0; y < TY; ++y) {
+      const float* r = sm + (size_t)y * 2 * a.C;
+      for (int c = g * a.cpg; c < (g + 1) * a.cpg; ++c) {
+        dsu += (double)r[c];
+        dsq += (double)r[a.C + c];
+      }
     }
     double* dst = a.partial + (((long long)b * a.S + s) * a.G + g) * 2;
-    dst[0] = su;
-    dst[1] = sq;
+    dst[0] = dsu;
+    dst[1] = dsq;
   }
   __threadfence();
   __syncthreads();
-  if (threadIdx.x == 0) {
+  if (tid == 0) {
     const unsigned int prev = atomicAdd(&a.counters[b], 1u);
     is_last = (prev == (unsigned int)(a.S - 1));
   }
   __syncthreads();
   if (!is_last) return;
   __threadfence();
-  for (int g = threadIdx.x; g < a.G; g += kGNThreads) {
-    double su = 0.0, sq = 0.0;
+  for (int g = tid; g < a.G; g += nthr) {
+    double dsu = 0.0, dsq = 0.0;
     for (int k = 0; k < a.S; ++k) {  // fixed order -> deterministic
       const double* src = a.partial + (((long long)b * a.S + k) * a.G + g) * 2;
-      su += __ldcg(src);
-      sq += __ldcg(src + 1);
+      dsu += __ldcg(src);
+      dsq += __ldcg(src + 1);
     }
     const double n = (double)a.HW * a.cpg;
-    const double mean = su / n;
-    double var = sq / n - mean * mean;
+    const double mean = dsu / n;
+    double var = dsq / n - mean * mean;
     if (var < 0.0) var = 0.0;
     a.stats[((long long)b * a.G + g) * 2 + 0] = (float)mean;
     a.stats[((long long)b * a.G + g) * 2 + 1] = (float)(1.0 / sqrt(var + (double)a.eps));
   }
-  if (threadIdx.x == 0) a.counters[b] = 0;  // re-arm for the next call
+  if (tid == 0) a.counters[b] = 0;  // re-arm for the next call
 }
 
 // grid (ceil(HW / rows_per_cta), B): thread handles 4 consecutive channels
 __global__ void __launch_bounds__(kGNThreads) gn_apply_kernel(GNArgs a, int rows_per_cta) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ float sm[];  // mean[G], rstd[G]
   const int b = blockIdx.y;
   for (int g = threadIdx.x; g < a.G; g += kGNThreads) {
@@ -144,42 +180,56 @@ __global__ void __launch_bounds__(kGNThreads) gn_apply_kernel(GNArgs a, int rows
   }
 }
 
-// one warp per row
+// one warp per row; the row (C <= 2048) is read once into registers (float4 per lane per 128 channels)
+constexpr int kLNMaxVec = 16;
 __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, long long rows, int C, float eps,
                                                         const float* __restrict__ gamma, const float* __restrict__ beta,
                                                         __nv_bfloat16* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
   const float* xr = x + row * C;
+  float4 v[kLNMaxVec];
   float su = 0.f;
-  for (int c = lane * 4; c < C; c += 128) {
-    const float4 v = *reinterpret_cast<const float4*>(xr + c);
-    su += (v.x + v.y) + (v.z + v.w);
+#pragma unroll
+  for (int k = 0; k < kLNMaxVec; ++k) {
+    const int c = lane * 4 + k * 128;
+    if (c < C) {
+      v[k] = *reinterpret_cast<const float4*>(xr + c);
+      su += (v[k].x + v[k].y) + (v[k].z + v[k].w);
+    }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) su += __shfl_xor_sync(0xffffffffu, su, o);
   const float mean = su / (float)C;
   float sq = 0.f;
-  for (int c = lane * 4; c < C; c += 128) {
-    const float4 v = *reinterpret_cast<const float4*>(xr + c);
-    const float d0 = v.x - mean, d1 = v.y - mean, d2 = v.z - mean, d3 = v.w - mean;
-    sq += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
+#pragma unroll
+  for (int k = 0; k < kLNMaxVec; ++k) {
+    const int c = lane * 4 + k * 128;
+    if (c < C) {
+      const float d0 = v[k].x - mean, d1 = v[k].y - mean, d2 = v[k].z - mean, d3 = v[k].w - mean;
+      sq += (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
+    }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
   const float rstd = rsqrtf(sq / (float)C + eps);
   __nv_bfloat16* orow = out + row * C;
-  for (int c = lane * 4; c < C; c += 128) {
-    const float4 v = *reinterpret_cast<const float4*>(xr + c);
-    const float4 g = *reinterpret_cast<const float4*>(gamma + c);
-    const float4 bb = *reinterpret_cast<const float4*>(beta + c);
-    __nv_bfloat162 h0 = __floats2bfloat162_rn((v.x - mean) * rstd * g.x + bb.x, (v.y - mean) * rstd * g.y + bb.y);
-    __nv_bfloat162 h1 = __floats2bfloat162_rn((v.z - mean) * rstd * g.z + bb.z, (v.w - mean) * rstd * g.w + bb.w);
-    uint2 pk;
-    pk.x = *reinterpret_cast<uint32_t*>(&h0);
-    pk.y = *reinterpret_cast<uint32_t*>(&h1);
-    *reinterpret_cast<uint2*>(orow + c) = pk;
+#pragma unroll
+  for (int k = 0; k < kLNMaxVec; ++k) {
+    const int c = lane * 4 + k * 128;
+    if (c < C) {
+      const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c));
+      const float4 bb = __ldg(reinterpret_cast<const float4*>(beta + c));
+      __nv_bfloat162 h0 = __floats2bfloat162_rn((v[k].x - mean) * rstd * g.x + bb.x, (v[k].y - mean) * rstd * g.y + bb.y);
+      __nv_bfloat162 h1 = __floats2bfloat162_rn((v[k].z - mean) * rstd * g.z + bb.z, (v[k].w - mean) * rstd * g.w + bb.w);
+      uint2 pk;
+      pk.x = *reinterpret_cast<uint32_t*>(&h0);
+      pk.y = *reinterpret_cast<uint32_t*>(&h1);
+      *reinterpret_cast<uint2*>(orow + c) = pk;
+    }
   }
 }
 
@@ -212,9 +262,20 @@ extern "C" int ae_groupnorm(const float* x1, int C1, const float* x2, int C2, in
   a.cpg = C / groups;
   a.B = B;
   a.HW = HW;
-  int S = (int)ceil_div64(HW, 16);
+  // thread block: TX channel quads x TY positions (<= 512 threads, <= 4 quads per thread)
+  const int nq = C / 4;
+  int TX = nq < 64 ? nq : 64;
+  while ((nq + TX - 1) / TX > kGNMaxQuadsPerThread) TX *= 2;
+  AE_CHECK_ARG(TX <= 512, "ae_groupnorm: C=%d too wide", C);
+  int TY = 512 / TX;
+  if (TY > 16) TY = 16;
+  if (TY < 1) TY = 1;
+  // position splits: enough CTAs to cover the machine at small batch, never more than kMaxSplits per sample
+  int S = (int)ceil_div64(HW, 4 * TY);
+  const int want = (296 + B - 1) / B;
+  if (S > want) S = want;
   if (S > kMaxSplits) S = kMaxSplits;
-  a.S = S;
+  if (S < 1) S = 1;
   a.chunk = ceil_div64(HW, S);
   a.S = (int)ceil_div64(HW, a.chunk);
   a.eps = eps;
@@ -231,7 +292,16 @@ extern "C" int ae_groupnorm(const float* x1, int C1, const float* x2, int C2, in
   ws += (size_t)B * groups * 2 * 4;
   a.counters = reinterpret_cast<unsigned int*>(ws);
   cudaStream_t st = as_stream(stream);
-  gn_stats_kernel<<<dim3(a.S, B), kGNThreads, 2 * C * sizeof(float), st>>>(a);
+  {
+    const size_t smem = (size_t)TY * 2 * C * sizeof(float);
+    static size_t smem_set = 48 * 1024;
+    if (smem > smem_set) {
+      cudaFuncSetAttribute(gn_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+      smem_set = 160 * 1024;
+    }
+    AE_CHECK_ARG(smem <= 160 * 1024, "ae_groupnorm: C=%d needs too much shared memory", C);
+    launch_kernel(gn_stats_kernel, dim3(a.S, B), dim3(TX, TY), smem, st, a);
+  }
   int rc = launched("ae_groupnorm(stats)");
   if (rc) return rc;
   // ~8 KiB of fp32 per CTA pass keeps the grid >= 2 waves at the U-Net's top level
@@ -239,17 +309,15 @@ extern "C" int ae_groupnorm(const float* x1, int C1, const float* x2, int C2, in
   if (rows_per_cta < 1) rows_per_cta = 1;
   if (rows_per_cta > 64) rows_per_cta = 64;
   rows_per_cta *= 4;
-  gn_apply_kernel<<<dim3((unsigned)ceil_div64(HW, rows_per_cta), B), kGNThreads, 2 * groups * sizeof(float), st>>>(
-      a, rows_per_cta);
+  launch_kernel(gn_apply_kernel, dim3(dim3((unsigned)ceil_div64(HW, rows_per_cta), B)), dim3(kGNThreads), (size_t)(2 * groups * sizeof(float)), st, a, rows_per_cta);
   return launched("ae_groupnorm(apply)");
 }
 
 extern "C" int ae_layernorm(const float* x, int64_t rows, int C, float eps, const float* gamma, const float* beta,
                             void* out_bf16, ae_stream stream) {
   AE_CHECK_ARG(x && gamma && beta && out_bf16 && rows > 0 && C > 0, "ae_layernorm: bad argument");
-  AE_CHECK_ARG(C % 4 == 0, "ae_layernorm: C=%d must be a multiple of 4", C);
+  AE_CHECK_ARG(C % 4 == 0 && C <= 128 * kLNMaxVec, "ae_layernorm: C=%d must be a multiple of 4 and <= 2048", C);
   const int warps = 8;
-  layernorm_kernel<<<(unsigned)ceil_div64(rows, warps), warps * 32, 0, as_stream(stream)>>>(
-      x, rows, C, eps, gamma, beta, reinterpret_cast<__nv_bfloat16*>(out_bf16));
+  launch_kernel(layernorm_kernel, dim3((unsigned)ceil_div64(rows, warps)), dim3(warps * 32), (size_t)(0), as_stream(stream), x, rows, C, eps, gamma, beta, reinterpret_cast<__nv_bfloat16*>(out_bf16));
   return launched("ae_layernorm");
 }

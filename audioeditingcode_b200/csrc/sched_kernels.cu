@@ -175,6 +175,8 @@ __device__ __forceinline__ float dir_coeff(const ae_sched_row& r, float eta) {
 
 __global__ void sample_xts_kernel(const ae_sched_row* __restrict__ rows, int N, const float* __restrict__ x0,
                                   const float* __restrict__ noise, float* __restrict__ xts, int64_t n_el) {
+  pdl_trigger();
+  pdl_wait();
   // grid.y = slot 0..N (slot 0 copies x0); slot s>0 <-> pos = N - s, draw k = N-1-pos = s-1
   const int s = blockIdx.y;
   float a = 1.0f, b = 0.0f;
@@ -210,6 +212,8 @@ struct InvArgs {
 };
 
 __global__ void cfg_inv_step_kernel(InvArgs a) {
+  pdl_trigger();
+  pdl_wait();
   const int j = blockIdx.y;
   const int pos = a.pos0 + j;
   const int idx = a.N - pos - 1;  // inversion_utils.py:75
@@ -262,6 +266,8 @@ struct RevArgs {
 };
 
 __global__ void cfg_rev_step_kernel(RevArgs a) {
+  pdl_trigger();
+  pdl_wait();
   const int pos = a.d_pos ? *a.d_pos : a.pos;
   const ae_sched_row r = a.rows[pos];
   const float c_dir = a.eta_tab ? a.eta_tab[pos] : dir_coeff(r, a.eta);
@@ -299,6 +305,8 @@ __global__ void ddim_step_kernel(const ae_sched_row* __restrict__ rows, int pos,
                                  const float* __restrict__ eps_u, const float* __restrict__ eps_c,
                                  const float* __restrict__ sample, const float* __restrict__ vnoise,
                                  float* __restrict__ prev_out, float* __restrict__ x0_out, int64_t n_el) {
+  pdl_trigger();
+  pdl_wait();
   const ae_sched_row r = rows[pos];
   const float std_t = __fmul_rn(eta, r.sqrt_var);
   const float c_dir = __fsqrt_rn(__fsub_rn(__fsub_rn(1.0f, r.alpha_prod_t_prev), __fmul_rn(std_t, std_t)));
@@ -336,7 +344,7 @@ extern "C" int ae_sample_xts(const ae_sched* s, const float* x0, const float* no
                              ae_stream stream) {
   AE_CHECK_ARG(s && s->d_rows && x0 && noise && xts && n_el > 0, "ae_sample_xts: bad argument");
   dim3 grid(grid_for(n_el, 256, s->N + 1), s->N + 1);
-  sample_xts_kernel<<<grid, 256, 0, as_stream(stream)>>>(s->d_rows, s->N, x0, noise, xts, n_el);
+  launch_kernel(sample_xts_kernel, dim3(grid), dim3(256), (size_t)(0), as_stream(stream), s->d_rows, s->N, x0, noise, xts, n_el);
   return launched("ae_sample_xts");
 }
 
@@ -352,7 +360,7 @@ extern "C" int ae_cfg_inv_step(const ae_sched* s, int pos0, int count, float eta
   InvArgs a{s->has_eta ? s->d_eta : nullptr, s->d_rows, s->N, pos0, s->pred_type, P, numerical_fix, eta, eps_u, ld_eps_u, eps_c, ld_eps_c,
             cfg_map, xt_src, xts, zs, n_el};
   dim3 grid(grid_for(n_el, 256, count), count);
-  cfg_inv_step_kernel<<<grid, 256, 0, as_stream(stream)>>>(a);
+  launch_kernel(cfg_inv_step_kernel, dim3(grid), dim3(256), (size_t)(0), as_stream(stream), a);
   return launched("ae_cfg_inv_step");
 }
 
@@ -390,7 +398,7 @@ extern "C" int ae_cfg_rev_step(const ae_sched* s, int pos, const int32_t* d_pos,
     a.do_fix = 1;
   }
   a.n_el = n_el;
-  cfg_rev_step_kernel<<<grid_for(n_el, 256, 1), 256, 0, as_stream(stream)>>>(a);
+  launch_kernel(cfg_rev_step_kernel, dim3(grid_for(n_el, 256, 1)), dim3(256), (size_t)(0), as_stream(stream), a);
   return launched("ae_cfg_rev_step");
 }
 
@@ -400,7 +408,7 @@ extern "C" int ae_ddim_step(const ae_sched* s, int pos, float eta, float cfg_sca
   AE_CHECK_ARG(s && s->d_rows && pos >= 0 && pos < s->N, "ae_ddim_step: bad scheduler/position");
   AE_CHECK_ARG(eps_u && sample && prev_sample && n_el > 0, "ae_ddim_step: null pointer");
   AE_CHECK_ARG(eta == 0.0f || vnoise, "ae_ddim_step: eta > 0 needs variance_noise");
-  ddim_step_kernel<<<grid_for(n_el, 256, 1), 256, 0, as_stream(stream)>>>(s->d_rows, pos, s->pred_type, eta, cfg_scale,
+  launch_kernel(ddim_step_kernel, dim3(grid_for(n_el, 256, 1)), dim3(256), (size_t)(0), as_stream(stream), s->d_rows, pos, s->pred_type, eta, cfg_scale,
                                                                           eps_u, eps_c, sample, vnoise, prev_sample,
                                                                           pred_x0, n_el);
   return launched("ae_ddim_step");

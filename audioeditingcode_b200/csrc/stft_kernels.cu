@@ -14,6 +14,8 @@ __global__ void __launch_bounds__(256) stft_mel_kernel(const float* __restrict__
                                                        const float* __restrict__ window,
                                                        const float* __restrict__ mel_basis, int n_mels, int n_frames,
                                                        float* __restrict__ mag_out, float* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ float sm[];
   float* frame = sm;              // [n_fft]
   float* ctab = frame + n_fft;    // [n_fft]
@@ -73,7 +75,7 @@ extern "C" int ae_stft_mel(const float* wav, int n_samples, int n_fft, int hop, 
     cudaFuncSetAttribute(stft_mel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
     attr_set = true;
   }
-  stft_mel_kernel<<<n_frames, 256, smem, as_stream(stream)>>>(wav, n_samples, n_fft, hop, window, mel_basis, n_mels,
+  launch_kernel(stft_mel_kernel, dim3(n_frames), dim3(256), (size_t)(smem), as_stream(stream), wav, n_samples, n_fft, hop, window, mel_basis, n_mels,
                                                             n_frames, mag_workspace, out_logmel);
   return launched("ae_stft_mel");
 }

@@ -35,9 +35,21 @@ class CudaOps:
     name = "cuda"
     act_dtype = BF16
 
+    SPLITK_WS_BYTES = 64 << 20
+
     def __init__(self):
         self.lib = _lib.load()
         self._gn_ws = {}
+        self._splitk_ws = {}
+        import os
+        self.lib.ae_set_pdl(0 if os.environ.get("AEDIT_PDL", "1") == "0" else 1)
+
+    def _splitk_workspace(self, device):
+        ws = self._splitk_ws.get(str(device))
+        if ws is None:
+            ws = torch.empty(self.SPLITK_WS_BYTES // 4, dtype=torch.float32, device=device)
+            self._splitk_ws[str(device)] = ws
+        return ws
 
     # ---------------------------------------------------------------- memory
     def empty(self, shape, dtype, device):
@@ -49,7 +61,7 @@ class CudaOps:
     # ---------------------------------------------------------------- GEMM / conv
     def gemm(self, A, W, *, out_f32=None, out_bf16=None, bias=None, rowbias=None, rows_per_group=1, residual=None,
              act=0, alpha=1.0, conv=None, M=None, K=None, force_bn=0, batch=1, strideA=0, strideW=0, stride_out=0,
-             stride_res=0, lda=None, ldw=None):
+             stride_res=0, lda=None, ldw=None, force_split=0):
         """D = alpha*A@W^T (+bias)(+rowbias[row//rows_per_group])(+residual) -> act.  conv=(B,H,W,C,kh,kw,dh,dw)
         turns A (channels-last image) into an implicit-GEMM operand."""
         a = AeGemmArgs()
@@ -89,6 +101,11 @@ class CudaOps:
         a.act = act
         a.alpha = alpha
         a.force_bn = force_bn
+        a.force_split = force_split
+        if batch == 1 and act != 2:
+            ws = self._splitk_workspace(A.device)
+            a.splitk_ws = ws.data_ptr()
+            a.splitk_ws_bytes = ws.numel() * 4
         check(self.lib.ae_gemm(C.byref(a), _stream()), "ae_gemm")
 
     def conv_supported(self, B, H, W, C_) -> bool:

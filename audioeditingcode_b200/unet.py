@@ -86,6 +86,9 @@ class UNetEngine:
         self._pack(weights)
         self._graphs: Dict = {}
         self.kernels_per_forward: Dict = {}
+        import os
+        # below this width the 4-D TMA boxes degenerate into 256-byte bursts; gather patches explicitly instead
+        self.min_implicit_w = int(os.environ.get("AEDIT_MIN_IMPLICIT_W", "4"))
 
     def graphed(self, B, H, W, text=None, slot_map=None, class_labels=None, slot_key=None) -> GraphedForward:
         """Cached CUDA-graph evaluator for this geometry / text binding.  `slot_key`: hashable description of
@@ -131,6 +134,17 @@ class UNetEngine:
         self.temb_total = off
         P["__temb_all.weight"] = self._to(torch.cat(temb_w, 0), self.adt)
         P["__temb_all.bias"] = self._to(torch.cat(temb_b, 0), F32)
+        # GEGLU feed-forward: interleave value / gate rows in blocks of 16 so the GEMM epilogue (act=2) can form
+        # value * gelu(gate) inside one 32-column accumulator chunk (attention.py:37-44 chunk(2) semantics)
+        for name in [k for k in w if k.endswith(".ff.net.0.proj.weight")]:
+            p = name[: -len(".weight")]
+            Wf, bf = w[name], w[p + ".bias"]
+            inner = Wf.shape[0] // 2
+            assert inner % 16 == 0
+            idx = torch.arange(inner).view(-1, 16)
+            perm = torch.cat([idx, idx + inner], dim=1).reshape(-1)
+            P[p + ".geglu.weight"] = self._to(Wf[perm], self.adt)
+            P[p + ".geglu.bias"] = self._to(bf[perm], F32)
         # fused q|k|v (self) and k|v (cross) projections
         for name in [k for k in w if k.endswith(".to_q.weight")]:
             p = name[: -len(".to_q.weight")]
@@ -187,7 +201,7 @@ class UNetEngine:
         """a_bf16: [B,H,W,Cin] channels-last operand; out fp32 [B*H*W, Cout]."""
         ops = self.ops
         Wt, bias = self.w[name + ".weight"], self.w[name + ".bias"]
-        if ops.conv_supported(B, H, W, Cin):
+        if W >= self.min_implicit_w and ops.conv_supported(B, H, W, Cin):
             ops.gemm(a_bf16, Wt, out_f32=out, bias=bias, rowbias=rowbias, rows_per_group=rows_per_group,
                      residual=residual, conv=(B, H, W, Cin, 3, 3, 1, 1))
         else:
@@ -272,10 +286,9 @@ class UNetEngine:
                      residual=hs)
             # --- GEGLU feed-forward
             ops.layernorm(hs, self.w[q + ".norm3.weight"], self.w[q + ".norm3.bias"], n)
-            ff = ops.empty((M, 8 * C), self.adt, self.device)
-            ops.gemm(n, self.w[q + ".ff.net.0.proj.weight"], out_bf16=ff, bias=self.w[q + ".ff.net.0.proj.bias"])
             gg = ops.empty((M, 4 * C), self.adt, self.device)
-            ops.geglu(ff, gg)
+            ops.gemm(n, self.w[q + ".ff.net.0.proj.geglu.weight"], out_bf16=gg,
+                     bias=self.w[q + ".ff.net.0.proj.geglu.bias"], act=2)
             if l == nl - 1:
                 hs_b = ops.empty((M, C), self.adt, self.device)
             ops.gemm(gg, self.w[q + ".ff.net.2.weight"], out_f32=hs, out_bf16=hs_b if l == nl - 1 else None,

@@ -37,6 +37,9 @@ int ae_version(void);
 int64_t ae_launch_count(void);
 /* 1 if the current device is compute capability 10.x */
 int ae_device_ok(void);
+/* Programmatic dependent launch for every kernel of the library (default on): each kernel lets its successor in the
+ * stream start early (prologue overlap) and waits for its predecessor before touching global memory. */
+void ae_set_pdl(int enable);
 
 /* ------------------------------------------------------------------------------------------------
  * Scheduler table  (code/models.py:85-158, :539-549; integer index math of
@@ -134,12 +137,18 @@ typedef struct {
   int64_t ld_out_f32;
   void* out_bf16;
   int64_t ld_out_bf16;
-  int32_t act; /* 0 none, 1 SiLU */
+  int32_t act; /* 0 none, 1 SiLU, 2 GEGLU: W rows interleaved in blocks of 32 (16 value rows, 16 gate rows); the
+                  output has N/2 columns: out[16q+i] = acc[32q+i] * gelu(acc[32q+16+i])   (attention.py:37-44) */
   float alpha;
   /* implicit convolution */
   int32_t conv;
   int32_t B, H, W_, C, kh, kw, dil_h, dil_w;
   int32_t force_bn; /* 0 = auto tile width, else 32/64/128 */
+  /* split-K (small-M layers): fp32 partial tiles go to this workspace, a second kernel reduces them in fixed order
+   * and applies the epilogue.  NULL = never split.  force_split: 0 auto, 1 never, >1 exactly that many K slices. */
+  float* splitk_ws;
+  int64_t splitk_ws_bytes;
+  int32_t force_split;
 } ae_gemm_args;
 int ae_gemm(const ae_gemm_args*, ae_stream stream);
 /* 1 if the implicit-conv fast path supports this geometry (else use ae_im2col + plain GEMM) */

@@ -49,6 +49,49 @@ def test_gemm_plain(ops, M, N, K, bn):
     assert relerr(o32, F.silu(A.float() @ W.float().t())) < 2e-5
 
 
+@pytest.mark.parametrize("M,N,K,S", [(128, 960, 8640, 0), (128, 960, 8640, 9), (256, 576, 5184, 4), (100, 200, 1000, 3),
+                                     (128, 7680, 960, 0)])
+def test_gemm_splitk(ops, M, N, K, S):
+    """split-K (fp32 partials + fixed-order reduce kernel) gives the same result as the single-pass kernel up to
+    fp32 summation order, with every epilogue term applied exactly once."""
+    A = rnd((M, K), 1, dtype=BF)
+    W = rnd((N, K), 2, 1 / math.sqrt(K), dtype=BF)
+    bias, res = rnd((N,), 3), rnd((M, N), 4)
+    rowbias = rnd(((M + 63) // 64, N), 5)
+    o32 = torch.empty(M, N, device="cuda")
+    o16 = torch.empty(M, N, device="cuda", dtype=BF)
+    ops.gemm(A, W, out_f32=o32, out_bf16=o16, bias=bias, rowbias=rowbias, rows_per_group=64, residual=res, act=1,
+             alpha=0.5, force_split=S)
+    ref = F.silu(0.5 * (A.float() @ W.float().t()) + bias + res + rowbias.repeat_interleave(64, 0)[:M])
+    assert relerr(o32, ref) < 2e-5
+    assert relerr(o16, ref) < 4e-3
+    o_ns = torch.empty_like(o32)
+    ops.gemm(A, W, out_f32=o_ns, bias=bias, rowbias=rowbias, rows_per_group=64, residual=res, act=1, alpha=0.5,
+             force_split=1)
+    assert relerr(o32, o_ns) < 1e-5
+    # determinism: same call, same bits
+    o_b = torch.empty_like(o32)
+    ops.gemm(A, W, out_f32=o_b, bias=bias, rowbias=rowbias, rows_per_group=64, residual=res, act=1, alpha=0.5,
+             force_split=S)
+    assert torch.equal(o32, o_b)
+
+
+@pytest.mark.parametrize("M,C", [(300, 64), (4096, 192), (128, 960)])
+def test_gemm_geglu_epilogue(ops, M, C):
+    """FF1 + GEGLU fused (act=2, interleaved weight rows) == chunk(2) -> value * gelu(gate) (attention.py:37-44)."""
+    inner = 4 * C
+    x = rnd((M, C), 1, dtype=BF)
+    Wf = rnd((2 * inner, C), 2, 1 / math.sqrt(C), dtype=BF)
+    bf = rnd((2 * inner,), 3)
+    idx = torch.arange(inner).view(-1, 16)
+    perm = torch.cat([idx, idx + inner], 1).reshape(-1).cuda()
+    out = torch.empty(M, inner, device="cuda", dtype=BF)
+    ops.gemm(x, Wf[perm].contiguous(), out_bf16=out, bias=bf[perm].contiguous(), act=2)
+    h = x.float() @ Wf.float().t() + bf
+    a, g = h.chunk(2, -1)
+    assert relerr(out, a * F.gelu(g)) < 4e-3
+
+
 def test_gemm_batched(ops):
     Bz, M, N, K = 3, 200, 96, 160
     A = rnd((Bz, M, K), 1, dtype=BF)

@@ -54,6 +54,9 @@ class TorchOps:
             acc = acc + residual.reshape(acc.shape)
         if act == 1:
             acc = F.silu(acc)
+        elif act == 2:
+            a3 = acc.reshape(acc.shape[0], -1, 2, 16)
+            acc = (a3[:, :, 0] * F.gelu(a3[:, :, 1])).reshape(acc.shape[0], -1)
         if out_f32 is not None:
             out_f32.reshape(acc.shape).copy_(acc) if out_f32.is_contiguous() else out_f32.copy_(acc)
         if out_bf16 is not None:
