@@ -27,7 +27,7 @@ class AeGemmArgs(C.Structure):
                 ("out_f32", vp), ("ld_out_f32", i64), ("out_bf16", vp), ("ld_out_bf16", i64), ("act", i32),
                 ("alpha", f32), ("conv", i32), ("B", i32), ("H", i32), ("W_", i32), ("C", i32), ("kh", i32),
                 ("kw", i32), ("dil_h", i32), ("dil_w", i32), ("force_bn", i32), ("splitk_ws", vp), ("splitk_ws_bytes", i64),
-                ("force_split", i32)]
+                ("force_split", i32), ("force_stages", i32)]
 
 
 _SIGS = {
@@ -65,7 +65,7 @@ _SIGS = {
     "ae_softmax_rows": (i32, [vp, i64, i32, i64, vp, i64, vp]),
     "ae_transpose_bf16": (i32, [vp, i32, i32, i32, vp, vp]),
     "ae_stft_mel": (i32, [vp, i32, i32, i32, vp, vp, i32, i32, vp, vp, vp]),
-    "ae_leaky_relu_bf16": (i32, [vp, i64, f32, vp, vp]),
+    "ae_leaky_relu_bf16": (i32, [vp, i64, f32, f32, vp, vp]),
     "ae_tanh_f32": (i32, [vp, i64, vp, vp]),
 }
 

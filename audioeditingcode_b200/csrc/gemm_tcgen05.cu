@@ -27,14 +27,13 @@
 #include "ptx.cuh"
 
 namespace aedit {
-int g_use_pdl = 1;
+int g_use_pdl = 0;
 namespace {
 
 constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int kThreads = 192;
 constexpr int kATileBytes = BM * BK * 2;  // 16 KiB
-constexpr int kStages = 3;
 
 struct GemmDev {
   int M, N;
@@ -59,21 +58,22 @@ struct GemmDev {
   float alpha;
 };
 
-template <int BN>
+// STAGES = 3: 2-3 CTAs per SM (large grids: one CTA's epilogue overlaps another's main loop).
+// STAGES = 6: grids that cannot fill the machine anyway (one CTA per SM) need the deeper ring to cover TMA latency.
+template <int BN, int STAGES>
 struct SmemLayout {
   static constexpr int kBTileBytes = BN * BK * 2;
   static constexpr int kStageBytes = kATileBytes + kBTileBytes;
   static constexpr int kBarBytes = 128;
-  static constexpr int kTotal = kStages * kStageBytes + kBarBytes + 1024;  // +1024 manual alignment slack
+  static constexpr int kTotal = STAGES * kStageBytes + kBarBytes + 1024;  // +1024 manual alignment slack
 };
 
 __device__ __forceinline__ float gelu_erf_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 
-template <int BN>
+template <int BN, int STAGES>
 __global__ void __launch_bounds__(kThreads)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmDev p) {
-  using L = SmemLayout<BN>;
-  constexpr int STAGES = kStages;
+  using L = SmemLayout<BN, STAGES>;
   constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
   extern __shared__ uint8_t smem_raw[];
   pdl_trigger();
@@ -427,17 +427,17 @@ bool conv_box(int B, int H, int W, ConvBox* bx) {
   return true;
 }
 
-template <int BN>
+template <int BN, int STAGES>
 int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmDev& p, int gz, cudaStream_t st) {
-  using L = SmemLayout<BN>;
+  using L = SmemLayout<BN, STAGES>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
     if (e != cudaSuccess) return fail(AE_ECUDA, "cudaFuncSetAttribute(smem=%d): %s", L::kTotal, cudaGetErrorString(e));
     attr_set = true;
   }
   dim3 grid((p.M + BM - 1) / BM, (p.N + BN - 1) / BN, gz);
-  cudaError_t e = launch_kernel(gemm_tcgen05_kernel<BN>, grid, dim3(kThreads), (size_t)L::kTotal, st, tmA, tmB, p);
+  cudaError_t e = launch_kernel(gemm_tcgen05_kernel<BN, STAGES>, grid, dim3(kThreads), (size_t)L::kTotal, st, tmA, tmB, p);
   if (e != cudaSuccess) return fail(AE_ECUDA, "ae_gemm launch: %s", cudaGetErrorString(e));
   return launched("ae_gemm");
 }
@@ -543,9 +543,9 @@ extern "C" int ae_gemm(const ae_gemm_args* a, ae_stream stream) {
   if (batch == 1 && a->act != 2 && a->splitk_ws && a->N % 4 == 0 && a->force_split != 1) {
     if (a->force_split > 1)
       S = a->force_split;
-    else if (tiles <= 48 && p.num_kblocks >= 8) {
+    else if (tiles <= 48 && p.num_kblocks >= 12) {
       S = (int)(148 / tiles);
-      const int max_by_k = p.num_kblocks / 4;
+      const int max_by_k = p.num_kblocks / 6;
       if (S > max_by_k) S = max_by_k;
       if (S > 32) S = 32;
     }
@@ -578,15 +578,17 @@ extern "C" int ae_gemm(const ae_gemm_args* a, ae_stream stream) {
     q.act = 0;
     q.alpha = 1.0f;
   }
+  const long long ctas = tiles * gz;
+  const bool deep = a->force_stages ? (a->force_stages > 3) : (ctas <= 160);
   switch (bn) {
     case 32:
-      rc = launch<32>(tmA, tmB, q, gz, st);
+      rc = deep ? launch<32, 6>(tmA, tmB, q, gz, st) : launch<32, 3>(tmA, tmB, q, gz, st);
       break;
     case 64:
-      rc = launch<64>(tmA, tmB, q, gz, st);
+      rc = deep ? launch<64, 6>(tmA, tmB, q, gz, st) : launch<64, 3>(tmA, tmB, q, gz, st);
       break;
     default:
-      rc = launch<128>(tmA, tmB, q, gz, st);
+      rc = deep ? launch<128, 6>(tmA, tmB, q, gz, st) : launch<128, 3>(tmA, tmB, q, gz, st);
       break;
   }
   if (rc || S == 1) return rc;

@@ -168,12 +168,12 @@ __global__ void add_f32_kernel(const float* __restrict__ a, const float* __restr
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     out[i] = a[i] + sb * b[i];
 }
-__global__ void leaky_relu_bf16_kernel(const float* __restrict__ x, long long n, float slope,
+__global__ void leaky_relu_bf16_kernel(const float* __restrict__ x, long long n, float scale, float slope,
                                        __nv_bfloat16* __restrict__ out) {
   pdl_trigger();
   pdl_wait();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const float v = x[i];
+    const float v = x[i] * scale;
     out[i] = __float2bfloat16_rn(v > 0.f ? v : v * slope);
   }
 }
@@ -314,9 +314,9 @@ extern "C" int ae_add_f32(const float* a, const float* b, float scale_b, int64_t
   return launched("ae_add_f32");
 }
 
-extern "C" int ae_leaky_relu_bf16(const float* x, int64_t n, float slope, void* out_bf16, ae_stream stream) {
+extern "C" int ae_leaky_relu_bf16(const float* x, int64_t n, float scale, float slope, void* out_bf16, ae_stream stream) {
   AE_CHECK_ARG(x && out_bf16 && n > 0, "ae_leaky_relu_bf16: bad argument");
-  launch_kernel(leaky_relu_bf16_kernel, dim3(ew_grid(n, 256)), dim3(256), (size_t)(0), as_stream(stream), x, n, slope,
+  launch_kernel(leaky_relu_bf16_kernel, dim3(ew_grid(n, 256)), dim3(256), (size_t)(0), as_stream(stream), x, n, scale, slope,
                                                                          reinterpret_cast<__nv_bfloat16*>(out_bf16));
   return launched("ae_leaky_relu_bf16");
 }

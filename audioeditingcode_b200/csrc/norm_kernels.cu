@@ -110,25 +110,37 @@ __global__ void __launch_bounds__(512) gn_stats_kernel(GNArgs a) {
   __syncthreads();
   if (!is_last) return;
   __threadfence();
-  for (int g = tid; g < a.G; g += nthr) {
-    double dsu = 0.0, dsq = 0.0;
-    for (int k = 0; k < a.S; ++k) {  // fixed order -> deterministic
-      const double* src = a.partial + (((long long)b * a.S + k) * a.G + g) * 2;
-      dsu += __ldcg(src);
-      dsq += __ldcg(src + 1);
+  {
+    // one warp per group; lane k holds partials k, k+32 (S <= 64); fixed-shape shuffle tree -> deterministic
+    const int lane = tid & 31, wid = tid >> 5, nw = nthr >> 5;
+    for (int g = wid; g < a.G; g += nw) {
+      double dsu = 0.0, dsq = 0.0;
+      for (int k = lane; k < a.S; k += 32) {
+        const double* src = a.partial + (((long long)b * a.S + k) * a.G + g) * 2;
+        dsu += __ldcg(src);
+        dsq += __ldcg(src + 1);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        dsu += __shfl_down_sync(0xffffffffu, dsu, o);
+        dsq += __shfl_down_sync(0xffffffffu, dsq, o);
+      }
+      if (lane == 0) {
+        const double n = (double)a.HW * a.cpg;
+        const double mean = dsu / n;
+        double var = dsq / n - mean * mean;
+        if (var < 0.0) var = 0.0;
+        a.stats[((long long)b * a.G + g) * 2 + 0] = (float)mean;
+        a.stats[((long long)b * a.G + g) * 2 + 1] = (float)(1.0 / sqrt(var + (double)a.eps));
+      }
     }
-    const double n = (double)a.HW * a.cpg;
-    const double mean = dsu / n;
-    double var = dsq / n - mean * mean;
-    if (var < 0.0) var = 0.0;
-    a.stats[((long long)b * a.G + g) * 2 + 0] = (float)mean;
-    a.stats[((long long)b * a.G + g) * 2 + 1] = (float)(1.0 / sqrt(var + (double)a.eps));
   }
   if (tid == 0) a.counters[b] = 0;  // re-arm for the next call
 }
 
-// grid (ceil(HW / rows_per_cta), B): thread handles 4 consecutive channels
-__global__ void __launch_bounds__(kGNThreads) gn_apply_kernel(GNArgs a, int rows_per_cta) {
+// grid (ceil(HW*C/4 / (256*kGNItems)), B): each thread normalises kGNItems float4 items (coalesced along channels)
+constexpr int kGNItems = 2;
+__global__ void __launch_bounds__(kGNThreads) gn_apply_kernel(GNArgs a) {
   pdl_trigger();
   pdl_wait();
   extern __shared__ float sm[];  // mean[G], rstd[G]
@@ -139,25 +151,37 @@ __global__ void __launch_bounds__(kGNThreads) gn_apply_kernel(GNArgs a, int rows
   }
   __syncthreads();
   const int vec_per_row = a.C >> 2;
-  const long long p0 = (long long)blockIdx.x * rows_per_cta;
-  const long long p1 = min(a.HW, p0 + rows_per_cta);
-  const long long total = (p1 - p0) * vec_per_row;
-  for (long long i = threadIdx.x; i < total; i += kGNThreads) {
-    const long long p = p0 + i / vec_per_row;
-    const int c = (int)(i % vec_per_row) << 2;
+  const long long total = a.HW * vec_per_row;
+  const long long base = (long long)blockIdx.x * (kGNThreads * kGNItems) + threadIdx.x;
+  float4 v[kGNItems];
+  long long idx[kGNItems];
+#pragma unroll
+  for (int it = 0; it < kGNItems; ++it) {
+    idx[it] = base + (long long)it * kGNThreads;
+    if (idx[it] < total) {
+      const long long p = idx[it] / vec_per_row;
+      const int c = (int)(idx[it] - p * vec_per_row) << 2;
+      const long long row = (long long)b * a.HW + p;
+      v[it] = c < a.C1 ? *reinterpret_cast<const float4*>(a.x1 + row * a.C1 + c)
+                       : *reinterpret_cast<const float4*>(a.x2 + row * a.C2 + (c - a.C1));
+    }
+  }
+#pragma unroll
+  for (int it = 0; it < kGNItems; ++it) {
+    if (idx[it] >= total) continue;
+    const long long p = idx[it] / vec_per_row;
+    const int c = (int)(idx[it] - p * vec_per_row) << 2;
     const long long row = (long long)b * a.HW + p;
-    float4 v;
-    if (c < a.C1)
-      v = *reinterpret_cast<const float4*>(a.x1 + row * a.C1 + c);
-    else
-      v = *reinterpret_cast<const float4*>(a.x2 + row * a.C2 + (c - a.C1));
-    const float in[4] = {v.x, v.y, v.z, v.w};
+    const float in[4] = {v[it].x, v[it].y, v[it].z, v[it].w};
+    const float4 gm = __ldg(reinterpret_cast<const float4*>(a.gamma + c));
+    const float4 bt = __ldg(reinterpret_cast<const float4*>(a.beta + c));
+    const float gmv[4] = {gm.x, gm.y, gm.z, gm.w}, btv[4] = {bt.x, bt.y, bt.z, bt.w};
     float o[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const int g = (c + k) / a.cpg;
       float y = (in[k] - sm[g]) * sm[a.G + g];
-      y = y * __ldg(a.gamma + c + k) + __ldg(a.beta + c + k);
+      y = y * gmv[k] + btv[k];
       if (a.silu) y = silu_f(y);
       o[k] = y;
     }
@@ -176,12 +200,12 @@ __global__ void __launch_bounds__(kGNThreads) gn_apply_kernel(GNArgs a, int rows
       rk.y = *reinterpret_cast<uint32_t*>(&r1);
       *reinterpret_cast<uint2*>(a.raw_out + off) = rk;
     }
-    if (a.cat_out) *reinterpret_cast<float4*>(a.cat_out + off) = v;
+    if (a.cat_out) *reinterpret_cast<float4*>(a.cat_out + off) = v[it];
   }
 }
 
-// one warp per row; the row (C <= 2048) is read once into registers (float4 per lane per 128 channels)
-constexpr int kLNMaxVec = 16;
+// one warp per row; the row is read once into registers: NV float4 per lane (C <= 128*NV), NV a template constant
+template <int NV>
 __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, long long rows, int C, float eps,
                                                         const float* __restrict__ gamma, const float* __restrict__ beta,
                                                         __nv_bfloat16* __restrict__ out) {
@@ -191,22 +215,20 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
   const float* xr = x + row * C;
-  float4 v[kLNMaxVec];
+  float4 v[NV];
   float su = 0.f;
 #pragma unroll
-  for (int k = 0; k < kLNMaxVec; ++k) {
+  for (int k = 0; k < NV; ++k) {
     const int c = lane * 4 + k * 128;
-    if (c < C) {
-      v[k] = *reinterpret_cast<const float4*>(xr + c);
-      su += (v[k].x + v[k].y) + (v[k].z + v[k].w);
-    }
+    v[k] = c < C ? *reinterpret_cast<const float4*>(xr + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    su += (v[k].x + v[k].y) + (v[k].z + v[k].w);
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) su += __shfl_xor_sync(0xffffffffu, su, o);
   const float mean = su / (float)C;
   float sq = 0.f;
 #pragma unroll
-  for (int k = 0; k < kLNMaxVec; ++k) {
+  for (int k = 0; k < NV; ++k) {
     const int c = lane * 4 + k * 128;
     if (c < C) {
       const float d0 = v[k].x - mean, d1 = v[k].y - mean, d2 = v[k].z - mean, d3 = v[k].w - mean;
@@ -218,7 +240,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
   const float rstd = rsqrtf(sq / (float)C + eps);
   __nv_bfloat16* orow = out + row * C;
 #pragma unroll
-  for (int k = 0; k < kLNMaxVec; ++k) {
+  for (int k = 0; k < NV; ++k) {
     const int c = lane * 4 + k * 128;
     if (c < C) {
       const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c));
@@ -231,6 +253,14 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
       *reinterpret_cast<uint2*>(orow + c) = pk;
     }
   }
+}
+
+template <int NV>
+cudaError_t launch_ln(const float* x, long long rows, int C, float eps, const float* gamma, const float* beta,
+                      __nv_bfloat16* out, cudaStream_t st) {
+  const int warps = 4;  // small CTAs: more of them, shorter tails
+  return launch_kernel(layernorm_kernel<NV>, dim3((unsigned)ceil_div64(rows, warps)), dim3(warps * 32), (size_t)0, st, x,
+                       rows, C, eps, gamma, beta, out);
 }
 
 }  // namespace
@@ -304,20 +334,32 @@ extern "C" int ae_groupnorm(const float* x1, int C1, const float* x2, int C2, in
   }
   int rc = launched("ae_groupnorm(stats)");
   if (rc) return rc;
-  // ~8 KiB of fp32 per CTA pass keeps the grid >= 2 waves at the U-Net's top level
-  int rows_per_cta = (int)(2048 / C);
-  if (rows_per_cta < 1) rows_per_cta = 1;
-  if (rows_per_cta > 64) rows_per_cta = 64;
-  rows_per_cta *= 4;
-  launch_kernel(gn_apply_kernel, dim3(dim3((unsigned)ceil_div64(HW, rows_per_cta), B)), dim3(kGNThreads), (size_t)(2 * groups * sizeof(float)), st, a, rows_per_cta);
+  {
+    const long long items = HW * (C / 4);
+    const unsigned gx = (unsigned)ceil_div64(items, (long long)kGNThreads * kGNItems);
+    launch_kernel(gn_apply_kernel, dim3(gx, B), dim3(kGNThreads), (size_t)(2 * groups * sizeof(float)), st, a);
+  }
   return launched("ae_groupnorm(apply)");
 }
 
 extern "C" int ae_layernorm(const float* x, int64_t rows, int C, float eps, const float* gamma, const float* beta,
                             void* out_bf16, ae_stream stream) {
   AE_CHECK_ARG(x && gamma && beta && out_bf16 && rows > 0 && C > 0, "ae_layernorm: bad argument");
-  AE_CHECK_ARG(C % 4 == 0 && C <= 128 * kLNMaxVec, "ae_layernorm: C=%d must be a multiple of 4 and <= 2048", C);
-  const int warps = 8;
-  launch_kernel(layernorm_kernel, dim3((unsigned)ceil_div64(rows, warps)), dim3(warps * 32), (size_t)(0), as_stream(stream), x, rows, C, eps, gamma, beta, reinterpret_cast<__nv_bfloat16*>(out_bf16));
+  AE_CHECK_ARG(C % 4 == 0 && C <= 2048, "ae_layernorm: C=%d must be a multiple of 4 and <= 2048", C);
+  __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out_bf16);
+  cudaStream_t st = as_stream(stream);
+  const int nv = (C + 127) / 128;
+  cudaError_t e;
+  if (nv <= 1) e = launch_ln<1>(x, rows, C, eps, gamma, beta, o, st);
+  else if (nv <= 2) e = launch_ln<2>(x, rows, C, eps, gamma, beta, o, st);
+  else if (nv <= 3) e = launch_ln<3>(x, rows, C, eps, gamma, beta, o, st);
+  else if (nv <= 4) e = launch_ln<4>(x, rows, C, eps, gamma, beta, o, st);
+  else if (nv <= 5) e = launch_ln<5>(x, rows, C, eps, gamma, beta, o, st);
+  else if (nv <= 6) e = launch_ln<6>(x, rows, C, eps, gamma, beta, o, st);
+  else if (nv <= 8) e = launch_ln<8>(x, rows, C, eps, gamma, beta, o, st);
+  else if (nv <= 10) e = launch_ln<10>(x, rows, C, eps, gamma, beta, o, st);
+  else if (nv <= 12) e = launch_ln<12>(x, rows, C, eps, gamma, beta, o, st);
+  else e = launch_ln<16>(x, rows, C, eps, gamma, beta, o, st);
+  if (e != cudaSuccess) return fail(AE_ECUDA, "ae_layernorm launch: %s", cudaGetErrorString(e));
   return launched("ae_layernorm");
 }

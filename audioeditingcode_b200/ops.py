@@ -42,7 +42,8 @@ class CudaOps:
         self._gn_ws = {}
         self._splitk_ws = {}
         import os
-        self.lib.ae_set_pdl(0 if os.environ.get("AEDIT_PDL", "1") == "0" else 1)
+        # programmatic dependent launch measured slower end to end on B200 (profiles/r01_*): opt-in only
+        self.lib.ae_set_pdl(1 if os.environ.get("AEDIT_PDL", "0") == "1" else 0)
 
     def _splitk_workspace(self, device):
         ws = self._splitk_ws.get(str(device))
@@ -61,7 +62,7 @@ class CudaOps:
     # ---------------------------------------------------------------- GEMM / conv
     def gemm(self, A, W, *, out_f32=None, out_bf16=None, bias=None, rowbias=None, rows_per_group=1, residual=None,
              act=0, alpha=1.0, conv=None, M=None, K=None, force_bn=0, batch=1, strideA=0, strideW=0, stride_out=0,
-             stride_res=0, lda=None, ldw=None, force_split=0):
+             stride_res=0, lda=None, ldw=None, force_split=0, ld_out_f32=None, ld_out_bf16=None, force_stages=0):
         """D = alpha*A@W^T (+bias)(+rowbias[row//rows_per_group])(+residual) -> act.  conv=(B,H,W,C,kh,kw,dh,dw)
         turns A (channels-last image) into an implicit-GEMM operand."""
         a = AeGemmArgs()
@@ -94,14 +95,15 @@ class CudaOps:
             a.ld_res = residual.stride(-2)
         if out_f32 is not None:
             a.out_f32 = out_f32.data_ptr()
-            a.ld_out_f32 = out_f32.stride(-2)
+            a.ld_out_f32 = int(ld_out_f32 if ld_out_f32 is not None else out_f32.stride(-2))
         if out_bf16 is not None:
             a.out_bf16 = out_bf16.data_ptr()
-            a.ld_out_bf16 = out_bf16.stride(-2)
+            a.ld_out_bf16 = int(ld_out_bf16 if ld_out_bf16 is not None else out_bf16.stride(-2))
         a.act = act
         a.alpha = alpha
         a.force_bn = force_bn
         a.force_split = force_split
+        a.force_stages = force_stages
         if batch == 1 and act != 2:
             ws = self._splitk_workspace(A.device)
             a.splitk_ws = ws.data_ptr()
@@ -178,8 +180,8 @@ class CudaOps:
         b = x.numel() // (x.shape[-1] * x.shape[-2])
         check(self.lib.ae_transpose_bf16(_p(x), b, x.shape[-2], x.shape[-1], _p(out), _stream()), "ae_transpose_bf16")
 
-    def leaky_relu_bf16(self, x, slope, out):
-        check(self.lib.ae_leaky_relu_bf16(_p(x), x.numel(), slope, _p(out), _stream()), "ae_leaky_relu_bf16")
+    def leaky_relu_bf16(self, x, slope, out, scale=1.0):
+        check(self.lib.ae_leaky_relu_bf16(_p(x), x.numel(), scale, slope, _p(out), _stream()), "ae_leaky_relu_bf16")
 
     def tanh(self, x, out):
         check(self.lib.ae_tanh_f32(_p(x), x.numel(), _p(out), _stream()), "ae_tanh_f32")

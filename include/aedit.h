@@ -149,6 +149,7 @@ typedef struct {
   float* splitk_ws;
   int64_t splitk_ws_bytes;
   int32_t force_split;
+  int32_t force_stages; /* 0 auto (deep 6-stage ring for grids <= 160 CTAs, else 3 stages x 2-3 CTAs/SM), 3 or 6 */
 } ae_gemm_args;
 int ae_gemm(const ae_gemm_args*, ae_stream stream);
 /* 1 if the implicit-conv fast path supports this geometry (else use ae_im2col + plain GEMM) */
@@ -211,7 +212,8 @@ int ae_stft_mel(const float* wav, int n_samples, int n_fft, int hop, const float
                 int n_mels, int n_frames, float* mag_workspace, float* out_logmel, ae_stream stream);
 
 /* 1-D ops of the HiFi-GAN vocoder (code/audioldm/hifigan/models.py:20-165), channels-last [B,T,C] fp32 */
-int ae_leaky_relu_bf16(const float* x, int64_t n, float slope, void* out_bf16, ae_stream stream);
+/* out = leaky_relu(scale * x, slope) as bf16 (scale carries the 1/num_kernels of the MRF average, models.py:160) */
+int ae_leaky_relu_bf16(const float* x, int64_t n, float scale, float slope, void* out_bf16, ae_stream stream);
 int ae_tanh_f32(const float* x, int64_t n, float* out, ae_stream stream);
 
 #ifdef __cplusplus
