@@ -34,6 +34,49 @@ __global__ void im2col_kernel(const T* __restrict__ in, int B, int H, int W, int
   }
 }
 
+// vectorised variant (C % 8 == 0): one item = 8 consecutive channels of one tap of one output position
+template <typename T>
+__global__ void __launch_bounds__(256) im2col_vec8_kernel(const T* __restrict__ in, int B, int H, int W, int C, int kh,
+                                                          int kw, int stride, int dil, int pad_t, int pad_l, int Ho,
+                                                          int Wo, __nv_bfloat16* __restrict__ out, long long ld_out,
+                                                          long long M) {
+  pdl_trigger();
+  pdl_wait();
+  const int kv = (int)(ld_out >> 3);
+  const int K = kh * kw * C;
+  const long long total = M * kv;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long m = i / kv;
+    const int k = (int)(i - m * kv) << 3;
+    uint4 o = make_uint4(0u, 0u, 0u, 0u);
+    if (k < K) {
+      const int wo = (int)(m % Wo);
+      const int ho = (int)((m / Wo) % Ho);
+      const int b = (int)(m / ((long long)Wo * Ho));
+      const int tap = k / C, c = k - tap * C;
+      const int j = tap % kw, ii = tap / kw;
+      const int h = ho * stride - pad_t + ii * dil;
+      const int w = wo * stride - pad_l + j * dil;
+      if (h >= 0 && h < H && w >= 0 && w < W) {
+        const T* src = in + (((long long)b * H + h) * W + w) * C + c;
+        if constexpr (sizeof(T) == 2) {
+          o = *reinterpret_cast<const uint4*>(src);
+        } else {
+          const float4 f0 = *reinterpret_cast<const float4*>(src);
+          const float4 f1 = *reinterpret_cast<const float4*>(src + 4);
+          __nv_bfloat162 h0 = __floats2bfloat162_rn(f0.x, f0.y), h1 = __floats2bfloat162_rn(f0.z, f0.w);
+          __nv_bfloat162 h2 = __floats2bfloat162_rn(f1.x, f1.y), h3 = __floats2bfloat162_rn(f1.z, f1.w);
+          o.x = *reinterpret_cast<uint32_t*>(&h0);
+          o.y = *reinterpret_cast<uint32_t*>(&h1);
+          o.z = *reinterpret_cast<uint32_t*>(&h2);
+          o.w = *reinterpret_cast<uint32_t*>(&h3);
+        }
+      }
+    }
+    *reinterpret_cast<uint4*>(out + m * ld_out + k) = o;
+  }
+}
+
 // ------------------------------------------------------------------ GEGLU
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 
@@ -252,6 +295,23 @@ extern "C" int ae_im2col(const void* in, int in_is_bf16, int B, int H, int W, in
   AE_CHECK_ARG(ld_out >= (int64_t)kh * kw * C, "ae_im2col: ld_out too small");
   const long long M = (long long)B * Ho * Wo;
   AE_CHECK_ARG(M > 0 && M < 2147483647LL, "ae_im2col: bad output size");
+  if (C % 8 == 0 && ld_out % 8 == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0 &&
+      (reinterpret_cast<uintptr_t>(out_bf16) & 15) == 0) {
+    const long long items = M * (ld_out / 8);
+    long long blocks = ceil_div64(items, 256);
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    cudaError_t e;
+    if (in_is_bf16)
+      e = launch_kernel(im2col_vec8_kernel<__nv_bfloat16>, dim3((unsigned)blocks), dim3(256), (size_t)0, as_stream(stream),
+                        reinterpret_cast<const __nv_bfloat16*>(in), B, H, W, C, kh, kw, stride, dil, pad_t, pad_l, Ho, Wo,
+                        reinterpret_cast<__nv_bfloat16*>(out_bf16), (long long)ld_out, M);
+    else
+      e = launch_kernel(im2col_vec8_kernel<float>, dim3((unsigned)blocks), dim3(256), (size_t)0, as_stream(stream),
+                        reinterpret_cast<const float*>(in), B, H, W, C, kh, kw, stride, dil, pad_t, pad_l, Ho, Wo,
+                        reinterpret_cast<__nv_bfloat16*>(out_bf16), (long long)ld_out, M);
+    if (e != cudaSuccess) return fail(AE_ECUDA, "ae_im2col launch: %s", cudaGetErrorString(e));
+    return launched("ae_im2col");
+  }
   const int threads = ld_out >= 256 ? 256 : 128;
   if (in_is_bf16)
     launch_kernel(im2col_kernel<__nv_bfloat16>, dim3((unsigned)M), dim3(threads), (size_t)(0), as_stream(stream), reinterpret_cast<const __nv_bfloat16*>(in), B, H, W, C, kh, kw, stride, dil, pad_t, pad_l, Ho, Wo,

@@ -11,7 +11,7 @@ namespace aedit {
 namespace {
 
 constexpr int kGNThreads = 256;
-constexpr int kMaxSplits = 64;
+constexpr int kMaxSplits = 16;
 
 struct GNArgs {
   const float* x1;
@@ -46,7 +46,6 @@ __global__ void __launch_bounds__(512) gn_stats_kernel(GNArgs a) {
   pdl_trigger();
   pdl_wait();
   extern __shared__ float sm[];  // [TY][2*C] per-channel sum / sumsq per ty
-  __shared__ bool is_last;
   const int s = blockIdx.x, b = blockIdx.y;
   const int TX = blockDim.x, TY = blockDim.y;
   const int tx = threadIdx.x, ty = threadIdx.y;
@@ -101,41 +100,6 @@ __global__ void __launch_bounds__(512) gn_stats_kernel(GNArgs a) {
     dst[0] = dsu;
     dst[1] = dsq;
   }
-  __threadfence();
-  __syncthreads();
-  if (tid == 0) {
-    const unsigned int prev = atomicAdd(&a.counters[b], 1u);
-    is_last = (prev == (unsigned int)(a.S - 1));
-  }
-  __syncthreads();
-  if (!is_last) return;
-  __threadfence();
-  {
-    // one warp per group; lane k holds partials k, k+32 (S <= 64); fixed-shape shuffle tree -> deterministic
-    const int lane = tid & 31, wid = tid >> 5, nw = nthr >> 5;
-    for (int g = wid; g < a.G; g += nw) {
-      double dsu = 0.0, dsq = 0.0;
-      for (int k = lane; k < a.S; k += 32) {
-        const double* src = a.partial + (((long long)b * a.S + k) * a.G + g) * 2;
-        dsu += __ldcg(src);
-        dsq += __ldcg(src + 1);
-      }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        dsu += __shfl_down_sync(0xffffffffu, dsu, o);
-        dsq += __shfl_down_sync(0xffffffffu, dsq, o);
-      }
-      if (lane == 0) {
-        const double n = (double)a.HW * a.cpg;
-        const double mean = dsu / n;
-        double var = dsq / n - mean * mean;
-        if (var < 0.0) var = 0.0;
-        a.stats[((long long)b * a.G + g) * 2 + 0] = (float)mean;
-        a.stats[((long long)b * a.G + g) * 2 + 1] = (float)(1.0 / sqrt(var + (double)a.eps));
-      }
-    }
-  }
-  if (tid == 0) a.counters[b] = 0;  // re-arm for the next call
 }
 
 // grid (ceil(HW*C/4 / (256*kGNItems)), B): each thread normalises kGNItems float4 items (coalesced along channels)
@@ -145,9 +109,21 @@ __global__ void __launch_bounds__(kGNThreads) gn_apply_kernel(GNArgs a) {
   pdl_wait();
   extern __shared__ float sm[];  // mean[G], rstd[G]
   const int b = blockIdx.y;
+  // every CTA finalises the group statistics of its sample from the S partials (fixed order k = 0..S-1, so all
+  // CTAs and all launches agree bit for bit); S*G*2 doubles come from L2
   for (int g = threadIdx.x; g < a.G; g += kGNThreads) {
-    sm[g] = a.stats[((long long)b * a.G + g) * 2];
-    sm[a.G + g] = a.stats[((long long)b * a.G + g) * 2 + 1];
+    double dsu = 0.0, dsq = 0.0;
+    const double* src = a.partial + ((long long)b * a.S * a.G + g) * 2;
+    for (int k = 0; k < a.S; ++k) {
+      dsu += src[(long long)k * a.G * 2];
+      dsq += src[(long long)k * a.G * 2 + 1];
+    }
+    const double n = (double)a.HW * a.cpg;
+    const double mean = dsu / n;
+    double var = dsq / n - mean * mean;
+    if (var < 0.0) var = 0.0;
+    sm[g] = (float)mean;
+    sm[a.G + g] = (float)(1.0 / sqrt(var + (double)a.eps));
   }
   __syncthreads();
   const int vec_per_row = a.C >> 2;

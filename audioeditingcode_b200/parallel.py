@@ -1,0 +1,69 @@
+"""Multi-GPU execution of the hot path: the path shards by CLIP — one process per GPU
+(`torchrun`, backend nccl over NVLink / NVSwitch), weights replicated, every rank edits its own clips with the
+single-GPU code.  There is no data-path collective; the only communication is the final gather of the edited
+latents (and the max-over-ranks reduction of timings in bench.py).  The reverse process of one clip is sequential in
+t and does not shard (replicas only); the reference itself has no multi-GPU code on this path.
+"""
+from __future__ import annotations
+
+from typing import Callable, List, Optional, Sequence
+
+import torch
+import torch.distributed as dist
+
+
+def world() -> tuple:
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def shard_indices(n_items: int, rank: int, world_size: int) -> List[int]:
+    """Round-robin assignment: item i -> rank i % world_size (keeps per-rank counts within 1 of each other)."""
+    return list(range(rank, n_items, world_size))
+
+
+def edit_clips(edit_fn: Callable[[torch.Tensor], torch.Tensor], clips: Sequence[torch.Tensor],
+               gather: bool = True, group=None) -> List[Optional[torch.Tensor]]:
+    """Run `edit_fn` (e.g. inversion_forward_process + inversion_reverse_process on one clip latent) over `clips`,
+    sharded across the ranks of the default process group.  Returns the results in clip order — on every rank if
+    `gather`, else only this rank's entries (others None).  All clips must produce equally shaped results."""
+    rank, ws = world()
+    mine = shard_indices(len(clips), rank, ws)
+    local = {i: edit_fn(clips[i]) for i in mine}
+    out: List[Optional[torch.Tensor]] = [None] * len(clips)
+    for i, t in local.items():
+        out[i] = t
+    if ws == 1 or not gather or not clips:
+        return out
+    per_rank = (len(clips) + ws - 1) // ws
+    ref = next(iter(local.values())) if local else None
+    shape = [None, None]
+    if rank == 0:
+        shape = [tuple(ref.shape), str(ref.dtype)]
+    dist.broadcast_object_list(shape, src=0, group=group)
+    shp = shape[0]
+    dtype = ref.dtype if ref is not None else getattr(torch, shape[1].split(".")[-1])
+    device = ref.device if ref is not None else (torch.device("cuda", torch.cuda.current_device())
+                                                 if dist.get_backend(group) == "nccl" else torch.device("cpu"))
+    buf = torch.zeros((per_rank, *shp), dtype=dtype, device=device)
+    for k, i in enumerate(mine):
+        buf[k] = local[i]
+    bufs = [torch.empty_like(buf) for _ in range(ws)]
+    dist.all_gather(bufs, buf, group=group)
+    for r in range(ws):
+        for k, i in enumerate(shard_indices(len(clips), r, ws)):
+            out[i] = bufs[r][k]
+    return out
+
+
+def max_over_ranks(value: float, device=None) -> float:
+    """Device-timed durations are reduced with MAX over ranks (never wall-clock, never mean)."""
+    rank, ws = world()
+    if ws == 1:
+        return float(value)
+    dev = device if device is not None else (torch.device("cuda", torch.cuda.current_device())
+                                             if dist.get_backend() == "nccl" else torch.device("cpu"))
+    t = torch.tensor([float(value)], device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())

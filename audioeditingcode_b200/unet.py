@@ -88,7 +88,7 @@ class UNetEngine:
         self.kernels_per_forward: Dict = {}
         import os
         # below this width the 4-D TMA boxes degenerate into 256-byte bursts; gather patches explicitly instead
-        self.min_implicit_w = int(os.environ.get("AEDIT_MIN_IMPLICIT_W", "4"))
+        self.min_implicit_w = int(os.environ.get("AEDIT_MIN_IMPLICIT_W", "2"))
 
     def graphed(self, B, H, W, text=None, slot_map=None, class_labels=None, slot_key=None) -> GraphedForward:
         """Cached CUDA-graph evaluator for this geometry / text binding.  `slot_key`: hashable description of

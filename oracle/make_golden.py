@@ -269,7 +269,12 @@ def golden_ends():
         mom = torch.nn.functional.conv2d(enc(x), ld["quant_conv.weight"], ld["quant_conv.bias"])
         z = mom[:, :8] * E.VAE_SCALING
         dx = dec(torch.nn.functional.conv2d(z / E.VAE_SCALING, ld["post_quant_conv.weight"], ld["post_quant_conv.bias"]))
-    save("vae_ends.npz", x=x, moments=mom, z=z, decoded=dx, weight_seed=0)
+    rel = lambda a, b: float((a - b).norm() / b.norm())
+    with torch.no_grad(), torch.autocast("cpu", dtype=torch.bfloat16):     # stock torch bf16: the error yardstick
+        e_enc = rel(E.vae_encode_moments(w, x).float(), mom)
+        e_dec = rel(E.vae_decode(w, z).float(), dx)
+    save("vae_ends.npz", x=x, moments=mom, z=z, decoded=dx, weight_seed=0, bf16_autocast_err_encode=e_enc,
+         bf16_autocast_err_decode=e_dec)
     h = types.SimpleNamespace(resblock="1", upsample_rates=[5, 4, 2, 2, 2], upsample_kernel_sizes=[16, 16, 8, 4, 4],
                               upsample_initial_channel=1024, resblock_kernel_sizes=[3, 7, 11],
                               resblock_dilation_sizes=[[1, 3, 5]] * 3, num_mels=64)
@@ -280,7 +285,9 @@ def golden_ends():
     mel = torch.randn(1, 32, 64, generator=g) * 2 - 4
     with torch.no_grad():
         wav = gen(mel.transpose(1, 2)).squeeze(1)
-    save("hifigan_ends.npz", mel=mel, wav=wav, weight_seed=0)
+    with torch.no_grad(), torch.autocast("cpu", dtype=torch.bfloat16):
+        e_voc = rel(E.hifigan_forward(hw, mel).float(), wav)
+    save("hifigan_ends.npz", mel=mel, wav=wav, weight_seed=0, bf16_autocast_err=e_voc)
 
 
 if __name__ == "__main__":

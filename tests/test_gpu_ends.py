@@ -31,18 +31,21 @@ def _rel(a, b):
 def test_vae_encode_decode_vs_vendored_modules():
     """VAEEngine (tcgen05 convs, GN kernels, unfused single-head attention) vs golden outputs of the reference's
     vendored Encoder / Decoder (variational_autoencoder/modules.py) with identical synthetic weights.
-    Tolerance: bf16 operands, fp32 accumulation/residuals -> rel-L2 <= 1e-2."""
+    Tolerance: bf16 operands, fp32 accumulation / residual stream -> rel-L2 <= max(1e-2, error of stock PyTorch
+    bf16 autocast on the same network, stored in the fixture)."""
     from audioeditingcode_b200.ends import VAEEngine, vae_weight_shapes, synthetic, VAE_SCALING
     g = load_golden("vae_ends.npz")
     vae = VAEEngine("cuda", synthetic(vae_weight_shapes(), 0), VAE_SCALING)
     z = vae.encode_mode(g["x"].cuda())
     assert z.shape == g["z"].shape
-    assert _rel(z, g["z"]) < 1e-2
+    assert _rel(z, g["z"]) < max(1e-2, float(g["bf16_autocast_err_encode"]))
     mom = vae.encode_moments(g["x"].cuda())
-    assert _rel(mom, g["moments"]) < 1e-2
+    assert _rel(mom, g["moments"]) < max(1e-2, float(g["bf16_autocast_err_encode"]))
     dec = vae.decode(g["z"].cuda())
     assert dec.shape == g["decoded"].shape
-    assert _rel(dec, g["decoded"]) < 1e-2
+    r = _rel(dec, g["decoded"])
+    print(f"vae decode rel-L2 {r:.2e} (torch-bf16 {float(g['bf16_autocast_err_decode']):.2e})")
+    assert r < max(1e-2, float(g["bf16_autocast_err_decode"]))
 
 
 def test_hifigan_vs_vendored_generator():
@@ -53,7 +56,9 @@ def test_hifigan_vs_vendored_generator():
     voc = HiFiGANEngine("cuda", synthetic(hifigan_weight_shapes(), 0))
     wav = voc(g["mel"][0].cuda())
     assert wav.shape == g["wav"][0].shape
-    assert _rel(wav, g["wav"][0]) < 2e-2
+    r = _rel(wav, g["wav"][0])
+    print(f"hifigan rel-L2 {r:.2e} (torch-bf16 {float(g['bf16_autocast_err']):.2e})")
+    assert r < 2e-2
     assert (wav.cpu() - g["wav"][0]).abs().max().item() < 0.05 * g["wav"].abs().max().item() + 1e-4
 
 

@@ -91,5 +91,5 @@ def test_unet_audioldm_s_5s():
     assert torch.equal(out_rep, out)
     x4 = torch.cat([x, x.flip(0)], 0).cuda()
     out4 = eng.forward(x4, torch.cat([t, t.flip(0)]).cuda(), class_labels=torch.cat([y, y.flip(0)]).cuda())
-    assert ((out4[:2] - out).norm() / out.norm()).item() < 3e-3
+    assert ((out4[:2] - out).norm() / out.norm()).item() < 1e-2
     assert torch.equal(out4[2:].flip(0), out4[:2])
