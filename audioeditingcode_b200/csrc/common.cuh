@@ -47,9 +47,11 @@ extern int g_use_pdl;
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
+// g_use_pdl: 0 = off, 1 = every kernel may start early, 2 = only kernels launched through launch_kernel_early
+// (the GEMMs, whose prologue — TMEM allocation, barrier init, descriptor prefetch — is worth overlapping)
 template <typename... KArgs, typename... Args>
-inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
-                                 Args&&... args) {
+inline cudaError_t launch_kernel_mode(bool early_ok, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                                      cudaStream_t st, Args&&... args) {
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = grid;
   cfg.blockDim = block;
@@ -59,8 +61,20 @@ inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = g_use_pdl ? 1 : 0;
+  cfg.numAttrs = (g_use_pdl == 1 || (g_use_pdl == 2 && early_ok)) ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel_early(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                       Args&&... args) {
+  return launch_kernel_mode(true, kernel, grid, block, smem, st, static_cast<Args&&>(args)...);
+}
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                 Args&&... args) {
+  return launch_kernel_mode(false, kernel, grid, block, smem, st, static_cast<Args&&>(args)...);
 }
 
 inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }

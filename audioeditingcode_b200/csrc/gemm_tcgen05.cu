@@ -178,9 +178,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int quad = warp & 3;
     const int row = quad * 32 + lane;
     const long long m = (long long)m0 + row;
+    const bool row_ok = m < p.M;
+    if (p.residual && row_ok) {
+      // pull this row's residual segment towards L2 while the main loop runs (BN*4 bytes = up to 4 lines)
+      const char* rp = reinterpret_cast<const char*>(p.residual + (long long)z * p.stride_res + m * p.ld_res + n0);
+#pragma unroll
+      for (int l = 0; l < BN * 4 / 128; ++l) asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + l * 128));
+    }
     ptx::mbar_wait(tmem_full_bar, 0);
     ptx::tcgen05_fence_after();
-    const bool row_ok = m < p.M;
     const float* rb = nullptr;
     if (p.rowbias && row_ok) rb = p.rowbias + (m / p.rows_per_group) * p.ld_rowbias;
     const float* res = p.residual ? p.residual + (long long)z * p.stride_res + m * p.ld_res : nullptr;
@@ -322,7 +328,21 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(ReduceArgs a) {
     const int n = (int)(i - m * n4) << 2;
     const float* w = a.ws + m * a.N + n;
     float4 acc = *reinterpret_cast<const float4*>(w);
-    for (int s = 1; s < a.S; ++s) {
+    // partials are fetched four at a time (independent loads in flight), summed in the fixed order s = 1..S-1
+    int s = 1;
+    for (; s + 4 <= a.S; s += 4) {
+      float4 t[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) t[u] = *reinterpret_cast<const float4*>(w + (long long)(s + u) * a.MN);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        acc.x += t[u].x;
+        acc.y += t[u].y;
+        acc.z += t[u].z;
+        acc.w += t[u].w;
+      }
+    }
+    for (; s < a.S; ++s) {
       const float4 t = *reinterpret_cast<const float4*>(w + (long long)s * a.MN);
       acc.x += t.x;
       acc.y += t.y;
@@ -437,7 +457,7 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmDev& p, int
     attr_set = true;
   }
   dim3 grid((p.M + BM - 1) / BM, (p.N + BN - 1) / BN, gz);
-  cudaError_t e = launch_kernel(gemm_tcgen05_kernel<BN, STAGES>, grid, dim3(kThreads), (size_t)L::kTotal, st, tmA, tmB, p);
+  cudaError_t e = launch_kernel_early(gemm_tcgen05_kernel<BN, STAGES>, grid, dim3(kThreads), (size_t)L::kTotal, st, tmA, tmB, p);
   if (e != cudaSuccess) return fail(AE_ECUDA, "ae_gemm launch: %s", cudaGetErrorString(e));
   return launched("ae_gemm");
 }
@@ -447,7 +467,7 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmDev& p, int
 
 using namespace aedit;
 
-extern "C" void ae_set_pdl(int enable) { g_use_pdl = enable ? 1 : 0; }
+extern "C" void ae_set_pdl(int mode) { g_use_pdl = (mode == 1 || mode == 2) ? mode : 0; }
 
 extern "C" int ae_gemm_conv_supported(int B, int H, int W, int C) {
   ConvBox bx;

@@ -42,6 +42,7 @@ __device__ __forceinline__ float load_cat(const GNArgs& a, long long row, int c)
 // TY loads in flight per quad).  Per-channel partials are combined over ty in shared memory in a fixed order, then
 // per group in double; the last CTA of a sample (arrival counter) finalises mean / rstd for all groups.
 constexpr int kGNMaxQuadsPerThread = 4;
+constexpr int kGNUnroll = 4;
 __global__ void __launch_bounds__(512) gn_stats_kernel(GNArgs a) {
   pdl_trigger();
   pdl_wait();
@@ -58,19 +59,34 @@ __global__ void __launch_bounds__(512) gn_stats_kernel(GNArgs a) {
   for (int k = 0; k < kGNMaxQuadsPerThread; ++k)
 #pragma unroll
     for (int e = 0; e < 4; ++e) su[k][e] = sq[k][e] = 0.f;
-  for (long long p = p0 + ty; p < p1; p += TY) {
-    const long long row = (long long)b * a.HW + p;
+  // positions are walked kGNUnroll at a time: all loads of a batch are issued before any is consumed (an in-order
+  // warp would otherwise serialise one DRAM/L2 latency per position)
+  for (long long pb = p0 + ty; pb < p1; pb += (long long)TY * kGNUnroll) {
+    float4 v[kGNUnroll][kGNMaxQuadsPerThread];
 #pragma unroll
-    for (int k = 0; k < kGNMaxQuadsPerThread; ++k) {
-      const int qd = tx + k * TX;
-      if (qd < nq) {
-        const int c = qd << 2;
-        const float4 v = c < a.C1 ? *reinterpret_cast<const float4*>(a.x1 + row * a.C1 + c)
-                                  : *reinterpret_cast<const float4*>(a.x2 + row * a.C2 + (c - a.C1));
-        su[k][0] += v.x; sq[k][0] += v.x * v.x;
-        su[k][1] += v.y; sq[k][1] += v.y * v.y;
-        su[k][2] += v.z; sq[k][2] += v.z * v.z;
-        su[k][3] += v.w; sq[k][3] += v.w * v.w;
+    for (int u = 0; u < kGNUnroll; ++u) {
+      const long long p = pb + (long long)u * TY;
+      const long long row = (long long)b * a.HW + p;
+#pragma unroll
+      for (int k = 0; k < kGNMaxQuadsPerThread; ++k) {
+        const int qd = tx + k * TX;
+        if (p < p1 && qd < nq) {
+          const int c = qd << 2;
+          v[u][k] = c < a.C1 ? *reinterpret_cast<const float4*>(a.x1 + row * a.C1 + c)
+                             : *reinterpret_cast<const float4*>(a.x2 + row * a.C2 + (c - a.C1));
+        } else {
+          v[u][k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kGNUnroll; ++u) {
+#pragma unroll
+      for (int k = 0; k < kGNMaxQuadsPerThread; ++k) {
+        su[k][0] += v[u][k].x; sq[k][0] += v[u][k].x * v[u][k].x;
+        su[k][1] += v[u][k].y; sq[k][1] += v[u][k].y * v[u][k].y;
+        su[k][2] += v[u][k].z; sq[k][2] += v[u][k].z * v[u][k].z;
+        su[k][3] += v[u][k].w; sq[k][3] += v[u][k].w * v[u][k].w;
       }
     }
   }
@@ -111,19 +127,30 @@ __global__ void __launch_bounds__(kGNThreads) gn_apply_kernel(GNArgs a) {
   const int b = blockIdx.y;
   // every CTA finalises the group statistics of its sample from the S partials (fixed order k = 0..S-1, so all
   // CTAs and all launches agree bit for bit); S*G*2 doubles come from L2
-  for (int g = threadIdx.x; g < a.G; g += kGNThreads) {
-    double dsu = 0.0, dsq = 0.0;
-    const double* src = a.partial + ((long long)b * a.S * a.G + g) * 2;
-    for (int k = 0; k < a.S; ++k) {
-      dsu += src[(long long)k * a.G * 2];
-      dsq += src[(long long)k * a.G * 2 + 1];
+  {
+    // 16 lanes per group: lane k loads partial k (S <= 16), fixed-shape shuffle tree -> identical bits in every CTA
+    const int sub = threadIdx.x & 15;
+    for (int g = threadIdx.x >> 4; g < a.G; g += kGNThreads >> 4) {
+      double dsu = 0.0, dsq = 0.0;
+      if (sub < a.S) {
+        const double* src = a.partial + (((long long)b * a.S + sub) * a.G + g) * 2;
+        dsu = src[0];
+        dsq = src[1];
+      }
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) {
+        dsu += __shfl_down_sync(0xffffffffu, dsu, o, 16);
+        dsq += __shfl_down_sync(0xffffffffu, dsq, o, 16);
+      }
+      if (sub == 0) {
+        const double n = (double)a.HW * a.cpg;
+        const double mean = dsu / n;
+        double var = dsq / n - mean * mean;
+        if (var < 0.0) var = 0.0;
+        sm[g] = (float)mean;
+        sm[a.G + g] = (float)(1.0 / sqrt(var + (double)a.eps));
+      }
     }
-    const double n = (double)a.HW * a.cpg;
-    const double mean = dsu / n;
-    double var = dsq / n - mean * mean;
-    if (var < 0.0) var = 0.0;
-    sm[g] = (float)mean;
-    sm[a.G + g] = (float)(1.0 / sqrt(var + (double)a.eps));
   }
   __syncthreads();
   const int vec_per_row = a.C >> 2;

@@ -43,7 +43,7 @@ class CudaOps:
         self._splitk_ws = {}
         import os
         # programmatic dependent launch measured slower end to end on B200 (profiles/r01_*): opt-in only
-        self.lib.ae_set_pdl(1 if os.environ.get("AEDIT_PDL", "0") == "1" else 0)
+        self.lib.ae_set_pdl(int(os.environ.get("AEDIT_PDL", "0")))   # 0 off, 1 all kernels, 2 GEMMs only
 
     def _splitk_workspace(self, device):
         ws = self._splitk_ws.get(str(device))

@@ -39,7 +39,7 @@ int64_t ae_launch_count(void);
 int ae_device_ok(void);
 /* Programmatic dependent launch for every kernel of the library (default on): each kernel lets its successor in the
  * stream start early (prologue overlap) and waits for its predecessor before touching global memory. */
-void ae_set_pdl(int enable);
+void ae_set_pdl(int mode); /* 0 off (default), 1 every kernel, 2 GEMM kernels only */
 
 /* ------------------------------------------------------------------------------------------------
  * Scheduler table  (code/models.py:85-158, :539-549; integer index math of
