@@ -34,6 +34,12 @@ struct AttnArgs {
   float scale_log2;  // scale * log2(e)
 };
 
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 template <int D>
 struct AttnCfg {
   static constexpr int DP = (D + 15) / 16 * 16;
@@ -132,47 +138,60 @@ __global__ void __launch_bounds__(kAttnThreads) attention_kernel(AttnArgs a) {
         ptx::mma_m16n8k16_bf16(s[2 * np + 1], qf[ks], bf[2], bf[3]);
       }
     }
-    // ---- scale, bias, key-range mask, online softmax (rows g and g+8 of this warp's 16)
+    // ---- online softmax (rows g and g+8 of this warp's 16).  The raw scores stay unscaled: scale*log2(e) is
+    //      folded into the exponent FMA.  Key-range masking / additive bias only run on tiles that need them.
     const int key0 = it * BKV;
+    const bool full_tile = (key0 + BKV <= a.Tk);
+    if (biasp != nullptr || !full_tile) {
+      const float inv = 1.0f / a.scale_log2;   // bring the bias into raw-score units
+#pragma unroll
+      for (int n = 0; n < 8; ++n) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int key = key0 + n * 8 + t4 * 2 + (k & 1);
+          float val = s[n][k];
+          if (key < a.Tk) {
+            if (biasp) val += biasp[key] * (1.4426950408889634f * inv);
+          } else {
+            val = -INFINITY;
+          }
+          s[n][k] = val;
+        }
+      }
+    }
     float mx[2] = {-INFINITY, -INFINITY};
 #pragma unroll
     for (int n = 0; n < 8; ++n) {
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const int key = key0 + n * 8 + t4 * 2 + (k & 1);
-        float val = s[n][k] * a.scale_log2;
-        if (biasp && key < a.Tk) val += biasp[key] * 1.4426950408889634f;
-        if (key >= a.Tk) val = -INFINITY;
-        s[n][k] = val;
-        mx[k >> 1] = fmaxf(mx[k >> 1], val);
-      }
+      mx[0] = fmaxf(mx[0], fmaxf(s[n][0], s[n][1]));
+      mx[1] = fmaxf(mx[1], fmaxf(s[n][2], s[n][3]));
     }
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
       mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
       mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
     }
-    float corr[2], m_new[2];
+    float corr[2], msc[2];
+    bool changed = false;
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
-      m_new[r] = fmaxf(m_run[r], mx[r]);
-      corr[r] = (m_run[r] == -INFINITY) ? 0.f : exp2f(m_run[r] - m_new[r]);
-      m_run[r] = m_new[r];
+      const float m_new = fmaxf(m_run[r], mx[r]);
+      changed |= (m_new != m_run[r]);
+      corr[r] = (m_run[r] == -INFINITY) ? 0.f : fast_exp2((m_run[r] - m_new) * a.scale_log2);
+      m_run[r] = m_new;
+      msc[r] = m_new * a.scale_log2;
     }
     float rs[2] = {0.f, 0.f};
     uint32_t pf[4][4];  // P as A-operand fragments: 4 k-steps of 16 keys
 #pragma unroll
     for (int n = 0; n < 8; ++n) {
-      const float p0 = exp2f(s[n][0] - m_new[0]);
-      const float p1 = exp2f(s[n][1] - m_new[0]);
-      const float p2 = exp2f(s[n][2] - m_new[1]);
-      const float p3 = exp2f(s[n][3] - m_new[1]);
-      // sum what the tensor core will actually multiply (bf16-rounded probabilities)
+      const float p0 = fast_exp2(fmaf(s[n][0], a.scale_log2, -msc[0]));
+      const float p1 = fast_exp2(fmaf(s[n][1], a.scale_log2, -msc[0]));
+      const float p2 = fast_exp2(fmaf(s[n][2], a.scale_log2, -msc[1]));
+      const float p3 = fast_exp2(fmaf(s[n][3], a.scale_log2, -msc[1]));
+      rs[0] += p0 + p1;
+      rs[1] += p2 + p3;
       const __nv_bfloat162 h01 = __floats2bfloat162_rn(p0, p1);
       const __nv_bfloat162 h23 = __floats2bfloat162_rn(p2, p3);
-      const float2 f01 = __bfloat1622float2(h01), f23 = __bfloat1622float2(h23);
-      rs[0] += f01.x + f01.y;
-      rs[1] += f23.x + f23.y;
       pf[n >> 1][(n & 1) * 2 + 0] = *reinterpret_cast<const uint32_t*>(&h01);
       pf[n >> 1][(n & 1) * 2 + 1] = *reinterpret_cast<const uint32_t*>(&h23);
     }
@@ -182,12 +201,14 @@ __global__ void __launch_bounds__(kAttnThreads) attention_kernel(AttnArgs a) {
       rs[r] += __shfl_xor_sync(0xffffffffu, rs[r], 2);
       l_run[r] = l_run[r] * corr[r] + rs[r];
     }
+    if (__any_sync(0xffffffffu, changed)) {   // running max unchanged for the whole warp -> corr == 1, skip the rescale
 #pragma unroll
-    for (int n = 0; n < NB; ++n) {
-      o_acc[n][0] *= corr[0];
-      o_acc[n][1] *= corr[0];
-      o_acc[n][2] *= corr[1];
-      o_acc[n][3] *= corr[1];
+      for (int n = 0; n < NB; ++n) {
+        o_acc[n][0] *= corr[0];
+        o_acc[n][1] *= corr[0];
+        o_acc[n][2] *= corr[1];
+        o_acc[n][3] *= corr[1];
+      }
     }
     // ---- O += P V
 #pragma unroll

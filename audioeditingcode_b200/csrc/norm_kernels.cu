@@ -11,7 +11,7 @@ namespace aedit {
 namespace {
 
 constexpr int kGNThreads = 256;
-constexpr int kMaxSplits = 16;
+constexpr int kMaxSplits = 64;
 
 struct GNArgs {
   const float* x1;
@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(512) gn_stats_kernel(GNArgs a) {
 }
 
 // grid (ceil(HW*C/4 / (256*kGNItems)), B): each thread normalises kGNItems float4 items (coalesced along channels)
-constexpr int kGNItems = 2;
+constexpr int kGNItems = 8;
 __global__ void __launch_bounds__(kGNThreads) gn_apply_kernel(GNArgs a) {
   pdl_trigger();
   pdl_wait();
@@ -128,33 +128,42 @@ __global__ void __launch_bounds__(kGNThreads) gn_apply_kernel(GNArgs a) {
   // every CTA finalises the group statistics of its sample from the S partials (fixed order k = 0..S-1, so all
   // CTAs and all launches agree bit for bit); S*G*2 doubles come from L2
   {
-    // 16 lanes per group: lane k loads partial k (S <= 16), fixed-shape shuffle tree -> identical bits in every CTA
-    const int sub = threadIdx.x & 15;
-    for (int g = threadIdx.x >> 4; g < a.G; g += kGNThreads >> 4) {
+    // one warp per group: lane k loads partials k and k+32 (S <= 64), fixed-shape shuffle tree -> identical bits
+    // in every CTA
+    const int lane = threadIdx.x & 31;
+    for (int g = threadIdx.x >> 5; g < a.G; g += kGNThreads >> 5) {
       double dsu = 0.0, dsq = 0.0;
-      if (sub < a.S) {
-        const double* src = a.partial + (((long long)b * a.S + sub) * a.G + g) * 2;
-        dsu = src[0];
-        dsq = src[1];
+      const double* src = a.partial + ((long long)b * a.S * a.G + g) * 2;
+      const long long st = (long long)a.G * 2;
+      double p0 = 0.0, q0 = 0.0, p1 = 0.0, q1 = 0.0;
+      if (lane < a.S) {
+        p0 = src[lane * st];
+        q0 = src[lane * st + 1];
       }
+      if (lane + 32 < a.S) {
+        p1 = src[(lane + 32) * st];
+        q1 = src[(lane + 32) * st + 1];
+      }
+      dsu = p0 + p1;
+      dsq = q0 + q1;
 #pragma unroll
-      for (int o = 8; o > 0; o >>= 1) {
-        dsu += __shfl_down_sync(0xffffffffu, dsu, o, 16);
-        dsq += __shfl_down_sync(0xffffffffu, dsq, o, 16);
+      for (int o = 16; o > 0; o >>= 1) {
+        dsu += __shfl_down_sync(0xffffffffu, dsu, o);
+        dsq += __shfl_down_sync(0xffffffffu, dsq, o);
       }
-      if (sub == 0) {
+      if (lane == 0) {
         const double n = (double)a.HW * a.cpg;
         const double mean = dsu / n;
         double var = dsq / n - mean * mean;
         if (var < 0.0) var = 0.0;
         sm[g] = (float)mean;
-        sm[a.G + g] = (float)(1.0 / sqrt(var + (double)a.eps));
+        sm[a.G + g] = rsqrtf((float)var + a.eps);
       }
     }
   }
   __syncthreads();
   const int vec_per_row = a.C >> 2;
-  const long long total = a.HW * vec_per_row;
+  const long long total = a.HW * vec_per_row;   // < 2^31 for every tensor of the path (checked on the host)
   const long long base = (long long)blockIdx.x * (kGNThreads * kGNItems) + threadIdx.x;
   float4 v[kGNItems];
   long long idx[kGNItems];
@@ -162,8 +171,8 @@ __global__ void __launch_bounds__(kGNThreads) gn_apply_kernel(GNArgs a) {
   for (int it = 0; it < kGNItems; ++it) {
     idx[it] = base + (long long)it * kGNThreads;
     if (idx[it] < total) {
-      const long long p = idx[it] / vec_per_row;
-      const int c = (int)(idx[it] - p * vec_per_row) << 2;
+      const int p = (int)idx[it] / vec_per_row;
+      const int c = ((int)idx[it] - p * vec_per_row) << 2;
       const long long row = (long long)b * a.HW + p;
       v[it] = c < a.C1 ? *reinterpret_cast<const float4*>(a.x1 + row * a.C1 + c)
                        : *reinterpret_cast<const float4*>(a.x2 + row * a.C2 + (c - a.C1));
@@ -172,8 +181,8 @@ __global__ void __launch_bounds__(kGNThreads) gn_apply_kernel(GNArgs a) {
 #pragma unroll
   for (int it = 0; it < kGNItems; ++it) {
     if (idx[it] >= total) continue;
-    const long long p = idx[it] / vec_per_row;
-    const int c = (int)(idx[it] - p * vec_per_row) << 2;
+    const int p = (int)idx[it] / vec_per_row;
+    const int c = ((int)idx[it] - p * vec_per_row) << 2;
     const long long row = (long long)b * a.HW + p;
     const float in[4] = {v[it].x, v[it].y, v[it].z, v[it].w};
     const float4 gm = __ldg(reinterpret_cast<const float4*>(a.gamma + c));
@@ -285,6 +294,7 @@ extern "C" int ae_groupnorm(const float* x1, int C1, const float* x2, int C2, in
   AE_CHECK_ARG(C % groups == 0, "ae_groupnorm: C=%d not divisible by groups=%d", C, groups);
   AE_CHECK_ARG(C1 % 4 == 0 && C2 % 4 == 0, "ae_groupnorm: channel counts must be multiples of 4 (C1=%d C2=%d)", C1, C2);
   AE_CHECK_ARG(gamma && beta && out_bf16 && workspace, "ae_groupnorm: null pointer");
+  AE_CHECK_ARG(HW * (int64_t)(C / 4) < 2147483647LL, "ae_groupnorm: sample too large (HW*C/4 >= 2^31)");
   GNArgs a;
   a.x1 = x1;
   a.x2 = x2;

@@ -290,8 +290,29 @@ def golden_ends():
     save("hifigan_ends.npz", mel=mel, wav=wav, weight_seed=0, bf16_autocast_err=e_voc)
 
 
+def golden_ddim():
+    """Reference DDIM baseline (code/ddm_inversion/ddim_inversion.py, unmodified): ddim_inversion + text2image_ldm_stable
+    on the fake wrapper; the diffusers scheduler.step is substituted by oracle MiniDDIM.step ([UPSTREAM] restatement)."""
+    ref = ref_import.load()
+    cfg = C.preset("tiny-audioldm")
+    w = U.synthetic_weights(cfg, seed=0)
+    N = 10
+    model = make_fake_wrapper(ref, cfg, w, N)
+    # ddim_inversion.py:23-41 calls model.unet_forward with the encode_text() tuples
+    g = torch.Generator().manual_seed(61)
+    w0 = 0.5 * torch.randn(1, 8, 16, 16, generator=g)
+    import ddm_inversion.ddim_inversion as DI
+    with torch.no_grad():
+        wT = DI.ddim_inversion(model, w0, ["a dog"], 3.0, num_inference_steps=N, skip=0)
+        wrec = DI.text2image_ldm_stable(model, ["a cat"], N, 5.0, wT, skip=0)
+    save("ddim_mode.npz", w0=w0, wT=wT, w_rec=wrec, n_steps=N, uncond=prompt_vector(""), src=prompt_vector("a dog"),
+         tgt=prompt_vector("a cat"))
+
+
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
+    if what in ("all", "ddim"):
+        golden_ddim()
     if what in ("all", "loops"):
         main()
     if what in ("all", "stft"):
