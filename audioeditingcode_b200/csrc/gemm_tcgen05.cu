@@ -54,6 +54,7 @@ struct GemmDev {
   __nv_bfloat16* out_bf16;
   long long ld_out_bf16;
   long long stride_out, stride_res;
+  int w_dynamic;  // 1: the W operand is produced by a preceding kernel (never prefetch it ahead of the dependency)
   int act;  // 0 none, 1 SiLU, 2 GEGLU (output width N/2: out[16q+i] = acc[32q+i] * gelu(acc[32q+16+i]))
   float alpha;
 };
@@ -113,8 +114,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   __syncthreads();
   ptx::tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  pdl_wait();  // everything above overlapped the previous kernel; from here on we touch global memory
-
+  // Everything above overlapped the previous kernel (programmatic dependent launch).  The weight operand W never
+  // depends on the previous kernel, so the producer also streams the first ring of W tiles before blocking; all
+  // other global traffic (activations A, residual, outputs) waits for the dependency.
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (ptx::elect_one()) {
@@ -125,11 +127,20 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         h0 = rem / p.W;
         w0 = rem - h0 * p.W;
       }
+      const int npre = p.w_dynamic ? 0 : min(STAGES, kb1 - kb0);
+      for (int s = 0; s < npre; ++s) {
+        ptx::mbar_expect_tx(&full_bar[s], L::kStageBytes);
+        ptx::tma_load_3d(&tmB, &full_bar[s], sB + s * L::kBTileBytes, (kb0 + s) * BK, n0, zb);
+      }
+      pdl_wait();
       int stage = 0;
       uint32_t phase = 0;
       for (int kb = kb0; kb < kb1; ++kb) {
-        ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
-        ptx::mbar_expect_tx(&full_bar[stage], L::kStageBytes);
+        const bool pre = (kb - kb0) < npre;   // first ring: slot known free, barrier armed, W already in flight
+        if (!pre) {
+          ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+          ptx::mbar_expect_tx(&full_bar[stage], L::kStageBytes);
+        }
         if (p.conv) {
           const int tap = kb / p.cblocks;
           const int cb = kb - tap * p.cblocks;
@@ -140,7 +151,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         } else {
           ptx::tma_load_3d(&tmA, &full_bar[stage], sA + stage * kATileBytes, kb * BK, m0, zb);
         }
-        ptx::tma_load_3d(&tmB, &full_bar[stage], sB + stage * L::kBTileBytes, kb * BK, n0, zb);
+        if (!pre) ptx::tma_load_3d(&tmB, &full_bar[stage], sB + stage * L::kBTileBytes, kb * BK, n0, zb);
         if (++stage == STAGES) {
           stage = 0;
           phase ^= 1;
@@ -178,6 +189,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int quad = warp & 3;
     const int row = quad * 32 + lane;
     const long long m = (long long)m0 + row;
+    pdl_wait();
     const bool row_ok = m < p.M;
     if (p.residual && row_ok) {
       // pull this row's residual segment towards L2 while the main loop runs (BN*4 bytes = up to 4 lines)
@@ -498,6 +510,7 @@ extern "C" int ae_gemm(const ae_gemm_args* a, ae_stream stream) {
   p.stride_out = a->stride_out;
   p.stride_res = a->stride_res;
   p.act = a->act;
+  p.w_dynamic = a->w_dynamic ? 1 : 0;
   p.alpha = a->alpha == 0.0f ? 1.0f : a->alpha;
   p.H = p.W = p.HW = p.cblocks = p.kw = 1;
   p.dil_h = p.dil_w = 1;

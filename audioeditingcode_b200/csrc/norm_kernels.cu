@@ -103,36 +103,65 @@ __global__ void __launch_bounds__(512) gn_stats_kernel(GNArgs a) {
     }
   }
   __syncthreads();
-  for (int g = tid; g < a.G; g += nthr) {
-    double dsu = 0.0, dsq = 0.0;
-    for (int y = 0; y < TY; ++y) {
-      const float* r = sm + (size_t)y * 2 * a.C;
-      for (int c = g * a.cpg; c < (g + 1) * a.cpg; ++c) {
+  {
+    // one warp per group: lanes stride over the TY x cpg per-channel partials of the group (fixed assignment),
+    // fixed-shape shuffle tree -> deterministic
+    const int lane = tid & 31, wid = tid >> 5, nw = nthr >> 5;
+    const int per = TY * a.cpg;
+    for (int g = wid; g < a.G; g += nw) {
+      double dsu = 0.0, dsq = 0.0;
+      for (int e = lane; e < per; e += 32) {
+        const int y = e / a.cpg, c = g * a.cpg + (e - y * a.cpg);
+        const float* r = sm + (size_t)y * 2 * a.C;
         dsu += (double)r[c];
         dsq += (double)r[a.C + c];
       }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        dsu += __shfl_down_sync(0xffffffffu, dsu, o);
+        dsq += __shfl_down_sync(0xffffffffu, dsq, o);
+      }
+      if (lane == 0) {
+        double* dst = a.partial + (((long long)b * a.S + s) * a.G + g) * 2;
+        dst[0] = dsu;
+        dst[1] = dsq;
+      }
     }
-    double* dst = a.partial + (((long long)b * a.S + s) * a.G + g) * 2;
-    dst[0] = dsu;
-    dst[1] = dsq;
   }
 }
 
-// grid (ceil(HW*C/4 / (256*kGNItems)), B): each thread normalises kGNItems float4 items (coalesced along channels)
+// grid (ceil(HW*C/4 / (256*kGNItems)), B): each thread normalises kGNItems float4 items (coalesced along channels).
+// Order of work in a CTA: (1) issue the data loads, (2) finalise the group statistics of the sample from the S
+// partials (one warp per group, fixed-shape tree: identical bits in every CTA), (3) build the per-channel affine
+// table y = x*A[c] + B[c] in shared memory, (4) apply + SiLU + bf16 store.
 constexpr int kGNItems = 8;
 __global__ void __launch_bounds__(kGNThreads) gn_apply_kernel(GNArgs a) {
   pdl_trigger();
   pdl_wait();
-  extern __shared__ float sm[];  // mean[G], rstd[G]
+  extern __shared__ float sm[];  // mean[G], rstd[G], A[C], B[C]
+  float* s_mean = sm;
+  float* s_rstd = sm + a.G;
+  float* s_A = sm + 2 * a.G;
+  float* s_B = s_A + a.C;
   const int b = blockIdx.y;
-  // every CTA finalises the group statistics of its sample from the S partials (fixed order k = 0..S-1, so all
-  // CTAs and all launches agree bit for bit); S*G*2 doubles come from L2
+  const int vec_per_row = a.C >> 2;
+  const int total = (int)(a.HW * vec_per_row);   // < 2^31, checked on the host
+  const int base = blockIdx.x * (kGNThreads * kGNItems) + threadIdx.x;
+  float4 v[kGNItems];
+#pragma unroll
+  for (int it = 0; it < kGNItems; ++it) {
+    const int idx = base + it * kGNThreads;
+    if (idx < total) {
+      const int p = idx / vec_per_row;
+      const int c = (idx - p * vec_per_row) << 2;
+      const long long row = (long long)b * a.HW + p;
+      v[it] = c < a.C1 ? *reinterpret_cast<const float4*>(a.x1 + row * a.C1 + c)
+                       : *reinterpret_cast<const float4*>(a.x2 + row * a.C2 + (c - a.C1));
+    }
+  }
   {
-    // one warp per group: lane k loads partials k and k+32 (S <= 64), fixed-shape shuffle tree -> identical bits
-    // in every CTA
     const int lane = threadIdx.x & 31;
     for (int g = threadIdx.x >> 5; g < a.G; g += kGNThreads >> 5) {
-      double dsu = 0.0, dsq = 0.0;
       const double* src = a.partial + ((long long)b * a.S * a.G + g) * 2;
       const long long st = (long long)a.G * 2;
       double p0 = 0.0, q0 = 0.0, p1 = 0.0, q1 = 0.0;
@@ -144,58 +173,44 @@ __global__ void __launch_bounds__(kGNThreads) gn_apply_kernel(GNArgs a) {
         p1 = src[(lane + 32) * st];
         q1 = src[(lane + 32) * st + 1];
       }
-      dsu = p0 + p1;
-      dsq = q0 + q1;
+      double dsu = p0 + p1, dsq = q0 + q1;
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) {
         dsu += __shfl_down_sync(0xffffffffu, dsu, o);
         dsq += __shfl_down_sync(0xffffffffu, dsq, o);
       }
       if (lane == 0) {
-        const double n = (double)a.HW * a.cpg;
-        const double mean = dsu / n;
-        double var = dsq / n - mean * mean;
+        const double inv_n = 1.0 / ((double)a.HW * a.cpg);
+        const double mean = dsu * inv_n;
+        double var = dsq * inv_n - mean * mean;
         if (var < 0.0) var = 0.0;
-        sm[g] = (float)mean;
-        sm[a.G + g] = rsqrtf((float)var + a.eps);
+        s_mean[g] = (float)mean;
+        s_rstd[g] = rsqrtf((float)var + a.eps);
       }
     }
   }
   __syncthreads();
-  const int vec_per_row = a.C >> 2;
-  const long long total = a.HW * vec_per_row;   // < 2^31 for every tensor of the path (checked on the host)
-  const long long base = (long long)blockIdx.x * (kGNThreads * kGNItems) + threadIdx.x;
-  float4 v[kGNItems];
-  long long idx[kGNItems];
-#pragma unroll
-  for (int it = 0; it < kGNItems; ++it) {
-    idx[it] = base + (long long)it * kGNThreads;
-    if (idx[it] < total) {
-      const int p = (int)idx[it] / vec_per_row;
-      const int c = ((int)idx[it] - p * vec_per_row) << 2;
-      const long long row = (long long)b * a.HW + p;
-      v[it] = c < a.C1 ? *reinterpret_cast<const float4*>(a.x1 + row * a.C1 + c)
-                       : *reinterpret_cast<const float4*>(a.x2 + row * a.C2 + (c - a.C1));
-    }
+  for (int c = threadIdx.x; c < a.C; c += kGNThreads) {
+    const int g = c / a.cpg;
+    const float A = s_rstd[g] * __ldg(a.gamma + c);
+    s_A[c] = A;
+    s_B[c] = __ldg(a.beta + c) - s_mean[g] * A;
   }
+  __syncthreads();
 #pragma unroll
   for (int it = 0; it < kGNItems; ++it) {
-    if (idx[it] >= total) continue;
-    const int p = (int)idx[it] / vec_per_row;
-    const int c = ((int)idx[it] - p * vec_per_row) << 2;
+    const int idx = base + it * kGNThreads;
+    if (idx >= total) continue;
+    const int p = idx / vec_per_row;
+    const int c = (idx - p * vec_per_row) << 2;
     const long long row = (long long)b * a.HW + p;
     const float in[4] = {v[it].x, v[it].y, v[it].z, v[it].w};
-    const float4 gm = __ldg(reinterpret_cast<const float4*>(a.gamma + c));
-    const float4 bt = __ldg(reinterpret_cast<const float4*>(a.beta + c));
-    const float gmv[4] = {gm.x, gm.y, gm.z, gm.w}, btv[4] = {bt.x, bt.y, bt.z, bt.w};
-    float o[4];
+    const float4 A4 = *reinterpret_cast<const float4*>(s_A + c);
+    const float4 B4 = *reinterpret_cast<const float4*>(s_B + c);
+    float o[4] = {fmaf(in[0], A4.x, B4.x), fmaf(in[1], A4.y, B4.y), fmaf(in[2], A4.z, B4.z), fmaf(in[3], A4.w, B4.w)};
+    if (a.silu) {
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int g = (c + k) / a.cpg;
-      float y = (in[k] - sm[g]) * sm[a.G + g];
-      y = y * gmv[k] + btv[k];
-      if (a.silu) y = silu_f(y);
-      o[k] = y;
+      for (int k = 0; k < 4; ++k) o[k] = silu_f(o[k]);
     }
     const long long off = row * a.C + c;
     __nv_bfloat162 h0 = __floats2bfloat162_rn(o[0], o[1]);
@@ -350,7 +365,7 @@ extern "C" int ae_groupnorm(const float* x1, int C1, const float* x2, int C2, in
   {
     const long long items = HW * (C / 4);
     const unsigned gx = (unsigned)ceil_div64(items, (long long)kGNThreads * kGNItems);
-    launch_kernel(gn_apply_kernel, dim3(gx, B), dim3(kGNThreads), (size_t)(2 * groups * sizeof(float)), st, a);
+    launch_kernel(gn_apply_kernel, dim3(gx, B), dim3(kGNThreads), (size_t)((2 * groups + 2 * C) * sizeof(float)), st, a);
   }
   return launched("ae_groupnorm(apply)");
 }

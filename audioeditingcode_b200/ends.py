@@ -232,10 +232,11 @@ class VAEEngine(_Net):
         for b in range(B):
             s = ops.empty((T, T), F32, self.device)
             qb = qk[b * T:(b + 1) * T]
-            ops.gemm(qb, qb[:, C:], out_f32=s, alpha=float(C) ** -0.5, K=C, lda=2 * C, ldw=2 * C, force_split=1)
+            ops.gemm(qb, qb[:, C:], out_f32=s, alpha=float(C) ** -0.5, K=C, lda=2 * C, ldw=2 * C, force_split=1,
+                     w_dynamic=True)
             pm = ops.empty((T, T), self.adt, self.device)
             ops.softmax_rows(s, pm)
-            ops.gemm(pm, vT[b], out_bf16=a[b * T:(b + 1) * T], force_split=1)
+            ops.gemm(pm, vT[b], out_bf16=a[b * T:(b + 1) * T], force_split=1, w_dynamic=True)
         out = ops.empty((M, C), F32, self.device)
         ops.gemm(a, self.w[p + ".to_out.0.weight"], out_f32=out, bias=self.w[p + ".to_out.0.bias"],
                  residual=x.reshape(M, C))

@@ -305,8 +305,21 @@ def golden_ddim():
     with torch.no_grad():
         wT = DI.ddim_inversion(model, w0, ["a dog"], 3.0, num_inference_steps=N, skip=0)
         wrec = DI.text2image_ldm_stable(model, ["a cat"], N, 5.0, wT, skip=0)
+    # stock torch bf16-autocast yardstick on the same two loops
+    orig_fwd = model.unet_forward
+
+    def bf16_fwd(*a, **k):
+        with torch.autocast("cpu", dtype=torch.bfloat16):
+            out, h, e = orig_fwd(*a, **k)
+        out.sample = out.sample.float()
+        return out, h, e
+    model.unet_forward = bf16_fwd
+    with torch.no_grad():
+        wT_b = DI.ddim_inversion(model, w0, ["a dog"], 3.0, num_inference_steps=N, skip=0)
+        wrec_b = DI.text2image_ldm_stable(model, ["a cat"], N, 5.0, wT, skip=0)
+    rel = lambda a, b: float((a - b).norm() / b.norm())
     save("ddim_mode.npz", w0=w0, wT=wT, w_rec=wrec, n_steps=N, uncond=prompt_vector(""), src=prompt_vector("a dog"),
-         tgt=prompt_vector("a cat"))
+         tgt=prompt_vector("a cat"), bf16_autocast_err_inv=rel(wT_b, wT), bf16_autocast_err_rec=rel(wrec_b, wrec))
 
 
 if __name__ == "__main__":
