@@ -27,7 +27,7 @@ class AeGemmArgs(C.Structure):
                 ("out_f32", vp), ("ld_out_f32", i64), ("out_bf16", vp), ("ld_out_bf16", i64), ("act", i32),
                 ("alpha", f32), ("conv", i32), ("B", i32), ("H", i32), ("W_", i32), ("C", i32), ("kh", i32),
                 ("kw", i32), ("dil_h", i32), ("dil_w", i32), ("force_bn", i32), ("splitk_ws", vp), ("splitk_ws_bytes", i64),
-                ("force_split", i32), ("w_dynamic", i32), ("force_stages", i32)]
+                ("force_split", i32), ("force_csplit", i32), ("w_dynamic", i32), ("force_stages", i32)]
 
 
 _SIGS = {

@@ -40,6 +40,8 @@ struct GemmDev {
   int num_kblocks;
   int kb_per_split;  // == num_kblocks when not split
   int split;         // 1: blockIdx.z is a K split (partials to out_f32 + z*stride_out), else a batch index
+  int csplit;        // >1: blockIdx.z is the rank in a thread-block cluster of that many CTAs sharing one output
+                     //     tile; partial accumulators are reduced through distributed shared memory (no workspace)
   // implicit conv
   int conv, H, W, HW, cblocks, kw, dil_h, dil_w, pad_h, pad_w;
   // epilogue
@@ -71,6 +73,106 @@ struct SmemLayout {
 
 __device__ __forceinline__ float gelu_erf_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 
+// Fused epilogue of one 32-column chunk of one output row: bias, time-embedding row bias, residual, activation,
+// fp32 / bf16 stores.  `acc` already holds alpha * accumulator.
+__device__ __forceinline__ void epilogue_chunk(const GemmDev& p, float (&acc)[32], long long m, int nbase, int z) {
+  if (m >= p.M || nbase >= p.N) return;
+  const int nvalid = min(32, p.N - nbase);
+  if (p.bias) {
+    if (nvalid == 32) {
+      const float4* b4 = reinterpret_cast<const float4*>(p.bias + nbase);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 t = __ldg(b4 + j);
+        acc[4 * j + 0] += t.x;
+        acc[4 * j + 1] += t.y;
+        acc[4 * j + 2] += t.z;
+        acc[4 * j + 3] += t.w;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < nvalid) acc[j] += __ldg(p.bias + nbase + j);
+    }
+  }
+  if (p.rowbias) {
+    const float* rb = p.rowbias + (m / p.rows_per_group) * p.ld_rowbias;
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (j < nvalid) acc[j] += __ldg(rb + nbase + j);
+  }
+  if (p.residual) {
+    const float* res = p.residual + (long long)z * p.stride_res + m * p.ld_res;
+    if (nvalid == 32 && ((reinterpret_cast<uintptr_t>(res + nbase) & 15) == 0)) {
+      const float4* r4 = reinterpret_cast<const float4*>(res + nbase);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 t = r4[j];
+        acc[4 * j + 0] += t.x;
+        acc[4 * j + 1] += t.y;
+        acc[4 * j + 2] += t.z;
+        acc[4 * j + 3] += t.w;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < nvalid) acc[j] += res[nbase + j];
+    }
+  }
+  int obase = nbase, ovalid = nvalid;
+  if (p.act == 1) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) acc[j] = silu_f(acc[j]);
+  } else if (p.act == 2) {
+    // weight rows were interleaved host-side: columns [32q, 32q+16) = value, [32q+16, 32q+32) = gate
+#pragma unroll
+    for (int j = 0; j < 16; ++j) acc[j] = acc[j] * gelu_erf_f(acc[16 + j]);
+    obase = nbase >> 1;
+    ovalid = nvalid >> 1;
+  }
+  if (p.out_f32) {
+    float* of = p.out_f32 + (long long)z * p.stride_out + m * p.ld_out_f32;
+    if (ovalid == 32 && ((reinterpret_cast<uintptr_t>(of + obase) & 15) == 0)) {
+      float4* o4 = reinterpret_cast<float4*>(of + obase);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o4[j] = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < ovalid) of[obase + j] = acc[j];
+    }
+  }
+  if (p.out_bf16) {
+    __nv_bfloat16* ob = p.out_bf16 + (long long)z * p.stride_out + m * p.ld_out_bf16;
+    if ((ovalid == 32 || ovalid == 16) && ((reinterpret_cast<uintptr_t>(ob + obase) & 15) == 0)) {
+      uint4* o4 = reinterpret_cast<uint4*>(ob + obase);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (8 * j < ovalid) {
+          __nv_bfloat162 h0 = __floats2bfloat162_rn(acc[8 * j + 0], acc[8 * j + 1]);
+          __nv_bfloat162 h1 = __floats2bfloat162_rn(acc[8 * j + 2], acc[8 * j + 3]);
+          __nv_bfloat162 h2 = __floats2bfloat162_rn(acc[8 * j + 4], acc[8 * j + 5]);
+          __nv_bfloat162 h3 = __floats2bfloat162_rn(acc[8 * j + 6], acc[8 * j + 7]);
+          uint4 pk;
+          pk.x = *reinterpret_cast<uint32_t*>(&h0);
+          pk.y = *reinterpret_cast<uint32_t*>(&h1);
+          pk.z = *reinterpret_cast<uint32_t*>(&h2);
+          pk.w = *reinterpret_cast<uint32_t*>(&h3);
+          o4[j] = pk;
+        }
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < ovalid) ob[obase + j] = __float2bfloat16_rn(acc[j]);
+    }
+  }
+}
+
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.aligned;\n\tbarrier.cluster.wait.aligned;" ::: "memory");
+}
+
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(kThreads)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmDev p) {
@@ -95,9 +197,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const int z = blockIdx.z;
   const int m0 = tile_m * BM;
   const int n0 = tile_n * BN;
-  const int zb = p.split ? 0 : z;  // batch coordinate of the tensor maps
-  const int kb0 = p.split ? z * p.kb_per_split : 0;
-  const int kb1 = p.split ? min(p.num_kblocks, kb0 + p.kb_per_split) : p.num_kblocks;
+  const bool ksplit = p.split || p.csplit > 1;
+  const int zb = ksplit ? 0 : z;  // batch coordinate of the tensor maps
+  const int kb0 = ksplit ? z * p.kb_per_split : 0;
+  const int kb1 = ksplit ? min(p.num_kblocks, kb0 + p.kb_per_split) : p.num_kblocks;
+  const int zo = p.csplit > 1 ? 0 : z;  // output / residual batch-or-partial index
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&tmA);
@@ -191,117 +295,76 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const long long m = (long long)m0 + row;
     pdl_wait();
     const bool row_ok = m < p.M;
-    if (p.residual && row_ok) {
+    if (p.residual && row_ok && p.csplit <= 1) {
       // pull this row's residual segment towards L2 while the main loop runs (BN*4 bytes = up to 4 lines)
-      const char* rp = reinterpret_cast<const char*>(p.residual + (long long)z * p.stride_res + m * p.ld_res + n0);
+      const char* rp = reinterpret_cast<const char*>(p.residual + (long long)zo * p.stride_res + m * p.ld_res + n0);
 #pragma unroll
       for (int l = 0; l < BN * 4 / 128; ++l) asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + l * 128));
     }
     ptx::mbar_wait(tmem_full_bar, 0);
     ptx::tcgen05_fence_after();
-    const float* rb = nullptr;
-    if (p.rowbias && row_ok) rb = p.rowbias + (m / p.rows_per_group) * p.ld_rowbias;
-    const float* res = p.residual ? p.residual + (long long)z * p.stride_res + m * p.ld_res : nullptr;
-    float* of = p.out_f32 ? p.out_f32 + (long long)z * p.stride_out + m * p.ld_out_f32 : nullptr;
-    __nv_bfloat16* ob = p.out_bf16 ? p.out_bf16 + (long long)z * p.stride_out + m * p.ld_out_bf16 : nullptr;
+    // cluster split-K: raw fp32 partial tile into this CTA's shared memory (the stage ring is idle once the
+    // accumulator is complete); row pitch BN+4 floats keeps the 16-byte row-owner stores conflict-free
+    float* red = reinterpret_cast<float*>(smem);
 #pragma unroll 1
     for (int c = 0; c < BN / 32; ++c) {
       uint32_t v[32];
       ptx::tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + c * 32, v);
       ptx::tmem_ld_wait();
-      const int nbase = n0 + c * 32;
-      if (!row_ok || nbase >= p.N) continue;
-      const int nvalid = min(32, p.N - nbase);
-      float acc[32];
+      if (p.csplit > 1) {
+        float4* dst = reinterpret_cast<float4*>(red + row * (BN + 4) + c * 32);
 #pragma unroll
-      for (int j = 0; j < 32; ++j) acc[j] = __uint_as_float(v[j]) * p.alpha;
-      if (p.bias) {
-        if (nvalid == 32) {
-          const float4* b4 = reinterpret_cast<const float4*>(p.bias + nbase);
+        for (int j = 0; j < 8; ++j)
+          dst[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                               __uint_as_float(v[4 * j + 3]));
+      } else {
+        float acc[32];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 t = __ldg(b4 + j);
-            acc[4 * j + 0] += t.x;
-            acc[4 * j + 1] += t.y;
-            acc[4 * j + 2] += t.z;
-            acc[4 * j + 3] += t.w;
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (j < nvalid) acc[j] += __ldg(p.bias + nbase + j);
-        }
-      }
-      if (rb) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (j < nvalid) acc[j] += __ldg(rb + nbase + j);
-      }
-      if (res) {
-        if (nvalid == 32 && ((reinterpret_cast<uintptr_t>(res + nbase) & 15) == 0)) {
-          const float4* r4 = reinterpret_cast<const float4*>(res + nbase);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 t = r4[j];
-            acc[4 * j + 0] += t.x;
-            acc[4 * j + 1] += t.y;
-            acc[4 * j + 2] += t.z;
-            acc[4 * j + 3] += t.w;
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (j < nvalid) acc[j] += res[nbase + j];
-        }
-      }
-      int obase = nbase, ovalid = nvalid;
-      if (p.act == 1) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) acc[j] = silu_f(acc[j]);
-      } else if (p.act == 2) {
-        // weight rows were interleaved host-side: columns [32q, 32q+16) = value, [32q+16, 32q+32) = gate
-#pragma unroll
-        for (int j = 0; j < 16; ++j) acc[j] = acc[j] * gelu_erf_f(acc[16 + j]);
-        obase = nbase >> 1;
-        ovalid = nvalid >> 1;
-      }
-      if (of) {
-        if (ovalid == 32 && ((reinterpret_cast<uintptr_t>(of + obase) & 15) == 0)) {
-          float4* o4 = reinterpret_cast<float4*>(of + obase);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) o4[j] = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (j < ovalid) of[obase + j] = acc[j];
-        }
-      }
-      if (ob) {
-        if ((ovalid == 32 || ovalid == 16) && ((reinterpret_cast<uintptr_t>(ob + obase) & 15) == 0)) {
-          uint4* o4 = reinterpret_cast<uint4*>(ob + obase);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            if (8 * j < ovalid) {
-              __nv_bfloat162 h0 = __floats2bfloat162_rn(acc[8 * j + 0], acc[8 * j + 1]);
-              __nv_bfloat162 h1 = __floats2bfloat162_rn(acc[8 * j + 2], acc[8 * j + 3]);
-              __nv_bfloat162 h2 = __floats2bfloat162_rn(acc[8 * j + 4], acc[8 * j + 5]);
-              __nv_bfloat162 h3 = __floats2bfloat162_rn(acc[8 * j + 6], acc[8 * j + 7]);
-              uint4 pk;
-              pk.x = *reinterpret_cast<uint32_t*>(&h0);
-              pk.y = *reinterpret_cast<uint32_t*>(&h1);
-              pk.z = *reinterpret_cast<uint32_t*>(&h2);
-              pk.w = *reinterpret_cast<uint32_t*>(&h3);
-              o4[j] = pk;
-            }
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (j < ovalid) ob[obase + j] = __float2bfloat16_rn(acc[j]);
-        }
+        for (int j = 0; j < 32; ++j) acc[j] = __uint_as_float(v[j]) * p.alpha;
+        epilogue_chunk(p, acc, m, n0 + c * 32, zo);
       }
     }
     ptx::tcgen05_fence_before();
+  }
+  if (p.csplit > 1) {
+    // ---- distributed-shared-memory reduction: CTA `z` of the cluster finalises rows [z*R, (z+1)*R), R = 128/csplit,
+    //      summing the csplit partial tiles in rank order (fixed order -> deterministic), then runs the epilogue
+    cluster_sync_all();
+    if (warp >= 2) {
+      const int S = p.csplit;
+      const int R = BM / S;
+      constexpr int CH = BN / 32;
+      const uint32_t red_local = ptx::smem_u32(smem);
+      for (int item = threadIdx.x - 64; item < R * CH; item += kThreads - 64) {
+        const int lr = item / CH, c = item - lr * CH;
+        const int rrow = z * R + lr;
+        float acc[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc[j] = 0.f;
+        const uint32_t off = static_cast<uint32_t>((rrow * (BN + 4) + c * 32) * 4);
+        for (int s = 0; s < S; ++s) {
+          uint32_t raddr;
+          asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(red_local + off), "r"(s));
+          float4 t[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];"
+                         : "=f"(t[j].x), "=f"(t[j].y), "=f"(t[j].z), "=f"(t[j].w)
+                         : "r"(raddr + j * 16));
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            acc[4 * j + 0] += t[j].x;
+            acc[4 * j + 1] += t[j].y;
+            acc[4 * j + 2] += t[j].z;
+            acc[4 * j + 3] += t[j].w;
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc[j] *= p.alpha;
+        epilogue_chunk(p, acc, (long long)m0 + rrow, n0 + c * 32, 0);
+      }
+    }
+    cluster_sync_all();  // nobody leaves while a peer may still read its partial tile
   }
   __syncthreads();
   if (warp == 1) {
@@ -469,7 +532,27 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmDev& p, int
     attr_set = true;
   }
   dim3 grid((p.M + BM - 1) / BM, (p.N + BN - 1) / BN, gz);
-  cudaError_t e = launch_kernel_early(gemm_tcgen05_kernel<BN, STAGES>, grid, dim3(kThreads), (size_t)L::kTotal, st, tmA, tmB, p);
+  cudaError_t e;
+  if (p.csplit > 1) {
+    // thread-block cluster (1,1,csplit): the K slices of one output tile are co-scheduled and reduce through DSMEM
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = (size_t)L::kTotal;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 1;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = (unsigned)p.csplit;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = g_use_pdl ? 2 : 1;
+    e = cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<BN, STAGES>, tmA, tmB, p);
+  } else {
+    e = launch_kernel_early(gemm_tcgen05_kernel<BN, STAGES>, grid, dim3(kThreads), (size_t)L::kTotal, st, tmA, tmB, p);
+  }
   if (e != cudaSuccess) return fail(AE_ECUDA, "ae_gemm launch: %s", cudaGetErrorString(e));
   return launched("ae_gemm");
 }
@@ -516,6 +599,7 @@ extern "C" int ae_gemm(const ae_gemm_args* a, ae_stream stream) {
   p.dil_h = p.dil_w = 1;
   p.pad_h = p.pad_w = 0;
   p.split = 0;
+  p.csplit = 0;
 
   CUtensorMap tmA, tmB;
   int rc;
@@ -571,9 +655,23 @@ extern "C" int ae_gemm(const ae_gemm_args* a, ae_stream stream) {
   AE_CHECK_ARG(bn == 32 || bn == 64 || bn == 128, "ae_gemm: force_bn must be 32, 64 or 128");
   const long long tiles = tiles_m * ((a->N + bn - 1) / bn);
 
-  // ---- split-K: only un-batched problems whose tile grid leaves most SMs idle and whose K is deep enough
+  // ---- cluster split-K (preferred): the K slices of a tile form a thread-block cluster and reduce through DSMEM —
+  //      one launch, no workspace.  Cluster sizes 2 / 4 / 8 (must divide the 128 tile rows).
+  int CS = 1;
+  if (batch == 1 && a->force_csplit != 1 && a->force_split <= 1) {
+    if (a->force_csplit > 1)
+      CS = a->force_csplit;
+    else if (tiles <= 64 && p.num_kblocks >= 6) {
+      int lim = (int)(148 / tiles);
+      if (lim > p.num_kblocks / 3) lim = p.num_kblocks / 3;
+      CS = lim >= 8 ? 8 : (lim >= 4 ? 4 : (lim >= 2 ? 2 : 1));
+    }
+    if (CS > p.num_kblocks) CS = 1;
+    AE_CHECK_ARG(CS == 1 || CS == 2 || CS == 4 || CS == 8, "ae_gemm: force_csplit must be 1, 2, 4 or 8");
+  }
+  // ---- workspace split-K (two launches): kept for explicit requests (force_split > 1)
   int S = 1;
-  if (batch == 1 && a->act != 2 && a->splitk_ws && a->N % 4 == 0 && a->force_split != 1) {
+  if (CS == 1 && batch == 1 && a->act != 2 && a->splitk_ws && a->N % 4 == 0 && a->force_split > 1) {
     if (a->force_split > 1)
       S = a->force_split;
     else if (tiles <= 48 && p.num_kblocks >= 12) {
@@ -596,6 +694,11 @@ extern "C" int ae_gemm(const ae_gemm_args* a, ae_stream stream) {
   cudaStream_t st = as_stream(stream);
   int gz = batch;
   GemmDev q = p;
+  if (CS > 1) {
+    q.csplit = CS;
+    q.kb_per_split = (p.num_kblocks + CS - 1) / CS;
+    gz = CS;
+  }
   if (S > 1) {
     q.split = 1;
     q.kb_per_split = (p.num_kblocks + S - 1) / S;
@@ -612,7 +715,7 @@ extern "C" int ae_gemm(const ae_gemm_args* a, ae_stream stream) {
     q.alpha = 1.0f;
   }
   const long long ctas = tiles * gz;
-  const bool deep = a->force_stages ? (a->force_stages > 3) : (ctas <= 160);
+  const bool deep = a->force_stages ? (a->force_stages > 3) : (ctas <= 160 || CS > 1);
   switch (bn) {
     case 32:
       rc = deep ? launch<32, 6>(tmA, tmB, q, gz, st) : launch<32, 3>(tmA, tmB, q, gz, st);

@@ -62,7 +62,7 @@ class CudaOps:
     # ---------------------------------------------------------------- GEMM / conv
     def gemm(self, A, W, *, out_f32=None, out_bf16=None, bias=None, rowbias=None, rows_per_group=1, residual=None,
              act=0, alpha=1.0, conv=None, M=None, K=None, force_bn=0, batch=1, strideA=0, strideW=0, stride_out=0,
-             stride_res=0, lda=None, ldw=None, force_split=0, ld_out_f32=None, ld_out_bf16=None, force_stages=0, w_dynamic=False):
+             stride_res=0, lda=None, ldw=None, force_split=0, ld_out_f32=None, ld_out_bf16=None, force_stages=0, w_dynamic=False, force_csplit=0):
         """D = alpha*A@W^T (+bias)(+rowbias[row//rows_per_group])(+residual) -> act.  conv=(B,H,W,C,kh,kw,dh,dw)
         turns A (channels-last image) into an implicit-GEMM operand."""
         a = AeGemmArgs()
@@ -105,6 +105,7 @@ class CudaOps:
         a.force_split = force_split
         a.force_stages = force_stages
         a.w_dynamic = 1 if w_dynamic else 0
+        a.force_csplit = force_csplit
         if batch == 1 and act != 2:
             ws = self._splitk_workspace(A.device)
             a.splitk_ws = ws.data_ptr()

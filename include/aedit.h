@@ -149,6 +149,8 @@ typedef struct {
   float* splitk_ws;
   int64_t splitk_ws_bytes;
   int32_t force_split;
+  int32_t force_csplit; /* cluster split-K (K slices of a tile in one thread-block cluster, DSMEM reduction, single
+                           launch): 0 auto, 1 never, 2/4/8 exactly that cluster size */
   int32_t w_dynamic;    /* 1 if W is written by a preceding kernel on the stream (e.g. K or V^T of an unfused attention):
                            disables the early W prefetch that otherwise overlaps the previous kernel's tail */
   int32_t force_stages; /* 0 auto (deep 6-stage ring for grids <= 160 CTAs, else 3 stages x 2-3 CTAs/SM), 3 or 6 */

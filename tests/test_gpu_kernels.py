@@ -76,6 +76,57 @@ def test_gemm_splitk(ops, M, N, K, S):
     assert torch.equal(o32, o_b)
 
 
+@pytest.mark.parametrize("M,N,K,CS", [(128, 960, 960, 2), (128, 960, 960, 4), (128, 960, 8640, 8), (512, 576, 576, 2),
+                                      (100, 200, 1000, 4), (2048, 384, 384, 2), (128, 7680, 960, 0), (256, 64, 4096, 8)])
+def test_gemm_cluster_splitk(ops, M, N, K, CS):
+    """cluster split-K: the K slices of one tile run as a thread-block cluster and reduce through distributed
+    shared memory in rank order; every epilogue term applied once; bit-reproducible."""
+    A = rnd((M, K), 1, dtype=BF)
+    W = rnd((N, K), 2, 1 / math.sqrt(K), dtype=BF)
+    bias, res = rnd((N,), 3), rnd((M, N), 4)
+    rowbias = rnd(((M + 63) // 64, N), 5)
+    o32 = torch.empty(M, N, device="cuda")
+    o16 = torch.empty(M, N, device="cuda", dtype=BF)
+    kw = dict(bias=bias, rowbias=rowbias, rows_per_group=64, residual=res, act=1, alpha=0.5)
+    ops.gemm(A, W, out_f32=o32, out_bf16=o16, force_csplit=CS, **kw)
+    ref = F.silu(0.5 * (A.float() @ W.float().t()) + bias + res + rowbias.repeat_interleave(64, 0)[:M])
+    assert relerr(o32, ref) < 2e-5
+    assert relerr(o16, ref) < 4e-3
+    o_b = torch.empty_like(o32)
+    ops.gemm(A, W, out_f32=o_b, force_csplit=CS, **kw)
+    assert torch.equal(o32, o_b)
+    # in-place residual (out == residual) as used by the transformer blocks
+    hs = res.clone()
+    ops.gemm(A, W, out_f32=hs, bias=bias, residual=hs, force_csplit=CS)
+    assert relerr(hs, A.float() @ W.float().t() + bias + res) < 2e-5
+
+
+def test_gemm_cluster_splitk_conv_and_geglu(ops):
+    B, H, Wd, C, Co = 2, 32, 2, 960, 960
+    x = rnd((B, H, Wd, C), 1, dtype=BF)
+    wt = rnd((Co, C, 3, 3), 2, 1 / math.sqrt(C * 9), dtype=BF)
+    bias = rnd((Co,), 3)
+    Wp = wt.permute(0, 2, 3, 1).reshape(Co, -1).contiguous()
+    out = torch.empty(B * H * Wd, Co, device="cuda")
+    for cs in (0, 2, 4, 8):
+        ops.gemm(x, Wp, out_f32=out, bias=bias, conv=(B, H, Wd, C, 3, 3, 1, 1), force_csplit=cs)
+        ref = F.conv2d(x.float().permute(0, 3, 1, 2), wt.float(), bias, padding=1).permute(0, 2, 3, 1).reshape(-1, Co)
+        assert relerr(out, ref) < 2e-5, cs
+    # GEGLU epilogue through the cluster reduction
+    M, Cc = 128, 960
+    inner = 4 * Cc
+    xx = rnd((M, Cc), 4, dtype=BF)
+    Wf = rnd((2 * inner, Cc), 5, 1 / math.sqrt(Cc), dtype=BF)
+    bf = rnd((2 * inner,), 6)
+    idx = torch.arange(inner).view(-1, 16)
+    perm = torch.cat([idx, idx + inner], 1).reshape(-1).cuda()
+    o = torch.empty(M, inner, device="cuda", dtype=BF)
+    ops.gemm(xx, Wf[perm].contiguous(), out_bf16=o, bias=bf[perm].contiguous(), act=2, force_csplit=2)
+    h = xx.float() @ Wf.float().t() + bf
+    a, gt = h.chunk(2, -1)
+    assert relerr(o, a * F.gelu(gt)) < 4e-3
+
+
 @pytest.mark.parametrize("M,C", [(300, 64), (4096, 192), (128, 960)])
 def test_gemm_geglu_epilogue(ops, M, C):
     """FF1 + GEGLU fused (act=2, interleaved weight rows) == chunk(2) -> value * gelu(gate) (attention.py:37-44)."""
