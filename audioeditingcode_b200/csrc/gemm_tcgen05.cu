@@ -564,6 +564,9 @@ using namespace aedit;
 
 extern "C" void ae_set_pdl(int mode) { g_use_pdl = (mode == 1 || mode == 2) ? mode : 0; }
 
+static int g_splitk_ctas = 148;
+extern "C" void ae_set_splitk_ctas(int ctas) { g_splitk_ctas = ctas < 1 ? 148 : ctas; }
+
 extern "C" int ae_gemm_conv_supported(int B, int H, int W, int C) {
   ConvBox bx;
   return (C % BK == 0 && conv_box(B, H, W, &bx)) ? 1 : 0;
@@ -655,27 +658,23 @@ extern "C" int ae_gemm(const ae_gemm_args* a, ae_stream stream) {
   AE_CHECK_ARG(bn == 32 || bn == 64 || bn == 128, "ae_gemm: force_bn must be 32, 64 or 128");
   const long long tiles = tiles_m * ((a->N + bn - 1) / bn);
 
-  // ---- cluster split-K (preferred): the K slices of a tile form a thread-block cluster and reduce through DSMEM —
-  //      one launch, no workspace.  Cluster sizes 2 / 4 / 8 (must divide the 128 tile rows).
+  // ---- cluster split-K (opt-in, force_csplit = 2 / 4 / 8): the K slices of a tile form a thread-block cluster and
+  //      reduce through DSMEM in one launch.  Measured slower than the workspace variant on B200 (cluster launch +
+  //      two cluster barriers cost ~7 us, profiles/r01_microbench_v8.log), so it is never chosen automatically.
   int CS = 1;
-  if (batch == 1 && a->force_csplit != 1 && a->force_split <= 1) {
-    if (a->force_csplit > 1)
-      CS = a->force_csplit;
-    else if (tiles <= 64 && p.num_kblocks >= 6) {
-      int lim = (int)(148 / tiles);
-      if (lim > p.num_kblocks / 3) lim = p.num_kblocks / 3;
-      CS = lim >= 8 ? 8 : (lim >= 4 ? 4 : (lim >= 2 ? 2 : 1));
-    }
-    if (CS > p.num_kblocks) CS = 1;
-    AE_CHECK_ARG(CS == 1 || CS == 2 || CS == 4 || CS == 8, "ae_gemm: force_csplit must be 1, 2, 4 or 8");
+  if (batch == 1 && a->force_csplit > 1) {
+    CS = a->force_csplit;
+    AE_CHECK_ARG(CS == 2 || CS == 4 || CS == 8, "ae_gemm: force_csplit must be 1, 2, 4 or 8");
+    // every rank needs at least one K block (an idle rank would publish an unwritten accumulator)
+    while (CS > 1 && (long long)(CS - 1) * ((p.num_kblocks + CS - 1) / CS) >= p.num_kblocks) CS >>= 1;
   }
-  // ---- workspace split-K (two launches): kept for explicit requests (force_split > 1)
+  // ---- workspace split-K (two launches): partial tiles to an fp32 workspace, fixed-order reduce + epilogue kernel
   int S = 1;
-  if (CS == 1 && batch == 1 && a->act != 2 && a->splitk_ws && a->N % 4 == 0 && a->force_split > 1) {
+  if (CS == 1 && batch == 1 && a->act != 2 && a->splitk_ws && a->N % 4 == 0 && a->force_split != 1) {
     if (a->force_split > 1)
       S = a->force_split;
     else if (tiles <= 48 && p.num_kblocks >= 12) {
-      S = (int)(148 / tiles);
+      S = (int)(g_splitk_ctas / tiles);
       const int max_by_k = p.num_kblocks / 6;
       if (S > max_by_k) S = max_by_k;
       if (S > 32) S = 32;

@@ -231,6 +231,210 @@ __global__ void __launch_bounds__(kGNThreads) gn_apply_kernel(GNArgs a) {
   }
 }
 
+// ---- small-batch path: ONE launch per GroupNorm.  grid (CS, B) with thread-block clusters of CS CTAs along x: the
+// CS CTAs of a sample each own HW/CS positions, (1) read them once — keeping them in shared memory when the slice
+// fits (STAGE) —, (2) reduce to per-group partial sums, (3) exchange the partials through distributed shared
+// memory in rank order (fixed order -> the same bits in every CTA, independent of the batch), (4) normalise from
+// the staged copy.  Replaces a stats launch + an apply launch when the whole tensor is a few MB and the two
+// launches' latency, not bandwidth, is the cost (reverse process, B = 2).
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+
+template <bool STAGE>
+__global__ void __launch_bounds__(512) gn_fused_kernel(GNArgs a) {
+  pdl_trigger();
+  pdl_wait();
+  extern __shared__ __align__(16) float sm[];
+  // layout: part[G][2] double | mean[G] rstd[G] | A[C] B[C] | red[TY][2C] | stage[chunk][C] (STAGE only)
+  const int TX = blockDim.x, TY = blockDim.y;
+  double* s_part = reinterpret_cast<double*>(sm);
+  float* s_mean = sm + 4 * a.G;
+  float* s_rstd = s_mean + a.G;
+  float* s_A = s_rstd + a.G;
+  float* s_B = s_A + a.C;
+  float* s_red = s_B + a.C;
+  float* s_stage = s_red + (size_t)TY * 2 * a.C;
+  const int rank = blockIdx.x, CS = gridDim.x, b = blockIdx.y;
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int tid = ty * TX + tx, nthr = TX * TY;
+  const int lane = tid & 31, wid = tid >> 5, nw = nthr >> 5;
+  const long long p0 = (long long)rank * a.chunk;
+  const long long p1 = min(a.HW, p0 + a.chunk);
+  const int nq = a.C >> 2;
+  float su[kGNMaxQuadsPerThread][4], sq[kGNMaxQuadsPerThread][4];
+#pragma unroll
+  for (int k = 0; k < kGNMaxQuadsPerThread; ++k)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) su[k][e] = sq[k][e] = 0.f;
+  for (long long pb = p0 + ty; pb < p1; pb += (long long)TY * kGNUnroll) {
+    float4 v[kGNUnroll][kGNMaxQuadsPerThread];
+#pragma unroll
+    for (int u = 0; u < kGNUnroll; ++u) {
+      const long long p = pb + (long long)u * TY;
+      const long long row = (long long)b * a.HW + p;
+#pragma unroll
+      for (int k = 0; k < kGNMaxQuadsPerThread; ++k) {
+        const int qd = tx + k * TX;
+        if (p < p1 && qd < nq) {
+          const int c = qd << 2;
+          v[u][k] = c < a.C1 ? *reinterpret_cast<const float4*>(a.x1 + row * a.C1 + c)
+                             : *reinterpret_cast<const float4*>(a.x2 + row * a.C2 + (c - a.C1));
+        } else {
+          v[u][k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kGNUnroll; ++u) {
+      const long long p = pb + (long long)u * TY;
+#pragma unroll
+      for (int k = 0; k < kGNMaxQuadsPerThread; ++k) {
+        su[k][0] += v[u][k].x; sq[k][0] += v[u][k].x * v[u][k].x;
+        su[k][1] += v[u][k].y; sq[k][1] += v[u][k].y * v[u][k].y;
+        su[k][2] += v[u][k].z; sq[k][2] += v[u][k].z * v[u][k].z;
+        su[k][3] += v[u][k].w; sq[k][3] += v[u][k].w * v[u][k].w;
+        if (STAGE) {
+          const int qd = tx + k * TX;
+          if (p < p1 && qd < nq) *reinterpret_cast<float4*>(s_stage + (size_t)(p - p0) * a.C + (qd << 2)) = v[u][k];
+        }
+      }
+    }
+  }
+  {
+    float* mysum = s_red + (size_t)ty * 2 * a.C;
+#pragma unroll
+    for (int k = 0; k < kGNMaxQuadsPerThread; ++k) {
+      const int qd = tx + k * TX;
+      if (qd < nq) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          mysum[(qd << 2) + e] = su[k][e];
+          mysum[a.C + (qd << 2) + e] = sq[k][e];
+        }
+      }
+    }
+  }
+  __syncthreads();
+  {
+    const int per = TY * a.cpg;
+    for (int g = wid; g < a.G; g += nw) {
+      double dsu = 0.0, dsq = 0.0;
+      for (int e = lane; e < per; e += 32) {
+        const int y = e / a.cpg, c = g * a.cpg + (e - y * a.cpg);
+        const float* r = s_red + (size_t)y * 2 * a.C;
+        dsu += (double)r[c];
+        dsq += (double)r[a.C + c];
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        dsu += __shfl_down_sync(0xffffffffu, dsu, o);
+        dsq += __shfl_down_sync(0xffffffffu, dsq, o);
+      }
+      if (lane == 0) {
+        s_part[2 * g] = dsu;
+        s_part[2 * g + 1] = dsq;
+      }
+    }
+  }
+  __syncthreads();
+  cluster_arrive();   // release: this CTA's partials are published
+  cluster_wait();     // acquire: every peer's partials are visible
+  {
+    // group g <- thread g: the CS partials are fetched with independent DSMEM loads, then summed in rank order
+    const uint32_t part_addr = (uint32_t)__cvta_generic_to_shared(s_part);
+    for (int g = tid; g < a.G; g += nthr) {
+      double ps[16], pq[16];
+#pragma unroll
+      for (int r = 0; r < 16; ++r) {
+        ps[r] = 0.0;
+        pq[r] = 0.0;
+        if (r < CS) {
+          uint32_t raddr;
+          asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(part_addr + (uint32_t)g * 16u), "r"(r));
+          asm volatile("ld.shared::cluster.v2.f64 {%0, %1}, [%2];" : "=d"(ps[r]), "=d"(pq[r]) : "r"(raddr) : "memory");
+        }
+      }
+      double dsu = 0.0, dsq = 0.0;
+#pragma unroll
+      for (int r = 0; r < 16; ++r) {
+        dsu += ps[r];
+        dsq += pq[r];
+      }
+      const double inv_n = 1.0 / ((double)a.HW * a.cpg);
+      const double mean = dsu * inv_n;
+      double var = dsq * inv_n - mean * mean;
+      if (var < 0.0) var = 0.0;
+      s_mean[g] = (float)mean;
+      s_rstd[g] = rsqrtf((float)var + a.eps);
+    }
+  }
+  __syncthreads();
+  cluster_arrive();   // this CTA no longer reads its peers' shared memory (matched by the wait before exit)
+  for (int c = tid; c < a.C; c += nthr) {
+    const int g = c / a.cpg;
+    const float A = s_rstd[g] * __ldg(a.gamma + c);
+    s_A[c] = A;
+    s_B[c] = __ldg(a.beta + c) - s_mean[g] * A;
+  }
+  __syncthreads();
+  for (long long pb = p0 + ty; pb < p1; pb += (long long)TY * kGNUnroll) {
+    float4 v[kGNUnroll][kGNMaxQuadsPerThread];
+#pragma unroll
+    for (int u = 0; u < kGNUnroll; ++u) {
+      const long long p = pb + (long long)u * TY;
+      const long long row = (long long)b * a.HW + p;
+#pragma unroll
+      for (int k = 0; k < kGNMaxQuadsPerThread; ++k) {
+        const int qd = tx + k * TX;
+        if (p < p1 && qd < nq) {
+          const int c = qd << 2;
+          if (STAGE)
+            v[u][k] = *reinterpret_cast<const float4*>(s_stage + (size_t)(p - p0) * a.C + c);
+          else
+            v[u][k] = c < a.C1 ? *reinterpret_cast<const float4*>(a.x1 + row * a.C1 + c)
+                               : *reinterpret_cast<const float4*>(a.x2 + row * a.C2 + (c - a.C1));
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kGNUnroll; ++u) {
+      const long long p = pb + (long long)u * TY;
+      const long long row = (long long)b * a.HW + p;
+#pragma unroll
+      for (int k = 0; k < kGNMaxQuadsPerThread; ++k) {
+        const int qd = tx + k * TX;
+        if (p >= p1 || qd >= nq) continue;
+        const int c = qd << 2;
+        const float in[4] = {v[u][k].x, v[u][k].y, v[u][k].z, v[u][k].w};
+        const float4 A4 = *reinterpret_cast<const float4*>(s_A + c);
+        const float4 B4 = *reinterpret_cast<const float4*>(s_B + c);
+        float o[4] = {fmaf(in[0], A4.x, B4.x), fmaf(in[1], A4.y, B4.y), fmaf(in[2], A4.z, B4.z), fmaf(in[3], A4.w, B4.w)};
+        if (a.silu) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) o[e] = silu_f(o[e]);
+        }
+        const long long off = row * a.C + c;
+        __nv_bfloat162 h0 = __floats2bfloat162_rn(o[0], o[1]);
+        __nv_bfloat162 h1 = __floats2bfloat162_rn(o[2], o[3]);
+        uint2 pk;
+        pk.x = *reinterpret_cast<uint32_t*>(&h0);
+        pk.y = *reinterpret_cast<uint32_t*>(&h1);
+        *reinterpret_cast<uint2*>(a.out + off) = pk;
+        if (a.raw_out) {
+          __nv_bfloat162 r0 = __floats2bfloat162_rn(in[0], in[1]);
+          __nv_bfloat162 r1 = __floats2bfloat162_rn(in[2], in[3]);
+          uint2 rk;
+          rk.x = *reinterpret_cast<uint32_t*>(&r0);
+          rk.y = *reinterpret_cast<uint32_t*>(&r1);
+          *reinterpret_cast<uint2*>(a.raw_out + off) = rk;
+        }
+        if (a.cat_out) *reinterpret_cast<float4*>(a.cat_out + off) = v[u][k];
+      }
+    }
+  }
+  cluster_wait();     // do not exit (and free shared memory) while a peer may still be reading the partials
+}
+
 // one warp per row; the row is read once into registers: NV float4 per lane (C <= 128*NV), NV a template constant
 template <int NV>
 __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, long long rows, int C, float eps,
@@ -295,6 +499,9 @@ cudaError_t launch_ln(const float* x, long long rows, int C, float eps, const fl
 
 using namespace aedit;
 
+static int g_gn_fused = 1;
+extern "C" void ae_set_gn_fused(int on) { g_gn_fused = on ? 1 : 0; }
+
 extern "C" int64_t ae_groupnorm_workspace_bytes(int B, int groups) {
   // partial sums [B, kMaxSplits, G, 2] double + stats [B, G, 2] float + counters [B] u32 (must start zeroed)
   return (int64_t)B * kMaxSplits * groups * 2 * 8 + (int64_t)B * groups * 2 * 4 + (int64_t)B * 4 + 64;
@@ -328,6 +535,61 @@ extern "C" int ae_groupnorm(const float* x1, int C1, const float* x2, int C2, in
   int TY = 512 / TX;
   if (TY > 16) TY = 16;
   if (TY < 1) TY = 1;
+  a.eps = eps;
+  a.gamma = gamma;
+  a.beta = beta;
+  a.silu = silu;
+  a.out = reinterpret_cast<__nv_bfloat16*>(out_bf16);
+  a.raw_out = reinterpret_cast<__nv_bfloat16*>(raw_out_bf16);
+  a.cat_out = cat_out_f32;
+  a.partial = nullptr;
+  a.stats = nullptr;
+  a.counters = nullptr;
+  if (g_gn_fused && B <= 8 && HW * (int64_t)C * 4 <= (8ll << 20) && groups % 2 == 0) {
+    // fused single-launch path (thread-block clusters); cluster size: up to 16 (non-portable, enabled once),
+    // at least TY positions per CTA
+    static int max_cs = 0;
+    if (max_cs == 0) {
+      max_cs = 8;
+      if (cudaFuncSetAttribute(gn_fused_kernel<true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess &&
+          cudaFuncSetAttribute(gn_fused_kernel<false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess)
+        max_cs = 16;
+      cudaFuncSetAttribute(gn_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      cudaFuncSetAttribute(gn_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+      cudaGetLastError();
+    }
+    int CS = max_cs;
+    while (CS > 1 && HW / CS < TY) CS >>= 1;
+    a.S = CS;
+    a.chunk = ceil_div64(HW, CS);
+    if ((int)ceil_div64(HW, a.chunk) == CS) {   // every rank owns at least one position
+      const size_t fixed = (size_t)(4 * groups + 2 * groups + 2 * C + TY * 2 * C) * sizeof(float);
+      const size_t stage = (size_t)a.chunk * C * sizeof(float);
+      const bool staged = fixed + stage <= 200 * 1024;
+      const size_t smem = fixed + (staged ? stage : 0);
+      if (smem <= 227 * 1024) {
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(CS, B);
+        cfg.blockDim = dim3(TX, TY);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = as_stream(stream);
+        cudaLaunchAttribute attr[2];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = (unsigned)CS;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[1].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = g_use_pdl == 1 ? 2 : 1;
+        if (staged)
+          cudaLaunchKernelEx(&cfg, gn_fused_kernel<true>, a);
+        else
+          cudaLaunchKernelEx(&cfg, gn_fused_kernel<false>, a);
+        return launched("ae_groupnorm(fused)");
+      }
+    }
+  }
   // position splits: enough CTAs to cover the machine at small batch, never more than kMaxSplits per sample
   int S = (int)ceil_div64(HW, 4 * TY);
   const int want = (296 + B - 1) / B;

@@ -30,7 +30,7 @@ from tqdm import tqdm
 from .. import _lib
 from ..models import PipelineWrapper, _ptr, _stream
 
-DEFAULT_FORWARD_BATCH = int(os.environ.get("AEDIT_FORWARD_BATCH", "8"))
+DEFAULT_FORWARD_BATCH = int(os.environ.get("AEDIT_FORWARD_BATCH", "50"))
 USE_CUDA_GRAPHS = os.environ.get("AEDIT_CUDA_GRAPH", "1") != "0"
 
 

@@ -42,8 +42,13 @@ class CudaOps:
         self._gn_ws = {}
         self._splitk_ws = {}
         import os
-        # programmatic dependent launch measured slower end to end on B200 (profiles/r01_*): opt-in only
-        self.lib.ae_set_pdl(int(os.environ.get("AEDIT_PDL", "0")))   # 0 off, 1 all kernels, 2 GEMMs only
+        # programmatic dependent launch: GEMM-only mode (weight prefetch ahead of the dependency wait) measured +2-4 %
+        # end to end on B200, all-kernel mode measured slower (profiles/r01_bench_v7_*, r01_bench_v8_*)
+        self.lib.ae_set_pdl(int(os.environ.get("AEDIT_PDL", "2")))   # 0 off, 1 all kernels, 2 GEMMs only
+        if "AEDIT_GN_FUSED" in os.environ:
+            self.lib.ae_set_gn_fused(int(os.environ["AEDIT_GN_FUSED"]))
+        if "AEDIT_SPLITK_CTAS" in os.environ:
+            self.lib.ae_set_splitk_ctas(int(os.environ["AEDIT_SPLITK_CTAS"]))
 
     def _splitk_workspace(self, device):
         ws = self._splitk_ws.get(str(device))

@@ -51,18 +51,44 @@ class GraphedForward:
         self.slot = None if slot_map is None else slot_map.to(dev, torch.int32).clone()
         self.cl = None if class_labels is None else class_labels.to(dev, F32).clone()
         self.text = text
+        # Small batches are launch-latency bound (each kernel is a fraction of a wave): with AEDIT_DUAL_STREAM=1 the
+        # batch is cut in two halves captured on two forked streams of the same graph, so the two dependency chains
+        # interleave on the SMs.  Each chain owns its workspaces (second CudaOps instance).
+        self.dual = engine.dual_stream and B % 2 == 0 and B <= engine.dual_stream_max_b
         cur = torch.cuda.current_stream()
         side = torch.cuda.Stream()
+        self._side2 = torch.cuda.Stream() if self.dual else None
         side.wait_stream(cur)
         with torch.cuda.stream(side):
             for _ in range(2):          # warm-up outside capture: workspaces, smem attributes, lazy allocations
-                engine.forward(self.x, self.t, text=text, slot_map=self.slot, class_labels=self.cl)
+                self._run(engine)
         cur.wait_stream(side)
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
-            self.out = engine.forward(self.x, self.t, text=text, slot_map=self.slot, class_labels=self.cl)
-        self.launches = 0
+            self.out = self._run(engine)
+
+    def _run(self, engine):
+        if not self.dual:
+            return engine.forward(self.x, self.t, text=self.text, slot_map=self.slot, class_labels=self.cl)
+        h = self.x.shape[0] // 2
+        sl = (lambda v, a, b: None if v is None else v[a:b])
+        cur = torch.cuda.current_stream()
+        s2 = self._side2
+        out = torch.empty((self.x.shape[0], engine.cfg.out_channels, *self.x.shape[2:]), device=self.x.device, dtype=F32)
+        s2.wait_stream(cur)                                            # fork
+        engine.forward(self.x[:h], self.t[:h], text=self.text, slot_map=sl(self.slot, 0, h),
+                       class_labels=sl(self.cl, 0, h), out=out[:h])
+        main_ops = engine.ops
+        engine.ops = engine.ops_b()
+        try:
+            with torch.cuda.stream(s2):
+                engine.forward(self.x[h:], self.t[h:], text=self.text, slot_map=sl(self.slot, h, None),
+                               class_labels=sl(self.cl, h, None), out=out[h:])
+        finally:
+            engine.ops = main_ops
+        cur.wait_stream(s2)                                            # join
+        return out
 
     def __call__(self, x, t, class_labels=None):
         self.x.copy_(x)
@@ -89,6 +115,15 @@ class UNetEngine:
         import os
         # below this width the 4-D TMA boxes degenerate into 256-byte bursts; gather patches explicitly instead
         self.min_implicit_w = int(os.environ.get("AEDIT_MIN_IMPLICIT_W", "2"))
+        self.dual_stream = os.environ.get("AEDIT_DUAL_STREAM", "0") != "0"
+        self.dual_stream_max_b = int(os.environ.get("AEDIT_DUAL_STREAM_MAX_B", "4"))
+        self._ops_b = None
+
+    def ops_b(self):
+        """Second ops instance (own split-K / GroupNorm workspaces) for the forked chain of a dual-stream graph."""
+        if self._ops_b is None:
+            self._ops_b = type(self.ops)()
+        return self._ops_b
 
     def graphed(self, B, H, W, text=None, slot_map=None, class_labels=None, slot_key=None) -> GraphedForward:
         """Cached CUDA-graph evaluator for this geometry / text binding.  `slot_key`: hashable description of

@@ -246,7 +246,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="audioldm2-large-10s", choices=sorted(CONFIGS))
-    ap.add_argument("--forward-batch", type=int, default=int(os.environ.get("AEDIT_FORWARD_BATCH", "8")))
+    ap.add_argument("--forward-batch", type=int, default=int(os.environ.get("AEDIT_FORWARD_BATCH", "50")))
     ap.add_argument("--cpu-steps", type=int, default=0, help="CFG steps of the cpu_baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

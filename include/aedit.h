@@ -37,9 +37,17 @@ int ae_version(void);
 int64_t ae_launch_count(void);
 /* 1 if the current device is compute capability 10.x */
 int ae_device_ok(void);
-/* Programmatic dependent launch for every kernel of the library (default on): each kernel lets its successor in the
- * stream start early (prologue overlap) and waits for its predecessor before touching global memory. */
+/* Programmatic dependent launch: a kernel launched with it may start (prologue, weight prefetch) before its
+ * predecessor in the stream has drained, and waits for it before touching dependent global memory. */
 void ae_set_pdl(int mode); /* 0 off (default), 1 every kernel, 2 GEMM kernels only */
+
+/* CTA budget the automatic split-K heuristic fills (default 148 = one per SM).  Callers that run two dependency chains
+ * concurrently on forked streams lower it so that the chains share the SMs instead of queueing behind each other. */
+void ae_set_splitk_ctas(int ctas);
+
+/* GroupNorm of small tensors (B <= 8, <= 8 MB per sample) as ONE thread-block-cluster launch (default on) instead of a
+ * statistics launch + an apply launch. */
+void ae_set_gn_fused(int on);
 
 /* ------------------------------------------------------------------------------------------------
  * Scheduler table  (code/models.py:85-158, :539-549; integer index math of

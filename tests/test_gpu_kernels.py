@@ -190,9 +190,33 @@ def test_im2col(ops, stride, pad, H, W, C):
     assert torch.equal(col[:, :K], cols.to(BF))
 
 
+@pytest.mark.parametrize("fused", [1, 0])
 @pytest.mark.parametrize("B,HW,C1,C2,G,silu", [(2, 4096, 128, 0, 32, True), (3, 64, 640, 640, 32, True),
-                                               (2, 256, 192, 96, 32, False), (1, 1000, 576, 384, 32, True)])
-def test_groupnorm(ops, B, HW, C1, C2, G, silu):
+                                               (2, 256, 192, 96, 32, False), (1, 1000, 576, 384, 32, True),
+                                               (2, 4096, 192, 0, 32, True), (2, 1024, 576, 384, 32, True),
+                                               (12, 256, 192, 0, 32, True), (1, 7, 64, 0, 32, True)])
+def test_groupnorm(ops, B, HW, C1, C2, G, silu, fused):
+    """fused=1: single-launch thread-block-cluster path (small tensors); fused=0: stats + apply launches."""
+    ops.lib.ae_set_gn_fused(fused)
+    try:
+        _groupnorm_case(ops, B, HW, C1, C2, G, silu)
+    finally:
+        ops.lib.ae_set_gn_fused(1)
+
+
+def test_groupnorm_fused_batch_independent(ops):
+    """A sample's GroupNorm bits do not depend on what else is in the batch (fixed-order cluster reduction)."""
+    x = rnd((4, 1024, 384), 7) * 3 + 0.2
+    gamma, beta = rnd((384,), 3) * 0.1 + 1, rnd((384,), 4) * 0.1
+    o4 = torch.empty(4, 1024, 384, device="cuda", dtype=BF)
+    o1 = torch.empty(1, 1024, 384, device="cuda", dtype=BF)
+    ops.groupnorm(x, None, gamma, beta, 1e-5, 32, True, o4)
+    for b in range(4):
+        ops.groupnorm(x[b:b + 1].contiguous(), None, gamma, beta, 1e-5, 32, True, o1)
+        assert torch.equal(o1[0], o4[b])
+
+
+def _groupnorm_case(ops, B, HW, C1, C2, G, silu):
     x1 = rnd((B, HW, C1), 1) + 0.5
     x2 = rnd((B, HW, C2), 2, 2.0) if C2 else None
     C = C1 + C2

@@ -93,3 +93,30 @@ def test_unet_audioldm_s_5s():
     out4 = eng.forward(x4, torch.cat([t, t.flip(0)]).cuda(), class_labels=torch.cat([y, y.flip(0)]).cuda())
     assert ((out4[:2] - out).norm() / out.norm()).item() < 1e-2
     assert torch.equal(out4[2:].flip(0), out4[:2])
+
+
+def test_dual_stream_graph_matches_single_sample_forwards():
+    """AEDIT_DUAL_STREAM: a B=2 CUDA graph whose halves run as two forked chains equals two B=1 evaluations bit for
+    bit (each chain IS a B=1 evaluation with its own workspaces), also after several replays."""
+    cfg = C.preset("tiny-audioldm2")
+    w = U.synthetic_weights(cfg, seed=0)
+    eng = _engine(cfg, w)
+    eng.dual_stream = True
+    gen = torch.Generator().manual_seed(5)
+    x = torch.randn(2, 8, 32, 16, generator=gen).cuda()
+    t = torch.tensor([441, 441]).cuda()
+    dims = {s[1]: s[0] for s in cfg.transformer_specs if s is not None}
+    streams = [torch.randn(2, [8, 5][i % 2], dims[i], generator=gen).cuda() for i in range(cfg.n_streams)]
+    masks = [torch.ones(2, [8, 5][i % 2]).cuda() for i in range(cfg.n_streams)]
+    text = eng.prepare_text(streams, masks)
+    slot = torch.tensor([0, 1], dtype=torch.int32).cuda()
+    g = eng.graphed(2, 32, 16, text, slot, None)
+    assert g.dual
+    ref = torch.cat([eng.forward(x[i:i + 1], t[i:i + 1], text=text, slot_map=slot[i:i + 1]) for i in range(2)])
+    for _ in range(3):
+        out = g(x, t)
+        torch.cuda.synchronize()
+        assert torch.equal(out, ref)
+    x2 = x * 0.5 + 0.1
+    ref2 = torch.cat([eng.forward(x2[i:i + 1], t[i:i + 1], text=text, slot_map=slot[i:i + 1]) for i in range(2)])
+    assert torch.equal(g(x2, t), ref2)

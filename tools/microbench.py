@@ -67,12 +67,18 @@ ln_o2 = torch.empty(8192, 192, device=dev, dtype=BF)
 g192, b192 = torch.ones(192, device=dev), torch.zeros(192, device=dev)
 bench("layernorm rows=8192 C=192", lambda: ops.layernorm(ln_x2, g192, b192, ln_o2))
 
-for (B, HW, C) in [(2, 64, 960), (2, 4096, 192), (16, 4096, 192), (16, 64, 960), (2, 256, 1536)]:
+for (B, HW, C) in [(2, 64, 960), (2, 4096, 192), (1, 4096, 192), (2, 4096, 384), (2, 1024, 576), (2, 1024, 960),
+                   (2, 256, 1536), (16, 4096, 192), (16, 64, 960)]:
     gx = torch.randn(B, HW, C, device=dev)
     gg, gb = torch.ones(C, device=dev), torch.zeros(C, device=dev)
     go = torch.empty(B, HW, C, device=dev, dtype=BF)
-    bench(f"groupnorm B={B} HW={HW} C={C} (2 launches)", lambda: ops.groupnorm(gx, None, gg, gb, 1e-5, 32, True, go),
-          launches_per_call=2)
+    for fused in (0, 1):
+        if fused and B > 8:
+            continue
+        ops.lib.ae_set_gn_fused(fused)
+        bench(f"groupnorm B={B} HW={HW} C={C} " + ("(fused cluster launch)" if fused else "(stats + apply launches)"),
+              lambda: ops.groupnorm(gx, None, gg, gb, 1e-5, 32, True, go), launches_per_call=1 if fused else 2)
+    ops.lib.ae_set_gn_fused(1)
 
 for bn in (32, 64, 128):
     fn, fl = gemm_case(128, 960, 960, bn, csplit=1)
