@@ -155,7 +155,13 @@ def inversion_forward_process(model: PipelineWrapper,
                               duration: Optional[float] = None,
                               first_order: bool = False,
                               forward_batch: Optional[int] = None,
-                              noise: Optional[torch.Tensor] = None) -> Tuple:
+                              noise: Optional[torch.Tensor] = None,
+                              group=None) -> Tuple:
+    """Extensions over the reference signature (all default to the reference behaviour): `forward_batch` timesteps
+    per U-Net launch, explicit `noise`, and `group` — a torch.distributed process group over which the
+    timestep chunks of ONE clip are sharded: chunk k runs on group rank k % world, `xts` is
+    broadcast from rank 0 once, and `zs` / `xts` are merged by one sum-all-reduce each at the end (every row is owned
+    by exactly one rank, the others contribute zeros, so the merge is exact and every rank returns the full tensors)."""
     if len(prompts) > 1 and extract_h_space:
         raise NotImplementedError("How do you split cfg_scales for hspace? TODO")
     if extract_h_space or extract_skipconns:
@@ -180,6 +186,15 @@ def inversion_forward_process(model: PipelineWrapper,
 
     tb = forward_batch if forward_batch is not None else DEFAULT_FORWARD_BATCH
     tb = max(1, min(int(tb), N))
+    g_rank, g_ws = (0, 1)
+    if group is not None:
+        from .. import parallel as _par
+        g_rank, g_ws = _par.world(group)
+        if g_ws > 1:
+            if tb == 1:
+                raise ValueError("timestep sharding needs forward_batch > 1 (the step-sequential mode chains x_t)")
+            _par.broadcast_(xts, 0, group)            # one noise draw for all ranks
+    owned: List[int] = []
     n_el = x0[0].numel()
     xt_src = xts.clone() if tb > 1 else xts      # batched: every U-Net input is the directly sampled x_t (F8)
     ts_cpu = sched.timesteps_cpu
@@ -187,8 +202,12 @@ def inversion_forward_process(model: PipelineWrapper,
     it = range(0, N, tb)
     if prog_bar:
         it = tqdm(it)
-    for pos0 in it:
+    for chunk_no, pos0 in enumerate(it):
         count = min(tb, N - pos0)
+        if g_ws > 1:
+            if chunk_no % g_ws != g_rank:
+                continue
+            owned.extend(range(N - pos0 - count, N - pos0))
         # loop position pos <-> idx = N - pos - 1 (inversion_utils.py:75); U-Net input xts[idx+1] = xts[N - pos]
         src_rows = torch.arange(N - pos0, N - pos0 - count, -1, device=model.device)
         xt_b = xt_src.index_select(0, src_rows)                                    # [count, C, H, W]
@@ -206,6 +225,9 @@ def inversion_forward_process(model: PipelineWrapper,
         eta = float(etas[N - pos0 - 1])
         model.k_cfg_inv_step(pos0, count, eta, eps, eps[count:] if P > 0 else None, P, cfg_map, xt_src, xts, zs,
                              numerical_fix)
+    if g_ws > 1:
+        _par.merge_owned_rows_(zs, owned, group)
+        _par.merge_owned_rows_(xts[:N], owned, group)
     xt = xts[1][None] if N >= 1 else x0                 # the reference returns the last loop's xt = xts[1]
     zs[0] = torch.zeros_like(zs[0])                     # inversion_utils.py:133
     return xt, zs, xts, extra_info

@@ -12,10 +12,29 @@ import torch
 import torch.distributed as dist
 
 
-def world() -> tuple:
+def world(group=None) -> tuple:
     if dist.is_available() and dist.is_initialized():
-        return dist.get_rank(), dist.get_world_size()
+        return dist.get_rank(group), dist.get_world_size(group)
     return 0, 1
+
+
+def broadcast_(t: torch.Tensor, src: int = 0, group=None) -> torch.Tensor:
+    """In-place broadcast from group rank `src` (no-op without a process group)."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.broadcast(t, src=dist.get_global_rank(group, src) if group is not None else src, group=group)
+    return t
+
+
+def allreduce_rows(local: Optional[torch.Tensor], rows: Sequence[int], like: torch.Tensor, group=None) -> torch.Tensor:
+    """Assemble a `[n_rows, ...]` tensor whose rows were computed on different ranks: every rank scatters its rows
+    (`local[k]` -> row `rows[k]`) into a zero buffer shaped like `like`, then one SUM all-reduce.  Adding zeros is
+    exact, so every rank ends with bit-identical rows (the pc_drift iterate reduction named by BASELINE config 4)."""
+    buf = torch.zeros_like(like)
+    if rows:
+        buf[list(rows)] = local.to(buf.dtype)
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
+    return buf
 
 
 def shard_indices(n_items: int, rank: int, world_size: int) -> List[int]:
@@ -55,6 +74,18 @@ def edit_clips(edit_fn: Callable[[torch.Tensor], torch.Tensor], clips: Sequence[
         for k, i in enumerate(shard_indices(len(clips), r, ws)):
             out[i] = bufs[r][k]
     return out
+
+
+def merge_owned_rows_(t: torch.Tensor, owned: Sequence[int], group=None) -> torch.Tensor:
+    """In place: rows of `t` (dim 0) not in `owned` are zeroed, then one SUM all-reduce — afterwards every rank holds
+    every row from its owner, bit-exactly (x + 0 + ... + 0).  Rows must be owned by exactly one rank."""
+    keep = torch.zeros(t.shape[0], dtype=torch.bool, device=t.device)
+    if len(owned):
+        keep[torch.as_tensor(list(owned), device=t.device)] = True
+    t[~keep] = 0
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return t
 
 
 def max_over_ranks(value: float, device=None) -> float:

@@ -6,6 +6,12 @@ sort-before-permute behaviour, SURVEY.md Appendix D — reproduced, not repaired
 Device work: U-Net evaluations through the wrapper (UNetEngine), the CFG combine + DDIM step in one kernel
 (ae_ddim_step via DDIMScheduler.step); the small dense linear algebra of the iteration (norms, QR of [D, n_ev],
 sort) stays in torch (cuSOLVER) — it is O(D*n_ev^2) per iteration against two U-Net evaluations.
+
+Multi-GPU (BASELINE config 4): `get_eigenvectors(..., group=<process group>)` shards the n_ev
+directions of the power iteration across the ranks — each rank runs the U-Net only on its own rows — and
+sum-all-reduces the zero-padded `[n_ev, D]` posterior-mean iterate once per iteration (NCCL over NVLink on the GPU box);
+normalisation, QR and sorting are then done redundantly on every rank, so every rank returns the same tensors as a
+single-process run.  This is the only data-path collective of the repo.
 """
 from __future__ import annotations
 
@@ -71,9 +77,14 @@ def forward_directional(ldm_stable, xt: torch.Tensor, timestep: torch.Tensor, la
 def get_eigenvectors(ldm_stable, xt: torch.Tensor, text_emb: PromptEmbeddings, uncond_emb: PromptEmbeddings,
                      latents: torch.Tensor, mask: torch.Tensor, t: torch.Tensor, x0_pred: torch.Tensor,
                      pc_mode: PCStreamChoice = PCStreamChoice.BOTH, const: float = 1e-3, cfg_tar: float = 3,
-                     iters: int = 50, double_precision: bool = False, eta: float = 1, n_ev: int = 1
+                     iters: int = 50, double_precision: bool = False, eta: float = 1, n_ev: int = 1, group=None
                      ) -> Tuple[torch.Tensor, torch.Tensor, List[torch.Tensor], List[torch.Tensor],
                                 Dict[int, torch.Tensor], Dict[int, torch.Tensor]]:
+    """`group` (extension, default None = the reference's single-process behaviour): a torch.distributed process
+    group over which the n_ev directions are sharded (see module docstring)."""
+    from . import parallel as _par
+    rank, ws = _par.world(group) if group is not None else (0, 1)
+    rows = _par.shard_indices(n_ev, rank, ws) if ws > 1 else None
     if n_ev > 1:
         x0_pred = expand_for_evs(x0_pred, n_ev)
         xt = expand_for_evs(xt, n_ev)
@@ -86,14 +97,26 @@ def get_eigenvectors(ldm_stable, xt: torch.Tensor, text_emb: PromptEmbeddings, u
             boolean_prompt_mask=expand_for_evs(text_emb.boolean_prompt_mask, n_ev),
             embedding_class_lables=expand_for_evs(text_emb.embedding_class_lables, n_ev))
     eigvecs = torch.randn_like(xt) * mask * const
+    if rows is not None:
+        _par.broadcast_(eigvecs, 0, group)      # one random start for all ranks
     prev_ev = eigvecs.detach().clone()
     in_corr, in_norm = [], []
     interm_eigvecs, interm_eigvals = {}, {}
     with torch.no_grad():
         for i in range(iters):
-            _, unmaksed_out = forward_directional(ldm_stable, xt, t, latents, uncond_emb, text_emb, cfg_tar, eta=eta,
-                                                  eigvecs=eigvecs, amount=1, double_precision=double_precision,
-                                                  mode=pc_mode)
+            if rows is None:
+                _, unmaksed_out = forward_directional(ldm_stable, xt, t, latents, uncond_emb, text_emb, cfg_tar,
+                                                      eta=eta, eigvecs=eigvecs, amount=1,
+                                                      double_precision=double_precision, mode=pc_mode)
+            else:
+                local = None
+                if rows:
+                    pick = (lambda v: v if v is None or len(v) != n_ev else v[rows])
+                    _, local = forward_directional(
+                        ldm_stable, xt[rows], t, pick(latents), PromptEmbeddings(*[pick(v) for v in uncond_emb]),
+                        PromptEmbeddings(*[pick(v) for v in text_emb]), cfg_tar, eta=eta, eigvecs=eigvecs[rows],
+                        amount=1, double_precision=double_precision, mode=pc_mode)
+                unmaksed_out = _par.allreduce_rows(local, rows, xt, group)
             out = unmaksed_out * mask
             Ab = out - x0_pred
             if n_ev > 1:

