@@ -57,6 +57,7 @@ struct GemmDev {
   long long ld_out_bf16;
   long long stride_out, stride_res;
   int w_dynamic;  // 1: the W operand is produced by a preceding kernel (never prefetch it ahead of the dependency)
+  int fast_epi;  // 1: operands / outputs are 16-byte tileable -> coalesced staged epilogue (epilogue_strip)
   int act;  // 0 none, 1 SiLU, 2 GEGLU (output width N/2: out[16q+i] = acc[32q+i] * gelu(acc[32q+16+i]))
   float alpha;
 };
@@ -165,6 +166,123 @@ __device__ __forceinline__ void epilogue_chunk(const GemmDev& p, float (&acc)[32
 #pragma unroll
       for (int j = 0; j < 32; ++j)
         if (j < ovalid) ob[obase + j] = __float2bfloat16_rn(acc[j]);
+    }
+  }
+}
+
+// ---- coalesced epilogue of one warp's 32-row strip of the output tile -------------------------------------------
+// tcgen05.ld hands every thread one accumulator ROW (TMEM lane); writing that row straight to global memory makes
+// each warp instruction touch 32 different rows, 16 bytes each (the pre-r9 epilogue: 2.1 TB/s on the residual
+// linears, one exposed L2 round trip per 32-column chunk).  Here the strip is transposed through shared memory (the
+// TMA ring is idle once the accumulator is complete; row pitch BN+4 floats keeps both the row-owner float4 writes and
+// the row-contiguous float4 reads conflict-free), and every global access — residual read, time-embedding row bias,
+// fp32 / bf16 stores — is a row-contiguous 16 bytes per lane (BN/4 lanes per row, 128/BN rows per instruction).
+// The residual (and bias) loads of the first PF iterations are issued BEFORE the accumulator barrier is waited on, so
+// their latency overlaps the main loop; ALL = the whole strip (small latency-bound grids, one CTA per SM), otherwise
+// batches of PF iterations are double-buffered.
+template <int BN, bool ALL>
+__device__ __forceinline__ void epilogue_strip(const GemmDev& p, float* strip, uint32_t tmem_strip, uint64_t* tmem_full_bar,
+                                               long long m_base, int n0, int zo, int lane) {
+  constexpr int PITCH = BN + 4;
+  constexpr int LPR = BN / 4;      // lanes per output row
+  constexpr int RPI = 32 / LPR;    // rows per iteration
+  constexpr int NIT = 32 / RPI;    // iterations per strip
+  constexpr int PF = ALL ? NIT : (BN == 128 ? 8 : 4);
+  constexpr int NB = NIT / PF;
+  const int sub = lane / LPR, c4 = lane % LPR;
+  const bool geglu = p.act == 2;
+  // column(s) owned by this lane: plain -> 4 consecutive columns; GEGLU -> 2 value + 2 gate columns of a 32-block
+  const int oc = c4 * 2, q = oc >> 4, off = oc & 15;
+  const int ncol = geglu ? (32 * q + off) : c4 * 4;       // tile-local column of the first (value) element
+  const int n = n0 + ncol;
+  const bool col_ok = geglu ? (n0 + 32 * q + 16 + off + 1 < p.N) : (n + 3 < p.N);
+  float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);            // plain: bias[n..n+3]; GEGLU: value bias x,y  gate bias z,w
+  if (p.bias && col_ok) {
+    if (geglu) {
+      const float2 bv = *reinterpret_cast<const float2*>(p.bias + n);
+      const float2 bg = *reinterpret_cast<const float2*>(p.bias + n + 16);
+      b4 = make_float4(bv.x, bv.y, bg.x, bg.y);
+    } else {
+      b4 = *reinterpret_cast<const float4*>(p.bias + n);
+    }
+  }
+  // time-embedding row bias: one value per (row group, column); constant over the strip unless a group ends inside
+  const bool rb_const = p.rowbias && (m_base / p.rows_per_group) == ((m_base + 31) / p.rows_per_group);
+  float4 rb4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (rb_const && col_ok && m_base < p.M)
+    rb4 = *reinterpret_cast<const float4*>(p.rowbias + (m_base / p.rows_per_group) * p.ld_rowbias + n);
+  const float* res_base = p.residual ? p.residual + (long long)zo * p.stride_res + n : nullptr;
+  float4 res[2][PF];
+  auto load_res = [&](int b, float4 (&dst)[PF]) {
+#pragma unroll
+    for (int i = 0; i < PF; ++i) {
+      const long long m = m_base + (long long)(b * PF + i) * RPI + sub;
+      dst[i] = (res_base && col_ok && m < p.M) ? *reinterpret_cast<const float4*>(res_base + m * p.ld_res)
+                                                : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  };
+  load_res(0, res[0]);
+
+  ptx::mbar_wait(tmem_full_bar, 0);
+  ptx::tcgen05_fence_after();
+#pragma unroll 1
+  for (int c = 0; c < BN / 32; ++c) {
+    uint32_t v[32];
+    ptx::tmem_ld_32x32b_x32(tmem_strip + c * 32, v);
+    ptx::tmem_ld_wait();
+    float4* dst = reinterpret_cast<float4*>(strip + lane * PITCH + c * 32);
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      dst[j] = make_float4(__uint_as_float(v[4 * j]) * p.alpha, __uint_as_float(v[4 * j + 1]) * p.alpha,
+                           __uint_as_float(v[4 * j + 2]) * p.alpha, __uint_as_float(v[4 * j + 3]) * p.alpha);
+  }
+  __syncwarp();
+#pragma unroll
+  for (int b = 0; b < NB; ++b) {
+    if (b + 1 < NB) load_res(b + 1, res[(b + 1) & 1]);
+#pragma unroll
+    for (int i = 0; i < PF; ++i) {
+      const int rl = (b * PF + i) * RPI + sub;
+      const long long m = m_base + rl;
+      if (!col_ok || m >= p.M) continue;
+      const float* srow = strip + rl * PITCH;
+      if (geglu) {
+        const float2 va = *reinterpret_cast<const float2*>(srow + ncol);
+        const float2 ga = *reinterpret_cast<const float2*>(srow + ncol + 16);
+        const float o0 = (va.x + b4.x) * gelu_erf_f(ga.x + b4.z);
+        const float o1 = (va.y + b4.y) * gelu_erf_f(ga.y + b4.w);
+        const long long ocol = (n0 >> 1) + oc;
+        if (p.out_f32)
+          *reinterpret_cast<float2*>(p.out_f32 + (long long)zo * p.stride_out + m * p.ld_out_f32 + ocol) = make_float2(o0, o1);
+        if (p.out_bf16) {
+          __nv_bfloat162 h = __floats2bfloat162_rn(o0, o1);
+          *reinterpret_cast<__nv_bfloat162*>(p.out_bf16 + (long long)zo * p.stride_out + m * p.ld_out_bf16 + ocol) = h;
+        }
+        continue;
+      }
+      float4 a = *reinterpret_cast<const float4*>(srow + ncol);
+      a.x += b4.x; a.y += b4.y; a.z += b4.z; a.w += b4.w;
+      if (p.rowbias) {
+        float4 t = rb4;
+        if (!rb_const) t = *reinterpret_cast<const float4*>(p.rowbias + (m / p.rows_per_group) * p.ld_rowbias + n);
+        a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w;
+      }
+      {
+        const float4 t = res[b & 1][i];
+        a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w;
+      }
+      if (p.act == 1) {
+        a.x = silu_f(a.x); a.y = silu_f(a.y); a.z = silu_f(a.z); a.w = silu_f(a.w);
+      }
+      if (p.out_f32) *reinterpret_cast<float4*>(p.out_f32 + (long long)zo * p.stride_out + m * p.ld_out_f32 + n) = a;
+      if (p.out_bf16) {
+        __nv_bfloat162 h0 = __floats2bfloat162_rn(a.x, a.y);
+        __nv_bfloat162 h1 = __floats2bfloat162_rn(a.z, a.w);
+        uint2 pk;
+        pk.x = *reinterpret_cast<uint32_t*>(&h0);
+        pk.y = *reinterpret_cast<uint32_t*>(&h1);
+        *reinterpret_cast<uint2*>(p.out_bf16 + (long long)zo * p.stride_out + m * p.ld_out_bf16 + n) = pk;
+      }
     }
   }
 }
@@ -294,6 +412,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int row = quad * 32 + lane;
     const long long m = (long long)m0 + row;
     pdl_wait();
+    if (p.fast_epi) {
+      float* strip = reinterpret_cast<float*>(smem) + (size_t)quad * 32 * (BN + 4);
+      epilogue_strip<BN, (STAGES > 3)>(p, strip, tmem_base + (static_cast<uint32_t>(quad * 32) << 16), tmem_full_bar,
+                                       (long long)m0 + quad * 32, n0, zo, lane);
+      ptx::tcgen05_fence_before();
+    } else {
     const bool row_ok = m < p.M;
     if (p.residual && row_ok && p.csplit <= 1) {
       // pull this row's residual segment towards L2 while the main loop runs (BN*4 bytes = up to 4 lines)
@@ -325,6 +449,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
     }
     ptx::tcgen05_fence_before();
+    }
   }
   if (p.csplit > 1) {
     // ---- distributed-shared-memory reduction: CTA `z` of the cluster finalises rows [z*R, (z+1)*R), R = 128/csplit,
@@ -565,6 +690,8 @@ using namespace aedit;
 extern "C" void ae_set_pdl(int mode) { g_use_pdl = (mode == 1 || mode == 2) ? mode : 0; }
 
 static int g_splitk_ctas = 148;
+static int g_fast_epi = 1;
+extern "C" void ae_set_fast_epilogue(int on) { g_fast_epi = on ? 1 : 0; }
 extern "C" void ae_set_splitk_ctas(int ctas) { g_splitk_ctas = ctas < 1 ? 148 : ctas; }
 
 extern "C" int ae_gemm_conv_supported(int B, int H, int W, int C) {
@@ -603,6 +730,7 @@ extern "C" int ae_gemm(const ae_gemm_args* a, ae_stream stream) {
   p.pad_h = p.pad_w = 0;
   p.split = 0;
   p.csplit = 0;
+  p.fast_epi = 0;
 
   CUtensorMap tmA, tmB;
   int rc;
@@ -712,6 +840,20 @@ extern "C" int ae_gemm(const ae_gemm_args* a, ae_stream stream) {
     q.stride_out = (long long)a->M * a->N;
     q.act = 0;
     q.alpha = 1.0f;
+  }
+  {
+    // coalesced staged epilogue: every pointer / pitch the strip touches must be 16-byte tileable (8 for bf16 rows,
+    // half of that for the GEGLU output whose lanes own 2 columns)
+    auto al = [](const void* ptr, uintptr_t b) { return (reinterpret_cast<uintptr_t>(ptr) & (b - 1)) == 0; };
+    const bool g = q.act == 2;
+    bool ok = CS == 1 && g_fast_epi && (g ? (a->N % 32 == 0 && !q.residual && !q.rowbias) : (a->N % 4 == 0));
+    ok = ok && (!q.bias || al(q.bias, 16));
+    ok = ok && (!q.rowbias || (al(q.rowbias, 16) && q.ld_rowbias % 4 == 0));
+    ok = ok && (!q.residual || (al(q.residual, 16) && q.ld_res % 4 == 0 && q.stride_res % 4 == 0));
+    ok = ok && (!q.out_f32 || (al(q.out_f32, g ? 8 : 16) && q.ld_out_f32 % (g ? 2 : 4) == 0));
+    ok = ok && (!q.out_bf16 || (al(q.out_bf16, g ? 4 : 8) && q.ld_out_bf16 % (g ? 2 : 4) == 0));
+    ok = ok && q.stride_out % 4 == 0;
+    q.fast_epi = ok ? 1 : 0;
   }
   const long long ctas = tiles * gz;
   const bool deep = a->force_stages ? (a->force_stages > 3) : (ctas <= 160 || CS > 1);

@@ -499,7 +499,7 @@ cudaError_t launch_ln(const float* x, long long rows, int C, float eps, const fl
 
 using namespace aedit;
 
-static int g_gn_fused = 1;
+static int g_gn_fused = 0;  // measured slower than stats + apply on B200 (profiles/r01_microbench_v9.log): opt-in
 extern "C" void ae_set_gn_fused(int on) { g_gn_fused = on ? 1 : 0; }
 
 extern "C" int64_t ae_groupnorm_workspace_bytes(int B, int groups) {

@@ -49,6 +49,34 @@ def test_gemm_plain(ops, M, N, K, bn):
     assert relerr(o32, F.silu(A.float() @ W.float().t())) < 2e-5
 
 
+@pytest.mark.parametrize("M,N,K,bn,rpg", [(128, 128, 64, 0, 16), (256, 256, 512, 128, 64), (300, 200, 200, 64, 16),
+                                          (64, 40, 72, 32, 8), (4096, 128, 1152, 0, 4096), (2048, 384, 384, 0, 1024),
+                                          (512, 576, 576, 0, 256), (130, 960, 960, 0, 64), (1000, 192, 192, 0, 100)])
+@pytest.mark.parametrize("stages", [3, 6])
+def test_gemm_epilogue_paths_bitexact(ops, M, N, K, bn, rpg, stages):
+    """The coalesced shared-memory-staged epilogue (default) and the row-per-thread epilogue apply the same terms in
+    the same order: identical bits, for both pipeline depths (the deep variant preloads the whole residual strip)."""
+    A = rnd((M, K), 1, dtype=BF)
+    W = rnd((N, K), 2, 1 / math.sqrt(K), dtype=BF)
+    bias, res = rnd((N,), 3), rnd((M, N), 4)
+    rowbias = rnd(((M + rpg - 1) // rpg, N), 5)
+    outs = []
+    for fast in (1, 0):
+        ops.lib.ae_set_fast_epilogue(fast)
+        try:
+            o32 = torch.zeros(M, N, device="cuda")
+            o16 = torch.zeros(M, N, device="cuda", dtype=BF)
+            ops.gemm(A, W, out_f32=o32, out_bf16=o16, bias=bias, rowbias=rowbias, rows_per_group=rpg, residual=res,
+                     act=1, alpha=0.7, force_bn=bn, force_split=1, force_stages=stages)
+            outs.append((o32, o16))
+        finally:
+            ops.lib.ae_set_fast_epilogue(1)
+    ref = F.silu(0.7 * (A.float() @ W.float().t()) + bias + res + rowbias.repeat_interleave(rpg, 0)[:M])
+    assert relerr(outs[0][0], ref) < 2e-5
+    assert torch.equal(outs[0][0], outs[1][0])
+    assert torch.equal(outs[0][1], outs[1][1])
+
+
 @pytest.mark.parametrize("M,N,K,S", [(128, 960, 8640, 0), (128, 960, 8640, 9), (256, 576, 5184, 4), (100, 200, 1000, 3),
                                      (128, 7680, 960, 0)])
 def test_gemm_splitk(ops, M, N, K, S):
@@ -141,6 +169,14 @@ def test_gemm_geglu_epilogue(ops, M, C):
     h = x.float() @ Wf.float().t() + bf
     a, g = h.chunk(2, -1)
     assert relerr(out, a * F.gelu(g)) < 4e-3
+    # row-per-thread epilogue: same bits
+    out2 = torch.empty_like(out)
+    ops.lib.ae_set_fast_epilogue(0)
+    try:
+        ops.gemm(x, Wf[perm].contiguous(), out_bf16=out2, bias=bf[perm].contiguous(), act=2)
+    finally:
+        ops.lib.ae_set_fast_epilogue(1)
+    assert torch.equal(out, out2)
 
 
 def test_gemm_batched(ops):
