@@ -57,6 +57,7 @@ struct GemmDev {
   long long ld_out_bf16;
   long long stride_out, stride_res;
   int w_dynamic;  // 1: the W operand is produced by a preceding kernel (never prefetch it ahead of the dependency)
+  int m_in_x;    // 1: M tiles on blockIdx.x (only when there are more than 65535 of them), else N tiles (default)
   int fast_epi;  // 1: operands / outputs are 16-byte tileable -> coalesced staged epilogue (epilogue_strip)
   int act;  // 0 none, 1 SiLU, 2 GEGLU (output width N/2: out[16q+i] = acc[32q+i] * gelu(acc[32q+16+i]))
   float alpha;
@@ -177,17 +178,18 @@ __device__ __forceinline__ void epilogue_chunk(const GemmDev& p, float (&acc)[32
 // TMA ring is idle once the accumulator is complete; row pitch BN+4 floats keeps both the row-owner float4 writes and
 // the row-contiguous float4 reads conflict-free), and every global access — residual read, time-embedding row bias,
 // fp32 / bf16 stores — is a row-contiguous 16 bytes per lane (BN/4 lanes per row, 128/BN rows per instruction).
-// The residual (and bias) loads of the first PF iterations are issued BEFORE the accumulator barrier is waited on, so
-// their latency overlaps the main loop; ALL = the whole strip (small latency-bound grids, one CTA per SM), otherwise
-// batches of PF iterations are double-buffered.
-template <int BN, bool ALL>
+// The bias / row-bias loads, an L2 prefetch of the strip's residual and the residual loads of the first PF iterations
+// are issued BEFORE the accumulator barrier is waited on, so their latency overlaps the main loop; later batches are
+// loaded one batch ahead.  The iteration loops are deliberately NOT fully unrolled: the epilogue runs once per CTA, so
+// its instructions are fetched cold — a 32x unrolled body (v10a) cost +10 us per launch in instruction-cache misses.
+template <int BN>
 __device__ __forceinline__ void epilogue_strip(const GemmDev& p, float* strip, uint32_t tmem_strip, uint64_t* tmem_full_bar,
                                                long long m_base, int n0, int zo, int lane) {
   constexpr int PITCH = BN + 4;
   constexpr int LPR = BN / 4;      // lanes per output row
   constexpr int RPI = 32 / LPR;    // rows per iteration
   constexpr int NIT = 32 / RPI;    // iterations per strip
-  constexpr int PF = ALL ? NIT : (BN == 128 ? 8 : 4);
+  constexpr int PF = BN == 128 ? 8 : 4;   // iterations per residual batch (one batch of loads in flight)
   constexpr int NB = NIT / PF;
   const int sub = lane / LPR, c4 = lane % LPR;
   const bool geglu = p.act == 2;
@@ -212,16 +214,19 @@ __device__ __forceinline__ void epilogue_strip(const GemmDev& p, float* strip, u
   if (rb_const && col_ok && m_base < p.M)
     rb4 = *reinterpret_cast<const float4*>(p.rowbias + (m_base / p.rows_per_group) * p.ld_rowbias + n);
   const float* res_base = p.residual ? p.residual + (long long)zo * p.stride_res + n : nullptr;
-  float4 res[2][PF];
-  auto load_res = [&](int b, float4 (&dst)[PF]) {
+  if (res_base && m_base + lane < p.M) {
+    // pull the whole strip of the residual towards L2 (row `lane`, BN*4 bytes) while the main loop runs ...
+    const char* rp = reinterpret_cast<const char*>(p.residual + (long long)zo * p.stride_res + (m_base + lane) * p.ld_res + n0);
 #pragma unroll
-    for (int i = 0; i < PF; ++i) {
-      const long long m = m_base + (long long)(b * PF + i) * RPI + sub;
-      dst[i] = (res_base && col_ok && m < p.M) ? *reinterpret_cast<const float4*>(res_base + m * p.ld_res)
-                                                : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-  };
-  load_res(0, res[0]);
+    for (int l = 0; l < BN * 4 / 128; ++l) asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + l * 128));
+  }
+  float4 cur[PF];   // ... and the first batch into registers
+#pragma unroll
+  for (int i = 0; i < PF; ++i) {
+    const long long m = m_base + (long long)i * RPI + sub;
+    cur[i] = (res_base && col_ok && m < p.M) ? *reinterpret_cast<const float4*>(res_base + m * p.ld_res)
+                                             : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
 
   ptx::mbar_wait(tmem_full_bar, 0);
   ptx::tcgen05_fence_after();
@@ -237,51 +242,68 @@ __device__ __forceinline__ void epilogue_strip(const GemmDev& p, float* strip, u
                            __uint_as_float(v[4 * j + 2]) * p.alpha, __uint_as_float(v[4 * j + 3]) * p.alpha);
   }
   __syncwarp();
-#pragma unroll
+  if (!col_ok) return;
+  if (geglu) {
+    const long long ocol = (n0 >> 1) + oc;
+#pragma unroll 1
+    for (int it = 0; it < NIT; ++it) {
+      const int rl = it * RPI + sub;
+      const long long m = m_base + rl;
+      if (m >= p.M) break;
+      const float* srow = strip + rl * PITCH;
+      const float2 va = *reinterpret_cast<const float2*>(srow + ncol);
+      const float2 ga = *reinterpret_cast<const float2*>(srow + ncol + 16);
+      const float o0 = (va.x + b4.x) * gelu_erf_f(ga.x + b4.z);
+      const float o1 = (va.y + b4.y) * gelu_erf_f(ga.y + b4.w);
+      if (p.out_f32)
+        *reinterpret_cast<float2*>(p.out_f32 + (long long)zo * p.stride_out + m * p.ld_out_f32 + ocol) = make_float2(o0, o1);
+      if (p.out_bf16) {
+        __nv_bfloat162 h = __floats2bfloat162_rn(o0, o1);
+        *reinterpret_cast<__nv_bfloat162*>(p.out_bf16 + (long long)zo * p.stride_out + m * p.ld_out_bf16 + ocol) = h;
+      }
+    }
+    return;
+  }
+  float* of = p.out_f32 ? p.out_f32 + (long long)zo * p.stride_out + n : nullptr;
+  __nv_bfloat16* ob = p.out_bf16 ? p.out_bf16 + (long long)zo * p.stride_out + n : nullptr;
+#pragma unroll 1
   for (int b = 0; b < NB; ++b) {
-    if (b + 1 < NB) load_res(b + 1, res[(b + 1) & 1]);
+    float4 r[PF];
+#pragma unroll
+    for (int i = 0; i < PF; ++i) r[i] = cur[i];
+    if (b + 1 < NB) {
+#pragma unroll
+      for (int i = 0; i < PF; ++i) {
+        const long long m = m_base + (long long)((b + 1) * PF + i) * RPI + sub;
+        cur[i] = (res_base && m < p.M) ? *reinterpret_cast<const float4*>(res_base + m * p.ld_res)
+                                       : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
 #pragma unroll
     for (int i = 0; i < PF; ++i) {
       const int rl = (b * PF + i) * RPI + sub;
       const long long m = m_base + rl;
-      if (!col_ok || m >= p.M) continue;
-      const float* srow = strip + rl * PITCH;
-      if (geglu) {
-        const float2 va = *reinterpret_cast<const float2*>(srow + ncol);
-        const float2 ga = *reinterpret_cast<const float2*>(srow + ncol + 16);
-        const float o0 = (va.x + b4.x) * gelu_erf_f(ga.x + b4.z);
-        const float o1 = (va.y + b4.y) * gelu_erf_f(ga.y + b4.w);
-        const long long ocol = (n0 >> 1) + oc;
-        if (p.out_f32)
-          *reinterpret_cast<float2*>(p.out_f32 + (long long)zo * p.stride_out + m * p.ld_out_f32 + ocol) = make_float2(o0, o1);
-        if (p.out_bf16) {
-          __nv_bfloat162 h = __floats2bfloat162_rn(o0, o1);
-          *reinterpret_cast<__nv_bfloat162*>(p.out_bf16 + (long long)zo * p.stride_out + m * p.ld_out_bf16 + ocol) = h;
+      if (m < p.M) {
+        float4 a = *reinterpret_cast<const float4*>(strip + rl * PITCH + ncol);
+        a.x += b4.x; a.y += b4.y; a.z += b4.z; a.w += b4.w;
+        if (p.rowbias) {
+          float4 t = rb4;
+          if (!rb_const) t = *reinterpret_cast<const float4*>(p.rowbias + (m / p.rows_per_group) * p.ld_rowbias + n);
+          a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w;
         }
-        continue;
-      }
-      float4 a = *reinterpret_cast<const float4*>(srow + ncol);
-      a.x += b4.x; a.y += b4.y; a.z += b4.z; a.w += b4.w;
-      if (p.rowbias) {
-        float4 t = rb4;
-        if (!rb_const) t = *reinterpret_cast<const float4*>(p.rowbias + (m / p.rows_per_group) * p.ld_rowbias + n);
-        a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w;
-      }
-      {
-        const float4 t = res[b & 1][i];
-        a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w;
-      }
-      if (p.act == 1) {
-        a.x = silu_f(a.x); a.y = silu_f(a.y); a.z = silu_f(a.z); a.w = silu_f(a.w);
-      }
-      if (p.out_f32) *reinterpret_cast<float4*>(p.out_f32 + (long long)zo * p.stride_out + m * p.ld_out_f32 + n) = a;
-      if (p.out_bf16) {
-        __nv_bfloat162 h0 = __floats2bfloat162_rn(a.x, a.y);
-        __nv_bfloat162 h1 = __floats2bfloat162_rn(a.z, a.w);
-        uint2 pk;
-        pk.x = *reinterpret_cast<uint32_t*>(&h0);
-        pk.y = *reinterpret_cast<uint32_t*>(&h1);
-        *reinterpret_cast<uint2*>(p.out_bf16 + (long long)zo * p.stride_out + m * p.ld_out_bf16 + n) = pk;
+        a.x += r[i].x; a.y += r[i].y; a.z += r[i].z; a.w += r[i].w;
+        if (p.act == 1) {
+          a.x = silu_f(a.x); a.y = silu_f(a.y); a.z = silu_f(a.z); a.w = silu_f(a.w);
+        }
+        if (of) *reinterpret_cast<float4*>(of + m * p.ld_out_f32) = a;
+        if (ob) {
+          __nv_bfloat162 h0 = __floats2bfloat162_rn(a.x, a.y);
+          __nv_bfloat162 h1 = __floats2bfloat162_rn(a.z, a.w);
+          uint2 pk;
+          pk.x = *reinterpret_cast<uint32_t*>(&h0);
+          pk.y = *reinterpret_cast<uint32_t*>(&h1);
+          *reinterpret_cast<uint2*>(ob + m * p.ld_out_bf16) = pk;
+        }
       }
     }
   }
@@ -310,8 +332,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int tile_m = blockIdx.x;
-  const int tile_n = blockIdx.y;
+  // N tiles vary fastest in launch order: the CTAs that share one 128-row A tile are co-resident and the tile is
+  // fetched from HBM once (W is small and stays in L2 either way).  ncu on the r9 build (M fastest) showed
+  // dram__bytes_read = 2.6x the algorithmic bytes for [102400 x 1536] x [384 x 1536]: A re-read once per N tile.
+  const int tile_m = p.m_in_x ? blockIdx.x : blockIdx.y;
+  const int tile_n = p.m_in_x ? blockIdx.y : blockIdx.x;
   const int z = blockIdx.z;
   const int m0 = tile_m * BM;
   const int n0 = tile_n * BN;
@@ -414,7 +439,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     pdl_wait();
     if (p.fast_epi) {
       float* strip = reinterpret_cast<float*>(smem) + (size_t)quad * 32 * (BN + 4);
-      epilogue_strip<BN, (STAGES > 3)>(p, strip, tmem_base + (static_cast<uint32_t>(quad * 32) << 16), tmem_full_bar,
+      epilogue_strip<BN>(p, strip, tmem_base + (static_cast<uint32_t>(quad * 32) << 16), tmem_full_bar,
                                        (long long)m0 + quad * 32, n0, zo, lane);
       ptx::tcgen05_fence_before();
     } else {
@@ -656,7 +681,8 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmDev& p, int
     if (e != cudaSuccess) return fail(AE_ECUDA, "cudaFuncSetAttribute(smem=%d): %s", L::kTotal, cudaGetErrorString(e));
     attr_set = true;
   }
-  dim3 grid((p.M + BM - 1) / BM, (p.N + BN - 1) / BN, gz);
+  const unsigned tm = (unsigned)((p.M + BM - 1) / BM), tn = (unsigned)((p.N + BN - 1) / BN);
+  dim3 grid = p.m_in_x ? dim3(tm, tn, gz) : dim3(tn, tm, gz);
   cudaError_t e;
   if (p.csplit > 1) {
     // thread-block cluster (1,1,csplit): the K slices of one output tile are co-scheduled and reduce through DSMEM
@@ -731,6 +757,7 @@ extern "C" int ae_gemm(const ae_gemm_args* a, ae_stream stream) {
   p.split = 0;
   p.csplit = 0;
   p.fast_epi = 0;
+  p.m_in_x = (a->M + BM - 1) / BM > 65535 ? 1 : 0;
 
   CUtensorMap tmA, tmB;
   int rc;

@@ -36,7 +36,7 @@ import torch.nn.functional as F
 def timestep_embedding(t: torch.Tensor, dim: int) -> torch.Tensor:
     """util.py:173-197 == diffusers Timesteps(flip_sin_to_cos=True, downscale_freq_shift=0)."""
     half = dim // 2
-    freqs = torch.exp(-math.log(10000.0) * torch.arange(half, dtype=torch.float32) / half)
+    freqs = torch.exp(-math.log(10000.0) * torch.arange(half, dtype=torch.float32, device=t.device) / half)
     args = t[:, None].float() * freqs[None]
     return torch.cat([torch.cos(args), torch.sin(args)], dim=-1)
 

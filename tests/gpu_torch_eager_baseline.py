@@ -43,7 +43,7 @@ def run(spec, mode, n_steps, batched, device="cuda:0"):
         yc = torch.nn.functional.normalize(torch.randn(1, 512, generator=g), dim=-1).to(dev)
     torch.backends.cuda.matmul.allow_tf32 = mode == "tf32"
     torch.backends.cudnn.allow_tf32 = mode == "tf32"
-    ac = torch.autocast(dev.type, dtype=torch.bfloat16, enabled=(mode == "bf16"))
+    ac = torch.autocast(dev.type if dev.type != "meta" else "cpu", dtype=torch.bfloat16, enabled=(mode == "bf16"))
 
     def unet(x, t, st, y):
         tt = torch.full((x.shape[0],), int(t), dtype=torch.int64, device=dev)
