@@ -61,7 +61,7 @@ def test_gemm_epilogue_paths_bitexact(ops, M, N, K, bn, rpg, stages):
     bias, res = rnd((N,), 3), rnd((M, N), 4)
     rowbias = rnd(((M + rpg - 1) // rpg, N), 5)
     outs = []
-    for fast in (1, 0):
+    for fast in (2, 0):
         ops.lib.ae_set_fast_epilogue(fast)
         try:
             o32 = torch.zeros(M, N, device="cuda")
@@ -78,7 +78,8 @@ def test_gemm_epilogue_paths_bitexact(ops, M, N, K, bn, rpg, stages):
 
 
 @pytest.mark.parametrize("M,N,K,S", [(128, 960, 8640, 0), (128, 960, 8640, 9), (256, 576, 5184, 4), (100, 200, 1000, 3),
-                                     (128, 7680, 960, 0)])
+                                     (128, 7680, 960, 0), (512, 576, 2304, 0), (128, 960, 960, 5), (130, 960, 1920, 7),
+                                     (128, 64, 4096, 32)])
 def test_gemm_splitk(ops, M, N, K, S):
     """split-K (fp32 partials + fixed-order reduce kernel) gives the same result as the single-pass kernel up to
     fp32 summation order, with every epilogue term applied exactly once."""
@@ -97,11 +98,14 @@ def test_gemm_splitk(ops, M, N, K, S):
     ops.gemm(A, W, out_f32=o_ns, bias=bias, rowbias=rowbias, rows_per_group=64, residual=res, act=1, alpha=0.5,
              force_split=1)
     assert relerr(o32, o_ns) < 1e-5
-    # determinism: same call, same bits
-    o_b = torch.empty_like(o32)
-    ops.gemm(A, W, out_f32=o_b, bias=bias, rowbias=rowbias, rows_per_group=64, residual=res, act=1, alpha=0.5,
-             force_split=S)
-    assert torch.equal(o32, o_b)
+    # determinism: same call, same bits; and the single-launch variant (counter rendezvous + in-kernel slice reduce,
+    # the default when all K slices are co-resident) gives the same bits as partial pass + reduce kernel
+    for fs in (0, 1, 0):
+        o_b = torch.zeros_like(o32)
+        o_h = torch.zeros_like(o16)
+        ops.gemm(A, W, out_f32=o_b, out_bf16=o_h, bias=bias, rowbias=rowbias, rows_per_group=64, residual=res, act=1,
+                 alpha=0.5, force_split=S, fused_split=fs)
+        assert torch.equal(o32, o_b) and torch.equal(o16, o_h)
 
 
 @pytest.mark.parametrize("M,N,K,CS", [(128, 960, 960, 2), (128, 960, 960, 4), (128, 960, 8640, 8), (512, 576, 576, 2),
@@ -171,7 +175,7 @@ def test_gemm_geglu_epilogue(ops, M, C):
     assert relerr(out, a * F.gelu(g)) < 4e-3
     # row-per-thread epilogue: same bits
     out2 = torch.empty_like(out)
-    ops.lib.ae_set_fast_epilogue(0)
+    ops.lib.ae_set_fast_epilogue(2)
     try:
         ops.gemm(x, Wf[perm].contiguous(), out_bf16=out2, bias=bf[perm].contiguous(), act=2)
     finally:
