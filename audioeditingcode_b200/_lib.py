@@ -27,8 +27,7 @@ class AeGemmArgs(C.Structure):
                 ("out_f32", vp), ("ld_out_f32", i64), ("out_bf16", vp), ("ld_out_bf16", i64), ("act", i32),
                 ("alpha", f32), ("conv", i32), ("B", i32), ("H", i32), ("W_", i32), ("C", i32), ("kh", i32),
                 ("kw", i32), ("dil_h", i32), ("dil_w", i32), ("force_bn", i32), ("splitk_ws", vp), ("splitk_ws_bytes", i64),
-                ("force_split", i32), ("force_csplit", i32), ("w_dynamic", i32), ("force_stages", i32),
-                ("splitk_counters", vp), ("fused_split", i32)]
+                ("force_split", i32), ("force_csplit", i32), ("w_dynamic", i32), ("force_stages", i32)]
 
 
 _SIGS = {
@@ -39,7 +38,6 @@ _SIGS = {
     "ae_set_pdl": (None, [i32]),
     "ae_set_splitk_ctas": (None, [i32]),
     "ae_set_fast_epilogue": (None, [i32]),
-    "ae_set_fused_splitk": (None, [i32]),
     "ae_set_gn_fused": (None, [i32]),
     "ae_sched_create": (i32, [vp, i32, f32, vp, i32, i32, C.POINTER(vp)]),
     "ae_sched_create_from_rows": (i32, [C.POINTER(AeSchedRow), i32, i32, i32, C.POINTER(vp)]),

@@ -57,9 +57,6 @@ struct GemmDev {
   long long ld_out_bf16;
   long long stride_out, stride_res;
   int w_dynamic;  // 1: the W operand is produced by a preceding kernel (never prefetch it ahead of the dependency)
-  int fsplit;    // 1: single-launch split-K (partials to fs_ws, per-tile counter rendezvous, in-kernel slice reduce)
-  float* fs_ws;
-  unsigned int* fs_counters;
   int m_in_x;    // 1: M tiles on blockIdx.x (only when there are more than 65535 of them), else N tiles (default)
   int fast_epi;  // 1: operands / outputs are 16-byte tileable -> coalesced staged epilogue (epilogue_strip)
   int act;  // 0 none, 1 SiLU, 2 GEGLU (output width N/2: out[16q+i] = acc[32q+i] * gelu(acc[32q+16+i]))
@@ -312,72 +309,6 @@ __device__ __forceinline__ void epilogue_strip(const GemmDev& p, float* strip, u
   }
 }
 
-// ---- single-launch split-K: finish rows [r0, r1) of this CTA's output tile from the S published partial tiles.
-// Same arithmetic as splitk_reduce_kernel (sum s = 0..S-1 in order, then alpha, bias, row bias, residual, act).
-template <int BN>
-__device__ __forceinline__ void fsplit_finish_rows(const GemmDev& p, int S, int m0, int n0, int r0, int r1, int tid) {
-  constexpr int Q = BN / 4;
-  const long long MN = (long long)p.M * p.N;
-  const int items = (r1 - r0) * Q;
-  for (int it = tid; it < items; it += 128) {
-    const int rl = r0 + it / Q;
-    const long long m = (long long)m0 + rl;
-    const int n = n0 + (it % Q) * 4;
-    if (m >= p.M || n >= p.N) continue;
-    const float* w = p.fs_ws + m * p.N + n;
-    float4 acc = __ldcg(reinterpret_cast<const float4*>(w));
-    int s = 1;
-    for (; s + 4 <= S; s += 4) {
-      float4 t[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) t[u] = __ldcg(reinterpret_cast<const float4*>(w + (long long)(s + u) * MN));
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        acc.x += t[u].x;
-        acc.y += t[u].y;
-        acc.z += t[u].z;
-        acc.w += t[u].w;
-      }
-    }
-    for (; s < S; ++s) {
-      const float4 t = __ldcg(reinterpret_cast<const float4*>(w + (long long)s * MN));
-      acc.x += t.x;
-      acc.y += t.y;
-      acc.z += t.z;
-      acc.w += t.w;
-    }
-    float v[4] = {acc.x * p.alpha, acc.y * p.alpha, acc.z * p.alpha, acc.w * p.alpha};
-    if (p.bias) {
-#pragma unroll
-      for (int k = 0; k < 4; ++k) v[k] += __ldg(p.bias + n + k);
-    }
-    if (p.rowbias) {
-      const float* rb = p.rowbias + (m / p.rows_per_group) * p.ld_rowbias + n;
-#pragma unroll
-      for (int k = 0; k < 4; ++k) v[k] += __ldg(rb + k);
-    }
-    if (p.residual) {
-      const float* r = p.residual + m * p.ld_res + n;
-#pragma unroll
-      for (int k = 0; k < 4; ++k) v[k] += r[k];
-    }
-    if (p.act == 1) {
-#pragma unroll
-      for (int k = 0; k < 4; ++k) v[k] = silu_f(v[k]);
-    }
-    if (p.out_f32) {
-      float* o = p.out_f32 + m * p.ld_out_f32 + n;
-#pragma unroll
-      for (int k = 0; k < 4; ++k) o[k] = v[k];
-    }
-    if (p.out_bf16) {
-      __nv_bfloat16* o = p.out_bf16 + m * p.ld_out_bf16 + n;
-#pragma unroll
-      for (int k = 0; k < 4; ++k) o[k] = __float2bfloat16_rn(v[k]);
-    }
-  }
-}
-
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.aligned;\n\tbarrier.cluster.wait.aligned;" ::: "memory");
 }
@@ -506,53 +437,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int row = quad * 32 + lane;
     const long long m = (long long)m0 + row;
     pdl_wait();
-    if (p.fsplit) {
-      // ---- single-launch split-K.  (1) raw partial tile -> workspace [z][M][N]
-      const int S = (int)gridDim.z;
-      ptx::mbar_wait(tmem_full_bar, 0);
-      ptx::tcgen05_fence_after();
-      float* wrow = p.fs_ws + ((long long)z * p.M + m) * p.N;
-#pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        uint32_t v[32];
-        ptx::tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + c * 32, v);
-        ptx::tmem_ld_wait();
-        if (m < p.M) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const int n = n0 + c * 32 + 4 * j;
-            if (n < p.N)
-              __stcg(reinterpret_cast<float4*>(wrow + n), make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
-                                                                        __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3])));
-          }
-        }
-      }
-      ptx::tcgen05_fence_before();
-      // (2) rendezvous of the S co-resident CTAs of this tile on its arrival counter (release / acquire at gpu scope)
-      const int etid = (int)threadIdx.x - 64;
-      unsigned int* ctr = p.fs_counters + (tile_m * (int)(p.m_in_x ? gridDim.y : gridDim.x) + tile_n);
-      __threadfence();
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (etid == 0) {
-        atomicAdd(ctr, 1u);
-        unsigned int seen = 0, spins = 0;
-        do {
-          asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(ctr) : "memory");
-          if (seen < (unsigned)S && ++spins > (1u << 26)) __trap();   // a lost peer must fail loudly, not hang
-        } while (seen < (unsigned)S);
-      }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      __threadfence();
-      // (3) this CTA finishes rows [z*R, (z+1)*R) of the tile
-      const int R = (BM + S - 1) / S;
-      fsplit_finish_rows<BN>(p, S, m0, n0, min(BM, z * R), min(BM, (z + 1) * R), etid);
-      // (4) departure; the last CTA re-arms the counter for the next launch
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      if (etid == 0) {
-        const unsigned int old = atomicAdd(ctr, 1u);
-        if (old == 2u * (unsigned)S - 1u) atomicExch(ctr, 0u);
-      }
-    } else if (p.fast_epi) {
+    if (p.fast_epi) {
       float* strip = reinterpret_cast<float*>(smem) + (size_t)quad * 32 * (BN + 4);
       epilogue_strip<BN>(p, strip, tmem_base + (static_cast<uint32_t>(quad * 32) << 16), tmem_full_bar,
                                        (long long)m0 + quad * 32, n0, zo, lane);
@@ -832,8 +717,6 @@ extern "C" void ae_set_pdl(int mode) { g_use_pdl = (mode == 1 || mode == 2) ? mo
 
 static int g_splitk_ctas = 148;
 static int g_fast_epi = 1;
-static int g_fused_split = 1;
-extern "C" void ae_set_fused_splitk(int on) { g_fused_split = on ? 1 : 0; }
 extern "C" void ae_set_fast_epilogue(int mode) { g_fast_epi = (mode == 0 || mode == 2) ? mode : 1; }
 extern "C" void ae_set_splitk_ctas(int ctas) { g_splitk_ctas = ctas < 1 ? 148 : ctas; }
 
@@ -874,9 +757,6 @@ extern "C" int ae_gemm(const ae_gemm_args* a, ae_stream stream) {
   p.split = 0;
   p.csplit = 0;
   p.fast_epi = 0;
-  p.fsplit = 0;
-  p.fs_ws = nullptr;
-  p.fs_counters = nullptr;
   p.m_in_x = (a->M + BM - 1) / BM > 65535 ? 1 : 0;
 
   CUtensorMap tmA, tmB;
@@ -973,27 +853,11 @@ extern "C" int ae_gemm(const ae_gemm_args* a, ae_stream stream) {
     q.kb_per_split = (p.num_kblocks + CS - 1) / CS;
     gz = CS;
   }
-  bool fused = false;
   if (S > 1) {
     q.split = 1;
     q.kb_per_split = (p.num_kblocks + S - 1) / S;
     S = (p.num_kblocks + q.kb_per_split - 1) / q.kb_per_split;  // no empty splits
     gz = S;
-    // single-launch variant: every K slice of every tile must be resident at once (they wait for each other)
-    static int n_sm = 0;
-    if (n_sm == 0) {
-      int dev = 0;
-      cudaGetDevice(&dev);
-      if (cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n_sm <= 0) n_sm = 1;
-    }
-    fused = g_fused_split && a->fused_split != 1 && a->splitk_counters && tiles <= AE_SPLITK_COUNTERS &&
-            tiles * S <= n_sm;
-  }
-  if (fused) {
-    q.fsplit = 1;
-    q.fs_ws = a->splitk_ws;
-    q.fs_counters = a->splitk_counters;
-  } else if (S > 1) {
     q.bias = nullptr;
     q.rowbias = nullptr;
     q.residual = nullptr;
@@ -1036,7 +900,7 @@ extern "C" int ae_gemm(const ae_gemm_args* a, ae_stream stream) {
       rc = deep ? launch<128, 6>(tmA, tmB, q, gz, st) : launch<128, 3>(tmA, tmB, q, gz, st);
       break;
   }
-  if (rc || S == 1 || fused) return rc;
+  if (rc || S == 1) return rc;
   ReduceArgs r;
   r.ws = a->splitk_ws;
   r.S = S;

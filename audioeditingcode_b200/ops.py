@@ -45,8 +45,6 @@ class CudaOps:
         # programmatic dependent launch: GEMM-only mode (weight prefetch ahead of the dependency wait) measured +2-4 %
         # end to end on B200, all-kernel mode measured slower (profiles/r01_bench_v7_*, r01_bench_v8_*)
         self.lib.ae_set_pdl(int(os.environ.get("AEDIT_PDL", "2")))   # 0 off, 1 all kernels, 2 GEMMs only
-        if "AEDIT_FUSED_SPLITK" in os.environ:
-            self.lib.ae_set_fused_splitk(int(os.environ["AEDIT_FUSED_SPLITK"]))
         if "AEDIT_FAST_EPILOGUE" in os.environ:
             self.lib.ae_set_fast_epilogue(int(os.environ["AEDIT_FAST_EPILOGUE"]))
         if "AEDIT_GN_FUSED" in os.environ:
@@ -57,8 +55,7 @@ class CudaOps:
     def _splitk_workspace(self, device):
         ws = self._splitk_ws.get(str(device))
         if ws is None:
-            ws = (torch.empty(self.SPLITK_WS_BYTES // 4, dtype=torch.float32, device=device),
-                  torch.zeros(1024, dtype=torch.int32, device=device))     # partial tiles, per-tile arrival counters
+            ws = torch.empty(self.SPLITK_WS_BYTES // 4, dtype=torch.float32, device=device)
             self._splitk_ws[str(device)] = ws
         return ws
 
@@ -73,7 +70,7 @@ class CudaOps:
     def gemm(self, A, W, *, out_f32=None, out_bf16=None, bias=None, rowbias=None, rows_per_group=1, residual=None,
              act=0, alpha=1.0, conv=None, M=None, K=None, force_bn=0, batch=1, strideA=0, strideW=0, stride_out=0,
              stride_res=0, lda=None, ldw=None, force_split=0, ld_out_f32=None, ld_out_bf16=None, force_stages=0,
-             w_dynamic=False, force_csplit=0, fused_split=0):
+             w_dynamic=False, force_csplit=0):
         """D = alpha*A@W^T (+bias)(+rowbias[row//rows_per_group])(+residual) -> act.  conv=(B,H,W,C,kh,kw,dh,dw)
         turns A (channels-last image) into an implicit-GEMM operand."""
         a = AeGemmArgs()
@@ -118,11 +115,9 @@ class CudaOps:
         a.w_dynamic = 1 if w_dynamic else 0
         a.force_csplit = force_csplit
         if batch == 1 and act != 2:
-            ws, counters = self._splitk_workspace(A.device)
+            ws = self._splitk_workspace(A.device)
             a.splitk_ws = ws.data_ptr()
             a.splitk_ws_bytes = ws.numel() * 4
-            a.splitk_counters = counters.data_ptr()
-            a.fused_split = fused_split
         check(self.lib.ae_gemm(C.byref(a), _stream()), "ae_gemm")
 
     def conv_supported(self, B, H, W, C_) -> bool:

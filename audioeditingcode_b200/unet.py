@@ -55,9 +55,6 @@ class GraphedForward:
         # batch is cut in two halves captured on two forked streams of the same graph, so the two dependency chains
         # interleave on the SMs.  Each chain owns its workspaces (second CudaOps instance).
         self.dual = engine.dual_stream and B % 2 == 0 and B <= engine.dual_stream_max_b
-        if self.dual:
-            # two grids of rendezvousing split-K CTAs could starve each other of SMs: use the two-launch split-K
-            engine.ops.lib.ae_set_fused_splitk(0)
         cur = torch.cuda.current_stream()
         side = torch.cuda.Stream()
         self._side2 = torch.cuda.Stream() if self.dual else None

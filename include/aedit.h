@@ -50,11 +50,6 @@ void ae_set_splitk_ctas(int ctas);
  * 0 = always the row-per-thread epilogue.  All three give identical bits (tests/test_gpu_kernels.py). */
 void ae_set_fast_epilogue(int mode);
 
-/* split-K as one launch (default on, needs ae_gemm_args.splitk_counters) or as partial pass + reduce kernel.
- * The single-launch variant makes the K slices of a tile wait for each other, which is only safe while no other grid
- * that also waits on peers runs CONCURRENTLY on the device (two streams issuing split-K GEMMs at once, MPS sharing):
- * turn it off in such set-ups.  Stream-ordered use, CUDA graphs and programmatic dependent launch are fine. */
-void ae_set_fused_splitk(int on);
 
 /* GroupNorm of small tensors (B <= 8, <= 8 MB per sample) as ONE thread-block-cluster launch instead of a statistics
  * launch + an apply launch.  Default OFF: 16 CTAs reading 200 KB each measured 2-3x slower than the two wide launches. */
@@ -173,15 +168,7 @@ typedef struct {
   int32_t w_dynamic;    /* 1 if W is written by a preceding kernel on the stream (e.g. K or V^T of an unfused attention):
                            disables the early W prefetch that otherwise overlaps the previous kernel's tail */
   int32_t force_stages; /* 0 auto (deep 6-stage ring for grids <= 160 CTAs, else 3 stages x 2-3 CTAs/SM), 3 or 6 */
-  /* single-launch split-K: AE_SPLITK_COUNTERS uint32 arrival counters (one per output tile), ZERO-initialised once by
-   * the caller; the kernel re-arms them.  With it, the K slices of a tile (all co-resident: tiles * splits <= #SMs)
-   * publish their partials to splitk_ws, wait for each other on the tile's counter and each reduce + finish a row
-   * slice of the tile in the fixed order s = 0..S-1 — same bits as the two-launch variant, one launch less.
-   * NULL (or fused_split = 1... see below) = two launches.  fused_split: 0 auto, 1 never. */
-  uint32_t* splitk_counters;
-  int32_t fused_split;
 } ae_gemm_args;
-#define AE_SPLITK_COUNTERS 1024
 int ae_gemm(const ae_gemm_args*, ae_stream stream);
 /* 1 if the implicit-conv fast path supports this geometry (else use ae_im2col + plain GEMM) */
 int ae_gemm_conv_supported(int B, int H, int W, int C);

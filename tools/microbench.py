@@ -36,7 +36,7 @@ def bench(name, fn, R=100, reps=5, flops=0.0, launches_per_call=1):
     return us
 
 
-def gemm_case(M, N, K, bn, conv=None, res=False, split=0, csplit=0, fused=0):
+def gemm_case(M, N, K, bn, conv=None, res=False, split=0, csplit=0):
     if conv is not None:
         B, H, W, C = conv
         A = torch.randn(B, H, W, C, device=dev).to(BF)
@@ -49,7 +49,7 @@ def gemm_case(M, N, K, bn, conv=None, res=False, split=0, csplit=0, fused=0):
     r = torch.randn(M, N, device=dev) if res else None
 
     def fn():
-        ops.gemm(A, Wt, out_f32=out, bias=bias, residual=r, force_bn=bn, force_split=split, force_csplit=csplit, fused_split=fused,
+        ops.gemm(A, Wt, out_f32=out, bias=bias, residual=r, force_bn=bn, force_split=split, force_csplit=csplit,
                  conv=None if conv is None else (*conv, 3, 3, 1, 1))
     return fn, 2.0 * M * N * K
 
@@ -99,14 +99,8 @@ for cs in (1, 2, 4):
     fn, fl = gemm_case(512, 576, 2304, 128, csplit=cs)
     bench(f"gemm M=512 N=576 K=2304 bn=128 cluster-split={cs}", fn, flops=fl)
 for sp in (4, 9, 18):
-    fn, fl = gemm_case(128, 960, 8640, 128, split=sp, fused=1)
+    fn, fl = gemm_case(128, 960, 8640, 128, split=sp)
     bench(f"gemm M=128 N=960 K=8640 bn=128 ws-split={sp} (2 launches)", fn, flops=fl)
-    fn, fl = gemm_case(128, 960, 8640, 128, split=sp, fused=0)
-    bench(f"gemm M=128 N=960 K=8640 bn=128 split={sp} (single launch, rendezvous)", fn, flops=fl)
-for (M, N, K) in [(128, 960, 960), (128, 960, 3840), (512, 576, 2304), (2048, 384, 1536)]:
-    for fu in (1, 0):
-        fn, fl = gemm_case(M, N, K, 0, res=True, fused=fu)
-        bench(f"gemm M={M} N={N} K={K} +res auto-split " + ("(2 launches)" if fu else "(single launch)"), fn, flops=fl)
 fn, fl = gemm_case(128, 960, 0, 128, conv=(2, 32, 2, 960), split=0)
 bench("conv3x3 B=2 32x2 C=960->960 bn=128 split=auto (implicit)", fn, flops=fl)
 fn, fl = gemm_case(512, 576, 0, 0, conv=(2, 64, 4, 576), split=0)
