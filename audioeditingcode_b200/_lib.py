@@ -38,6 +38,7 @@ _SIGS = {
     "ae_set_pdl": (None, [i32]),
     "ae_set_splitk_ctas": (None, [i32]),
     "ae_set_fast_epilogue": (None, [i32]),
+    "ae_set_tile_model": (None, [i32]),
     "ae_set_gn_fused": (None, [i32]),
     "ae_sched_create": (i32, [vp, i32, f32, vp, i32, i32, C.POINTER(vp)]),
     "ae_sched_create_from_rows": (i32, [C.POINTER(AeSchedRow), i32, i32, i32, C.POINTER(vp)]),

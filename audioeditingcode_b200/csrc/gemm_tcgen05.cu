@@ -717,6 +717,8 @@ extern "C" void ae_set_pdl(int mode) { g_use_pdl = (mode == 1 || mode == 2) ? mo
 
 static int g_splitk_ctas = 148;
 static int g_fast_epi = 1;
+static int g_tile_model = 1;
+extern "C" void ae_set_tile_model(int on) { g_tile_model = on ? 1 : 0; }
 extern "C" void ae_set_fast_epilogue(int mode) { g_fast_epi = (mode == 0 || mode == 2) ? mode : 1; }
 extern "C" void ae_set_splitk_ctas(int ctas) { g_splitk_ctas = ctas < 1 ? 148 : ctas; }
 
@@ -798,10 +800,15 @@ extern "C" int ae_gemm(const ae_gemm_args* a, ae_stream stream) {
   AE_CHECK_ARG(a->ldw >= a->K, "ae_gemm: ldw < K");
   p.kb_per_split = p.num_kblocks;
 
-  // ---- tile width.  Wide tiles minimise shared-memory traffic per FLOP; parallelism for small grids comes from
-  //      split-K (below), not from narrow tiles.
+  // ---- tile width and K split.  Grids of at least one wave: 128-wide tiles (least shared-memory traffic per FLOP).
+  //      Sub-wave grids (reverse process at batch 2) are bound by how fast ONE SM can pull its CTA's operands through
+  //      L2 (~70 KB/us measured: [128x960x960] takes 9.9 / 7.7 / 6.5 us at BN = 128 / 64 / 32), so the tile width and
+  //      the K split are chosen together to minimise the operand bytes per SM, charging a split for its reduce launch.
   const long long tiles_m = (a->M + BM - 1) / BM;
+  const bool may_split = batch == 1 && a->act != 2 && a->splitk_ws && a->N % 4 == 0 && a->force_split != 1 &&
+                         a->force_csplit <= 1;
   int bn = a->force_bn;
+  int S_model = 0;   // 0: no model decision (forced / large grid)
   if (bn == 0) {
     if (a->N <= 32)
       bn = 32;
@@ -809,6 +816,39 @@ extern "C" int ae_gemm(const ae_gemm_args* a, ae_stream stream) {
       bn = 64;
     else
       bn = 128;
+    const long long tiles128 = tiles_m * ((a->N + 127) / 128);
+    if (g_tile_model && batch == 1 && tiles128 < g_splitk_ctas && a->force_split <= 1) {
+      double best = 1e30;
+      const int cands[3] = {128, 64, 32};
+      for (int ci = 0; ci < 3; ++ci) {
+        const int c = cands[ci];
+        if (a->act == 2 && c < 32) continue;
+        if (c > 32 && a->N <= c / 2) continue;                       // mostly padding
+        const long long t = tiles_m * ((a->N + c - 1) / c);
+        const double stage_kb = 16.0 + c / 8.0;                       // A tile + W tile per K block
+        int smax = 1;
+        if (may_split && a->force_split == 0 && t < g_splitk_ctas) {
+          smax = (int)(g_splitk_ctas / t);
+          if (smax > p.num_kblocks / 4) smax = p.num_kblocks / 4;     // >= 4 K blocks per slice
+          if (smax > 32) smax = 32;
+          if (smax < 1) smax = 1;
+        }
+        for (int sp = 1; sp <= smax; sp = (sp < 4 ? sp + 1 : sp + 2)) {
+          if (sp > 1 && (long long)sp * a->M * a->N * 4 > a->splitk_ws_bytes) break;
+          const int kbs = (p.num_kblocks + sp - 1) / sp;
+          const long long ctas_c = t * sp;
+          const double waves = ctas_c <= g_splitk_ctas ? 1.0 : (double)ctas_c / g_splitk_ctas;
+          double cost = waves * kbs * stage_kb / 70.0          // us to stream one SM's operands
+                        + (c / 128.0) * 1.0                     // epilogue
+                        + (sp > 1 ? 3.0 : 0.0);                 // reduce launch
+          if (cost < best - 1e-9) {
+            best = cost;
+            bn = c;
+            S_model = sp;
+          }
+        }
+      }
+    }
   }
   AE_CHECK_ARG(bn == 32 || bn == 64 || bn == 128, "ae_gemm: force_bn must be 32, 64 or 128");
   const long long tiles = tiles_m * ((a->N + bn - 1) / bn);
@@ -828,6 +868,8 @@ extern "C" int ae_gemm(const ae_gemm_args* a, ae_stream stream) {
   if (CS == 1 && batch == 1 && a->act != 2 && a->splitk_ws && a->N % 4 == 0 && a->force_split != 1) {
     if (a->force_split > 1)
       S = a->force_split;
+    else if (S_model > 0)
+      S = S_model;
     else if (tiles <= 48 && p.num_kblocks >= 12) {
       S = (int)(g_splitk_ctas / tiles);
       const int max_by_k = p.num_kblocks / 6;
@@ -921,7 +963,7 @@ extern "C" int ae_gemm(const ae_gemm_args* a, ae_stream stream) {
   r.alpha = p.alpha;
   long long blocks = ceil_div64(r.MN / 4, 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
-  cudaError_t e = launch_kernel(splitk_reduce_kernel, dim3((unsigned)blocks), dim3(256), (size_t)0, st, r);
+  cudaError_t e = launch_kernel_early(splitk_reduce_kernel, dim3((unsigned)blocks), dim3(256), (size_t)0, st, r);
   if (e != cudaSuccess) return fail(AE_ECUDA, "splitk_reduce launch: %s", cudaGetErrorString(e));
   return launched("ae_gemm(splitk_reduce)");
 }

@@ -45,6 +45,8 @@ class CudaOps:
         # programmatic dependent launch: GEMM-only mode (weight prefetch ahead of the dependency wait) measured +2-4 %
         # end to end on B200, all-kernel mode measured slower (profiles/r01_bench_v7_*, r01_bench_v8_*)
         self.lib.ae_set_pdl(int(os.environ.get("AEDIT_PDL", "2")))   # 0 off, 1 all kernels, 2 GEMMs only
+        if "AEDIT_TILE_MODEL" in os.environ:
+            self.lib.ae_set_tile_model(int(os.environ["AEDIT_TILE_MODEL"]))
         if "AEDIT_FAST_EPILOGUE" in os.environ:
             self.lib.ae_set_fast_epilogue(int(os.environ["AEDIT_FAST_EPILOGUE"]))
         if "AEDIT_GN_FUSED" in os.environ:

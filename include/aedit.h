@@ -50,6 +50,10 @@ void ae_set_splitk_ctas(int ctas);
  * 0 = always the row-per-thread epilogue.  All three give identical bits (tests/test_gpu_kernels.py). */
 void ae_set_fast_epilogue(int mode);
 
+/* 1 (default): sub-wave GEMM grids choose tile width and K split jointly from an operand-bytes-per-SM model;
+ * 0: fixed rule (128-wide tiles, split only for >= 12 K blocks) — kept for A/B measurements. */
+void ae_set_tile_model(int on);
+
 
 /* GroupNorm of small tensors (B <= 8, <= 8 MB per sample) as ONE thread-block-cluster launch instead of a statistics
  * launch + an apply launch.  Default OFF: 16 CTAs reading 200 KB each measured 2-3x slower than the two wide launches. */

@@ -206,3 +206,38 @@ def test_ddim_mode_vs_reference_golden():
     y1, y2 = float(g["bf16_autocast_err_inv"]), float(g["bf16_autocast_err_rec"])
     print(f"ddim inversion rel-L2 {r1:.2e} (torch-bf16 {y1:.2e}); regeneration rel-L2 {r2:.2e} (torch-bf16 {y2:.2e})")
     assert r1 <= max(5e-2, y1) and r2 <= max(5e-2, y2)
+
+
+def test_full_size_properties_audioldm2_large():
+    """BASELINE configs[1] geometry (AudioLDM2-large architecture, 10 s clip -> latent [1,8,256,16], two text
+    streams), where the CPU oracle takes minutes per step: size-independent properties instead of a direct
+    comparison.  (i) xts[0] == x0 and zs[0] == 0 (inversion_utils.py:133); (ii) replay invariant F9 at full size:
+    the reverse process with the inversion's own prompt / cfg reproduces every stored x_t bit for bit
+    (step-sequential forward); (iii) the timestep-batched forward process (F8) agrees with the sequential one to
+    bf16-operand accuracy; (iv) determinism: the same call twice gives the same bits."""
+    from audioeditingcode_b200 import models, unet_config as C
+    from audioeditingcode_b200.ddm_inversion import inversion_utils as IU
+    N, ts = 12, 8
+    dev = torch.device("cuda")
+    m = models.load_model("cvssp/audioldm2-large", dev, N, config=C.preset("audioldm2-large"))
+    g = torch.Generator().manual_seed(1)
+    x0 = (0.5 * torch.randn(1, 8, 256, 16, generator=g)).to(dev)
+    noise = torch.randn(N, 8, 256, 16, generator=g).to(dev)
+    kw = dict(etas=1.0, prompts=["a recording of a dog barking"], cfg_scales=[3.0], num_inference_steps=N,
+              numerical_fix=True, noise=noise)
+    _, zs, xts, _ = IU.inversion_forward_process(m, x0, forward_batch=1, **kw)
+    assert torch.equal(xts[0], x0[0]) and int(zs[0].abs().max()) == 0
+    assert torch.isfinite(zs).all() and torch.isfinite(xts).all()
+    trace = []
+    w, _ = IU.inversion_reverse_process(m, xT=xts, tstart=torch.tensor([ts], dtype=torch.int), etas=1.0,
+                                        prompts=["a recording of a dog barking"], neg_prompts=[""], cfg_scales=[3.0],
+                                        zs=zs[:ts], trace=trace)
+    for k, xt in enumerate(trace):
+        level = ts - k - 1
+        if level >= 1:
+            assert torch.equal(xt[0], xts[level]), f"full-size replay mismatch at level {level}"
+    _, zs_b, xts_b, _ = IU.inversion_forward_process(m, x0, forward_batch=6, **kw)
+    rel = ((zs_b - zs).norm() / zs.norm()).item()
+    assert rel < 6e-2, f"batched vs sequential forward: rel-L2(zs) {rel}"
+    _, zs_b2, xts_b2, _ = IU.inversion_forward_process(m, x0, forward_batch=6, **kw)
+    assert torch.equal(zs_b, zs_b2) and torch.equal(xts_b, xts_b2)
