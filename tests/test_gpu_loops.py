@@ -211,7 +211,7 @@ def test_ddim_mode_vs_reference_golden():
 def test_full_size_properties_audioldm2_large():
     """BASELINE configs[1] geometry (AudioLDM2-large architecture, 10 s clip -> latent [1,8,256,16], two text
     streams), where the CPU oracle takes minutes per step: size-independent properties instead of a direct
-    comparison.  (i) xts[0] == x0 and zs[0] == 0 (inversion_utils.py:133); (ii) replay invariant F9 at full size:
+    comparison.  (i) xts[0] == x0 up to fp32 rounding and zs[0] == 0 (inversion_utils.py:127-133); (ii) replay invariant F9 at full size:
     the reverse process with the inversion's own prompt / cfg reproduces every stored x_t bit for bit
     (step-sequential forward); (iii) the timestep-batched forward process (F8) agrees with the sequential one to
     bf16-operand accuracy; (iv) determinism: the same call twice gives the same bits."""
@@ -226,7 +226,8 @@ def test_full_size_properties_audioldm2_large():
     kw = dict(etas=1.0, prompts=["a recording of a dog barking"], cfg_scales=[3.0], num_inference_steps=N,
               numerical_fix=True, noise=noise)
     _, zs, xts, _ = IU.inversion_forward_process(m, x0, forward_batch=1, **kw)
-    assert torch.equal(xts[0], x0[0]) and int(zs[0].abs().max()) == 0
+    # xts[0] is overwritten by the last step's recomputed x_{t-1} = mu + sigma*z (numerical_fix): x0 up to rounding
+    assert torch.allclose(xts[0], x0[0], atol=1e-5, rtol=0) and float(zs[0].abs().max()) == 0.0
     assert torch.isfinite(zs).all() and torch.isfinite(xts).all()
     trace = []
     w, _ = IU.inversion_reverse_process(m, xT=xts, tstart=torch.tensor([ts], dtype=torch.int), etas=1.0,
