@@ -231,34 +231,31 @@ __global__ void __launch_bounds__(kGNThreads) gn_apply_kernel(GNArgs a) {
   }
 }
 
-// ---- small-batch path: ONE launch per GroupNorm.  grid (CS, B) with thread-block clusters of CS CTAs along x: the
-// CS CTAs of a sample each own HW/CS positions, (1) read them once — keeping them in shared memory when the slice
-// fits (STAGE) —, (2) reduce to per-group partial sums, (3) exchange the partials through distributed shared
-// memory in rank order (fixed order -> the same bits in every CTA, independent of the batch), (4) normalise from
-// the staged copy.  Replaces a stats launch + an apply launch when the whole tensor is a few MB and the two
-// launches' latency, not bandwidth, is the cost (reverse process, B = 2).
-__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
-__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
-
-template <bool STAGE>
-__global__ void __launch_bounds__(512) gn_fused_kernel(GNArgs a) {
+// ---- small-batch path: ONE launch per GroupNorm.  grid (S, B) with S*B <= #SMs, so every CTA is resident at the
+// same time (one per SM).  The S CTAs of a sample each own HW/S positions: (1) read them once into shared memory,
+// (2) reduce them to per-group partial sums (double) published to the workspace, (3) rendezvous on the sample's
+// arrival counter (release / acquire at gpu scope; a lost peer traps instead of hanging), (4) every CTA reduces the S
+// partials of its sample in a fixed shape (same bits in every CTA, independent of what else is in the batch) and
+// (5) normalises its shared-memory slice.  One launch instead of stats + apply, and the tensor is read once.
+// Only used when the whole grid fits on the machine; callers that run several such grids CONCURRENTLY (two streams)
+// must disable it (ae_set_gn_fused(0)), because waiting CTAs of two grids could starve each other of SMs.
+__global__ void __launch_bounds__(512) gn_resident_kernel(GNArgs a) {
   pdl_trigger();
   pdl_wait();
   extern __shared__ __align__(16) float sm[];
-  // layout: part[G][2] double | mean[G] rstd[G] | A[C] B[C] | red[TY][2C] | stage[chunk][C] (STAGE only)
+  // layout: mean[G] rstd[G] | A[C] B[C] | red[TY][2C] | stage[chunk][C]
   const int TX = blockDim.x, TY = blockDim.y;
-  double* s_part = reinterpret_cast<double*>(sm);
-  float* s_mean = sm + 4 * a.G;
+  float* s_mean = sm;
   float* s_rstd = s_mean + a.G;
   float* s_A = s_rstd + a.G;
   float* s_B = s_A + a.C;
   float* s_red = s_B + a.C;
   float* s_stage = s_red + (size_t)TY * 2 * a.C;
-  const int rank = blockIdx.x, CS = gridDim.x, b = blockIdx.y;
+  const int s = blockIdx.x, b = blockIdx.y;
   const int tx = threadIdx.x, ty = threadIdx.y;
   const int tid = ty * TX + tx, nthr = TX * TY;
   const int lane = tid & 31, wid = tid >> 5, nw = nthr >> 5;
-  const long long p0 = (long long)rank * a.chunk;
+  const long long p0 = (long long)s * a.chunk;
   const long long p1 = min(a.HW, p0 + a.chunk);
   const int nq = a.C >> 2;
   float su[kGNMaxQuadsPerThread][4], sq[kGNMaxQuadsPerThread][4];
@@ -293,10 +290,8 @@ __global__ void __launch_bounds__(512) gn_fused_kernel(GNArgs a) {
         su[k][1] += v[u][k].y; sq[k][1] += v[u][k].y * v[u][k].y;
         su[k][2] += v[u][k].z; sq[k][2] += v[u][k].z * v[u][k].z;
         su[k][3] += v[u][k].w; sq[k][3] += v[u][k].w * v[u][k].w;
-        if (STAGE) {
-          const int qd = tx + k * TX;
-          if (p < p1 && qd < nq) *reinterpret_cast<float4*>(s_stage + (size_t)(p - p0) * a.C + (qd << 2)) = v[u][k];
-        }
+        const int qd = tx + k * TX;
+        if (p < p1 && qd < nq) *reinterpret_cast<float4*>(s_stage + (size_t)(p - p0) * a.C + (qd << 2)) = v[u][k];
       }
     }
   }
@@ -331,45 +326,62 @@ __global__ void __launch_bounds__(512) gn_fused_kernel(GNArgs a) {
         dsq += __shfl_down_sync(0xffffffffu, dsq, o);
       }
       if (lane == 0) {
-        s_part[2 * g] = dsu;
-        s_part[2 * g + 1] = dsq;
+        double* dst = a.partial + (((long long)b * a.S + s) * a.G + g) * 2;
+        __stcg(dst, dsu);
+        __stcg(dst + 1, dsq);
       }
     }
   }
+  // ---- rendezvous of the S resident CTAs of sample b
+  __threadfence();
   __syncthreads();
-  cluster_arrive();   // release: this CTA's partials are published
-  cluster_wait();     // acquire: every peer's partials are visible
+  unsigned int* ctr = a.counters + b;
+  if (tid == 0) {
+    atomicAdd(ctr, 1u);
+    unsigned int seen = 0, spins = 0;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(ctr) : "memory");
+      if (seen < (unsigned)a.S && ++spins > (1u << 26)) __trap();
+    } while (seen < (unsigned)a.S);
+  }
+  __syncthreads();
+  __threadfence();
   {
-    // group g <- thread g: the CS partials are fetched with independent DSMEM loads, then summed in rank order
-    const uint32_t part_addr = (uint32_t)__cvta_generic_to_shared(s_part);
-    for (int g = tid; g < a.G; g += nthr) {
-      double ps[16], pq[16];
-#pragma unroll
-      for (int r = 0; r < 16; ++r) {
-        ps[r] = 0.0;
-        pq[r] = 0.0;
-        if (r < CS) {
-          uint32_t raddr;
-          asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(part_addr + (uint32_t)g * 16u), "r"(r));
-          asm volatile("ld.shared::cluster.v2.f64 {%0, %1}, [%2];" : "=d"(ps[r]), "=d"(pq[r]) : "r"(raddr) : "memory");
-        }
+    // one warp per group: lane l sums partials l, l+32, l+64 (S <= 64 -> at most 2 per lane) in that order, then a
+    // fixed-shape shuffle tree
+    for (int g = wid; g < a.G; g += nw) {
+      const double* src = a.partial + ((long long)b * a.S * a.G + g) * 2;
+      const long long st = (long long)a.G * 2;
+      double p0s = 0.0, q0s = 0.0, p1s = 0.0, q1s = 0.0;
+      if (lane < a.S) {
+        p0s = __ldcg(src + lane * st);
+        q0s = __ldcg(src + lane * st + 1);
       }
-      double dsu = 0.0, dsq = 0.0;
-#pragma unroll
-      for (int r = 0; r < 16; ++r) {
-        dsu += ps[r];
-        dsq += pq[r];
+      if (lane + 32 < a.S) {
+        p1s = __ldcg(src + (lane + 32) * st);
+        q1s = __ldcg(src + (lane + 32) * st + 1);
       }
-      const double inv_n = 1.0 / ((double)a.HW * a.cpg);
-      const double mean = dsu * inv_n;
-      double var = dsq * inv_n - mean * mean;
-      if (var < 0.0) var = 0.0;
-      s_mean[g] = (float)mean;
-      s_rstd[g] = rsqrtf((float)var + a.eps);
+      double dsu = p0s + p1s, dsq = q0s + q1s;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        dsu += __shfl_down_sync(0xffffffffu, dsu, o);
+        dsq += __shfl_down_sync(0xffffffffu, dsq, o);
+      }
+      if (lane == 0) {
+        const double inv_n = 1.0 / ((double)a.HW * a.cpg);
+        const double mean = dsu * inv_n;
+        double var = dsq * inv_n - mean * mean;
+        if (var < 0.0) var = 0.0;
+        s_mean[g] = (float)mean;
+        s_rstd[g] = rsqrtf((float)var + a.eps);
+      }
     }
   }
   __syncthreads();
-  cluster_arrive();   // this CTA no longer reads its peers' shared memory (matched by the wait before exit)
+  if (tid == 0) {   // departure: the last CTA of the sample re-arms the counter for the next launch
+    const unsigned int old = atomicAdd(ctr, 1u);
+    if (old == 2u * (unsigned)a.S - 1u) atomicExch(ctr, 0u);
+  }
   for (int c = tid; c < a.C; c += nthr) {
     const int g = c / a.cpg;
     const float A = s_rstd[g] * __ldg(a.gamma + c);
@@ -377,62 +389,40 @@ __global__ void __launch_bounds__(512) gn_fused_kernel(GNArgs a) {
     s_B[c] = __ldg(a.beta + c) - s_mean[g] * A;
   }
   __syncthreads();
-  for (long long pb = p0 + ty; pb < p1; pb += (long long)TY * kGNUnroll) {
-    float4 v[kGNUnroll][kGNMaxQuadsPerThread];
+  for (long long p = p0 + ty; p < p1; p += TY) {
+    const long long row = (long long)b * a.HW + p;
 #pragma unroll
-    for (int u = 0; u < kGNUnroll; ++u) {
-      const long long p = pb + (long long)u * TY;
-      const long long row = (long long)b * a.HW + p;
+    for (int k = 0; k < kGNMaxQuadsPerThread; ++k) {
+      const int qd = tx + k * TX;
+      if (qd >= nq) continue;
+      const int c = qd << 2;
+      const float4 v = *reinterpret_cast<const float4*>(s_stage + (size_t)(p - p0) * a.C + c);
+      const float in[4] = {v.x, v.y, v.z, v.w};
+      const float4 A4 = *reinterpret_cast<const float4*>(s_A + c);
+      const float4 B4 = *reinterpret_cast<const float4*>(s_B + c);
+      float o[4] = {fmaf(in[0], A4.x, B4.x), fmaf(in[1], A4.y, B4.y), fmaf(in[2], A4.z, B4.z), fmaf(in[3], A4.w, B4.w)};
+      if (a.silu) {
 #pragma unroll
-      for (int k = 0; k < kGNMaxQuadsPerThread; ++k) {
-        const int qd = tx + k * TX;
-        if (p < p1 && qd < nq) {
-          const int c = qd << 2;
-          if (STAGE)
-            v[u][k] = *reinterpret_cast<const float4*>(s_stage + (size_t)(p - p0) * a.C + c);
-          else
-            v[u][k] = c < a.C1 ? *reinterpret_cast<const float4*>(a.x1 + row * a.C1 + c)
-                               : *reinterpret_cast<const float4*>(a.x2 + row * a.C2 + (c - a.C1));
-        }
+        for (int e = 0; e < 4; ++e) o[e] = silu_f(o[e]);
       }
-    }
-#pragma unroll
-    for (int u = 0; u < kGNUnroll; ++u) {
-      const long long p = pb + (long long)u * TY;
-      const long long row = (long long)b * a.HW + p;
-#pragma unroll
-      for (int k = 0; k < kGNMaxQuadsPerThread; ++k) {
-        const int qd = tx + k * TX;
-        if (p >= p1 || qd >= nq) continue;
-        const int c = qd << 2;
-        const float in[4] = {v[u][k].x, v[u][k].y, v[u][k].z, v[u][k].w};
-        const float4 A4 = *reinterpret_cast<const float4*>(s_A + c);
-        const float4 B4 = *reinterpret_cast<const float4*>(s_B + c);
-        float o[4] = {fmaf(in[0], A4.x, B4.x), fmaf(in[1], A4.y, B4.y), fmaf(in[2], A4.z, B4.z), fmaf(in[3], A4.w, B4.w)};
-        if (a.silu) {
-#pragma unroll
-          for (int e = 0; e < 4; ++e) o[e] = silu_f(o[e]);
-        }
-        const long long off = row * a.C + c;
-        __nv_bfloat162 h0 = __floats2bfloat162_rn(o[0], o[1]);
-        __nv_bfloat162 h1 = __floats2bfloat162_rn(o[2], o[3]);
-        uint2 pk;
-        pk.x = *reinterpret_cast<uint32_t*>(&h0);
-        pk.y = *reinterpret_cast<uint32_t*>(&h1);
-        *reinterpret_cast<uint2*>(a.out + off) = pk;
-        if (a.raw_out) {
-          __nv_bfloat162 r0 = __floats2bfloat162_rn(in[0], in[1]);
-          __nv_bfloat162 r1 = __floats2bfloat162_rn(in[2], in[3]);
-          uint2 rk;
-          rk.x = *reinterpret_cast<uint32_t*>(&r0);
-          rk.y = *reinterpret_cast<uint32_t*>(&r1);
-          *reinterpret_cast<uint2*>(a.raw_out + off) = rk;
-        }
-        if (a.cat_out) *reinterpret_cast<float4*>(a.cat_out + off) = v[u][k];
+      const long long off = row * a.C + c;
+      __nv_bfloat162 h0 = __floats2bfloat162_rn(o[0], o[1]);
+      __nv_bfloat162 h1 = __floats2bfloat162_rn(o[2], o[3]);
+      uint2 pk;
+      pk.x = *reinterpret_cast<uint32_t*>(&h0);
+      pk.y = *reinterpret_cast<uint32_t*>(&h1);
+      *reinterpret_cast<uint2*>(a.out + off) = pk;
+      if (a.raw_out) {
+        __nv_bfloat162 r0 = __floats2bfloat162_rn(in[0], in[1]);
+        __nv_bfloat162 r1 = __floats2bfloat162_rn(in[2], in[3]);
+        uint2 rk;
+        rk.x = *reinterpret_cast<uint32_t*>(&r0);
+        rk.y = *reinterpret_cast<uint32_t*>(&r1);
+        *reinterpret_cast<uint2*>(a.raw_out + off) = rk;
       }
+      if (a.cat_out) *reinterpret_cast<float4*>(a.cat_out + off) = v;
     }
   }
-  cluster_wait();     // do not exit (and free shared memory) while a peer may still be reading the partials
 }
 
 // one warp per row; the row is read once into registers: NV float4 per lane (C <= 128*NV), NV a template constant
@@ -489,7 +479,9 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
 template <int NV>
 cudaError_t launch_ln(const float* x, long long rows, int C, float eps, const float* gamma, const float* beta,
                       __nv_bfloat16* out, cudaStream_t st) {
-  const int warps = 4;  // small CTAs: more of them, shorter tails
+  // one warp per row; few rows (reverse process at batch 2: 128-2048 rows) -> fewer rows per CTA so the rows spread
+  // over all SMs instead of queueing on a few
+  const int warps = rows >= 148 * 16 ? 4 : (rows >= 148 * 4 ? 2 : 1);
   return launch_kernel(layernorm_kernel<NV>, dim3((unsigned)ceil_div64(rows, warps)), dim3(warps * 32), (size_t)0, st, x,
                        rows, C, eps, gamma, beta, out);
 }
@@ -499,7 +491,7 @@ cudaError_t launch_ln(const float* x, long long rows, int C, float eps, const fl
 
 using namespace aedit;
 
-static int g_gn_fused = 0;  // measured slower than stats + apply on B200 (profiles/r01_microbench_v9.log): opt-in
+static int g_gn_fused = 1;
 extern "C" void ae_set_gn_fused(int on) { g_gn_fused = on ? 1 : 0; }
 
 extern "C" int64_t ae_groupnorm_workspace_bytes(int B, int groups) {
@@ -542,51 +534,30 @@ extern "C" int ae_groupnorm(const float* x1, int C1, const float* x2, int C2, in
   a.out = reinterpret_cast<__nv_bfloat16*>(out_bf16);
   a.raw_out = reinterpret_cast<__nv_bfloat16*>(raw_out_bf16);
   a.cat_out = cat_out_f32;
-  a.partial = nullptr;
-  a.stats = nullptr;
-  a.counters = nullptr;
-  if (g_gn_fused && B <= 8 && HW * (int64_t)C * 4 <= (8ll << 20) && groups % 2 == 0) {
-    // fused single-launch path (thread-block clusters); cluster size: up to 16 (non-portable, enabled once),
-    // at least TY positions per CTA
-    static int max_cs = 0;
-    if (max_cs == 0) {
-      max_cs = 8;
-      if (cudaFuncSetAttribute(gn_fused_kernel<true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess &&
-          cudaFuncSetAttribute(gn_fused_kernel<false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess)
-        max_cs = 16;
-      cudaFuncSetAttribute(gn_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-      cudaFuncSetAttribute(gn_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  char* wsb = reinterpret_cast<char*>(workspace);
+  a.partial = reinterpret_cast<double*>(wsb);
+  a.stats = reinterpret_cast<float*>(wsb + (size_t)B * kMaxSplits * groups * 2 * 8);
+  a.counters = reinterpret_cast<unsigned int*>(wsb + (size_t)B * kMaxSplits * groups * 2 * 8 + (size_t)B * groups * 2 * 4);
+  if (g_gn_fused && groups % 2 == 0) {
+    // single resident launch (see gn_resident_kernel): the whole grid must fit on the machine, one CTA per SM
+    static int n_sm = 0;
+    if (n_sm == 0) {
+      int dev = 0;
+      cudaGetDevice(&dev);
+      if (cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n_sm <= 0) n_sm = 1;
+      cudaFuncSetAttribute(gn_resident_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
       cudaGetLastError();
     }
-    int CS = max_cs;
-    while (CS > 1 && HW / CS < TY) CS >>= 1;
-    a.S = CS;
-    a.chunk = ceil_div64(HW, CS);
-    if ((int)ceil_div64(HW, a.chunk) == CS) {   // every rank owns at least one position
-      const size_t fixed = (size_t)(4 * groups + 2 * groups + 2 * C + TY * 2 * C) * sizeof(float);
-      const size_t stage = (size_t)a.chunk * C * sizeof(float);
-      const bool staged = fixed + stage <= 200 * 1024;
-      const size_t smem = fixed + (staged ? stage : 0);
-      if (smem <= 227 * 1024) {
-        cudaLaunchConfig_t cfg{};
-        cfg.gridDim = dim3(CS, B);
-        cfg.blockDim = dim3(TX, TY);
-        cfg.dynamicSmemBytes = smem;
-        cfg.stream = as_stream(stream);
-        cudaLaunchAttribute attr[2];
-        attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = (unsigned)CS;
-        attr[0].val.clusterDim.y = 1;
-        attr[0].val.clusterDim.z = 1;
-        attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        attr[1].val.programmaticStreamSerializationAllowed = 1;
-        cfg.attrs = attr;
-        cfg.numAttrs = g_use_pdl == 1 ? 2 : 1;
-        if (staged)
-          cudaLaunchKernelEx(&cfg, gn_fused_kernel<true>, a);
-        else
-          cudaLaunchKernelEx(&cfg, gn_fused_kernel<false>, a);
-        return launched("ae_groupnorm(fused)");
+    int S = n_sm / B;
+    if (S > kMaxSplits) S = kMaxSplits;
+    if (S > HW / 2) S = (int)(HW / 2);
+    if (S >= 2) {
+      a.chunk = ceil_div64(HW, S);
+      a.S = (int)ceil_div64(HW, a.chunk);
+      const size_t smem = (size_t)(2 * groups + 2 * C + TY * 2 * C) * sizeof(float) + (size_t)a.chunk * C * sizeof(float);
+      if (smem <= 200 * 1024 && (long long)a.S * B <= n_sm) {
+        launch_kernel(gn_resident_kernel, dim3(a.S, B), dim3(TX, TY), smem, as_stream(stream), a);
+        return launched("ae_groupnorm(resident)");
       }
     }
   }
@@ -598,19 +569,6 @@ extern "C" int ae_groupnorm(const float* x1, int C1, const float* x2, int C2, in
   if (S < 1) S = 1;
   a.chunk = ceil_div64(HW, S);
   a.S = (int)ceil_div64(HW, a.chunk);
-  a.eps = eps;
-  a.gamma = gamma;
-  a.beta = beta;
-  a.silu = silu;
-  a.out = reinterpret_cast<__nv_bfloat16*>(out_bf16);
-  a.raw_out = reinterpret_cast<__nv_bfloat16*>(raw_out_bf16);
-  a.cat_out = cat_out_f32;
-  char* ws = reinterpret_cast<char*>(workspace);
-  a.partial = reinterpret_cast<double*>(ws);
-  ws += (size_t)B * kMaxSplits * groups * 2 * 8;
-  a.stats = reinterpret_cast<float*>(ws);
-  ws += (size_t)B * groups * 2 * 4;
-  a.counters = reinterpret_cast<unsigned int*>(ws);
   cudaStream_t st = as_stream(stream);
   {
     const size_t smem = (size_t)TY * 2 * C * sizeof(float);

@@ -55,6 +55,8 @@ class GraphedForward:
         # batch is cut in two halves captured on two forked streams of the same graph, so the two dependency chains
         # interleave on the SMs.  Each chain owns its workspaces (second CudaOps instance).
         self.dual = engine.dual_stream and B % 2 == 0 and B <= engine.dual_stream_max_b
+        if self.dual:
+            engine.ops.lib.ae_set_gn_fused(0)     # two concurrent resident GroupNorm grids could starve each other
         cur = torch.cuda.current_stream()
         side = torch.cuda.Stream()
         self._side2 = torch.cuda.Stream() if self.dual else None

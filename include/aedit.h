@@ -55,8 +55,10 @@ void ae_set_fast_epilogue(int mode);
 void ae_set_tile_model(int on);
 
 
-/* GroupNorm of small tensors (B <= 8, <= 8 MB per sample) as ONE thread-block-cluster launch instead of a statistics
- * launch + an apply launch.  Default OFF: 16 CTAs reading 200 KB each measured 2-3x slower than the two wide launches. */
+/* GroupNorm as ONE launch whenever the grid (<= 64 position slices per sample x B) fits on the machine with one CTA
+ * per SM and a slice fits in shared memory: the CTAs of a sample rendezvous on an arrival counter between the
+ * statistics and the normalisation (default on).  Turn it off when several GroupNorm grids may run CONCURRENTLY
+ * (two streams): CTAs of one grid waiting for peers that cannot be scheduled would hang (the kernel traps then). */
 void ae_set_gn_fused(int on);
 
 /* ------------------------------------------------------------------------------------------------

@@ -234,7 +234,8 @@ def test_im2col(ops, stride, pad, H, W, C):
                                                (2, 4096, 192, 0, 32, True), (2, 1024, 576, 384, 32, True),
                                                (12, 256, 192, 0, 32, True), (1, 7, 64, 0, 32, True)])
 def test_groupnorm(ops, B, HW, C1, C2, G, silu, fused):
-    """fused=1: single-launch thread-block-cluster path (small tensors); fused=0: stats + apply launches."""
+    """fused=1: single resident launch (counter rendezvous between statistics and normalisation) whenever the grid
+    fits on the machine; fused=0: stats + apply launches."""
     ops.lib.ae_set_gn_fused(fused)
     try:
         _groupnorm_case(ops, B, HW, C1, C2, G, silu)

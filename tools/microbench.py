@@ -76,7 +76,7 @@ for (B, HW, C) in [(2, 64, 960), (2, 4096, 192), (1, 4096, 192), (2, 4096, 384),
         if fused and B > 8:
             continue
         ops.lib.ae_set_gn_fused(fused)
-        bench(f"groupnorm B={B} HW={HW} C={C} " + ("(fused cluster launch)" if fused else "(stats + apply launches)"),
+        bench(f"groupnorm B={B} HW={HW} C={C} " + ("(single resident launch)" if fused else "(stats + apply launches)"),
               lambda: ops.groupnorm(gx, None, gg, gb, 1e-5, 32, True, go), launches_per_call=1 if fused else 2)
     ops.lib.ae_set_gn_fused(1)
 
