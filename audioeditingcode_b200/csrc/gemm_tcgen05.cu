@@ -838,9 +838,11 @@ extern "C" int ae_gemm(const ae_gemm_args* a, ae_stream stream) {
           const int kbs = (p.num_kblocks + sp - 1) / sp;
           const long long ctas_c = t * sp;
           const double waves = ctas_c <= g_splitk_ctas ? 1.0 : (double)ctas_c / g_splitk_ctas;
+          // reduce pass: launch + (S partial tiles written and read back, residual, outputs) at ~3 MB/us
+          const double reduce_us = sp > 1 ? 2.5 + (sp + 2.5) * (double)a->M * a->N * 4.0 / 3.0e6 : 0.0;
           double cost = waves * kbs * stage_kb / 70.0          // us to stream one SM's operands
                         + (c / 128.0) * 1.0                     // epilogue
-                        + (sp > 1 ? 3.0 : 0.0);                 // reduce launch
+                        + reduce_us;
           if (cost < best - 1e-9) {
             best = cost;
             bn = c;

@@ -548,8 +548,9 @@ extern "C" int ae_groupnorm(const float* x1, int C1, const float* x2, int C2, in
       cudaFuncSetAttribute(gn_resident_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
       cudaGetLastError();
     }
-    int S = n_sm / B;
-    if (S > kMaxSplits) S = kMaxSplits;
+    // slices per sample depend on the geometry only (never on B), so a sample's statistics have the same bits in
+    // every batch this path serves
+    int S = kMaxSplits;
     if (S > HW / 2) S = (int)(HW / 2);
     if (S >= 2) {
       a.chunk = ceil_div64(HW, S);
