@@ -491,7 +491,7 @@ cudaError_t launch_ln(const float* x, long long rows, int C, float eps, const fl
 
 using namespace aedit;
 
-static int g_gn_fused = 1;
+static int g_gn_fused = 0;  // measured no faster than stats + apply (profiles/r01_microbench_v15_gn_resident.log): opt-in
 extern "C" void ae_set_gn_fused(int on) { g_gn_fused = on ? 1 : 0; }
 
 extern "C" int64_t ae_groupnorm_workspace_bytes(int B, int groups) {
