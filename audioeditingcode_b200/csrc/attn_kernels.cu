@@ -44,7 +44,10 @@ template <int D>
 struct AttnCfg {
   static constexpr int DP = (D + 15) / 16 * 16;
   static constexpr int LDS = DP + 8;  // padded row (elements): conflict-free ldmatrix
-  static constexpr int kSmemBytes = (BQ + 4 * BKV) * LDS * 2;
+  // K/V ring depth: one 64-key tile takes ~0.2 us of MMA + softmax but ~1 us to arrive from L2, so a 2-deep ring
+  // stalls every iteration; 4 stages keep 3 tiles in flight (shared memory permitting for the wide heads)
+  static constexpr int NS = D <= 64 ? 4 : (D <= 96 ? 3 : 2);
+  static constexpr int kSmemBytes = (BQ + 2 * NS * BKV) * LDS * 2;
 };
 
 template <int D>
@@ -72,7 +75,8 @@ __global__ void __launch_bounds__(kAttnThreads) attention_kernel(AttnArgs a) {
   extern __shared__ __align__(16) uint8_t smem_attn[];
   __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(smem_attn);
   __nv_bfloat16* sK = sQ + BQ * LDS;
-  __nv_bfloat16* sV = sK + 2 * BKV * LDS;
+  constexpr int NS = C::NS;
+  __nv_bfloat16* sV = sK + NS * BKV * LDS;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t4 = lane & 3;
@@ -85,10 +89,17 @@ __global__ void __launch_bounds__(kAttnThreads) attention_kernel(AttnArgs a) {
   const __nv_bfloat16* vp = a.v + (long long)bkv * a.bs_v + (long long)head * D;
   const float* biasp = a.bias ? a.bias + (long long)bkv * a.ld_bias : nullptr;
 
+  const int ntiles = (a.Tk + BKV - 1) / BKV;
+  // prologue: Q and the first NS-1 key/value tiles, one commit group per tile (empty groups keep the count uniform)
   load_tile<D>(sQ, qp, a.ld_q, q0, a.Tq, tid);
-  load_tile<D>(sK, kp, a.ld_k, 0, a.Tk, tid);
-  load_tile<D>(sV, vp, a.ld_v, 0, a.Tk, tid);
-  ptx::cp_async_commit();
+#pragma unroll
+  for (int t = 0; t < NS - 1; ++t) {
+    if (t < ntiles) {
+      load_tile<D>(sK + t * BKV * LDS, kp, a.ld_k, t * BKV, a.Tk, tid);
+      load_tile<D>(sV + t * BKV * LDS, vp, a.ld_v, t * BKV, a.Tk, tid);
+    }
+    ptx::cp_async_commit();
+  }
 
   float o_acc[NB][4];
 #pragma unroll
@@ -99,16 +110,18 @@ __global__ void __launch_bounds__(kAttnThreads) attention_kernel(AttnArgs a) {
   float l_run[2] = {0.f, 0.f};
   uint32_t qf[KS][4];
 
-  const int ntiles = (a.Tk + BKV - 1) / BKV;
   for (int it = 0; it < ntiles; ++it) {
-    const int buf = it & 1;
-    if (it + 1 < ntiles) {
-      load_tile<D>(sK + (buf ^ 1) * BKV * LDS, kp, a.ld_k, (it + 1) * BKV, a.Tk, tid);
-      load_tile<D>(sV + (buf ^ 1) * BKV * LDS, vp, a.ld_v, (it + 1) * BKV, a.Tk, tid);
+    const int buf = it % NS;
+    {
+      // refill the slot consumed in the previous iteration (protected by that iteration's trailing barrier)
+      const int nt = it + NS - 1;
+      if (nt < ntiles) {
+        const int nb = nt % NS;
+        load_tile<D>(sK + nb * BKV * LDS, kp, a.ld_k, nt * BKV, a.Tk, tid);
+        load_tile<D>(sV + nb * BKV * LDS, vp, a.ld_v, nt * BKV, a.Tk, tid);
+      }
       ptx::cp_async_commit();
-      ptx::cp_async_wait<1>();
-    } else {
-      ptx::cp_async_wait<0>();
+      ptx::cp_async_wait<NS - 1>();   // tile `it` (and Q) have landed
     }
     __syncthreads();
     if (it == 0) {

@@ -123,17 +123,58 @@ __global__ void __launch_bounds__(512) gn_stats_kernel(GNArgs a) {
       }
       if (lane == 0) {
         double* dst = a.partial + (((long long)b * a.S + s) * a.G + g) * 2;
-        dst[0] = dsu;
-        dst[1] = dsq;
+        __stcg(dst, dsu);
+        __stcg(dst + 1, dsq);
       }
     }
+  }
+  // ---- the last CTA of the sample to arrive (ticket counter, no waiting) turns the S partials into mean / rstd:
+  // one warp per group, lane l sums partials l and l+32 (S <= 64), fixed-shape shuffle tree -> the bits do not depend
+  // on which CTA happens to be last.  The apply kernel then needs a single round of independent loads.
+  __shared__ int s_last;
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_last = (atomicAdd(a.counters + b, 1u) == (unsigned)a.S - 1u) ? 1 : 0;
+  __syncthreads();
+  if (s_last) {
+    __threadfence();
+    const int lane = tid & 31, wid = tid >> 5, nw = nthr >> 5;
+    for (int g = wid; g < a.G; g += nw) {
+      const double* src = a.partial + ((long long)b * a.S * a.G + g) * 2;
+      const long long st = (long long)a.G * 2;
+      double p0 = 0.0, q0 = 0.0, p1 = 0.0, q1 = 0.0;
+      if (lane < a.S) {
+        p0 = __ldcg(src + lane * st);
+        q0 = __ldcg(src + lane * st + 1);
+      }
+      if (lane + 32 < a.S) {
+        p1 = __ldcg(src + (lane + 32) * st);
+        q1 = __ldcg(src + (lane + 32) * st + 1);
+      }
+      double dsu = p0 + p1, dsq = q0 + q1;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        dsu += __shfl_down_sync(0xffffffffu, dsu, o);
+        dsq += __shfl_down_sync(0xffffffffu, dsq, o);
+      }
+      if (lane == 0) {
+        const double inv_n = 1.0 / ((double)a.HW * a.cpg);
+        const double mean = dsu * inv_n;
+        double var = dsq * inv_n - mean * mean;
+        if (var < 0.0) var = 0.0;
+        float* dst = a.stats + ((long long)b * a.G + g) * 2;
+        dst[0] = (float)mean;
+        dst[1] = rsqrtf((float)var + a.eps);
+      }
+    }
+    if (tid == 0) a.counters[b] = 0u;   // re-arm for the next launch (stream-ordered after this kernel)
   }
 }
 
 // grid (ceil(HW*C/4 / (256*kGNItems)), B): each thread normalises kGNItems float4 items (coalesced along channels).
-// Order of work in a CTA: (1) issue the data loads, (2) finalise the group statistics of the sample from the S
-// partials (one warp per group, fixed-shape tree: identical bits in every CTA), (3) build the per-channel affine
-// table y = x*A[c] + B[c] in shared memory, (4) apply + SiLU + bf16 store.
+// Order of work in a CTA: (1) issue the data loads, (2) load mean / rstd (finalised by the last statistics CTA) and
+// gamma / beta — independent of (1), so one memory round trip covers both —, (3) build the per-channel affine table
+// y = x*A[c] + B[c] in shared memory, (4) apply + SiLU + bf16 store.
 constexpr int kGNItems = 8;
 __global__ void __launch_bounds__(kGNThreads) gn_apply_kernel(GNArgs a) {
   pdl_trigger();
@@ -159,42 +200,14 @@ __global__ void __launch_bounds__(kGNThreads) gn_apply_kernel(GNArgs a) {
                        : *reinterpret_cast<const float4*>(a.x2 + row * a.C2 + (c - a.C1));
     }
   }
-  {
-    const int lane = threadIdx.x & 31;
-    for (int g = threadIdx.x >> 5; g < a.G; g += kGNThreads >> 5) {
-      const double* src = a.partial + ((long long)b * a.S * a.G + g) * 2;
-      const long long st = (long long)a.G * 2;
-      double p0 = 0.0, q0 = 0.0, p1 = 0.0, q1 = 0.0;
-      if (lane < a.S) {
-        p0 = src[lane * st];
-        q0 = src[lane * st + 1];
-      }
-      if (lane + 32 < a.S) {
-        p1 = src[(lane + 32) * st];
-        q1 = src[(lane + 32) * st + 1];
-      }
-      double dsu = p0 + p1, dsq = q0 + q1;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        dsu += __shfl_down_sync(0xffffffffu, dsu, o);
-        dsq += __shfl_down_sync(0xffffffffu, dsq, o);
-      }
-      if (lane == 0) {
-        const double inv_n = 1.0 / ((double)a.HW * a.cpg);
-        const double mean = dsu * inv_n;
-        double var = dsq * inv_n - mean * mean;
-        if (var < 0.0) var = 0.0;
-        s_mean[g] = (float)mean;
-        s_rstd[g] = rsqrtf((float)var + a.eps);
-      }
-    }
-  }
-  __syncthreads();
+  // mean / rstd were finalised by the statistics kernel: one round of independent loads (in flight together with
+  // the data loads above) builds the per-channel affine table
   for (int c = threadIdx.x; c < a.C; c += kGNThreads) {
     const int g = c / a.cpg;
-    const float A = s_rstd[g] * __ldg(a.gamma + c);
+    const float2 mr = *reinterpret_cast<const float2*>(a.stats + ((long long)b * a.G + g) * 2);
+    const float A = mr.y * __ldg(a.gamma + c);
     s_A[c] = A;
-    s_B[c] = __ldg(a.beta + c) - s_mean[g] * A;
+    s_B[c] = __ldg(a.beta + c) - mr.x * A;
   }
   __syncthreads();
 #pragma unroll
