@@ -44,9 +44,9 @@ template <int D>
 struct AttnCfg {
   static constexpr int DP = (D + 15) / 16 * 16;
   static constexpr int LDS = DP + 8;  // padded row (elements): conflict-free ldmatrix
-  // K/V ring depth: one 64-key tile takes ~0.2 us of MMA + softmax but ~1 us to arrive from L2, so a 2-deep ring
-  // stalls every iteration; 4 stages keep 3 tiles in flight (shared memory permitting for the wide heads)
-  static constexpr int NS = D <= 64 ? 4 : (D <= 96 ? 3 : 2);
+  // K/V ring depth.  Deeper rings (3-4 stages) were measured: no gain at B=2, -8 % at B=16 (the loop is issue-bound,
+  // not load-latency-bound, and the extra shared memory costs occupancy) -> double buffering.
+  static constexpr int NS = 2;
   static constexpr int kSmemBytes = (BQ + 2 * NS * BKV) * LDS * 2;
 };
 
@@ -65,7 +65,6 @@ __device__ __forceinline__ void load_tile(__nv_bfloat16* dst, const __nv_bfloat1
 
 template <int D>
 __global__ void __launch_bounds__(kAttnThreads) attention_kernel(AttnArgs a) {
-  pdl_trigger();
   pdl_wait();
   using C = AttnCfg<D>;
   constexpr int DP = C::DP;
@@ -240,6 +239,7 @@ __global__ void __launch_bounds__(kAttnThreads) attention_kernel(AttnArgs a) {
     __syncthreads();  // all warps done with this buffer before the next prefetch overwrites it
   }
 
+  pdl_trigger();   // key/value loop done: the normalise + store tail may overlap the next launch
   // ---- normalise and store (bf16 pairs)
   const int r0 = q0 + warp * 16 + g;
   const float inv0 = l_run[0] > 0.f ? 1.f / l_run[0] : 0.f;

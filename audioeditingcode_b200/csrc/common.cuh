@@ -40,9 +40,11 @@ inline int launched(const char* what) {
 
 inline cudaStream_t as_stream(ae_stream s) { return reinterpret_cast<cudaStream_t>(s); }
 
-// Programmatic dependent launch (PDL): every kernel of the library starts with pdl_trigger() (lets the next kernel
-// in the stream be scheduled early so its prologue overlaps this kernel) and calls pdl_wait() before its first
-// global-memory access (blocks until the previous kernel has completed and its writes are visible).
+// Programmatic dependent launch (PDL): every kernel calls pdl_wait() before its first dependent global-memory access
+// (blocks until the previous kernel has completed and its writes are visible) and pdl_trigger() once its own main
+// work is issued (loads done / last MMA issued), which lets the NEXT kernel of the stream be scheduled so that its
+// launch latency and prologue overlap this kernel's tail.  Triggering at the very top instead lets a whole chain of
+// kernels become resident and wait on each other, which measured slower (profiles/r01_bench_v8_pdl1.json).
 extern int g_use_pdl;
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }

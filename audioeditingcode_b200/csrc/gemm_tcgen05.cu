@@ -319,7 +319,6 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   using L = SmemLayout<BN, STAGES>;
   constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
   extern __shared__ uint8_t smem_raw[];
-  pdl_trigger();
   // 1024-byte alignment is required by the 128B swizzle atoms (TMA and UMMA both derive the XOR from address bits)
   const uint32_t raw_addr = ptx::smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
@@ -430,6 +429,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
       }
       ptx::umma_commit(tmem_full_bar);  // accumulator complete
+      // every MMA of this CTA is issued: let the next kernel of the stream be scheduled now, so that its launch
+      // latency and prologue overlap this CTA's epilogue (it still waits for this grid's completion before reading)
+      pdl_trigger();
     }
   } else {
     // ===================== epilogue (warps 2..5 -> TMEM lane quadrants 2,3,0,1) =====================
@@ -544,8 +546,8 @@ struct ReduceArgs {
 };
 
 __global__ void __launch_bounds__(256) splitk_reduce_kernel(ReduceArgs a) {
-  pdl_trigger();
   pdl_wait();
+  bool triggered = false;
   const int n4 = a.N >> 2;
   const long long total = (long long)a.M * n4;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -573,6 +575,10 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(ReduceArgs a) {
       acc.y += t.y;
       acc.z += t.z;
       acc.w += t.w;
+    }
+    if (!triggered) {   // partial sums of the first item are in: the tail of this kernel may overlap the next launch
+      pdl_trigger();
+      triggered = true;
     }
     float v[4] = {acc.x * a.alpha, acc.y * a.alpha, acc.z * a.alpha, acc.w * a.alpha};
     if (a.bias) {

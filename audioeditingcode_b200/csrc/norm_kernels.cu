@@ -44,7 +44,6 @@ __device__ __forceinline__ float load_cat(const GNArgs& a, long long row, int c)
 constexpr int kGNMaxQuadsPerThread = 4;
 constexpr int kGNUnroll = 4;
 __global__ void __launch_bounds__(512) gn_stats_kernel(GNArgs a) {
-  pdl_trigger();
   pdl_wait();
   extern __shared__ float sm[];  // [TY][2*C] per-channel sum / sumsq per ty
   const int s = blockIdx.x, b = blockIdx.y;
@@ -90,6 +89,7 @@ __global__ void __launch_bounds__(512) gn_stats_kernel(GNArgs a) {
       }
     }
   }
+  pdl_trigger();   // all loads of this CTA are done: overlap the next launch with the reduction tail
   float* mysum = sm + (size_t)ty * 2 * a.C;
 #pragma unroll
   for (int k = 0; k < kGNMaxQuadsPerThread; ++k) {
@@ -177,7 +177,6 @@ __global__ void __launch_bounds__(512) gn_stats_kernel(GNArgs a) {
 // y = x*A[c] + B[c] in shared memory, (4) apply + SiLU + bf16 store.
 constexpr int kGNItems = 8;
 __global__ void __launch_bounds__(kGNThreads) gn_apply_kernel(GNArgs a) {
-  pdl_trigger();
   pdl_wait();
   extern __shared__ float sm[];  // mean[G], rstd[G], A[C], B[C]
   float* s_mean = sm;
@@ -200,6 +199,7 @@ __global__ void __launch_bounds__(kGNThreads) gn_apply_kernel(GNArgs a) {
                        : *reinterpret_cast<const float4*>(a.x2 + row * a.C2 + (c - a.C1));
     }
   }
+  pdl_trigger();   // data loads are in flight
   // mean / rstd were finalised by the statistics kernel: one round of independent loads (in flight together with
   // the data loads above) builds the per-channel affine table
   for (int c = threadIdx.x; c < a.C; c += kGNThreads) {
@@ -443,7 +443,6 @@ template <int NV>
 __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, long long rows, int C, float eps,
                                                         const float* __restrict__ gamma, const float* __restrict__ beta,
                                                         __nv_bfloat16* __restrict__ out) {
-  pdl_trigger();
   pdl_wait();
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -459,6 +458,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) su += __shfl_xor_sync(0xffffffffu, su, o);
+  pdl_trigger();   // the row is in registers: the rest of this kernel may overlap the next launch
   const float mean = su / (float)C;
   float sq = 0.f;
 #pragma unroll
