@@ -139,32 +139,38 @@ __global__ void __launch_bounds__(512) gn_stats_kernel(GNArgs a) {
   if (s_last) {
     __threadfence();
     const int lane = tid & 31, wid = tid >> 5, nw = nthr >> 5;
-    for (int g = wid; g < a.G; g += nw) {
-      const double* src = a.partial + ((long long)b * a.S * a.G + g) * 2;
+    // two groups per warp and pass: the (up to) 8 partial loads of a pass are issued together
+    for (int g0 = wid; g0 < a.G; g0 += 2 * nw) {
       const long long st = (long long)a.G * 2;
-      double p0 = 0.0, q0 = 0.0, p1 = 0.0, q1 = 0.0;
-      if (lane < a.S) {
-        p0 = __ldcg(src + lane * st);
-        q0 = __ldcg(src + lane * st + 1);
-      }
-      if (lane + 32 < a.S) {
-        p1 = __ldcg(src + (lane + 32) * st);
-        q1 = __ldcg(src + (lane + 32) * st + 1);
-      }
-      double dsu = p0 + p1, dsq = q0 + q1;
+      double pv[2][4];
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        dsu += __shfl_down_sync(0xffffffffu, dsu, o);
-        dsq += __shfl_down_sync(0xffffffffu, dsq, o);
+      for (int u = 0; u < 2; ++u) {
+        const int g = g0 + u * nw;
+        const double* src = a.partial + ((long long)b * a.S * a.G + g) * 2;
+        const bool ok = g < a.G;
+        pv[u][0] = (ok && lane < a.S) ? __ldcg(src + lane * st) : 0.0;
+        pv[u][1] = (ok && lane < a.S) ? __ldcg(src + lane * st + 1) : 0.0;
+        pv[u][2] = (ok && lane + 32 < a.S) ? __ldcg(src + (lane + 32) * st) : 0.0;
+        pv[u][3] = (ok && lane + 32 < a.S) ? __ldcg(src + (lane + 32) * st + 1) : 0.0;
       }
-      if (lane == 0) {
-        const double inv_n = 1.0 / ((double)a.HW * a.cpg);
-        const double mean = dsu * inv_n;
-        double var = dsq * inv_n - mean * mean;
-        if (var < 0.0) var = 0.0;
-        float* dst = a.stats + ((long long)b * a.G + g) * 2;
-        dst[0] = (float)mean;
-        dst[1] = rsqrtf((float)var + a.eps);
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int g = g0 + u * nw;
+        double dsu = pv[u][0] + pv[u][2], dsq = pv[u][1] + pv[u][3];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          dsu += __shfl_down_sync(0xffffffffu, dsu, o);
+          dsq += __shfl_down_sync(0xffffffffu, dsq, o);
+        }
+        if (lane == 0 && g < a.G) {
+          const double inv_n = 1.0 / ((double)a.HW * a.cpg);
+          const double mean = dsu * inv_n;
+          double var = dsq * inv_n - mean * mean;
+          if (var < 0.0) var = 0.0;
+          float* dst = a.stats + ((long long)b * a.G + g) * 2;
+          dst[0] = (float)mean;
+          dst[1] = rsqrtf((float)var + a.eps);
+        }
       }
     }
     if (tid == 0) a.counters[b] = 0u;   // re-arm for the next launch (stream-ordered after this kernel)
@@ -176,7 +182,18 @@ __global__ void __launch_bounds__(512) gn_stats_kernel(GNArgs a) {
 // gamma / beta — independent of (1), so one memory round trip covers both —, (3) build the per-channel affine table
 // y = x*A[c] + B[c] in shared memory, (4) apply + SiLU + bf16 store.
 constexpr int kGNItems = 8;
+constexpr int kGNTab = 10;   // channel-table entries per thread: C <= 256 * kGNTab (checked on the host)
 __global__ void __launch_bounds__(kGNThreads) gn_apply_kernel(GNArgs a) {
+  // gamma / beta are weights (never written by the previous kernel): fetched before the dependency wait
+  float gpre[kGNTab], bpre[kGNTab];
+#pragma unroll
+  for (int k = 0; k < kGNTab; ++k) {
+    const int c = threadIdx.x + k * kGNThreads;
+    if (c < a.C) {
+      gpre[k] = __ldg(a.gamma + c);
+      bpre[k] = __ldg(a.beta + c);
+    }
+  }
   pdl_wait();
   extern __shared__ float sm[];  // mean[G], rstd[G], A[C], B[C]
   float* s_mean = sm;
@@ -200,14 +217,24 @@ __global__ void __launch_bounds__(kGNThreads) gn_apply_kernel(GNArgs a) {
     }
   }
   pdl_trigger();   // data loads are in flight
-  // mean / rstd were finalised by the statistics kernel: one round of independent loads (in flight together with
-  // the data loads above) builds the per-channel affine table
-  for (int c = threadIdx.x; c < a.C; c += kGNThreads) {
-    const int g = c / a.cpg;
-    const float2 mr = *reinterpret_cast<const float2*>(a.stats + ((long long)b * a.G + g) * 2);
-    const float A = mr.y * __ldg(a.gamma + c);
-    s_A[c] = A;
-    s_B[c] = __ldg(a.beta + c) - mr.x * A;
+  // mean / rstd were finalised by the statistics kernel.  All table loads are issued before any is consumed (a
+  // rolled loop would expose one L2 round trip per 256 channels); they are in flight together with the data loads.
+  {
+    float2 mr[kGNTab];
+#pragma unroll
+    for (int k = 0; k < kGNTab; ++k) {
+      const int c = threadIdx.x + k * kGNThreads;
+      if (c < a.C) mr[k] = *reinterpret_cast<const float2*>(a.stats + ((long long)b * a.G + c / a.cpg) * 2);
+    }
+#pragma unroll
+    for (int k = 0; k < kGNTab; ++k) {
+      const int c = threadIdx.x + k * kGNThreads;
+      if (c < a.C) {
+        const float A = mr[k].y * gpre[k];
+        s_A[c] = A;
+        s_B[c] = bpre[k] - mr[k].x * A;
+      }
+    }
   }
   __syncthreads();
 #pragma unroll
@@ -443,10 +470,21 @@ template <int NV>
 __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, long long rows, int C, float eps,
                                                         const float* __restrict__ gamma, const float* __restrict__ beta,
                                                         __nv_bfloat16* __restrict__ out) {
-  pdl_wait();
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= rows) return;
   const int lane = threadIdx.x & 31;
+  // the affine parameters are weights (never written by the previous kernel): fetch them before the dependency wait
+  // and before the row, so their latency is not a second round trip after the reductions
+  float4 gm[NV], bt[NV];
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const int c = lane * 4 + k * 128;
+    if (c < C) {
+      gm[k] = __ldg(reinterpret_cast<const float4*>(gamma + c));
+      bt[k] = __ldg(reinterpret_cast<const float4*>(beta + c));
+    }
+  }
+  pdl_wait();
+  if (row >= rows) return;
   const float* xr = x + row * C;
   float4 v[NV];
   float su = 0.f;
@@ -477,8 +515,8 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
   for (int k = 0; k < NV; ++k) {
     const int c = lane * 4 + k * 128;
     if (c < C) {
-      const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c));
-      const float4 bb = __ldg(reinterpret_cast<const float4*>(beta + c));
+      const float4 g = gm[k];
+      const float4 bb = bt[k];
       __nv_bfloat162 h0 = __floats2bfloat162_rn((v[k].x - mean) * rstd * g.x + bb.x, (v[k].y - mean) * rstd * g.y + bb.y);
       __nv_bfloat162 h1 = __floats2bfloat162_rn((v[k].z - mean) * rstd * g.z + bb.z, (v[k].w - mean) * rstd * g.w + bb.w);
       uint2 pk;
@@ -522,6 +560,7 @@ extern "C" int ae_groupnorm(const float* x1, int C1, const float* x2, int C2, in
   AE_CHECK_ARG(C1 % 4 == 0 && C2 % 4 == 0, "ae_groupnorm: channel counts must be multiples of 4 (C1=%d C2=%d)", C1, C2);
   AE_CHECK_ARG(gamma && beta && out_bf16 && workspace, "ae_groupnorm: null pointer");
   AE_CHECK_ARG(HW * (int64_t)(C / 4) < 2147483647LL, "ae_groupnorm: sample too large (HW*C/4 >= 2^31)");
+  AE_CHECK_ARG(C <= 2560, "ae_groupnorm: C=%d > 2560 channels", C);
   GNArgs a;
   a.x1 = x1;
   a.x2 = x2;

@@ -25,7 +25,7 @@ def main():
     dev = torch.device("cuda", lr)
     from audioeditingcode_b200 import models, unet_config as C, parallel as P, pc_drift as PC
     from audioeditingcode_b200.ddm_inversion import inversion_utils as IU
-    cfg = C.preset("tiny-audioldm2")
+    cfg = C.preset("audioldm2")      # full AudioLDM2 architecture (347 M synthetic parameters)
     N = 20
     m = models.load_model("cvssp/audioldm2", dev, N, config=cfg)
     g = torch.Generator().manual_seed(1)
