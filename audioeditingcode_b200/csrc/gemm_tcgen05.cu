@@ -70,17 +70,24 @@ struct SmemLayout {
   static constexpr int kBTileBytes = BN * BK * 2;
   static constexpr int kStageBytes = kATileBytes + kBTileBytes;
   static constexpr int kBarBytes = 128;
-  static constexpr int kTotal = STAGES * kStageBytes + kBarBytes + 1024;  // +1024 manual alignment slack
+  static constexpr int kEpiBytes = 2 * BN * 4;  // bias / row-bias values of the tile (row-per-thread epilogue)
+  static constexpr int kTotal = STAGES * kStageBytes + kBarBytes + kEpiBytes + 1024;  // +1024 manual alignment slack
 };
 
 __device__ __forceinline__ float gelu_erf_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 
 // Fused epilogue of one 32-column chunk of one output row: bias, time-embedding row bias, residual, activation,
 // fp32 / bf16 stores.  `acc` already holds alpha * accumulator.
-__device__ __forceinline__ void epilogue_chunk(const GemmDev& p, float (&acc)[32], long long m, int nbase, int z) {
+// `sb` / `srb` (optional): the tile's bias / row-bias values staged in shared memory by the caller (indexed from the
+// chunk's first column) — fetched once per CTA before the accumulator is ready instead of once per chunk after it.
+__device__ __forceinline__ void epilogue_chunk(const GemmDev& p, float (&acc)[32], long long m, int nbase, int z,
+                                               const float* sb = nullptr, const float* srb = nullptr) {
   if (m >= p.M || nbase >= p.N) return;
   const int nvalid = min(32, p.N - nbase);
-  if (p.bias) {
+  if (p.bias && sb) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) acc[j] += sb[j];     // columns >= N hold 0
+  } else if (p.bias) {
     if (nvalid == 32) {
       const float4* b4 = reinterpret_cast<const float4*>(p.bias + nbase);
 #pragma unroll
@@ -97,7 +104,10 @@ __device__ __forceinline__ void epilogue_chunk(const GemmDev& p, float (&acc)[32
         if (j < nvalid) acc[j] += __ldg(p.bias + nbase + j);
     }
   }
-  if (p.rowbias) {
+  if (p.rowbias && srb) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) acc[j] += srb[j];
+  } else if (p.rowbias) {
     const float* rb = p.rowbias + (m / p.rows_per_group) * p.ld_rowbias;
 #pragma unroll
     for (int j = 0; j < 32; ++j)
@@ -328,6 +338,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full_bar = empty_bar + STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  float* s_bias = reinterpret_cast<float*>(smem + STAGES * L::kStageBytes + L::kBarBytes);
+  float* s_rowb = s_bias + BN;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -452,6 +464,20 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
       for (int l = 0; l < BN * 4 / 128; ++l) asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + l * 128));
     }
+    // bias / row bias of the tile -> shared memory, one coalesced fetch per CTA while the main loop runs (the row bias
+    // only when the whole tile lies in one row group, which is the rule for the time-embedding bias of the ResBlocks)
+    const int etid = (int)threadIdx.x - 64;
+    const bool stage_b = p.bias != nullptr && p.csplit <= 1;
+    const long long mlast = min((long long)m0 + BM - 1, (long long)p.M - 1);
+    const bool stage_rb = p.rowbias != nullptr && p.csplit <= 1 && (m0 / p.rows_per_group) == (mlast / p.rows_per_group);
+    if (stage_b || stage_rb) {
+      for (int i = etid; i < BN; i += 128) {
+        const bool ok = n0 + i < p.N;
+        if (stage_b) s_bias[i] = ok ? __ldg(p.bias + n0 + i) : 0.f;
+        if (stage_rb) s_rowb[i] = ok ? __ldg(p.rowbias + (m0 / p.rows_per_group) * p.ld_rowbias + n0 + i) : 0.f;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+    }
     ptx::mbar_wait(tmem_full_bar, 0);
     ptx::tcgen05_fence_after();
     // cluster split-K: raw fp32 partial tile into this CTA's shared memory (the stage ring is idle once the
@@ -472,7 +498,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         float acc[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) acc[j] = __uint_as_float(v[j]) * p.alpha;
-        epilogue_chunk(p, acc, m, n0 + c * 32, zo);
+        epilogue_chunk(p, acc, m, n0 + c * 32, zo, stage_b ? s_bias + c * 32 : nullptr, stage_rb ? s_rowb + c * 32 : nullptr);
       }
     }
     ptx::tcgen05_fence_before();
@@ -543,6 +569,7 @@ struct ReduceArgs {
   long long ld_out_bf16;
   int act;
   float alpha;
+  int res_vec;   // bit 0 / 1 / 2: residual / bias / row-bias rows are 16-byte aligned (pointer and pitch)
 };
 
 __global__ void __launch_bounds__(256) splitk_reduce_kernel(ReduceArgs a) {
@@ -554,6 +581,21 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(ReduceArgs a) {
     const long long m = i / n4;
     const int n = (int)(i - m * n4) << 2;
     const float* w = a.ws + m * a.N + n;
+    // epilogue operands first: independent of the partial sums, so one memory round trip covers everything
+    float4 bia = make_float4(0.f, 0.f, 0.f, 0.f), rbi = bia, rsd = bia;
+    if (a.bias) {
+      const float* q = a.bias + n;
+      bia = (a.res_vec & 2) ? __ldg(reinterpret_cast<const float4*>(q)) : make_float4(__ldg(q), __ldg(q + 1), __ldg(q + 2), __ldg(q + 3));
+    }
+    if (a.rowbias) {
+      const float* q = a.rowbias + (m / a.rows_per_group) * a.ld_rowbias + n;
+      rbi = (a.res_vec & 4) ? __ldg(reinterpret_cast<const float4*>(q)) : make_float4(__ldg(q), __ldg(q + 1), __ldg(q + 2), __ldg(q + 3));
+    }
+    if (a.residual) {
+      const float* r = a.residual + m * a.ld_res + n;
+      if (a.res_vec & 1) rsd = *reinterpret_cast<const float4*>(r);
+      else rsd = make_float4(r[0], r[1], r[2], r[3]);
+    }
     float4 acc = *reinterpret_cast<const float4*>(w);
     // partials are fetched four at a time (independent loads in flight), summed in the fixed order s = 1..S-1
     int s = 1;
@@ -582,18 +624,13 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(ReduceArgs a) {
     }
     float v[4] = {acc.x * a.alpha, acc.y * a.alpha, acc.z * a.alpha, acc.w * a.alpha};
     if (a.bias) {
-#pragma unroll
-      for (int k = 0; k < 4; ++k) v[k] += __ldg(a.bias + n + k);
+      v[0] += bia.x; v[1] += bia.y; v[2] += bia.z; v[3] += bia.w;
     }
     if (a.rowbias) {
-      const float* rb = a.rowbias + (m / a.rows_per_group) * a.ld_rowbias + n;
-#pragma unroll
-      for (int k = 0; k < 4; ++k) v[k] += __ldg(rb + k);
+      v[0] += rbi.x; v[1] += rbi.y; v[2] += rbi.z; v[3] += rbi.w;
     }
     if (a.residual) {
-      const float* r = a.residual + m * a.ld_res + n;
-#pragma unroll
-      for (int k = 0; k < 4; ++k) v[k] += r[k];
+      v[0] += rsd.x; v[1] += rsd.y; v[2] += rsd.z; v[3] += rsd.w;
     }
     if (a.act == 1) {
 #pragma unroll
@@ -969,6 +1006,9 @@ extern "C" int ae_gemm(const ae_gemm_args* a, ae_stream stream) {
   r.ld_out_bf16 = p.ld_out_bf16;
   r.act = p.act;
   r.alpha = p.alpha;
+  r.res_vec = ((p.residual && (reinterpret_cast<uintptr_t>(p.residual) & 15) == 0 && p.ld_res % 4 == 0) ? 1 : 0) |
+              ((p.bias && (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0) ? 2 : 0) |
+              ((p.rowbias && (reinterpret_cast<uintptr_t>(p.rowbias) & 15) == 0 && p.ld_rowbias % 4 == 0) ? 4 : 0);
   long long blocks = ceil_div64(r.MN / 4, 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
   cudaError_t e = launch_kernel_early(splitk_reduce_kernel, dim3((unsigned)blocks), dim3(256), (size_t)0, st, r);
