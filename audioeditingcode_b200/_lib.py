@@ -36,6 +36,8 @@ _SIGS = {
     "ae_launch_count": (i64, []),
     "ae_device_ok": (i32, []),
     "ae_set_pdl": (None, [i32]),
+    "ae_set_launch_priority": (None, [i32]),
+    "ae_greatest_priority": (i32, []),
     "ae_set_splitk_ctas": (None, [i32]),
     "ae_set_fast_epilogue": (None, [i32]),
     "ae_set_tile_model": (None, [i32]),

@@ -46,6 +46,10 @@ inline cudaStream_t as_stream(ae_stream s) { return reinterpret_cast<cudaStream_
 // launch latency and prologue overlap this kernel's tail.  Triggering at the very top instead lets a whole chain of
 // kernels become resident and wait on each other, which measured slower (profiles/r01_bench_v8_pdl1.json).
 extern int g_use_pdl;
+// Launch priority attached to every kernel launched (and therefore to every kernel NODE captured) while it is set:
+// the reverse-process graph is captured with the device's highest priority so that its sub-wave kernels take the next
+// free SM slots ahead of the pending CTAs of a forward-process chunk running concurrently on another stream.
+extern int g_launch_priority;       // 0 = leave the stream's priority
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
@@ -59,11 +63,20 @@ inline cudaError_t launch_kernel_mode(bool early_ok, void (*kernel)(KArgs...), d
   cfg.blockDim = block;
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (g_use_pdl == 1 || (g_use_pdl == 2 && early_ok)) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  if (g_launch_priority != 0) {
+    attr[na].id = cudaLaunchAttributePriority;
+    attr[na].val.priority = g_launch_priority;
+    ++na;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = (g_use_pdl == 1 || (g_use_pdl == 2 && early_ok)) ? 1 : 0;
+  cfg.numAttrs = na;
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 

@@ -28,6 +28,7 @@
 
 namespace aedit {
 int g_use_pdl = 0;
+int g_launch_priority = 0;
 namespace {
 
 constexpr int BM = 128;
@@ -757,6 +758,15 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmDev& p, int
 using namespace aedit;
 
 extern "C" void ae_set_pdl(int mode) { g_use_pdl = (mode == 1 || mode == 2) ? mode : 0; }
+extern "C" void ae_set_launch_priority(int prio) { g_launch_priority = prio; }
+extern "C" int ae_greatest_priority(void) {
+  int least = 0, greatest = 0;
+  if (cudaDeviceGetStreamPriorityRange(&least, &greatest) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return greatest;   // numerically lowest value = highest priority (0 if the device has a single level)
+}
 
 static int g_splitk_ctas = 148;
 static int g_fast_epi = 1;

@@ -32,14 +32,89 @@ from ..models import PipelineWrapper, _ptr, _stream
 
 DEFAULT_FORWARD_BATCH = int(os.environ.get("AEDIT_FORWARD_BATCH", "50"))
 USE_CUDA_GRAPHS = os.environ.get("AEDIT_CUDA_GRAPH", "1") != "0"
+# Forward / reverse overlap (see _PendingForward): 1 = on (default), 0 = both processes on the caller's stream.
+OVERLAP = os.environ.get("AEDIT_OVERLAP", "1") != "0"
 
 
-def _unet_eval(model, x_in, t_in, text, slot, cl, slot_key=None):
-    """One batched U-Net evaluation, through a cached CUDA graph unless AEDIT_CUDA_GRAPH=0."""
+class _PendingForward:
+    """Book-keeping of a forward process whose timestep chunks were enqueued on the model's forward lane.
+
+    The forward process is throughput-bound (B = 2 x forward_batch rows per launch fill the machine) and its
+    timesteps are independent; the reverse process is a strictly sequential chain of sub-wave launches
+    that leaves most SMs idle.  So the two run CONCURRENTLY: the forward chunks are enqueued on a side stream in the
+    order the reverse process will consume them, each followed by an event; `inversion_reverse_process` — called right
+    after, exactly like reference main_run.py:128-158 — runs on a second, high-priority side stream and waits only
+    for the events of the chunks whose rows (`zs[idx]`, `xts[tstart]`) it is about to read.  The caller's stream waits
+    for the whole forward lane when `inversion_forward_process` returns and for the reverse lane when
+    `inversion_reverse_process` returns, so every other consumer of the returned tensors sees ordinary stream
+    semantics.  The fast path is taken only if the tensors handed to the reverse process are the ones the forward
+    process returned, unmodified (same storage, same torch version counters) — anything else falls back to plain
+    stream order.  Results are bit-identical to the non-overlapped execution (same kernels, same batches; tested)."""
+    __slots__ = ("zs_ptr", "zs_ver", "xts_ptr", "xts_ver", "chunks", "eta_key", "N", "done")
+
+    def __init__(self):
+        self.chunks = []          # (idx_lo, idx_hi, event): rows zs[lo..hi], xts[lo..hi] are final once event fired
+
+    def matches(self, zs, xT, eta_key) -> bool:
+        try:
+            return (zs.data_ptr() == self.zs_ptr and zs._version == self.zs_ver and xT.data_ptr() == self.xts_ptr
+                    and xT._version == self.xts_ver and zs.shape[0] <= self.N and xT.shape[0] == self.N + 1
+                    and eta_key == self.eta_key)
+        except RuntimeError:      # inference tensors carry no version counter: cannot prove they are unmodified
+            return False
+
+    def event_for(self, idx):
+        for lo, hi, ev in self.chunks:
+            if lo <= idx <= hi:
+                return ev
+        return None
+
+
+def _lane(model, name: str):
+    """Side streams of a model: 'fwd' (default priority) and 'rev' (highest priority)."""
+    lanes = model.__dict__.setdefault("_lanes", {})
+    st = lanes.get(name)
+    if st is None:
+        st = torch.cuda.Stream(device=model.device, priority=-1 if name == "rev" else 0)
+        lanes[name] = st
+    return st
+
+
+def _chunk_plan(N: int, tb: int, hint: Optional[int]) -> List[Tuple[int, int]]:
+    """(pos0, count) of the forward-process chunks in launch order.  Without a hint: loop order, boundaries at
+    multiples of `tb`.  With hint = tstart of the reverse process that follows: the rows idx (= N - pos - 1) are cut
+    so that row `hint` is the TOP of a chunk — the reverse process starts from xts[hint] and then consumes zs[hint-1],
+    zs[hint-2], ..., so one chunk is all it has to wait for — and the chunks are launched downwards from there, the
+    rows above `hint` last.  A remainder shorter than tb/4 is merged into its neighbour.  The plan depends only on
+    (N, tb, hint), never on whether the lanes overlap, so both modes run identical batches (bit-identical results)."""
+    if tb <= 1 or hint is None or not (0 <= hint <= N):
+        return [(p, min(tb, N - p)) for p in range(0, N, tb)]
+    top = min(hint, N - 1)
+    down, up = [], []                       # (lo, hi) in idx space
+    hi = top
+    while hi >= 0:
+        lo = max(0, hi - tb + 1)
+        if lo > 0 and lo < max(1, tb // 4):
+            lo = 0
+        down.append((lo, hi))
+        hi = lo - 1
+    lo = top + 1
+    while lo <= N - 1:
+        hi = min(N - 1, lo + tb - 1)
+        if N - 1 - hi < max(1, tb // 4):
+            hi = N - 1
+        up.append((lo, hi))
+        lo = hi + 1
+    return [(N - 1 - hi, hi - lo + 1) for lo, hi in down + up]
+
+
+def _unet_eval(model, x_in, t_in, text, slot, cl, slot_key=None, lane=0):
+    """One batched U-Net evaluation, through a cached CUDA graph unless AEDIT_CUDA_GRAPH=0.  lane 1 = the reverse
+    lane's graph: own workspaces, kernel nodes captured with the highest launch priority (unet.GraphedForward)."""
     eng = model.engine
     slot_arg = slot if text is not None else None
     if USE_CUDA_GRAPHS and x_in.is_cuda:
-        g = eng.graphed(x_in.shape[0], x_in.shape[2], x_in.shape[3], text, slot_arg, cl, slot_key=slot_key)
+        g = eng.graphed(x_in.shape[0], x_in.shape[2], x_in.shape[3], text, slot_arg, cl, slot_key=slot_key, lane=lane)
         model.graph_replays = getattr(model, "graph_replays", 0) + 1
         model.graph_kernels = getattr(model, "graph_kernels", 0) + g.kernels
         return g(x_in, t_in, cl)
@@ -135,6 +210,13 @@ def _loop_text(model: PipelineWrapper, neg_prompts, prompts):
     return hit[0], hit[1]
 
 
+def _loop_text_cached(model: PipelineWrapper, neg_prompts, prompts) -> bool:
+    """True if _loop_text would be a cache hit (no text-encoder / K|V-projection launches)."""
+    enc = model.encode_text
+    key = (tuple(neg_prompts), None if prompts is None else tuple(prompts), id(getattr(enc, "__self__", enc)))
+    return key in model.__dict__.get("_loop_text_cache", {})
+
+
 def _t_to_idx(timesteps):
     if timesteps[0].dtype == torch.int64:
         return {int(v): k for k, v in enumerate(timesteps)}
@@ -156,9 +238,12 @@ def inversion_forward_process(model: PipelineWrapper,
                               first_order: bool = False,
                               forward_batch: Optional[int] = None,
                               noise: Optional[torch.Tensor] = None,
-                              group=None) -> Tuple:
+                              group=None,
+                              reverse_hint: Optional[int] = None) -> Tuple:
     """Extensions over the reference signature (all default to the reference behaviour): `forward_batch` timesteps
-    per U-Net launch, explicit `noise`, and `group` — a torch.distributed process group over which the
+    per U-Net launch, explicit `noise`, `reverse_hint` — the `tstart` the following reverse process will
+    use (default N // 2, the ratio of main_run.py's own defaults 200 / 100); it only orders the chunk launches so the
+    reverse process can start early (see _PendingForward), never changes a result — and `group` — a torch.distributed process group over which the
     timestep chunks of ONE clip are sharded: chunk k runs on group rank k % world, `xts` is
     broadcast from rank 0 once, and `zs` / `xts` are merged by one sum-all-reduce each at the end (every row is owned
     by exactly one rank, the others contribute zeros, so the merge is exact and every rank returns the full tensors)."""
@@ -179,10 +264,12 @@ def inversion_forward_process(model: PipelineWrapper,
     N = num_inference_steps
     if type(etas) in [int, float]:
         etas = [etas] * sched.num_inference_steps
-    xts = model.sample_xts_from_x0(x0, num_inference_steps=N, noise=noise)
-    zs = torch.zeros(size=model.get_noise_shape(x0, N), device=model.device)
+    with torch.inference_mode(False):      # normal tensors: their version counters guard the overlap fast path
+        xts = model.sample_xts_from_x0(x0, num_inference_steps=N, noise=noise)
+        zs = torch.zeros(size=model.get_noise_shape(x0, N), device=model.device)
     extra_info = [None] * len(zs)
     model.setup_extra_inputs(x0, init_timestep=timesteps[0], audio_end_in_s=duration)
+    model.__dict__.pop("_pending_forward", None)
 
     tb = forward_batch if forward_batch is not None else DEFAULT_FORWARD_BATCH
     tb = max(1, min(int(tb), N))
@@ -199,38 +286,72 @@ def inversion_forward_process(model: PipelineWrapper,
     xt_src = xts.clone() if tb > 1 else xts      # batched: every U-Net input is the directly sampled x_t (F8)
     ts_cpu = sched.timesteps_cpu
     model.sched_table.set_etas(etas)
-    it = range(0, N, tb)
-    if prog_bar:
-        it = tqdm(it)
-    for chunk_no, pos0 in enumerate(it):
-        count = min(tb, N - pos0)
+    overlap = OVERLAP and USE_CUDA_GRAPHS and x0.is_cuda and tb > 1 and g_ws == 1 and not prog_bar
+    plan = _chunk_plan(N, tb, (N // 2 if reverse_hint is None else int(reverse_hint)) if g_ws == 1 else None)
+    it = tqdm(plan) if prog_bar else plan
+    # everything a chunk needs from the host is staged BEFORE the first launch: a pageable host->device copy on a busy
+    # stream blocks the host until the stream drains, which would serialise the launches of the two lanes
+    slots = {}
+    for count in {c for _, c in plan}:
+        if P > 0:
+            sl = torch.cat([torch.zeros(count, dtype=torch.int32), (1 + torch.arange(P, dtype=torch.int32)).repeat(count)])
+        else:
+            sl = torch.zeros(count, dtype=torch.int32)
+        sl = sl.to(model.device)
+        slots[count] = (sl, None if cl is None else cl.index_select(0, sl.long()))
+    cur = torch.cuda.current_stream() if x0.is_cuda else None
+    pend = None
+    if overlap:
+        pend = _PendingForward()
+        lane = _lane(model, "fwd")
+        lane.wait_stream(cur)
+    for chunk_no, (pos0, count) in enumerate(it):
         if g_ws > 1:
             if chunk_no % g_ws != g_rank:
                 continue
             owned.extend(range(N - pos0 - count, N - pos0))
-        # loop position pos <-> idx = N - pos - 1 (inversion_utils.py:75); U-Net input xts[idx+1] = xts[N - pos]
-        src_rows = torch.arange(N - pos0, N - pos0 - count, -1, device=model.device)
-        xt_b = xt_src.index_select(0, src_rows)                                    # [count, C, H, W]
-        t_b = ts_cpu[pos0:pos0 + count].to(model.device)
-        if P > 0:
-            x_in = torch.cat([xt_b, xt_b.repeat_interleave(P, 0)], 0)
-            t_in = torch.cat([t_b, t_b.repeat_interleave(P)], 0)
-            slot = torch.cat([torch.zeros(count, dtype=torch.int32),
-                              (1 + torch.arange(P, dtype=torch.int32)).repeat(count)]).to(model.device)
-        else:
-            x_in, t_in = xt_b, t_b
-            slot = torch.zeros(count, dtype=torch.int32, device=model.device)
-        cl_b = None if cl is None else cl.index_select(0, slot.long())
-        eps = _unet_eval(model, x_in, t_in, text, slot, cl_b, slot_key=("fwd", count, P))
-        eta = float(etas[N - pos0 - 1])
-        model.k_cfg_inv_step(pos0, count, eta, eps, eps[count:] if P > 0 else None, P, cfg_map, xt_src, xts, zs,
-                             numerical_fix)
+        with torch.cuda.stream(lane) if overlap else _NullCtx():
+            # loop position pos <-> idx = N - pos - 1 (inversion_utils.py:75); U-Net input xts[idx+1] = xts[N - pos]
+            src_rows = torch.arange(N - pos0, N - pos0 - count, -1, device=model.device)
+            xt_b = xt_src.index_select(0, src_rows)                                    # [count, C, H, W]
+            t_b = timesteps[pos0:pos0 + count]
+            slot, cl_b = slots[count]
+            if P > 0:
+                x_in = torch.cat([xt_b, xt_b.repeat_interleave(P, 0)], 0)
+                t_in = torch.cat([t_b, t_b.repeat_interleave(P)], 0)
+            else:
+                x_in, t_in = xt_b, t_b
+            eps = _unet_eval(model, x_in, t_in, text, slot, cl_b, slot_key=("fwd", count, P))
+            eta = float(etas[N - pos0 - 1])
+            model.k_cfg_inv_step(pos0, count, eta, eps, eps[count:] if P > 0 else None, P, cfg_map, xt_src, xts, zs,
+                                 numerical_fix)
+            if overlap:
+                lo, hi = N - pos0 - count, N - pos0 - 1
+                if lo == 0:
+                    zs[0] = torch.zeros_like(zs[0])     # inversion_utils.py:133, in lane order
+                ev = torch.cuda.Event()
+                ev.record(lane)
+                pend.chunks.append((lo, hi, ev))
     if g_ws > 1:
         _par.merge_owned_rows_(zs, owned, group)
         _par.merge_owned_rows_(xts[:N], owned, group)
     xt = xts[1][None] if N >= 1 else x0                 # the reference returns the last loop's xt = xts[1]
-    zs[0] = torch.zeros_like(zs[0])                     # inversion_utils.py:133
+    if overlap:
+        cur.wait_stream(lane)                           # ordinary stream semantics for every other consumer
+        pend.zs_ptr, pend.zs_ver, pend.xts_ptr, pend.xts_ver = zs.data_ptr(), zs._version, xts.data_ptr(), xts._version
+        pend.eta_key, pend.N = model.sched_table._eta_key, N
+        model.__dict__["_pending_forward"] = pend
+    else:
+        zs[0] = torch.zeros_like(zs[0])                 # inversion_utils.py:133
     return xt, zs, xts, extra_info
+
+
+class _NullCtx:
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *a):
+        return False
 
 
 def inversion_reverse_process(model: PipelineWrapper,
@@ -263,47 +384,84 @@ def inversion_reverse_process(model: PipelineWrapper,
                                 cutoff_points, hspace_add, hspace_replace, skipconns_replace, zero_out_resconns,
                                 extract_h_space, extract_skipconns, duration, first_order, extra_info)
     P = len(prompts)
-    text, cl = _loop_text(model, neg_prompts, prompts)
-    cfg_map, masks = _build_cfg_maps(P, xT.shape[1:], cfg_scales, cutoff_points, model.device, xT.dtype, masks_too=True)
     sched = model.model.scheduler
     N = sched.num_inference_steps
-    xt = xT[int(tstart.max())].unsqueeze(0).to(torch.float32).contiguous().clone()
     if etas is None:
         etas = 0
     if type(etas) in [int, float]:
         etas = [etas] * N
     assert len(etas) == N
     n = zs.shape[0]
-    ts_cpu = sched.timesteps_cpu[-n:]
-    model.setup_extra_inputs(xt, extra_info=extra_info, init_timestep=ts_cpu[0], audio_end_in_s=duration)
-    rows = 1 + P
-    model.sched_table.set_etas(etas)
-    slot = torch.arange(rows, dtype=torch.int32, device=model.device)
-    zs = zs.contiguous()
     tmax = int(tstart.max())
-    it = range(n)
-    if prog_bar:
-        it = tqdm(it)
-    x_in = torch.empty((rows, *xt.shape[1:]), device=model.device, dtype=torch.float32)
-    for k in it:
-        t = int(ts_cpu[k])
-        pos = N - n + k
-        idx = n - k - 1                                                      # inversion_utils.py:222-224
-        x_in.copy_(xt.expand(rows, -1, -1, -1))
-        t_in = torch.full((rows,), t, dtype=torch.int64, device=model.device)
-        eps = _unet_eval(model, x_in, t_in, text, slot, cl, slot_key=("rev", P))
-        apply_fix = ((tstart.max() - tstart) > k)
-        fa = None
-        xT_fix = None
-        if apply_fix.any():                                                  # inversion_utils.py:308-315
-            fa = [float(v) for v in (apply_fix * fix_alpha).to(torch.float32)]
-            xT_fix = xT[tmax - k - 1].to(torch.float32).contiguous()
-        out = torch.empty_like(xt)
-        model.k_cfg_rev_step(pos, float(etas[idx]), eps, eps[1:], P, cfg_map, xt, zs[idx], out, masks=masks,
-                             fix_alpha=fa, xT_fix=xT_fix)
-        xt = out
+    eta_key = tuple(float(e) for e in etas)
+
+    # ---- lanes (see _PendingForward): run on the high-priority reverse lane; wait per chunk when the forward process
+    # that produced (zs, xT) is still in flight, else behind the caller's stream
+    lanes = OVERLAP and USE_CUDA_GRAPHS and xT.is_cuda
+    pend = model.__dict__.pop("_pending_forward", None) if lanes else None
+    cur = torch.cuda.current_stream() if xT.is_cuda else None
+    if pend is not None and not (pend.matches(zs, xT, eta_key) and _loop_text_cached(model, neg_prompts, prompts)
+                                 and bool((tstart == tmax).all())):
+        pend = None
+    if lanes:
+        lane = _lane(model, "rev")
+        if pend is None:
+            lane.wait_stream(cur)
+        else:
+            model.overlap_hits = getattr(model, "overlap_hits", 0) + 1
+    waited = set()
+
+    def need(idx):
+        """Make the reverse lane wait for the forward chunk that finalises row idx of zs / xts."""
+        if pend is None or idx >= pend.N:       # row N of xts is never rewritten by the forward process
+            return
+        ev = pend.event_for(idx)
+        if ev is not None and id(ev) not in waited:
+            waited.add(id(ev))
+            lane.wait_event(ev)
+
+    with torch.cuda.stream(lane) if lanes else _NullCtx():
+        text, cl = _loop_text(model, neg_prompts, prompts)
+        cfg_map, masks = _build_cfg_maps(P, xT.shape[1:], cfg_scales, cutoff_points, model.device, xT.dtype,
+                                         masks_too=True)
+        need(tmax)
+        xt = xT[tmax].unsqueeze(0).to(torch.float32).contiguous().clone()
+        ts_cpu = sched.timesteps_cpu[-n:]
+        model.setup_extra_inputs(xt, extra_info=extra_info, init_timestep=ts_cpu[0], audio_end_in_s=duration)
+        rows = 1 + P
+        model.sched_table.set_etas(etas)
+        slot = torch.arange(rows, dtype=torch.int32, device=model.device)
+        zs = zs.contiguous()
+        it = range(n)
+        if prog_bar:
+            it = tqdm(it)
+        x_in = torch.empty((rows, *xt.shape[1:]), device=model.device, dtype=torch.float32)
+        for k in it:
+            t = int(ts_cpu[k])
+            pos = N - n + k
+            idx = n - k - 1                                                      # inversion_utils.py:222-224
+            x_in.copy_(xt.expand(rows, -1, -1, -1))
+            t_in = torch.full((rows,), t, dtype=torch.int64, device=model.device)
+            eps = _unet_eval(model, x_in, t_in, text, slot, cl, slot_key=("rev", P), lane=1 if lanes else 0)
+            apply_fix = ((tstart.max() - tstart) > k)
+            fa = None
+            xT_fix = None
+            if apply_fix.any():                                                  # inversion_utils.py:308-315
+                fa = [float(v) for v in (apply_fix * fix_alpha).to(torch.float32)]
+                xT_fix = xT[tmax - k - 1].to(torch.float32).contiguous()
+            out = torch.empty_like(xt)
+            need(idx)
+            model.k_cfg_rev_step(pos, float(etas[idx]), eps, eps[1:], P, cfg_map, xt, zs[idx], out, masks=masks,
+                                 fix_alpha=fa, xT_fix=xT_fix)
+            xt = out
+            if trace is not None:
+                trace.append(xt.clone())
+    if lanes:
+        cur.wait_stream(lane)
+        xt.record_stream(cur)                   # allocated on the lane, handed to the caller's stream
         if trace is not None:
-            trace.append(xt.clone())
+            for t_ in trace:
+                t_.record_stream(cur)
     return xt, zs
 
 

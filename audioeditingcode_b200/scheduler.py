@@ -72,6 +72,8 @@ class SchedTable:
         key = tuple(float(e) for e in etas)
         if key == self._eta_key:
             return
+        if self._eta_key is not None and torch.cuda.is_available() and torch.cuda.is_initialized():
+            torch.cuda.synchronize()      # kernels of a run in flight on a side lane may still read the old table
         N = self.N
         cdir = (C.c_float * N)()
         sig = (C.c_float * N)()

@@ -44,8 +44,13 @@ class GraphedForward:
     (and their TMA descriptors, encoded once at capture) replay with a single host call — the launch-latency
     answer SURVEY.md §7 'hard parts' asks for.  Inputs / output live in static buffers."""
 
-    def __init__(self, engine: "UNetEngine", B, H, W, text, slot_map, class_labels):
+    def __init__(self, engine: "UNetEngine", B, H, W, text, slot_map, class_labels, lane: int = 0):
         dev = engine.device
+        # lane 1 = the reverse-process lane (ddm_inversion/inversion_utils._PendingForward): its graph may replay
+        # while a forward-process graph is running on another stream, so it owns its workspaces (second CudaOps
+        # instance: split-K partial tiles, GroupNorm partials / tickets) and its kernel nodes carry the device's
+        # highest launch priority (the sub-wave kernels of the sequential chain take the next free SM slots).
+        self.lane = lane
         self.x = torch.zeros(B, engine.cfg.in_channels, H, W, device=dev, dtype=F32)
         self.t = torch.zeros(B, device=dev, dtype=torch.int64)
         self.slot = None if slot_map is None else slot_map.to(dev, torch.int32).clone()
@@ -54,21 +59,30 @@ class GraphedForward:
         # Small batches are launch-latency bound (each kernel is a fraction of a wave): with AEDIT_DUAL_STREAM=1 the
         # batch is cut in two halves captured on two forked streams of the same graph, so the two dependency chains
         # interleave on the SMs.  Each chain owns its workspaces (second CudaOps instance).
-        self.dual = engine.dual_stream and B % 2 == 0 and B <= engine.dual_stream_max_b
+        self.dual = engine.dual_stream and B % 2 == 0 and B <= engine.dual_stream_max_b and lane == 0
         if self.dual:
             engine.ops.lib.ae_set_gn_fused(0)     # two concurrent resident GroupNorm grids could starve each other
         cur = torch.cuda.current_stream()
-        side = torch.cuda.Stream()
+        side = torch.cuda.Stream(priority=-1 if lane == 1 else 0)
         self._side2 = torch.cuda.Stream() if self.dual else None
-        side.wait_stream(cur)
-        with torch.cuda.stream(side):
-            for _ in range(2):          # warm-up outside capture: workspaces, smem attributes, lazy allocations
-                self._run(engine)
-        cur.wait_stream(side)
-        torch.cuda.synchronize()
-        self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
-            self.out = self._run(engine)
+        main_ops = engine.ops
+        if lane == 1:
+            engine.ops = engine.ops_b()
+            engine.ops.lib.ae_set_launch_priority(engine.ops.lib.ae_greatest_priority())
+        try:
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                for _ in range(2):          # warm-up outside capture: workspaces, smem attributes, lazy allocations
+                    self._run(engine)
+            cur.wait_stream(side)
+            torch.cuda.synchronize()        # also drains the other lane: nothing runs during the capture
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph, stream=side):
+                self.out = self._run(engine)
+        finally:
+            if lane == 1:
+                engine.ops.lib.ae_set_launch_priority(0)
+            engine.ops = main_ops
 
     def _run(self, engine):
         if not self.dual:
@@ -127,16 +141,17 @@ class UNetEngine:
             self._ops_b = type(self.ops)()
         return self._ops_b
 
-    def graphed(self, B, H, W, text=None, slot_map=None, class_labels=None, slot_key=None) -> GraphedForward:
+    def graphed(self, B, H, W, text=None, slot_map=None, class_labels=None, slot_key=None, lane: int = 0
+                ) -> GraphedForward:
         """Cached CUDA-graph evaluator for this geometry / text binding.  `slot_key`: hashable description of
-        slot_map known on the host (avoids a device read-back per call)."""
+        slot_map known on the host (avoids a device read-back per call).  `lane`: see GraphedForward."""
         if slot_key is None and slot_map is not None:
             slot_key = tuple(int(v) for v in slot_map.tolist())
-        key = (B, H, W, id(text), slot_key, class_labels is not None)
+        key = (B, H, W, id(text), slot_key, class_labels is not None, lane)
         g = self._graphs.get(key)
         if g is None:
             l0 = self.ops.launch_count()
-            g = GraphedForward(self, B, H, W, text, slot_map, class_labels)
+            g = GraphedForward(self, B, H, W, text, slot_map, class_labels, lane=lane)
             g.kernels = (self.ops.launch_count() - l0) // 3       # 2 warm-ups + 1 capture
             self._graphs[key] = g
         return g

@@ -393,7 +393,10 @@ def main():
             "config": {"workload": args.config, "arch": spec["preset"], "weights": m.weights_source,
                        "latent": [1, 8, spec["H"], spec["W"]], "n_inv": spec["n_inv"], "tstart": spec["tstart"],
                        "denoising_steps_per_bench_step": steps_per_job, "forward_batch_timesteps": args.forward_batch,
-                       "parallelism": f"clip-dp{world}", "l2": "256 MiB flush between jobs; weights (1.5 GB) >> L2"},
+                       "parallelism": f"clip-dp{world}", "l2": "256 MiB flush between jobs; weights (1.5 GB) >> L2",
+                       "lanes": ("forward chunks and reverse steps of the clip on two streams (reverse lane high priority), "
+                                 f"fast path taken {getattr(m, 'overlap_hits', 0)}x") if getattr(m, "overlap_hits", 0)
+                       else "single stream"},
             "e2e": {"value": e2e_value, "unit": "steps/s", "h2d_bytes_per_step": x0_host.numel() * 4,
                     "d2h_bytes_per_step": e2e_out.numel() * 4},
             "gpu_launches": int(launches), "clocks": clocks}

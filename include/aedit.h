@@ -41,6 +41,15 @@ int ae_device_ok(void);
  * predecessor in the stream has drained, and waits for it before touching dependent global memory. */
 void ae_set_pdl(int mode); /* 0 off (default), 1 every kernel, 2 GEMM kernels only */
 
+/* Launch priority (cudaLaunchAttributePriority) attached to every kernel this library launches while it is set; 0 (the
+ * default) leaves the stream's own priority.  The host captures the reverse-process U-Net graph (reference
+ * inversion_utils.py:229-320, a strictly sequential chain of sub-wave kernels) with the device's highest priority,
+ * so that it can run CONCURRENTLY with the throughput-bound forward-process chunks (inversion_utils.py:69-131) of
+ * the same clip and still get the next free SM slots. */
+void ae_set_launch_priority(int prio);
+/* the current device's highest stream / launch priority (numerically lowest value; 0 when there is one level) */
+int ae_greatest_priority(void);
+
 /* CTA budget the automatic split-K heuristic fills (default 148 = one per SM).  Callers that run two dependency chains
  * concurrently on forked streams lower it so that the chains share the SMs instead of queueing behind each other. */
 void ae_set_splitk_ctas(int ctas);

@@ -185,6 +185,58 @@ def test_replay_invariant_bitexact_sequential():
     assert torch.equal(finals[0], finals[1])
 
 
+@pytest.mark.parametrize("N,ts,fb", [(12, 6, 3), (12, 12, 4), (10, 3, 4)])
+def test_forward_reverse_overlap_bitexact(N, ts, fb):
+    """The forward-process chunks (own lane, reordered so the reverse process can start early) running concurrently
+    with the reverse process (high-priority lane, own workspaces) give the same bits as plain stream order."""
+    from audioeditingcode_b200.ddm_inversion import inversion_utils as IU
+    g = load_golden("loop_eps_single.npz")
+    m = _wrapper(N)
+    x0 = g["x0"].cuda()
+    noise = torch.randn(N, *x0.shape[1:], generator=torch.Generator().manual_seed(5)).cuda()
+    res = {}
+    txt_src, txt_tgt = _GoldText(g, "src"), _GoldText(g, "tgt")     # persistent: the text cache is keyed by encoder
+    old = IU.OVERLAP
+    try:
+        for mode in (False, True, True):
+            IU.OVERLAP = mode
+            hits0 = getattr(m, "overlap_hits", 0)
+            m.encode_text = txt_src
+            with torch.inference_mode():                      # as main_run.py:117 does
+                _, zs, xts, _ = IU.inversion_forward_process(m, x0, etas=1.0, prompts=["p"], cfg_scales=[3.0],
+                                                             num_inference_steps=N, numerical_fix=True,
+                                                             forward_batch=fb, noise=noise, reverse_hint=ts)
+                m.encode_text = txt_tgt
+                w, _ = IU.inversion_reverse_process(m, xT=xts, tstart=torch.tensor([ts], dtype=torch.int), etas=1.0,
+                                                    prompts=["q"], neg_prompts=[""], cfg_scales=[5.0], zs=zs[:ts])
+            if mode and "warm" in res:
+                assert getattr(m, "overlap_hits", 0) == hits0 + 1, "overlap fast path not taken"
+            res.setdefault("warm" if mode else "seq", (zs.clone(), xts.clone(), w.clone()))
+            if mode:
+                res["ovl"] = (zs.clone(), xts.clone(), w.clone())
+    finally:
+        IU.OVERLAP = old
+    for a, b in zip(res["seq"], res["ovl"]):
+        assert torch.equal(a, b)
+    # a tensor modified between the two calls must not take the fast path (version counter guard)
+    IU.OVERLAP = True
+    try:
+        m.encode_text = txt_src
+        _, zs, xts, _ = IU.inversion_forward_process(m, x0, etas=1.0, prompts=["p"], cfg_scales=[3.0],
+                                                     num_inference_steps=N, numerical_fix=True, forward_batch=fb,
+                                                     noise=noise)
+        zs[1] += 1.0
+        hits0 = getattr(m, "overlap_hits", 0)
+        m.encode_text = txt_tgt
+        w2, _ = IU.inversion_reverse_process(m, xT=xts, tstart=torch.tensor([ts], dtype=torch.int), etas=1.0,
+                                             prompts=["q"], neg_prompts=[""], cfg_scales=[5.0], zs=zs[:ts])
+        assert getattr(m, "overlap_hits", 0) == hits0
+        if ts > 1:
+            assert not torch.equal(w2, res["seq"][2])
+    finally:
+        IU.OVERLAP = old
+
+
 def test_ddim_mode_vs_reference_golden():
     """`--mode ddim` baseline (ddim_inversion.py:10-84): deterministic inversion + guided regeneration through the
     drop-in functions vs the unmodified reference's outputs.  10 large DDIM steps amplify the bf16 U-Net error;
@@ -242,3 +294,21 @@ def test_full_size_properties_audioldm2_large():
     assert rel < 6e-2, f"batched vs sequential forward: rel-L2(zs) {rel}"
     _, zs_b2, xts_b2, _ = IU.inversion_forward_process(m, x0, forward_batch=6, **kw)
     assert torch.equal(zs_b, zs_b2) and torch.equal(xts_b, xts_b2)
+    # (v) forward / reverse overlap (two lanes) == plain stream order, bit for bit, at full size
+    outs = []
+    old = IU.OVERLAP
+    try:
+        for mode in (False, True):
+            IU.OVERLAP = mode
+            hits0 = getattr(m, "overlap_hits", 0)
+            _, zs_o, xts_o, _ = IU.inversion_forward_process(m, x0, forward_batch=3, reverse_hint=ts, **kw)
+            w_o, _ = IU.inversion_reverse_process(m, xT=xts_o, tstart=torch.tensor([ts], dtype=torch.int), etas=1.0,
+                                                  prompts=["a recording of a cat meowing"], neg_prompts=[""],
+                                                  cfg_scales=[12.0], zs=zs_o[:ts])
+            outs.append((zs_o.clone(), xts_o.clone(), w_o.clone()))
+            if mode:      # the target prompt was encoded by the first pass, so the fast path must be taken
+                assert getattr(m, "overlap_hits", 0) == hits0 + 1
+    finally:
+        IU.OVERLAP = old
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)

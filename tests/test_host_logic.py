@@ -86,3 +86,48 @@ def test_conv_fast_path_geometry():
     assert ok(2, 256, 16, 128) and ok(2, 128, 8, 256) and ok(2, 64, 4, 384) and ok(2, 32, 2, 640)   # AudioLDM-S levels
     assert ok(1, 1, 1024, 64) and ok(1, 1024, 64, 128)                                             # vocoder / VAE
     assert not ok(2, 256, 16, 8) and not ok(1, 141, 16, 128) and not ok(1, 20, 16, 128)
+
+
+def test_forward_chunk_plan():
+    """inversion_utils._chunk_plan: a partition of the N loop positions; with a hint, row `hint` tops the first
+    chunk, the rows below follow in descending order, the rows above come last."""
+    from audioeditingcode_b200.ddm_inversion.inversion_utils import _chunk_plan
+    for N, tb in [(200, 50), (200, 25), (50, 50), (12, 5), (7, 3), (10, 1), (13, 4)]:
+        natural = [(p, min(tb, N - p)) for p in range(0, N, tb)]
+        assert _chunk_plan(N, tb, None) == natural
+        for hint in range(0, N + 1):
+            plan = _chunk_plan(N, tb, hint)
+            pos = sorted(q for p, c in plan for q in range(p, p + c))
+            assert pos == list(range(N)), (N, tb, hint, plan)
+            if tb == 1:
+                assert plan == natural
+                continue
+            rows = [(N - p - c, N - p - 1) for p, c in plan]          # (lo, hi) in idx space
+            top = min(hint, N - 1)
+            assert rows[0][1] == top
+            below = [r for r in rows if r[1] <= top]
+            assert rows[:len(below)] == below and below == sorted(below, key=lambda r: -r[1])
+            assert all(c <= tb + max(1, tb // 4) for _, c in plan)
+    assert _chunk_plan(200, 50, 100) == [(99, 50), (149, 51), (49, 50), (0, 49)]
+    assert _chunk_plan(200, 50, 200) == [(0, 50), (50, 50), (100, 50), (150, 50)]
+
+
+def test_pending_forward_guard():
+    """The overlap fast path is refused unless the reverse process receives the forward process's own, unmodified
+    tensors (storage + version counters) and the same eta table."""
+    import torch
+    from audioeditingcode_b200.ddm_inversion.inversion_utils import _PendingForward
+    with torch.inference_mode():
+        with torch.inference_mode(False):
+            zs, xts = torch.zeros(4, 3), torch.zeros(5, 3)
+        p = _PendingForward()
+        p.zs_ptr, p.zs_ver, p.xts_ptr, p.xts_ver, p.eta_key, p.N = zs.data_ptr(), zs._version, xts.data_ptr(), xts._version, (1.0,) * 4, 4
+        p.chunks = [(2, 3, "e1"), (0, 1, "e0")]
+        assert p.matches(zs[:2], xts, (1.0,) * 4)
+        assert not p.matches(zs[1:3], xts, (1.0,) * 4)            # different rows
+        assert not p.matches(zs[:2], xts, (0.5,) * 4)             # different eta table
+        assert not p.matches(zs[:2].clone(), xts, (1.0,) * 4)     # a copy
+        assert not p.matches(torch.zeros(4, 3), xts, (1.0,) * 4)  # inference tensor: no version counter
+        assert p.event_for(3) == "e1" and p.event_for(0) == "e0" and p.event_for(9) is None
+        zs[1] += 1
+        assert not p.matches(zs[:2], xts, (1.0,) * 4)             # modified in place after the forward process
