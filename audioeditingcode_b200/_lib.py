@@ -27,7 +27,8 @@ class AeGemmArgs(C.Structure):
                 ("out_f32", vp), ("ld_out_f32", i64), ("out_bf16", vp), ("ld_out_bf16", i64), ("act", i32),
                 ("alpha", f32), ("conv", i32), ("B", i32), ("H", i32), ("W_", i32), ("C", i32), ("kh", i32),
                 ("kw", i32), ("dil_h", i32), ("dil_w", i32), ("force_bn", i32), ("splitk_ws", vp), ("splitk_ws_bytes", i64),
-                ("force_split", i32), ("force_csplit", i32), ("w_dynamic", i32), ("force_stages", i32)]
+                ("force_split", i32), ("force_csplit", i32), ("w_dynamic", i32), ("force_stages", i32),
+                ("colstats", vp), ("cs_rows_per_sample", i32)]
 
 
 _SIGS = {
@@ -38,6 +39,10 @@ _SIGS = {
     "ae_set_pdl": (None, [i32]),
     "ae_set_launch_priority": (None, [i32]),
     "ae_greatest_priority": (i32, []),
+    "ae_set_shared_sm": (None, [i32]),
+    "ae_set_skip_mask": (None, [i32]),
+    "ae_set_pdl_extra": (None, [i32]),
+    "ae_set_gn_stream_min_bytes": (None, [i64]),
     "ae_set_splitk_ctas": (None, [i32]),
     "ae_set_fast_epilogue": (None, [i32]),
     "ae_set_tile_model": (None, [i32]),
@@ -58,6 +63,7 @@ _SIGS = {
     "ae_im2col": (i32, [vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp, i64, vp]),
     "ae_groupnorm_workspace_bytes": (i64, [i32, i32]),
     "ae_groupnorm": (i32, [vp, i32, vp, i32, i32, i64, i32, f32, vp, vp, i32, vp, vp, vp, vp, vp]),
+    "ae_groupnorm_cs": (i32, [vp, i32, vp, vp, i32, vp, i32, i64, i32, f32, vp, vp, i32, vp, vp, vp, vp, vp]),
     "ae_layernorm": (i32, [vp, i64, i32, f32, vp, vp, vp, vp]),
     "ae_geglu": (i32, [vp, i64, i32, vp, vp]),
     "ae_attention": (i32, [vp, i64, i64, vp, i64, i64, vp, i64, i64, vp, vp, i64, i32, i32, i32, i32, i32, f32, vp,

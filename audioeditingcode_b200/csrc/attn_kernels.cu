@@ -270,7 +270,7 @@ int launch_attn(const AttnArgs& a, int B, int heads, cudaStream_t st) {
     attr_set = true;
   }
   dim3 grid((a.Tq + BQ - 1) / BQ, heads, B);
-  launch_kernel(attention_kernel<D>, dim3(grid), dim3(kAttnThreads), (size_t)(C::kSmemBytes), st, a);
+  launch_kernel_family(8, attention_kernel<D>, dim3(grid), dim3(kAttnThreads), (size_t)(C::kSmemBytes), st, a);
   return launched("ae_attention");
 }
 
@@ -306,6 +306,7 @@ extern "C" int ae_attention(const void* q, int64_t ld_q, int64_t q_bs, const voi
   a.Tk = Tk;
   a.scale_log2 = scale * 1.4426950408889634f;
   cudaStream_t st = as_stream(stream);
+  if (g_skip_mask & 32) return AE_OK;
   switch (d) {
     case 32: return launch_attn<32>(a, B, heads, st);
     case 40: return launch_attn<40>(a, B, heads, st);

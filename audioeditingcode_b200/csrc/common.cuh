@@ -50,6 +50,12 @@ extern int g_use_pdl;
 // the reverse-process graph is captured with the device's highest priority so that its sub-wave kernels take the next
 // free SM slots ahead of the pending CTAs of a forward-process chunk running concurrently on another stream.
 extern int g_launch_priority;       // 0 = leave the stream's priority
+// Diagnostic only (ae_set_skip_mask, tools/kernel_share.py): kernel families whose launches are dropped, to measure
+// each family's marginal cost inside a captured graph.  Results are garbage while it is non-zero.
+// In PDL mode 2 (GEMMs only) the kernel families of this mask are launched with the PDL attribute as well:
+// 1 GroupNorm statistics, 2 GroupNorm apply, 4 LayerNorm, 8 attention (ae_set_pdl_extra; A/B in profiles/).
+extern int g_pdl_extra;
+extern int g_skip_mask;             // 1 gemm, 2 split-K reduce, 4 GN stats, 8 GN apply, 16 LayerNorm, 32 attention
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
@@ -90,6 +96,13 @@ template <typename... KArgs, typename... Args>
 inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
                                  Args&&... args) {
   return launch_kernel_mode(false, kernel, grid, block, smem, st, static_cast<Args&&>(args)...);
+}
+
+// family: bit of g_pdl_extra that lets this launch start early in PDL mode 2
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel_family(int family, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                                        cudaStream_t st, Args&&... args) {
+  return launch_kernel_mode((g_pdl_extra & family) != 0, kernel, grid, block, smem, st, static_cast<Args&&>(args)...);
 }
 
 inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }

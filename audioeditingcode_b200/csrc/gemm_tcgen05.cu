@@ -29,6 +29,8 @@
 namespace aedit {
 int g_use_pdl = 0;
 int g_launch_priority = 0;
+int g_skip_mask = 0;
+int g_pdl_extra = 0;
 namespace {
 
 constexpr int BM = 128;
@@ -62,7 +64,21 @@ struct GemmDev {
   int fast_epi;  // 1: operands / outputs are 16-byte tileable -> coalesced staged epilogue (epilogue_strip)
   int act;  // 0 none, 1 SiLU, 2 GEGLU (output width N/2: out[16q+i] = acc[32q+i] * gelu(acc[32q+16+i]))
   float alpha;
+  // GroupNorm column statistics of the OUTPUT (see ae_gemm_args.colstats): fixed-point accumulators [sample][N][2]
+  unsigned long long* colstats;
+  int cs_rows;   // rows per sample (multiple of 32)
 };
+
+// Fixed-point scales of the column statistics: sum * 2^28, sum of squares * 2^24, accumulated with integer atomics —
+// integer addition is associative, so the totals do not depend on the order in which CTAs arrive (deterministic),
+// unlike floating-point atomics.  Headroom: |sum| < 3.4e10, sum of squares < 5.5e11 per (sample, channel).
+constexpr double kCsScaleSum = 268435456.0;
+constexpr double kCsScaleSq = 16777216.0;
+__device__ __forceinline__ void colstats_add(unsigned long long* cs, long long sample, int N, int col, float s, float q) {
+  unsigned long long* dst = cs + ((sample * N + col) << 1);
+  atomicAdd(dst, (unsigned long long)__double2ll_rn((double)s * kCsScaleSum));
+  atomicAdd(dst + 1, (unsigned long long)__double2ll_rn((double)q * kCsScaleSq));
+}
 
 // STAGES = 3: 2-3 CTAs per SM (large grids: one CTA's epilogue overlaps another's main loop).
 // STAGES = 6: grids that cannot fill the machine anyway (one CTA per SM) need the deeper ring to cover TMA latency.
@@ -253,6 +269,7 @@ __device__ __forceinline__ void epilogue_strip(const GemmDev& p, float* strip, u
                            __uint_as_float(v[4 * j + 2]) * p.alpha, __uint_as_float(v[4 * j + 3]) * p.alpha);
   }
   __syncwarp();
+  const unsigned cs_mask = __ballot_sync(0xffffffffu, col_ok);   // lanes that stay (whole column classes)
   if (!col_ok) return;
   if (geglu) {
     const long long ocol = (n0 >> 1) + oc;
@@ -277,6 +294,9 @@ __device__ __forceinline__ void epilogue_strip(const GemmDev& p, float* strip, u
   }
   float* of = p.out_f32 ? p.out_f32 + (long long)zo * p.stride_out + n : nullptr;
   __nv_bfloat16* ob = p.out_bf16 ? p.out_bf16 + (long long)zo * p.stride_out + n : nullptr;
+  // column statistics of this strip (rows in increasing order per lane, then a fixed tree over the lanes that share
+  // the columns): per-column sum and sum of squares of the final fp32 values
+  float4 cs_s = make_float4(0.f, 0.f, 0.f, 0.f), cs_q = cs_s;
 #pragma unroll 1
   for (int b = 0; b < NB; ++b) {
     float4 r[PF];
@@ -306,6 +326,11 @@ __device__ __forceinline__ void epilogue_strip(const GemmDev& p, float* strip, u
         if (p.act == 1) {
           a.x = silu_f(a.x); a.y = silu_f(a.y); a.z = silu_f(a.z); a.w = silu_f(a.w);
         }
+        if (p.colstats) {
+          cs_s.x += a.x; cs_s.y += a.y; cs_s.z += a.z; cs_s.w += a.w;
+          cs_q.x = fmaf(a.x, a.x, cs_q.x); cs_q.y = fmaf(a.y, a.y, cs_q.y);
+          cs_q.z = fmaf(a.z, a.z, cs_q.z); cs_q.w = fmaf(a.w, a.w, cs_q.w);
+        }
         if (of) *reinterpret_cast<float4*>(of + m * p.ld_out_f32) = a;
         if (ob) {
           __nv_bfloat162 h0 = __floats2bfloat162_rn(a.x, a.y);
@@ -316,6 +341,22 @@ __device__ __forceinline__ void epilogue_strip(const GemmDev& p, float* strip, u
           *reinterpret_cast<uint2*>(ob + m * p.ld_out_bf16) = pk;
         }
       }
+    }
+  }
+  if (p.colstats) {
+#pragma unroll
+    for (int o = LPR; o < 32; o <<= 1) {
+      cs_s.x += __shfl_xor_sync(cs_mask, cs_s.x, o); cs_s.y += __shfl_xor_sync(cs_mask, cs_s.y, o);
+      cs_s.z += __shfl_xor_sync(cs_mask, cs_s.z, o); cs_s.w += __shfl_xor_sync(cs_mask, cs_s.w, o);
+      cs_q.x += __shfl_xor_sync(cs_mask, cs_q.x, o); cs_q.y += __shfl_xor_sync(cs_mask, cs_q.y, o);
+      cs_q.z += __shfl_xor_sync(cs_mask, cs_q.z, o); cs_q.w += __shfl_xor_sync(cs_mask, cs_q.w, o);
+    }
+    if (sub == 0 && m_base < p.M) {
+      const long long sample = m_base / p.cs_rows;     // a 32-row strip never straddles samples (cs_rows % 32 == 0)
+      colstats_add(p.colstats, sample, p.N, n + 0, cs_s.x, cs_q.x);
+      colstats_add(p.colstats, sample, p.N, n + 1, cs_s.y, cs_q.y);
+      colstats_add(p.colstats, sample, p.N, n + 2, cs_s.z, cs_q.z);
+      colstats_add(p.colstats, sample, p.N, n + 3, cs_s.w, cs_q.w);
     }
   }
 }
@@ -571,6 +612,8 @@ struct ReduceArgs {
   int act;
   float alpha;
   int res_vec;   // bit 0 / 1 / 2: residual / bias / row-bias rows are 16-byte aligned (pointer and pitch)
+  unsigned long long* colstats;   // optional GroupNorm column statistics of the output (splitk_reduce_stats_kernel)
+  int cs_rows;
 };
 
 __global__ void __launch_bounds__(256) splitk_reduce_kernel(ReduceArgs a) {
@@ -650,6 +693,105 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(ReduceArgs a) {
   }
 }
 
+// Reduce + epilogue + GroupNorm column statistics.  A block owns 32 rows x 128 columns: warp w sums / finishes rows
+// 4w..4w+3 (lane = column quad; same arithmetic and order as splitk_reduce_kernel -> same output bits), the eight
+// warps' per-column sums are combined through shared memory in warp order, and one fixed-point atomic per column and
+// moment goes to the accumulators.  grid (ceil(N/128), ceil(M/32)).
+__global__ void __launch_bounds__(256) splitk_reduce_stats_kernel(ReduceArgs a) {
+  pdl_wait();
+  __shared__ float s_sum[8][128];
+  __shared__ float s_sq[8][128];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int n = blockIdx.x * 128 + lane * 4;
+  const long long m_base = (long long)blockIdx.y * 32;
+  const bool col_ok = n + 3 < a.N;
+  float4 cs = make_float4(0.f, 0.f, 0.f, 0.f), cq = cs;
+  // all loads of the warp's four rows first (S partials each), then the arithmetic
+  float4 bia = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (a.bias && col_ok) bia = (a.res_vec & 2) ? __ldg(reinterpret_cast<const float4*>(a.bias + n))
+                                              : make_float4(__ldg(a.bias + n), __ldg(a.bias + n + 1), __ldg(a.bias + n + 2), __ldg(a.bias + n + 3));
+  float4 acc[4], rbi[4], rsd[4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const long long m = m_base + warp * 4 + r;
+    acc[r] = rbi[r] = rsd[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (!col_ok || m >= a.M) continue;
+    if (a.rowbias) {
+      const float* q = a.rowbias + (m / a.rows_per_group) * a.ld_rowbias + n;
+      rbi[r] = (a.res_vec & 4) ? __ldg(reinterpret_cast<const float4*>(q)) : make_float4(__ldg(q), __ldg(q + 1), __ldg(q + 2), __ldg(q + 3));
+    }
+    if (a.residual) {
+      const float* q = a.residual + m * a.ld_res + n;
+      rsd[r] = (a.res_vec & 1) ? *reinterpret_cast<const float4*>(q) : make_float4(q[0], q[1], q[2], q[3]);
+    }
+    acc[r] = *reinterpret_cast<const float4*>(a.ws + m * a.N + n);
+  }
+  for (int s0 = 1; s0 < a.S; s0 += 2) {
+    float4 t[4][2];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const long long m = m_base + warp * 4 + r;
+      const bool ok = col_ok && m < a.M;
+#pragma unroll
+      for (int u = 0; u < 2; ++u)
+        t[r][u] = (ok && s0 + u < a.S) ? *reinterpret_cast<const float4*>(a.ws + (long long)(s0 + u) * a.MN + m * a.N + n)
+                                       : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        if (s0 + u < a.S) {    // fixed order s = 1..S-1, exactly as splitk_reduce_kernel
+          acc[r].x += t[r][u].x; acc[r].y += t[r][u].y; acc[r].z += t[r][u].z; acc[r].w += t[r][u].w;
+        }
+      }
+    }
+  }
+  pdl_trigger();
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const long long m = m_base + warp * 4 + r;
+    if (!col_ok || m >= a.M) continue;
+    float v[4] = {acc[r].x * a.alpha, acc[r].y * a.alpha, acc[r].z * a.alpha, acc[r].w * a.alpha};
+    if (a.bias) {
+      v[0] += bia.x; v[1] += bia.y; v[2] += bia.z; v[3] += bia.w;
+    }
+    if (a.rowbias) {
+      v[0] += rbi[r].x; v[1] += rbi[r].y; v[2] += rbi[r].z; v[3] += rbi[r].w;
+    }
+    if (a.residual) {
+      v[0] += rsd[r].x; v[1] += rsd[r].y; v[2] += rsd[r].z; v[3] += rsd[r].w;
+    }
+    if (a.act == 1) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) v[k] = silu_f(v[k]);
+    }
+    cs.x += v[0]; cs.y += v[1]; cs.z += v[2]; cs.w += v[3];
+    cq.x = fmaf(v[0], v[0], cq.x); cq.y = fmaf(v[1], v[1], cq.y); cq.z = fmaf(v[2], v[2], cq.z); cq.w = fmaf(v[3], v[3], cq.w);
+    if (a.out_f32) *reinterpret_cast<float4*>(a.out_f32 + m * a.ld_out_f32 + n) = make_float4(v[0], v[1], v[2], v[3]);
+    if (a.out_bf16) {
+      __nv_bfloat16* o = a.out_bf16 + m * a.ld_out_bf16 + n;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) o[k] = __float2bfloat16_rn(v[k]);
+    }
+  }
+  *reinterpret_cast<float4*>(&s_sum[warp][lane * 4]) = cs;
+  *reinterpret_cast<float4*>(&s_sq[warp][lane * 4]) = cq;
+  __syncthreads();
+  if (threadIdx.x < 128) {
+    const int c = threadIdx.x, col = blockIdx.x * 128 + c;
+    if (col < a.N && m_base < a.M) {
+      float su = s_sum[0][c], sq = s_sq[0][c];
+#pragma unroll
+      for (int w = 1; w < 8; ++w) {
+        su += s_sum[w][c];
+        sq += s_sq[w][c];
+      }
+      colstats_add(a.colstats, m_base / a.cs_rows, a.N, col, su, sq);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -725,6 +867,7 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmDev& p, int
     if (e != cudaSuccess) return fail(AE_ECUDA, "cudaFuncSetAttribute(smem=%d): %s", L::kTotal, cudaGetErrorString(e));
     attr_set = true;
   }
+  if (g_skip_mask & 1) return AE_OK;
   const unsigned tm = (unsigned)((p.M + BM - 1) / BM), tn = (unsigned)((p.N + BN - 1) / BN);
   dim3 grid = p.m_in_x ? dim3(tm, tn, gz) : dim3(tn, tm, gz);
   cudaError_t e;
@@ -759,6 +902,8 @@ using namespace aedit;
 
 extern "C" void ae_set_pdl(int mode) { g_use_pdl = (mode == 1 || mode == 2) ? mode : 0; }
 extern "C" void ae_set_launch_priority(int prio) { g_launch_priority = prio; }
+extern "C" void ae_set_skip_mask(int mask) { g_skip_mask = mask; }
+extern "C" void ae_set_pdl_extra(int mask) { g_pdl_extra = mask; }
 extern "C" int ae_greatest_priority(void) {
   int least = 0, greatest = 0;
   if (cudaDeviceGetStreamPriorityRange(&least, &greatest) != cudaSuccess) {
@@ -770,6 +915,8 @@ extern "C" int ae_greatest_priority(void) {
 
 static int g_splitk_ctas = 148;
 static int g_fast_epi = 1;
+static int g_shared_sm = 0;
+extern "C" void ae_set_shared_sm(int on) { g_shared_sm = on ? 1 : 0; }
 static int g_tile_model = 1;
 extern "C" void ae_set_tile_model(int on) { g_tile_model = on ? 1 : 0; }
 extern "C" void ae_set_fast_epilogue(int mode) { g_fast_epi = (mode == 0 || mode == 2) ? mode : 1; }
@@ -813,6 +960,18 @@ extern "C" int ae_gemm(const ae_gemm_args* a, ae_stream stream) {
   p.csplit = 0;
   p.fast_epi = 0;
   p.m_in_x = (a->M + BM - 1) / BM > 65535 ? 1 : 0;
+  p.colstats = nullptr;
+  p.cs_rows = 1;
+  if (a->colstats) {
+    AE_CHECK_ARG(batch == 1 && a->act != 2 && a->N % 4 == 0 && a->out_f32 && a->force_csplit <= 1,
+                 "ae_gemm: colstats needs batch 1, a plain fp32 output with N %% 4 == 0 and no cluster split");
+    AE_CHECK_ARG(a->cs_rows_per_sample > 0 && a->cs_rows_per_sample % 32 == 0 && a->M % a->cs_rows_per_sample == 0,
+                 "ae_gemm: colstats needs rows per sample (%d) to be a multiple of 32 dividing M", a->cs_rows_per_sample);
+    AE_CHECK_ARG(a->ld_out_f32 % 4 == 0 && (reinterpret_cast<uintptr_t>(a->out_f32) & 15) == 0,
+                 "ae_gemm: colstats needs a 16-byte tileable fp32 output");
+    p.colstats = reinterpret_cast<unsigned long long*>(a->colstats);
+    p.cs_rows = a->cs_rows_per_sample;
+  }
 
   CUtensorMap tmA, tmB;
   int rc;
@@ -964,6 +1123,7 @@ extern "C" int ae_gemm(const ae_gemm_args* a, ae_stream stream) {
     q.stride_out = (long long)a->M * a->N;
     q.act = 0;
     q.alpha = 1.0f;
+    q.colstats = nullptr;   // the reduce kernel sees the final values
   }
   {
     // coalesced staged epilogue: every pointer / pitch the strip touches must be 16-byte tileable (8 for bf16 rows,
@@ -981,20 +1141,31 @@ extern "C" int ae_gemm(const ae_gemm_args* a, ae_stream stream) {
     // (165 -> 111 us on [102400x384x384]+res) or a wide fp32 tile is written by a multi-wave grid; for bf16-only,
     // GEGLU and small-grid outputs its extra shared-memory round trip costs 1-2 us per tile, so those keep the
     // row-per-thread stores.  g_fast_epi: 0 never, 1 this rule, 2 whenever legal.
-    const bool want = g_fast_epi == 2 || q.residual || (q.out_f32 && !g && tiles * gz > 2 * 148);
+    const bool want = g_fast_epi == 2 || q.residual || (q.out_f32 && !g && tiles * gz > 2 * 148) || q.colstats;
     q.fast_epi = (ok && want) ? 1 : 0;
+    if (q.colstats && !q.fast_epi)
+      return fail(AE_EUNSUPPORTED, "ae_gemm: colstats needs the staged epilogue (16-byte tileable operands, "
+                                   "ae_set_fast_epilogue != 0)");
   }
   const long long ctas = tiles * gz;
   const bool deep = a->force_stages ? (a->force_stages > 3) : (ctas <= 160 || CS > 1);
+  // g_shared_sm (ae_set_shared_sm): this launch will share the SMs with a throughput-bound grid of another stream
+  // whose CTAs hold ~100 KB of shared memory each (two per SM).  A 6-stage ring (120-192 KB) would only fit after BOTH
+  // of them have retired with no successor taking the slot, i.e. practically never; the deepest ring that fits beside
+  // ONE such CTA (<= ~103 KB: 3 / 4 / 5 stages at BN = 128 / 64 / 32) gets the next free slot.  Same bits either way:
+  // the ring depth changes the buffering, not the order of the accumulation.
+  const bool shared_sm = g_shared_sm && CS == 1 && !a->force_stages;
   switch (bn) {
     case 32:
-      rc = deep ? launch<32, 6>(tmA, tmB, q, gz, st) : launch<32, 3>(tmA, tmB, q, gz, st);
+      rc = deep ? (shared_sm ? launch<32, 5>(tmA, tmB, q, gz, st) : launch<32, 6>(tmA, tmB, q, gz, st))
+                : launch<32, 3>(tmA, tmB, q, gz, st);
       break;
     case 64:
-      rc = deep ? launch<64, 6>(tmA, tmB, q, gz, st) : launch<64, 3>(tmA, tmB, q, gz, st);
+      rc = deep ? (shared_sm ? launch<64, 4>(tmA, tmB, q, gz, st) : launch<64, 6>(tmA, tmB, q, gz, st))
+                : launch<64, 3>(tmA, tmB, q, gz, st);
       break;
     default:
-      rc = deep ? launch<128, 6>(tmA, tmB, q, gz, st) : launch<128, 3>(tmA, tmB, q, gz, st);
+      rc = (deep && !shared_sm) ? launch<128, 6>(tmA, tmB, q, gz, st) : launch<128, 3>(tmA, tmB, q, gz, st);
       break;
   }
   if (rc || S == 1) return rc;
@@ -1019,9 +1190,17 @@ extern "C" int ae_gemm(const ae_gemm_args* a, ae_stream stream) {
   r.res_vec = ((p.residual && (reinterpret_cast<uintptr_t>(p.residual) & 15) == 0 && p.ld_res % 4 == 0) ? 1 : 0) |
               ((p.bias && (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0) ? 2 : 0) |
               ((p.rowbias && (reinterpret_cast<uintptr_t>(p.rowbias) & 15) == 0 && p.ld_rowbias % 4 == 0) ? 4 : 0);
+  r.colstats = p.colstats;
+  r.cs_rows = p.cs_rows;
   long long blocks = ceil_div64(r.MN / 4, 256);
   if (blocks > 148 * 8) blocks = 148 * 8;
-  cudaError_t e = launch_kernel_early(splitk_reduce_kernel, dim3((unsigned)blocks), dim3(256), (size_t)0, st, r);
+  if (g_skip_mask & 2) return AE_OK;
+  cudaError_t e;
+  if (r.colstats)
+    e = launch_kernel_early(splitk_reduce_stats_kernel, dim3((unsigned)((a->N + 127) / 128), (unsigned)((a->M + 31) / 32)),
+                            dim3(256), (size_t)0, st, r);
+  else
+    e = launch_kernel_early(splitk_reduce_kernel, dim3((unsigned)blocks), dim3(256), (size_t)0, st, r);
   if (e != cudaSuccess) return fail(AE_ECUDA, "splitk_reduce launch: %s", cudaGetErrorString(e));
   return launched("ae_gemm(splitk_reduce)");
 }

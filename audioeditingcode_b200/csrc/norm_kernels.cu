@@ -31,7 +31,40 @@ struct GNArgs {
   double* partial;     // [B, S, G, 2]
   float* stats;        // [B, G, 2] mean, rstd
   unsigned int* counters;  // [B]
+  // statistics handed over by the producing GEMMs (ae_gemm_args.colstats): fixed-point per-(sample, channel) sums of
+  // x1 / x2; when set, no statistics kernel runs and the apply kernels derive mean / rstd themselves
+  const long long* cs1;    // [B, C1, 2]
+  const long long* cs2;    // [B, C2, 2] (or null when C2 == 0)
 };
+
+// mean / rstd of every group of sample b from the producers' fixed-point column sums -> s_mean / s_rstd (shared).
+// Integer adds are exact, so the result does not depend on the order of the lanes / of the producing CTAs.
+__device__ __forceinline__ void gn_stats_from_colsums(const GNArgs& a, int b, float* s_mean, float* s_rstd) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int g = wid; g < a.G; g += nw) {
+    long long su = 0, sq = 0;
+    for (int e = lane; e < a.cpg; e += 32) {
+      const int c = g * a.cpg + e;
+      const longlong2 v = c < a.C1 ? __ldcg(reinterpret_cast<const longlong2*>(a.cs1 + ((long long)b * a.C1 + c) * 2))
+                                   : __ldcg(reinterpret_cast<const longlong2*>(a.cs2 + ((long long)b * a.C2 + (c - a.C1)) * 2));
+      su += v.x;
+      sq += v.y;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      su += __shfl_down_sync(0xffffffffu, su, o);
+      sq += __shfl_down_sync(0xffffffffu, sq, o);
+    }
+    if (lane == 0) {
+      const double inv_n = 1.0 / ((double)a.HW * a.cpg);
+      const double mean = (double)su * (1.0 / 268435456.0) * inv_n;
+      double var = (double)sq * (1.0 / 16777216.0) * inv_n - mean * mean;
+      if (var < 0.0) var = 0.0;
+      s_mean[g] = (float)mean;
+      s_rstd[g] = rsqrtf((float)var + a.eps);
+    }
+  }
+}
 
 __device__ __forceinline__ float load_cat(const GNArgs& a, long long row, int c) {
   return c < a.C1 ? a.x1[row * a.C1 + c] : a.x2[row * a.C2 + (c - a.C1)];
@@ -217,6 +250,20 @@ __global__ void __launch_bounds__(kGNThreads) gn_apply_kernel(GNArgs a) {
     }
   }
   pdl_trigger();   // data loads are in flight
+  if (a.cs1) {
+    gn_stats_from_colsums(a, b, s_mean, s_rstd);
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < kGNTab; ++k) {
+      const int c = threadIdx.x + k * kGNThreads;
+      if (c < a.C) {
+        const int g = c / a.cpg;
+        const float A = s_rstd[g] * gpre[k];
+        s_A[c] = A;
+        s_B[c] = bpre[k] - s_mean[g] * A;
+      }
+    }
+  } else
   // mean / rstd were finalised by the statistics kernel.  All table loads are issued before any is consumed (a
   // rolled loop would expose one L2 round trip per 256 channels); they are in flight together with the data loads.
   {
@@ -269,6 +316,85 @@ __global__ void __launch_bounds__(kGNThreads) gn_apply_kernel(GNArgs a) {
     }
     if (a.cat_out) *reinterpret_cast<float4*>(a.cat_out + off) = v[it];
   }
+}
+
+// Streaming variant of gn_apply_kernel for large tensors: grid (row chunks, B); a CTA builds the per-channel affine
+// table once, then walks its rows with kGNStreamItems independent float4 loads in flight per thread.  Same
+// arithmetic (A = rstd*gamma, B = beta - mean*A, y = fma(x, A, B), SiLU) -> same bits as gn_apply_kernel.
+constexpr int kGNStreamItems = 4;
+constexpr long long kGNStreamBytesPerCta = 96 * 1024;
+__global__ void __launch_bounds__(kGNThreads) gn_apply_stream_kernel(GNArgs a, int rows_per_cta) {
+  pdl_wait();
+  extern __shared__ float sm[];  // A[C], B[C], mean[G], rstd[G]
+  float* s_A = sm;
+  float* s_B = sm + a.C;
+  float* s_mean = s_B + a.C;
+  float* s_rstd = s_mean + a.G;
+  const int b = blockIdx.y;
+  if (a.cs1) {
+    gn_stats_from_colsums(a, b, s_mean, s_rstd);
+    __syncthreads();
+  }
+  for (int c = threadIdx.x; c < a.C; c += kGNThreads) {
+    const int g = c / a.cpg;
+    const float2 mr = a.cs1 ? make_float2(s_mean[g], s_rstd[g])
+                            : *reinterpret_cast<const float2*>(a.stats + ((long long)b * a.G + g) * 2);
+    const float A = mr.y * __ldg(a.gamma + c);
+    s_A[c] = A;
+    s_B[c] = __ldg(a.beta + c) - mr.x * A;
+  }
+  __syncthreads();
+  const int vec_per_row = a.C >> 2;
+  const long long p0 = (long long)blockIdx.x * rows_per_cta;
+  const long long p1 = min(a.HW, p0 + (long long)rows_per_cta);
+  const int n_items = (int)((p1 - p0) * vec_per_row);
+  const long long row0 = (long long)b * a.HW + p0;
+  for (int i0 = threadIdx.x; i0 < n_items; i0 += kGNThreads * kGNStreamItems) {
+    float4 v[kGNStreamItems];
+    int pr[kGNStreamItems], cc[kGNStreamItems];
+#pragma unroll
+    for (int k = 0; k < kGNStreamItems; ++k) {
+      const int idx = i0 + k * kGNThreads;
+      if (idx < n_items) {
+        pr[k] = idx / vec_per_row;
+        cc[k] = (idx - pr[k] * vec_per_row) << 2;
+        const long long row = row0 + pr[k];
+        v[k] = cc[k] < a.C1 ? __ldcs(reinterpret_cast<const float4*>(a.x1 + row * a.C1 + cc[k]))
+                            : __ldcs(reinterpret_cast<const float4*>(a.x2 + row * a.C2 + (cc[k] - a.C1)));
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < kGNStreamItems; ++k) {
+      const int idx = i0 + k * kGNThreads;
+      if (idx >= n_items) continue;
+      const int c = cc[k];
+      const float in[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
+      const float4 A4 = *reinterpret_cast<const float4*>(s_A + c);
+      const float4 B4 = *reinterpret_cast<const float4*>(s_B + c);
+      float o[4] = {fmaf(in[0], A4.x, B4.x), fmaf(in[1], A4.y, B4.y), fmaf(in[2], A4.z, B4.z), fmaf(in[3], A4.w, B4.w)};
+      if (a.silu) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) o[e] = silu_f(o[e]);
+      }
+      const long long off = (row0 + pr[k]) * a.C + c;
+      __nv_bfloat162 h0 = __floats2bfloat162_rn(o[0], o[1]);
+      __nv_bfloat162 h1 = __floats2bfloat162_rn(o[2], o[3]);
+      uint2 pk;
+      pk.x = *reinterpret_cast<uint32_t*>(&h0);
+      pk.y = *reinterpret_cast<uint32_t*>(&h1);
+      *reinterpret_cast<uint2*>(a.out + off) = pk;
+      if (a.raw_out) {
+        __nv_bfloat162 r0 = __floats2bfloat162_rn(in[0], in[1]);
+        __nv_bfloat162 r1 = __floats2bfloat162_rn(in[2], in[3]);
+        uint2 rk;
+        rk.x = *reinterpret_cast<uint32_t*>(&r0);
+        rk.y = *reinterpret_cast<uint32_t*>(&r1);
+        *reinterpret_cast<uint2*>(a.raw_out + off) = rk;
+      }
+      if (a.cat_out) *reinterpret_cast<float4*>(a.cat_out + off) = v[k];
+    }
+  }
+  pdl_trigger();
 }
 
 // ---- small-batch path: ONE launch per GroupNorm.  grid (S, B) with S*B <= #SMs, so every CTA is resident at the
@@ -533,7 +659,7 @@ cudaError_t launch_ln(const float* x, long long rows, int C, float eps, const fl
   // one warp per row; few rows (reverse process at batch 2: 128-2048 rows) -> fewer rows per CTA so the rows spread
   // over all SMs instead of queueing on a few
   const int warps = rows >= 148 * 16 ? 4 : (rows >= 148 * 4 ? 2 : 1);
-  return launch_kernel(layernorm_kernel<NV>, dim3((unsigned)ceil_div64(rows, warps)), dim3(warps * 32), (size_t)0, st, x,
+  return launch_kernel_family(4, layernorm_kernel<NV>, dim3((unsigned)ceil_div64(rows, warps)), dim3(warps * 32), (size_t)0, st, x,
                        rows, C, eps, gamma, beta, out);
 }
 
@@ -542,6 +668,8 @@ cudaError_t launch_ln(const float* x, long long rows, int C, float eps, const fl
 
 using namespace aedit;
 
+static long long g_gn_stream_min_bytes = 8ll << 20;
+extern "C" void ae_set_gn_stream_min_bytes(int64_t bytes) { g_gn_stream_min_bytes = bytes; }
 static int g_gn_fused = 0;  // measured no faster than stats + apply (profiles/r01_microbench_v15_gn_resident.log): opt-in
 extern "C" void ae_set_gn_fused(int on) { g_gn_fused = on ? 1 : 0; }
 
@@ -550,9 +678,9 @@ extern "C" int64_t ae_groupnorm_workspace_bytes(int B, int groups) {
   return (int64_t)B * kMaxSplits * groups * 2 * 8 + (int64_t)B * groups * 2 * 4 + (int64_t)B * 4 + 64;
 }
 
-extern "C" int ae_groupnorm(const float* x1, int C1, const float* x2, int C2, int B, int64_t HW, int groups, float eps,
-                            const float* gamma, const float* beta, int silu, void* out_bf16, void* raw_out_bf16,
-                            float* cat_out_f32, float* workspace, ae_stream stream) {
+static int groupnorm_impl(const float* x1, int C1, const float* x2, int C2, int B, int64_t HW, int groups, float eps,
+                          const float* gamma, const float* beta, int silu, void* out_bf16, void* raw_out_bf16,
+                          float* cat_out_f32, float* workspace, const int64_t* cs1, const int64_t* cs2, ae_stream stream) {
   AE_CHECK_ARG(x1 && C1 > 0 && B > 0 && HW > 0 && groups > 0, "ae_groupnorm: bad argument");
   AE_CHECK_ARG((x2 != nullptr) == (C2 > 0), "ae_groupnorm: x2/C2 mismatch");
   const int C = C1 + C2;
@@ -571,6 +699,8 @@ extern "C" int ae_groupnorm(const float* x1, int C1, const float* x2, int C2, in
   a.cpg = C / groups;
   a.B = B;
   a.HW = HW;
+  a.cs1 = reinterpret_cast<const long long*>(cs1);
+  a.cs2 = reinterpret_cast<const long long*>(cs2);
   // thread block: TX channel quads x TY positions (<= 512 threads, <= 4 quads per thread)
   const int nq = C / 4;
   int TX = nq < 64 ? nq : 64;
@@ -590,7 +720,7 @@ extern "C" int ae_groupnorm(const float* x1, int C1, const float* x2, int C2, in
   a.partial = reinterpret_cast<double*>(wsb);
   a.stats = reinterpret_cast<float*>(wsb + (size_t)B * kMaxSplits * groups * 2 * 8);
   a.counters = reinterpret_cast<unsigned int*>(wsb + (size_t)B * kMaxSplits * groups * 2 * 8 + (size_t)B * groups * 2 * 4);
-  if (g_gn_fused && groups % 2 == 0) {
+  if (g_gn_fused && groups % 2 == 0 && !cs1) {
     // single resident launch (see gn_resident_kernel): the whole grid must fit on the machine, one CTA per SM
     static int n_sm = 0;
     if (n_sm == 0) {
@@ -623,7 +753,7 @@ extern "C" int ae_groupnorm(const float* x1, int C1, const float* x2, int C2, in
   a.chunk = ceil_div64(HW, S);
   a.S = (int)ceil_div64(HW, a.chunk);
   cudaStream_t st = as_stream(stream);
-  {
+  if (!cs1) {
     const size_t smem = (size_t)TY * 2 * C * sizeof(float);
     static size_t smem_set = 48 * 1024;
     if (smem > smem_set) {
@@ -631,16 +761,50 @@ extern "C" int ae_groupnorm(const float* x1, int C1, const float* x2, int C2, in
       smem_set = 160 * 1024;
     }
     AE_CHECK_ARG(smem <= 160 * 1024, "ae_groupnorm: C=%d needs too much shared memory", C);
-    launch_kernel(gn_stats_kernel, dim3(a.S, B), dim3(TX, TY), smem, st, a);
+    if (!(g_skip_mask & 4)) launch_kernel_family(1, gn_stats_kernel, dim3(a.S, B), dim3(TX, TY), smem, st, a);
   }
-  int rc = launched("ae_groupnorm(stats)");
-  if (rc) return rc;
+  if (!cs1) {
+    int rc = launched("ae_groupnorm(stats)");
+    if (rc) return rc;
+  }
   {
     const long long items = HW * (C / 4);
     const unsigned gx = (unsigned)ceil_div64(items, (long long)kGNThreads * kGNItems);
-    launch_kernel(gn_apply_kernel, dim3(gx, B), dim3(kGNThreads), (size_t)((2 * groups + 2 * C) * sizeof(float)), st, a);
+    // large tensors (forward-process chunks): streaming variant — the one-round kernel keeps ~100 registers per
+    // thread (2 CTAs per SM) and reaches ~2 TB/s; small ones (reverse process) are latency-bound and keep it
+    const long long bytes = (long long)B * HW * C * 4;
+    if (g_skip_mask & 8) {
+    } else if (bytes >= g_gn_stream_min_bytes) {
+      const long long row_bytes = (long long)C * 4;
+      long long rows_per_cta = (kGNStreamBytesPerCta + row_bytes - 1) / row_bytes;
+      if (rows_per_cta > HW) rows_per_cta = HW;
+      const unsigned sx = (unsigned)ceil_div64(HW, rows_per_cta);
+      launch_kernel_family(2, gn_apply_stream_kernel, dim3(sx, B), dim3(kGNThreads),
+                           (size_t)((2 * C + 2 * groups) * sizeof(float)), st, a, (int)rows_per_cta);
+    } else {
+      launch_kernel_family(2, gn_apply_kernel, dim3(gx, B), dim3(kGNThreads),
+                           (size_t)((2 * groups + 2 * C) * sizeof(float)), st, a);
+    }
   }
   return launched("ae_groupnorm(apply)");
+}
+
+extern "C" int ae_groupnorm(const float* x1, int C1, const float* x2, int C2, int B, int64_t HW, int groups, float eps,
+                            const float* gamma, const float* beta, int silu, void* out_bf16, void* raw_out_bf16,
+                            float* cat_out_f32, float* workspace, ae_stream stream) {
+  return groupnorm_impl(x1, C1, x2, C2, B, HW, groups, eps, gamma, beta, silu, out_bf16, raw_out_bf16, cat_out_f32,
+                        workspace, nullptr, nullptr, stream);
+}
+
+extern "C" int ae_groupnorm_cs(const float* x1, int C1, const int64_t* colstats1, const float* x2, int C2,
+                               const int64_t* colstats2, int B, int64_t HW, int groups, float eps, const float* gamma,
+                               const float* beta, int silu, void* out_bf16, void* raw_out_bf16, float* cat_out_f32,
+                               float* workspace, ae_stream stream) {
+  AE_CHECK_ARG(colstats1 && ((colstats2 != nullptr) == (C2 > 0)), "ae_groupnorm_cs: column statistics missing");
+  AE_CHECK_ARG((reinterpret_cast<uintptr_t>(colstats1) & 15) == 0 && (reinterpret_cast<uintptr_t>(colstats2) & 15) == 0,
+               "ae_groupnorm_cs: column statistics must be 16-byte aligned");
+  return groupnorm_impl(x1, C1, x2, C2, B, HW, groups, eps, gamma, beta, silu, out_bf16, raw_out_bf16, cat_out_f32,
+                        workspace, colstats1, colstats2, stream);
 }
 
 extern "C" int ae_layernorm(const float* x, int64_t rows, int C, float eps, const float* gamma, const float* beta,
@@ -651,6 +815,7 @@ extern "C" int ae_layernorm(const float* x, int64_t rows, int C, float eps, cons
   cudaStream_t st = as_stream(stream);
   const int nv = (C + 127) / 128;
   cudaError_t e;
+  if (g_skip_mask & 16) return AE_OK;
   if (nv <= 1) e = launch_ln<1>(x, rows, C, eps, gamma, beta, o, st);
   else if (nv <= 2) e = launch_ln<2>(x, rows, C, eps, gamma, beta, o, st);
   else if (nv <= 3) e = launch_ln<3>(x, rows, C, eps, gamma, beta, o, st);

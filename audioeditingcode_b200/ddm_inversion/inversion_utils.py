@@ -34,6 +34,11 @@ DEFAULT_FORWARD_BATCH = int(os.environ.get("AEDIT_FORWARD_BATCH", "50"))
 USE_CUDA_GRAPHS = os.environ.get("AEDIT_CUDA_GRAPH", "1") != "0"
 # Forward / reverse overlap (see _PendingForward): 1 = on (default), 0 = both processes on the caller's stream.
 OVERLAP = os.environ.get("AEDIT_OVERLAP", "1") != "0"
+# Which graph variant the reverse lane replays while forward chunks are still running: "adaptive" (default) = the
+# shared-SM variant (unet.GraphedForward lane 2) until the forward lane's last event has fired, then the solo variant;
+# "solo" / "shared" pin one variant (A/B measurements).  All variants give identical bits.
+REV_VARIANT = os.environ.get("AEDIT_REV_VARIANT", "adaptive")
+REV_LOOKAHEAD = int(os.environ.get("AEDIT_REV_LOOKAHEAD", "2"))
 
 
 class _PendingForward:
@@ -50,7 +55,7 @@ class _PendingForward:
     semantics.  The fast path is taken only if the tensors handed to the reverse process are the ones the forward
     process returned, unmodified (same storage, same torch version counters) — anything else falls back to plain
     stream order.  Results are bit-identical to the non-overlapped execution (same kernels, same batches; tested)."""
-    __slots__ = ("zs_ptr", "zs_ver", "xts_ptr", "xts_ver", "chunks", "eta_key", "N", "done")
+    __slots__ = ("zs_ptr", "zs_ver", "xts_ptr", "xts_ver", "chunks", "eta_key", "N")
 
     def __init__(self):
         self.chunks = []          # (idx_lo, idx_hi, event): rows zs[lo..hi], xts[lo..hi] are final once event fired
@@ -80,18 +85,28 @@ def _lane(model, name: str):
     return st
 
 
-def _chunk_plan(N: int, tb: int, hint: Optional[int]) -> List[Tuple[int, int]]:
+DEFAULT_HEAD_CHUNK = int(os.environ.get("AEDIT_HEAD_CHUNK", "10"))
+
+
+def _chunk_plan(N: int, tb: int, hint: Optional[int], head: Optional[int] = None) -> List[Tuple[int, int]]:
     """(pos0, count) of the forward-process chunks in launch order.  Without a hint: loop order, boundaries at
     multiples of `tb`.  With hint = tstart of the reverse process that follows: the rows idx (= N - pos - 1) are cut
     so that row `hint` is the TOP of a chunk — the reverse process starts from xts[hint] and then consumes zs[hint-1],
     zs[hint-2], ..., so one chunk is all it has to wait for — and the chunks are launched downwards from there, the
-    rows above `hint` last.  A remainder shorter than tb/4 is merged into its neighbour.  The plan depends only on
-    (N, tb, hint), never on whether the lanes overlap, so both modes run identical batches (bit-identical results)."""
+    rows above `hint` last.  The first chunk holds only `head` rows (default AEDIT_HEAD_CHUNK = 10): it is all the
+    reverse process waits for before its first step, and the rows it consumes next are delivered by the following
+    chunk while it works through those.  A remainder shorter than tb/4 is merged into its neighbour.  The plan depends
+    only on (N, tb, hint, head), never on whether the lanes overlap, so both modes run identical batches
+    (bit-identical results)."""
     if tb <= 1 or hint is None or not (0 <= hint <= N):
         return [(p, min(tb, N - p)) for p in range(0, N, tb)]
+    head = DEFAULT_HEAD_CHUNK if head is None else head
     top = min(hint, N - 1)
     down, up = [], []                       # (lo, hi) in idx space
     hi = top
+    if 0 < head < tb and top - head + 1 > 0:
+        down.append((top - head + 1, top))
+        hi = top - head
     while hi >= 0:
         lo = max(0, hi - tb + 1)
         if lo > 0 and lo < max(1, tb // 4):
@@ -436,13 +451,25 @@ def inversion_reverse_process(model: PipelineWrapper,
         if prog_bar:
             it = tqdm(it)
         x_in = torch.empty((rows, *xt.shape[1:]), device=model.device, dtype=torch.float32)
+        # While forward chunks are still running, the steps replay the shared-SM graph variant and are enqueued at
+        # most REV_LOOKAHEAD steps ahead of the device, so that the switch to the solo variant happens (up to that
+        # look-ahead) when the forward lane has actually drained — the host polls its last event.
+        fwd_done = None if pend is None else pend.chunks[-1][2]
+        contended = fwd_done is not None and REV_VARIANT != "solo"
+        in_flight = []
         for k in it:
             t = int(ts_cpu[k])
             pos = N - n + k
             idx = n - k - 1                                                      # inversion_utils.py:222-224
+            if contended and REV_VARIANT == "adaptive":
+                if len(in_flight) >= REV_LOOKAHEAD:
+                    in_flight.pop(0).synchronize()
+                if fwd_done.query():
+                    contended = False
+            variant = 0 if not lanes else (2 if (contended or REV_VARIANT == "shared") else 1)
             x_in.copy_(xt.expand(rows, -1, -1, -1))
             t_in = torch.full((rows,), t, dtype=torch.int64, device=model.device)
-            eps = _unet_eval(model, x_in, t_in, text, slot, cl, slot_key=("rev", P), lane=1 if lanes else 0)
+            eps = _unet_eval(model, x_in, t_in, text, slot, cl, slot_key=("rev", P), lane=variant)
             apply_fix = ((tstart.max() - tstart) > k)
             fa = None
             xT_fix = None
@@ -454,6 +481,10 @@ def inversion_reverse_process(model: PipelineWrapper,
             model.k_cfg_rev_step(pos, float(etas[idx]), eps, eps[1:], P, cfg_map, xt, zs[idx], out, masks=masks,
                                  fix_alpha=fa, xT_fix=xT_fix)
             xt = out
+            if contended and REV_VARIANT == "adaptive":
+                ev = torch.cuda.Event()
+                ev.record(lane)
+                in_flight.append(ev)
             if trace is not None:
                 trace.append(xt.clone())
     if lanes:

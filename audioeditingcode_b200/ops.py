@@ -45,6 +45,10 @@ class CudaOps:
         # programmatic dependent launch: GEMM-only mode (weight prefetch ahead of the dependency wait) measured +2-4 %
         # end to end on B200, all-kernel mode measured slower (profiles/r01_bench_v7_*, r01_bench_v8_*)
         self.lib.ae_set_pdl(int(os.environ.get("AEDIT_PDL", "2")))   # 0 off, 1 all kernels, 2 GEMMs only
+        if "AEDIT_PDL_EXTRA" in os.environ:
+            self.lib.ae_set_pdl_extra(int(os.environ["AEDIT_PDL_EXTRA"]))
+        if "AEDIT_GN_STREAM_MIN_BYTES" in os.environ:
+            self.lib.ae_set_gn_stream_min_bytes(int(os.environ["AEDIT_GN_STREAM_MIN_BYTES"]))
         if "AEDIT_TILE_MODEL" in os.environ:
             self.lib.ae_set_tile_model(int(os.environ["AEDIT_TILE_MODEL"]))
         if "AEDIT_FAST_EPILOGUE" in os.environ:
@@ -72,7 +76,7 @@ class CudaOps:
     def gemm(self, A, W, *, out_f32=None, out_bf16=None, bias=None, rowbias=None, rows_per_group=1, residual=None,
              act=0, alpha=1.0, conv=None, M=None, K=None, force_bn=0, batch=1, strideA=0, strideW=0, stride_out=0,
              stride_res=0, lda=None, ldw=None, force_split=0, ld_out_f32=None, ld_out_bf16=None, force_stages=0,
-             w_dynamic=False, force_csplit=0):
+             w_dynamic=False, force_csplit=0, colstats=None, cs_rows=0):
         """D = alpha*A@W^T (+bias)(+rowbias[row//rows_per_group])(+residual) -> act.  conv=(B,H,W,C,kh,kw,dh,dw)
         turns A (channels-last image) into an implicit-GEMM operand."""
         a = AeGemmArgs()
@@ -116,6 +120,9 @@ class CudaOps:
         a.force_stages = force_stages
         a.w_dynamic = 1 if w_dynamic else 0
         a.force_csplit = force_csplit
+        if colstats is not None:            # GroupNorm statistics of the output, accumulated by the epilogue
+            a.colstats = colstats.data_ptr()
+            a.cs_rows_per_sample = int(cs_rows)
         if batch == 1 and act != 2:
             ws = self._splitk_workspace(A.device)
             a.splitk_ws = ws.data_ptr()
@@ -139,13 +146,20 @@ class CudaOps:
             self._gn_ws[key] = ws
         return ws
 
-    def groupnorm(self, x1, x2, gamma, beta, eps, groups, silu, out, raw_out=None, cat_out=None):
-        """x1 [B,HW,C1] (+ x2 [B,HW,C2] virtually concatenated) fp32 -> out bf16 [B,HW,C1+C2]."""
+    def groupnorm(self, x1, x2, gamma, beta, eps, groups, silu, out, raw_out=None, cat_out=None, cs1=None, cs2=None):
+        """x1 [B,HW,C1] (+ x2 [B,HW,C2] virtually concatenated) fp32 -> out bf16 [B,HW,C1+C2].
+        cs1 / cs2: int64 [B, C_i, 2] column statistics accumulated by the GEMMs that produced x1 / x2 (gemm(colstats=));
+        with them the statistics pass over the tensor is skipped (one launch instead of two)."""
         B = x1.shape[0]
         C1 = x1.shape[-1]
         HW = x1.numel() // (B * C1)
         C2 = 0 if x2 is None else x2.shape[-1]
         ws = self._gn_workspace(B, groups, x1.device)
+        if cs1 is not None and (x2 is None or cs2 is not None):
+            check(self.lib.ae_groupnorm_cs(_p(x1), C1, _p(cs1), _p(x2), C2, _p(cs2), B, HW, groups, eps, _p(gamma),
+                                           _p(beta), int(silu), _p(out), _p(raw_out), _p(cat_out), _p(ws), _stream()),
+                  "ae_groupnorm_cs")
+            return
         check(self.lib.ae_groupnorm(_p(x1), C1, _p(x2), C2, B, HW, groups, eps, _p(gamma), _p(beta), int(silu), _p(out),
                                     _p(raw_out), _p(cat_out), _p(ws), _stream()), "ae_groupnorm")
 

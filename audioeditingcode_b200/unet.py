@@ -17,6 +17,7 @@ Weights arrive under diffusers state-dict names (what the reference's checkpoint
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, List, Optional, Sequence
 
 import torch
@@ -44,17 +45,25 @@ class GraphedForward:
     (and their TMA descriptors, encoded once at capture) replay with a single host call — the launch-latency
     answer SURVEY.md §7 'hard parts' asks for.  Inputs / output live in static buffers."""
 
-    def __init__(self, engine: "UNetEngine", B, H, W, text, slot_map, class_labels, lane: int = 0):
+    def __init__(self, engine: "UNetEngine", B, H, W, text, slot_map, class_labels, lane: int = 0,
+                 capture_stream=None):
         dev = engine.device
-        # lane 1 = the reverse-process lane (ddm_inversion/inversion_utils._PendingForward): its graph may replay
+        # lane >= 1 = the reverse-process lane (ddm_inversion/inversion_utils._PendingForward): its graph may replay
         # while a forward-process graph is running on another stream, so it owns its workspaces (second CudaOps
         # instance: split-K partial tiles, GroupNorm partials / tickets) and its kernel nodes carry the device's
         # highest launch priority (the sub-wave kernels of the sequential chain take the next free SM slots).
+        # lane 2 additionally sizes the GEMM operand rings to fit beside a resident forward-process CTA
+        # (ae_set_shared_sm); lane 1 is the variant for the steps that have the machine to themselves.
         self.lane = lane
-        self.x = torch.zeros(B, engine.cfg.in_channels, H, W, device=dev, dtype=F32)
-        self.t = torch.zeros(B, device=dev, dtype=torch.int64)
-        self.slot = None if slot_map is None else slot_map.to(dev, torch.int32).clone()
-        self.cl = None if class_labels is None else class_labels.to(dev, F32).clone()
+        with torch.inference_mode(False):   # static buffers outlive the caller's inference_mode scope (copy_ targets)
+            self.x = torch.zeros(B, engine.cfg.in_channels, H, W, device=dev, dtype=F32)
+            self.t = torch.zeros(B, device=dev, dtype=torch.int64)
+            self.slot = None if slot_map is None else torch.empty(slot_map.shape, device=dev, dtype=torch.int32)
+            self.cl = None if class_labels is None else torch.empty(class_labels.shape, device=dev, dtype=F32)
+        if self.slot is not None:
+            self.slot.copy_(slot_map)
+        if self.cl is not None:
+            self.cl.copy_(class_labels)
         self.text = text
         # Small batches are launch-latency bound (each kernel is a fraction of a wave): with AEDIT_DUAL_STREAM=1 the
         # batch is cut in two halves captured on two forked streams of the same graph, so the two dependency chains
@@ -63,12 +72,15 @@ class GraphedForward:
         if self.dual:
             engine.ops.lib.ae_set_gn_fused(0)     # two concurrent resident GroupNorm grids could starve each other
         cur = torch.cuda.current_stream()
-        side = torch.cuda.Stream(priority=-1 if lane == 1 else 0)
+        side = capture_stream if capture_stream is not None else torch.cuda.Stream(priority=-1 if lane >= 1 else 0)
         self._side2 = torch.cuda.Stream() if self.dual else None
         main_ops = engine.ops
-        if lane == 1:
+        if lane >= 1:
+            import os
             engine.ops = engine.ops_b()
-            engine.ops.lib.ae_set_launch_priority(engine.ops.lib.ae_greatest_priority())
+            if os.environ.get("AEDIT_REV_PRIORITY", "1") != "0":
+                engine.ops.lib.ae_set_launch_priority(engine.ops.lib.ae_greatest_priority())
+            engine.ops.lib.ae_set_shared_sm(1 if lane == 2 else 0)
         try:
             side.wait_stream(cur)
             with torch.cuda.stream(side):
@@ -80,8 +92,9 @@ class GraphedForward:
             with torch.cuda.graph(self.graph, stream=side):
                 self.out = self._run(engine)
         finally:
-            if lane == 1:
+            if lane >= 1:
                 engine.ops.lib.ae_set_launch_priority(0)
+                engine.ops.lib.ae_set_shared_sm(0)
             engine.ops = main_ops
 
     def _run(self, engine):
@@ -134,6 +147,53 @@ class UNetEngine:
         self.dual_stream = os.environ.get("AEDIT_DUAL_STREAM", "0") != "0"
         self.dual_stream_max_b = int(os.environ.get("AEDIT_DUAL_STREAM_MAX_B", "4"))
         self._ops_b = None
+        # GroupNorm statistics from the producing GEMM's epilogue (ae_gemm_args.colstats): every GEMM whose fp32 output
+        # feeds a GroupNorm accumulates per-(sample, channel) sums into a slice of one arena that is zeroed once per
+        # evaluation; ops.groupnorm then runs a single launch.  AEDIT_GN_COLSTATS=0 restores the statistics kernel.
+        self.gn_colstats = os.environ.get("AEDIT_GN_COLSTATS", "1") != "0" and hasattr(ops, "lib")
+        self._cs_channels = sum(int(t.shape[0]) for n, t in weights.items()
+                                if n.endswith((".conv1.bias", ".conv2.bias", ".proj_out.bias", "conv_in.bias",
+                                               ".downsamplers.0.conv.bias", ".upsamplers.0.conv.bias")))
+        self._cs_arena = None
+        self._cs_off = 0
+        self._cs_map: Dict[int, torch.Tensor] = {}
+
+    # ------------------------------------------------------------------------------------------ GroupNorm statistics
+    def _cs_begin(self, B: int):
+        self._cs_map = {}
+        self._cs_off = 0
+        self._cs_arena = (torch.zeros(B * self._cs_channels * 2, dtype=torch.int64, device=self.device)
+                          if self.gn_colstats else None)
+
+    def _cs_take(self, out: torch.Tensor, B: int, rows_per_sample: int):
+        """kwargs for ops.gemm that make it accumulate the column statistics of `out` ([B*rows, N] fp32), or {}."""
+        N = out.shape[-1]
+        self._cs_map.pop(out.data_ptr(), None)      # a recycled address must not inherit an older tensor's entry
+        if self._cs_arena is None or rows_per_sample % 32 != 0 or N % 4 != 0:
+            return {}
+        n = B * N * 2
+        if self._cs_off + n > self._cs_arena.numel():
+            return {}
+        cs = self._cs_arena[self._cs_off:self._cs_off + n]
+        self._cs_off += n
+        self._cs_map[out.data_ptr()] = cs
+        return dict(colstats=cs, cs_rows=rows_per_sample)
+
+    def _cs_forget(self, *tensors):
+        """Tensors that were NOT produced by a statistics-accumulating GEMM (tap / replace paths)."""
+        for t in tensors:
+            if t is not None:
+                self._cs_map.pop(t.data_ptr(), None)
+
+    def _cs_of(self, x: Optional[torch.Tensor]):
+        return None if x is None else self._cs_map.get(x.data_ptr())
+
+    def _groupnorm(self, x1, x2, gamma, beta, eps, groups, silu, out, raw_out=None):
+        cs1, cs2 = self._cs_of(x1), self._cs_of(x2)
+        if cs1 is not None and (x2 is None or cs2 is not None):
+            self.ops.groupnorm(x1, x2, gamma, beta, eps, groups, silu, out, raw_out=raw_out, cs1=cs1, cs2=cs2)
+        else:
+            self.ops.groupnorm(x1, x2, gamma, beta, eps, groups, silu, out, raw_out=raw_out)
 
     def ops_b(self):
         """Second ops instance (own split-K / GroupNorm workspaces) for the forked chain of a dual-stream graph."""
@@ -249,20 +309,21 @@ class UNetEngine:
         return tc
 
     # ------------------------------------------------------------------------------------------ blocks
-    def _conv3x3(self, a_bf16, B, H, W, Cin, name, out, rowbias=None, rows_per_group=1, residual=None):
-        """a_bf16: [B,H,W,Cin] channels-last operand; out fp32 [B*H*W, Cout]."""
+    def _conv3x3(self, a_bf16, B, H, W, Cin, name, out, rowbias=None, rows_per_group=1, residual=None, stats=False):
+        """a_bf16: [B,H,W,Cin] channels-last operand; out fp32 [B*H*W, Cout].  stats: the output feeds a GroupNorm."""
         ops = self.ops
         Wt, bias = self.w[name + ".weight"], self.w[name + ".bias"]
+        cs = self._cs_take(out, B, H * W) if stats else {}
         if W >= self.min_implicit_w and ops.conv_supported(B, H, W, Cin):
             ops.gemm(a_bf16, Wt, out_f32=out, bias=bias, rowbias=rowbias, rows_per_group=rows_per_group,
-                     residual=residual, conv=(B, H, W, Cin, 3, 3, 1, 1))
+                     residual=residual, conv=(B, H, W, Cin, 3, 3, 1, 1), **cs)
         else:
             K = 9 * Cin
             ld = (K + 7) // 8 * 8
             col = ops.empty((B * H * W, ld), self.adt, self.device)
             ops.im2col(a_bf16, B, H, W, Cin, 3, 3, 1, 1, 1, 1, H, W, col)
             ops.gemm(col, Wt, out_f32=out, bias=bias, rowbias=rowbias, rows_per_group=rows_per_group,
-                     residual=residual, K=K)
+                     residual=residual, K=K, **cs)
 
     def _resnet(self, x1, x2, B, H, W, p, temb_all):
         ops, cfg = self.ops, self.cfg
@@ -274,21 +335,22 @@ class UNetEngine:
         has_sc = (p + ".conv_shortcut.weight") in self.w
         a1 = ops.empty((B, H, W, Cin), self.adt, self.device)
         raw = ops.empty((M, Cin), self.adt, self.device) if has_sc else None
-        ops.groupnorm(x1, x2, self.w[p + ".norm1.weight"], self.w[p + ".norm1.bias"], cfg.norm_eps,
-                      cfg.norm_num_groups, True, a1, raw_out=raw)
+        self._groupnorm(x1, x2, self.w[p + ".norm1.weight"], self.w[p + ".norm1.bias"], cfg.norm_eps,
+                        cfg.norm_num_groups, True, a1, raw_out=raw)
         h = ops.empty((M, Cout), F32, self.device)
         off = self.temb_off[p]
-        self._conv3x3(a1, B, H, W, Cin, p + ".conv1", h, rowbias=temb_all[:, off:off + Cout], rows_per_group=H * W)
+        self._conv3x3(a1, B, H, W, Cin, p + ".conv1", h, rowbias=temb_all[:, off:off + Cout], rows_per_group=H * W,
+                      stats=True)
         a2 = ops.empty((B, H, W, Cout), self.adt, self.device)
-        ops.groupnorm(h.view(B, H * W, Cout), None, self.w[p + ".norm2.weight"], self.w[p + ".norm2.bias"],
-                      cfg.norm_eps, cfg.norm_num_groups, True, a2)
+        self._groupnorm(h.view(B, H * W, Cout), None, self.w[p + ".norm2.weight"], self.w[p + ".norm2.bias"],
+                        cfg.norm_eps, cfg.norm_num_groups, True, a2)
         if has_sc:
             res = ops.empty((M, Cout), F32, self.device)
             ops.gemm(raw, self.w[p + ".conv_shortcut.weight"], out_f32=res, bias=self.w[p + ".conv_shortcut.bias"])
         else:
             res = x1.reshape(M, Cout)
         out = ops.empty((M, Cout), F32, self.device)
-        self._conv3x3(a2, B, H, W, Cout, p + ".conv2", out, residual=res)
+        self._conv3x3(a2, B, H, W, Cout, p + ".conv2", out, residual=res, stats=True)
         return out.view(B, H * W, Cout)
 
     def _attention(self, q, k, v, out, heads, B, Tq, Tk, ld_q, bs_q, ld_k, bs_k, ld_v, bs_v, kv_map=None, bias=None):
@@ -302,7 +364,7 @@ class UNetEngine:
         T = H * W
         M = B * T
         g = ops.empty((M, C), self.adt, self.device)
-        ops.groupnorm(x, None, self.w[p + ".norm.weight"], self.w[p + ".norm.bias"], 1e-6, cfg.norm_num_groups, False, g)
+        self._groupnorm(x, None, self.w[p + ".norm.weight"], self.w[p + ".norm.bias"], 1e-6, cfg.norm_num_groups, False, g)
         hs = ops.empty((M, C), F32, self.device)
         ops.gemm(g, self.w[p + ".proj_in.weight"], out_f32=hs, bias=self.w[p + ".proj_in.bias"])
         hs_b = None
@@ -347,7 +409,7 @@ class UNetEngine:
                      bias=self.w[q + ".ff.net.2.bias"], residual=hs)
         out = ops.empty((M, C), F32, self.device)
         ops.gemm(hs_b, self.w[p + ".proj_out.weight"], out_f32=out, bias=self.w[p + ".proj_out.bias"],
-                 residual=x.reshape(M, C))
+                 residual=x.reshape(M, C), **self._cs_take(out, B, T))
         return out.view(B, T, C)
 
     def _site(self, x, B, H, W, base, idx0, level, text, slot_map):
@@ -379,6 +441,7 @@ class UNetEngine:
         nlev = len(ch)
         ted = 4 * ch[0]
         temb_ch = self.w["__temb_all.weight"].shape[1]
+        self._cs_begin(B)
 
         # ---- time / class embedding (models.py:231-256); silu(emb) is the only consumer of emb
         tproj = ops.empty((B, ch[0]), self.adt, dev)
@@ -408,7 +471,8 @@ class UNetEngine:
         col = ops.empty((B * H * W, (K0 + 7) // 8 * 8), self.adt, dev)
         ops.im2col(x_nhwc, B, H, W, Cin, 3, 3, 1, 1, 1, 1, H, W, col)
         h = ops.empty((B * H * W, ch[0]), F32, dev)
-        ops.gemm(col, self.w["conv_in.weight"], out_f32=h, bias=self.w["conv_in.bias"], K=K0)
+        ops.gemm(col, self.w["conv_in.weight"], out_f32=h, bias=self.w["conv_in.bias"], K=K0,
+                 **self._cs_take(h, B, H * W))
         h = h.view(B, H * W, ch[0])
 
         sizes = [(H, W)]
@@ -427,7 +491,7 @@ class UNetEngine:
                 ops.im2col(h, B, hh, ww, C, 3, 3, 2, 1, 1, 1, ho, wo, col)
                 d = ops.empty((B * ho * wo, C), F32, dev)
                 p = f"down_blocks.{i}.downsamplers.0.conv"
-                ops.gemm(col, self.w[p + ".weight"], out_f32=d, bias=self.w[p + ".bias"])
+                ops.gemm(col, self.w[p + ".weight"], out_f32=d, bias=self.w[p + ".bias"], **self._cs_take(d, B, ho * wo))
                 hh, ww = ho, wo
                 sizes.append((hh, ww))
                 h = d.view(B, hh * ww, C)
@@ -445,6 +509,7 @@ class UNetEngine:
             rep = ops.empty((B, hh, ww, Cm), F32, dev)
             ops.nchw_to_nhwc(replace_h_space.to(dev, F32).expand(B, -1, -1, -1).contiguous(), out_f32=rep)
             h = rep.view(B, hh * ww, Cm)
+            self._cs_forget(h)
         elif want_taps:
             h_space = ops.empty((B, Cm, hh, ww), F32, dev)
             ops.nhwc_to_nchw(h, B, Cm, hh, ww, h_space)
@@ -454,6 +519,7 @@ class UNetEngine:
             h2 = ops.empty((B, hh * ww, Cm), F32, dev)
             ops.add(h, add.view(B, hh * ww, Cm), h2)
             h = h2
+            self._cs_forget(h)
 
         extracted = {}
         n_up = cfg.layers_per_block + 1
@@ -464,10 +530,12 @@ class UNetEngine:
             skips = skips[:-n_up]
             if replace_skip_conns is not None and replace_skip_conns.get(i):
                 res = [self._from_nchw(t, B) for t in replace_skip_conns.get(i)]
+                self._cs_forget(*res)
             if zero_out_resconns is not None:
                 if (type(zero_out_resconns) is int and i >= (zero_out_resconns - 1)) or \
                         (type(zero_out_resconns) is list and i in zero_out_resconns):
                     res = [torch.zeros_like(t) for t in res]
+                    self._cs_forget(*res)
             if want_taps:
                 extracted[i] = [self._to_nchw(t, B, hh, ww) for t in res]
             res = list(res)
@@ -481,13 +549,13 @@ class UNetEngine:
                 up = ops.empty((B, ho, wo, C), self.adt, dev)
                 ops.upsample_nearest(h, B, hh, ww, C, ho, wo, up)
                 u = ops.empty((B * ho * wo, C), F32, dev)
-                self._conv3x3(up, B, ho, wo, C, f"up_blocks.{i}.upsamplers.0.conv", u)
+                self._conv3x3(up, B, ho, wo, C, f"up_blocks.{i}.upsamplers.0.conv", u, stats=True)
                 h = u.view(B, ho * wo, C)
 
         # ---- conv_norm_out -> SiLU -> conv_out (models.py:385-388)
         a = ops.empty((B, H, W, ch[0]), self.adt, dev)
-        ops.groupnorm(h, None, self.w["conv_norm_out.weight"], self.w["conv_norm_out.bias"], cfg.norm_eps,
-                      cfg.norm_num_groups, True, a)
+        self._groupnorm(h, None, self.w["conv_norm_out.weight"], self.w["conv_norm_out.bias"], cfg.norm_eps,
+                        cfg.norm_num_groups, True, a)
         Co = cfg.out_channels
         o = ops.empty((B * H * W, Co), F32, dev)
         self._conv3x3(a, B, H, W, ch[0], "conv_out", o)

@@ -47,6 +47,19 @@ void ae_set_pdl(int mode); /* 0 off (default), 1 every kernel, 2 GEMM kernels on
  * so that it can run CONCURRENTLY with the throughput-bound forward-process chunks (inversion_utils.py:69-131) of
  * the same clip and still get the next free SM slots. */
 void ae_set_launch_priority(int prio);
+/* PDL mode 2 extension: kernel families that are also launched with the PDL attribute (1 GroupNorm statistics,
+ * 2 GroupNorm apply, 4 LayerNorm, 8 attention).  Default 0. */
+void ae_set_pdl_extra(int mask);
+/* GroupNorm tensors of at least this many bytes (default 8 MiB) take the streaming apply kernel (same bits). */
+void ae_set_gn_stream_min_bytes(int64_t bytes);
+/* DIAGNOSTIC ONLY: drop the launches of kernel families (1 GEMM, 2 split-K reduce, 4 GroupNorm statistics,
+ * 8 GroupNorm apply, 16 LayerNorm, 32 attention) to measure a family's marginal cost inside a captured graph
+ * (tools/kernel_share.py).  Outputs are meaningless while the mask is non-zero. */
+void ae_set_skip_mask(int mask);
+/* 1: the GEMMs launched (captured) from now on will share the SMs with a throughput-bound grid of another stream;
+ * sub-wave grids then take the deepest operand ring that fits beside one resident ~100 KB CTA instead of the 6-stage
+ * ring.  0 (default): sub-wave grids own their SM.  Results are bit-identical in both modes. */
+void ae_set_shared_sm(int on);
 /* the current device's highest stream / launch priority (numerically lowest value; 0 when there is one level) */
 int ae_greatest_priority(void);
 
@@ -183,6 +196,14 @@ typedef struct {
   int32_t w_dynamic;    /* 1 if W is written by a preceding kernel on the stream (e.g. K or V^T of an unfused attention):
                            disables the early W prefetch that otherwise overlaps the previous kernel's tail */
   int32_t force_stages; /* 0 auto (deep 6-stage ring for grids <= 160 CTAs, else 3 stages x 2-3 CTAs/SM), 3 or 6 */
+  /* GroupNorm statistics of the OUTPUT, produced by the epilogue (or the split-K reduce) instead of a separate pass
+   * over the tensor (the GroupNorm that follows — openaimodel.py:213-216,238-239 — needs per-sample sums over
+   * positions): colstats[(sample*N + n)*2 + {0,1}] += fixed-point (sum * 2^28, sum of squares * 2^24) of column n over
+   * the rows of the sample, sample = row / cs_rows_per_sample.  int64 accumulators, ZEROED by the caller; integer
+   * atomics make the totals independent of CTA arrival order.  Needs batch == 1, act != 2, fp32 output, N % 4 == 0,
+   * cs_rows_per_sample % 32 == 0.  Consumed by ae_groupnorm_cs.  NULL = off. */
+  int64_t* colstats;
+  int32_t cs_rows_per_sample;
 } ae_gemm_args;
 int ae_gemm(const ae_gemm_args*, ae_stream stream);
 /* 1 if the implicit-conv fast path supports this geometry (else use ae_im2col + plain GEMM) */
@@ -203,6 +224,12 @@ int64_t ae_groupnorm_workspace_bytes(int B, int groups);
 int ae_groupnorm(const float* x1, int C1, const float* x2, int C2, int B, int64_t HW, int groups, float eps,
                  const float* gamma, const float* beta, int silu, void* out_bf16, void* raw_out_bf16,
                  float* cat_out_f32, float* workspace, ae_stream stream);
+
+/* Same, with the statistics taken from the fixed-point column sums that the GEMMs producing x1 / x2 accumulated in
+ * their epilogues (ae_gemm_args.colstats, layout [B, C_i, 2] int64): one launch, one pass over the tensor. */
+int ae_groupnorm_cs(const float* x1, int C1, const int64_t* colstats1, const float* x2, int C2, const int64_t* colstats2,
+                    int B, int64_t HW, int groups, float eps, const float* gamma, const float* beta, int silu,
+                    void* out_bf16, void* raw_out_bf16, float* cat_out_f32, float* workspace, ae_stream stream);
 
 /* LayerNorm over the last dim of fp32 [rows, C] -> bf16 (attention.py:393-395, eps 1e-5) */
 int ae_layernorm(const float* x, int64_t rows, int C, float eps, const float* gamma, const float* beta, void* out_bf16,

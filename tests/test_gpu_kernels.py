@@ -106,6 +106,70 @@ def test_gemm_splitk(ops, M, N, K, S):
     assert torch.equal(o32, o_b) and torch.equal(o16, o_h)
 
 
+@pytest.mark.parametrize("M,N,K,rows,S,bn", [(128, 960, 960, 64, 1, 0), (128, 960, 8640, 64, 0, 0), (512, 576, 2304, 256, 4, 0),
+                                             (2048, 384, 384, 1024, 1, 32), (8192, 192, 1728, 4096, 1, 64),
+                                             (8192, 192, 1728, 4096, 1, 128), (256, 200, 512, 32, 3, 0),
+                                             (96, 960, 960, 32, 1, 0), (6400, 384, 384, 64, 1, 0)])
+def test_gemm_column_statistics(ops, M, N, K, rows, S, bn):
+    """ae_gemm_args.colstats: fixed-point per-(sample, column) sum / sum of squares of the final fp32 output, from the
+    staged epilogue (S == 1) or the split-K reduce kernel; the output bits are those of the plain call; accumulating
+    twice doubles the integers exactly (order-independent integer atomics => deterministic)."""
+    A = rnd((M, K), 1, dtype=BF)
+    W = rnd((N, K), 2, 1 / math.sqrt(K), dtype=BF)
+    bias, res = rnd((N,), 3), rnd((M, N), 4)
+    rowbias = rnd((M // rows, N), 5)
+    o_ref = torch.empty(M, N, device="cuda")
+    ops.gemm(A, W, out_f32=o_ref, bias=bias, rowbias=rowbias, rows_per_group=rows, residual=res, force_split=S,
+             force_bn=bn)
+    nb = M // rows
+    cs = torch.zeros(nb, N, 2, dtype=torch.int64, device="cuda")
+    o = torch.empty_like(o_ref)
+    ops.gemm(A, W, out_f32=o, bias=bias, rowbias=rowbias, rows_per_group=rows, residual=res, force_split=S, force_bn=bn,
+             colstats=cs, cs_rows=rows)
+    assert torch.equal(o, o_ref)
+    x = o.double().view(nb, rows, N)
+    su = cs[..., 0].double() / 2 ** 28
+    sq = cs[..., 1].double() / 2 ** 24
+    assert (su - x.sum(1)).abs().max().item() < 1e-3 * max(1.0, x.sum(1).abs().max().item())
+    assert ((sq - (x * x).sum(1)).abs() / (x * x).sum(1)).max().item() < 1e-5
+    cs2 = cs.clone()
+    ops.gemm(A, W, out_f32=o, bias=bias, rowbias=rowbias, rows_per_group=rows, residual=res, force_split=S, force_bn=bn,
+             colstats=cs2, cs_rows=rows)
+    assert torch.equal(cs2, 2 * cs)
+
+
+@pytest.mark.parametrize("B,HW,C1,C2,silu,stream", [(2, 4096, 192, 0, True, 0), (2, 1024, 576, 384, True, 0),
+                                                    (2, 64, 960, 960, False, 0), (3, 256, 960, 576, True, 1),
+                                                    (5, 1024, 384, 0, True, 1)])
+def test_groupnorm_from_column_statistics(ops, B, HW, C1, C2, silu, stream):
+    """ae_groupnorm_cs (statistics from the producers' column sums, one launch) agrees with ae_groupnorm (statistics
+    pass over the tensor) to fp32 rounding of mean / rstd, in both apply kernels."""
+    x1 = rnd((B, HW, C1), 1) + 0.5
+    x2 = rnd((B, HW, C2), 2, 2.0) if C2 else None
+    C = C1 + C2
+    gamma, beta = rnd((C,), 3) * 0.1 + 1, rnd((C,), 4) * 0.1
+
+    def colsums(x):
+        xd = x.double()
+        return torch.stack([(xd.sum(1) * 2 ** 28).round(), ((xd * xd).sum(1) * 2 ** 24).round()], -1).to(torch.int64).contiguous()
+    cs1 = colsums(x1)
+    cs2 = colsums(x2) if C2 else None
+    ops.lib.ae_set_gn_stream_min_bytes(0 if stream else 1 << 60)
+    try:
+        ref = torch.zeros(B, HW, C, device="cuda", dtype=BF)
+        ops.groupnorm(x1, x2, gamma, beta, 1e-5, 32, silu, ref)
+        out = torch.zeros_like(ref)
+        raw = torch.zeros_like(ref)
+        ops.groupnorm(x1, x2, gamma, beta, 1e-5, 32, silu, out, raw_out=raw, cs1=cs1, cs2=cs2)
+    finally:
+        ops.lib.ae_set_gn_stream_min_bytes(8 << 20)
+    d = (out.float() - ref.float()).abs()
+    # identical up to a bf16 ulp where the fp32 mean / rstd differ in their last bit
+    assert (d > 0).float().mean().item() < 0.02 and d.max().item() <= 0.04
+    x = x1 if x2 is None else torch.cat([x1, x2], -1)
+    assert torch.equal(raw, x.to(BF))
+
+
 @pytest.mark.parametrize("M,N,K,CS", [(128, 960, 960, 2), (128, 960, 960, 4), (128, 960, 8640, 8), (512, 576, 576, 2),
                                       (100, 200, 1000, 4), (2048, 384, 384, 2), (128, 7680, 960, 0), (256, 64, 4096, 8)])
 def test_gemm_cluster_splitk(ops, M, N, K, CS):
@@ -260,6 +324,33 @@ def test_groupnorm_fused_batch_independent(ops):
     o2b = torch.empty_like(o2)
     ops.groupnorm(y, None, gamma, beta, 1e-5, 32, True, o2b)
     assert torch.equal(o2b[0], o2[0])
+
+
+@pytest.mark.parametrize("B,HW,C1,C2,silu", [(3, 1000, 192, 0, True), (2, 4096, 384, 192, True), (5, 64, 960, 960, False),
+                                             (2, 256, 960, 576, True)])
+def test_groupnorm_stream_apply_same_bits(ops, B, HW, C1, C2, silu):
+    """The streaming apply kernel (large tensors: forward-process chunks) and the one-round apply kernel (small
+    tensors: reverse process) produce identical bits, including the raw bf16 copy and the concatenated input."""
+    x1 = rnd((B, HW, C1), 1) + 0.5
+    x2 = rnd((B, HW, C2), 2, 2.0) if C2 else None
+    C = C1 + C2
+    gamma, beta = rnd((C,), 3) * 0.1 + 1, rnd((C,), 4) * 0.1
+    outs = []
+    try:
+        for min_bytes in (1 << 60, 0):
+            ops.lib.ae_set_gn_stream_min_bytes(min_bytes)
+            out = torch.zeros(B, HW, C, device="cuda", dtype=BF)
+            raw = torch.zeros(B, HW, C, device="cuda", dtype=BF)
+            ops.groupnorm(x1, x2, gamma, beta, 1e-5, 32, silu, out, raw_out=raw)
+            outs.append((out, raw))
+    finally:
+        ops.lib.ae_set_gn_stream_min_bytes(8 << 20)
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    x = x1 if x2 is None else torch.cat([x1, x2], -1)
+    ref = F.group_norm(x.permute(0, 2, 1), 32, gamma, beta, 1e-5).permute(0, 2, 1)
+    if silu:
+        ref = F.silu(ref)
+    assert (outs[1][0].float() - ref).abs().max().item() < 0.05
 
 
 def _groupnorm_case(ops, B, HW, C1, C2, G, silu):

@@ -108,8 +108,10 @@ def test_forward_chunk_plan():
             below = [r for r in rows if r[1] <= top]
             assert rows[:len(below)] == below and below == sorted(below, key=lambda r: -r[1])
             assert all(c <= tb + max(1, tb // 4) for _, c in plan)
-    assert _chunk_plan(200, 50, 100) == [(99, 50), (149, 51), (49, 50), (0, 49)]
-    assert _chunk_plan(200, 50, 200) == [(0, 50), (50, 50), (100, 50), (150, 50)]
+    assert _chunk_plan(200, 50, 100, head=0) == [(99, 50), (149, 51), (49, 50), (0, 49)]
+    assert _chunk_plan(200, 50, 100, head=10) == [(99, 10), (109, 50), (159, 41), (49, 50), (0, 49)]
+    assert _chunk_plan(200, 50, 200, head=0) == [(0, 50), (50, 50), (100, 50), (150, 50)]
+    assert _chunk_plan(200, 50, 200) == [(0, 10), (10, 50), (60, 50), (110, 50), (160, 40)]
 
 
 def test_pending_forward_guard():
