@@ -88,7 +88,10 @@ struct SmemLayout {
   static constexpr int kStageBytes = kATileBytes + kBTileBytes;
   static constexpr int kBarBytes = 128;
   static constexpr int kEpiBytes = 2 * BN * 4;  // bias / row-bias values of the tile (row-per-thread epilogue)
-  static constexpr int kTotal = STAGES * kStageBytes + kBarBytes + kEpiBytes + 1024;  // +1024 manual alignment slack
+  // the staged epilogue transposes the four 32-row strips through the (then idle) ring: pitch BN+4 floats
+  static constexpr int kStripBytes = 4 * 32 * (BN + 4) * 4;
+  static constexpr int kRingBytes = STAGES * kStageBytes > kStripBytes ? STAGES * kStageBytes : ((kStripBytes + 1023) / 1024) * 1024;
+  static constexpr int kTotal = kRingBytes + kBarBytes + kEpiBytes + 1024;  // +1024 manual alignment slack
 };
 
 __device__ __forceinline__ float gelu_erf_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
@@ -211,7 +214,8 @@ __device__ __forceinline__ void epilogue_chunk(const GemmDev& p, float (&acc)[32
 // its instructions are fetched cold — a 32x unrolled body (v10a) cost +10 us per launch in instruction-cache misses.
 template <int BN>
 __device__ __forceinline__ void epilogue_strip(const GemmDev& p, float* strip, uint32_t tmem_strip, uint64_t* tmem_full_bar,
-                                               long long m_base, int n0, int zo, int lane) {
+                                               long long m_base, int n0, int zo, int lane, uint32_t parity = 0,
+                                               uint64_t* tmem_release_bar = nullptr) {
   constexpr int PITCH = BN + 4;
   constexpr int LPR = BN / 4;      // lanes per output row
   constexpr int RPI = 32 / LPR;    // rows per iteration
@@ -255,8 +259,9 @@ __device__ __forceinline__ void epilogue_strip(const GemmDev& p, float* strip, u
                                              : make_float4(0.f, 0.f, 0.f, 0.f);
   }
 
-  ptx::mbar_wait(tmem_full_bar, 0);
+  ptx::mbar_wait(tmem_full_bar, parity);
   ptx::tcgen05_fence_after();
+  __syncwarp();   // persistent kernel: every lane is done reading the previous tile's strip
 #pragma unroll 1
   for (int c = 0; c < BN / 32; ++c) {
     uint32_t v[32];
@@ -269,6 +274,11 @@ __device__ __forceinline__ void epilogue_strip(const GemmDev& p, float* strip, u
                            __uint_as_float(v[4 * j + 2]) * p.alpha, __uint_as_float(v[4 * j + 3]) * p.alpha);
   }
   __syncwarp();
+  if (tmem_release_bar) {
+    // persistent kernel: the accumulator buffer is in shared memory now, hand it back to the MMA warp
+    ptx::tcgen05_fence_before();
+    if (lane == 0) ptx::mbar_arrive(tmem_release_bar);
+  }
   const unsigned cs_mask = __ballot_sync(0xffffffffu, col_ok);   // lanes that stay (whole column classes)
   if (!col_ok) return;
   if (geglu) {
@@ -376,11 +386,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
   uint8_t* sA = smem;
   uint8_t* sB = smem + STAGES * kATileBytes;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * L::kStageBytes);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kRingBytes);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full_bar = empty_bar + STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
-  float* s_bias = reinterpret_cast<float*>(smem + STAGES * L::kStageBytes + L::kBarBytes);
+  float* s_bias = reinterpret_cast<float*>(smem + L::kRingBytes + L::kBarBytes);
   float* s_rowb = s_bias + BN;
 
   const int warp = threadIdx.x >> 5;
@@ -585,6 +595,224 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
     }
     cluster_sync_all();  // nobody leaves while a peer may still read its partial tile
+  }
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tcgen05_fence_after();
+    ptx::tmem_dealloc<TMEM_COLS>(tmem_base);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Persistent variant for multi-wave grids (forward-process chunks): one CTA per SM walks the output tiles
+// t = blockIdx.x, blockIdx.x + gridDim.x, ... (N tiles fastest, so the CTAs that share an A tile run at the same
+// time).  The accumulator is double-buffered in TMEM (2 x BN columns): the MMA warp starts tile i+1 while the epilogue
+// warps drain tile i, the TMA ring keeps streaming across tile boundaries, and the per-CTA fixed costs (launch, TMEM
+// allocation, barrier init, pipeline ramp) are paid once per SM instead of once per tile.  Same arithmetic per
+// output element as gemm_tcgen05_kernel (same K order, same epilogue code) -> same bits.
+template <int BN, int STAGES, bool STAGED>
+struct PersistLayout {
+  static constexpr int kBTileBytes = BN * BK * 2;
+  static constexpr int kStageBytes = kATileBytes + kBTileBytes;
+  static constexpr int kRingBytes = STAGES * kStageBytes;
+  static constexpr int kStripBytes = STAGED ? ((4 * 32 * (BN + 4) * 4 + 1023) / 1024) * 1024 : 0;
+  static constexpr int kBarBytes = 256;
+  static constexpr int kEpiBytes = 2 * 2 * BN * 4;   // bias / row-bias values, one set per accumulator buffer
+  static constexpr int kTotal = kRingBytes + kStripBytes + kBarBytes + kEpiBytes + 1024;
+};
+
+template <int BN, int STAGES, bool STAGED>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmDev p,
+                       int tiles_n, int n_tiles) {
+  using L = PersistLayout<BN, STAGES, STAGED>;
+  constexpr uint32_t TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = ptx::smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES * kATileBytes;
+  float* strips = reinterpret_cast<float*>(smem + L::kRingBytes);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kRingBytes + L::kStripBytes);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;     // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;     // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  float* s_bias = reinterpret_cast<float*>(smem + L::kRingBytes + L::kStripBytes + L::kBarBytes);   // [2][BN]
+  float* s_rowb = s_bias + 2 * BN;                                                                  // [2][BN]
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int nkb = p.num_kblocks;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tensormap(&tmA);
+    ptx::prefetch_tensormap(&tmB);
+    for (int s = 0; s < STAGES; ++s) {
+      ptx::mbar_init(&full_bar[s], 1);
+      ptx::mbar_init(&empty_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      ptx::mbar_init(&tmem_full_bar[s], 1);
+      ptx::mbar_init(&tmem_empty_bar[s], 4);   // one arrival per epilogue warp
+    }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 1) ptx::tmem_alloc<TMEM_COLS>(tmem_slot);
+  ptx::tcgen05_fence_before();
+  __syncthreads();
+  ptx::tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (ptx::elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      long long it = 0;     // K blocks issued so far (over all tiles of this CTA)
+      int npre = 0;
+      {
+        // first ring of W tiles of the first tile: weights never depend on the previous kernel
+        const int t0 = blockIdx.x;
+        if (t0 < n_tiles && !p.w_dynamic) {
+          const int n0 = (t0 % tiles_n) * BN;
+          npre = min(STAGES, nkb);
+          for (int s = 0; s < npre; ++s) {
+            ptx::mbar_expect_tx(&full_bar[s], L::kStageBytes);
+            ptx::tma_load_3d(&tmB, &full_bar[s], sB + s * L::kBTileBytes, s * BK, n0, 0);
+          }
+        }
+      }
+      pdl_wait();
+      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        const int tile_n = t % tiles_n, tile_m = t / tiles_n;
+        const int m0 = tile_m * BM, n0 = tile_n * BN;
+        int b0 = 0, h0 = 0, w0 = 0;
+        if (p.conv) {
+          b0 = m0 / p.HW;
+          const int rem = m0 - b0 * p.HW;
+          h0 = rem / p.W;
+          w0 = rem - h0 * p.W;
+        }
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const bool pre = it < npre;
+          if (!pre) {
+            ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+            ptx::mbar_expect_tx(&full_bar[stage], L::kStageBytes);
+          }
+          if (p.conv) {
+            const int tap = kb / p.cblocks;
+            const int cb = kb - tap * p.cblocks;
+            const int i = tap / p.kw;
+            const int j = tap - i * p.kw;
+            ptx::tma_load_4d(&tmA, &full_bar[stage], sA + stage * kATileBytes, cb * BK, w0 + j * p.dil_w - p.pad_w,
+                             h0 + i * p.dil_h - p.pad_h, b0);
+          } else {
+            ptx::tma_load_3d(&tmA, &full_bar[stage], sA + stage * kATileBytes, kb * BK, m0, 0);
+          }
+          if (!pre) ptx::tma_load_3d(&tmB, &full_bar[stage], sB + stage * L::kBTileBytes, kb * BK, n0, 0);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (ptx::elect_one()) {
+      constexpr uint32_t idesc = ptx::umma_idesc_bf16_f32(BM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int i = 0;
+      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++i) {
+        const int acc = i & 1;
+        const uint32_t use = static_cast<uint32_t>(i >> 1);
+        // wait until the epilogue has drained this accumulator buffer (first use: passes on the fresh barrier)
+        ptx::mbar_wait(&tmem_empty_bar[acc], (use & 1) ^ 1);
+        ptx::tcgen05_fence_after();
+        const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * BN);
+        for (int kb = 0; kb < nkb; ++kb) {
+          ptx::mbar_wait(&full_bar[stage], phase);
+          ptx::tcgen05_fence_after();
+          const uint32_t a_addr = ptx::smem_u32(sA + stage * kATileBytes);
+          const uint32_t b_addr = ptx::smem_u32(sB + stage * L::kBTileBytes);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t da = ptx::umma_desc_k_sw128(a_addr + k * 32);
+            const uint64_t db = ptx::umma_desc_k_sw128(b_addr + k * 32);
+            ptx::umma_bf16_ss(tmem_d, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          ptx::umma_commit(&empty_bar[stage]);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        ptx::umma_commit(&tmem_full_bar[acc]);
+      }
+      pdl_trigger();
+    }
+  } else {
+    // ===================== epilogue (warps 2..5 -> TMEM lane quadrants 2,3,0,1) =====================
+    const int quad = warp & 3;
+    const int etid = (int)threadIdx.x - 64;
+    pdl_wait();
+    int i = 0;
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++i) {
+      const int acc = i & 1;
+      const uint32_t par = static_cast<uint32_t>(i >> 1) & 1u;
+      const int tile_n = t % tiles_n, tile_m = t / tiles_n;
+      const int m0 = tile_m * BM, n0 = tile_n * BN;
+      const uint32_t tmem_q = tmem_base + static_cast<uint32_t>(acc * BN) + (static_cast<uint32_t>(quad * 32) << 16);
+      if (STAGED && p.fast_epi) {
+        float* strip = strips + (size_t)quad * 32 * (BN + 4);
+        epilogue_strip<BN>(p, strip, tmem_q, &tmem_full_bar[acc], (long long)m0 + quad * 32, n0, 0, lane, par,
+                           &tmem_empty_bar[acc]);
+      } else {
+        const long long m = (long long)m0 + quad * 32 + lane;
+        const bool row_ok = m < p.M;
+        if (p.residual && row_ok) {
+          const char* rp = reinterpret_cast<const char*>(p.residual + m * p.ld_res + n0);
+#pragma unroll
+          for (int l = 0; l < BN * 4 / 128; ++l) asm volatile("prefetch.global.L2 [%0];" ::"l"(rp + l * 128));
+        }
+        const bool stage_b = p.bias != nullptr;
+        const long long mlast = min((long long)m0 + BM - 1, (long long)p.M - 1);
+        const bool stage_rb = p.rowbias != nullptr && (m0 / p.rows_per_group) == (mlast / p.rows_per_group);
+        float* sb = s_bias + acc * BN;
+        float* srb = s_rowb + acc * BN;
+        if (stage_b || stage_rb) {
+          for (int c = etid; c < BN; c += 128) {
+            const bool ok = n0 + c < p.N;
+            if (stage_b) sb[c] = ok ? __ldg(p.bias + n0 + c) : 0.f;
+            if (stage_rb) srb[c] = ok ? __ldg(p.rowbias + (m0 / p.rows_per_group) * p.ld_rowbias + n0 + c) : 0.f;
+          }
+        }
+        // also orders the epilogue warps tile by tile: buffer `acc` of sb / srb is rewritten two tiles later, after
+        // every warp has passed the barrier of the tile in between
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        ptx::mbar_wait(&tmem_full_bar[acc], par);
+        ptx::tcgen05_fence_after();
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          uint32_t v[32];
+          ptx::tmem_ld_32x32b_x32(tmem_q + c * 32, v);
+          ptx::tmem_ld_wait();
+          if (c == BN / 32 - 1) {
+            // last read of this accumulator buffer: hand it back before the global stores of the chunk
+            ptx::tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[acc]);
+          }
+          float a32[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) a32[j] = __uint_as_float(v[j]) * p.alpha;
+          epilogue_chunk(p, a32, m, n0 + c * 32, 0, stage_b ? sb + c * 32 : nullptr, stage_rb ? srb + c * 32 : nullptr);
+        }
+      }
+    }
+    ptx::tcgen05_fence_before();
   }
   __syncthreads();
   if (warp == 1) {
@@ -858,15 +1086,46 @@ bool conv_box(int B, int H, int W, ConvBox* bx) {
   return true;
 }
 
+template <int BN, int STAGES, bool STAGED>
+int launch_persistent(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmDev& p, long long tiles_m, cudaStream_t st) {
+  using L = PersistLayout<BN, STAGES, STAGED>;
+  static bool attr_set = false;
+  static int n_sm = 0;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_persistent_kernel<BN, STAGES, STAGED>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
+    if (e != cudaSuccess) return fail(AE_ECUDA, "cudaFuncSetAttribute(persistent smem=%d): %s", L::kTotal, cudaGetErrorString(e));
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n_sm <= 0) n_sm = 148;
+    attr_set = true;
+  }
+  if (g_skip_mask & 1) return AE_OK;
+  const int tiles_n = (p.N + BN - 1) / BN;
+  const long long n_tiles = tiles_m * tiles_n;
+  const unsigned grid = (unsigned)(n_tiles < n_sm ? n_tiles : n_sm);
+  cudaError_t e = launch_kernel_early(gemm_persistent_kernel<BN, STAGES, STAGED>, dim3(grid), dim3(kThreads),
+                                      (size_t)L::kTotal, st, tmA, tmB, p, tiles_n, (int)n_tiles);
+  if (e != cudaSuccess) return fail(AE_ECUDA, "ae_gemm persistent launch: %s", cudaGetErrorString(e));
+  return launched("ae_gemm(persistent)");
+}
+
+constexpr int kHeadroomSmem = 116 * 1024;
+int g_headroom = 0;
+
 template <int BN, int STAGES>
 int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmDev& p, int gz, cudaStream_t st) {
   using L = SmemLayout<BN, STAGES>;
   static bool attr_set = false;
+  constexpr int kMaxDyn = L::kTotal > kHeadroomSmem ? L::kTotal : kHeadroomSmem;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
-    if (e != cudaSuccess) return fail(AE_ECUDA, "cudaFuncSetAttribute(smem=%d): %s", L::kTotal, cudaGetErrorString(e));
+    cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDyn);
+    if (e != cudaSuccess) return fail(AE_ECUDA, "cudaFuncSetAttribute(smem=%d): %s", kMaxDyn, cudaGetErrorString(e));
     attr_set = true;
   }
+  // g_headroom (ae_set_headroom): request at least half of the SM's shared memory, i.e. ONE CTA of this grid per SM —
+  // the other half stays free for the sub-wave kernels of a latency-bound chain running on another stream
+  const size_t dyn_smem = (g_headroom && L::kTotal < kHeadroomSmem) ? (size_t)kHeadroomSmem : (size_t)L::kTotal;
   if (g_skip_mask & 1) return AE_OK;
   const unsigned tm = (unsigned)((p.M + BM - 1) / BM), tn = (unsigned)((p.N + BN - 1) / BN);
   dim3 grid = p.m_in_x ? dim3(tm, tn, gz) : dim3(tn, tm, gz);
@@ -876,7 +1135,7 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmDev& p, int
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = grid;
     cfg.blockDim = dim3(kThreads);
-    cfg.dynamicSmemBytes = (size_t)L::kTotal;
+    cfg.dynamicSmemBytes = dyn_smem;
     cfg.stream = st;
     cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -889,7 +1148,7 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmDev& p, int
     cfg.numAttrs = g_use_pdl ? 2 : 1;
     e = cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<BN, STAGES>, tmA, tmB, p);
   } else {
-    e = launch_kernel_early(gemm_tcgen05_kernel<BN, STAGES>, grid, dim3(kThreads), (size_t)L::kTotal, st, tmA, tmB, p);
+    e = launch_kernel_early(gemm_tcgen05_kernel<BN, STAGES>, grid, dim3(kThreads), dyn_smem, st, tmA, tmB, p);
   }
   if (e != cudaSuccess) return fail(AE_ECUDA, "ae_gemm launch: %s", cudaGetErrorString(e));
   return launched("ae_gemm");
@@ -903,6 +1162,7 @@ using namespace aedit;
 extern "C" void ae_set_pdl(int mode) { g_use_pdl = (mode == 1 || mode == 2) ? mode : 0; }
 extern "C" void ae_set_launch_priority(int prio) { g_launch_priority = prio; }
 extern "C" void ae_set_skip_mask(int mask) { g_skip_mask = mask; }
+extern "C" void ae_set_headroom(int on) { g_headroom = on ? 1 : 0; }
 extern "C" void ae_set_pdl_extra(int mask) { g_pdl_extra = mask; }
 extern "C" int ae_greatest_priority(void) {
   int least = 0, greatest = 0;
@@ -915,6 +1175,10 @@ extern "C" int ae_greatest_priority(void) {
 
 static int g_splitk_ctas = 148;
 static int g_fast_epi = 1;
+static long long g_persist_min_tiles = 296;   // two waves of 148 SMs; 0 = never (see ae_set_persistent_min_tiles)
+extern "C" void ae_set_persistent_min_tiles(int tiles) { g_persist_min_tiles = tiles; }
+static int g_shallow_kb = 0;
+extern "C" void ae_set_shallow_kblocks(int kb) { g_shallow_kb = kb; }
 static int g_shared_sm = 0;
 extern "C" void ae_set_shared_sm(int on) { g_shared_sm = on ? 1 : 0; }
 static int g_tile_model = 1;
@@ -1155,6 +1419,28 @@ extern "C" int ae_gemm(const ae_gemm_args* a, ae_stream stream) {
   // ONE such CTA (<= ~103 KB: 3 / 4 / 5 stages at BN = 128 / 64 / 32) gets the next free slot.  Same bits either way:
   // the ring depth changes the buffering, not the order of the accumulation.
   const bool shared_sm = g_shared_sm && CS == 1 && !a->force_stages;
+  // multi-wave grids with a short K loop: a 2-stage ring lets three CTAs share an SM (the CTA's fixed costs — launch,
+  // TMEM allocation, pipeline ramp, epilogue — dominate its lifetime, so residency buys more than ring depth)
+  // multi-wave grids: persistent CTAs with a double-buffered TMEM accumulator (gemm_persistent_kernel)
+  // Where it pays (profiles/r01_gemm_table_persistent.log, B = 100): linears with a bf16-only or GEGLU output or a K
+  // loop of >= 9 blocks (-10 .. -32 %).  Not the implicit convolutions (long K loops are bound by the operand bytes
+  // in flight per SM, and two or three co-resident CTAs keep more rings in flight than one persistent CTA: +7 .. +55 %)
+  // and not the K = 384 linears with an fp32 output, which are bound by their epilogue's HBM traffic (+5 %).
+  const bool persist_auto = g_persist_min_tiles > 0 && tiles >= g_persist_min_tiles && !p.conv &&
+                            (!q.out_f32 || q.act == 2 || p.num_kblocks >= 9);
+  const bool persist = CS == 1 && S == 1 && batch == 1 && !a->force_stages && (bn == 128 || bn == 64) &&
+                       (a->force_persistent > 0 || (a->force_persistent == 0 && persist_auto)) &&
+                       tiles * 1ll < 2147483647ll;
+  if (persist) {
+    if (bn == 128)
+      rc = q.fast_epi ? launch_persistent<128, 4, true>(tmA, tmB, q, tiles_m, st)
+                      : launch_persistent<128, 6, false>(tmA, tmB, q, tiles_m, st);
+    else
+      rc = q.fast_epi ? launch_persistent<64, 6, true>(tmA, tmB, q, tiles_m, st)
+                      : launch_persistent<64, 6, false>(tmA, tmB, q, tiles_m, st);
+  } else if (!deep && bn == 128 && CS == 1 && (a->force_stages == 2 || (!a->force_stages && p.num_kblocks <= g_shallow_kb)))
+    rc = launch<128, 2>(tmA, tmB, q, gz, st);
+  else
   switch (bn) {
     case 32:
       rc = deep ? (shared_sm ? launch<32, 5>(tmA, tmB, q, gz, st) : launch<32, 6>(tmA, tmB, q, gz, st))

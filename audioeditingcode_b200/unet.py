@@ -75,8 +75,12 @@ class GraphedForward:
         side = capture_stream if capture_stream is not None else torch.cuda.Stream(priority=-1 if lane >= 1 else 0)
         self._side2 = torch.cuda.Stream() if self.dual else None
         main_ops = engine.ops
+        # PDL attribute on the norm / attention kernels, per lane (measured on the whole job, profiles/r01_lanes_ab*.log)
+        pdlx = int(os.environ.get(("AEDIT_PDLX_FWD", "AEDIT_PDLX_SOLO", "AEDIT_PDLX_SHARED")[lane],
+                                  os.environ.get("AEDIT_PDL_EXTRA", str(engine.pdl_extra[lane]))))
+        engine.ops.lib.ae_set_pdl_extra(pdlx)
+        engine.ops.lib.ae_set_headroom(1 if (lane == 0 and engine.fwd_headroom and B > 8) else 0)
         if lane >= 1:
-            import os
             engine.ops = engine.ops_b()
             if os.environ.get("AEDIT_REV_PRIORITY", "1") != "0":
                 engine.ops.lib.ae_set_launch_priority(engine.ops.lib.ae_greatest_priority())
@@ -96,6 +100,8 @@ class GraphedForward:
                 engine.ops.lib.ae_set_launch_priority(0)
                 engine.ops.lib.ae_set_shared_sm(0)
             engine.ops = main_ops
+            engine.ops.lib.ae_set_pdl_extra(int(os.environ.get("AEDIT_PDL_EXTRA", "0")))
+            engine.ops.lib.ae_set_headroom(0)
 
     def _run(self, engine):
         if not self.dual:
@@ -147,6 +153,8 @@ class UNetEngine:
         self.dual_stream = os.environ.get("AEDIT_DUAL_STREAM", "0") != "0"
         self.dual_stream_max_b = int(os.environ.get("AEDIT_DUAL_STREAM_MAX_B", "4"))
         self._ops_b = None
+        self.fwd_headroom = os.environ.get("AEDIT_FWD_HEADROOM", "0") != "0"
+        self.pdl_extra = [0, 0, 15]     # per lane (forward chunks, reverse solo, reverse shared-SM); see GraphedForward
         # GroupNorm statistics from the producing GEMM's epilogue (ae_gemm_args.colstats): every GEMM whose fp32 output
         # feeds a GroupNorm accumulates per-(sample, channel) sums into a slice of one arena that is zeroed once per
         # evaluation; ops.groupnorm then runs a single launch.  AEDIT_GN_COLSTATS=0 restores the statistics kernel.

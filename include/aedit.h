@@ -52,6 +52,18 @@ void ae_set_launch_priority(int prio);
 void ae_set_pdl_extra(int mask);
 /* GroupNorm tensors of at least this many bytes (default 8 MiB) take the streaming apply kernel (same bits). */
 void ae_set_gn_stream_min_bytes(int64_t bytes);
+/* Multi-wave 128-wide GEMM grids whose K loop has at most this many 64-wide blocks use a 2-stage operand ring (three
+ * CTAs per SM instead of two).  0 = never.  Same bits. */
+void ae_set_shallow_kblocks(int kb);
+/* 1: GEMM grids launched (captured) from now on keep ONE CTA per SM (they request at least half of the SM's shared
+ * memory), leaving the other half to the sub-wave kernels of a latency-bound chain on another stream — the
+ * forward-process chunks are captured this way when they overlap the reverse process.  0 (default): 2-3 CTAs per SM. */
+void ae_set_headroom(int on);
+/* GEMM grids of at least this many 128 x BN output tiles (no K split, no batch) run as persistent CTAs, one per SM,
+ * with the accumulator double-buffered in TMEM so that a tile's epilogue overlaps the next tile's main loop — for the
+ * shapes where that measured faster (linears with a bf16 / GEGLU output or >= 9 K blocks).  Default 296; 0 = never.
+ * Same bits as the one-CTA-per-tile kernel. */
+void ae_set_persistent_min_tiles(int tiles);
 /* DIAGNOSTIC ONLY: drop the launches of kernel families (1 GEMM, 2 split-K reduce, 4 GroupNorm statistics,
  * 8 GroupNorm apply, 16 LayerNorm, 32 attention) to measure a family's marginal cost inside a captured graph
  * (tools/kernel_share.py).  Outputs are meaningless while the mask is non-zero. */
@@ -204,6 +216,7 @@ typedef struct {
    * cs_rows_per_sample % 32 == 0.  Consumed by ae_groupnorm_cs.  NULL = off. */
   int64_t* colstats;
   int32_t cs_rows_per_sample;
+  int32_t force_persistent; /* 0 auto (ae_set_persistent_min_tiles), 1 persistent kernel, -1 one CTA per tile */
 } ae_gemm_args;
 int ae_gemm(const ae_gemm_args*, ae_stream stream);
 /* 1 if the implicit-conv fast path supports this geometry (else use ae_im2col + plain GEMM) */

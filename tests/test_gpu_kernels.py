@@ -221,6 +221,73 @@ def test_gemm_cluster_splitk_conv_and_geglu(ops):
     assert relerr(o, a * F.gelu(gt)) < 4e-3
 
 
+@pytest.mark.parametrize("M,N,K,kind", [
+    (128 * 160 + 37, 384, 384, "res"),        # > one tile per SM, ragged M tail, residual + bias + fp32/bf16 out (staged)
+    (128 * 300, 192, 1728, "rowbias"),        # BN = 64 tiles, time-embedding row bias (staged, multi-wave fp32 out)
+    (128 * 170, 1152, 384, "bf16"),           # bf16-only output (row-per-thread epilogue)
+    (128 * 40, 200, 72, "res"),               # K shorter than the ring, ragged N
+    (128 * 64, 1536, 384, "geglu"),           # GEGLU epilogue
+    (128 * 64, 384, 384, "stats"),            # GroupNorm column statistics from the staged epilogue
+    (128 * 3, 960, 960, "res"),               # fewer tiles than SMs
+])
+def test_gemm_persistent_same_bits(ops, M, N, K, kind):
+    """The persistent kernel (one CTA per SM walking the tiles, TMEM accumulator double-buffered) produces the bits of the
+    one-CTA-per-tile kernel for every epilogue."""
+    A = rnd((M, K), 1, dtype=BF)
+    W = rnd((N, K), 2, 1 / math.sqrt(K), dtype=BF)
+    bias = rnd((N,), 3)
+    outs = []
+    for fp in (-1, 1, 1):
+        kw = dict(force_persistent=fp, force_split=1)
+        if kind == "res":
+            res = rnd((M, N), 4)
+            o32 = torch.zeros(M, N, device="cuda")
+            o16 = torch.zeros(M, N, device="cuda", dtype=BF)
+            ops.gemm(A, W, out_f32=o32, out_bf16=o16, bias=bias, residual=res, **kw)
+            outs.append((o32, o16))
+        elif kind == "rowbias":
+            rb = rnd((M // 128 // 4 + 1, N), 5)
+            o32 = torch.zeros(M, N, device="cuda")
+            ops.gemm(A, W, out_f32=o32, bias=bias, rowbias=rb, rows_per_group=512, **kw)
+            outs.append((o32,))
+        elif kind == "bf16":
+            o16 = torch.zeros(M, N, device="cuda", dtype=BF)
+            ops.gemm(A, W, out_bf16=o16, **kw)
+            outs.append((o16,))
+        elif kind == "geglu":
+            o16 = torch.zeros(M, N // 2, device="cuda", dtype=BF)
+            ops.gemm(A, W, out_bf16=o16, bias=bias, act=2, **kw)
+            outs.append((o16,))
+        elif kind == "stats":
+            res = rnd((M, N), 4)
+            o32 = torch.zeros(M, N, device="cuda")
+            cs = torch.zeros(M // 1024, N, 2, dtype=torch.int64, device="cuda")
+            ops.gemm(A, W, out_f32=o32, bias=bias, residual=res, colstats=cs, cs_rows=1024, **kw)
+            outs.append((o32, cs))
+    for a, b, c in zip(*outs):
+        assert torch.equal(a, b) and torch.equal(b, c)
+    if kind == "res":
+        ref = A.float() @ W.float().t() + bias + res
+        assert relerr(outs[1][0], ref) < 2e-5
+
+
+def test_gemm_persistent_implicit_conv(ops):
+    B, H, Wd, C, Co = 24, 64, 16, 192, 192
+    x = rnd((B, H, Wd, C), 1, dtype=BF)
+    wt = rnd((Co, C, 3, 3), 2, 1 / math.sqrt(C * 9), dtype=BF)
+    bias = rnd((Co,), 3)
+    Wp = wt.permute(0, 2, 3, 1).reshape(Co, -1).contiguous()
+    res = rnd((B * H * Wd, Co), 4)
+    outs = []
+    for fp in (-1, 1):
+        o = torch.zeros(B * H * Wd, Co, device="cuda")
+        ops.gemm(x, Wp, out_f32=o, bias=bias, residual=res, conv=(B, H, Wd, C, 3, 3, 1, 1), force_persistent=fp, force_split=1)
+        outs.append(o)
+    assert torch.equal(outs[0], outs[1])
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), wt.float(), bias, padding=1).permute(0, 2, 3, 1).reshape(-1, Co) + res
+    assert relerr(outs[1], ref) < 2e-5
+
+
 @pytest.mark.parametrize("M,C", [(300, 64), (4096, 192), (128, 960)])
 def test_gemm_geglu_epilogue(ops, M, C):
     """FF1 + GEGLU fused (act=2, interleaved weight rows) == chunk(2) -> value * gelu(gate) (attention.py:37-44)."""
