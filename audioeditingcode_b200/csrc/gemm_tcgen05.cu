@@ -94,7 +94,22 @@ struct SmemLayout {
   static constexpr int kTotal = kRingBytes + kBarBytes + kEpiBytes + 1024;  // +1024 manual alignment slack
 };
 
-__device__ __forceinline__ float gelu_erf_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+// gelu(x) = x * Phi(x) (erf form, attention.py:37-44 / torch F.gelu default).  Branch-free: erf(|z|), z = x / sqrt(2),
+// from Abramowitz & Stegun 7.1.26 (|error| <= 1.5e-7): erf(z) = 1 - (a1 t + ... + a5 t^5) exp(-z^2), t = 1 / (1 + p z);
+// for x < 0, Phi = 0.5 * poly * exp(-z^2) directly (no cancellation in the tail).  libdevice's erff has two regimes, so
+// a warp whose lanes straddle |z| ~ 0.9 executes both; the GEGLU epilogue is ALU-bound (one value per 2 accumulators).
+__device__ __forceinline__ float gelu_erf_f(float x) {
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  float t, e;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(z * z * -1.4426950408889634f));
+  float pl = fmaf(1.061405429f, t, -1.453152027f);
+  pl = fmaf(pl, t, 1.421413741f);
+  pl = fmaf(pl, t, -0.284496736f);
+  pl = fmaf(pl, t, 0.254829592f);
+  const float half_tail = 0.5f * pl * t * e;            // 0.5 * erfc(|z|)
+  return x * (x >= 0.f ? 1.0f - half_tail : half_tail);
+}
 
 // Fused epilogue of one 32-column chunk of one output row: bias, time-embedding row bias, residual, activation,
 // fp32 / bf16 stores.  `acc` already holds alpha * accumulator.
@@ -1426,7 +1441,11 @@ extern "C" int ae_gemm(const ae_gemm_args* a, ae_stream stream) {
   // loop of >= 9 blocks (-10 .. -32 %).  Not the implicit convolutions (long K loops are bound by the operand bytes
   // in flight per SM, and two or three co-resident CTAs keep more rings in flight than one persistent CTA: +7 .. +55 %)
   // and not the K = 384 linears with an fp32 output, which are bound by their epilogue's HBM traffic (+5 %).
-  const bool persist_auto = g_persist_min_tiles > 0 && tiles >= g_persist_min_tiles && !p.conv &&
+  // The automatic choice is further limited to the row-per-thread epilogue (bf16-only / GEGLU outputs — the shapes
+  // that gain most), whose persistent CTA fits in ~100 KB with a 3-stage ring: a persistent CTA holds its SM for the
+  // whole kernel, and with the 200 KB staged variant no CTA of the reverse-process lane could become resident anywhere
+  // on the machine meanwhile (whole job: 836 -> 862 ms with every shape persistent, profiles/r01_lanes_ab6.log).
+  const bool persist_auto = g_persist_min_tiles > 0 && tiles >= g_persist_min_tiles && !p.conv && !q.fast_epi &&
                             (!q.out_f32 || q.act == 2 || p.num_kblocks >= 9);
   const bool persist = CS == 1 && S == 1 && batch == 1 && !a->force_stages && (bn == 128 || bn == 64) &&
                        (a->force_persistent > 0 || (a->force_persistent == 0 && persist_auto)) &&
@@ -1434,10 +1453,10 @@ extern "C" int ae_gemm(const ae_gemm_args* a, ae_stream stream) {
   if (persist) {
     if (bn == 128)
       rc = q.fast_epi ? launch_persistent<128, 4, true>(tmA, tmB, q, tiles_m, st)
-                      : launch_persistent<128, 6, false>(tmA, tmB, q, tiles_m, st);
+                      : launch_persistent<128, 3, false>(tmA, tmB, q, tiles_m, st);
     else
       rc = q.fast_epi ? launch_persistent<64, 6, true>(tmA, tmB, q, tiles_m, st)
-                      : launch_persistent<64, 6, false>(tmA, tmB, q, tiles_m, st);
+                      : launch_persistent<64, 4, false>(tmA, tmB, q, tiles_m, st);
   } else if (!deep && bn == 128 && CS == 1 && (a->force_stages == 2 || (!a->force_stages && p.num_kblocks <= g_shallow_kb)))
     rc = launch<128, 2>(tmA, tmB, q, gz, st);
   else

@@ -404,15 +404,24 @@ def main():
     if rank == 0:
         peaks = load_peaks()
         fl2 = flops_per_eval(cfg, spec, 2)
-        Bf = 2 * args.forward_batch
-        flf = flops_per_eval(cfg, spec, Bf)
         gp = gemm_event_pass(m, spec, cfg, 2)
-        gpf = gemm_event_pass(m, spec, cfg, Bf)
-        # dominant kernel over the job: n_inv/forward_batch chunk evaluations at B=2*forward_batch + tstart at B=2
-        n_chunks = (spec["n_inv"] + args.forward_batch - 1) // args.forward_batch
-        gemm_flops = n_chunks * (flf["conv"] + flf["linear"]) + spec["tstart"] * (fl2["conv"] + fl2["linear"])
-        gemm_ms_job = n_chunks * gpf["gemm_ms"] + spec["tstart"] * gp["gemm_ms"]
-        eval_ms_job = n_chunks * gpf["eval_ms"] + spec["tstart"] * gp["eval_ms"]
+        # dominant kernel over the job: the forward-process chunks of the plan the loop actually runs (B = 2 x
+        # timesteps per chunk) + tstart reverse steps at B = 2
+        from collections import Counter
+        from audioeditingcode_b200.ddm_inversion.inversion_utils import _chunk_plan
+        plan = Counter(c for _, c in _chunk_plan(spec["n_inv"], args.forward_batch, spec["n_inv"] // 2))
+        gemm_flops = spec["tstart"] * (fl2["conv"] + fl2["linear"])
+        gemm_ms_job = spec["tstart"] * gp["gemm_ms"]
+        eval_ms_job = spec["tstart"] * gp["eval_ms"]
+        per_chunk = {}
+        for count, n_c in sorted(plan.items()):
+            flc = flops_per_eval(cfg, spec, 2 * count)
+            gpc = gemm_event_pass(m, spec, cfg, 2 * count)
+            gemm_flops += n_c * (flc["conv"] + flc["linear"])
+            gemm_ms_job += n_c * gpc["gemm_ms"]
+            eval_ms_job += n_c * gpc["eval_ms"]
+            per_chunk[f"B{2 * count}"] = {"chunks": n_c, "gemm_ms": gpc["gemm_ms"], "eval_ms": gpc["eval_ms"],
+                                          "tflops": (flc["conv"] + flc["linear"]) / gpc["gemm_ms"] / 1e9}
         achieved = gemm_flops / (gemm_ms_job / 1000.0) / 1e12
         # whole-job FLOPs: forward batches B = 2*forward_batch per launch, reverse B = 2
         job_flops = (spec["n_inv"] + spec["tstart"]) * fl2["total"]
@@ -427,11 +436,11 @@ def main():
                             "peak_source": peaks["source"],
                             "flops_per_job": gemm_flops, "gemm_ms_per_job": gemm_ms_job,
                             "gemm_share_of_unet_time": gemm_ms_job / eval_ms_job,
-                            "unet_share_of_job_time": eval_ms_job / (ms / args.steps),
-                            "per_eval": {"B2": {"gemm_ms": gp["gemm_ms"], "eval_ms": gp["eval_ms"], "gemm_calls": gp["n_gemm"],
-                                                "tflops": (fl2["conv"] + fl2["linear"]) / gp["gemm_ms"] / 1e9},
-                                         f"B{Bf}": {"gemm_ms": gpf["gemm_ms"], "eval_ms": gpf["eval_ms"],
-                                                    "tflops": (flf["conv"] + flf["linear"]) / gpf["gemm_ms"] / 1e9}},
+                            "unet_time_serial_over_job_time": eval_ms_job / (ms / args.steps),
+                            "per_eval": dict({"B2": {"gemm_ms": gp["gemm_ms"], "eval_ms": gp["eval_ms"],
+                                                     "gemm_calls": gp["n_gemm"],
+                                                     "tflops": (fl2["conv"] + fl2["linear"]) / gp["gemm_ms"] / 1e9}},
+                                             **per_chunk),
                             "job_tflops_all_kernels": job_flops * args.steps / (ms / 1000.0) / 1e12}
         if not args.no_cpu_baseline and world == 1:
             threads = pick_threads(cores)
