@@ -41,6 +41,7 @@ _SIGS = {
     "ae_greatest_priority": (i32, []),
     "ae_set_shared_sm": (None, [i32]),
     "ae_set_skip_mask": (None, [i32]),
+    "ae_set_tile_model_reduce": (None, [i32, i32]),
     "ae_set_persistent_min_tiles": (None, [i32]),
     "ae_set_headroom": (None, [i32]),
     "ae_set_shallow_kblocks": (None, [i32]),
@@ -71,6 +72,10 @@ _SIGS = {
     "ae_geglu": (i32, [vp, i64, i32, vp, vp]),
     "ae_attention": (i32, [vp, i64, i64, vp, i64, i64, vp, i64, i64, vp, vp, i64, i32, i32, i32, i32, i32, f32, vp,
                            i64, i64, vp]),
+    "ae_attention_ws": (i32, [vp, i64, i64, vp, i64, i64, vp, i64, i64, vp, vp, i64, i32, i32, i32, i32, i32, f32, vp,
+                              i64, i64, vp, i64, vp]),
+    "ae_attention_workspace_bytes": (i64, [i32, i32, i32, i32]),
+    "ae_set_attention_split": (None, [i32]),
     "ae_timestep_embedding": (i32, [vp, i32, i32, vp, vp]),
     "ae_upsample_nearest": (i32, [vp, i32, i32, i32, i32, i32, i32, vp, vp]),
     "ae_nchw_to_nhwc": (i32, [vp, i32, i32, i32, i32, vp, vp, vp]),

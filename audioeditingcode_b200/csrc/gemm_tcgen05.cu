@@ -1229,6 +1229,11 @@ static int g_splitk_ctas = 148;
 static int g_fast_epi = 1;
 static long long g_persist_min_tiles = 296;   // two waves of 148 SMs; 0 = never (see ae_set_persistent_min_tiles)
 extern "C" void ae_set_persistent_min_tiles(int tiles) { g_persist_min_tiles = tiles; }
+static double g_reduce_us = 2.5, g_reduce_bw = 3.0e6;   // tile model: cost of the split-K reduce launch / its bytes per us
+extern "C" void ae_set_tile_model_reduce(int launch_ns, int bytes_per_us) {
+  g_reduce_us = launch_ns * 1e-3;
+  g_reduce_bw = bytes_per_us;
+}
 static int g_shallow_kb = 0;
 extern "C" void ae_set_shallow_kblocks(int kb) { g_shallow_kb = kb; }
 static int g_shared_sm = 0;
@@ -1367,7 +1372,7 @@ extern "C" int ae_gemm(const ae_gemm_args* a, ae_stream stream) {
           const long long ctas_c = t * sp;
           const double waves = ctas_c <= g_splitk_ctas ? 1.0 : (double)ctas_c / g_splitk_ctas;
           // reduce pass: launch + (S partial tiles written and read back, residual, outputs) at ~3 MB/us
-          const double reduce_us = sp > 1 ? 2.5 + (sp + 2.5) * (double)a->M * a->N * 4.0 / 3.0e6 : 0.0;
+          const double reduce_us = sp > 1 ? g_reduce_us + (sp + 2.5) * (double)a->M * a->N * 4.0 / g_reduce_bw : 0.0;
           double cost = waves * kbs * stage_kb / 70.0          // us to stream one SM's operands
                         + (c / 128.0) * 1.0                     // epilogue
                         + reduce_us;

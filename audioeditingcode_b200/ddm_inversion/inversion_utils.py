@@ -302,7 +302,8 @@ def inversion_forward_process(model: PipelineWrapper,
     ts_cpu = sched.timesteps_cpu
     model.sched_table.set_etas(etas)
     overlap = OVERLAP and USE_CUDA_GRAPHS and x0.is_cuda and tb > 1 and g_ws == 1 and not prog_bar
-    plan = _chunk_plan(N, tb, (N // 2 if reverse_hint is None else int(reverse_hint)) if g_ws == 1 else None)
+    # the same plan with and without a process group: a chunk's bits depend on its batch, so sharded == single-GPU
+    plan = _chunk_plan(N, tb, N // 2 if reverse_hint is None else int(reverse_hint))
     it = tqdm(plan) if prog_bar else plan
     # everything a chunk needs from the host is staged BEFORE the first launch: a pageable host->device copy on a busy
     # stream blocks the host until the stream drains, which would serialise the launches of the two lanes

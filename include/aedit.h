@@ -64,6 +64,8 @@ void ae_set_headroom(int on);
  * shapes where that measured faster (linears with a bf16 / GEGLU output or >= 9 K blocks).  Default 296; 0 = never.
  * Same bits as the one-CTA-per-tile kernel. */
 void ae_set_persistent_min_tiles(int tiles);
+/* Tile model constants: what a split-K reduce pass is charged (launch nanoseconds, bytes per microsecond). */
+void ae_set_tile_model_reduce(int launch_ns, int bytes_per_us);
 /* DIAGNOSTIC ONLY: drop the launches of kernel families (1 GEMM, 2 split-K reduce, 4 GroupNorm statistics,
  * 8 GroupNorm apply, 16 LayerNorm, 32 attention) to measure a family's marginal cost inside a captured graph
  * (tools/kernel_share.py).  Outputs are meaningless while the mask is non-zero. */
@@ -259,6 +261,19 @@ int ae_attention(const void* q, int64_t ld_q, int64_t q_batch_stride, const void
                  int64_t k_batch_stride, const void* v, int64_t ld_v, int64_t v_batch_stride, const int32_t* kv_batch_map,
                  const float* key_bias, int64_t ld_bias, int B, int heads, int d, int Tq, int Tk, float scale, void* out,
                  int64_t ld_o, int64_t o_batch_stride, ae_stream stream);
+
+/* Same, with a workspace that lets the kernel split the KEYS of small grids over several CTAs (split-KV; the partial
+ * accumulators are merged in split order by the last CTA of a query tile to arrive, so the result is deterministic).
+ * workspace: ae_attention_workspace_bytes(B, heads, Tq, d) bytes, its first B*heads*ceil(Tq/64)*4 bytes ZERO-initialised
+ * once by the caller (arrival counters, re-armed by the kernel).  ae_set_attention_split: 0 auto, 1 never (the default:
+ * at batch 2 the split measured slower, 6.04 -> 6.14-6.37 ms per evaluation), n forced. */
+int64_t ae_attention_workspace_bytes(int B, int heads, int Tq, int d);
+void ae_set_attention_split(int n);
+int ae_attention_ws(const void* q, int64_t ld_q, int64_t q_batch_stride, const void* k, int64_t ld_k,
+                    int64_t k_batch_stride, const void* v, int64_t ld_v, int64_t v_batch_stride,
+                    const int32_t* kv_batch_map, const float* key_bias, int64_t ld_bias, int B, int heads, int d, int Tq,
+                    int Tk, float scale, void* out, int64_t ld_o, int64_t o_batch_stride, void* workspace,
+                    int64_t workspace_bytes, ae_stream stream);
 
 /* Sinusoidal timestep embedding [cos | sin] (util.py:173-197), bf16 out [B, dim]; t: int64 [B] */
 int ae_timestep_embedding(const int64_t* t, int B, int dim, void* out_bf16, ae_stream stream);

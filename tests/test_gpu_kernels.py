@@ -468,6 +468,33 @@ def test_attention_self(ops, d, heads, Tq, Tk):
     assert relerr(out, ref) < 1e-2
 
 
+@pytest.mark.parametrize("d,heads,Tq,Tk,split", [(48, 8, 1024, 1024, 0), (48, 8, 1024, 1024, 4), (48, 8, 1024, 1000, 3),
+                                                  (72, 8, 256, 256, 2), (120, 8, 64, 300, 2), (48, 8, 1024, 1024, 8)])
+def test_attention_split_kv(ops, d, heads, Tq, Tk, split):
+    """Split-KV (small grids): the keys are divided over several CTAs and merged in split order by the last one to
+    arrive — same result as the single-pass kernel up to fp32 merge rounding, deterministic, counters re-armed."""
+    B, C = 2, heads * d
+    q = rnd((B, Tq, C), 1, dtype=BF)
+    k = rnd((B, Tk, C), 2, dtype=BF)
+    v = rnd((B, Tk, C), 3, dtype=BF)
+    args = (heads, d, d ** -0.5, Tq, Tk, B, C, Tq * C, C, Tk * C, C, Tk * C)
+    outs = []
+    try:
+        for ns in (1, split, split):
+            ops.lib.ae_set_attention_split(ns)
+            o = torch.zeros(B * Tq, C, device="cuda", dtype=BF)
+            ops.attention(q, k, v, o, *args)
+            outs.append(o)
+    finally:
+        ops.lib.ae_set_attention_split(0)
+    assert torch.equal(outs[1], outs[2])                       # same call twice: same bits (and the counters were re-armed)
+    qh, kh, vh = (t.float().view(B, -1, heads, d).transpose(1, 2) for t in (q, k, v))
+    ref = (qh @ kh.transpose(-1, -2) * d ** -0.5).softmax(-1) @ vh
+    ref = ref.transpose(1, 2).reshape(B * Tq, C)
+    assert relerr(outs[1], ref) < 1e-2 and relerr(outs[0], ref) < 1e-2
+    assert relerr(outs[1], outs[0]) < 4e-3                     # bf16 output rounding of slightly different fp32 values
+
+
 def test_attention_cross_masked(ops):
     B, heads, d, Tq, R, L = 4, 8, 48, 256, 2, 13
     C = heads * d

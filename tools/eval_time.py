@@ -27,7 +27,7 @@ def main():
     lib = m.engine.ops.lib
     for kv in a.env:
         k, v = kv.split("=")
-        getattr(lib, k)(int(v))
+        getattr(lib, k)(*[int(x) for x in v.split(",")])
     for Bq in a.B:
         slot = torch.cat([torch.zeros(Bq // 2, dtype=torch.int32), torch.ones(Bq // 2, dtype=torch.int32)]).to(dev)
         for px in a.pdlx:
