@@ -28,7 +28,8 @@ class AeGemmArgs(C.Structure):
                 ("alpha", f32), ("conv", i32), ("B", i32), ("H", i32), ("W_", i32), ("C", i32), ("kh", i32),
                 ("kw", i32), ("dil_h", i32), ("dil_w", i32), ("force_bn", i32), ("splitk_ws", vp), ("splitk_ws_bytes", i64),
                 ("force_split", i32), ("force_csplit", i32), ("w_dynamic", i32), ("force_stages", i32),
-                ("colstats", vp), ("cs_rows_per_sample", i32), ("force_persistent", i32)]
+                ("colstats", vp), ("cs_rows_per_sample", i32), ("force_persistent", i32),
+                ("force_multicast", i32)]
 
 
 _SIGS = {
@@ -41,6 +42,7 @@ _SIGS = {
     "ae_greatest_priority": (i32, []),
     "ae_set_shared_sm": (None, [i32]),
     "ae_set_skip_mask": (None, [i32]),
+    "ae_set_multicast": (None, [i32]),
     "ae_set_tile_model_reduce": (None, [i32, i32]),
     "ae_set_persistent_min_tiles": (None, [i32]),
     "ae_set_headroom": (None, [i32]),

@@ -422,7 +422,11 @@ __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.aligned;\n\tbarrier.cluster.wait.aligned;" ::: "memory");
 }
 
-template <int BN, int STAGES>
+// MC = 2: the two CTAs of a cluster (adjacent N tiles of one M tile) share the A tile — each fetches half of its rows
+// and TMA-multicasts them into both CTAs' rings, so a CTA pulls half of the A panel through L2 (the sub-wave layers of
+// the reverse process are bound by exactly that: ~70 KB/us per SM).  A ring slot is free once BOTH MMA warps are done
+// with it (empty barrier counts 2, each commit is multicast to both CTAs).  Linear (non-conv) operands only.
+template <int BN, int STAGES, int MC = 1>
 __global__ void __launch_bounds__(kThreads)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmDev p) {
   using L = SmemLayout<BN, STAGES>;
@@ -462,16 +466,19 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     ptx::prefetch_tensormap(&tmB);
     for (int s = 0; s < STAGES; ++s) {
       ptx::mbar_init(&full_bar[s], 1);
-      ptx::mbar_init(&empty_bar[s], 1);
+      ptx::mbar_init(&empty_bar[s], MC);
     }
     ptx::mbar_init(tmem_full_bar, 1);
     ptx::fence_mbar_init();
   }
+  uint32_t crank = 0;
+  if constexpr (MC == 2) crank = ptx::cluster_ctarank();
   if (warp == 1) ptx::tmem_alloc<TMEM_COLS>(tmem_slot);
   if (p.colstats && warp >= 2)
     for (int i = (int)threadIdx.x - 64; i < 2 * BN + 1; i += kThreads - 64) s_cs[i] = 0ull;
   ptx::tcgen05_fence_before();
   __syncthreads();
+  if constexpr (MC == 2) cluster_sync_all();   // the peer's barriers exist before anything is multicast to them
   ptx::tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   // Everything above overlapped the previous kernel (programmatic dependent launch).  The weight operand W never
@@ -508,6 +515,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           const int j = tap - i * p.kw;
           ptx::tma_load_4d(&tmA, &full_bar[stage], sA + stage * kATileBytes, cb * BK, w0 + j * p.dil_w - p.pad_w,
                            h0 + i * p.dil_h - p.pad_h, b0);
+        } else if constexpr (MC == 2) {
+          // my half of the A tile's rows (tmA's box is 64 rows here), delivered to both CTAs of the pair
+          ptx::tma_load_3d_multicast(&tmA, &full_bar[stage], sA + stage * kATileBytes + crank * (kATileBytes / 2),
+                                     kb * BK, m0 + (int)crank * (BM / 2), zb, (uint16_t)0x3);
         } else {
           ptx::tma_load_3d(&tmA, &full_bar[stage], sA + stage * kATileBytes, kb * BK, m0, zb);
         }
@@ -536,7 +547,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           const uint64_t db = ptx::umma_desc_k_sw128(b_addr + k * 32);
           ptx::umma_bf16_ss(tmem_base, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
         }
-        ptx::umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+        // frees the smem slot when these MMAs retire (pair: in both CTAs — either producer may refill either ring)
+        if constexpr (MC == 2) ptx::umma_commit_multicast(&empty_bar[stage], (uint16_t)0x3);
+        else ptx::umma_commit(&empty_bar[stage]);
         if (++stage == STAGES) {
           stage = 0;
           phase ^= 1;
@@ -648,6 +661,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     cluster_sync_all();  // nobody leaves while a peer may still read its partial tile
   }
+  if constexpr (MC == 2) cluster_sync_all();   // the peer's last commits still arrive on this CTA's barriers
   __syncthreads();
   if (warp == 1) {
     ptx::tcgen05_fence_after();
@@ -1165,13 +1179,13 @@ int launch_persistent(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gemm
 constexpr int kHeadroomSmem = 116 * 1024;
 int g_headroom = 0;
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int MC = 1>
 int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmDev& p, int gz, cudaStream_t st) {
   using L = SmemLayout<BN, STAGES>;
   static bool attr_set = false;
   constexpr int kMaxDyn = L::kTotal > kHeadroomSmem ? L::kTotal : kHeadroomSmem;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDyn);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, STAGES, MC>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDyn);
     if (e != cudaSuccess) return fail(AE_ECUDA, "cudaFuncSetAttribute(smem=%d): %s", kMaxDyn, cudaGetErrorString(e));
     attr_set = true;
   }
@@ -1182,7 +1196,34 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmDev& p, int
   const unsigned tm = (unsigned)((p.M + BM - 1) / BM), tn = (unsigned)((p.N + BN - 1) / BN);
   dim3 grid = p.m_in_x ? dim3(tm, tn, gz) : dim3(tn, tm, gz);
   cudaError_t e;
-  if (p.csplit > 1) {
+  if constexpr (MC == 2) {
+    // CTA pairs along the N tiles (blockIdx.x): TMA multicast of the shared A tile
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = dyn_smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[3];
+    int na = 0;
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = 2;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+    if (g_use_pdl) {
+      attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[na].val.programmaticStreamSerializationAllowed = 1;
+      ++na;
+    }
+    if (g_launch_priority != 0) {
+      attr[na].id = cudaLaunchAttributePriority;
+      attr[na].val.priority = g_launch_priority;
+      ++na;
+    }
+    cfg.attrs = attr;
+    cfg.numAttrs = na;
+    e = cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<BN, STAGES, MC>, tmA, tmB, p);
+  } else if (p.csplit > 1) {
     // thread-block cluster (1,1,csplit): the K slices of one output tile are co-scheduled and reduce through DSMEM
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = grid;
@@ -1198,9 +1239,9 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmDev& p, int
     attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = g_use_pdl ? 2 : 1;
-    e = cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<BN, STAGES>, tmA, tmB, p);
+    e = cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<BN, STAGES, MC>, tmA, tmB, p);
   } else {
-    e = launch_kernel_early(gemm_tcgen05_kernel<BN, STAGES>, grid, dim3(kThreads), dyn_smem, st, tmA, tmB, p);
+    e = launch_kernel_early(gemm_tcgen05_kernel<BN, STAGES, MC>, grid, dim3(kThreads), dyn_smem, st, tmA, tmB, p);
   }
   if (e != cudaSuccess) return fail(AE_ECUDA, "ae_gemm launch: %s", cudaGetErrorString(e));
   return launched("ae_gemm");
@@ -1234,6 +1275,8 @@ extern "C" void ae_set_tile_model_reduce(int launch_ns, int bytes_per_us) {
   g_reduce_us = launch_ns * 1e-3;
   g_reduce_bw = bytes_per_us;
 }
+static int g_multicast = 0;   // measured slower at batch 2 (+5..+21 % per shape, profiles/r01_gemm_table_v33_B2_multicast.log): opt-in
+extern "C" void ae_set_multicast(int on) { g_multicast = on ? 1 : 0; }
 static int g_shallow_kb = 0;
 extern "C" void ae_set_shallow_kblocks(int kb) { g_shallow_kb = kb; }
 static int g_shared_sm = 0;
@@ -1476,6 +1519,18 @@ extern "C" int ae_gemm(const ae_gemm_args* a, ae_stream stream) {
   // ONE such CTA (<= ~103 KB: 3 / 4 / 5 stages at BN = 128 / 64 / 32) gets the next free slot.  Same bits either way:
   // the ring depth changes the buffering, not the order of the accumulation.
   const bool shared_sm = g_shared_sm && CS == 1 && !a->force_stages;
+  // A-tile multicast across a pair of N tiles: sub-wave (deep) linear grids with an even number of N tiles
+  const long long tiles_n_ll = (a->N + bn - 1) / bn;
+  const bool mc = deep && CS == 1 && !p.conv && batch == 1 && !q.m_in_x && tiles_n_ll % 2 == 0 && !a->force_stages &&
+                  (a->force_multicast > 0 || (a->force_multicast == 0 && g_multicast));
+  CUtensorMap tmA_mc;
+  if (mc) {
+    uint64_t dims[3] = {(uint64_t)a->K, (uint64_t)a->M, 1};
+    uint64_t str[2] = {(uint64_t)a->lda * 2, (uint64_t)((int64_t)a->M * a->lda) * 2};
+    uint32_t box[3] = {BK, BM / 2, 1};
+    rc = make_tmap(&tmA_mc, a->A, 3, dims, str, box);
+    if (rc) return rc;
+  }
   // multi-wave grids with a short K loop: a 2-stage ring lets three CTAs share an SM (the CTA's fixed costs — launch,
   // TMEM allocation, pipeline ramp, epilogue — dominate its lifetime, so residency buys more than ring depth)
   // multi-wave grids: persistent CTAs with a double-buffered TMEM accumulator (gemm_persistent_kernel)
@@ -1502,6 +1557,19 @@ extern "C" int ae_gemm(const ae_gemm_args* a, ae_stream stream) {
   } else if (!deep && bn == 128 && CS == 1 && (a->force_stages == 2 || (!a->force_stages && p.num_kblocks <= g_shallow_kb)))
     rc = launch<128, 2>(tmA, tmB, q, gz, st);
   else
+  if (mc) {
+    switch (bn) {
+      case 32:
+        rc = shared_sm ? launch<32, 5, 2>(tmA_mc, tmB, q, gz, st) : launch<32, 6, 2>(tmA_mc, tmB, q, gz, st);
+        break;
+      case 64:
+        rc = shared_sm ? launch<64, 4, 2>(tmA_mc, tmB, q, gz, st) : launch<64, 6, 2>(tmA_mc, tmB, q, gz, st);
+        break;
+      default:
+        rc = shared_sm ? launch<128, 3, 2>(tmA_mc, tmB, q, gz, st) : launch<128, 6, 2>(tmA_mc, tmB, q, gz, st);
+        break;
+    }
+  } else
   switch (bn) {
     case 32:
       rc = deep ? (shared_sm ? launch<32, 5>(tmA, tmB, q, gz, st) : launch<32, 6>(tmA, tmB, q, gz, st))

@@ -66,6 +66,9 @@ void ae_set_headroom(int on);
 void ae_set_persistent_min_tiles(int tiles);
 /* Tile model constants: what a split-K reduce pass is charged (launch nanoseconds, bytes per microsecond). */
 void ae_set_tile_model_reduce(int launch_ns, int bytes_per_us);
+/* 1: sub-wave linear GEMM grids with an even number of N tiles run as CTA pairs (thread-block clusters of 2 along N)
+ * that share the A tile by TMA multicast: each CTA pulls half of the A panel through L2.  Same bits. */
+void ae_set_multicast(int on);
 /* DIAGNOSTIC ONLY: drop the launches of kernel families (1 GEMM, 2 split-K reduce, 4 GroupNorm statistics,
  * 8 GroupNorm apply, 16 LayerNorm, 32 attention) to measure a family's marginal cost inside a captured graph
  * (tools/kernel_share.py).  Outputs are meaningless while the mask is non-zero. */
@@ -219,6 +222,7 @@ typedef struct {
   int64_t* colstats;
   int32_t cs_rows_per_sample;
   int32_t force_persistent; /* 0 auto (ae_set_persistent_min_tiles), 1 persistent kernel, -1 one CTA per tile */
+  int32_t force_multicast;  /* 0 auto (ae_set_multicast), 1 pair the N tiles and TMA-multicast the A tile, -1 never */
 } ae_gemm_args;
 int ae_gemm(const ae_gemm_args*, ae_stream stream);
 /* 1 if the implicit-conv fast path supports this geometry (else use ae_im2col + plain GEMM) */

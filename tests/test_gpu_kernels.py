@@ -271,6 +271,28 @@ def test_gemm_persistent_same_bits(ops, M, N, K, kind):
         assert relerr(outs[1][0], ref) < 2e-5
 
 
+@pytest.mark.parametrize("M,N,K,S,bn", [(128, 960, 960, 1, 0), (128, 960, 960, 1, 64), (512, 576, 576, 1, 0),
+                                        (128, 960, 3840, 0, 0), (128, 960, 3840, 3, 32), (100, 960, 960, 1, 0),
+                                        (128, 7680, 960, 1, 128), (256, 2880, 960, 1, 0), (128, 64, 4096, 8, 32)])
+def test_gemm_multicast_pairs_same_bits(ops, M, N, K, S, bn):
+    """CTA pairs that share the A tile by TMA multicast (sub-wave linear grids) produce the bits of the unpaired
+    kernel, with and without split-K, ragged M included."""
+    A = rnd((M, K), 1, dtype=BF)
+    W = rnd((N, K), 2, 1 / math.sqrt(K), dtype=BF)
+    bias, res = rnd((N,), 3), rnd((M, N), 4)
+    outs = []
+    for mc in (-1, 1, 1):
+        o32 = torch.zeros(M, N, device="cuda")
+        o16 = torch.zeros(M, N, device="cuda", dtype=BF)
+        ops.gemm(A, W, out_f32=o32, out_bf16=o16, bias=bias, residual=res, force_split=S, force_bn=bn,
+                 force_multicast=mc)
+        outs.append((o32, o16))
+    for a, b, c in zip(*outs):
+        assert torch.equal(a, b) and torch.equal(b, c)
+    ref = A.float() @ W.float().t() + bias + res
+    assert relerr(outs[1][0], ref) < 2e-5
+
+
 def test_gemm_persistent_implicit_conv(ops):
     B, H, Wd, C, Co = 24, 64, 16, 192, 192
     x = rnd((B, H, Wd, C), 1, dtype=BF)
