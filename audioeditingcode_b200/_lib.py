@@ -29,7 +29,8 @@ class AeGemmArgs(C.Structure):
                 ("kw", i32), ("dil_h", i32), ("dil_w", i32), ("force_bn", i32), ("splitk_ws", vp), ("splitk_ws_bytes", i64),
                 ("force_split", i32), ("force_csplit", i32), ("w_dynamic", i32), ("force_stages", i32),
                 ("colstats", vp), ("cs_rows_per_sample", i32), ("force_persistent", i32),
-                ("force_multicast", i32)]
+                ("force_multicast", i32), ("sm_L", i32), ("sm_block", i32), ("sm_rows", i32), ("sm_slot", vp),
+                ("sm_bias", vp)]
 
 
 _SIGS = {

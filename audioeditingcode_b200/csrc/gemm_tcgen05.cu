@@ -67,7 +67,46 @@ struct GemmDev {
   // GroupNorm column statistics of the OUTPUT (see ae_gemm_args.colstats): fixed-point accumulators [sample][N][2]
   unsigned long long* colstats;
   int cs_rows;   // rows per sample (multiple of 32)
+  // act == 3: grouped softmax over the output columns (cross-attention against frozen text folded into two GEMMs,
+  // see ae_gemm_args.sm_*): column n = (text_row * heads + head) * sm_L + key
+  int sm_L, sm_block, sm_rows;
+  const int* sm_slot;
+  const float* sm_bias;
 };
+
+// softmax over groups of L consecutive accumulator columns of one output row (one (text row, head) each); groups of
+// other text rows than the sample's own are zeroed.  `bias` (optional): additive, per (text row, key).
+template <int L>
+__device__ __forceinline__ void softmax_groups(float (&acc)[32], int nbase, int block, int my_row, const float* bias) {
+#pragma unroll
+  for (int g = 0; g < 32 / L; ++g) {
+    const int r = (nbase + g * L) / block;
+    if (r != my_row) {
+#pragma unroll
+      for (int l = 0; l < L; ++l) acc[g * L + l] = 0.f;
+      continue;
+    }
+    float mx = -INFINITY;
+#pragma unroll
+    for (int l = 0; l < L; ++l) {
+      float v = acc[g * L + l];
+      if (bias) v += __ldg(bias + r * L + l);
+      acc[g * L + l] = v;
+      mx = fmaxf(mx, v);
+    }
+    float sum = 0.f;
+#pragma unroll
+    for (int l = 0; l < L; ++l) {
+      float e;
+      asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"((acc[g * L + l] - mx) * 1.4426950408889634f));
+      acc[g * L + l] = e;
+      sum += e;
+    }
+    const float inv = 1.0f / sum;
+#pragma unroll
+    for (int l = 0; l < L; ++l) acc[g * L + l] *= inv;
+  }
+}
 
 // Fixed-point scales of the column statistics: sum * 2^28, sum of squares * 2^24, accumulated with integer atomics —
 // integer addition is associative, so the totals do not depend on the order in which CTAs arrive (deterministic),
@@ -168,7 +207,12 @@ __device__ __forceinline__ void epilogue_chunk(const GemmDev& p, float (&acc)[32
     }
   }
   int obase = nbase, ovalid = nvalid;
-  if (p.act == 1) {
+  if (p.act == 3) {
+    const int my_row = __ldg(p.sm_slot + m / p.sm_rows);
+    if (p.sm_L == 8) softmax_groups<8>(acc, nbase, p.sm_block, my_row, p.sm_bias);
+    else if (p.sm_L == 16) softmax_groups<16>(acc, nbase, p.sm_block, my_row, p.sm_bias);
+    else softmax_groups<32>(acc, nbase, p.sm_block, my_row, p.sm_bias);
+  } else if (p.act == 1) {
 #pragma unroll
     for (int j = 0; j < 32; ++j) acc[j] = silu_f(acc[j]);
   } else if (p.act == 2) {
@@ -1295,7 +1339,7 @@ extern "C" int ae_gemm(const ae_gemm_args* a, ae_stream stream) {
   AE_CHECK_ARG(a && a->A && a->W, "ae_gemm: null operand");
   AE_CHECK_ARG(a->M > 0 && a->N > 0 && a->K > 0, "ae_gemm: bad shape M=%d N=%d K=%d", a->M, a->N, a->K);
   AE_CHECK_ARG(a->out_f32 || a->out_bf16, "ae_gemm: no output");
-  AE_CHECK_ARG(a->act >= 0 && a->act <= 2, "ae_gemm: act must be 0 (none), 1 (SiLU) or 2 (GEGLU)");
+  AE_CHECK_ARG(a->act >= 0 && a->act <= 3, "ae_gemm: act must be 0 (none), 1 (SiLU), 2 (GEGLU) or 3 (grouped softmax)");
   AE_CHECK_ARG(a->act != 2 || a->N % 32 == 0, "ae_gemm: GEGLU epilogue needs N %% 32 == 0 (N=%d)", a->N);
   const int batch = a->batch > 0 ? a->batch : 1;
   GemmDev p;
@@ -1324,6 +1368,21 @@ extern "C" int ae_gemm(const ae_gemm_args* a, ae_stream stream) {
   p.csplit = 0;
   p.fast_epi = 0;
   p.m_in_x = (a->M + BM - 1) / BM > 65535 ? 1 : 0;
+  p.sm_L = p.sm_block = p.sm_rows = 0;
+  p.sm_slot = nullptr;
+  p.sm_bias = nullptr;
+  if (a->act == 3) {
+    AE_CHECK_ARG(batch == 1 && !a->out_f32 && a->out_bf16 && !a->residual && !a->rowbias && !a->bias,
+                 "ae_gemm: act 3 (grouped softmax) takes a plain bf16 output");
+    AE_CHECK_ARG((a->sm_L == 8 || a->sm_L == 16 || a->sm_L == 32) && a->sm_block > 0 && a->sm_block % a->sm_L == 0 &&
+                     a->N % a->sm_block == 0 && a->N % 32 == 0 && a->sm_slot && a->sm_rows > 0 && a->M % a->sm_rows == 0,
+                 "ae_gemm: bad grouped-softmax geometry (L=%d block=%d N=%d rows=%d)", a->sm_L, a->sm_block, a->N, a->sm_rows);
+    p.sm_L = a->sm_L;
+    p.sm_block = a->sm_block;
+    p.sm_rows = a->sm_rows;
+    p.sm_slot = a->sm_slot;
+    p.sm_bias = a->sm_bias;
+  }
   p.colstats = nullptr;
   p.cs_rows = 1;
   if (a->colstats) {
@@ -1381,8 +1440,8 @@ extern "C" int ae_gemm(const ae_gemm_args* a, ae_stream stream) {
   //      L2 (~70 KB/us measured: [128x960x960] takes 9.9 / 7.7 / 6.5 us at BN = 128 / 64 / 32), so the tile width and
   //      the K split are chosen together to minimise the operand bytes per SM, charging a split for its reduce launch.
   const long long tiles_m = (a->M + BM - 1) / BM;
-  const bool may_split = batch == 1 && a->act != 2 && a->splitk_ws && a->N % 4 == 0 && a->force_split != 1 &&
-                         a->force_csplit <= 1;
+  const bool may_split = batch == 1 && a->act != 2 && a->act != 3 && a->splitk_ws && a->N % 4 == 0 &&
+                         a->force_split != 1 && a->force_csplit <= 1;
   int bn = a->force_bn;
   int S_model = 0;   // 0: no model decision (forced / large grid)
   if (bn == 0) {
@@ -1443,7 +1502,7 @@ extern "C" int ae_gemm(const ae_gemm_args* a, ae_stream stream) {
   }
   // ---- workspace split-K (two launches): partial tiles to an fp32 workspace, fixed-order reduce + epilogue kernel
   int S = 1;
-  if (CS == 1 && batch == 1 && a->act != 2 && a->splitk_ws && a->N % 4 == 0 && a->force_split != 1) {
+  if (CS == 1 && batch == 1 && a->act != 2 && a->act != 3 && a->splitk_ws && a->N % 4 == 0 && a->force_split != 1) {
     if (a->force_split > 1)
       S = a->force_split;
     else if (S_model > 0)
@@ -1494,7 +1553,7 @@ extern "C" int ae_gemm(const ae_gemm_args* a, ae_stream stream) {
     // half of that for the GEGLU output whose lanes own 2 columns)
     auto al = [](const void* ptr, uintptr_t b) { return (reinterpret_cast<uintptr_t>(ptr) & (b - 1)) == 0; };
     const bool g = q.act == 2;
-    bool ok = CS == 1 && g_fast_epi && (g ? (a->N % 32 == 0 && !q.residual && !q.rowbias) : (a->N % 4 == 0));
+    bool ok = CS == 1 && g_fast_epi && q.act != 3 && (g ? (a->N % 32 == 0 && !q.residual && !q.rowbias) : (a->N % 4 == 0));
     ok = ok && (!q.bias || al(q.bias, 16));
     ok = ok && (!q.rowbias || (al(q.rowbias, 16) && q.ld_rowbias % 4 == 0));
     ok = ok && (!q.residual || (al(q.residual, 16) && q.ld_res % 4 == 0 && q.stride_res % 4 == 0));

@@ -85,7 +85,7 @@ class CudaOps:
     def gemm(self, A, W, *, out_f32=None, out_bf16=None, bias=None, rowbias=None, rows_per_group=1, residual=None,
              act=0, alpha=1.0, conv=None, M=None, K=None, force_bn=0, batch=1, strideA=0, strideW=0, stride_out=0,
              stride_res=0, lda=None, ldw=None, force_split=0, ld_out_f32=None, ld_out_bf16=None, force_stages=0,
-             w_dynamic=False, force_csplit=0, colstats=None, cs_rows=0, force_persistent=0, force_multicast=0):
+             w_dynamic=False, force_csplit=0, colstats=None, cs_rows=0, force_persistent=0, force_multicast=0, softmax=None):
         """D = alpha*A@W^T (+bias)(+rowbias[row//rows_per_group])(+residual) -> act.  conv=(B,H,W,C,kh,kw,dh,dw)
         turns A (channels-last image) into an implicit-GEMM operand."""
         a = AeGemmArgs()
@@ -131,10 +131,17 @@ class CudaOps:
         a.force_csplit = force_csplit
         a.force_persistent = force_persistent
         a.force_multicast = force_multicast
+        if softmax is not None:             # act 3: (keys per group, columns per text row, slot map, rows per sample, bias)
+            L_, block, slot, rows, sbias = softmax
+            a.act = 3
+            a.sm_L, a.sm_block, a.sm_rows = int(L_), int(block), int(rows)
+            a.sm_slot = slot.data_ptr()
+            if sbias is not None:
+                a.sm_bias = sbias.data_ptr()
         if colstats is not None:            # GroupNorm statistics of the output, accumulated by the epilogue
             a.colstats = colstats.data_ptr()
             a.cs_rows_per_sample = int(cs_rows)
-        if batch == 1 and act != 2:
+        if batch == 1 and act != 2 and softmax is None:
             ws = self._splitk_workspace(A.device)
             a.splitk_ws = ws.data_ptr()
             a.splitk_ws_bytes = ws.numel() * 4

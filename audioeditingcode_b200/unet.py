@@ -36,6 +36,9 @@ class TextCache:
     def __init__(self, n_rows: int):
         self.n_rows = n_rows
         self.kv: Dict[str, torch.Tensor] = {}       # layer prefix -> bf16 [n_rows, L, 2C]
+        # layer prefix -> (KW [R*heads*Lp, C], VW [C, R*heads*Lp], Lp, heads, bias [R, Lp] or None): the cross-attention
+        # of the layer folded into two GEMMs (the text is frozen: K.Wq and Wo.V^T are constants of the run)
+        self.folded: Dict[str, tuple] = {}
         self.bias: List[Optional[torch.Tensor]] = []  # per stream: fp32 [n_rows, L] or None
         self.lens: List[int] = []
 
@@ -154,6 +157,7 @@ class UNetEngine:
         self.dual_stream_max_b = int(os.environ.get("AEDIT_DUAL_STREAM_MAX_B", "4"))
         self._ops_b = None
         self.fwd_headroom = os.environ.get("AEDIT_FWD_HEADROOM", "0") != "0"
+        self.fold_cross_attn = os.environ.get("AEDIT_FOLD_CROSS_ATTN", "1") != "0" and hasattr(ops, "lib")
         self.pdl_extra = [0, 0, 15]     # per lane (forward chunks, reverse solo, reverse shared-SM); see GraphedForward
         # GroupNorm statistics from the producing GEMM's epilogue (ae_gemm_args.colstats): every GEMM whose fp32 output
         # feeds a GroupNorm accumulates per-(sample, channel) sums into a slice of one arena that is zeroed once per
@@ -314,7 +318,54 @@ class UNetEngine:
             out = self.ops.empty((R, s.shape[1], Wkv.shape[0]), self.adt, self.device)
             self.ops.gemm(s.reshape(-1, s.shape[-1]), Wkv, out_bf16=out.reshape(-1, Wkv.shape[0]))
             tc.kv[p] = out
+            if self.fold_cross_attn:
+                self._fold_cross_attention(tc, p, out, tc.bias[spec[1]])
         return tc
+
+    def _heads_of(self, prefix: str) -> int:
+        parts = prefix.split(".")
+        nlev = len(self.cfg.block_out_channels)
+        if parts[0] == "down_blocks":
+            level = int(parts[1])
+        elif parts[0] == "up_blocks":
+            level = nlev - 1 - int(parts[1])
+        else:
+            level = nlev - 1
+        return self.cfg.num_heads[level]
+
+    def _fold_cross_attention(self, tc: TextCache, p: str, kv: torch.Tensor, bias: Optional[torch.Tensor]):
+        """Cross-attention against frozen text as two GEMMs (include/aedit.h, ae_gemm_args.sm_*): precompute
+        KW[(r,h,l), c] = scale * sum_j K_r[l, h*d+j] Wq[h*d+j, c] and VW[c, (r,h,l)] = sum_j Wo[c, h*d+j] V_r[l, h*d+j]
+        with the library's own GEMM (one batched call over the heads per text row)."""
+        ops = self.ops
+        R, L, C2 = kv.shape
+        C = C2 // 2
+        heads = self._heads_of(p)
+        d = C // heads
+        Lp = 8 if L <= 8 else (16 if L <= 16 else (32 if L <= 32 else 0))
+        if Lp == 0 or (d * 2) % 16 != 0 or (R * heads * Lp) % 32 != 0:
+            return
+        WqT = self.w.get(p + ".to_q.weightT")
+        if WqT is None:
+            WqT = self.w[p + ".to_q.weight"].t().contiguous()        # [C_in, C_out]: row c, column h*d+j
+            self.w[p + ".to_q.weightT"] = WqT
+        Wo = self.w[p + ".to_out.0.weight"]                             # [C_out, C_in = heads*d]
+        NK = R * heads * Lp
+        KW = torch.zeros((NK, C), dtype=self.adt, device=self.device)
+        VW = torch.zeros((C, NK), dtype=self.adt, device=self.device)
+        scale = float(d) ** -0.5
+        for r in range(R):
+            # KW rows of text row r: per head z, A = K_r[:, z*d:(z+1)*d] (L x d), W = WqT[:, z*d:(z+1)*d] (C x d)
+            ops.gemm(kv[r], WqT, out_bf16=KW[r * heads * Lp:], M=L, K=d, lda=C2, ldw=C, batch=heads, strideA=d,
+                     strideW=d, stride_out=Lp * C, ld_out_bf16=C, alpha=scale, w_dynamic=True)
+            # VW columns of text row r: per head z, A = Wo[:, z*d:(z+1)*d] (C x d), W = V_r[:, z*d:(z+1)*d] (L x d)
+            ops.gemm(Wo, kv[r, :, C:], out_bf16=VW[:, r * heads * Lp:], M=C, K=d, lda=C, ldw=C2, batch=heads,
+                     strideA=d, strideW=d, stride_out=Lp, ld_out_bf16=NK, w_dynamic=True)
+        bias_p = None
+        if bias is not None or L != Lp:
+            bias_p = torch.full((R, Lp), NEG_PAD, dtype=F32, device=self.device)
+            bias_p[:, :L] = 0.0 if bias is None else bias.to(F32)
+        tc.folded[p] = (KW, VW, Lp, heads, bias_p)
 
     # ------------------------------------------------------------------------------------------ blocks
     def _conv3x3(self, a_bf16, B, H, W, Cin, name, out, rowbias=None, rows_per_group=1, residual=None, stats=False):
@@ -390,11 +441,20 @@ class UNetEngine:
             ops.gemm(a, self.w[q + ".attn1.to_out.0.weight"], out_f32=hs, bias=self.w[q + ".attn1.to_out.0.bias"],
                      residual=hs)
             # --- attn2 (self or cross)
+            folded = False
             ops.layernorm(hs, self.w[q + ".norm2.weight"], self.w[q + ".norm2.bias"], n)
             if spec is None:
                 ops.gemm(n, self.w[q + ".attn2.qkv.weight"], out_bf16=qkv)
                 self._attention(qkv, qkv[:, C:], qkv[:, 2 * C:], a, heads, B, T, T, 3 * C, T * 3 * C, 3 * C,
                                 T * 3 * C, 3 * C, T * 3 * C)
+            elif text is not None and (q + ".attn2") in text.folded:
+                # frozen text: scores = n . KW^T with the per-head softmax in the epilogue, out = P . VW^T (+ bias + hs)
+                KW, VW, Lp, fh, fbias = text.folded[q + ".attn2"]
+                sm = slot_map if slot_map is not None else self._identity_slots(B)
+                P = ops.empty((M, KW.shape[0]), self.adt, self.device)
+                ops.gemm(n, KW, out_bf16=P, softmax=(Lp, fh * Lp, sm, T, fbias))
+                ops.gemm(P, VW, out_f32=hs, bias=self.w[q + ".attn2.to_out.0.bias"], residual=hs)
+                folded = True
             else:
                 if text is None or (q + ".attn2") not in text.kv:
                     raise ValueError("cross-attention layer needs prepared text (UNetEngine.prepare_text)")
@@ -404,8 +464,9 @@ class UNetEngine:
                 L = kv.shape[1]
                 self._attention(qq, kv, kv[:, :, C:], a, heads, B, T, L, 3 * C, T * 3 * C, 2 * C, L * 2 * C, 2 * C,
                                 L * 2 * C, kv_map=slot_map, bias=text.bias[spec[1]])
-            ops.gemm(a, self.w[q + ".attn2.to_out.0.weight"], out_f32=hs, bias=self.w[q + ".attn2.to_out.0.bias"],
-                     residual=hs)
+            if not folded:
+                ops.gemm(a, self.w[q + ".attn2.to_out.0.weight"], out_f32=hs, bias=self.w[q + ".attn2.to_out.0.bias"],
+                         residual=hs)
             # --- GEGLU feed-forward
             ops.layernorm(hs, self.w[q + ".norm3.weight"], self.w[q + ".norm3.bias"], n)
             gg = ops.empty((M, 4 * C), self.adt, self.device)
@@ -419,6 +480,13 @@ class UNetEngine:
         ops.gemm(hs_b, self.w[p + ".proj_out.weight"], out_f32=out, bias=self.w[p + ".proj_out.bias"],
                  residual=x.reshape(M, C), **self._cs_take(out, B, T))
         return out.view(B, T, C)
+
+    def _identity_slots(self, B: int) -> torch.Tensor:
+        t = self.__dict__.setdefault("_id_slots", {}).get(B)
+        if t is None:
+            t = torch.arange(B, dtype=torch.int32, device=self.device)
+            self._id_slots[B] = t
+        return t
 
     def _site(self, x, B, H, W, base, idx0, level, text, slot_map):
         cfg = self.cfg

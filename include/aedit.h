@@ -196,7 +196,7 @@ typedef struct {
   int64_t ld_out_f32;
   void* out_bf16;
   int64_t ld_out_bf16;
-  int32_t act; /* 0 none, 1 SiLU, 2 GEGLU: W rows interleaved in blocks of 32 (16 value rows, 16 gate rows); the
+  int32_t act; /* 3 = grouped softmax (see sm_* below); 0 none, 1 SiLU, 2 GEGLU: W rows interleaved in blocks of 32 (16 value rows, 16 gate rows); the
                   output has N/2 columns: out[16q+i] = acc[32q+i] * gelu(acc[32q+16+i])   (attention.py:37-44) */
   float alpha;
   /* implicit convolution */
@@ -223,6 +223,17 @@ typedef struct {
   int32_t cs_rows_per_sample;
   int32_t force_persistent; /* 0 auto (ae_set_persistent_min_tiles), 1 persistent kernel, -1 one CTA per tile */
   int32_t force_multicast;  /* 0 auto (ae_set_multicast), 1 pair the N tiles and TMA-multicast the A tile, -1 never */
+  /* act == 3 — grouped softmax epilogue.  Cross-attention against FROZEN text (attention.py:234-262 with context =
+   * the prompt embedding, constant over all denoising steps) folds into two small GEMMs:
+   *   scores[m, (r,h,l)] = LN(x)[m,:] . KW[(r,h,l),:],  KW[(r,h,l), c] = scale * sum_j K_r[l, h*d+j] * Wq[h*d+j, c]
+   *   out[m, c]          = sum_(r,h,l) P[m,(r,h,l)] * VW[c,(r,h,l)] (+ bias + residual),  VW = Wo_h . V_r,h^T
+   * where P = softmax over l within each (r, h) group for r = sm_slot[m / sm_rows] (the sample's text row) and 0 for the
+   * other text rows.  This call computes `scores` and writes P (bf16): sm_L = padded keys per group (8, 16 or 32),
+   * sm_block = heads * sm_L columns per text row, sm_bias (optional) additive fp32 [rows, sm_L] (key mask: 0 keep,
+   * -10000 discard as models.py:204-210, -1e30 for padding keys). */
+  int32_t sm_L, sm_block, sm_rows;
+  const int32_t* sm_slot;
+  const float* sm_bias;
 } ae_gemm_args;
 int ae_gemm(const ae_gemm_args*, ae_stream stream);
 /* 1 if the implicit-conv fast path supports this geometry (else use ae_im2col + plain GEMM) */

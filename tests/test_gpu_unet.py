@@ -68,6 +68,34 @@ def test_unet_tiny_vs_oracle(name, H):
     _check(hs, hs_ref, rel=2e-2)
 
 
+@pytest.mark.parametrize("name", ["tiny-audioldm2", "tiny-tango"])
+def test_folded_cross_attention_matches_attention_kernel(name):
+    """Cross-attention against the frozen text as two GEMMs (scores = LN(x).(K.Wq)^T with the per-head softmax in the
+    epilogue, out = P.(Wo.V^T)^T) agrees with the q-projection / attention kernel / out-projection path to bf16
+    accuracy; masks, padded key slots and the per-sample text row selection included."""
+    cfg = C.preset(name)
+    w = U.synthetic_weights(cfg, seed=0)
+    gen = torch.Generator().manual_seed(5)
+    B, H, W = 4, 32, 16
+    x = torch.randn(B, 8, H, W, generator=gen).cuda()
+    t = torch.tensor([981, 441, 1, 601]).cuda()
+    dims = {s[1]: s[0] for s in cfg.transformer_specs if s is not None}
+    lens = [8, 13]
+    streams = [torch.randn(2, lens[i % 2], dims[i], generator=gen).cuda() for i in range(cfg.n_streams)]
+    masks = [torch.ones(2, lens[i % 2]).cuda() for i in range(cfg.n_streams)]
+    masks[-1][1, -3:] = 0
+    slot = torch.tensor([0, 1, 1, 0], dtype=torch.int32).cuda()
+    outs = []
+    for fold in (False, True):
+        eng = _engine(cfg, w)
+        eng.fold_cross_attn = fold
+        text = eng.prepare_text(streams, masks)
+        assert bool(text.folded) == fold
+        outs.append(eng.forward(x, t, text=text, slot_map=slot))
+    r = ((outs[0] - outs[1]).norm() / outs[0].norm()).item()
+    assert r < 1e-2, r
+
+
 def test_unet_audioldm_s_5s():
     """BASELINE config 1 geometry: AudioLDM-S, 5 s clip -> latent [*,8,128,16]; B=2 (one CFG pair)."""
     cfg = C.preset("audioldm-s")
