@@ -26,6 +26,10 @@ def get_noise_pred(ldm_model: PipelineWrapper, latent: torch.Tensor, t: torch.Te
     text_hs, text_cl, text_mask = text_emb
     un_hs, un_cl, un_mask = uncond_emb
     with torch.no_grad():
+        if hasattr(ldm_model, "cfg_pair_eval") and latent.is_cuda:
+            # one batched, graph-cached evaluation for the pair (the reference issues two: ddim_inversion.py:31-38)
+            eps_u, eps_c = ldm_model.cfg_pair_eval(latent, latent, t, (un_hs, un_cl, un_mask), (text_hs, text_cl, text_mask))
+            return eps_u + cfg_scale * (eps_c - eps_u)
         uncond_out, _, _ = ldm_model.unet_forward(latent, timestep=t, encoder_hidden_states=un_hs, class_labels=un_cl,
                                                   encoder_attention_mask=un_mask)
         cond_out, _, _ = ldm_model.unet_forward(latent, timestep=t, encoder_hidden_states=text_hs, class_labels=text_cl,

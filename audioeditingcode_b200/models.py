@@ -266,6 +266,41 @@ class PipelineWrapper(torch.nn.Module):
             return (out,)
         return UNet2DConditionOutput(sample=out), h_space, extracted
 
+    def cfg_pair_eval(self, x_u: torch.Tensor, x_c: torch.Tensor, timestep, uncond, cond
+                      ) -> Tuple[torch.Tensor, torch.Tensor]:
+        """eps(x_u | uncond) and eps(x_c | cond) — what two `unet_forward` calls return as `.sample` (pc_drift.py:70-83,
+        ddim_inversion.py:23-41) — as ONE batched, CUDA-graph-cached U-Net evaluation (B = 2n rows) instead of two eager
+        ones.  uncond / cond: (encoder_hidden_states, class_labels, encoder_attention_mask) triples as returned by
+        encode_text, with 1 or n rows each."""
+        from .ddm_inversion import inversion_utils as IU
+        n = x_u.shape[0]
+        flat = [v for tr in (uncond, cond) for v in tr]
+        key = ("pair", n) + tuple(None if v is None else (v.data_ptr(), tuple(v.shape), v._version) for v in flat)
+        cache = self.__dict__.setdefault("_pair_text_cache", {})
+        hit = cache.get(key)
+        if hit is None:
+            if len(cache) > 8:
+                cache.clear()
+            streams, masks, cl = IU._cat_text(self, uncond, cond)
+            ru = next((v.shape[0] for v in uncond if v is not None), 1)
+            rc = next((v.shape[0] for v in cond if v is not None), 1)
+            if ru not in (1, n) or rc not in (1, n):
+                raise ValueError(f"text batches {ru} / {rc} do not match the sample batch {n}")
+            slot = torch.cat([torch.arange(n, dtype=torch.int32) if ru == n else torch.zeros(n, dtype=torch.int32),
+                              ru + (torch.arange(n, dtype=torch.int32) if rc == n else torch.zeros(n, dtype=torch.int32))]
+                             ).to(self.device)
+            text = self.engine.prepare_text(streams, masks) if streams else None
+            cl_rows = None if cl is None else cl.index_select(0, slot.long())
+            hit = (text, cl_rows, slot, (ru, rc), (flat, streams, masks))
+            cache[key] = hit
+        text, cl_rows, slot, (ru, rc), _ = hit
+        if not torch.is_tensor(timestep):
+            timestep = torch.tensor(timestep)
+        t_in = timestep.reshape(-1)[:1].to(self.device, torch.int64).expand(2 * n).contiguous()
+        x = torch.cat([x_u, x_c], 0).to(self.device, torch.float32)
+        eps = IU._unet_eval(self, x, t_in, text, slot, cl_rows, slot_key=("pair", n, ru, rc))
+        return eps[:n], eps[n:]
+
     # ---------------------------------------------------------------- text (a13) — synthetic fallback
     def _synthetic_text(self, prompts: List[str], dim: int, L: Optional[int], normalize: bool, salt: int):
         """Deterministic stand-in embeddings when no text-encoder checkpoint is on disk (no network here):

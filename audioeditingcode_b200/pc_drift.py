@@ -60,16 +60,25 @@ def forward_directional(ldm_stable, xt: torch.Tensor, timestep: torch.Tensor, la
             embedding_hidden_states=expand_for_evs(text_emb.embedding_hidden_states, n_ev),
             boolean_prompt_mask=expand_for_evs(text_emb.boolean_prompt_mask, n_ev),
             embedding_class_lables=expand_for_evs(text_emb.embedding_class_lables, n_ev))
+    x_u = input if mode == PCStreamChoice.BOTH or mode == PCStreamChoice.UNCOND else xt
+    x_c = input if mode == PCStreamChoice.BOTH or mode == PCStreamChoice.TEXT else xt
     with torch.no_grad():
-        uncond_out, _, _ = ldm_stable.unet_forward(
-            input if mode == PCStreamChoice.BOTH or mode == PCStreamChoice.UNCOND else xt, timestep=timestep,
-            encoder_hidden_states=uncond_emb.embedding_hidden_states, class_labels=uncond_emb.embedding_class_lables,
-            encoder_attention_mask=uncond_emb.boolean_prompt_mask)
-        cond_out, _, _ = ldm_stable.unet_forward(
-            input if mode == PCStreamChoice.BOTH or mode == PCStreamChoice.TEXT else xt, timestep=timestep,
-            encoder_hidden_states=text_emb.embedding_hidden_states, class_labels=text_emb.embedding_class_lables,
-            encoder_attention_mask=text_emb.boolean_prompt_mask)
-    noise_pred = uncond_out.sample + cfg_tar * (cond_out.sample - uncond_out.sample)             # pc_drift.py:83
+        if hasattr(ldm_stable, "cfg_pair_eval") and x_u.is_cuda:
+            # one batched, graph-cached evaluation for the pair (the reference issues two: pc_drift.py:70-81)
+            eps_u, eps_c = ldm_stable.cfg_pair_eval(
+                x_u, x_c, timestep,
+                (uncond_emb.embedding_hidden_states, uncond_emb.embedding_class_lables, uncond_emb.boolean_prompt_mask),
+                (text_emb.embedding_hidden_states, text_emb.embedding_class_lables, text_emb.boolean_prompt_mask))
+        else:
+            eps_u = ldm_stable.unet_forward(
+                x_u, timestep=timestep, encoder_hidden_states=uncond_emb.embedding_hidden_states,
+                class_labels=uncond_emb.embedding_class_lables,
+                encoder_attention_mask=uncond_emb.boolean_prompt_mask)[0].sample
+            eps_c = ldm_stable.unet_forward(
+                x_c, timestep=timestep, encoder_hidden_states=text_emb.embedding_hidden_states,
+                class_labels=text_emb.embedding_class_lables,
+                encoder_attention_mask=text_emb.boolean_prompt_mask)[0].sample
+    noise_pred = eps_u + cfg_tar * (eps_c - eps_u)                                               # pc_drift.py:83
     res = ldm_stable.model.scheduler.step(noise_pred, timestep, input, eta=eta, variance_noise=latent)
     return res.prev_sample, res.pred_original_sample
 

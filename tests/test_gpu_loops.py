@@ -237,6 +237,37 @@ def test_forward_reverse_overlap_bitexact(N, ts, fb):
         IU.OVERLAP = old
 
 
+@pytest.mark.parametrize("name,model_id", [("tiny-audioldm", "synthetic/audioldm-tiny"), ("tiny-audioldm2", "synthetic/audioldm2-tiny"),
+                                           ("tiny-tango", "synthetic/tango-tiny")])
+def test_cfg_pair_eval_matches_two_unet_forward_calls(name, model_id):
+    """PipelineWrapper.cfg_pair_eval (one batched, graph-cached evaluation; used by pc_drift.forward_directional and the
+    DDIM baseline) returns what the reference's two unet_forward calls return, for n = 1 and n = 3 samples."""
+    from audioeditingcode_b200 import models, unet_config as C
+    cfg = C.preset(name)
+    m = models.load_model(model_id, torch.device("cuda"), 10, weights=U.synthetic_weights(cfg, seed=0), config=cfg)
+    gen = torch.Generator().manual_seed(11)
+    dims = {sp[1]: sp[0] for sp in cfg.transformer_specs if sp is not None}
+
+    def triple(L):           # (encoder_hidden_states, class_labels, encoder_attention_mask) in the wrapper's convention
+        if name == "tiny-audioldm":
+            return None, torch.nn.functional.normalize(torch.randn(1, 512, generator=gen), dim=-1).cuda(), None
+        if name == "tiny-audioldm2":   # GPT-2 stream as hidden states, T5 stream + its mask as class_labels / mask
+            return (torch.randn(1, 8, dims[0], generator=gen).cuda(), torch.randn(1, L, dims[1], generator=gen).cuda(),
+                    torch.ones(1, L).cuda())
+        return torch.randn(1, L, dims[0], generator=gen).cuda(), None, torch.ones(1, L).cuda()
+    un, co = triple(1), triple(7)
+    for n in (1, 3):
+        x_u = torch.randn(n, 8, 32, 16, generator=gen).cuda()
+        x_c = x_u + 0.01 * torch.randn(n, 8, 32, 16, generator=gen).cuda()
+        t = m.model.scheduler.timesteps[3]
+        e_u, e_c = m.cfg_pair_eval(x_u, x_c, t, un, co)
+        r_u = m.unet_forward(x_u, timestep=t, encoder_hidden_states=un[0], class_labels=un[1], encoder_attention_mask=un[2])[0].sample
+        r_c = m.unet_forward(x_c, timestep=t, encoder_hidden_states=co[0], class_labels=co[1], encoder_attention_mask=co[2])[0].sample
+        assert _rel(e_u, r_u.cpu()) < 1e-2 and _rel(e_c, r_c.cpu()) < 1e-2
+        e_u2, e_c2 = m.cfg_pair_eval(x_u, x_c, t, un, co)          # cached graph replay: same bits
+        assert torch.equal(e_u, e_u2) and torch.equal(e_c, e_c2)
+
+
 def test_ddim_mode_vs_reference_golden():
     """`--mode ddim` baseline (ddim_inversion.py:10-84): deterministic inversion + guided regeneration through the
     drop-in functions vs the unmodified reference's outputs.  10 large DDIM steps amplify the bf16 U-Net error;
