@@ -35,6 +35,14 @@ class UNet2DConditionOutput:
         self.sample = sample
 
 
+def _ver(t: torch.Tensor) -> int:
+    """torch version counter of a tensor, or -1 for inference tensors (they carry none)."""
+    try:
+        return t._version
+    except RuntimeError:
+        return -1
+
+
 def _ptr(t: Optional[torch.Tensor]):
     return None if t is None else C.c_void_p(t.data_ptr())
 
@@ -210,7 +218,7 @@ class PipelineWrapper(torch.nn.Module):
         raise NotImplementedError
 
     def _cached_text(self, streams, masks) -> TextCache:
-        key = tuple((None if s is None else (s.data_ptr(), tuple(s.shape), s._version)) for s in list(streams) + list(masks))
+        key = tuple((None if s is None else (s.data_ptr(), tuple(s.shape), _ver(s))) for s in list(streams) + list(masks))
         tc = self._text_cache.get(key)
         if tc is None:
             if len(self._text_cache) > 16:
@@ -275,7 +283,7 @@ class PipelineWrapper(torch.nn.Module):
         from .ddm_inversion import inversion_utils as IU
         n = x_u.shape[0]
         flat = [v for tr in (uncond, cond) for v in tr]
-        key = ("pair", n) + tuple(None if v is None else (v.data_ptr(), tuple(v.shape), v._version) for v in flat)
+        key = ("pair", n) + tuple(None if v is None else (v.data_ptr(), tuple(v.shape), _ver(v)) for v in flat)
         cache = self.__dict__.setdefault("_pair_text_cache", {})
         hit = cache.get(key)
         if hit is None:

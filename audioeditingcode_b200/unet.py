@@ -87,7 +87,7 @@ class GraphedForward:
             engine.ops = engine.ops_b()
             if os.environ.get("AEDIT_REV_PRIORITY", "1") != "0":
                 engine.ops.lib.ae_set_launch_priority(engine.ops.lib.ae_greatest_priority())
-            engine.ops.lib.ae_set_shared_sm(1 if lane == 2 else 0)
+            engine.ops.lib.ae_set_shared_sm(1 if (lane == 2 and engine.shared_sm_rings) else 0)
         try:
             side.wait_stream(cur)
             with torch.cuda.stream(side):
@@ -158,6 +158,8 @@ class UNetEngine:
         self._ops_b = None
         self.fwd_headroom = os.environ.get("AEDIT_FWD_HEADROOM", "0") != "0"
         self.fold_cross_attn = os.environ.get("AEDIT_FOLD_CROSS_ATTN", "1") != "0" and hasattr(ops, "lib")
+        self.graph_placement_tries = int(os.environ.get("AEDIT_GRAPH_PLACEMENT_TRIES", "4"))
+        self.shared_sm_rings = os.environ.get("AEDIT_SHARED_SM_RINGS", "1") != "0"
         self.pdl_extra = [0, 0, 15]     # per lane (forward chunks, reverse solo, reverse shared-SM); see GraphedForward
         # GroupNorm statistics from the producing GEMM's epilogue (ae_gemm_args.colstats): every GEMM whose fp32 output
         # feeds a GroupNorm accumulates per-(sample, channel) sums into a slice of one arena that is zeroed once per
@@ -225,8 +227,41 @@ class UNetEngine:
             l0 = self.ops.launch_count()
             g = GraphedForward(self, B, H, W, text, slot_map, class_labels, lane=lane)
             g.kernels = (self.ops.launch_count() - l0) // 3       # 2 warm-ups + 1 capture
+            if B <= 4 and self.graph_placement_tries > 1:
+                g = self._tune_placement(g, (B, H, W, text, slot_map, class_labels), lane)
             self._graphs[key] = g
         return g
+
+    def _tune_placement(self, g: GraphedForward, args, lane: int) -> GraphedForward:
+        """A small-batch evaluation graph (a latency-bound chain of ~900 kernels) runs 4 % slower or faster depending on
+        where its private memory pool happens to land (bimodal: 5.97 / 6.20 ms on the same build and box,
+        profiles/r01_bimodal_probe.log) — a placement effect of the memory system, not of any setting.  The graph is
+        replayed ~100 times per job, so it is captured up to a few times (each capture gets its own pool) and the fastest
+        capture is kept."""
+        def timed(gr):
+            for _ in range(2):
+                gr.graph.replay()
+            torch.cuda.synchronize()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            for _ in range(8):
+                gr.graph.replay()
+            e.record()
+            torch.cuda.synchronize()
+            return s.elapsed_time(e) / 8
+        # every candidate stays alive until the choice is made: a freed pool would simply be handed to the next capture
+        cands, times = [g], [timed(g)]
+        for i in range(1, self.graph_placement_tries):
+            if min(times) < 0.985 * max(times):
+                break                                 # both modes seen, the fast one is in hand
+            cand = GraphedForward(self, *args, lane=lane)
+            cand.kernels = g.kernels
+            cands.append(cand)
+            times.append(timed(cand))
+        best = cands[times.index(min(times))]
+        del cands
+        best.placement_ms = [round(t, 3) for t in times]
+        return best
 
     # ------------------------------------------------------------------------------------------ weights
     def _to(self, t, dtype):

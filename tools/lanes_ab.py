@@ -11,7 +11,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench as B  # noqa: E402
 from audioeditingcode_b200.ddm_inversion import inversion_utils as IU  # noqa: E402
 
-DEFAULTS = dict(overlap=1, fb=50, head=10, rev="adaptive", pdlx=0, gnstream=1, pf=0, ps=0, pc=15, skb=0, hr=0, pmt=296)
+DEFAULTS = dict(overlap=1, fb=50, head=10, rev="adaptive", pdlx=0, gnstream=1, pf=0, ps=0, pc=15, skb=0, hr=0, pmt=296, gpt=4, rep=0, ssm=1)
 
 
 def timed(fn, reps, flush):
@@ -48,7 +48,7 @@ def main():
         for kv in v.split(","):
             k, val = kv.split("=")
             o[k] = val if k == "rev" else int(val)
-        key = (o["pdlx"], o["gnstream"], o["pf"], o["ps"], o["pc"], o["skb"], o["hr"], o["pmt"])
+        key = (o["pdlx"], o["gnstream"], o["pf"], o["ps"], o["pc"], o["skb"], o["hr"], o["pmt"], o["gpt"], o["rep"], o["ssm"])
         if key != last:
             torch.cuda.synchronize()
             m.engine._graphs.clear()
@@ -56,6 +56,8 @@ def main():
             lib.ae_set_shallow_kblocks(o["skb"])
             m.engine.fwd_headroom = bool(o["hr"])
             lib.ae_set_persistent_min_tiles(o["pmt"])
+            m.engine.graph_placement_tries = o["gpt"]
+            m.engine.shared_sm_rings = bool(o["ssm"])
             lib.ae_set_gn_stream_min_bytes((8 << 20) if o["gnstream"] else (1 << 60))
             last = key
         IU.OVERLAP = bool(o["overlap"])
@@ -63,8 +65,10 @@ def main():
         IU.DEFAULT_HEAD_CHUNK = o["head"]
         h0 = getattr(m, "overlap_hits", 0)
         ms = timed(lambda: B.run_job(m, spec, x0, o["fb"]), a.reps, flush)
+        place = {str(k[0]) + "/lane" + str(k[-1]): getattr(g, "placement_ms", None) for k, g in m.engine._graphs.items()
+                 if k[0] <= 4}
         print(json.dumps({"variant": v, "ms_per_job": round(ms, 2), "steps_per_s": round(steps / ms * 1e3, 1),
-                          "overlap_hits": getattr(m, "overlap_hits", 0) - h0}), flush=True)
+                          "overlap_hits": getattr(m, "overlap_hits", 0) - h0, "placement_ms": place}), flush=True)
 
 
 if __name__ == "__main__":
