@@ -468,6 +468,8 @@ def inversion_reverse_process(model: PipelineWrapper,
                 if fwd_done.query():
                     contended = False
             variant = 0 if not lanes else (2 if (contended or REV_VARIANT == "shared") else 1)
+            if variant == 1 and REV_VARIANT == "adaptive":
+                variant = model.engine.solo_lane(rows, x_in.shape[2], x_in.shape[3], text, ("rev", P), cl is not None)
             x_in.copy_(xt.expand(rows, -1, -1, -1))
             t_in = torch.full((rows,), t, dtype=torch.int64, device=model.device)
             eps = _unet_eval(model, x_in, t_in, text, slot, cl, slot_key=("rev", P), lane=variant)

@@ -232,6 +232,16 @@ class UNetEngine:
             self._graphs[key] = g
         return g
 
+    def solo_lane(self, B, H, W, text, slot_key, has_cl: bool) -> int:
+        """Which reverse-lane graph variant to replay when the lane has the machine to itself: 1 (deep rings, PDL on the
+        GEMMs only) unless variant 2 (rings sized for shared SMs, PDL on every family) measured faster ALONE at capture
+        time — it does for TANGO-full (6.2 vs 6.8 ms) and AudioLDM-S (2.38 vs 2.46 ms), not for AudioLDM2-large (6.47 vs
+        5.97 ms); profiles/r01_other_configs.log.  Decided from the capture-time timings, so it costs nothing per step."""
+        g1 = self._graphs.get((B, H, W, id(text), slot_key, has_cl, 1))
+        g2 = self._graphs.get((B, H, W, id(text), slot_key, has_cl, 2))
+        t1, t2 = getattr(g1, "placement_ms", None), getattr(g2, "placement_ms", None)
+        return 2 if (t1 and t2 and min(t2) < 0.99 * min(t1)) else 1
+
     def _tune_placement(self, g: GraphedForward, args, lane: int) -> GraphedForward:
         """A small-batch evaluation graph (a latency-bound chain of ~900 kernels) runs 4 % slower or faster depending on
         where its private memory pool happens to land (bimodal: 5.97 / 6.20 ms on the same build and box,

@@ -39,6 +39,12 @@ CONFIGS = {
     # BASELINE.json configs[0] geometry (the reference's CPU-runnable case) — parity-test sized
     "audioldm-s-5s": dict(preset="audioldm-s", model_id="cvssp/audioldm-s-full-v2", H=128, W=16, n_inv=50, tstart=50,
                           cfg_src=1.0, cfg_tar=3.0, text_lens=()),
+    # BASELINE.json configs[2] geometry (TANGO-full, v-prediction scheduler of the checkpoint is set by the wrapper), one clip
+    "tango-10s": dict(preset="tango", model_id="declare-lab/tango", H=256, W=16, n_inv=200, tstart=100, cfg_src=3.0,
+                      cfg_tar=12.0, text_lens=(16,)),
+    # BASELINE.json configs[4] geometry: 30 s clip, AudioLDM2 (whole clip on one GPU)
+    "audioldm2-30s": dict(preset="audioldm2", model_id="cvssp/audioldm2", H=768, W=16, n_inv=200, tstart=100, cfg_src=3.0,
+                          cfg_tar=12.0, text_lens=(8, 16)),
     "tiny": dict(preset="tiny-audioldm2", model_id="synthetic/audioldm2-tiny", H=32, W=16, n_inv=20, tstart=10,
                  cfg_src=3.0, cfg_tar=12.0, text_lens=(8, 16)),
 }

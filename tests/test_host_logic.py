@@ -133,3 +133,27 @@ def test_pending_forward_guard():
         assert p.event_for(3) == "e1" and p.event_for(0) == "e0" and p.event_for(9) is None
         zs[1] += 1
         assert not p.matches(zs[:2], xts, (1.0,) * 4)             # modified in place after the forward process
+
+
+def test_solo_lane_choice_from_capture_timings():
+    """UNetEngine.solo_lane: variant 2 only when both variants were timed at capture and 2 was faster alone."""
+    from audioeditingcode_b200.unet import UNetEngine
+
+    class G:
+        def __init__(self, ms):
+            if ms is not None:
+                self.placement_ms = ms
+    eng = UNetEngine.__new__(UNetEngine)
+    text = object()
+    key = lambda lane: (2, 256, 16, id(text), ("rev", 1), False, lane)
+    eng._graphs = {}
+    assert eng.solo_lane(2, 256, 16, text, ("rev", 1), False) == 1            # nothing captured yet
+    eng._graphs[key(2)] = G([6.2, 6.19])
+    assert eng.solo_lane(2, 256, 16, text, ("rev", 1), False) == 1            # variant 1 not timed yet
+    eng._graphs[key(1)] = G([6.8, 6.81])
+    assert eng.solo_lane(2, 256, 16, text, ("rev", 1), False) == 2            # TANGO-like: the shared variant wins alone
+    eng._graphs[key(1)] = G([5.97, 6.2])
+    eng._graphs[key(2)] = G([6.47])
+    assert eng.solo_lane(2, 256, 16, text, ("rev", 1), False) == 1            # AudioLDM2-large-like
+    eng._graphs[key(1)] = G(None)
+    assert eng.solo_lane(2, 256, 16, text, ("rev", 1), False) == 1            # untimed graph (placement tuning off)
