@@ -157,3 +157,24 @@ def test_solo_lane_choice_from_capture_timings():
     assert eng.solo_lane(2, 256, 16, text, ("rev", 1), False) == 1            # AudioLDM2-large-like
     eng._graphs[key(1)] = G(None)
     assert eng.solo_lane(2, 256, 16, text, ("rev", 1), False) == 1            # untimed graph (placement tuning off)
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside ours): one JSON line with the contract's keys,
+    timed on the oracle port, no GPU needed.  Tiny workload so the whole CPU suite stays fast."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--config", "tiny",
+                        "--steps", "1", "--warmup", "1", "--cpu-steps", "1"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "impl", "cpu_baseline", "e2e"):
+        assert k in line, k
+    assert line["impl"] == "reference" and line["metric"] == "denoising-steps/sec" and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["value"] == line["value"]
+    assert line["config"]["workload"] == "tiny" and "model" not in line["config"]
