@@ -178,3 +178,45 @@ def test_bench_reference_arm_contract():
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["value"] == line["value"]
     assert line["config"]["workload"] == "tiny" and "model" not in line["config"]
+
+
+def test_c_abi_argument_errors_without_a_device():
+    """Error behaviour of the C ABI (include/aedit.h: negative AE_E* + ae_last_error message).  Every call here is
+    rejected by argument validation BEFORE the library touches the device, so it runs without a GPU (the pointers are
+    dummies that are never dereferenced on the host)."""
+    import ctypes as C
+    lib = _lib.load()
+    dummy = 0x10000
+    a = _lib.AeGemmArgs()
+    assert lib.ae_gemm(C.byref(a), None) == -1 and b"null operand" in lib.ae_last_error()
+    a.A, a.W, a.M, a.N, a.K, a.lda, a.ldw = dummy, dummy, 128, 128, 64, 64, 64
+    assert lib.ae_gemm(C.byref(a), None) == -1 and b"no output" in lib.ae_last_error()
+    a.out_bf16 = dummy
+    a.act = 4
+    assert lib.ae_gemm(C.byref(a), None) == -1 and b"act must be" in lib.ae_last_error()
+    a.act = 3                                   # grouped softmax without its geometry
+    assert lib.ae_gemm(C.byref(a), None) == -1 and b"grouped-softmax" in lib.ae_last_error()
+    a.sm_L, a.sm_block, a.sm_rows, a.sm_slot = 8, 64, 64, dummy
+    a.out_f32 = dummy                           # act 3 takes a plain bf16 output
+    assert lib.ae_gemm(C.byref(a), None) == -1 and b"plain bf16 output" in lib.ae_last_error()
+    a.act, a.sm_L, a.sm_block, a.sm_rows, a.sm_slot = 0, 0, 0, 0, None
+    a.ld_out_f32 = 128
+    a.colstats, a.cs_rows_per_sample = dummy, 48     # rows per sample must be a multiple of 32 dividing M
+    assert lib.ae_gemm(C.byref(a), None) == -1 and b"multiple of 32" in lib.ae_last_error()
+    a.colstats, a.cs_rows_per_sample = None, 0
+    a.act, a.N = 2, 100                         # GEGLU needs N % 32 == 0
+    assert lib.ae_gemm(C.byref(a), None) == -1 and b"GEGLU" in lib.ae_last_error()
+    # attention: a head dim that is not instantiated, and misaligned strides
+    rc = lib.ae_attention(dummy, 64, 64, dummy, 64, 64, dummy, 64, 64, None, None, 0, 1, 1, 50, 64, 64, 1.0, dummy, 64, 64,
+                          None)
+    assert rc == -3 and b"head dim 50" in lib.ae_last_error()
+    rc = lib.ae_attention(dummy, 60, 64, dummy, 64, 64, dummy, 64, 64, None, None, 0, 1, 1, 64, 64, 64, 1.0, dummy, 64, 64,
+                          None)
+    assert rc == -1 and b"alignment" in lib.ae_last_error()
+    # GroupNorm from column statistics without the statistics
+    rc = lib.ae_groupnorm_cs(dummy, 64, None, None, 0, None, 1, 64, 32, 1e-5, dummy, dummy, 1, dummy, None, None, dummy, None)
+    assert rc == -1 and b"column statistics missing" in lib.ae_last_error()
+    rc = lib.ae_groupnorm(dummy, 60, None, 0, 1, 64, 32, 1e-5, dummy, dummy, 1, dummy, None, None, dummy, None)
+    assert rc == -1 and b"divisible" in lib.ae_last_error()
+    assert lib.ae_layernorm(dummy, 4, 4096, 1e-5, dummy, dummy, dummy, None) == -1
+    assert lib.ae_attention_workspace_bytes(2, 8, 1024, 48) > 0
