@@ -20,15 +20,13 @@ Two execution paths, both on the libaedit kernels:
 """
 from __future__ import annotations
 
-import ctypes as C
 import os
 from typing import Dict, List, Optional, Tuple, Union
 
 import torch
 from tqdm import tqdm
 
-from .. import _lib
-from ..models import PipelineWrapper, _ptr, _stream
+from ..models import PipelineWrapper
 
 DEFAULT_FORWARD_BATCH = int(os.environ.get("AEDIT_FORWARD_BATCH", "50"))
 USE_CUDA_GRAPHS = os.environ.get("AEDIT_CUDA_GRAPH", "1") != "0"
