@@ -32,8 +32,32 @@ class TorchOps:
         return (H % rows == 0) if H >= rows else (rows % H == 0)
 
     def gemm(self, A, W, *, out_f32=None, out_bf16=None, bias=None, rowbias=None, rows_per_group=1, residual=None,
-             act=0, alpha=1.0, conv=None, M=None, K=None, force_bn=0, **kw):
+             act=0, alpha=1.0, conv=None, M=None, K=None, force_bn=0, batch=1, strideA=0, strideW=0, stride_out=0,
+             lda=None, ldw=None, ld_out_bf16=None, softmax=None, colstats=None, cs_rows=0, **kw):
         self.launches += 1
+        if batch > 1:
+            # independent problems z with element strides, exactly the pointer arithmetic of ae_gemm (include/aedit.h)
+            N = W.shape[-2]
+            Az = torch.as_strided(A, (batch, M, K), (strideA, lda, 1), A.storage_offset())
+            Wz = torch.as_strided(W, (batch, N, K), (strideW, ldw, 1), W.storage_offset())
+            Oz = torch.as_strided(out_bf16, (batch, M, N), (stride_out, ld_out_bf16, 1), out_bf16.storage_offset())
+            Oz.copy_(alpha * torch.einsum("zmk,znk->zmn", Az, Wz))
+            return
+        if softmax is not None:
+            # act 3 (include/aedit.h, ae_gemm_args.sm_*): per (text row, head) softmax over L columns for the sample's
+            # own text row, zeros for the other text rows
+            L, block, slot, rows, sbias = softmax
+            acc = A.reshape(-1, A.shape[-1]) @ W.t()
+            Mr, N = acc.shape
+            r_of_row = slot.long()[torch.arange(Mr) // rows]                        # [M]
+            g = acc.reshape(Mr, N // L, L)
+            r_of_group = (torch.arange(N // L) * L) // block                        # [N/L]
+            if sbias is not None:
+                g = g + sbias[r_of_group][None]
+            p = torch.softmax(g, dim=-1)
+            p = p * (r_of_group[None, :] == r_of_row[:, None]).to(p.dtype)[..., None]
+            out_bf16.copy_(p.reshape(Mr, N))
+            return
         if conv is not None:
             B, H, W_, C, kh, kw_, dh, dw = conv
             x = A.reshape(B, H, W_, C).permute(0, 3, 1, 2)
@@ -61,6 +85,12 @@ class TorchOps:
             out_f32.reshape(acc.shape).copy_(acc) if out_f32.is_contiguous() else out_f32.copy_(acc)
         if out_bf16 is not None:
             out_bf16.copy_(acc)
+        if colstats is not None:
+            # ae_gemm_args.colstats: fixed-point per-(sample, column) sum / sum of squares, ACCUMULATED into the caller's
+            # zeroed int64 buffer [sample][N][2]
+            xs = acc.double().reshape(-1, cs_rows, acc.shape[-1])
+            add = torch.stack([(xs.sum(1) * 2.0 ** 28).round(), ((xs * xs).sum(1) * 2.0 ** 24).round()], -1).to(torch.int64)
+            colstats.add_(add.reshape(-1))
 
     def im2col(self, x, B, H, W, C, kh, kw, stride, dil, pad_t, pad_l, Ho, Wo, out):
         self.launches += 1
@@ -74,12 +104,24 @@ class TorchOps:
         out.zero_()
         out[:, : kh * kw * C] = cols
 
-    def groupnorm(self, x1, x2, gamma, beta, eps, groups, silu, out, raw_out=None, cat_out=None):
+    def groupnorm(self, x1, x2, gamma, beta, eps, groups, silu, out, raw_out=None, cat_out=None, cs1=None, cs2=None):
         self.launches += 1
         x = x1 if x2 is None else torch.cat([x1, x2], dim=-1)
         B, C = x.shape[0], x.shape[-1]
         xc = x.reshape(B, -1, C).permute(0, 2, 1)
-        y = F.group_norm(xc, groups, gamma, beta, eps).permute(0, 2, 1)
+        if cs1 is not None:
+            # ae_groupnorm_cs: statistics from the producers' fixed-point column sums (concatenated inputs: two buffers)
+            cs = cs1.reshape(B, -1, 2) if cs2 is None else torch.cat([cs1.reshape(B, -1, 2), cs2.reshape(B, -1, 2)], 1)
+            n = xc.shape[-1] * (C // groups)
+            su = cs[..., 0].reshape(B, groups, -1).sum(-1).double() / 2.0 ** 28
+            sq = cs[..., 1].reshape(B, groups, -1).sum(-1).double() / 2.0 ** 24
+            mean = su / n
+            rstd = 1.0 / torch.sqrt((sq / n - mean * mean).clamp_min(0).float() + eps)
+            mean_c = mean.float().repeat_interleave(C // groups, 1)[:, :, None]
+            rstd_c = rstd.repeat_interleave(C // groups, 1)[:, :, None]
+            y = ((xc - mean_c) * rstd_c * gamma[None, :, None] + beta[None, :, None]).permute(0, 2, 1)
+        else:
+            y = F.group_norm(xc, groups, gamma, beta, eps).permute(0, 2, 1)
         if silu:
             y = F.silu(y)
         out.reshape(B, -1, C).copy_(y)
