@@ -454,16 +454,27 @@ class HiFiGANEngine(_Net):
 class AudioEnds:
     """VAE + vocoder of one model, built lazily (models.py wrappers call into this)."""
 
-    def __init__(self, device, ckpt_dir: Optional[str] = None):
+    def __init__(self, device, ckpt_dir: Optional[str] = None, allow_synthetic: bool = False):
         self.device = torch.device(device)
         self.ckpt_dir = ckpt_dir
+        self.allow_synthetic = allow_synthetic
         self._vae: Optional[VAEEngine] = None
         self._voc: Optional[HiFiGANEngine] = None
+
+    def _require(self, sub: str) -> bool:
+        """True if <ckpt>/<sub> holds weights; otherwise seeded synthetic weights only on explicit request."""
+        if self.ckpt_dir and os.path.isdir(os.path.join(self.ckpt_dir, sub)):
+            return True
+        if not self.allow_synthetic:
+            raise FileNotFoundError(
+                f"no {sub}/ weights under {self.ckpt_dir!r} and synthetic weights were not requested "
+                "(allow_synthetic=True / AEDIT_ALLOW_SYNTHETIC=1)")
+        return False
 
     def vae(self) -> VAEEngine:
         if self._vae is None:
             w, sf = None, VAE_SCALING
-            if self.ckpt_dir and os.path.isdir(os.path.join(self.ckpt_dir, "vae")):
+            if self._require("vae"):
                 import json
                 w = _load_state(os.path.join(self.ckpt_dir, "vae"))
                 cfgp = os.path.join(self.ckpt_dir, "vae", "config.json")
@@ -475,7 +486,7 @@ class AudioEnds:
     def voc(self) -> HiFiGANEngine:
         if self._voc is None:
             w, nb = None, False
-            if self.ckpt_dir and os.path.isdir(os.path.join(self.ckpt_dir, "vocoder")):
+            if self._require("vocoder"):
                 import json
                 w = _load_state(os.path.join(self.ckpt_dir, "vocoder"))
                 cfgp = os.path.join(self.ckpt_dir, "vocoder", "config.json")

@@ -52,11 +52,21 @@ def _stream():
 
 
 class PipelineWrapper(torch.nn.Module):
+    family = "audioldm"
+
     def __init__(self, model_id: str, device: torch.device, double_precision: bool = False,
                  token: Optional[str] = None, *args, weights: Optional[Dict[str, torch.Tensor]] = None,
-                 config: Optional[UNetConfig] = None, weight_seed: int = 0, **kwargs) -> None:
+                 config: Optional[UNetConfig] = None, weight_seed: int = 0, allow_synthetic: Optional[bool] = None,
+                 **kwargs) -> None:
         super().__init__()
         self.model_id = model_id
+        # Seeded synthetic weights / text embeddings stand in for a checkpoint ONLY on explicit request (there is no
+        # network here, so benchmarks and tests use them): `allow_synthetic=True`, AEDIT_ALLOW_SYNTHETIC=1, or a model id
+        # under the reserved "synthetic/" namespace.  Otherwise a model id that is not a local checkpoint directory raises
+        # (the reference would download it, models.py:478,556-564) instead of silently editing with random weights.
+        if allow_synthetic is None:
+            allow_synthetic = os.environ.get("AEDIT_ALLOW_SYNTHETIC", "0") != "0" or model_id.startswith("synthetic/")
+        self.allow_synthetic = bool(allow_synthetic)
         self.device = torch.device(device)
         self.double_precision = double_precision
         self.token = token
@@ -64,20 +74,36 @@ class PipelineWrapper(torch.nn.Module):
             raise NotImplementedError("double_precision: the B200 path computes U-Net internals in bf16/fp32")
         cfg = config
         ckpt_dir = model_id if os.path.isdir(model_id) else None
+        unet_path = None
+        if ckpt_dir:
+            # TANGO snapshots keep the U-Net inside pytorch_model_main.bin at the snapshot root (models.py:418-422) and
+            # its architecture in the tango package; diffusers pipelines keep unet/config.json next to the weights
+            root_main = os.path.join(ckpt_dir, "pytorch_model_main.bin")
+            unet_path = root_main if (self.family == "tango" and os.path.exists(root_main)) else os.path.join(ckpt_dir, "unet")
         if cfg is None:
-            if ckpt_dir and os.path.exists(os.path.join(ckpt_dir, "unet", "config.json")):
-                cfg = W.unet_config_from_json(os.path.join(ckpt_dir, "unet", "config.json"), os.path.basename(ckpt_dir))
+            cfg_json = os.path.join(ckpt_dir, "unet", "config.json") if ckpt_dir else None
+            if cfg_json and os.path.exists(cfg_json):
+                cfg = W.unet_config_from_json(cfg_json, os.path.basename(os.path.normpath(ckpt_dir)),
+                                              scheduler_json=os.path.join(ckpt_dir, "scheduler", "scheduler_config.json"))
+            elif ckpt_dir and self.family != "tango" and weights is None:
+                # real weights must come with their architecture: a preset could silently disagree with the checkpoint
+                # (e.g. the attention head split, which does not change any weight shape)
+                raise FileNotFoundError(f"{cfg_json}: a checkpoint directory must carry unet/config.json")
             else:
                 cfg = from_model_id(model_id)
         self.unet_config = cfg
         if weights is None:
             if ckpt_dir:
-                weights = W.load_unet_checkpoint(os.path.join(ckpt_dir, "unet"), cfg)
+                weights = W.load_unet_checkpoint(unet_path, cfg)
                 self.weights_source = f"checkpoint:{ckpt_dir}"
-            else:
-                # no network / no weights on disk: seeded synthetic weights of the named architecture
+            elif self.allow_synthetic:
                 weights = W.synthetic_weights(cfg, seed=weight_seed)
                 self.weights_source = f"synthetic(seed={weight_seed})"
+            else:
+                raise FileNotFoundError(
+                    f"{model_id!r} is not a local checkpoint directory (no network: hub ids cannot be downloaded). Pass a "
+                    "directory laid out like the diffusers pipeline / TANGO snapshot the reference loads, or opt in to "
+                    "seeded synthetic weights with allow_synthetic=True / AEDIT_ALLOW_SYNTHETIC=1.")
         else:
             self.weights_source = "caller"
         self.engine = UNetEngine(cfg, weights, self.device)
@@ -89,6 +115,12 @@ class PipelineWrapper(torch.nn.Module):
         self.model = types.SimpleNamespace(unet=unet_ns, scheduler=None, vocoder=vocoder_ns, vae_scale_factor=4)
         self._text_cache: Dict[Any, TextCache] = {}
         self._sched_table: Optional[SchedTable] = None
+        # a13 / f4: real tokenizer + text encoder(s) when the checkpoint directory carries them
+        self.text_stack = None
+        self._ckpt_dir = ckpt_dir
+        from . import text_encoders as TE
+        if TE.has_text_checkpoint(ckpt_dir, self.family):
+            self.text_stack = TE.load_text_stack(ckpt_dir, self.family, self.device)
 
     # ---------------------------------------------------------------- scheduler plumbing
     @property
@@ -309,7 +341,18 @@ class PipelineWrapper(torch.nn.Module):
         eps = IU._unet_eval(self, x, t_in, text, slot, cl_rows, slot_key=("pair", n, ru, rc))
         return eps[:n], eps[n:]
 
-    # ---------------------------------------------------------------- text (a13) — synthetic fallback
+    # ---------------------------------------------------------------- text (a13)
+    def _encode_text_or_synthetic(self, prompts: List[str], synthetic):
+        """The checkpoint's tokenizer / text encoder(s) (text_encoders.py); seeded synthetic embeddings only when the
+        wrapper was explicitly created with allow_synthetic (benchmarks / tests without a checkpoint)."""
+        if self.text_stack is not None:
+            return self.text_stack(list(prompts))
+        if not self.allow_synthetic:
+            raise FileNotFoundError(
+                f"{self.model_id!r}: no tokenizer / text encoder found in the checkpoint directory and synthetic text "
+                "embeddings were not requested (allow_synthetic=True / AEDIT_ALLOW_SYNTHETIC=1)")
+        return synthetic(list(prompts))
+
     def _synthetic_text(self, prompts: List[str], dim: int, L: Optional[int], normalize: bool, salt: int):
         """Deterministic stand-in embeddings when no text-encoder checkpoint is on disk (no network here):
         N(0,1) seeded by the prompt string."""
@@ -328,7 +371,7 @@ class PipelineWrapper(torch.nn.Module):
     def _ends(self):
         if getattr(self, "_ends_obj", None) is None:
             from .ends import AudioEnds
-            self._ends_obj = AudioEnds(self.device, self.model_id if os.path.isdir(self.model_id) else None)
+            self._ends_obj = AudioEnds(self.device, self._ckpt_dir, allow_synthetic=self.allow_synthetic)
         return self._ends_obj
 
     def vae_encode(self, x: torch.Tensor) -> torch.Tensor:                                    # models.py:495-499
@@ -349,8 +392,9 @@ class AudioLDMWrapper(PipelineWrapper):
     def _text_for(self, encoder_hidden_states, class_labels, encoder_attention_mask):
         return [], [], class_labels
 
-    def encode_text(self, prompts: List[str], **kwargs) -> Tuple[None, Optional[torch.Tensor], None]:
-        return None, self._synthetic_text(prompts, 512, None, True, 0)[:, 0], None
+    def encode_text(self, prompts: List[str], **kwargs) -> Tuple[None, Optional[torch.Tensor], None]:   # :511-537
+        return self._encode_text_or_synthetic(
+            prompts, lambda ps: (None, self._synthetic_text(ps, 512, None, True, 0)[:, 0], None))
 
 
 class AudioLDM2Wrapper(PipelineWrapper):
@@ -360,7 +404,12 @@ class AudioLDM2Wrapper(PipelineWrapper):
     def _text_for(self, encoder_hidden_states, class_labels, encoder_attention_mask):
         return [encoder_hidden_states, class_labels], [None, encoder_attention_mask], None
 
-    def encode_text(self, prompts: List[str], **kwargs) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    family = "audioldm2"
+
+    def encode_text(self, prompts: List[str], **kwargs) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:   # :599-677
+        return self._encode_text_or_synthetic(prompts, self._synthetic_triple)
+
+    def _synthetic_triple(self, prompts: List[str]):
         L = max(1, max(len(p.split()) for p in prompts) + (1 if any(p for p in prompts) else 0))
         gen = self._synthetic_text(prompts, 768, 8, False, 1)
         t5 = self._synthetic_text(prompts, 1024, L, False, 2)
@@ -389,7 +438,12 @@ class TangoWrapper(PipelineWrapper):
             raise RuntimeWarning("This model dies at this point")
         return self._ends().vae_encode_sample(x).float()
 
+    family = "tango"
+
     def encode_text(self, prompts: List[str], **kwargs) -> Tuple[Optional[torch.Tensor], None, Optional[torch.Tensor]]:
+        return self._encode_text_or_synthetic(prompts, self._synthetic_triple)                               # :455-460
+
+    def _synthetic_triple(self, prompts: List[str]):
         L = max(1, max(len(p.split()) for p in prompts) + 1)
         t5 = self._synthetic_text(prompts, 1024, L, False, 3)
         mask = torch.zeros(len(prompts), L, dtype=torch.bool, device=self.device)

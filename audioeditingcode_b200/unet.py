@@ -171,6 +171,9 @@ class UNetEngine:
         self._cs_arena = None
         self._cs_off = 0
         self._cs_map: Dict[int, torch.Tensor] = {}
+        # probe(name, tensor fp32 [B, H*W, C], (H, W)): optional callback after conv_in and every block of an EAGER
+        # forward (error attribution against the oracle's probe of the same name, tools/error_attribution.py)
+        self.probe = None
 
     # ------------------------------------------------------------------------------------------ GroupNorm statistics
     def _cs_begin(self, B: int):
@@ -595,6 +598,8 @@ class UNetEngine:
         ops.gemm(col, self.w["conv_in.weight"], out_f32=h, bias=self.w["conv_in.bias"], K=K0,
                  **self._cs_take(h, B, H * W))
         h = h.view(B, H * W, ch[0])
+        probe = self.probe if self.probe is not None else (lambda name, t, hw: None)
+        probe("conv_in", h, (H, W))
 
         sizes = [(H, W)]
         skips = [h]
@@ -602,8 +607,10 @@ class UNetEngine:
         for i in range(nlev):
             for j in range(cfg.layers_per_block):
                 h = self._resnet(h, None, B, hh, ww, f"down_blocks.{i}.resnets.{j}", temb_all)
+                probe(f"down_blocks.{i}.resnets.{j}", h, (hh, ww))
                 if cfg.attn_levels[i]:
                     h = self._site(h, B, hh, ww, f"down_blocks.{i}.attentions", j, i, text, slot_map)
+                    probe(f"down_blocks.{i}.attentions.{j}", h, (hh, ww))
                 skips.append(h)
             if i != nlev - 1:
                 C = ch[i]
@@ -616,11 +623,15 @@ class UNetEngine:
                 hh, ww = ho, wo
                 sizes.append((hh, ww))
                 h = d.view(B, hh * ww, C)
+                probe(f"down_blocks.{i}.downsamplers.0", h, (hh, ww))
                 skips.append(h)
 
         h = self._resnet(h, None, B, hh, ww, "mid_block.resnets.0", temb_all)
+        probe("mid_block.resnets.0", h, (hh, ww))
         h = self._site(h, B, hh, ww, "mid_block.attentions", 0, nlev - 1, text, slot_map)
+        probe("mid_block.attentions.0", h, (hh, ww))
         h = self._resnet(h, None, B, hh, ww, "mid_block.resnets.1", temb_all)
+        probe("mid_block.resnets.1", h, (hh, ww))
 
         # ---- h-space tap / replace, additive residual (models.py:336-343)
         Cm = ch[-1]
@@ -662,8 +673,10 @@ class UNetEngine:
             res = list(res)
             for j in range(n_up):
                 h = self._resnet(h, res.pop(), B, hh, ww, f"up_blocks.{i}.resnets.{j}", temb_all)
+                probe(f"up_blocks.{i}.resnets.{j}", h, (hh, ww))
                 if cfg.attn_levels[level]:
                     h = self._site(h, B, hh, ww, f"up_blocks.{i}.attentions", j, level, text, slot_map)
+                    probe(f"up_blocks.{i}.attentions.{j}", h, (hh, ww))
             if i != nlev - 1:
                 C = ch[level]
                 ho, wo = sizes[level - 1]
@@ -672,6 +685,7 @@ class UNetEngine:
                 u = ops.empty((B * ho * wo, C), F32, dev)
                 self._conv3x3(up, B, ho, wo, C, f"up_blocks.{i}.upsamplers.0.conv", u, stats=True)
                 h = u.view(B, ho * wo, C)
+                probe(f"up_blocks.{i}.upsamplers.0", h, (ho, wo))
 
         # ---- conv_norm_out -> SiLU -> conv_out (models.py:385-388)
         a = ops.empty((B, H, W, ch[0]), self.adt, dev)

@@ -46,11 +46,16 @@ class UNetConfig:
         return json.dumps(asdict(self))
 
 
-def audioldm(width: int = 128, head_dim: int = 32, name: str = "audioldm-s") -> UNetConfig:
-    """AudioLDM-1 (audioldm/utils.py:142-157: channel_mult [1,2,3,5], 2 res blocks, attention at ds 2/4/8,
-    num_head_channels 32 (64 for -l-), FiLM concat of a 512-d CLAP vector)."""
+def audioldm(width: int = 128, head_dim: Optional[int] = None, name: str = "audioldm-s") -> UNetConfig:
+    """AudioLDM-1 (audioldm/utils.py:142-157: channel_mult [1,2,3,5], 2 res blocks, attention at ds 2/4/8, FiLM concat
+    of a 512-d CLAP vector).  Heads: the reference's hot path runs the diffusers UNet2DConditionModel of the converted
+    checkpoints, whose config carries `attention_head_dim: 8` = EIGHT HEADS at every level ([UPSTREAM], diffusers
+    reads that field as the head count) — not the original LDM's num_head_channels 32 (heads 4/8/12/20), which
+    `head_dim=32` still selects (the vendored UNetModel golden uses it).  Weight shapes are the same either way; real
+    checkpoints always take the split from their own unet/config.json (models.py requires it)."""
     ch = tuple(width * m for m in (1, 2, 3, 5))
-    return UNetConfig(name=name, block_out_channels=ch, num_heads=tuple(c // head_dim for c in ch),
+    heads = (8,) * len(ch) if head_dim is None else tuple(c // head_dim for c in ch)
+    return UNetConfig(name=name, block_out_channels=ch, num_heads=heads,
                       transformer_specs=(None,), class_embed_dim=512, class_embeddings_concat=True)
 
 
@@ -70,8 +75,8 @@ def tango(name: str = "tango") -> UNetConfig:
 
 
 PRESETS = {
-    "audioldm-s": lambda: audioldm(128, 32, "audioldm-s"),
-    "audioldm-m": lambda: audioldm(192, 32, "audioldm-m"),
+    "audioldm-s": lambda: audioldm(128, None, "audioldm-s"),
+    "audioldm-m": lambda: audioldm(192, None, "audioldm-m"),
     "audioldm-l": lambda: audioldm(256, 64, "audioldm-l"),
     "audioldm2": lambda: audioldm2(128, "audioldm2"),
     # width of -large is UNVERIFIED upstream; 192 reproduces the ~750 M U-Net

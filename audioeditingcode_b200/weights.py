@@ -10,7 +10,7 @@ from __future__ import annotations
 import json
 import math
 import os
-from typing import Dict, Tuple
+from typing import Optional, Dict, Tuple
 
 import torch
 
@@ -162,10 +162,17 @@ def load_unet_checkpoint(path: str, cfg: UNetConfig) -> Dict[str, torch.Tensor]:
     return out
 
 
-def unet_config_from_json(path: str, name: str = "checkpoint") -> UNetConfig:
-    """[UPSTREAM] diffusers unet/config.json -> UNetConfig (fields per SURVEY.md Appendix B)."""
+def unet_config_from_json(path: str, name: str = "checkpoint", scheduler_json: Optional[str] = None) -> UNetConfig:
+    """[UPSTREAM] diffusers unet/config.json -> UNetConfig (fields per SURVEY.md Appendix B).  diffusers treats
+    `attention_head_dim` as the NUMBER of heads when `num_attention_heads` is absent (UNet2DConditionModel.__init__);
+    so does this.  scheduler_json (scheduler/scheduler_config.json): beta range and prediction type."""
     with open(path) as fh:
         j = json.load(fh)
+    sched = {}
+    if scheduler_json and os.path.exists(scheduler_json):
+        with open(scheduler_json) as fh:
+            sj = json.load(fh)
+        sched = {k: sj[k] for k in ("beta_start", "beta_end", "prediction_type") if k in sj}
     ch = tuple(j["block_out_channels"])
     down = j["down_block_types"]
     attn = tuple("CrossAttn" in d for d in down)
@@ -192,4 +199,4 @@ def unet_config_from_json(path: str, name: str = "checkpoint") -> UNetConfig:
                       class_embed_dim=j.get("projection_class_embeddings_input_dim")
                       if j.get("class_embed_type") == "simple_projection" else None,
                       class_embeddings_concat=bool(j.get("class_embeddings_concat", False)),
-                      norm_eps=j.get("norm_eps", 1e-5), norm_num_groups=j.get("norm_num_groups", 32))
+                      norm_eps=j.get("norm_eps", 1e-5), norm_num_groups=j.get("norm_num_groups", 32), **sched)

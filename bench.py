@@ -121,7 +121,7 @@ def synth_text(cfg, lens, P, device, seed=4):
 def build_model(spec, device):
     from audioeditingcode_b200 import models, unet_config as C
     cfg = C.preset(spec["preset"])
-    m = models.load_model(spec["model_id"], device, spec["n_inv"], config=cfg)
+    m = models.load_model(spec["model_id"], device, spec["n_inv"], config=cfg, allow_synthetic=True)
     return m, cfg
 
 

@@ -118,13 +118,16 @@ def unet_forward(cfg, w: Dict[str, torch.Tensor], sample: torch.Tensor, timestep
                  streams: Sequence[Optional[torch.Tensor]] = (), stream_masks: Sequence[Optional[torch.Tensor]] = (),
                  class_labels: Optional[torch.Tensor] = None,
                  mid_block_additional_residual=None, replace_h_space=None, replace_skip_conns=None,
-                 zero_out_resconns=None):
+                 zero_out_resconns=None, probe=None):
     """Top-level order follows models.py:216-393 exactly (time emb → class emb concat → conv_in → down
     → mid → h-space tap/replace → +mid residual → up with skip replace/zero → GN/SiLU/conv_out).
 
     cfg: any object with the fields of audioeditingcode_b200.unet.UNetConfig (duck-typed so the oracle
     does not import the product).  streams[i]: [B, L_i, D_i] text stream i; stream_masks[i]: [B, L_i] 1=keep.
+    probe(name, tensor NCHW): optional callback after conv_in and every block (error attribution, tools/).
     Returns (eps [B,Cout,H,W], h_space, extracted_res_conns dict)."""
+    if probe is None:
+        probe = lambda name, t: None
     B = sample.shape[0]
     G = cfg.norm_num_groups
     eps = cfg.norm_eps
@@ -156,20 +159,27 @@ def unet_forward(cfg, w: Dict[str, torch.Tensor], sample: torch.Tensor, timestep
         return x
 
     h = _conv(sample, w, "conv_in")
+    probe("conv_in", h)
     skips = [h]
     for i in range(nlev):
         for j in range(cfg.layers_per_block):
             h = resnet_block(h, emb_act, w, f"down_blocks.{i}.resnets.{j}", eps, G)
+            probe(f"down_blocks.{i}.resnets.{j}", h)
             if cfg.attn_levels[i]:
                 h = attn_site(h, f"down_blocks.{i}.attentions", j, i)
+                probe(f"down_blocks.{i}.attentions.{j}", h)
             skips.append(h)
         if i != nlev - 1:
             h = _conv(h, w, f"down_blocks.{i}.downsamplers.0.conv", stride=2)
+            probe(f"down_blocks.{i}.downsamplers.0", h)
             skips.append(h)
 
     h = resnet_block(h, emb_act, w, "mid_block.resnets.0", eps, G)
+    probe("mid_block.resnets.0", h)
     h = attn_site(h, "mid_block.attentions", 0, nlev - 1)
+    probe("mid_block.attentions.0", h)
     h = resnet_block(h, emb_act, w, "mid_block.resnets.1", eps, G)
+    probe("mid_block.resnets.1", h)
 
     if replace_h_space is None:
         h_space = h.clone()
@@ -196,14 +206,17 @@ def unet_forward(cfg, w: Dict[str, torch.Tensor], sample: torch.Tensor, timestep
         for j in range(n_up):
             h = torch.cat([h, res.pop()], dim=1)
             h = resnet_block(h, emb_act, w, f"up_blocks.{i}.resnets.{j}", eps, G)
+            probe(f"up_blocks.{i}.resnets.{j}", h)
             if cfg.attn_levels[level]:
                 h = attn_site(h, f"up_blocks.{i}.attentions", j, level)
+                probe(f"up_blocks.{i}.attentions.{j}", h)
         if i != nlev - 1:
             if skips and skips[-1].shape[2:] != (h.shape[2] * 2, h.shape[3] * 2):
                 h = F.interpolate(h, size=skips[-1].shape[2:], mode="nearest")  # models.py:365-366
             else:
                 h = F.interpolate(h, scale_factor=2.0, mode="nearest")
             h = _conv(h, w, f"up_blocks.{i}.upsamplers.0.conv")
+            probe(f"up_blocks.{i}.upsamplers.0", h)
 
     h = F.silu(_gn(h, w, "conv_norm_out", eps, G))
     out = _conv(h, w, "conv_out")

@@ -27,7 +27,7 @@ def main():
     from audioeditingcode_b200.ddm_inversion import inversion_utils as IU
     cfg = C.preset("audioldm2")      # full AudioLDM2 architecture (347 M synthetic parameters)
     N = 20
-    m = models.load_model("cvssp/audioldm2", dev, N, config=cfg)
+    m = models.load_model("cvssp/audioldm2", dev, N, config=cfg, allow_synthetic=True)
     g = torch.Generator().manual_seed(1)
     x0 = (0.5 * torch.randn(1, 8, 32, 16, generator=g)).to(dev)
     noise = torch.randn(N, 8, 32, 16, generator=g).to(dev)

@@ -302,7 +302,7 @@ def test_full_size_properties_audioldm2_large():
     from audioeditingcode_b200.ddm_inversion import inversion_utils as IU
     N, ts = 12, 8
     dev = torch.device("cuda")
-    m = models.load_model("cvssp/audioldm2-large", dev, N, config=C.preset("audioldm2-large"))
+    m = models.load_model("cvssp/audioldm2-large", dev, N, config=C.preset("audioldm2-large"), allow_synthetic=True)
     g = torch.Generator().manual_seed(1)
     x0 = (0.5 * torch.randn(1, 8, 256, 16, generator=g)).to(dev)
     noise = torch.randn(N, 8, 256, 16, generator=g).to(dev)
