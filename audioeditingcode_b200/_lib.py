@@ -7,7 +7,12 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libaedit.so")
+# AEDIT_OPERANDS selects the build: fp16 operands (default, libaedit.so) or bf16 operands (libaedit_bf16.so) — see
+# include/aedit.h, ae_operand_dtype().  One process uses one of them.
+OPERANDS = os.environ.get("AEDIT_OPERANDS", "fp16").lower()
+if OPERANDS not in ("fp16", "bf16"):
+    raise ValueError(f"AEDIT_OPERANDS must be fp16 or bf16, not {OPERANDS!r}")
+LIB_PATH = os.path.join(_HERE, "libaedit.so" if OPERANDS == "fp16" else "libaedit_bf16.so")
 
 vp = C.c_void_p
 i32 = C.c_int32
@@ -36,6 +41,7 @@ class AeGemmArgs(C.Structure):
 _SIGS = {
     "ae_last_error": (C.c_char_p, []),
     "ae_version": (i32, []),
+    "ae_operand_dtype": (i32, []),
     "ae_launch_count": (i64, []),
     "ae_device_ok": (i32, []),
     "ae_set_pdl": (None, [i32]),
@@ -65,6 +71,10 @@ _SIGS = {
     "ae_cfg_inv_step": (i32, [vp, i32, i32, f32, vp, i64, vp, i64, i32, vp, vp, vp, vp, i32, i64, vp]),
     "ae_cfg_rev_step": (i32, [vp, i32, vp, f32, vp, vp, i32, vp, vp, vp, vp, vp, vp, vp, i64, vp]),
     "ae_ddim_step": (i32, [vp, i32, f32, f32, vp, vp, vp, vp, vp, vp, i64, vp]),
+    "ae_pc_workspace_bytes": (i64, [i32, i64]),
+    "ae_pc_perturb": (i32, [vp, i64, vp, f32, f32, i32, i32, vp, vp, i64, vp]),
+    "ae_pc_subspace_step": (i32, [vp, vp, vp, vp, i32, i64, f32, vp, vp, vp, vp, vp, i64, vp]),
+    "ae_pc_apply_drift": (i32, [vp, vp, vp, vp, f32, f32, f32, f32, i32, i32, i32, i64, vp, vp]),
     "ae_gemm": (i32, [C.POINTER(AeGemmArgs), vp]),
     "ae_gemm_conv_supported": (i32, [i32, i32, i32, i32]),
     "ae_im2col": (i32, [vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, vp, i64, vp]),
@@ -114,8 +124,16 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
+    if lib.ae_operand_dtype() != (1 if OPERANDS == "fp16" else 0):
+        raise AeditError(f"{LIB_PATH} was built for the other operand type (rebuild: python -m audioeditingcode_b200.build)")
     _lib = lib
     return lib
+
+
+def operand_torch_dtype():
+    """torch dtype of the library's 16-bit tensor-core operands."""
+    import torch
+    return torch.float16 if load().ae_operand_dtype() == 1 else torch.bfloat16
 
 
 def check(rc: int, what: str = "") -> None:

@@ -17,7 +17,8 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "csrc", "_obj")
-LIB = os.path.join(HERE, "libaedit.so")
+LIB = os.path.join(HERE, "libaedit.so")               # fp16 operands (default)
+LIB_BF16 = os.path.join(HERE, "libaedit_bf16.so")     # -DAE_OPERAND_BF16 (AEDIT_OPERANDS=bf16)
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
@@ -38,12 +39,12 @@ def _stale(src, obj):
     return any(os.path.getmtime(d) > mt for d in deps)
 
 
-def _compile(name, verbose):
+def _compile(name, verbose, bf16=False):
     src = os.path.join(CSRC, name)
-    obj = os.path.join(OBJ, name[:-3] + ".o")
+    obj = os.path.join(OBJ, name[:-3] + ("_bf16.o" if bf16 else ".o"))
     if not _stale(src, obj):
         return obj, ""
-    cmd = [NVCC, *FLAGS, "-c", src, "-o", obj]
+    cmd = [NVCC, *FLAGS, *(["-DAE_OPERAND_BF16"] if bf16 else []), "-c", src, "-o", obj]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     r = subprocess.run(cmd, capture_output=True, text=True)
@@ -52,24 +53,28 @@ def _compile(name, verbose):
     return obj, r.stderr
 
 
-def build(verbose: bool = False, force: bool = False) -> str:
+def build(verbose: bool = False, force: bool = False, variants=("fp16", "bf16")) -> str:
+    """Builds libaedit.so (fp16 operands) and libaedit_bf16.so (bf16 operands) from the same sources."""
     os.makedirs(OBJ, exist_ok=True)
     if force:
         for f in os.listdir(OBJ):
             os.remove(os.path.join(OBJ, f))
     srcs = sources()
-    with ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
-        results = list(ex.map(lambda n: _compile(n, verbose), srcs))
-    objs = [o for o, _ in results]
+    jobs = [(n, v == "bf16") for v in variants for n in srcs]
+    with ThreadPoolExecutor(max_workers=min(8, len(jobs))) as ex:
+        results = list(ex.map(lambda j: _compile(j[0], verbose, j[1]), jobs))
     if verbose:
         for _, log in results:
             if log:
                 print(log)
-    if (not os.path.exists(LIB)) or any(os.path.getmtime(o) > os.path.getmtime(LIB) for o in objs):
-        cmd = [NVCC, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"]
-        r = subprocess.run(cmd, capture_output=True, text=True)
-        if r.returncode != 0:
-            raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    for v in variants:
+        lib = LIB_BF16 if v == "bf16" else LIB
+        objs = [o for (n, b), (o, _) in zip(jobs, results) if b == (v == "bf16")]
+        if (not os.path.exists(lib)) or any(os.path.getmtime(o) > os.path.getmtime(lib) for o in objs):
+            cmd = [NVCC, "-shared", "-o", lib, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"]
+            r = subprocess.run(cmd, capture_output=True, text=True)
+            if r.returncode != 0:
+                raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
     return LIB
 
 

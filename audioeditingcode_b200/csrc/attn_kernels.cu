@@ -21,10 +21,10 @@ constexpr int BKV = 64;
 constexpr int kAttnThreads = 128;
 
 struct AttnArgs {
-  const __nv_bfloat16* q;
-  const __nv_bfloat16* k;
-  const __nv_bfloat16* v;
-  __nv_bfloat16* o;
+  const op_t* q;
+  const op_t* k;
+  const op_t* v;
+  op_t* o;
   long long ld_q, ld_k, ld_v, ld_o;
   long long bs_q, bs_k, bs_v, bs_o;
   const int* kv_map;
@@ -58,14 +58,14 @@ struct AttnCfg {
 };
 
 template <int D>
-__device__ __forceinline__ void load_tile(__nv_bfloat16* dst, const __nv_bfloat16* src, long long ld, int row0, int rows,
+__device__ __forceinline__ void load_tile(op_t* dst, const op_t* src, long long ld, int row0, int rows,
                                           int tid) {
   using C = AttnCfg<D>;
   constexpr int CH = C::DP / 8;  // 16-byte chunks per padded row
   for (int i = tid; i < 64 * CH; i += kAttnThreads) {
     const int r = i / CH, c = i % CH;
     const bool ok = (row0 + r < rows) && (c * 8 < D);
-    const __nv_bfloat16* g = ok ? src + (long long)(row0 + r) * ld + c * 8 : src;
+    const op_t* g = ok ? src + (long long)(row0 + r) * ld + c * 8 : src;
     ptx::cp_async_16(ptx::smem_u32(dst + r * C::LDS + c * 8), g, ok);
   }
 }
@@ -79,10 +79,10 @@ __global__ void __launch_bounds__(kAttnThreads) attention_kernel(AttnArgs a) {
   constexpr int KS = DP / 16;  // k-steps over the head dim for QK^T
   constexpr int NB = DP / 8;   // output n-blocks (head-dim columns / 8)
   extern __shared__ __align__(16) uint8_t smem_attn[];
-  __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(smem_attn);
-  __nv_bfloat16* sK = sQ + BQ * LDS;
+  op_t* sQ = reinterpret_cast<op_t*>(smem_attn);
+  op_t* sK = sQ + BQ * LDS;
   constexpr int NS = C::NS;
-  __nv_bfloat16* sV = sK + NS * BKV * LDS;
+  op_t* sV = sK + NS * BKV * LDS;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t4 = lane & 3;
@@ -92,9 +92,9 @@ __global__ void __launch_bounds__(kAttnThreads) attention_kernel(AttnArgs a) {
   const int head = blockIdx.y;
   const int b = blockIdx.z;
   const int bkv = a.kv_map ? a.kv_map[b] : b;
-  const __nv_bfloat16* qp = a.q + (long long)b * a.bs_q + (long long)head * D;
-  const __nv_bfloat16* kp = a.k + (long long)bkv * a.bs_k + (long long)head * D;
-  const __nv_bfloat16* vp = a.v + (long long)bkv * a.bs_v + (long long)head * D;
+  const op_t* qp = a.q + (long long)b * a.bs_q + (long long)head * D;
+  const op_t* kp = a.k + (long long)bkv * a.bs_k + (long long)head * D;
+  const op_t* vp = a.v + (long long)bkv * a.bs_v + (long long)head * D;
   const float* biasp = a.bias ? a.bias + (long long)bkv * a.ld_bias : nullptr;
 
   const int ntiles_all = (a.Tk + BKV - 1) / BKV;
@@ -140,8 +140,8 @@ __global__ void __launch_bounds__(kAttnThreads) attention_kernel(AttnArgs a) {
       for (int ks = 0; ks < KS; ++ks)
         ptx::ldmatrix_x4(qf[ks], ptx::smem_u32(sQ + (warp * 16 + (lane & 15)) * LDS + ks * 16 + (lane >> 4) * 8));
     }
-    const __nv_bfloat16* tK = sK + buf * BKV * LDS;
-    const __nv_bfloat16* tV = sV + buf * BKV * LDS;
+    const op_t* tK = sK + buf * BKV * LDS;
+    const op_t* tV = sV + buf * BKV * LDS;
 
     // ---- S = Q K^T  (16 x 64 per warp)
     float s[8][4];
@@ -214,8 +214,8 @@ __global__ void __launch_bounds__(kAttnThreads) attention_kernel(AttnArgs a) {
       const float p3 = fast_exp2(fmaf(s[n][3], a.scale_log2, -msc[1]));
       rs[0] += p0 + p1;
       rs[1] += p2 + p3;
-      const __nv_bfloat162 h01 = __floats2bfloat162_rn(p0, p1);
-      const __nv_bfloat162 h23 = __floats2bfloat162_rn(p2, p3);
+      const op2_t h01 = ff2op2(p0, p1);
+      const op2_t h23 = ff2op2(p2, p3);
       pf[n >> 1][(n & 1) * 2 + 0] = *reinterpret_cast<const uint32_t*>(&h01);
       pf[n >> 1][(n & 1) * 2 + 1] = *reinterpret_cast<const uint32_t*>(&h23);
     }
@@ -307,17 +307,17 @@ __global__ void __launch_bounds__(kAttnThreads) attention_kernel(AttnArgs a) {
   const int r0 = q0 + warp * 16 + g;
   const float inv0 = l_run[0] > 0.f ? 1.f / l_run[0] : 0.f;
   const float inv1 = l_run[1] > 0.f ? 1.f / l_run[1] : 0.f;
-  __nv_bfloat16* op = a.o + (long long)b * a.bs_o + (long long)head * D;
+  op_t* op = a.o + (long long)b * a.bs_o + (long long)head * D;
 #pragma unroll
   for (int n = 0; n < NB; ++n) {
     const int col = n * 8 + t4 * 2;
     if (col < D) {
       if (r0 < a.Tq)
-        *reinterpret_cast<__nv_bfloat162*>(op + (long long)r0 * a.ld_o + col) =
-            __floats2bfloat162_rn(o_acc[n][0] * inv0, o_acc[n][1] * inv0);
+        *reinterpret_cast<op2_t*>(op + (long long)r0 * a.ld_o + col) =
+            ff2op2(o_acc[n][0] * inv0, o_acc[n][1] * inv0);
       if (r0 + 8 < a.Tq)
-        *reinterpret_cast<__nv_bfloat162*>(op + (long long)(r0 + 8) * a.ld_o + col) =
-            __floats2bfloat162_rn(o_acc[n][2] * inv1, o_acc[n][3] * inv1);
+        *reinterpret_cast<op2_t*>(op + (long long)(r0 + 8) * a.ld_o + col) =
+            ff2op2(o_acc[n][2] * inv1, o_acc[n][3] * inv1);
     }
   }
 }
@@ -360,10 +360,10 @@ static int attention_impl(const void* q, int64_t ld_q, int64_t q_bs, const void*
   AE_CHECK_ARG(ld_q % 8 == 0 && ld_k % 8 == 0 && ld_v % 8 == 0 && ld_o % 2 == 0,
                "ae_attention: row strides must keep 16-byte alignment");
   AttnArgs a;
-  a.q = reinterpret_cast<const __nv_bfloat16*>(q);
-  a.k = reinterpret_cast<const __nv_bfloat16*>(k);
-  a.v = reinterpret_cast<const __nv_bfloat16*>(v);
-  a.o = reinterpret_cast<__nv_bfloat16*>(out);
+  a.q = reinterpret_cast<const op_t*>(q);
+  a.k = reinterpret_cast<const op_t*>(k);
+  a.v = reinterpret_cast<const op_t*>(v);
+  a.o = reinterpret_cast<op_t*>(out);
   a.ld_q = ld_q;
   a.ld_k = ld_k;
   a.ld_v = ld_v;

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdarg.h>
@@ -10,6 +11,36 @@
 #include "../../include/aedit.h"
 
 namespace aedit {
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Tensor-core OPERAND type ("op_t"): the 16-bit type of every GEMM / attention operand (activations after a norm /
+// activation, weights, text K/V).  Accumulation, the residual stream, norm statistics and the scheduler state are fp32
+// either way, and tcgen05 kind::f16 / mma.sync run fp16 and bf16 at the same rate.  Default: IEEE fp16 — every operand
+// of this path is normalised or O(1) (GroupNorm / LayerNorm outputs, softmax weights, fan-in scaled weights), so the
+// 5-bit exponent is enough and the 10-bit mantissa cuts the operand rounding error 8x versus bf16 (measured per block
+// in profiles/r02_error_attribution_*); conversions saturate to +-65504 instead of producing inf.  -DAE_OPERAND_BF16
+// builds the bf16 variant (libaedit_bf16.so, AEDIT_OPERANDS=bf16), the precision BASELINE.json names for configs[1].
+// ---------------------------------------------------------------------------------------------------------------------
+#ifdef AE_OPERAND_BF16
+using op_t = __nv_bfloat16;
+using op2_t = __nv_bfloat162;
+#define AE_OPERAND_DTYPE 0
+#define AE_TMAP_OPERAND_TYPE CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
+__host__ __device__ __forceinline__ op_t f2op(float x) { return __float2bfloat16_rn(x); }
+__host__ __device__ __forceinline__ float op2f(op_t x) { return __bfloat162float(x); }
+__device__ __forceinline__ op2_t ff2op2(float a, float b) { return __floats2bfloat162_rn(a, b); }
+__device__ __forceinline__ float2 op22f2(op2_t v) { return __bfloat1622float2(v); }
+#else
+using op_t = __half;
+using op2_t = __half2;
+#define AE_OPERAND_DTYPE 1
+#define AE_TMAP_OPERAND_TYPE CU_TENSOR_MAP_DATA_TYPE_FLOAT16
+__host__ __device__ __forceinline__ float ae_sat16(float x) { return fminf(fmaxf(x, -65504.0f), 65504.0f); }
+__host__ __device__ __forceinline__ op_t f2op(float x) { return __float2half_rn(ae_sat16(x)); }
+__host__ __device__ __forceinline__ float op2f(op_t x) { return __half2float(x); }
+__device__ __forceinline__ op2_t ff2op2(float a, float b) { return __floats2half2_rn(ae_sat16(a), ae_sat16(b)); }
+__device__ __forceinline__ float2 op22f2(op2_t v) { return __half22float2(v); }
+#endif
 
 extern thread_local char g_err[512];
 extern std::atomic<long long> g_launches;
@@ -109,10 +140,10 @@ inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
 
-__device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+__device__ __forceinline__ float op_round(float x) { return op2f(f2op(x)); }
 
-struct __align__(16) bf16x8 {
-  __nv_bfloat162 v[4];
+struct __align__(16) op_x8 {
+  op2_t v[4];
 };
 
 }  // namespace aedit

@@ -56,7 +56,7 @@ struct GemmDev {
   long long ld_res;
   float* out_f32;
   long long ld_out_f32;
-  __nv_bfloat16* out_bf16;
+  op_t* out_bf16;
   long long ld_out_bf16;
   long long stride_out, stride_res;
   int w_dynamic;  // 1: the W operand is produced by a preceding kernel (never prefetch it ahead of the dependency)
@@ -235,16 +235,16 @@ __device__ __forceinline__ void epilogue_chunk(const GemmDev& p, float (&acc)[32
     }
   }
   if (p.out_bf16) {
-    __nv_bfloat16* ob = p.out_bf16 + (long long)z * p.stride_out + m * p.ld_out_bf16;
+    op_t* ob = p.out_bf16 + (long long)z * p.stride_out + m * p.ld_out_bf16;
     if ((ovalid == 32 || ovalid == 16) && ((reinterpret_cast<uintptr_t>(ob + obase) & 15) == 0)) {
       uint4* o4 = reinterpret_cast<uint4*>(ob + obase);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         if (8 * j < ovalid) {
-          __nv_bfloat162 h0 = __floats2bfloat162_rn(acc[8 * j + 0], acc[8 * j + 1]);
-          __nv_bfloat162 h1 = __floats2bfloat162_rn(acc[8 * j + 2], acc[8 * j + 3]);
-          __nv_bfloat162 h2 = __floats2bfloat162_rn(acc[8 * j + 4], acc[8 * j + 5]);
-          __nv_bfloat162 h3 = __floats2bfloat162_rn(acc[8 * j + 6], acc[8 * j + 7]);
+          op2_t h0 = ff2op2(acc[8 * j + 0], acc[8 * j + 1]);
+          op2_t h1 = ff2op2(acc[8 * j + 2], acc[8 * j + 3]);
+          op2_t h2 = ff2op2(acc[8 * j + 4], acc[8 * j + 5]);
+          op2_t h3 = ff2op2(acc[8 * j + 6], acc[8 * j + 7]);
           uint4 pk;
           pk.x = *reinterpret_cast<uint32_t*>(&h0);
           pk.y = *reinterpret_cast<uint32_t*>(&h1);
@@ -256,7 +256,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmDev& p, float (&acc)[32
     } else {
 #pragma unroll
       for (int j = 0; j < 32; ++j)
-        if (j < ovalid) ob[obase + j] = __float2bfloat16_rn(acc[j]);
+        if (j < ovalid) ob[obase + j] = f2op(acc[j]);
     }
   }
 }
@@ -357,14 +357,14 @@ __device__ __forceinline__ void epilogue_strip(const GemmDev& p, float* strip, u
       if (p.out_f32)
         *reinterpret_cast<float2*>(p.out_f32 + (long long)zo * p.stride_out + m * p.ld_out_f32 + ocol) = make_float2(o0, o1);
       if (p.out_bf16) {
-        __nv_bfloat162 h = __floats2bfloat162_rn(o0, o1);
-        *reinterpret_cast<__nv_bfloat162*>(p.out_bf16 + (long long)zo * p.stride_out + m * p.ld_out_bf16 + ocol) = h;
+        op2_t h = ff2op2(o0, o1);
+        *reinterpret_cast<op2_t*>(p.out_bf16 + (long long)zo * p.stride_out + m * p.ld_out_bf16 + ocol) = h;
       }
     }
     return;
   }
   float* of = p.out_f32 ? p.out_f32 + (long long)zo * p.stride_out + n : nullptr;
-  __nv_bfloat16* ob = p.out_bf16 ? p.out_bf16 + (long long)zo * p.stride_out + n : nullptr;
+  op_t* ob = p.out_bf16 ? p.out_bf16 + (long long)zo * p.stride_out + n : nullptr;
   // column statistics of this strip (rows in increasing order per lane, then a fixed tree over the lanes that share
   // the columns): per-column sum and sum of squares of the final fp32 values
   float4 cs_s = make_float4(0.f, 0.f, 0.f, 0.f), cs_q = cs_s;
@@ -404,8 +404,8 @@ __device__ __forceinline__ void epilogue_strip(const GemmDev& p, float* strip, u
         }
         if (of) *reinterpret_cast<float4*>(of + m * p.ld_out_f32) = a;
         if (ob) {
-          __nv_bfloat162 h0 = __floats2bfloat162_rn(a.x, a.y);
-          __nv_bfloat162 h1 = __floats2bfloat162_rn(a.z, a.w);
+          op2_t h0 = ff2op2(a.x, a.y);
+          op2_t h1 = ff2op2(a.z, a.w);
           uint2 pk;
           pk.x = *reinterpret_cast<uint32_t*>(&h0);
           pk.y = *reinterpret_cast<uint32_t*>(&h1);
@@ -945,7 +945,7 @@ struct ReduceArgs {
   long long ld_res;
   float* out_f32;
   long long ld_out_f32;
-  __nv_bfloat16* out_bf16;
+  op_t* out_bf16;
   long long ld_out_bf16;
   int act;
   float alpha;
@@ -1024,9 +1024,9 @@ __global__ void __launch_bounds__(256) splitk_reduce_kernel(ReduceArgs a) {
       for (int k = 0; k < 4; ++k) o[k] = v[k];
     }
     if (a.out_bf16) {
-      __nv_bfloat16* o = a.out_bf16 + m * a.ld_out_bf16 + n;
+      op_t* o = a.out_bf16 + m * a.ld_out_bf16 + n;
 #pragma unroll
-      for (int k = 0; k < 4; ++k) o[k] = __float2bfloat16_rn(v[k]);
+      for (int k = 0; k < 4; ++k) o[k] = f2op(v[k]);
     }
   }
 }
@@ -1108,9 +1108,9 @@ __global__ void __launch_bounds__(256) splitk_reduce_stats_kernel(ReduceArgs a) 
     cq.x = fmaf(v[0], v[0], cq.x); cq.y = fmaf(v[1], v[1], cq.y); cq.z = fmaf(v[2], v[2], cq.z); cq.w = fmaf(v[3], v[3], cq.w);
     if (a.out_f32) *reinterpret_cast<float4*>(a.out_f32 + m * a.ld_out_f32 + n) = make_float4(v[0], v[1], v[2], v[3]);
     if (a.out_bf16) {
-      __nv_bfloat16* o = a.out_bf16 + m * a.ld_out_bf16 + n;
+      op_t* o = a.out_bf16 + m * a.ld_out_bf16 + n;
 #pragma unroll
-      for (int k = 0; k < 4; ++k) o[k] = __float2bfloat16_rn(v[k]);
+      for (int k = 0; k < 4; ++k) o[k] = f2op(v[k]);
     }
   }
   *reinterpret_cast<float4*>(&s_sum[warp][lane * 4]) = cs;
@@ -1166,7 +1166,7 @@ int make_tmap(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims,
   if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) return fail(AE_EINVAL, "TMA base pointer not 16-byte aligned");
   for (int i = 0; i < rank - 1; ++i)
     if (gs[i] % 16 != 0) return fail(AE_EINVAL, "TMA stride %d = %llu bytes not a multiple of 16", i, (unsigned long long)gs[i]);
-  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es,
+  CUresult r = enc(tm, AE_TMAP_OPERAND_TYPE, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(AE_ECUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
@@ -1354,7 +1354,7 @@ extern "C" int ae_gemm(const ae_gemm_args* a, ae_stream stream) {
   p.ld_res = a->ld_res;
   p.out_f32 = a->out_f32;
   p.ld_out_f32 = a->ld_out_f32;
-  p.out_bf16 = reinterpret_cast<__nv_bfloat16*>(a->out_bf16);
+  p.out_bf16 = reinterpret_cast<op_t*>(a->out_bf16);
   p.ld_out_bf16 = a->ld_out_bf16;
   p.stride_out = a->stride_out;
   p.stride_res = a->stride_res;

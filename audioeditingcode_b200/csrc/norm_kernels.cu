@@ -25,8 +25,8 @@ struct GNArgs {
   const float* gamma;
   const float* beta;
   int silu;
-  __nv_bfloat16* out;
-  __nv_bfloat16* raw_out;
+  op_t* out;
+  op_t* raw_out;
   float* cat_out;
   double* partial;     // [B, S, G, 2]
   float* stats;        // [B, G, 2] mean, rstd
@@ -300,15 +300,15 @@ __global__ void __launch_bounds__(kGNThreads) gn_apply_kernel(GNArgs a) {
       for (int k = 0; k < 4; ++k) o[k] = silu_f(o[k]);
     }
     const long long off = row * a.C + c;
-    __nv_bfloat162 h0 = __floats2bfloat162_rn(o[0], o[1]);
-    __nv_bfloat162 h1 = __floats2bfloat162_rn(o[2], o[3]);
+    op2_t h0 = ff2op2(o[0], o[1]);
+    op2_t h1 = ff2op2(o[2], o[3]);
     uint2 pk;
     pk.x = *reinterpret_cast<uint32_t*>(&h0);
     pk.y = *reinterpret_cast<uint32_t*>(&h1);
     *reinterpret_cast<uint2*>(a.out + off) = pk;
     if (a.raw_out) {
-      __nv_bfloat162 r0 = __floats2bfloat162_rn(in[0], in[1]);
-      __nv_bfloat162 r1 = __floats2bfloat162_rn(in[2], in[3]);
+      op2_t r0 = ff2op2(in[0], in[1]);
+      op2_t r1 = ff2op2(in[2], in[3]);
       uint2 rk;
       rk.x = *reinterpret_cast<uint32_t*>(&r0);
       rk.y = *reinterpret_cast<uint32_t*>(&r1);
@@ -377,15 +377,15 @@ __global__ void __launch_bounds__(kGNThreads) gn_apply_stream_kernel(GNArgs a, i
         for (int e = 0; e < 4; ++e) o[e] = silu_f(o[e]);
       }
       const long long off = (row0 + pr[k]) * a.C + c;
-      __nv_bfloat162 h0 = __floats2bfloat162_rn(o[0], o[1]);
-      __nv_bfloat162 h1 = __floats2bfloat162_rn(o[2], o[3]);
+      op2_t h0 = ff2op2(o[0], o[1]);
+      op2_t h1 = ff2op2(o[2], o[3]);
       uint2 pk;
       pk.x = *reinterpret_cast<uint32_t*>(&h0);
       pk.y = *reinterpret_cast<uint32_t*>(&h1);
       *reinterpret_cast<uint2*>(a.out + off) = pk;
       if (a.raw_out) {
-        __nv_bfloat162 r0 = __floats2bfloat162_rn(in[0], in[1]);
-        __nv_bfloat162 r1 = __floats2bfloat162_rn(in[2], in[3]);
+        op2_t r0 = ff2op2(in[0], in[1]);
+        op2_t r1 = ff2op2(in[2], in[3]);
         uint2 rk;
         rk.x = *reinterpret_cast<uint32_t*>(&r0);
         rk.y = *reinterpret_cast<uint32_t*>(&r1);
@@ -572,15 +572,15 @@ __global__ void __launch_bounds__(512) gn_resident_kernel(GNArgs a) {
         for (int e = 0; e < 4; ++e) o[e] = silu_f(o[e]);
       }
       const long long off = row * a.C + c;
-      __nv_bfloat162 h0 = __floats2bfloat162_rn(o[0], o[1]);
-      __nv_bfloat162 h1 = __floats2bfloat162_rn(o[2], o[3]);
+      op2_t h0 = ff2op2(o[0], o[1]);
+      op2_t h1 = ff2op2(o[2], o[3]);
       uint2 pk;
       pk.x = *reinterpret_cast<uint32_t*>(&h0);
       pk.y = *reinterpret_cast<uint32_t*>(&h1);
       *reinterpret_cast<uint2*>(a.out + off) = pk;
       if (a.raw_out) {
-        __nv_bfloat162 r0 = __floats2bfloat162_rn(in[0], in[1]);
-        __nv_bfloat162 r1 = __floats2bfloat162_rn(in[2], in[3]);
+        op2_t r0 = ff2op2(in[0], in[1]);
+        op2_t r1 = ff2op2(in[2], in[3]);
         uint2 rk;
         rk.x = *reinterpret_cast<uint32_t*>(&r0);
         rk.y = *reinterpret_cast<uint32_t*>(&r1);
@@ -595,7 +595,7 @@ __global__ void __launch_bounds__(512) gn_resident_kernel(GNArgs a) {
 template <int NV>
 __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, long long rows, int C, float eps,
                                                         const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                        __nv_bfloat16* __restrict__ out) {
+                                                        op_t* __restrict__ out) {
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   // the affine parameters are weights (never written by the previous kernel): fetch them before the dependency wait
@@ -636,15 +636,15 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
   const float rstd = rsqrtf(sq / (float)C + eps);
-  __nv_bfloat16* orow = out + row * C;
+  op_t* orow = out + row * C;
 #pragma unroll
   for (int k = 0; k < NV; ++k) {
     const int c = lane * 4 + k * 128;
     if (c < C) {
       const float4 g = gm[k];
       const float4 bb = bt[k];
-      __nv_bfloat162 h0 = __floats2bfloat162_rn((v[k].x - mean) * rstd * g.x + bb.x, (v[k].y - mean) * rstd * g.y + bb.y);
-      __nv_bfloat162 h1 = __floats2bfloat162_rn((v[k].z - mean) * rstd * g.z + bb.z, (v[k].w - mean) * rstd * g.w + bb.w);
+      op2_t h0 = ff2op2((v[k].x - mean) * rstd * g.x + bb.x, (v[k].y - mean) * rstd * g.y + bb.y);
+      op2_t h1 = ff2op2((v[k].z - mean) * rstd * g.z + bb.z, (v[k].w - mean) * rstd * g.w + bb.w);
       uint2 pk;
       pk.x = *reinterpret_cast<uint32_t*>(&h0);
       pk.y = *reinterpret_cast<uint32_t*>(&h1);
@@ -655,7 +655,7 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
 
 template <int NV>
 cudaError_t launch_ln(const float* x, long long rows, int C, float eps, const float* gamma, const float* beta,
-                      __nv_bfloat16* out, cudaStream_t st) {
+                      op_t* out, cudaStream_t st) {
   // one warp per row; few rows (reverse process at batch 2: 128-2048 rows) -> fewer rows per CTA so the rows spread
   // over all SMs instead of queueing on a few
   const int warps = rows >= 148 * 16 ? 4 : (rows >= 148 * 4 ? 2 : 1);
@@ -713,8 +713,8 @@ static int groupnorm_impl(const float* x1, int C1, const float* x2, int C2, int 
   a.gamma = gamma;
   a.beta = beta;
   a.silu = silu;
-  a.out = reinterpret_cast<__nv_bfloat16*>(out_bf16);
-  a.raw_out = reinterpret_cast<__nv_bfloat16*>(raw_out_bf16);
+  a.out = reinterpret_cast<op_t*>(out_bf16);
+  a.raw_out = reinterpret_cast<op_t*>(raw_out_bf16);
   a.cat_out = cat_out_f32;
   char* wsb = reinterpret_cast<char*>(workspace);
   a.partial = reinterpret_cast<double*>(wsb);
@@ -811,7 +811,7 @@ extern "C" int ae_layernorm(const float* x, int64_t rows, int C, float eps, cons
                             void* out_bf16, ae_stream stream) {
   AE_CHECK_ARG(x && gamma && beta && out_bf16 && rows > 0 && C > 0, "ae_layernorm: bad argument");
   AE_CHECK_ARG(C % 4 == 0 && C <= 2048, "ae_layernorm: C=%d must be a multiple of 4 and <= 2048", C);
-  __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out_bf16);
+  op_t* o = reinterpret_cast<op_t*>(out_bf16);
   cudaStream_t st = as_stream(stream);
   const int nv = (C + 127) / 128;
   cudaError_t e;

@@ -30,7 +30,8 @@ struct ae_sched {
 using namespace aedit;
 
 extern "C" const char* ae_last_error(void) { return g_err; }
-extern "C" int ae_version(void) { return 100; }
+extern "C" int ae_version(void) { return 200; }
+extern "C" int ae_operand_dtype(void) { return AE_OPERAND_DTYPE; }
 extern "C" int64_t ae_launch_count(void) { return g_launches.load(); }
 extern "C" int ae_device_ok(void) {
   int dev = 0;

@@ -53,7 +53,7 @@ class _PendingForward:
     semantics.  The fast path is taken only if the tensors handed to the reverse process are the ones the forward
     process returned, unmodified (same storage, same torch version counters) — anything else falls back to plain
     stream order.  Results are bit-identical to the non-overlapped execution (same kernels, same batches; tested)."""
-    __slots__ = ("zs_ptr", "zs_ver", "xts_ptr", "xts_ver", "chunks", "eta_key", "N")
+    __slots__ = ("zs_ptr", "zs_ver", "xts_ptr", "xts_ver", "chunks", "eta_key", "N", "setup_event")
 
     def __init__(self):
         self.chunks = []          # (idx_lo, idx_hi, event): rows zs[lo..hi], xts[lo..hi] are final once event fired
@@ -214,6 +214,7 @@ def _loop_text(model: PipelineWrapper, neg_prompts, prompts):
     if hit is None:
         if len(cache) > 8:
             cache.clear()
+            model.engine.evict_graphs(model.live_texts() if hasattr(model, "live_texts") else ())
         uncond = model.encode_text(list(neg_prompts), negative=True)
         cond = None if prompts is None else model.encode_text(list(prompts))
         streams, masks, cl = _cat_text(model, uncond, cond)
@@ -318,6 +319,11 @@ def inversion_forward_process(model: PipelineWrapper,
     if overlap:
         pend = _PendingForward()
         lane = _lane(model, "fwd")
+        # xts (ae_sample_xts) and the zs fill were enqueued on the caller's stream: the forward lane waits for them here,
+        # and the reverse lane — which on the fast path never joins the caller's stream — waits for this event before it
+        # reads xts[tstart] (row N is written by ae_sample_xts only, no forward chunk finalises it)
+        pend.setup_event = torch.cuda.Event()
+        pend.setup_event.record(cur)
         lane.wait_stream(cur)
     for chunk_no, (pos0, count) in enumerate(it):
         if g_ws > 1:
@@ -423,6 +429,7 @@ def inversion_reverse_process(model: PipelineWrapper,
             lane.wait_stream(cur)
         else:
             model.overlap_hits = getattr(model, "overlap_hits", 0) + 1
+            lane.wait_event(pend.setup_event)
     waited = set()
 
     def need(idx):

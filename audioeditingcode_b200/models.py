@@ -255,10 +255,18 @@ class PipelineWrapper(torch.nn.Module):
         if tc is None:
             if len(self._text_cache) > 16:
                 self._text_cache.clear()
+                self.engine.evict_graphs(self.live_texts())
             tc = self.engine.prepare_text(streams, masks)
             tc._keep = (streams, masks)
             self._text_cache[key] = tc
         return tc
+
+    def live_texts(self):
+        """TextCache objects still referenced by this wrapper's text caches (UNetEngine.evict_graphs keeps their graphs)."""
+        live = list(self._text_cache.values())
+        live += [h[0] for h in self.__dict__.get("_loop_text_cache", {}).values() if h[0] is not None]
+        live += [h[0] for h in self.__dict__.get("_pair_text_cache", {}).values() if h[0] is not None]
+        return live
 
     def unet_forward(self,
                      sample: torch.FloatTensor,
@@ -306,14 +314,9 @@ class PipelineWrapper(torch.nn.Module):
             return (out,)
         return UNet2DConditionOutput(sample=out), h_space, extracted
 
-    def cfg_pair_eval(self, x_u: torch.Tensor, x_c: torch.Tensor, timestep, uncond, cond
-                      ) -> Tuple[torch.Tensor, torch.Tensor]:
-        """eps(x_u | uncond) and eps(x_c | cond) — what two `unet_forward` calls return as `.sample` (pc_drift.py:70-83,
-        ddim_inversion.py:23-41) — as ONE batched, CUDA-graph-cached U-Net evaluation (B = 2n rows) instead of two eager
-        ones.  uncond / cond: (encoder_hidden_states, class_labels, encoder_attention_mask) triples as returned by
-        encode_text, with 1 or n rows each."""
+    def _pair_setup(self, n: int, uncond, cond):
+        """Text rows / slot map of a CFG pair batch [n uncond rows | n cond rows], cached per embedding tensors."""
         from .ddm_inversion import inversion_utils as IU
-        n = x_u.shape[0]
         flat = [v for tr in (uncond, cond) for v in tr]
         key = ("pair", n) + tuple(None if v is None else (v.data_ptr(), tuple(v.shape), _ver(v)) for v in flat)
         cache = self.__dict__.setdefault("_pair_text_cache", {})
@@ -321,6 +324,7 @@ class PipelineWrapper(torch.nn.Module):
         if hit is None:
             if len(cache) > 8:
                 cache.clear()
+                self.engine.evict_graphs(self.live_texts())
             streams, masks, cl = IU._cat_text(self, uncond, cond)
             ru = next((v.shape[0] for v in uncond if v is not None), 1)
             rc = next((v.shape[0] for v in cond if v is not None), 1)
@@ -333,12 +337,25 @@ class PipelineWrapper(torch.nn.Module):
             cl_rows = None if cl is None else cl.index_select(0, slot.long())
             hit = (text, cl_rows, slot, (ru, rc), (flat, streams, masks))
             cache[key] = hit
-        text, cl_rows, slot, (ru, rc), _ = hit
+        return hit
+
+    def cfg_pair_eval_batch(self, x: torch.Tensor, timestep, uncond, cond) -> torch.Tensor:
+        """eps of a prebuilt CFG pair batch x = [n rows evaluated under `uncond` | n rows under `cond`] as ONE batched,
+        CUDA-graph-cached U-Net evaluation (pc_drift.py:64-80 issues two eager calls).  uncond / cond: (encoder_hidden_states,
+        class_labels, encoder_attention_mask) triples as returned by encode_text, with 1 or n rows each."""
+        from .ddm_inversion import inversion_utils as IU
+        n = x.shape[0] // 2
+        text, cl_rows, slot, (ru, rc), _ = self._pair_setup(n, uncond, cond)
         if not torch.is_tensor(timestep):
             timestep = torch.tensor(timestep)
         t_in = timestep.reshape(-1)[:1].to(self.device, torch.int64).expand(2 * n).contiguous()
-        x = torch.cat([x_u, x_c], 0).to(self.device, torch.float32)
-        eps = IU._unet_eval(self, x, t_in, text, slot, cl_rows, slot_key=("pair", n, ru, rc))
+        return IU._unet_eval(self, x.to(self.device, torch.float32), t_in, text, slot, cl_rows, slot_key=("pair", n, ru, rc))
+
+    def cfg_pair_eval(self, x_u: torch.Tensor, x_c: torch.Tensor, timestep, uncond, cond
+                      ) -> Tuple[torch.Tensor, torch.Tensor]:
+        """eps(x_u | uncond) and eps(x_c | cond) — what two `unet_forward` calls return as `.sample` (ddim_inversion.py:23-41)."""
+        n = x_u.shape[0]
+        eps = self.cfg_pair_eval_batch(torch.cat([x_u, x_c], 0), timestep, uncond, cond)
         return eps[:n], eps[n:]
 
     # ---------------------------------------------------------------- text (a13)

@@ -33,12 +33,12 @@ class CudaOps:
     executor's wiring on CPU; that backend lives under tests/ and is never importable from this package."""
 
     name = "cuda"
-    act_dtype = BF16
 
     SPLITK_WS_BYTES = 64 << 20
 
     def __init__(self):
         self.lib = _lib.load()
+        self.act_dtype = _lib.operand_torch_dtype()      # fp16 (default build) or bf16 (AEDIT_OPERANDS=bf16)
         self._gn_ws = {}
         self._splitk_ws = {}
         self._attn_ws = {}
@@ -151,7 +151,7 @@ class CudaOps:
         return bool(self.lib.ae_gemm_conv_supported(B, H, W, C_))
 
     def im2col(self, x, B, H, W, C_, kh, kw, stride, dil, pad_t, pad_l, Ho, Wo, out):
-        check(self.lib.ae_im2col(_p(x), 1 if x.dtype == BF16 else 0, B, H, W, C_, kh, kw, stride, dil, pad_t, pad_l,
+        check(self.lib.ae_im2col(_p(x), 0 if x.dtype == F32 else 1, B, H, W, C_, kh, kw, stride, dil, pad_t, pad_l,
                                  Ho, Wo, _p(out), out.stride(0), _stream()), "ae_im2col")
 
     # ---------------------------------------------------------------- norms / activations

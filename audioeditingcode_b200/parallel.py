@@ -25,16 +25,24 @@ def broadcast_(t: torch.Tensor, src: int = 0, group=None) -> torch.Tensor:
     return t
 
 
-def allreduce_rows(local: Optional[torch.Tensor], rows: Sequence[int], like: torch.Tensor, group=None) -> torch.Tensor:
-    """Assemble a `[n_rows, ...]` tensor whose rows were computed on different ranks: every rank scatters its rows
-    (`local[k]` -> row `rows[k]`) into a zero buffer shaped like `like`, then one SUM all-reduce.  Adding zeros is
-    exact, so every rank ends with bit-identical rows (the pc_drift iterate reduction named by BASELINE config 4)."""
-    buf = torch.zeros_like(like)
-    if rows:
-        buf[list(rows)] = local.to(buf.dtype)
-    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-        dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
-    return buf
+def allgather_rows(local: Optional[torch.Tensor], n_rows: int, like_row: torch.Tensor, group=None) -> torch.Tensor:
+    """Assemble a `[n_rows, ...]` tensor whose rows were computed on different ranks (round-robin ownership, see
+    shard_indices): every rank contributes ONLY its owned rows — one all-gather of ceil(n_rows / world) rows per rank,
+    1/world of the bytes of a zero-padded sum-all-reduce — and every rank ends with bit-identical rows (the pc_drift
+    iterate exchange named by BASELINE configs[3])."""
+    rank, ws = world(group)
+    if ws == 1:
+        return local
+    per = (n_rows + ws - 1) // ws
+    send = torch.zeros((per, *like_row.shape), dtype=like_row.dtype, device=like_row.device)
+    mine = shard_indices(n_rows, rank, ws)
+    if mine:
+        send[:len(mine)] = local.to(send.dtype)
+    recv = torch.empty((ws * per, *like_row.shape), dtype=like_row.dtype, device=like_row.device)
+    dist.all_gather_into_tensor(recv, send, group=group)
+    # row i lives at rank i % ws, slot i // ws
+    idx = torch.as_tensor([(i % ws) * per + i // ws for i in range(n_rows)], device=like_row.device)
+    return recv.index_select(0, idx)
 
 
 def shard_indices(n_items: int, rank: int, world_size: int) -> List[int]:

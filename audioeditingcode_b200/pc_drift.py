@@ -1,24 +1,34 @@
-"""Unsupervised principal-direction editing — drop-in for code/pc_drift.py (same names, signatures, returns):
-PromptEmbeddings (:10-13), PCStreamChoice (:16-19), expand_for_evs (:22-26), forward_directional (:29-93),
-get_eigenvectors (:96-198; subspace iteration on the posterior-mean Jacobian, including the reference's
-sort-before-permute behaviour, SURVEY.md Appendix D — reproduced, not repaired), apply_drift (:201-278).
+"""Unsupervised principal-direction editing on the B200 path — drop-in for code/pc_drift.py (same public names,
+signatures and return tuples): PromptEmbeddings (:10-13), PCStreamChoice (:16-19), expand_for_evs (:22-26),
+forward_directional (:29-93), get_eigenvectors (:96-198), apply_drift (:201-278).
 
-Device work: U-Net evaluations through the wrapper (UNetEngine), the CFG combine + DDIM step in one kernel
-(ae_ddim_step via DDIMScheduler.step); the small dense linear algebra of the iteration (norms, QR of [D, n_ev],
-sort) stays in torch (cuSOLVER) — it is O(D*n_ev^2) per iteration against two U-Net evaluations.
+How it runs here (every tensor op of the iteration is a libaedit kernel, csrc/pc_kernels.cu):
 
-Multi-GPU (BASELINE config 4): `get_eigenvectors(..., group=<process group>)` shards the n_ev
-directions of the power iteration across the ranks — each rank runs the U-Net only on its own rows — and
-sum-all-reduces the zero-padded `[n_ev, D]` posterior-mean iterate once per iteration (NCCL over NVLink on the GPU box);
-normalisation, QR and sorting are then done redundantly on every rank, so every rank returns the same tensors as a
-single-process run.  This is the only data-path collective of the repo.
+  forward_directional   ae_pc_perturb writes `xt + amount*eigvecs*sqrt(alpha_bar_t)` straight into the 2n-row CFG batch
+                        (uncond rows | cond rows, per PCStreamChoice) -> ONE graph-cached U-Net evaluation for the pair
+                        (the reference issues two, :64-80) -> ae_ddim_step = CFG combine (:83) + DDIMScheduler.step (:89)
+  get_eigenvectors      per subspace iteration: forward_directional on the n_ev perturbed rows, then
+                        ae_pc_subspace_step = masked difference, per-direction norms, normalisation, re-orthonormalisation
+                        (CholeskyQR2 with LAPACK's Householder sign rule and the reference's `swap` / sort-before-permute
+                        behaviour, SURVEY.md Appendix D — reproduced, not repaired), correlation with the previous iterate
+                        and the next perturbation `const * eigvecs`.  No host synchronisation inside the loop (the
+                        reference syncs on `if swap < 0` every iteration, :165).
+  apply_drift           ae_pc_apply_drift: one elementwise kernel for :232-278
+
+Multi-GPU (BASELINE configs[3]): `get_eigenvectors(..., group=<process group>)` shards the n_ev
+directions over the ranks — each rank runs the U-Net only on its own rows — and ALL-GATHERS the owned rows of the
+posterior-mean iterate once per iteration (NCCL over NVLink: 1/world of the bytes of a zero-padded all-reduce); the
+n x n algebra then runs redundantly, so every rank returns the same tensors as a single-process run.
 """
 from __future__ import annotations
 
+import ctypes as C
 from enum import Enum
 from typing import Dict, List, NamedTuple, Optional, Tuple
 
 import torch
+
+from . import _lib
 
 
 class PromptEmbeddings(NamedTuple):
@@ -36,51 +46,66 @@ class PCStreamChoice(Enum):
 def expand_for_evs(x: torch.Tensor, n_ev: int) -> torch.Tensor:
     if x is None:
         return x
-    dev = x.device
-    return x.repeat(n_ev, *[1] * (len(x.shape) - 1)).to(dev)
+    return x.repeat(n_ev, *[1] * (len(x.shape) - 1)).to(x.device)
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _f32(t: torch.Tensor, device) -> torch.Tensor:
+    return t.to(device=device, dtype=torch.float32).contiguous()
+
+
+def _triple(e: PromptEmbeddings):
+    return (e.embedding_hidden_states, e.embedding_class_lables, e.boolean_prompt_mask)
 
 
 def forward_directional(ldm_stable, xt: torch.Tensor, timestep: torch.Tensor, latent: torch.Tensor,
                         uncond_emb: PromptEmbeddings, text_emb: PromptEmbeddings, cfg_tar: torch.Tensor,
                         eta: float = 1, eigvecs: torch.Tensor = 0, amount: float = 0, double_precision: bool = False,
-                        mode: PCStreamChoice = PCStreamChoice.BOTH) -> torch.Tensor:
+                        mode: PCStreamChoice = PCStreamChoice.BOTH) -> Tuple[torch.Tensor, torch.Tensor]:
+    """One CFG denoising step, optionally with the input shifted along `eigvecs` (pc_drift.py:29-93).  Returns
+    (prev_sample, pred_original_sample).  Embeddings with one row are shared by all rows of `xt` (the reference
+    repeats them, :46-58; here the text K/V of the single row are indexed by every sample)."""
     if double_precision:
         raise NotImplementedError("double_precision is not available on the B200 path")
-    with torch.no_grad():
-        input = xt + amount * eigvecs * torch.sqrt(ldm_stable.model.scheduler.alphas_cumprod[int(timestep)])
-    if len(xt) > 1 and \
-        ((uncond_emb.boolean_prompt_mask is not None and len(uncond_emb.boolean_prompt_mask) == 1) or
-         (uncond_emb.embedding_hidden_states is not None and len(uncond_emb.embedding_hidden_states) == 1)):
-        n_ev = len(xt)
-        uncond_emb = PromptEmbeddings(
-            embedding_hidden_states=expand_for_evs(uncond_emb.embedding_hidden_states, n_ev),
-            boolean_prompt_mask=expand_for_evs(uncond_emb.boolean_prompt_mask, n_ev),
-            embedding_class_lables=expand_for_evs(uncond_emb.embedding_class_lables, n_ev))
-        text_emb = PromptEmbeddings(
-            embedding_hidden_states=expand_for_evs(text_emb.embedding_hidden_states, n_ev),
-            boolean_prompt_mask=expand_for_evs(text_emb.boolean_prompt_mask, n_ev),
-            embedding_class_lables=expand_for_evs(text_emb.embedding_class_lables, n_ev))
-    x_u = input if mode == PCStreamChoice.BOTH or mode == PCStreamChoice.UNCOND else xt
-    x_c = input if mode == PCStreamChoice.BOTH or mode == PCStreamChoice.TEXT else xt
-    with torch.no_grad():
-        if hasattr(ldm_stable, "cfg_pair_eval") and x_u.is_cuda:
-            # one batched, graph-cached evaluation for the pair (the reference issues two: pc_drift.py:70-81)
-            eps_u, eps_c = ldm_stable.cfg_pair_eval(
-                x_u, x_c, timestep,
-                (uncond_emb.embedding_hidden_states, uncond_emb.embedding_class_lables, uncond_emb.boolean_prompt_mask),
-                (text_emb.embedding_hidden_states, text_emb.embedding_class_lables, text_emb.boolean_prompt_mask))
-        else:
-            eps_u = ldm_stable.unet_forward(
-                x_u, timestep=timestep, encoder_hidden_states=uncond_emb.embedding_hidden_states,
-                class_labels=uncond_emb.embedding_class_lables,
-                encoder_attention_mask=uncond_emb.boolean_prompt_mask)[0].sample
-            eps_c = ldm_stable.unet_forward(
-                x_c, timestep=timestep, encoder_hidden_states=text_emb.embedding_hidden_states,
-                class_labels=text_emb.embedding_class_lables,
-                encoder_attention_mask=text_emb.boolean_prompt_mask)[0].sample
-    noise_pred = eps_u + cfg_tar * (eps_c - eps_u)                                               # pc_drift.py:83
-    res = ldm_stable.model.scheduler.step(noise_pred, timestep, input, eta=eta, variance_noise=latent)
-    return res.prev_sample, res.pred_original_sample
+    lib = _lib.load()
+    dev = ldm_stable.device
+    sched = ldm_stable.model.scheduler
+    xt = _f32(xt, dev)
+    n = xt.shape[0]
+    n_el = xt[0].numel()
+    ev = None
+    if torch.is_tensor(eigvecs) and amount != 0:
+        ev = _f32(eigvecs, dev)
+        if ev.shape[0] != n:
+            ev = ev.expand(n, *ev.shape[1:]).contiguous()
+    # torch.sqrt on the host scalar like the reference (:42); alphas_cumprod lives on the CPU
+    sqrt_ab = float(torch.sqrt(sched.alphas_cumprod[int(timestep)]))
+    x_batch = torch.empty((2 * n, *xt.shape[1:]), device=dev, dtype=torch.float32)
+    inp = torch.empty_like(xt)
+    _lib.check(lib.ae_pc_perturb(_p(xt), n_el, _p(ev), float(amount), sqrt_ab, int(mode.value), n, _p(x_batch), _p(inp),
+                                 n_el, _stream()), "ae_pc_perturb")
+    eps = ldm_stable.cfg_pair_eval_batch(x_batch, timestep, _triple(uncond_emb), _triple(text_emb))
+    tab = sched.table
+    pos = tab.pos_of_t(int(timestep))
+    vn = None
+    if eta > 0:
+        if latent is None:
+            latent = torch.randn(xt.shape, device=dev)
+        vn = _f32(latent, dev)
+        if vn.shape[0] != n:
+            vn = vn.expand(n, *vn.shape[1:]).contiguous()
+    prev = torch.empty_like(xt)
+    x0p = torch.empty_like(xt)
+    _lib.check(lib.ae_ddim_step(tab.h, pos, float(eta), float(cfg_tar), _p(eps), _p(eps[n:]), _p(inp), _p(vn), _p(prev),
+                                _p(x0p), xt.numel(), _stream()), "ae_ddim_step")
+    return prev, x0p
 
 
 def get_eigenvectors(ldm_stable, xt: torch.Tensor, text_emb: PromptEmbeddings, uncond_emb: PromptEmbeddings,
@@ -89,77 +114,67 @@ def get_eigenvectors(ldm_stable, xt: torch.Tensor, text_emb: PromptEmbeddings, u
                      iters: int = 50, double_precision: bool = False, eta: float = 1, n_ev: int = 1, group=None
                      ) -> Tuple[torch.Tensor, torch.Tensor, List[torch.Tensor], List[torch.Tensor],
                                 Dict[int, torch.Tensor], Dict[int, torch.Tensor]]:
-    """`group` (extension, default None = the reference's single-process behaviour): a torch.distributed process
-    group over which the n_ev directions are sharded (see module docstring)."""
+    """Subspace (power) iteration on the Jacobian of the posterior mean (pc_drift.py:96-198).
+    `group` (extension; None = the reference's single-process behaviour): process group over which the n_ev directions
+    are sharded, see the module docstring."""
     from . import parallel as _par
+    lib = _lib.load()
+    dev = ldm_stable.device
     rank, ws = _par.world(group) if group is not None else (0, 1)
-    rows = _par.shard_indices(n_ev, rank, ws) if ws > 1 else None
-    if n_ev > 1:
-        x0_pred = expand_for_evs(x0_pred, n_ev)
-        xt = expand_for_evs(xt, n_ev)
-        uncond_emb = PromptEmbeddings(
-            embedding_hidden_states=expand_for_evs(uncond_emb.embedding_hidden_states, n_ev),
-            boolean_prompt_mask=expand_for_evs(uncond_emb.boolean_prompt_mask, n_ev),
-            embedding_class_lables=expand_for_evs(uncond_emb.embedding_class_lables, n_ev))
-        text_emb = PromptEmbeddings(
-            embedding_hidden_states=expand_for_evs(text_emb.embedding_hidden_states, n_ev),
-            boolean_prompt_mask=expand_for_evs(text_emb.boolean_prompt_mask, n_ev),
-            embedding_class_lables=expand_for_evs(text_emb.embedding_class_lables, n_ev))
-    eigvecs = torch.randn_like(xt) * mask * const
-    if rows is not None:
-        _par.broadcast_(eigvecs, 0, group)      # one random start for all ranks
-    prev_ev = eigvecs.detach().clone()
+    rows = _par.shard_indices(n_ev, rank, ws) if ws > 1 else list(range(n_ev))
+    xt1 = _f32(xt, dev)
+    shape = (n_ev, *xt1.shape[1:])
+    n_el = xt1[0].numel()
+    x0_ref = _f32(x0_pred, dev)[0].contiguous()
+    mask_d = _f32(mask, dev)
+    mask1 = mask_d[0].expand(xt1.shape[1:]).contiguous()
+    xt_n = xt1.expand(shape) if xt1.shape[0] == 1 else xt1
+    # random start: randn_like of the n_ev-row tensor like the reference (:130), one draw for all ranks
+    scaled = torch.randn(shape, device=dev, dtype=torch.float32) * mask_d * const
+    if ws > 1:
+        _par.broadcast_(scaled, 0, group)
+    prev = scaled.clone()
+    cur = torch.empty_like(scaled)
+    ws_bytes = int(lib.ae_pc_workspace_bytes(n_ev, n_el))
+    work = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     in_corr, in_norm = [], []
     interm_eigvecs, interm_eigvals = {}, {}
+    sigma2 = ldm_stable.get_sigma(t) ** 2
+    pick = (lambda v: v if (v is None or len(v) != n_ev) else v[rows])
+    unc_r = PromptEmbeddings(*[pick(v) for v in uncond_emb])
+    txt_r = PromptEmbeddings(*[pick(v) for v in text_emb])
+    lat_r = pick(latents)
     with torch.no_grad():
         for i in range(iters):
-            if rows is None:
-                _, unmaksed_out = forward_directional(ldm_stable, xt, t, latents, uncond_emb, text_emb, cfg_tar,
-                                                      eta=eta, eigvecs=eigvecs, amount=1,
-                                                      double_precision=double_precision, mode=pc_mode)
+            if ws == 1:
+                _, x0p = forward_directional(ldm_stable, xt_n, t, latents, uncond_emb, text_emb, cfg_tar, eta=eta,
+                                             eigvecs=scaled, amount=1, double_precision=double_precision, mode=pc_mode)
             else:
                 local = None
                 if rows:
-                    pick = (lambda v: v if v is None or len(v) != n_ev else v[rows])
-                    _, local = forward_directional(
-                        ldm_stable, xt[rows], t, pick(latents), PromptEmbeddings(*[pick(v) for v in uncond_emb]),
-                        PromptEmbeddings(*[pick(v) for v in text_emb]), cfg_tar, eta=eta, eigvecs=eigvecs[rows],
-                        amount=1, double_precision=double_precision, mode=pc_mode)
-                unmaksed_out = _par.allreduce_rows(local, rows, xt, group)
-            out = unmaksed_out * mask
-            Ab = out - x0_pred
-            if n_ev > 1:
-                if len(xt.shape) == 4:
-                    permute_arg = (1, 2, 3, 0)
-                elif len(xt.shape) == 3:
-                    permute_arg = (1, 2, 0)
-                elif len(xt.shape) == 2:
-                    permute_arg = (1, 0)
-                norm_of_Ab = Ab[:, mask[0].to(torch.bool)].norm(dim=1)
-                eigvecs = (Ab / norm_of_Ab.reshape(n_ev, *[1] * (len(xt.shape) - 1))) * mask
-                Q, R = torch.linalg.qr(eigvecs.permute(*permute_arg).reshape(-1, n_ev), mode='reduced')
-                swap = torch.prod(torch.linalg.diagonal(R))
-                if swap < 0:
-                    Q *= -1
-                eigvecs = Q / Q.norm(dim=0)
-                eigvecs = eigvecs.T.reshape(Ab.shape)
-                _, tmp = (norm_of_Ab / const * (ldm_stable.get_sigma(t) ** 2)).reshape(n_ev, ).sort(
-                    descending=True, stable=True)
-                eigvecs = eigvecs[tmp, ...]
-            else:
-                norm_of_Ab = Ab[mask.to(torch.bool)].norm()
-                eigvecs = (Ab / norm_of_Ab) * mask
+                    _, local = forward_directional(ldm_stable, xt_n[rows], t, lat_r, unc_r, txt_r, cfg_tar, eta=eta,
+                                                   eigvecs=scaled[rows], amount=1, double_precision=double_precision,
+                                                   mode=pc_mode)
+                x0p = _par.allgather_rows(local, n_ev, xt_n[0], group)
+            norms = torch.empty(n_ev, device=dev, dtype=torch.float32)
+            corr = torch.empty(n_ev, device=dev, dtype=torch.float32) if i > 0 else None
+            new_scaled = torch.empty_like(scaled)
+            _lib.check(lib.ae_pc_subspace_step(_p(x0p), _p(x0_ref), _p(mask1), _p(prev) if i > 0 else None, n_ev, n_el,
+                                               float(const), _p(cur), _p(new_scaled), _p(norms), _p(corr), _p(work),
+                                               ws_bytes, _stream()), "ae_pc_subspace_step")
+            norm_of_Ab = norms if n_ev > 1 else norms[0]
             if i > 0:
-                corr = ((prev_ev.reshape(n_ev, -1)) @ (eigvecs.reshape(n_ev, -1).T)).diag()
                 in_corr.append(corr)
             in_norm.append(norm_of_Ab)
-            prev_ev = eigvecs.detach().clone()
             if not (i % 10) and i > 15:
-                interm_eigvecs[i] = eigvecs
-                interm_eigvals[i] = norm_of_Ab / const * (ldm_stable.get_sigma(t) ** 2)
-            eigvecs *= const
-    eigval = (norm_of_Ab / const * (ldm_stable.get_sigma(t) ** 2))
-    eigvecs /= const
+                # the reference stores the tensor it then scales IN PLACE by `const` (:188-193): the stored
+                # intermediate directions carry that factor
+                interm_eigvecs[i] = new_scaled
+                interm_eigvals[i] = norm_of_Ab / const * sigma2
+            prev, cur = cur, prev
+            scaled = new_scaled
+    eigval = norm_of_Ab / const * sigma2                                               # :195
+    eigvecs = scaled / const                                                            # :196 (`eigvecs /= const`)
     return eigvecs, eigval, in_corr, in_norm, interm_eigvecs, interm_eigvals
 
 
@@ -169,25 +184,23 @@ def apply_drift(ldm_stable, xt_m1: torch.Tensor, x0_pred: torch.Tensor, t: torch
                 use_specific_ts_pc: Optional[int] = None, amount: float = 1, sub_iters: Optional[int] = None,
                 eta: float = 1, ev_nums: List[int] = [1], evals: Optional[Dict[int, torch.Tensor]] = None
                 ) -> torch.Tensor:
-    if use_specific_ts_pc is None:
-        use_t = t.item()
-    else:
-        use_t = timesteps[num_diff_steps - use_specific_ts_pc].item()
-    eigvec = eigdata[use_t]['eigvec'].to(device)
-    if evals is None:
-        eigval = eigdata[t.item()]['eigval'].to(device)
-    else:
-        eigval = torch.from_numpy(evals[t.item()]).to(device)
+    """Shift the posterior mean along the stored principal directions and re-compose x_{t-1} (pc_drift.py:201-278)."""
+    lib = _lib.load()
+    # ---- which stored direction / eigenvalue (host look-ups, :219-231)
+    use_t = t.item() if use_specific_ts_pc is None else timesteps[num_diff_steps - use_specific_ts_pc].item()
+    if sub_iters is not None and evals is not None:
+        raise ValueError("evals should be None if sub_iters is not None")
     if sub_iters is not None:
         eigvec = eigdata[use_t]['interm_eigvecs'][sub_iters].to(device)
-        if evals is not None:
-            raise ValueError("evals should be None if sub_iters is not None")
         eigval = eigdata[t.item()]['interm_eigvals'][sub_iters].to(device)
+    else:
+        eigvec = eigdata[use_t]['eigvec'].to(device)
+        eigval = eigdata[t.item()]['eigval'].to(device) if evals is None else torch.from_numpy(evals[t.item()]).to(device)
     shift_by = 0
-    for ev_num in ev_nums:
+    for ev_num in ev_nums:                                                                  # :232-235
         ev_idx = ev_num - 1
-        shift_by += amount * (eigval[ev_idx].unsqueeze(0).sqrt() * eigvec[ev_idx].unsqueeze(0))
-    x0_pred_drift = x0_pred.clone() + shift_by
+        shift_by = shift_by + amount * (eigval[ev_idx].unsqueeze(0).sqrt() * eigvec[ev_idx].unsqueeze(0))
+    # ---- scalars of the step, evaluated on the host with the reference's expressions (:240-249)
     sched = ldm_stable.model.scheduler
     prev_timestep = t - sched.config.num_train_timesteps // sched.num_inference_steps
     variance = sched._get_variance(t, prev_timestep)
@@ -195,14 +208,24 @@ def apply_drift(ldm_stable, xt_m1: torch.Tensor, x0_pred: torch.Tensor, t: torch
     alpha_prod_t_prev = sched.alphas_cumprod[int(prev_timestep)] if prev_timestep >= 0 else sched.final_alpha_cumprod
     alpha_prod_t = sched.alphas_cumprod[int(t)]
     beta_prod_t = 1 - alpha_prod_t
+    c_dir = (1 - alpha_prod_t_prev - std_dev_t ** 2) ** (0.5)
+    ratio = (alpha_prod_t ** (0.5)) / (beta_prod_t ** (0.5))
+    xm = _f32(xt_m1, device)
+    x0p = _f32(x0_pred, device)
+    if x0p.shape != xm.shape:
+        x0p = x0p.expand_as(xm).contiguous()
+    rows = xm.shape[0]
+    n_el = xm[0].numel()
+    sh = _f32(shift_by, device).reshape(-1)
+    if sh.numel() != n_el:
+        raise ValueError(f"eigvec has {sh.numel()} elements per direction, the latent {n_el}")
+    lat = None
     if eta > 0:
-        xt_m1 = xt_m1 - std_dev_t * latent
-    pred_sample_direction = xt_m1 - alpha_prod_t_prev ** (0.5) * x0_pred
-    pred_epsilon = pred_sample_direction / ((1 - alpha_prod_t_prev - std_dev_t ** 2) ** (0.5))
-    if use_shifted_x0_for_noisepred:
-        pred_epsilon = pred_epsilon - (alpha_prod_t ** (0.5)) / (beta_prod_t ** (0.5)) * shift_by
-    pred_sample_direction = (1 - alpha_prod_t_prev - std_dev_t ** 2) ** (0.5) * pred_epsilon
-    xt_m1 = alpha_prod_t_prev ** (0.5) * x0_pred_drift + pred_sample_direction
-    if eta > 0:
-        xt_m1 = xt_m1 + std_dev_t * latent
-    return xt_m1
+        lat = _f32(latent, device)
+        if lat.shape != xm.shape:
+            lat = lat.expand_as(xm).contiguous()
+    out = torch.empty_like(xm)
+    _lib.check(lib.ae_pc_apply_drift(_p(xm), _p(x0p), _p(lat), _p(sh), float(std_dev_t), float(alpha_prod_t_prev ** (0.5)),
+                                     float(c_dir), float(ratio), int(eta > 0), int(bool(use_shifted_x0_for_noisepred)),
+                                     rows, n_el, _p(out), _stream()), "ae_pc_apply_drift")
+    return out

@@ -18,6 +18,7 @@ Weights arrive under diffusers state-dict names (what the reference's checkpoint
 from __future__ import annotations
 
 import os
+from collections import OrderedDict
 from typing import Dict, List, Optional, Sequence
 
 import torch
@@ -148,9 +149,11 @@ class UNetEngine:
         self.adt = ops.act_dtype            # bf16 on the device path
         self.w: Dict[str, torch.Tensor] = {}
         self._pack(weights)
-        self._graphs: Dict = {}
+        # CUDA-graph cache, LRU-bounded: every GraphedForward owns a private memory pool, its static buffers and a reference
+        # to its TextCache, so an unbounded cache grows with every new prompt set / clip length of a dataset run
+        self._graphs: "OrderedDict" = OrderedDict()
+        self.max_graphs = int(os.environ.get("AEDIT_MAX_GRAPHS", "12"))
         self.kernels_per_forward: Dict = {}
-        import os
         # below this width the 4-D TMA boxes degenerate into 256-byte bursts; gather patches explicitly instead
         self.min_implicit_w = int(os.environ.get("AEDIT_MIN_IMPLICIT_W", "2"))
         self.dual_stream = os.environ.get("AEDIT_DUAL_STREAM", "0") != "0"
@@ -226,7 +229,11 @@ class UNetEngine:
             slot_key = tuple(int(v) for v in slot_map.tolist())
         key = (B, H, W, id(text), slot_key, class_labels is not None, lane)
         g = self._graphs.get(key)
+        if g is not None:
+            self._graphs.move_to_end(key)
         if g is None:
+            while len(self._graphs) >= max(1, self.max_graphs):
+                self._graphs.popitem(last=False)        # least recently used: frees its pool and unpins its text
             l0 = self.ops.launch_count()
             g = GraphedForward(self, B, H, W, text, slot_map, class_labels, lane=lane)
             g.kernels = (self.ops.launch_count() - l0) // 3       # 2 warm-ups + 1 capture
@@ -234,6 +241,15 @@ class UNetEngine:
                 g = self._tune_placement(g, (B, H, W, text, slot_map, class_labels), lane)
             self._graphs[key] = g
         return g
+
+    def evict_graphs(self, live_texts=()) -> int:
+        """Drop every cached graph whose TextCache is not in `live_texts` (called by the wrappers when they evict text
+        conditioning): a graph pins its text K/V and its private pool for as long as it is cached."""
+        live = {id(t) for t in live_texts}
+        dead = [k for k, g in self._graphs.items() if g.text is not None and id(g.text) not in live]
+        for k in dead:
+            del self._graphs[k]
+        return len(dead)
 
     def solo_lane(self, B, H, W, text, slot_key, has_cl: bool) -> int:
         """Which reverse-lane graph variant to replay when the lane has the machine to itself: 1 (deep rings, PDL on the

@@ -12,8 +12,12 @@
  *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*), never synchronises, never
  *     allocates device memory (the only allocations are in *_create), and is CUDA-graph capturable
  *   - return 0 on success, negative AE_E* otherwise; ae_last_error() returns a thread-local message
- *   - activations are channels-last: images [B,H,W,C], token sequences [B,T,C]; "f32" = float, "bf16" =
- *     __nv_bfloat16.  Latents / noise maps of the scheduler kernels are plain contiguous fp32 of any layout.
+ *   - activations are channels-last: images [B,H,W,C], token sequences [B,T,C]; "f32" = float.  Latents / noise maps of
+ *     the scheduler kernels are plain contiguous fp32 of any layout.
+ *   - "bf16" in parameter names below means THE LIBRARY'S 16-BIT TENSOR-CORE OPERAND TYPE, reported by
+ *     ae_operand_dtype(): 1 = IEEE fp16 (libaedit.so, the default build: same tcgen05 rate, 8x smaller operand rounding
+ *     error, conversions saturate at +-65504) or 0 = bfloat16 (libaedit_bf16.so, built with -DAE_OPERAND_BF16).
+ *     Accumulation, residual streams, norm statistics and all scheduler state are fp32 in both builds.
  */
 #ifndef AEDIT_H_
 #define AEDIT_H_
@@ -33,6 +37,8 @@ typedef void* ae_stream; /* cudaStream_t */
 
 const char* ae_last_error(void);
 int ae_version(void);
+/* 16-bit operand type of this build: 0 bfloat16, 1 IEEE fp16 (see conventions above) */
+int ae_operand_dtype(void);
 /* number of kernels this library has launched since load (bench.py's gpu_launches) */
 int64_t ae_launch_count(void);
 /* 1 if the current device is compute capability 10.x */
@@ -166,6 +172,39 @@ int ae_cfg_rev_step(const ae_sched*, int pos, const int32_t* d_pos, float eta, c
 int ae_ddim_step(const ae_sched*, int pos, float eta, float cfg_scale, const float* eps_u, const float* eps_c,
                  const float* sample, const float* variance_noise, float* prev_sample, float* pred_x0, int64_t n_el,
                  ae_stream stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Unsupervised principal-direction editing (code/pc_drift.py), all fp32, `n` direction rows of `n_el` elements.
+ */
+/* pc_drift.py:41-42, :64-80 — the input of forward_directional written as the 2n-row CFG batch of one U-Net launch:
+ *   inp[i]         = xt[i] + (amount * eigvecs[i]) * sqrt_ab          (eigvecs == NULL: inp = xt)
+ *   x_batch[i]     = mode in {1 both, 3 uncond} ? inp[i] : xt[i]      rows evaluated with the unconditional embedding
+ *   x_batch[n + i] = mode in {1 both, 2 text}   ? inp[i] : xt[i]      rows evaluated with the text embedding
+ * xt rows are xt_row_stride elements apart (0 = one row shared by all directions); inp_out (optional) [n, n_el] is the
+ * `sample` later handed to ae_ddim_step. */
+int ae_pc_perturb(const float* xt, int64_t xt_row_stride, const float* eigvecs, float amount, float sqrt_ab, int mode,
+                  int n, float* x_batch, float* inp_out, int64_t n_el, ae_stream stream);
+
+/* pc_drift.py:148-193 — one subspace-iteration update after the U-Net evaluation of the n perturbed rows:
+ *   Ab_i = x0_pred[i]*mask - x0_ref;  norms_out[i] = ||Ab_i[mask != 0]||;  V_i = Ab_i / norm_i * mask
+ *   n > 1: Q = torch.linalg.qr(V^T).Q — computed as CholeskyQR2 (Gram pass / n x n factorisation / transform pass, twice)
+ *          with LAPACK's Householder column-sign convention, `Q *= -1 if prod(diag R) < 0` (:164-166) and the rows then
+ *          re-ordered by norms_out descending, stable (:172-174);  n == 1: eig = V_0 (:175-177)
+ *   corr_out[k] = <prev[k], eig_out[k]> (:181-182; needs prev, which must not alias eig_out)
+ *   eig_scaled_out = cnst * eig_out (:193, the next iteration's perturbation)
+ * mask [n_el] (NULL = ones) and x0_ref [n_el] are shared by the n rows.  Deterministic: per-CTA partial sums are combined
+ * in a fixed order.  workspace: ae_pc_workspace_bytes(n, n_el) bytes, no initialisation needed.  1 <= n <= 16. */
+int64_t ae_pc_workspace_bytes(int n, int64_t n_el);
+int ae_pc_subspace_step(const float* x0_pred, const float* x0_ref, const float* mask, const float* prev, int n,
+                        int64_t n_el, float cnst, float* eig_out, float* eig_scaled_out, float* norms_out,
+                        float* corr_out, void* workspace, int64_t workspace_bytes, ae_stream stream);
+
+/* pc_drift.py:232-278 — apply_drift for `rows` samples sharing the shift `shift_by` [n_el] = sum_k amount*sqrt(eigval_k)*
+ * eigvec_k; scalars are the host-evaluated std_dev_t = eta*sqrt(var), sqrt(alpha_prod_t_prev),
+ * sqrt(1 - alpha_prod_t_prev - std_dev_t^2) and sqrt(alpha_prod_t)/sqrt(1 - alpha_prod_t). */
+int ae_pc_apply_drift(const float* xt_m1, const float* x0_pred, const float* latent, const float* shift_by,
+                      float std_dev_t, float sqrt_alpha_prev, float c_dir, float sqrt_ab_over_sqrt_1mab, int eta_positive,
+                      int use_shifted_x0_for_noisepred, int rows, int64_t n_el, float* out, ae_stream stream);
 
 /* ------------------------------------------------------------------------------------------------
  * U-Net building blocks (the math of `self.model.unet.*` called from models.py:231-388 / :772-894; in-tree

@@ -9,7 +9,8 @@ import torch.nn.functional as F
 
 pytestmark = pytest.mark.gpu
 
-BF = torch.bfloat16
+from audioeditingcode_b200._lib import operand_torch_dtype
+BF = operand_torch_dtype()        # the library build's 16-bit operand type (fp16 default, bf16 with AEDIT_OPERANDS=bf16)
 
 
 @pytest.fixture(scope="module")

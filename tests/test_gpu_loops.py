@@ -13,6 +13,14 @@ from tests.helpers import load_golden, tiny_cfg_and_weights, oracle_unet_fn, mak
 pytestmark = pytest.mark.gpu
 
 
+def _bf16_build():
+    """True when the bf16-operand library variant is loaded (AEDIT_OPERANDS=bf16).  The default fp16-operand build
+    meets SURVEY.md §8d's flat tolerances; the bf16 build (8x the operand rounding error) is judged against the error of
+    stock PyTorch bf16 autocast on the same loops, stored in each fixture."""
+    from audioeditingcode_b200 import _lib
+    return _lib.load().ae_operand_dtype() == 0
+
+
 def _wrapper(n_steps, pred="epsilon", name="tiny-audioldm"):
     from audioeditingcode_b200 import models, unet_config as C
     import dataclasses
@@ -138,18 +146,21 @@ def test_loops_vs_reference_golden(name, pred, fb):
         m, g["x0"].cuda(), etas=1.0, prompts=["p%d" % i for i in range(P)], cfg_scales=[float(v) for v in g["cfg_src"]],
         num_inference_steps=N, numerical_fix=True, forward_batch=fb, noise=g["noise"].cuda())
     assert torch.count_nonzero(zs[0]) == 0
-    # Tolerances.  The corrected trajectory xts only differs by the numerical-fix rounding (<= 1e-6).  zs and the
-    # edited latent carry the bf16-operand error of the U-Net, amplified by 1/sigma_t and by the guidance scale; the
-    # yardstick is the error of STOCK PyTorch bf16 autocast on the very same loops against the fp32 reference
-    # (stored in the fixture by oracle/make_golden.py): this path must be at least as accurate (it keeps an fp32
-    # residual stream), plus the SURVEY.md §8d absolute bounds where they are tighter than that yardstick.
+    # Tolerances: corrected trajectory xts <= 1e-6 (numerical-fix rounding only); zs rel-L2 <= 1e-2 and
+    # edited latent rel-L2 <= 5e-2 vs the fp32 reference with identical noise — flat, for the default fp16-operand build.
+    # The bf16-operand build carries 8x the operand rounding error, amplified by 1/sigma_t and the guidance scale: there
+    # the bound is the error of STOCK PyTorch bf16 autocast on the very same loops (stored in the fixture).
     r_x, r_z = _rel(xts, g["xts"]), _rel(zs, g["zs"])
     m_z = (zs.cpu() - g["zs"]).abs().max().item()
     print(f"[{name} fb={fb}] rel-L2 xts {r_x:.2e} zs {r_z:.2e} (torch-bf16 {float(g['bf16_autocast_err_zs']):.2e}) "
           f"max|dz| {m_z:.3f} (max|z| {g['zs'].abs().max().item():.2f})")
     assert r_x < 1e-6
-    assert r_z < 6e-2 and r_z <= float(g["bf16_autocast_err_zs"])
-    assert m_z < 0.10 * g["zs"].abs().max().item()
+    if _bf16_build():
+        assert r_z < 6e-2 and r_z <= float(g["bf16_autocast_err_zs"])
+        assert m_z < 0.10 * g["zs"].abs().max().item()
+    else:
+        assert r_z < 1e-2
+        assert m_z < 1e-2 * g["zs"].abs().max().item()
     m.encode_text = _GoldText(g, "tgt")
     tstart = g["tstart"].to(torch.int)
     skip = N - tstart
@@ -158,7 +169,7 @@ def test_loops_vs_reference_golden(name, pred, fb):
         cfg_scales=[float(v) for v in g["cfg_tar"]], zs=zs[:int(N - min(skip))])
     r_w = _rel(w_edit, g["w_edit"])
     print(f"[{name} fb={fb}] rel-L2 edited latent {r_w:.2e} (torch-bf16 {float(g['bf16_autocast_err_edit']):.2e})")
-    assert r_w <= max(5e-2, float(g["bf16_autocast_err_edit"]))
+    assert r_w <= (max(5e-2, float(g["bf16_autocast_err_edit"])) if _bf16_build() else 5e-2)
 
 
 def test_replay_invariant_bitexact_sequential():
@@ -288,7 +299,10 @@ def test_ddim_mode_vs_reference_golden():
     r2 = _rel(wrec, g["w_rec"])
     y1, y2 = float(g["bf16_autocast_err_inv"]), float(g["bf16_autocast_err_rec"])
     print(f"ddim inversion rel-L2 {r1:.2e} (torch-bf16 {y1:.2e}); regeneration rel-L2 {r2:.2e} (torch-bf16 {y2:.2e})")
-    assert r1 <= max(5e-2, y1) and r2 <= max(5e-2, y2)
+    if _bf16_build():
+        assert r1 <= max(5e-2, y1) and r2 <= max(5e-2, y2)
+    else:
+        assert r1 <= 5e-2 and r2 <= 5e-2
 
 
 def test_full_size_properties_audioldm2_large():

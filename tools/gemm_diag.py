@@ -8,7 +8,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from audioeditingcode_b200.ops import CudaOps  # noqa: E402
 
 ops = CudaOps()
-BF = torch.bfloat16
+from audioeditingcode_b200._lib import operand_torch_dtype
+BF = operand_torch_dtype()        # the library build's 16-bit operand type (fp16 default, bf16 with AEDIT_OPERANDS=bf16)
 
 
 def run(M, N, K, bn, pattern):

@@ -96,13 +96,13 @@ def main():
 
     # ---------------- GroupNorm apply (streaming) and LayerNorm at the B=100 forward-chunk shape of AudioLDM2-large
     B, HW, Cc = 100, 4096, 192
-    a = torch.randn(B * HW, 64, device=dev).to(BF16)
-    wt = (torch.randn(Cc, 64, device=dev) * 0.1).to(BF16)
+    a = torch.randn(B * HW, 64, device=dev).to(ops.act_dtype)
+    wt = (torch.randn(Cc, 64, device=dev) * 0.1).to(ops.act_dtype)
     x = torch.empty(B * HW, Cc, device=dev)
     cs = torch.zeros(B * Cc * 2, dtype=torch.int64, device=dev)
     ops.gemm(a, wt, out_f32=x, colstats=cs, cs_rows=HW)
     gamma, beta = torch.ones(Cc, device=dev), torch.zeros(Cc, device=dev)
-    o = torch.empty(B, HW, Cc, device=dev, dtype=BF16)
+    o = torch.empty(B, HW, Cc, device=dev, dtype=ops.act_dtype)
     bench(f"gn_apply_stream (colstats) [{B},{HW},{Cc}]", lambda: ops.groupnorm(x.view(B, HW, Cc), None, gamma, beta, 1e-5, 32,
                                                                               True, o, cs1=cs),
           B * HW * Cc * 6, "reads fp32 once, writes bf16")
@@ -112,11 +112,11 @@ def main():
     M, Cl = 100 * 1024, 384
     h = torch.randn(M, Cl, device=dev)
     g2, b2 = torch.ones(Cl, device=dev), torch.zeros(Cl, device=dev)
-    o2 = torch.empty(M, Cl, device=dev, dtype=BF16)
+    o2 = torch.empty(M, Cl, device=dev, dtype=ops.act_dtype)
     bench(f"layernorm_kernel [{M},{Cl}]", lambda: ops.layernorm(h, g2, b2, o2), M * Cl * 6, "reads fp32, writes bf16")
     M2 = 2 * 1024
     h2 = torch.randn(M2, Cl, device=dev)
-    o3 = torch.empty(M2, Cl, device=dev, dtype=BF16)
+    o3 = torch.empty(M2, Cl, device=dev, dtype=ops.act_dtype)
     bench(f"layernorm_kernel [{M2},{Cl}] (B=2 reverse step)", lambda: ops.layernorm(h2, g2, b2, o3), M2 * Cl * 6,
           "4.7 MB: latency bound")
 
@@ -126,7 +126,7 @@ def main():
     bench("nchw_to_nhwc [100,8,256,16]", lambda: ops.nchw_to_nhwc(xn, out_f32=xo), xn.numel() * 8)
     Tv, Cv = 163840, 32
     xv = torch.randn(1, Tv, Cv, device=dev)
-    ov = torch.empty(1, Tv, Cv, device=dev, dtype=BF16)
+    ov = torch.empty(1, Tv, Cv, device=dev, dtype=ops.act_dtype)
     bench(f"leaky_relu_bf16 [{Tv},{Cv}] (last vocoder stage)", lambda: ops.leaky_relu_bf16(xv, 0.1, ov), Tv * Cv * 6,
           "31 MB")
     ot = torch.empty(1, Tv, device=dev)
