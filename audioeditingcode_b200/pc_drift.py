@@ -111,12 +111,14 @@ def forward_directional(ldm_stable, xt: torch.Tensor, timestep: torch.Tensor, la
 def get_eigenvectors(ldm_stable, xt: torch.Tensor, text_emb: PromptEmbeddings, uncond_emb: PromptEmbeddings,
                      latents: torch.Tensor, mask: torch.Tensor, t: torch.Tensor, x0_pred: torch.Tensor,
                      pc_mode: PCStreamChoice = PCStreamChoice.BOTH, const: float = 1e-3, cfg_tar: float = 3,
-                     iters: int = 50, double_precision: bool = False, eta: float = 1, n_ev: int = 1, group=None
+                     iters: int = 50, double_precision: bool = False, eta: float = 1, n_ev: int = 1, group=None,
+                     init_eigvecs: Optional[torch.Tensor] = None
                      ) -> Tuple[torch.Tensor, torch.Tensor, List[torch.Tensor], List[torch.Tensor],
                                 Dict[int, torch.Tensor], Dict[int, torch.Tensor]]:
     """Subspace (power) iteration on the Jacobian of the posterior mean (pc_drift.py:96-198).
     `group` (extension; None = the reference's single-process behaviour): process group over which the n_ev directions
-    are sharded, see the module docstring."""
+    are sharded, see the module docstring.  `init_eigvecs` (extension): explicit start `[n_ev, C, H, W]` used instead of
+    the `randn_like(xt) * mask * const` draw of :130 (seed-independent comparisons against the reference)."""
     from . import parallel as _par
     lib = _lib.load()
     dev = ldm_stable.device
@@ -130,7 +132,10 @@ def get_eigenvectors(ldm_stable, xt: torch.Tensor, text_emb: PromptEmbeddings, u
     mask1 = mask_d[0].expand(xt1.shape[1:]).contiguous()
     xt_n = xt1.expand(shape) if xt1.shape[0] == 1 else xt1
     # random start: randn_like of the n_ev-row tensor like the reference (:130), one draw for all ranks
-    scaled = torch.randn(shape, device=dev, dtype=torch.float32) * mask_d * const
+    if init_eigvecs is not None:
+        scaled = _f32(init_eigvecs, dev).reshape(shape).clone()
+    else:
+        scaled = torch.randn(shape, device=dev, dtype=torch.float32) * mask_d * const
     if ws > 1:
         _par.broadcast_(scaled, 0, group)
     prev = scaled.clone()

@@ -322,8 +322,161 @@ def golden_ddim():
          tgt=prompt_vector("a cat"), bf16_autocast_err_inv=rel(wT_b, wT), bf16_autocast_err_rec=rel(wrec_b, wrec))
 
 
+# ------------------------------------------------------------------------------------------------------------------
+# pc_drift (code/pc_drift.py, unmodified) on a LINEAR denoiser with a known Jacobian spectrum
+# ------------------------------------------------------------------------------------------------------------------
+def linear_denoiser_factors(D, seed, lam_u=(0.9, 0.65, 0.45, 0.3, 0.2, 0.1), tilt=0.05):
+    """Low-rank symmetric maps S_u = U diag(lam_u) U^T (unconditional) and S_c = U diag(lam_c) U^T (conditional):
+    the posterior mean of the fake model is x0_hat = S x / sqrt(alpha_bar_t), i.e. eps = (x - S x) / sqrt(1 - alpha_bar_t)."""
+    g = torch.Generator().manual_seed(seed)
+    r = len(lam_u)
+    U_, _ = torch.linalg.qr(torch.randn(D, r, generator=g, dtype=torch.float64))
+    lam_u = torch.tensor(lam_u, dtype=torch.float64)
+    lam_c = lam_u * (1 + tilt * torch.linspace(-1, 1, r, dtype=torch.float64))
+    return U_.float(), lam_u.float(), lam_c.float()
+
+
+class LinearLDM:
+    """Duck-typed PipelineWrapper for the reference's pc_drift functions: linear denoiser + MiniDDIM scheduler."""
+
+    def __init__(self, shape, n_steps, factors):
+        self.device = torch.device("cpu")
+        self.shape = shape
+        self.U, self.lam_u, self.lam_c = factors
+        sch = MiniDDIM(0.0015, 0.0195)
+        sch.set_timesteps(n_steps)
+        self.model = types.SimpleNamespace(scheduler=sch)
+
+    def get_sigma(self, timestep):                      # models.py:25-27
+        return torch.sqrt(1.0 / self.model.scheduler.alphas_cumprod - 1)[timestep]
+
+    def eps(self, x, t, cond: bool):
+        ab = self.model.scheduler.alphas_cumprod[int(t)]
+        xf = x.reshape(x.shape[0], -1)
+        lam = self.lam_c if cond else self.lam_u
+        sx = ((xf @ self.U) * lam) @ self.U.T
+        return ((xf - sx) / (1 - ab) ** 0.5).reshape(x.shape)
+
+    def unet_forward(self, sample, timestep, encoder_hidden_states=None, class_labels=None, encoder_attention_mask=None,
+                     **kw):
+        cond = bool(class_labels is not None and float(class_labels.flatten()[0]) > 0.5)
+        return types.SimpleNamespace(sample=self.eps(sample, timestep, cond)), None, None
+
+
+def golden_pc_drift():
+    ref = ref_import.load()
+    PC = ref.pc_drift
+    C_, H_, W_ = 8, 4, 16
+    D = C_ * H_ * W_
+    N = 20
+    cases = [dict(name="a", n_ev=3, iters=12, seed=0, patch=None, mode="BOTH"),
+             dict(name="b", n_ev=4, iters=12, seed=1, patch=(1, 3), mode="TEXT"),
+             dict(name="c", n_ev=1, iters=8, seed=2, patch=None, mode="BOTH"),
+             dict(name="d", n_ev=8, iters=21, seed=3, patch=None, mode="BOTH",
+                  lam=(0.9, 0.8, 0.7, 0.6, 0.5, 0.4, 0.32, 0.25, 0.18, 0.1))]     # rank >= n_ev: no null directions
+    out = {}
+    for cs in cases:
+        fac = linear_denoiser_factors(D, 100 + cs["seed"], **({"lam_u": cs["lam"]} if "lam" in cs else {}))
+        ldm = LinearLDM((C_, H_, W_), N, fac)
+        g = torch.Generator().manual_seed(cs["seed"])
+        xt = torch.randn(1, C_, H_, W_, generator=g)
+        lat = torch.randn(1, C_, H_, W_, generator=g)
+        mask = torch.zeros(1, C_, H_, W_)
+        if cs["patch"] is None:
+            mask[:] = 1
+        else:
+            mask[:, :, cs["patch"][0]:cs["patch"][1], :] = 1
+        t = ldm.model.scheduler.timesteps[7]
+        unc = PC.PromptEmbeddings(None, torch.zeros(1, 4), None)          # class_labels row: 0 = uncond, 1 = cond
+        txt = PC.PromptEmbeddings(None, torch.ones(1, 4), None)
+        mode = getattr(PC.PCStreamChoice, cs["mode"])
+        _, x0_pred = PC.forward_directional(ldm, xt, t, lat, unc, txt, 3.0, eta=1)
+        rec = []
+        orig = PC.forward_directional
+
+        def spy(*a, **k):
+            r = orig(*a, **k)
+            rec.append((k["eigvecs"].clone(), r[1].clone()))
+            return r
+        PC.forward_directional = spy
+        try:
+            torch.manual_seed(1000 + cs["seed"])
+            eigvecs, eigval, in_corr, in_norm, interm_vec, interm_val = PC.get_eigenvectors(
+                ldm, xt, txt, unc, lat, mask, t, x0_pred, mode, 1e-3, 3.0, cs["iters"], False, 1, cs["n_ev"])
+        finally:
+            PC.forward_directional = orig
+        n = cs["n_ev"]
+        k = cs["name"]
+        scaled_in = torch.stack([r[0].reshape(n, D) for r in rec])            # perturbation fed to iteration i
+        x0p = torch.stack([r[1].reshape(n, D) for r in rec])                  # x0_pred of the perturbed rows
+        out.update({f"{k}_n_ev": n, f"{k}_iters": cs["iters"], f"{k}_mode": mode.value, f"{k}_t": int(t),
+                    f"{k}_xt": xt, f"{k}_lat": lat, f"{k}_mask": mask, f"{k}_x0_pred": x0_pred,
+                    f"{k}_U": fac[0], f"{k}_lam_u": fac[1], f"{k}_lam_c": fac[2],
+                    f"{k}_scaled_in": scaled_in, f"{k}_x0p": x0p, f"{k}_eigvecs": eigvecs.reshape(n, D),
+                    f"{k}_eigval": eigval.reshape(-1), f"{k}_in_norm": torch.stack([v.reshape(-1) for v in in_norm]),
+                    f"{k}_in_corr": torch.stack([v.reshape(-1) for v in in_corr]),
+                    f"{k}_interm_keys": np.asarray(sorted(interm_vec), np.int64)})
+        for i in interm_vec:
+            out[f"{k}_interm_vec_{i}"] = interm_vec[i].reshape(n, D)
+            out[f"{k}_interm_val_{i}"] = interm_val[i].reshape(-1)
+        if k == "a":
+            # forward_directional with a shifted input, all three stream choices (pc_drift.py:41-93)
+            ev = torch.nn.functional.normalize(torch.randn(2, C_, H_, W_, generator=g).reshape(2, -1), dim=1
+                                               ).reshape(2, C_, H_, W_)
+            xt2 = torch.randn(2, C_, H_, W_, generator=g)
+            lat2 = torch.randn(2, C_, H_, W_, generator=g)
+            for md in ("BOTH", "TEXT", "UNCOND"):
+                pr, x0 = PC.forward_directional(ldm, xt2, t, lat2, unc, txt, 3.0, eta=1, eigvecs=ev, amount=0.7,
+                                                mode=getattr(PC.PCStreamChoice, md))
+                out[f"fd_prev_{md}"], out[f"fd_x0_{md}"] = pr, x0
+            out["fd_xt"], out["fd_lat"], out["fd_ev"] = xt2, lat2, ev
+            # apply_drift (pc_drift.py:201-278) on the extracted directions
+            eigdata = {int(t): dict(eigvec=eigvecs, eigval=eigval, interm_eigvecs=interm_vec, interm_eigvals=interm_val)}
+            xm1, x0p1 = PC.forward_directional(ldm, xt, t, lat, unc, txt, 3.0, eta=1)
+            for eta in (1, 0):
+                for shifted in (True, False):
+                    o = PC.apply_drift(ldm, xm1, x0p1, t, ldm.model.scheduler.timesteps, N, eigdata, lat,
+                                       torch.device("cpu"), use_shifted_x0_for_noisepred=shifted, amount=1.5, eta=eta,
+                                       ev_nums=[1, 3])
+                    out[f"ad_eta{eta}_sh{int(shifted)}"] = o
+            out["ad_xm1"], out["ad_x0p"] = xm1, x0p1
+    save("pc_drift.npz", n_steps=N, shape=np.asarray([C_, H_, W_]), **out)
+
+
+def golden_sdedit():
+    """SDEdit flow of code/main_run_sdedit.py:78-100 (pre-drawn latents, add_noise at timesteps[skip], forward_directional
+    loop), reference pc_drift.forward_directional unmodified on the fake AudioLDM wrapper (vendored UNetModel); the
+    diffusers scheduler's add_noise / step / init_noise_sigma come from the MiniDDIM restatement."""
+    ref = ref_import.load()
+    PC = ref.pc_drift
+    cfg = C.preset("tiny-audioldm")
+    w = U.synthetic_weights(cfg, seed=0)
+    N, tstart = 10, 6
+    model = make_fake_wrapper(ref, cfg, w, N)
+    g = torch.Generator().manual_seed(71)
+    w0 = 0.5 * torch.randn(1, 8, 16, 16, generator=g)
+    timesteps = model.model.scheduler.timesteps
+    latents = [torch.randn(1, 8, 16, 16, generator=g) * model.model.scheduler.init_noise_sigma
+               for _ in range(len(timesteps) + 1)]                                                   # :79-87
+    skip = N - tstart                                                                                # :89
+    noise = torch.randn(w0.shape, generator=g)
+    xt = model.model.scheduler.add_noise(w0, noise, timesteps[skip].unsqueeze(0))                    # :92-93
+    unc = PC.PromptEmbeddings(None, prompt_vector(""), None)
+    txt = PC.PromptEmbeddings(None, prompt_vector("a cat"), None)
+    x_start = xt.clone()
+    with torch.no_grad():
+        for it, t in enumerate(timesteps[skip:]):                                                    # :97-100
+            xt, _ = PC.forward_directional(model, xt, t, latents[skip + it + 1], unc, txt, 5.0, eta=1)
+    save("sdedit.npz", n_steps=N, tstart=tstart, w0=w0, noise=noise, latents=torch.cat(latents), x_start=x_start,
+         w_edit=xt, uncond=prompt_vector(""), tgt=prompt_vector("a cat"), cfg_tar=5.0)
+
+
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "all"
+    if what in ("all", "pc"):
+        golden_pc_drift()
+    if what in ("all", "sdedit"):
+        golden_sdedit()
     if what in ("all", "ddim"):
         golden_ddim()
     if what in ("all", "loops"):

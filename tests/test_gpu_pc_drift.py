@@ -1,0 +1,222 @@
+"""GPU parity of the pc_drift device path (csrc/pc_kernels.cu + audioeditingcode_b200/pc_drift.py) against golden
+tensors produced by the UNMODIFIED reference code/pc_drift.py (oracle/make_golden.py golden_pc_drift) on a LINEAR
+denoiser with a known Jacobian spectrum:
+
+  * open loop, iterate by iterate: ae_pc_subspace_step fed the reference's own posterior means of every iteration must
+    return the reference's directions (including LAPACK's Householder column signs, the `swap` rule on prod(diag R) and
+    the sort-before-permute ordering), norms and correlations;
+  * closed loop: get_eigenvectors started from the reference's start vector converges to the same subspace / spectrum
+    (the finite difference at const = 1e-3 carries ~3 % fp32 rounding noise per iterate in the reference itself — its
+    own consecutive-iterate correlation saturates at 0.9995 — so vectors are compared by cosine, not elementwise);
+  * forward_directional (all three stream choices) and apply_drift (eta 0 / 1, shifted / unshifted noise prediction);
+  * the eigdata `.pt` schema written by main_pc_extract_inv.py:234-256 round-trips through apply_drift."""
+import types
+
+import pytest
+import torch
+
+from tests.helpers import load_golden
+
+pytestmark = pytest.mark.gpu
+
+CONST = 1e-3
+
+
+class LinearModelCUDA:
+    """The fake model of the golden run on the GPU: eps = (x - S x) / sqrt(1 - alpha_bar_t) with S = U diag(lam) U^T
+    (lam_u unconditional, lam_c conditional), evaluated by torch in fp32 — test scaffolding; everything else the
+    pc_drift functions launch is libaedit."""
+
+    def __init__(self, g, key):
+        from audioeditingcode_b200.scheduler import DDIMScheduler
+        self.device = torch.device("cuda")
+        self.U, self.lam_u, self.lam_c = g[f"{key}_U"].cuda(), g[f"{key}_lam_u"].cuda(), g[f"{key}_lam_c"].cuda()
+        sch = DDIMScheduler(0.0015, 0.0195)
+        sch.set_timesteps(int(g["n_steps"]), device=self.device)
+        self.model = types.SimpleNamespace(scheduler=sch)
+
+    def get_sigma(self, timestep):
+        return torch.sqrt(1.0 / self.model.scheduler.alphas_cumprod - 1)[int(timestep)]
+
+    def _eps(self, x, t, lam):
+        ab = self.model.scheduler.alphas_cumprod[int(t)]
+        xf = x.reshape(x.shape[0], -1)
+        sx = ((xf @ self.U) * lam) @ self.U.T
+        return ((xf - sx) / float((1 - ab) ** 0.5)).reshape(x.shape)
+
+    def cfg_pair_eval_batch(self, x, timestep, uncond, cond):
+        n = x.shape[0] // 2
+        return torch.cat([self._eps(x[:n], timestep, self.lam_u), self._eps(x[n:], timestep, self.lam_c)], 0)
+
+
+def _emb():
+    from audioeditingcode_b200.pc_drift import PromptEmbeddings
+    return PromptEmbeddings(None, torch.zeros(1, 4).cuda(), None), PromptEmbeddings(None, torch.ones(1, 4).cuda(), None)
+
+
+@pytest.mark.parametrize("key", ["a", "b", "c", "d"])
+def test_subspace_step_open_loop_vs_reference(key):
+    import ctypes as C
+    from audioeditingcode_b200 import _lib
+    lib = _lib.load()
+    g = load_golden("pc_drift.npz")
+    n, iters = int(g[f"{key}_n_ev"]), int(g[f"{key}_iters"])
+    x0_ref = g[f"{key}_x0_pred"].reshape(-1).cuda()
+    mask = g[f"{key}_mask"].reshape(-1).cuda()
+    D = x0_ref.numel()
+    x0p, scaled_in = g[f"{key}_x0p"].cuda(), g[f"{key}_scaled_in"].cuda()
+    ws_bytes = int(lib.ae_pc_workspace_bytes(n, D))
+    work = torch.empty(ws_bytes, dtype=torch.uint8, device="cuda")
+    p = lambda t: None if t is None else C.c_void_p(t.data_ptr())
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    prev = None
+    for i in range(iters):
+        eig, scaled = torch.empty(n, D, device="cuda"), torch.empty(n, D, device="cuda")
+        norms, corr = torch.empty(n, device="cuda"), torch.empty(n, device="cuda")
+        _lib.check(lib.ae_pc_subspace_step(p(x0p[i].contiguous()), p(x0_ref), p(mask), p(prev), n, D, CONST, p(eig), p(scaled),
+                                           p(norms), p(corr) if prev is not None else None, p(work), ws_bytes, st))
+        # the reference's unit directions of iteration i: what it feeds (scaled by const) to iteration i+1, or returns
+        ref_scaled = scaled_in[i + 1] if i + 1 < iters else g[f"{key}_eigvecs"].cuda() * CONST
+        ref_unit = ref_scaled / CONST
+        assert torch.allclose(norms.cpu(), g[f"{key}_in_norm"][i], rtol=2e-5, atol=0), f"iter {i} norms"
+        err = (eig - ref_unit).abs().max().item()
+        assert err < 5e-5, f"iter {i}: max |eig - ref| = {err} (unit vectors, |v_i| ~ {1 / D ** 0.5:.3f})"
+        assert torch.allclose(scaled, ref_scaled, rtol=0, atol=5e-8), f"iter {i} scaled"
+        if prev is not None:
+            assert torch.allclose(corr.cpu(), g[f"{key}_in_corr"][i - 1], atol=2e-4), f"iter {i} corr"
+        # orthonormality (CholeskyQR2): |Q Q^T - I| at rounding level
+        if n > 1:
+            gram = eig @ eig.T
+            assert (gram - torch.eye(n, device="cuda")).abs().max().item() < 2e-6
+        prev = ref_unit.contiguous()        # open loop: the reference's own previous iterate
+
+
+@pytest.mark.parametrize("key", ["a", "c", "d"])
+def test_get_eigenvectors_closed_loop_vs_reference(key):
+    from audioeditingcode_b200 import pc_drift as PC
+    g = load_golden("pc_drift.npz")
+    n, iters = int(g[f"{key}_n_ev"]), int(g[f"{key}_iters"])
+    shp = tuple(int(v) for v in g["shape"])
+    m = LinearModelCUDA(g, key)
+    unc, txt = _emb()
+    t = torch.tensor(int(g[f"{key}_t"]))
+    start = g[f"{key}_scaled_in"][0].reshape(n, *shp)
+    ev, eigval, in_corr, in_norm, ivec, ival = PC.get_eigenvectors(
+        m, g[f"{key}_xt"].cuda(), txt, unc, g[f"{key}_lat"].cuda(), g[f"{key}_mask"].cuda(), t, g[f"{key}_x0_pred"].cuda(),
+        PC.PCStreamChoice(int(g[f"{key}_mode"])), CONST, 3.0, iters, False, 1, n, init_eigvecs=start)
+    assert ev.shape == (n, *shp) and len(in_corr) == iters - 1 and len(in_norm) == iters
+    assert eigval.shape == (g[f"{key}_eigval"].shape if n > 1 else torch.Size([]))
+    ref_ev = g[f"{key}_eigvecs"].cuda()
+    cos = (ev.reshape(n, -1) * ref_ev).sum(1)
+    print(f"[{key}] cos(ours, reference) per direction: {[round(float(c), 4) for c in cos]}")
+    # the leading directions are converged after `iters` iterations; trailing ones of case d are still rotating
+    lead = n if n <= 3 else 3
+    assert (cos[:lead] > 0.995).all(), cos                                   # same direction AND same sign
+    assert torch.allclose(eigval.reshape(-1).cpu()[:lead], g[f"{key}_eigval"][:lead], rtol=1e-2)
+    # same subspace overall
+    P_o = ev.reshape(n, -1).T @ ev.reshape(n, -1)
+    P_r = ref_ev.T @ ref_ev
+    assert ((P_o - P_r).norm() / P_r.norm()).item() < (0.05 if n <= 3 else 0.25)
+    assert sorted(ivec) == [int(v) for v in g[f"{key}_interm_keys"]]
+    for i in ivec:   # stored intermediate directions carry the factor `const` like the reference's (in-place scaling quirk)
+        assert abs(float(ivec[i].reshape(n, -1).norm(dim=1)[0]) - CONST) < 1e-6
+
+
+@pytest.mark.parametrize("mode", ["BOTH", "TEXT", "UNCOND"])
+def test_forward_directional_vs_reference(mode):
+    from audioeditingcode_b200 import pc_drift as PC
+    g = load_golden("pc_drift.npz")
+    m = LinearModelCUDA(g, "a")
+    unc, txt = _emb()
+    t = torch.tensor(int(g["a_t"]))
+    prev, x0 = PC.forward_directional(m, g["fd_xt"].cuda(), t, g["fd_lat"].cuda(), unc, txt, 3.0, eta=1,
+                                      eigvecs=g["fd_ev"].cuda(), amount=0.7, mode=getattr(PC.PCStreamChoice, mode))
+    assert torch.allclose(prev.cpu(), g[f"fd_prev_{mode}"], atol=2e-5, rtol=1e-5)
+    assert torch.allclose(x0.cpu(), g[f"fd_x0_{mode}"], atol=2e-5, rtol=1e-5)
+
+
+def _eigdata_from_golden(g, key="a"):
+    n = int(g[f"{key}_n_ev"])
+    shp = tuple(int(v) for v in g["shape"])
+    return {int(g[f"{key}_t"]): dict(eigvec=g[f"{key}_eigvecs"].reshape(n, *shp), eigval=g[f"{key}_eigval"],
+                                     interm_eigvecs={}, interm_eigvals={})}
+
+
+@pytest.mark.parametrize("eta,shifted", [(1, True), (1, False), (0, True), (0, False)])
+def test_apply_drift_vs_reference(eta, shifted):
+    from audioeditingcode_b200 import pc_drift as PC
+    g = load_golden("pc_drift.npz")
+    m = LinearModelCUDA(g, "a")
+    t = torch.tensor(int(g["a_t"]))
+    out = PC.apply_drift(m, g["ad_xm1"].cuda(), g["ad_x0p"].cuda(), t, m.model.scheduler.timesteps, int(g["n_steps"]),
+                         _eigdata_from_golden(g), g["a_lat"].cuda(), m.device, use_shifted_x0_for_noisepred=shifted,
+                         amount=1.5, eta=eta, ev_nums=[1, 3])
+    ref = g[f"ad_eta{eta}_sh{int(shifted)}"]
+    assert torch.allclose(out.cpu(), ref, atol=1e-6, rtol=1e-6), (out.cpu() - ref).abs().max()
+
+
+def test_eigdata_pt_roundtrip(tmp_path):
+    """The extraction checkpoint of main_pc_extract_inv.py:234-256 (torch pickle: eigdata[t] = {eigvec, eigval,
+    interm_eigvecs, interm_eigvals, it, ts, norm_factor} + run lists) written from OUR get_eigenvectors outputs, loaded
+    back and consumed by apply_drift as main_pc_apply_drift.py:71-88,156-184 does (incl. sub_iters / use_specific_ts_pc)."""
+    from audioeditingcode_b200 import pc_drift as PC
+    g = load_golden("pc_drift.npz")
+    key = "d"
+    n, iters = int(g[f"{key}_n_ev"]), int(g[f"{key}_iters"])
+    shp = tuple(int(v) for v in g["shape"])
+    m = LinearModelCUDA(g, key)
+    unc, txt = _emb()
+    N = int(g["n_steps"])
+    t = torch.tensor(int(g[f"{key}_t"]))
+    it = [int(v) for v in m.model.scheduler.timesteps_cpu].index(int(t))
+    ev, eigval, in_corr, in_norm, ivec, ival = PC.get_eigenvectors(
+        m, g[f"{key}_xt"].cuda(), txt, unc, g[f"{key}_lat"].cuda(), g[f"{key}_mask"].cuda(), t, g[f"{key}_x0_pred"].cuda(),
+        PC.PCStreamChoice.BOTH, CONST, 3.0, iters, False, 1, n)
+    eigdata = {t.item(): {'eigvec': ev.detach().cpu(), 'eigval': eigval.detach().cpu(),
+                          'interm_eigvecs': {k: v.detach().cpu() for k, v in ivec.items()},
+                          'interm_eigvals': {k: v.detach().cpu() for k, v in ival.items()},
+                          'it': it, 'ts': N - it,
+                          'norm_factor': torch.sqrt(m.model.scheduler.alphas_cumprod[t])}}
+    path = tmp_path / "extraction.pt"
+    torch.save({'eigdata': eigdata, 'args': types.SimpleNamespace(n_evs=n, iters=iters), 'corrs': [],
+                'in_corrs': [in_corr], 'latents': [g[f"{key}_lat"]], 'in_norms': [in_norm], 'xts': []}, path)
+    back = torch.load(path, weights_only=False)
+    e = back['eigdata'][t.item()]
+    assert set(e) == {'eigvec', 'eigval', 'interm_eigvecs', 'interm_eigvals', 'it', 'ts', 'norm_factor'}
+    assert e['eigvec'].shape == (n, *shp) and e['eigval'].shape == (n,) and sorted(e['interm_eigvecs']) == [20]
+    xm1, x0p = PC.forward_directional(m, g[f"{key}_xt"].cuda(), t, g[f"{key}_lat"].cuda(), unc, txt, 3.0, eta=1)
+    kw = dict(latent=g[f"{key}_lat"].cuda(), device=m.device, amount=2.0, eta=1)
+    o1 = PC.apply_drift(m, xm1, x0p, t, m.model.scheduler.timesteps, N, back['eigdata'], ev_nums=[1, 2], **kw)
+    o2 = PC.apply_drift(m, xm1, x0p, t, m.model.scheduler.timesteps, N, back['eigdata'], ev_nums=[1], sub_iters=20, **kw)
+    o3 = PC.apply_drift(m, xm1, x0p, t, m.model.scheduler.timesteps, N, back['eigdata'], ev_nums=[1],
+                        use_specific_ts_pc=N - it, **kw)
+    assert o1.shape == xm1.shape and torch.isfinite(o1).all() and not torch.equal(o1, xm1)
+    assert torch.isfinite(o2).all() and torch.isfinite(o3).all()
+    with pytest.raises(ValueError):
+        PC.apply_drift(m, xm1, x0p, t, m.model.scheduler.timesteps, N, back['eigdata'], ev_nums=[1], sub_iters=20,
+                       evals={t.item(): eigval.cpu().numpy()}, **kw)
+
+
+def test_sdedit_flow_vs_reference_golden():
+    """SDEdit (main_run_sdedit.py:78-100): pre-drawn latents, scheduler.add_noise at timesteps[skip], then the
+    forward_directional loop — through the drop-in functions on the CUDA U-Net vs the unmodified reference's result.
+    Tolerance: SURVEY.md §8d end-to-end bound, rel-L2 <= 5e-2."""
+    from oracle import unet_torch as U
+    from audioeditingcode_b200 import models, pc_drift as PC, unet_config as UC
+    g = load_golden("sdedit.npz")
+    N, tstart = int(g["n_steps"]), int(g["tstart"])
+    cfg = UC.preset("tiny-audioldm")
+    m = models.load_model("synthetic/audioldm-tiny", torch.device("cuda"), N, weights=U.synthetic_weights(cfg, seed=0),
+                          config=cfg)
+    timesteps = m.model.scheduler.timesteps
+    skip = N - tstart
+    latents = g["latents"].cuda()
+    xt = m.model.scheduler.add_noise(g["w0"].cuda(), g["noise"].cuda(), timesteps[skip:][:1].unsqueeze(0))
+    assert torch.allclose(xt.cpu(), g["x_start"], atol=1e-6)
+    unc = PC.PromptEmbeddings(None, g["uncond"].cuda(), None)
+    txt = PC.PromptEmbeddings(None, g["tgt"].cuda(), None)
+    for it, t in enumerate(timesteps[skip:]):
+        xt, _ = PC.forward_directional(m, xt, t, latents[skip + it + 1][None], unc, txt, float(g["cfg_tar"]), eta=1)
+    r = ((xt.cpu() - g["w_edit"]).norm() / g["w_edit"].norm()).item()
+    print(f"sdedit {tstart} steps cfg {float(g['cfg_tar'])}: rel-L2 vs reference {r:.2e}")
+    assert r < 5e-2
