@@ -100,6 +100,7 @@ _SIGS = {
     "ae_stft_mel": (i32, [vp, i32, i32, i32, vp, vp, i32, i32, vp, vp, vp]),
     "ae_leaky_relu_bf16": (i32, [vp, i64, f32, f32, vp, vp]),
     "ae_tanh_f32": (i32, [vp, i64, vp, vp]),
+    "ae_wave_to_int16": (i32, [vp, i64, vp, vp]),
 }
 
 EXPORTS = tuple(_SIGS)

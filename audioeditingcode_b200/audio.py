@@ -182,3 +182,25 @@ def wav_to_fbank(filename: str, target_length: int = 1024, fn_STFT: Optional[Tac
     log_magnitudes_stft = log_magnitudes_stft.T
     fbank, log_magnitudes_stft = _pad_spec(fbank, target_length), _pad_spec(log_magnitudes_stft, target_length)
     return fbank, log_magnitudes_stft, waveform
+
+
+def save_wav(path: str, wav, sample_rate: int = 16000) -> None:
+    """16-bit PCM RIFF writer on the stdlib (what main_run.py:223-224 asks of torchaudio.save, which needs an I/O
+    backend this image may lack).  wav: float tensor in [-1, 1] ([T] or [1, T]; converted on the device when it lives
+    there, ae_wave_to_int16) or an int16 numpy array as TangoWrapper.decode_to_mel returns."""
+    if torch.is_tensor(wav):
+        w = wav.detach().reshape(-1).float().contiguous()
+        if w.is_cuda:
+            pcm = torch.empty(w.shape, dtype=torch.int16, device=w.device)
+            lib = _lib.load()
+            _lib.check(lib.ae_wave_to_int16(_ptr(w), w.numel(), _ptr(pcm), _stream()), "ae_wave_to_int16")
+            data = pcm.cpu().numpy()
+        else:
+            data = np.clip(w.numpy() * 32768.0, -32768.0, 32767.0).astype(np.int16)
+    else:
+        data = np.asarray(wav).reshape(-1).astype(np.int16)
+    with contextlib.closing(wave.open(path, "w")) as f:
+        f.setnchannels(1)
+        f.setsampwidth(2)
+        f.setframerate(int(sample_rate))
+        f.writeframes(data.astype("<i2").tobytes())

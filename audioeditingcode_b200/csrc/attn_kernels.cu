@@ -342,7 +342,7 @@ int launch_attn(const AttnArgs& a, int B, int heads, cudaStream_t st) {
 
 using namespace aedit;
 
-static int g_attn_split = 1;   // 0 auto, 1 never (default: measured slower), n > 1: that many key splits
+static thread_local int g_attn_split = 1;   // 0 auto, 1 never (default: measured slower), n > 1: that many key splits
 extern "C" void ae_set_attention_split(int n) { g_attn_split = n; }
 
 extern "C" int64_t ae_attention_workspace_bytes(int B, int heads, int Tq, int d) {

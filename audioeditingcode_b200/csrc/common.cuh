@@ -76,17 +76,17 @@ inline cudaStream_t as_stream(ae_stream s) { return reinterpret_cast<cudaStream_
 // work is issued (loads done / last MMA issued), which lets the NEXT kernel of the stream be scheduled so that its
 // launch latency and prologue overlap this kernel's tail.  Triggering at the very top instead lets a whole chain of
 // kernels become resident and wait on each other, which measured slower (profiles/r01_bench_v8_pdl1.json).
-extern int g_use_pdl;
+extern thread_local int g_use_pdl;
 // Launch priority attached to every kernel launched (and therefore to every kernel NODE captured) while it is set:
 // the reverse-process graph is captured with the device's highest priority so that its sub-wave kernels take the next
 // free SM slots ahead of the pending CTAs of a forward-process chunk running concurrently on another stream.
-extern int g_launch_priority;       // 0 = leave the stream's priority
+extern thread_local int g_launch_priority;       // 0 = leave the stream's priority
 // Diagnostic only (ae_set_skip_mask, tools/kernel_share.py): kernel families whose launches are dropped, to measure
 // each family's marginal cost inside a captured graph.  Results are garbage while it is non-zero.
 // In PDL mode 2 (GEMMs only) the kernel families of this mask are launched with the PDL attribute as well:
 // 1 GroupNorm statistics, 2 GroupNorm apply, 4 LayerNorm, 8 attention (ae_set_pdl_extra; A/B in profiles/).
-extern int g_pdl_extra;
-extern int g_skip_mask;             // 1 gemm, 2 split-K reduce, 4 GN stats, 8 GN apply, 16 LayerNorm, 32 attention
+extern thread_local int g_pdl_extra;
+extern thread_local int g_skip_mask;             // 1 gemm, 2 split-K reduce, 4 GN stats, 8 GN apply, 16 LayerNorm, 32 attention
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 

@@ -27,10 +27,12 @@
 #include "ptx.cuh"
 
 namespace aedit {
-int g_use_pdl = 0;
-int g_launch_priority = 0;
-int g_skip_mask = 0;
-int g_pdl_extra = 0;
+// Launch settings are PER HOST THREAD (include/aedit.h, "Settings"): the host toggles them around CUDA-graph captures,
+// and two threads driving different streams must not see each other's toggles.
+thread_local int g_use_pdl = 2;
+thread_local int g_launch_priority = 0;
+thread_local int g_skip_mask = 0;
+thread_local int g_pdl_extra = 0;
 namespace {
 
 constexpr int BM = 128;
@@ -1221,7 +1223,7 @@ int launch_persistent(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gemm
 }
 
 constexpr int kHeadroomSmem = 116 * 1024;
-int g_headroom = 0;
+thread_local int g_headroom = 0;
 
 template <int BN, int STAGES, int MC = 1>
 int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmDev& p, int gz, cudaStream_t st) {
@@ -1310,22 +1312,22 @@ extern "C" int ae_greatest_priority(void) {
   return greatest;   // numerically lowest value = highest priority (0 if the device has a single level)
 }
 
-static int g_splitk_ctas = 148;
-static int g_fast_epi = 1;
-static long long g_persist_min_tiles = 296;   // two waves of 148 SMs; 0 = never (see ae_set_persistent_min_tiles)
+static thread_local int g_splitk_ctas = 148;
+static thread_local int g_fast_epi = 1;
+static thread_local long long g_persist_min_tiles = 296;   // two waves of 148 SMs; 0 = never (see ae_set_persistent_min_tiles)
 extern "C" void ae_set_persistent_min_tiles(int tiles) { g_persist_min_tiles = tiles; }
-static double g_reduce_us = 2.5, g_reduce_bw = 3.0e6;   // tile model: cost of the split-K reduce launch / its bytes per us
+static thread_local double g_reduce_us = 2.5, g_reduce_bw = 3.0e6;   // tile model: cost of the split-K reduce launch / its bytes per us
 extern "C" void ae_set_tile_model_reduce(int launch_ns, int bytes_per_us) {
   g_reduce_us = launch_ns * 1e-3;
   g_reduce_bw = bytes_per_us;
 }
-static int g_multicast = 0;   // measured slower at batch 2 (+5..+21 % per shape, profiles/r01_gemm_table_v33_B2_multicast.log): opt-in
+static thread_local int g_multicast = 0;   // measured slower at batch 2 (+5..+21 % per shape, profiles/r01_gemm_table_v33_B2_multicast.log): opt-in
 extern "C" void ae_set_multicast(int on) { g_multicast = on ? 1 : 0; }
-static int g_shallow_kb = 0;
+static thread_local int g_shallow_kb = 0;
 extern "C" void ae_set_shallow_kblocks(int kb) { g_shallow_kb = kb; }
-static int g_shared_sm = 0;
+static thread_local int g_shared_sm = 0;
 extern "C" void ae_set_shared_sm(int on) { g_shared_sm = on ? 1 : 0; }
-static int g_tile_model = 1;
+static thread_local int g_tile_model = 1;
 extern "C" void ae_set_tile_model(int on) { g_tile_model = on ? 1 : 0; }
 extern "C" void ae_set_fast_epilogue(int mode) { g_fast_epi = (mode == 0 || mode == 2) ? mode : 1; }
 extern "C" void ae_set_splitk_ctas(int ctas) { g_splitk_ctas = ctas < 1 ? 148 : ctas; }

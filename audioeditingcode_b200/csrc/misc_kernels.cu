@@ -220,6 +220,17 @@ __global__ void leaky_relu_bf16_kernel(const float* __restrict__ x, long long n,
     out[i] = f2op(v > 0.f ? v : v * slope);
   }
 }
+// (wavs * 32768).astype("int16") of hifigan/utilities.py:80: truncation toward zero; tanh output is inside (-1, 1), the
+// clamp only guards the +-1.0 corner the fp32 tanh can round to
+__global__ void wave_to_int16_kernel(const float* __restrict__ x, long long n, int16_t* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float v = fminf(fmaxf(x[i] * 32768.0f, -32768.0f), 32767.0f);
+    out[i] = (int16_t)v;
+  }
+}
+
 __global__ void tanh_f32_kernel(const float* __restrict__ x, long long n, float* __restrict__ out) {
   pdl_trigger();
   pdl_wait();
@@ -379,6 +390,12 @@ extern "C" int ae_leaky_relu_bf16(const float* x, int64_t n, float scale, float 
   launch_kernel(leaky_relu_bf16_kernel, dim3(ew_grid(n, 256)), dim3(256), (size_t)(0), as_stream(stream), x, n, scale, slope,
                                                                          reinterpret_cast<op_t*>(out_bf16));
   return launched("ae_leaky_relu_bf16");
+}
+
+extern "C" int ae_wave_to_int16(const float* x, int64_t n, int16_t* out, ae_stream stream) {
+  AE_CHECK_ARG(x && out && n > 0, "ae_wave_to_int16: bad argument");
+  launch_kernel(wave_to_int16_kernel, dim3(ew_grid(n, 256)), dim3(256), (size_t)(0), as_stream(stream), x, n, out);
+  return launched("ae_wave_to_int16");
 }
 
 extern "C" int ae_tanh_f32(const float* x, int64_t n, float* out, ae_stream stream) {

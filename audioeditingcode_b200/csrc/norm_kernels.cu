@@ -668,9 +668,9 @@ cudaError_t launch_ln(const float* x, long long rows, int C, float eps, const fl
 
 using namespace aedit;
 
-static long long g_gn_stream_min_bytes = 8ll << 20;
+static thread_local long long g_gn_stream_min_bytes = 8ll << 20;
 extern "C" void ae_set_gn_stream_min_bytes(int64_t bytes) { g_gn_stream_min_bytes = bytes; }
-static int g_gn_fused = 0;  // measured no faster than stats + apply (profiles/r01_microbench_v15_gn_resident.log): opt-in
+static thread_local int g_gn_fused = 0;  // measured no faster than stats + apply (profiles/r01_microbench_v15_gn_resident.log): opt-in
 extern "C" void ae_set_gn_fused(int on) { g_gn_fused = on ? 1 : 0; }
 
 extern "C" int64_t ae_groupnorm_workspace_bytes(int B, int groups) {

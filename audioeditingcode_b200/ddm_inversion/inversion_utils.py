@@ -505,6 +505,136 @@ def inversion_reverse_process(model: PipelineWrapper,
 
 
 # ------------------------------------------------------------------------------------------------------------------
+# Multi-clip batches (BASELINE configs[2]: "batch of 32 clips sharded across 8 GPUs").  The reference has
+# no clip axis — its batch dimension means "prompts of one clip" (inversion_utils.py:78,88,252; get_noise_shape,
+# models.py:60-65) — so these are NEW entry points; the single-clip drop-in signatures above are untouched.  Every U-Net
+# launch carries B = K * (1 + P) rows (K clips x [uncond, P prompts]): the reverse process of one clip is a sequential
+# chain of sub-wave launches that leaves most SMs idle, K clips per launch turn that idle width into throughput.
+# Per clip the arithmetic is the same kernels on the same data as the single-clip functions (a row's bits depend on the
+# launch's batch size only through the fixed, batch-size-dependent split-K plan of the small-M GEMMs).
+# ------------------------------------------------------------------------------------------------------------------
+def _clip_prompts(prompts, K: int) -> List[List[str]]:
+    """prompts: List[str] shared by all clips, or List[List[str]] with one list per clip (equal lengths)."""
+    if len(prompts) and isinstance(prompts[0], (list, tuple)):
+        if len(prompts) != K:
+            raise ValueError(f"{len(prompts)} prompt lists for {K} clips")
+        if len({len(p) for p in prompts}) != 1:
+            raise ValueError("every clip needs the same number of prompts")
+        return [list(p) for p in prompts]
+    return [list(prompts) for _ in range(K)]
+
+
+def _batched_text(model: PipelineWrapper, neg_prompts: List[str], per_clip: List[List[str]]):
+    """Text rows of a multi-clip launch: row 0 = the negative / unconditional prompt, then the DISTINCT conditional prompts
+    (clips sharing a prompt share its K/V rows).  Returns (TextCache, class-label rows, {prompt: row})."""
+    uniq: List[str] = []
+    for ps in per_clip:
+        for q in ps:
+            if q not in uniq:
+                uniq.append(q)
+    text, cl = _loop_text(model, neg_prompts, uniq if uniq else None)
+    return text, cl, {q: 1 + i for i, q in enumerate(uniq)}
+
+
+def inversion_forward_process_batched(model: PipelineWrapper, x0s: torch.Tensor, etas: float = 1.0,
+                                      prompts=("",), cfg_scales: List[float] = [3.5], num_inference_steps: int = 50,
+                                      cutoff_points: Optional[List[float]] = None, numerical_fix: bool = True,
+                                      forward_batch: Optional[int] = None, noise: Optional[torch.Tensor] = None
+                                      ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """inversion_forward_process (reference :8-144) for K clips at once.  x0s: [K, C, H, W]; noise (optional):
+    [K, N, C, H, W]; prompts: shared List[str] or one list per clip.  Returns (xt [K,1,C,H,W], zs [K,N,C,H,W],
+    xts [K,N+1,C,H,W]) — per clip what the single-clip function returns."""
+    K = x0s.shape[0]
+    N = num_inference_steps
+    per_clip = _clip_prompts(list(prompts), K)
+    have_cond = len(per_clip[0]) > 1 or per_clip[0][0] != ""
+    P = len(per_clip[0]) if have_cond else 0
+    cfg_map = None
+    if have_cond:
+        cfg_map, _ = _build_cfg_maps(P, x0s.shape[1:], list(cfg_scales), cutoff_points, model.device, x0s.dtype, per_clip[0])
+    text, cl, row_of = _batched_text(model, [""], per_clip if have_cond else [[]] * K)
+    sched = model.model.scheduler
+    timesteps = sched.timesteps.to(model.device)
+    if type(etas) in [int, float]:
+        etas = [etas] * sched.num_inference_steps
+    xts = torch.stack([model.sample_xts_from_x0(x0s[k:k + 1], num_inference_steps=N,
+                                                noise=None if noise is None else noise[k]) for k in range(K)])
+    zs = torch.zeros((K, *model.get_noise_shape(x0s, N)), device=model.device)
+    model.sched_table.set_etas(etas)
+    tb = forward_batch if forward_batch is not None else DEFAULT_FORWARD_BATCH
+    tb = max(1, min(int(tb) // K if tb > 1 else 1, N))           # keep rows per launch ~ 2 * forward_batch
+    xt_src = xts.clone() if tb > 1 else xts
+    rows_per_clip = 1 + P
+    for pos0 in range(0, N, tb):
+        count = min(tb, N - pos0)
+        src_rows = torch.arange(N - pos0, N - pos0 - count, -1, device=model.device)
+        t_b = timesteps[pos0:pos0 + count]
+        xs, ts_, sl = [], [], []
+        for k in range(K):
+            xt_b = xt_src[k].index_select(0, src_rows)
+            xs += [xt_b] + ([xt_b.repeat_interleave(P, 0)] if P else [])
+            ts_ += [t_b] + ([t_b.repeat_interleave(P)] if P else [])
+            sl += [0] * count + [row_of[q] for _ in range(count) for q in per_clip[k]] if P else [0] * count
+        x_in, t_in = torch.cat(xs, 0), torch.cat(ts_, 0)
+        slot = torch.tensor(sl, dtype=torch.int32, device=model.device)
+        cl_b = None if cl is None else cl.index_select(0, slot.long())
+        eps = _unet_eval(model, x_in, t_in, text, slot, cl_b, slot_key=("fwdK", K, count, tuple(sl)))
+        eta = float(etas[N - pos0 - 1])
+        blk = count * rows_per_clip
+        for k in range(K):
+            e = eps[k * blk:(k + 1) * blk]
+            model.k_cfg_inv_step(pos0, count, eta, e, e[count:] if P else None, P, cfg_map, xt_src[k], xts[k], zs[k],
+                                 numerical_fix)
+    zs[:, 0] = 0                                                      # inversion_utils.py:133
+    return xts[:, 1:2], zs, xts
+
+
+def inversion_reverse_process_batched(model: PipelineWrapper, xT: torch.Tensor, tstart: int, etas: float = 1.0,
+                                      prompts=("",), neg_prompts: List[str] = [""],
+                                      cfg_scales: Optional[List[float]] = None, zs: Optional[torch.Tensor] = None,
+                                      cutoff_points: Optional[List[float]] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """inversion_reverse_process (reference :147-323) for K clips at once, one tstart for all prompts and clips.
+    xT: [K, N+1, C, H, W] (the xts of the forward process), zs: [K, n, C, H, W] (= zs[:, :tstart]).
+    Returns (edited latents [K, C, H, W], zs)."""
+    K = xT.shape[0]
+    per_clip = _clip_prompts(list(prompts), K)
+    P = len(per_clip[0])
+    sched = model.model.scheduler
+    N = sched.num_inference_steps
+    if type(etas) in [int, float]:
+        etas = [etas] * N
+    n = zs.shape[1]
+    tmax = int(tstart)
+    text, cl, row_of = _batched_text(model, neg_prompts, per_clip)
+    cfg_map, _ = _build_cfg_maps(P, xT.shape[2:], list(cfg_scales), cutoff_points, model.device, xT.dtype, masks_too=True)
+    model.sched_table.set_etas(etas)
+    rows = 1 + P
+    sl = []
+    for k in range(K):
+        sl += [0] + [row_of[q] for q in per_clip[k]]
+    slot = torch.tensor(sl, dtype=torch.int32, device=model.device)
+    cl_b = None if cl is None else cl.index_select(0, slot.long())
+    xt = xT[:, tmax].to(torch.float32).contiguous().clone()                             # [K, C, H, W]
+    zs = zs.contiguous()
+    ts_cpu = sched.timesteps_cpu[-n:]
+    lane = 1 if (USE_CUDA_GRAPHS and xT.is_cuda) else 0
+    x_in = torch.empty((K * rows, *xt.shape[1:]), device=model.device, dtype=torch.float32)
+    for k_step in range(n):
+        t = int(ts_cpu[k_step])
+        pos = N - n + k_step
+        idx = n - k_step - 1
+        x_in.copy_(xt.repeat_interleave(rows, 0))
+        t_in = torch.full((K * rows,), t, dtype=torch.int64, device=model.device)
+        eps = _unet_eval(model, x_in, t_in, text, slot, cl_b, slot_key=("revK", K, tuple(sl)), lane=lane)
+        out = torch.empty_like(xt)
+        for k in range(K):
+            e = eps[k * rows:(k + 1) * rows]
+            model.k_cfg_rev_step(pos, float(etas[idx]), e, e[1:], P, cfg_map, xt[k:k + 1], zs[k, idx], out[k:k + 1])
+        xt = out
+    return xt, zs
+
+
+# ------------------------------------------------------------------------------------------------------------------
 # General path: the reference's per-step structure (needed when h-space / skip-connection taps are requested).
 # ------------------------------------------------------------------------------------------------------------------
 def _forward_general(model, x0, etas, prog_bar, prompts, cfg_scales, num_inference_steps, cutoff_points,

@@ -428,8 +428,9 @@ class AudioLDM2Wrapper(PipelineWrapper):
 
     def _synthetic_triple(self, prompts: List[str]):
         L = max(1, max(len(p.split()) for p in prompts) + (1 if any(p for p in prompts) else 0))
-        gen = self._synthetic_text(prompts, 768, 8, False, 1)
-        t5 = self._synthetic_text(prompts, 1024, L, False, 2)
+        dims = {sp[1]: sp[0] for sp in self.unet_config.transformer_specs if sp is not None}     # 768 / 1024 at full size
+        gen = self._synthetic_text(prompts, dims.get(0, 768), 8, False, 1)
+        t5 = self._synthetic_text(prompts, dims.get(1, 1024), L, False, 2)
         mask = torch.zeros(len(prompts), L, dtype=torch.long, device=self.device)
         for i, p in enumerate(prompts):
             mask[i, : max(1, len(p.split()) + (1 if p else 0))] = 1
@@ -457,12 +458,25 @@ class TangoWrapper(PipelineWrapper):
 
     family = "tango"
 
+    def decode_to_mel(self, x: torch.Tensor):                                                 # models.py:452-453
+        """tango's AutoencoderKL.decode_to_waveform (in-tree twin autoencoder.py:63-66 -> hifigan/utilities.py:76-85):
+        vocoder on [B, T, 64], then `(wav * 32768).astype(int16)` — returned as an int16 numpy array [B, samples]; the
+        conversion runs on the device (ae_wave_to_int16), only the PCM samples cross to the host."""
+        wav = self._ends().vocoder(x[:, 0].detach().float())
+        if wav.dim() == 1:
+            wav = wav.unsqueeze(0)
+        wav = wav.contiguous()
+        pcm = torch.empty(wav.shape, dtype=torch.int16, device=wav.device)
+        self.engine.ops.wave_to_int16(wav, pcm)
+        return pcm.cpu().numpy()
+
     def encode_text(self, prompts: List[str], **kwargs) -> Tuple[Optional[torch.Tensor], None, Optional[torch.Tensor]]:
         return self._encode_text_or_synthetic(prompts, self._synthetic_triple)                               # :455-460
 
     def _synthetic_triple(self, prompts: List[str]):
         L = max(1, max(len(p.split()) for p in prompts) + 1)
-        t5 = self._synthetic_text(prompts, 1024, L, False, 3)
+        dims = {sp[1]: sp[0] for sp in self.unet_config.transformer_specs if sp is not None}
+        t5 = self._synthetic_text(prompts, dims.get(0, 1024), L, False, 3)
         mask = torch.zeros(len(prompts), L, dtype=torch.bool, device=self.device)
         for i, p in enumerate(prompts):
             mask[i, : len(p.split()) + 1] = True

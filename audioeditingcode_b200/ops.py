@@ -251,6 +251,9 @@ class CudaOps:
     def tanh(self, x, out):
         check(self.lib.ae_tanh_f32(_p(x), x.numel(), _p(out), _stream()), "ae_tanh_f32")
 
+    def wave_to_int16(self, x, out):
+        check(self.lib.ae_wave_to_int16(_p(x), x.numel(), _p(out), _stream()), "ae_wave_to_int16")
+
     def stft_mel(self, wav, n_fft, hop, window, mel_basis, n_frames, out, mag_ws=None):
         check(self.lib.ae_stft_mel(_p(wav), wav.numel(), n_fft, hop, _p(window), _p(mel_basis), mel_basis.shape[0],
                                    n_frames, _p(mag_ws), _p(out), _stream()), "ae_stft_mel")

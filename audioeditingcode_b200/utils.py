@@ -60,6 +60,7 @@ def set_reproducability(seed: int, extreme: bool = True) -> None:
     # the torch-side plumbing and are kept for script compatibility (utils.py:113-116)
     torch.backends.cuda.matmul.allow_tf32 = False
     torch.backends.cudnn.allow_tf32 = False
+    torch.set_float32_matmul_precision("high")      # utils.py:116 (torch-side matmuls only, e.g. the text encoders)
 
 
 def get_height_of_spectrogram(length: int, ldm_stable: PipelineWrapper) -> int:

@@ -45,9 +45,24 @@ CONFIGS = {
     # BASELINE.json configs[4] geometry: 30 s clip, AudioLDM2 (whole clip on one GPU)
     "audioldm2-30s": dict(preset="audioldm2", model_id="cvssp/audioldm2", H=768, W=16, n_inv=200, tstart=100, cfg_src=3.0,
                           cfg_tar=12.0, text_lens=(8, 16)),
+    # BASELINE.json configs[4]: SDEdit (main_run_sdedit.py:78-100), AudioLDM2, 30 s clip (whole clip on one GPU, DESIGN.md
+    # §5: overlapping tiles would change GroupNorm / self-attention results), add_noise at timesteps[100] + 100 steps
+    "sdedit-30s": dict(preset="audioldm2", model_id="cvssp/audioldm2", H=768, W=16, n_inv=200, tstart=100, cfg_src=3.0,
+                       cfg_tar=12.0, text_lens=(8, 16), mode="sdedit"),
+    # BASELINE.json configs[3]: unsupervised PC extraction (main_pc_extract_inv.py:199-209) at ONE timestep of the drift
+    # window: n_evs = 8 directions, 50 subspace iterations, const 1e-3; under torchrun the directions are sharded over the
+    # ranks (one all-gather of the iterate per iteration) -> strong scaling of one extraction
+    "pc-drift": dict(preset="audioldm2", model_id="cvssp/audioldm2", H=256, W=16, n_inv=200, tstart=100, cfg_src=3.0,
+                     cfg_tar=3.0, text_lens=(8, 16), mode="pc", n_ev=8, iters=50),
     "tiny": dict(preset="tiny-audioldm2", model_id="synthetic/audioldm2-tiny", H=32, W=16, n_inv=20, tstart=10,
                  cfg_src=3.0, cfg_tar=12.0, text_lens=(8, 16)),
 }
+
+
+def workload_config(name, spec, clips):
+    """The `config` object of the JSON line — identical for both arms (ours / --impl reference)."""
+    return {"workload": name, "arch": spec["preset"], "mode": spec.get("mode", "edit"), "clips_per_gpu": clips,
+            "latent": [1, 8, spec["H"], spec["W"]], "n_inv": spec["n_inv"], "tstart": spec["tstart"]}
 
 
 def load_peaks():
@@ -126,15 +141,65 @@ def build_model(spec, device):
 
 
 def run_job(m, spec, x0_dev, forward_batch):
+    """One bench step.  mode "edit" (default): inversion + edit of the clip(s) in x0_dev ([K,C,H,W]; K > 1 -> the
+    multi-clip entry points, B = K*(1+P) rows per launch); "sdedit": add_noise + tstart forward_directional steps;
+    "pc": one get_eigenvectors call (n_ev directions, `iters` subspace iterations)."""
     from audioeditingcode_b200.ddm_inversion import inversion_utils as IU
     N, ts = spec["n_inv"], spec["tstart"]
-    _, zs, xts, _ = IU.inversion_forward_process(m, x0_dev, etas=1.0, prompts=["a recording of a dog barking"],
-                                                 cfg_scales=[spec["cfg_src"]], num_inference_steps=N,
-                                                 numerical_fix=True, forward_batch=forward_batch)
-    w, _ = IU.inversion_reverse_process(m, xT=xts, tstart=torch.tensor([ts], dtype=torch.int), etas=1.0,
-                                        prompts=["a recording of a cat meowing"], neg_prompts=[""],
-                                        cfg_scales=[spec["cfg_tar"]], zs=zs[:ts])
-    return w
+    mode = spec.get("mode", "edit")
+    src, tgt = "a recording of a dog barking", "a recording of a cat meowing"
+    if mode == "edit" and x0_dev.shape[0] == 1:
+        _, zs, xts, _ = IU.inversion_forward_process(m, x0_dev, etas=1.0, prompts=[src], cfg_scales=[spec["cfg_src"]],
+                                                     num_inference_steps=N, numerical_fix=True, forward_batch=forward_batch)
+        w, _ = IU.inversion_reverse_process(m, xT=xts, tstart=torch.tensor([ts], dtype=torch.int), etas=1.0,
+                                            prompts=[tgt], neg_prompts=[""], cfg_scales=[spec["cfg_tar"]], zs=zs[:ts])
+        return w
+    if mode == "edit":
+        _, zs, xts = IU.inversion_forward_process_batched(m, x0_dev, etas=1.0, prompts=[src], cfg_scales=[spec["cfg_src"]],
+                                                          num_inference_steps=N, numerical_fix=True,
+                                                          forward_batch=forward_batch)
+        w, _ = IU.inversion_reverse_process_batched(m, xts, ts, etas=1.0, prompts=[tgt], neg_prompts=[""],
+                                                    cfg_scales=[spec["cfg_tar"]], zs=zs[:, :ts])
+        return w
+    from audioeditingcode_b200 import pc_drift as PC
+    st = _pc_state(m, spec, x0_dev, src)
+    if mode == "sdedit":                                        # main_run_sdedit.py:89-100
+        timesteps = m.model.scheduler.timesteps
+        skip = N - ts
+        xt = m.model.scheduler.add_noise(x0_dev, st["noise"], timesteps[skip:][:1].unsqueeze(0))
+        for it, t in enumerate(timesteps[skip:]):
+            xt, _ = PC.forward_directional(m, xt, t, st["latents"][skip + it + 1][None], st["unc"], st["txt"],
+                                           spec["cfg_tar"], eta=1)
+        return xt
+    # mode == "pc": main_pc_extract_inv.py:199-209 at one timestep of the drift window
+    t = m.model.scheduler.timesteps[N - ts]
+    _, x0p = PC.forward_directional(m, x0_dev, t, st["latents"][0][None], st["unc"], st["txt"], spec["cfg_tar"], eta=1)
+    ev = PC.get_eigenvectors(m, x0_dev, st["txt"], st["unc"], st["latents"][0][None], st["mask"], t, x0p,
+                             PC.PCStreamChoice.BOTH, 1e-3, spec["cfg_tar"], spec["iters"], False, 1, spec["n_ev"],
+                             group=st["group"])
+    return ev[0]
+
+
+_PC_STATE = {}
+
+
+def _pc_state(m, spec, x0_dev, prompt):
+    """Per-model constants of the sdedit / pc jobs (text embeddings, pre-drawn latents), built once outside the timing."""
+    st = _PC_STATE.get(id(m))
+    if st is None:
+        from audioeditingcode_b200 import pc_drift as PC
+        g = torch.Generator(device=x0_dev.device).manual_seed(7)
+        N = spec["n_inv"]
+        unc, txt = m.encode_text([""], negative=True), m.encode_text([prompt])
+        group = None
+        if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+            import torch.distributed as dist
+            group = dist.group.WORLD
+        st = dict(unc=PC.PromptEmbeddings(*unc), txt=PC.PromptEmbeddings(*txt), group=group,
+                  latents=torch.randn((N + 1, *x0_dev.shape[1:]), device=x0_dev.device, generator=g),
+                  noise=torch.randn(x0_dev.shape, device=x0_dev.device, generator=g), mask=torch.ones_like(x0_dev))
+        _PC_STATE[id(m)] = st
+    return st
 
 
 def gemm_event_pass(m, spec, cfg, B=2):
@@ -209,22 +274,23 @@ def usable_cores():
     return max(1, n)
 
 
-def pick_threads(limit):
-    """Thread count for the CPU arm: a 2-second calibration of a representative fp32 conv3x3 over a few candidate
-    counts <= the usable cores (more threads than the machine really grants is slower, not faster)."""
-    import torch.nn.functional as F
-    x = torch.randn(2, 384, 128, 8)
-    w = torch.randn(384, 384, 3, 3)
-    cands = sorted({c for c in (limit, limit // 2, limit // 4, 64, 32, 16, 8) if 1 <= c <= limit}, reverse=True)
+def pick_threads(limit, probe=None):
+    """Thread count for the CPU arm, calibrated ON THE WORKLOAD ITSELF: one U-Net evaluation of the oracle port (`probe`)
+    per candidate count <= the usable cores, after a warm-up evaluation; the fastest wins (more threads than the machine
+    really grants is slower, not faster).  Round 1 calibrated on a lone conv3x3 and picked 8 or 16 threads on the same
+    box class (0.90 vs 1.28 steps/s); the evaluation-level probe is what the arm then runs."""
+    cands = sorted({c for c in (limit, limit // 2, 16, 8) if 1 <= c <= limit}, reverse=True)
+    if probe is None or len(cands) == 1:
+        torch.set_num_threads(cands[0])
+        return cands[0]
     best, best_t = cands[0], float("inf")
     for c in cands:
         torch.set_num_threads(c)
-        F.conv2d(x, w, padding=1)
+        probe()
         t0 = time.perf_counter()
-        for _ in range(3):
-            F.conv2d(x, w, padding=1)
+        probe()
         dt = time.perf_counter() - t0
-        if dt < best_t * 0.95:
+        if dt < best_t:
             best, best_t = c, dt
     torch.set_num_threads(best)
     return best
@@ -294,11 +360,21 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="audioldm2-large-10s", choices=sorted(CONFIGS))
     ap.add_argument("--forward-batch", type=int, default=int(os.environ.get("AEDIT_FORWARD_BATCH", "50")))
+    ap.add_argument("--clips", type=int, default=1, help="clips per GPU per job (K > 1: multi-clip entry points, "
+                    "B = K*(1+P) rows per U-Net launch; BASELINE configs[2] uses 4)")
     ap.add_argument("--cpu-steps", type=int, default=0, help="CFG steps of the cpu_baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     spec = CONFIGS[args.config]
-    steps_per_job = spec["n_inv"] + spec["tstart"]
+    mode = spec.get("mode", "edit")
+    K = max(1, args.clips) if mode == "edit" else 1
+    # denoising steps (CFG-guided U-Net steps) one bench step performs on one GPU
+    if mode == "edit":
+        steps_per_job = (spec["n_inv"] + spec["tstart"]) * K
+    elif mode == "sdedit":
+        steps_per_job = spec["tstart"]
+    else:                                    # pc: 1 unperturbed step + iters iterations of n_ev perturbed CFG steps
+        steps_per_job = 1 + spec["iters"] * spec["n_ev"]
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -308,8 +384,8 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        threads = pick_threads(cores)
-        oracle = CpuOracle(spec, threads)
+        oracle = CpuOracle(spec, cores)
+        threads = pick_threads(cores, lambda: oracle.unet(oracle.xts[1][None], 1, "uncond"))
         oracle.unet(oracle.xts[1][None], 1, "uncond")     # one untimed evaluation: thread pool / primitive caches
         n_sample = args.cpu_steps or 1
         vals = []
@@ -325,8 +401,7 @@ def main():
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * tot_t / max(1, len(vals)),
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
                 "impl": "reference",
-                "config": {"workload": args.config, "arch": spec["preset"], "latent": [1, 8, spec["H"], spec["W"]],
-                           "n_inv": spec["n_inv"], "tstart": spec["tstart"]},
+                "config": workload_config(args.config, spec, K),
                 "cpu_baseline": {"value": value, "unit": "steps/s", "cores": cores, "kind": "port",
                                  "sample": f"{n_sample} CFG denoising steps (2 U-Net evals each, fp32 torch CPU oracle port) "
                                            f"per bench step of the {args.config} workload"},
@@ -345,7 +420,7 @@ def main():
     m, cfg = build_model(spec, dev)
     ops = m.engine.ops
     g = torch.Generator().manual_seed(1 + rank)
-    x0_host = (0.5 * torch.randn(1, cfg.in_channels, spec["H"], spec["W"], generator=g)).pin_memory()
+    x0_host = (0.5 * torch.randn(K, cfg.in_channels, spec["H"], spec["W"], generator=g)).pin_memory()
     x0_dev = x0_host.to(dev)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > L2 (126 MB)
 
@@ -373,7 +448,8 @@ def main():
     def job_resident():
         run_job(m, spec, x0_dev, args.forward_batch)
 
-    e2e_out = torch.empty(1, cfg.in_channels, spec["H"], spec["W"]).pin_memory()
+    out_rows = spec["n_ev"] if mode == "pc" else K
+    e2e_out = torch.empty(out_rows, cfg.in_channels, spec["H"], spec["W"]).pin_memory()
 
     def job_e2e():
         x = x0_host.to(dev, non_blocking=True)
@@ -389,25 +465,45 @@ def main():
         launches = ops.launch_count() + getattr(m, "graph_kernels", 0) - l0   # eager launches + kernels replayed in graphs
     clocks = cs.summary()
     ms_e2e = timed_loop(job_e2e, args.steps)
-    total_steps = steps_per_job * args.steps * world
+    # pc under torchrun shards ONE extraction over the ranks (strong scaling); everything else is one job per rank (weak)
+    strong = mode == "pc" and world > 1
+    total_steps = steps_per_job * args.steps * (1 if strong else world)
+    from audioeditingcode_b200 import _lib as _aelib
+    op_dtype = "fp16" if _aelib.load().ae_operand_dtype() == 1 else "bf16"
     value = total_steps / (ms / 1000.0)
     e2e_value = total_steps / (ms_e2e / 1000.0)
 
     line = {"metric": "denoising-steps/sec", "value": value, "unit": "steps/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": args.config, "arch": spec["preset"], "weights": m.weights_source,
-                       "latent": [1, 8, spec["H"], spec["W"]], "n_inv": spec["n_inv"], "tstart": spec["tstart"],
-                       "denoising_steps_per_bench_step": steps_per_job, "forward_batch_timesteps": args.forward_batch,
-                       "parallelism": f"clip-dp{world}", "l2": "256 MiB flush between jobs; weights (1.5 GB) >> L2",
-                       "lanes": ("forward chunks and reverse steps of the clip on two streams (reverse lane high priority), "
-                                 f"fast path taken {getattr(m, 'overlap_hits', 0)}x") if getattr(m, "overlap_hits", 0)
-                       else "single stream"},
+            "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "strong" if strong else "weak",
+            "vs_baseline": None, "dtype": op_dtype, "data": "synthetic",
+            "config": workload_config(args.config, spec, K),
+            "details": {"weights": m.weights_source,
+                        "precision": f"{op_dtype} tensor-core operands (AEDIT_OPERANDS), fp32 accumulate / residual stream / "
+                                     "scheduler state",
+                        "denoising_steps_per_bench_step": steps_per_job, "forward_batch_timesteps": args.forward_batch,
+                        "parallelism": (f"pc-directions-sharded-{world}" if strong else f"clip-dp{world}"),
+                        "l2": "256 MiB flush between jobs; weights (1.5 GB) >> L2",
+                        "lanes": ("forward chunks and reverse steps of the clip on two streams (reverse lane high priority), "
+                                  f"fast path taken {getattr(m, 'overlap_hits', 0)}x") if getattr(m, "overlap_hits", 0)
+                        else "single stream"},
             "e2e": {"value": e2e_value, "unit": "steps/s", "h2d_bytes_per_step": x0_host.numel() * 4,
                     "d2h_bytes_per_step": e2e_out.numel() * 4},
             "gpu_launches": int(launches), "clocks": clocks}
 
-    if rank == 0:
+    if rank == 0 and (mode != "edit" or K > 1):
+        # other workloads: one evaluation shape dominates; report its GEMM-family rate only
+        peaks = load_peaks()
+        rows = 2 * (spec["n_ev"] if mode == "pc" else K)
+        fl = flops_per_eval(cfg, spec, rows)
+        gp = gemm_event_pass(m, spec, cfg, rows)
+        ach = (fl["conv"] + fl["linear"]) / gp["gemm_ms"] / 1e9
+        line["roofline"] = {"bound": "tensor", "kernel": "gemm_tcgen05_kernel (conv3x3 / conv1x1 / linear)",
+                            "achieved": ach, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": ach / peaks["tflops"],
+                            "traffic": None, "peak_source": peaks["source"],
+                            "per_eval": {f"B{rows}": {"gemm_ms": gp["gemm_ms"], "eval_ms": gp["eval_ms"]}}}
+        print(json.dumps(line))
+    elif rank == 0:
         peaks = load_peaks()
         fl2 = flops_per_eval(cfg, spec, 2)
         gp = gemm_event_pass(m, spec, cfg, 2)
@@ -431,14 +527,23 @@ def main():
         achieved = gemm_flops / (gemm_ms_job / 1000.0) / 1e12
         # whole-job FLOPs: forward batches B = 2*forward_batch per launch, reverse B = 2
         job_flops = (spec["n_inv"] + spec["tstart"]) * fl2["total"]
-        traffic, traffic_src = None, None
-        tj = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_gemm_traffic.json")
-        if os.path.exists(tj):      # dram bytes per launch of the dominant kernel, from the committed ncu --set full capture
-            tinfo = json.load(open(tj))
-            traffic, traffic_src = tinfo["traffic_bytes_per_launch"], tinfo["source"]
+        traffic, traffic_src, alg_bytes = None, None, None
+        for tname in ("r02_gemm_traffic.json", "r01_gemm_traffic.json"):
+            tj = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", tname)
+            if os.path.exists(tj):  # dram bytes per launch of the dominant kernel, from the committed ncu --set full capture
+                tinfo = json.load(open(tj))
+                traffic, traffic_src = tinfo["traffic_bytes_per_launch"], tinfo["source"]
+                alg_bytes = tinfo.get("algorithmic_bytes_per_launch")
+                break
+        in_situ = gemm_flops / (ms / args.steps / 1000.0) / 1e12      # same FLOPs over the whole job time (all kernels)
         line["roofline"] = {"bound": "tensor", "kernel": "gemm_tcgen05_kernel (conv3x3 / conv1x1 / linear)",
                             "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s",
                             "frac": achieved / peaks["tflops"], "traffic": traffic, "traffic_source": traffic_src,
+                            "algorithmic_bytes_per_launch": alg_bytes,
+                            "achieved_in_situ": in_situ, "frac_in_situ": in_situ / peaks["tflops"],
+                            "how": "achieved = conv+linear FLOPs of the job (SURVEY 8d counting rule, the reference "
+                                   "algorithm's layers) / time of the job's ae_gemm launches replayed ALONE back to back in a "
+                                   "CUDA graph; achieved_in_situ = the same FLOPs / ms_per_step (all kernels, both lanes)",
                             "peak_source": peaks["source"],
                             "flops_per_job": gemm_flops, "gemm_ms_per_job": gemm_ms_job,
                             "gemm_share_of_unet_time": gemm_ms_job / eval_ms_job,
@@ -449,8 +554,8 @@ def main():
                                              **per_chunk),
                             "job_tflops_all_kernels": job_flops * args.steps / (ms / 1000.0) / 1e12}
         if not args.no_cpu_baseline and world == 1:
-            threads = pick_threads(cores)
-            oracle = CpuOracle(spec, threads)
+            oracle = CpuOracle(spec, cores)
+            threads = pick_threads(cores, lambda: oracle.unet(oracle.xts[1][None], 1, "uncond"))
             oracle.unet(oracle.xts[1][None], 1, "uncond")     # untimed warm-up evaluation
             n_sample = args.cpu_steps or 1
             dt = oracle.steps(n_sample)

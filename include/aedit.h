@@ -43,9 +43,14 @@ int ae_operand_dtype(void);
 int64_t ae_launch_count(void);
 /* 1 if the current device is compute capability 10.x */
 int ae_device_ok(void);
+/* ---- Settings.  Every ae_set_* below changes a setting OF THE CALLING HOST THREAD only (thread_local state): it
+ * affects the kernels that thread launches (or captures into a CUDA graph) afterwards, on whatever stream.  The host
+ * toggles some of them around graph captures (launch priority, PDL families, shared-SM rings); threads driving other
+ * streams are not affected, and a thread that never calls a setter runs with the documented defaults.  Work on several
+ * streams from ONE thread is unaffected by construction — a setting is read on the host when a kernel is launched. */
 /* Programmatic dependent launch: a kernel launched with it may start (prologue, weight prefetch) before its
  * predecessor in the stream has drained, and waits for it before touching dependent global memory. */
-void ae_set_pdl(int mode); /* 0 off (default), 1 every kernel, 2 GEMM kernels only */
+void ae_set_pdl(int mode); /* 0 off, 1 every kernel, 2 GEMM kernels only (default) */
 
 /* Launch priority (cudaLaunchAttributePriority) attached to every kernel this library launches while it is set; 0 (the
  * default) leaves the stream's own priority.  The host captures the reverse-process U-Net graph (reference
@@ -357,6 +362,8 @@ int ae_stft_mel(const float* wav, int n_samples, int n_fft, int hop, const float
 /* out = leaky_relu(scale * x, slope) as bf16 (scale carries the 1/num_kernels of the MRF average, models.py:160) */
 int ae_leaky_relu_bf16(const float* x, int64_t n, float scale, float slope, void* out_bf16, ae_stream stream);
 int ae_tanh_f32(const float* x, int64_t n, float* out, ae_stream stream);
+/* waveform float [-1,1] -> 16-bit PCM, (x * 32768) truncated toward zero (hifigan/utilities.py:76-85 vocoder_infer) */
+int ae_wave_to_int16(const float* x, int64_t n, int16_t* out, ae_stream stream);
 
 #ifdef __cplusplus
 }
