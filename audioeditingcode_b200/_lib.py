@@ -89,6 +89,7 @@ _SIGS = {
                               i64, i64, vp, i64, vp]),
     "ae_attention_workspace_bytes": (i64, [i32, i32, i32, i32]),
     "ae_set_attention_split": (None, [i32]),
+    "ae_set_attention_tc": (None, [i32]),
     "ae_timestep_embedding": (i32, [vp, i32, i32, vp, vp]),
     "ae_upsample_nearest": (i32, [vp, i32, i32, i32, i32, i32, i32, vp, vp]),
     "ae_nchw_to_nhwc": (i32, [vp, i32, i32, i32, i32, vp, vp, vp]),

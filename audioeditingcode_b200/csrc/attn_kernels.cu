@@ -340,6 +340,14 @@ int launch_attn(const AttnArgs& a, int B, int heads, cudaStream_t st) {
 }  // namespace
 }  // namespace aedit
 
+namespace aedit {
+// attn_tc.cu: the tcgen05 / TMEM / TMA attention path.  Returns 1 if it took the call (*rc = status), else 0.
+int attention_tc_try(const void* q, int64_t ld_q, int64_t q_bs, const void* k, int64_t ld_k, int64_t k_bs, const void* v,
+                     int64_t ld_v, int64_t v_bs, const int32_t* kv_map, const float* key_bias, int64_t ld_bias, int B,
+                     int Bkv, int heads, int d, int Tq, int Tk, float scale, void* out, int64_t ld_o, int64_t o_bs,
+                     cudaStream_t st, int* rc);
+}  // namespace aedit
+
 using namespace aedit;
 
 static thread_local int g_attn_split = 1;   // 0 auto, 1 never (default: measured slower), n > 1: that many key splits
@@ -405,6 +413,12 @@ static int attention_impl(const void* q, int64_t ld_q, int64_t q_bs, const void*
   }
   cudaStream_t st = as_stream(stream);
   if (g_skip_mask & 32) return AE_OK;
+  {
+    int rc = AE_OK;      // long sequences: tensor-core (tcgen05) kernel; everything else: the mma.sync kernel below
+    if (attention_tc_try(q, ld_q, q_bs, k, ld_k, k_bs, v, ld_v, v_bs, kv_batch_map, key_bias, ld_bias, B, B, heads, d, Tq, Tk,
+                         scale, out, ld_o, o_bs, st, &rc))
+      return rc;
+  }
   switch (d) {
     case 32: return launch_attn<32>(a, B, heads, st);
     case 40: return launch_attn<40>(a, B, heads, st);

@@ -136,6 +136,11 @@ inline cudaError_t launch_kernel_family(int family, void (*kernel)(KArgs...), di
   return launch_kernel_mode((g_pdl_extra & family) != 0, kernel, grid, block, smem, st, static_cast<Args&&>(args)...);
 }
 
+// 128-byte-swizzled TMA tensor map of operand-type elements (defined in gemm_tcgen05.cu); tm points at a CUtensorMap.
+// dims / box innermost first, strides in BYTES for dims 1..rank-1.
+int make_operand_tmap(void* tm, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                      const uint32_t* box);
+
 inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }

@@ -1294,6 +1294,12 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmDev& p, int
 }
 
 }  // namespace
+
+// operand-type tensor map (128-byte swizzle) for other translation units (attn_tc.cu)
+int make_operand_tmap(void* tm, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                      const uint32_t* box) {
+  return make_tmap(reinterpret_cast<CUtensorMap*>(tm), base, rank, dims, strides_bytes, box);
+}
 }  // namespace aedit
 
 using namespace aedit;

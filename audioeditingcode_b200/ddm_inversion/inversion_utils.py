@@ -460,8 +460,10 @@ def inversion_reverse_process(model: PipelineWrapper,
         # While forward chunks are still running, the steps replay the shared-SM graph variant and are enqueued at
         # most REV_LOOKAHEAD steps ahead of the device, so that the switch to the solo variant happens (up to that
         # look-ahead) when the forward lane has actually drained — the host polls its last event.
-        fwd_done = None if pend is None else pend.chunks[-1][2]
-        contended = fwd_done is not None and REV_VARIANT != "solo"
+        # "forward lane busy" = ANY forward-process work still queued on the model's forward lane: this clip's remaining
+        # chunks, or (edit_clips_pipelined) the next clip's forward process that was enqueued ahead of this call
+        fwd_lane = model.__dict__.get("_lanes", {}).get("fwd") if pend is not None else None
+        contended = fwd_lane is not None and REV_VARIANT != "solo"
         in_flight = []
         for k in it:
             t = int(ts_cpu[k])
@@ -470,7 +472,7 @@ def inversion_reverse_process(model: PipelineWrapper,
             if contended and REV_VARIANT == "adaptive":
                 if len(in_flight) >= REV_LOOKAHEAD:
                     in_flight.pop(0).synchronize()
-                if fwd_done.query():
+                if fwd_lane.query():
                     contended = False
             variant = 0 if not lanes else (2 if (contended or REV_VARIANT == "shared") else 1)
             if variant == 1 and REV_VARIANT == "adaptive":
@@ -505,6 +507,99 @@ def inversion_reverse_process(model: PipelineWrapper,
 
 
 # ------------------------------------------------------------------------------------------------------------------
+# Clip queue with cross-clip pipelining.  Within one clip the reverse process can only overlap the TAIL of its own
+# forward process (it needs zs[tstart-1..] first) and then runs alone for most of its steps, a latency-bound chain that
+# leaves most SMs idle — exactly the window in which the NEXT clip's throughput-bound forward process can run.  So the
+# queue enqueues forward(i+1) on the forward lane BEFORE it drives reverse(i) on the reverse lane; every call is the
+# unchanged single-clip drop-in function (same kernels, same batches, same bits as calling them one clip at a time).
+# ------------------------------------------------------------------------------------------------------------------
+def edit_clips_pipelined(model: PipelineWrapper, x0s, src_prompts: List[str], tgt_prompts: List[str], tstart: int,
+                         cfg_src: float = 3.0, cfg_tar: float = 12.0, num_inference_steps: int = 200, etas: float = 1.0,
+                         neg_prompts: List[str] = [""], numerical_fix: bool = True, forward_batch: Optional[int] = None,
+                         noises=None, on_result=None, group: int = 1) -> List[torch.Tensor]:
+    """Edit a queue of clips (main_run.py:127-160 per clip: inversion_forward_process, then inversion_reverse_process
+    from `tstart`) with the forward process of the NEXT clip(s) running concurrently with the reverse process of the
+    current one(s).  x0s: iterable of [1,C,H,W] latents (device tensors, or pinned host tensors that are copied in when
+    their turn comes); noises: optional per-clip [N,C,H,W]; on_result(i, w): optional callback as soon as clip i's edit
+    is enqueued (e.g. an asynchronous device-to-host copy).  Returns the edited latents [1,C,H,W] in queue order.
+
+    group = 1: every call is the unchanged single-clip drop-in function (same kernels, batches and bits as editing the
+    clips one at a time); forward(i+1) is enqueued on the forward lane BEFORE reverse(i) is driven on the reverse lane.
+    group = K > 1: K clips per reverse launch (inversion_*_batched, B = K*(1+P) rows): the latency-bound reverse chain
+    then carries K clips per step, and the next group's forward process fills the SMs it leaves idle."""
+    clips = list(x0s)
+    n = len(clips)
+    N = num_inference_steps
+    # text conditioning of both prompt sets is prepared up front on the caller's stream: its GEMMs share workspaces with
+    # the forward lane's kernels and must not run beside them
+    _loop_text(model, [""], list(src_prompts) if (len(src_prompts) > 1 or src_prompts[0] != "") else None)
+    _loop_text(model, list(neg_prompts), list(tgt_prompts))
+    if group <= 1:
+        ts = torch.tensor([int(tstart)], dtype=torch.int)
+
+        def forward(i):
+            x0 = clips[i].to(model.device, non_blocking=True)
+            _, zs, xts, _ = inversion_forward_process(model, x0, etas=etas, prompts=list(src_prompts), cfg_scales=[cfg_src],
+                                                      num_inference_steps=N, numerical_fix=numerical_fix,
+                                                      forward_batch=forward_batch, reverse_hint=int(tstart),
+                                                      noise=None if noises is None else noises[i])
+            return zs, xts, model.__dict__.pop("_pending_forward", None)
+
+        out: List[torch.Tensor] = []
+        nxt = forward(0) if n else None
+        for i in range(n):
+            zs, xts, pend = nxt
+            nxt = forward(i + 1) if i + 1 < n else None          # enqueued on the forward lane ahead of reverse(i)
+            if pend is not None:
+                model.__dict__["_pending_forward"] = pend
+            w, _ = inversion_reverse_process(model, xT=xts, tstart=ts, etas=etas, prompts=list(tgt_prompts),
+                                             neg_prompts=list(neg_prompts), cfg_scales=[cfg_tar], zs=zs[:int(tstart)])
+            out.append(w)
+            if on_result is not None:
+                on_result(i, w)
+        return out
+
+    # ---- groups of K clips: forward lane / reverse lane, one event per group
+    cur = torch.cuda.current_stream()
+    f_lane, r_lane = _lane(model, "fwd"), _lane(model, "rev")
+    groups = [list(range(g, min(n, g + group))) for g in range(0, n, group)]
+
+    def forward_group(ids):
+        f_lane.wait_stream(cur)
+        with torch.cuda.stream(f_lane):
+            x = torch.cat([clips[i].to(model.device, non_blocking=True) for i in ids], 0)
+            nz = None if noises is None else torch.stack([noises[i] for i in ids])
+            _, zs, xts = inversion_forward_process_batched(model, x, etas=etas, prompts=list(src_prompts),
+                                                           cfg_scales=[cfg_src], num_inference_steps=N,
+                                                           numerical_fix=numerical_fix, forward_batch=forward_batch, noise=nz)
+            ev = torch.cuda.Event()
+            ev.record(f_lane)
+        for t_ in (zs, xts):
+            t_.record_stream(r_lane)              # allocated on the forward lane, consumed on the reverse lane
+        return zs, xts, ev
+
+    out = [None] * n
+    nxt = forward_group(groups[0]) if groups else None
+    for gi, ids in enumerate(groups):
+        zs, xts, ev = nxt
+        more = gi + 1 < len(groups)
+        nxt = forward_group(groups[gi + 1]) if more else None       # ahead of this group's reverse process
+        r_lane.wait_event(ev)
+        with torch.cuda.stream(r_lane):
+            w, _ = inversion_reverse_process_batched(model, xts, int(tstart), etas=etas, prompts=list(tgt_prompts),
+                                                     neg_prompts=list(neg_prompts), cfg_scales=[cfg_tar],
+                                                     zs=zs[:, :int(tstart)], graph_lane=2 if more else 1)
+            for k, i in enumerate(ids):
+                out[i] = w[k:k + 1]
+                if on_result is not None:
+                    on_result(i, out[i])          # runs in reverse-lane stream order (e.g. an async D2H copy)
+        w.record_stream(cur)
+    cur.wait_stream(r_lane)
+    cur.wait_stream(f_lane)
+    return out
+
+
+# ------------------------------------------------------------------------------------------------------------------
 # Multi-clip batches (SURVEY.md §8e, BASELINE configs[2]: "batch of 32 clips sharded across 8 GPUs").  The reference has
 # no clip axis — its batch dimension means "prompts of one clip" (inversion_utils.py:78,88,252; get_noise_shape,
 # models.py:60-65) — so these are NEW entry points; the single-clip drop-in signatures above are untouched.  Every U-Net
@@ -522,6 +617,20 @@ def _clip_prompts(prompts, K: int) -> List[List[str]]:
             raise ValueError("every clip needs the same number of prompts")
         return [list(p) for p in prompts]
     return [list(prompts) for _ in range(K)]
+
+
+def _dev_i32(model: PipelineWrapper, values) -> torch.Tensor:
+    """Small int32 device constant, uploaded ONCE per model and value list: a pageable host->device copy blocks the host
+    until the stream it is enqueued on has drained, which would serialise the lanes of the clip queue."""
+    cache = model.__dict__.setdefault("_i32_consts", {})
+    key = tuple(values)
+    t = cache.get(key)
+    if t is None:
+        if len(cache) > 64:
+            cache.clear()
+        t = torch.tensor(list(values), dtype=torch.int32, device=model.device)
+        cache[key] = t
+    return t
 
 
 def _batched_text(model: PipelineWrapper, neg_prompts: List[str], per_clip: List[List[str]]):
@@ -576,7 +685,7 @@ def inversion_forward_process_batched(model: PipelineWrapper, x0s: torch.Tensor,
             ts_ += [t_b] + ([t_b.repeat_interleave(P)] if P else [])
             sl += [0] * count + [row_of[q] for _ in range(count) for q in per_clip[k]] if P else [0] * count
         x_in, t_in = torch.cat(xs, 0), torch.cat(ts_, 0)
-        slot = torch.tensor(sl, dtype=torch.int32, device=model.device)
+        slot = _dev_i32(model, sl)
         cl_b = None if cl is None else cl.index_select(0, slot.long())
         eps = _unet_eval(model, x_in, t_in, text, slot, cl_b, slot_key=("fwdK", K, count, tuple(sl)))
         eta = float(etas[N - pos0 - 1])
@@ -592,9 +701,12 @@ def inversion_forward_process_batched(model: PipelineWrapper, x0s: torch.Tensor,
 def inversion_reverse_process_batched(model: PipelineWrapper, xT: torch.Tensor, tstart: int, etas: float = 1.0,
                                       prompts=("",), neg_prompts: List[str] = [""],
                                       cfg_scales: Optional[List[float]] = None, zs: Optional[torch.Tensor] = None,
-                                      cutoff_points: Optional[List[float]] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+                                      cutoff_points: Optional[List[float]] = None, graph_lane: Optional[int] = None
+                                      ) -> Tuple[torch.Tensor, torch.Tensor]:
     """inversion_reverse_process (reference :147-323) for K clips at once, one tstart for all prompts and clips.
     xT: [K, N+1, C, H, W] (the xts of the forward process), zs: [K, n, C, H, W] (= zs[:, :tstart]).
+    graph_lane: which captured graph variant to replay (unet.GraphedForward: 1 = the lane has the machine to itself,
+    2 = rings / PDL sized for sharing the SMs with a forward-process grid on another stream); same bits either way.
     Returns (edited latents [K, C, H, W], zs)."""
     K = xT.shape[0]
     per_clip = _clip_prompts(list(prompts), K)
@@ -612,12 +724,12 @@ def inversion_reverse_process_batched(model: PipelineWrapper, xT: torch.Tensor, 
     sl = []
     for k in range(K):
         sl += [0] + [row_of[q] for q in per_clip[k]]
-    slot = torch.tensor(sl, dtype=torch.int32, device=model.device)
+    slot = _dev_i32(model, sl)
     cl_b = None if cl is None else cl.index_select(0, slot.long())
     xt = xT[:, tmax].to(torch.float32).contiguous().clone()                             # [K, C, H, W]
     zs = zs.contiguous()
     ts_cpu = sched.timesteps_cpu[-n:]
-    lane = 1 if (USE_CUDA_GRAPHS and xT.is_cuda) else 0
+    lane = (graph_lane if graph_lane is not None else 1) if (USE_CUDA_GRAPHS and xT.is_cuda) else 0
     x_in = torch.empty((K * rows, *xt.shape[1:]), device=model.device, dtype=torch.float32)
     for k_step in range(n):
         t = int(ts_cpu[k_step])

@@ -202,6 +202,41 @@ def _pc_state(m, spec, x0_dev, prompt):
     return st
 
 
+def ends_pass(m, spec, reps=3):
+    """The ends of the path timed on the device, reported beside the loop number as BASELINE.md §3 asks: log-mel STFT of
+    the clip's waveform (ae_stft_mel), VAE encode / decode (tcgen05 convs), HiFi-GAN vocoder (called twice per edit in
+    main_run.py:184-185).  Algorithmic FLOPs at 10.24 s from BASELINE.md §2 (scaled linearly with the clip length)."""
+    dev = m.device
+    T = spec["H"] * 4                                    # mel frames
+    scale = T / 1024.0
+    wav = (0.5 * torch.rand(1, T * 160, device=dev) - 0.25)
+    mel = torch.randn(1, 1, T, 64, device=dev) * 2.0 - 5.0
+    lat = torch.randn(1, 8, spec["H"], spec["W"], device=dev) * 0.5
+    stft = m.get_fn_STFT()
+
+    def timed(fn):
+        fn()
+        torch.cuda.synchronize()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(reps):
+            fn()
+        e.record()
+        torch.cuda.synchronize()
+        return s.elapsed_time(e) / reps
+    out = {}
+    for name, fn, gflop in (("stft_mel", lambda: stft.mel_spectrogram(wav), 2.2), ("vae_encode", lambda: m.vae_encode(mel), 345.0),
+                            ("vae_decode", lambda: m.vae_decode(lat), 636.0),
+                            ("vocoder", lambda: m.decode_to_mel(mel), 1030.0)):
+        ms = timed(fn)
+        out[name] = {"ms": round(ms, 3), "algorithmic_gflop": round(gflop * scale, 1),
+                     "tflops": round(gflop * scale / ms, 2)}
+    out["per_edit_ms"] = round(out["stft_mel"]["ms"] + out["vae_encode"]["ms"] + out["vae_decode"]["ms"] +
+                               2 * out["vocoder"]["ms"], 2)
+    out["what"] = "synthetic VAE / vocoder weights; one call each, CUDA events; vocoder runs twice per edit"
+    return out
+
+
 def gemm_event_pass(m, spec, cfg, B=2):
     """Time share and FLOP rate of the dominant kernel family (ae_gemm: tcgen05 GEMM / implicit conv + split-K reduce).
     The ae_gemm calls of one U-Net evaluation (batch B) are recorded, then replayed ALONE, back to back, inside one
@@ -362,8 +397,11 @@ def main():
     ap.add_argument("--forward-batch", type=int, default=int(os.environ.get("AEDIT_FORWARD_BATCH", "50")))
     ap.add_argument("--clips", type=int, default=1, help="clips per GPU per job (K > 1: multi-clip entry points, "
                     "B = K*(1+P) rows per U-Net launch; BASELINE configs[2] uses 4)")
+    ap.add_argument("--queue-group", type=int, default=4, help="clips per reverse launch of the extra throughput_queue "
+                    "measurement (0/1 = skip it)")
     ap.add_argument("--cpu-steps", type=int, default=0, help="CFG steps of the cpu_baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-ends", action="store_true", help="skip the STFT / VAE / vocoder timing")
     args = ap.parse_args()
     spec = CONFIGS[args.config]
     mode = spec.get("mode", "edit")
@@ -491,6 +529,31 @@ def main():
                     "d2h_bytes_per_step": e2e_out.numel() * 4},
             "gpu_launches": int(launches), "clocks": clocks}
 
+    # Serving-style throughput of the SAME workload with several clips in flight per GPU (N = 1 only): a queue of
+    # 2*Q clips edited with Q clips per reverse launch (B = 2Q rows) while the next group's forward process runs on the
+    # forward lane (inversion_utils.edit_clips_pipelined).  Reported beside `value` (one clip at a time), never instead.
+    if rank == 0 and world == 1 and mode == "edit" and K == 1 and args.queue_group > 1:
+        from audioeditingcode_b200.ddm_inversion import inversion_utils as IU
+        Q = args.queue_group
+        gq = torch.Generator().manual_seed(99)
+        q_host = [(0.5 * torch.randn(1, cfg.in_channels, spec["H"], spec["W"], generator=gq)).pin_memory()
+                  for _ in range(2 * Q)]
+        q_out = [torch.empty(1, cfg.in_channels, spec["H"], spec["W"]).pin_memory() for _ in range(2 * Q)]
+
+        def queue_job():
+            IU.edit_clips_pipelined(m, q_host, ["a recording of a dog barking"], ["a recording of a cat meowing"],
+                                    spec["tstart"], cfg_src=spec["cfg_src"], cfg_tar=spec["cfg_tar"],
+                                    num_inference_steps=spec["n_inv"], forward_batch=args.forward_batch, group=Q,
+                                    on_result=lambda i, w: q_out[i].copy_(w, non_blocking=True))
+            torch.cuda.synchronize()
+        queue_job()                                              # graph captures for the B = 2Q shapes
+        queue_job()
+        ms_q = timed_loop(queue_job, 1)
+        line["throughput_queue"] = {
+            "value": (spec["n_inv"] + spec["tstart"]) * 2 * Q / (ms_q / 1000.0), "unit": "steps/s",
+            "clips_in_flight": Q, "clips": 2 * Q, "ms_per_clip": ms_q / (2 * Q),
+            "what": "same workload, host-resident clips (H2D / D2H inside the timed region): groups of Q clips per "
+                    "reverse launch, the next group's forward process overlapped on the forward lane"}
     if rank == 0 and (mode != "edit" or K > 1):
         # other workloads: one evaluation shape dominates; report its GEMM-family rate only
         peaks = load_peaks()
@@ -553,6 +616,11 @@ def main():
                                                      "tflops": (fl2["conv"] + fl2["linear"]) / gp["gemm_ms"] / 1e9}},
                                              **per_chunk),
                             "job_tflops_all_kernels": job_flops * args.steps / (ms / 1000.0) / 1e12}
+        if world == 1 and not args.no_ends:
+            try:
+                line["ends"] = ends_pass(m, spec)
+            except Exception as ex:             # the loop numbers must not be lost to an ends problem
+                line["ends"] = {"error": repr(ex)[:200]}
         if not args.no_cpu_baseline and world == 1:
             oracle = CpuOracle(spec, cores)
             threads = pick_threads(cores, lambda: oracle.unet(oracle.xts[1][None], 1, "uncond"))

@@ -321,6 +321,11 @@ int ae_attention(const void* q, int64_t ld_q, int64_t q_batch_stride, const void
                  const float* key_bias, int64_t ld_bias, int B, int heads, int d, int Tq, int Tk, float scale, void* out,
                  int64_t ld_o, int64_t o_batch_stride, ae_stream stream);
 
+/* ae_attention dispatch: sequences with Tq, Tk >= 128, d <= 128 (multiple of 8), no kv_batch_map and 16-byte aligned
+ * strides run on the tcgen05 kernel (csrc/attn_tc.cu: S and the per-block P.V product in TMEM, Q / K / V by TMA, online
+ * softmax from tcgen05.ld); the rest on the mma.sync kernel.  ae_set_attention_tc(0) forces the mma.sync kernel (A/B). */
+void ae_set_attention_tc(int on);
+
 /* Same, with a workspace that lets the kernel split the KEYS of small grids over several CTAs (split-KV; the partial
  * accumulators are merged in split order by the last CTA of a query tile to arrive, so the result is deterministic).
  * workspace: ae_attention_workspace_bytes(B, heads, Tq, d) bytes, its first B*heads*ceil(Tq/64)*4 bytes ZERO-initialised

@@ -182,6 +182,11 @@ def load():
     _loaded["hifigan"] = importlib.import_module("audioldm.hifigan.models")
     _loaded["stft"] = importlib.import_module("audioldm.audio.stft")
     _loaded["audio_tools"] = importlib.import_module("audioldm.audio.tools")
+    for name in ("models", "pc_drift", "utils", "ddm_inversion", "ddm_inversion.inversion_utils",
+                 "ddm_inversion.ddim_inversion"):
+        mod = sys.modules.get(name)       # a same-named module from elsewhere (e.g. the dropin/ shims) must not shadow
+        if mod is not None and not str(getattr(mod, "__file__", "") or "").startswith(REF_CODE):
+            del sys.modules[name]
     _loaded["models"] = importlib.import_module("models")
     _bare_package("ddm_inversion", os.path.join(REF_CODE, "ddm_inversion"))
     _loaded["inversion_utils"] = importlib.import_module("ddm_inversion.inversion_utils")

@@ -25,13 +25,16 @@ pytestmark = [pytest.mark.refonly, pytest.mark.skipif(not ref_import.available()
 def _dropin(modname):
     import importlib
     saved = list(sys.path)
+    names = [k for k in list(sys.modules) if k in MODULES or k == "ddm_inversion"]
+    saved_mods = {k: sys.modules.pop(k) for k in names}   # the oracle harness may hold the REFERENCE modules under these names
     sys.path[:0] = [os.path.join(ROOT, "dropin"), ROOT]
     try:
-        for k in [k for k in sys.modules if k in MODULES or k == "ddm_inversion"]:
-            del sys.modules[k]           # the oracle harness may have imported the REFERENCE modules under these names
         return importlib.import_module(modname)
     finally:
         sys.path[:] = saved
+        for k in [k for k in list(sys.modules) if k in MODULES or k == "ddm_inversion"]:
+            del sys.modules[k]           # do not leave the shims registered under the reference's module names
+        sys.modules.update(saved_mods)
 
 
 @pytest.mark.parametrize("script", SCRIPTS)

@@ -503,6 +503,7 @@ def test_attention_split_kv(ops, d, heads, Tq, Tk, split):
     args = (heads, d, d ** -0.5, Tq, Tk, B, C, Tq * C, C, Tk * C, C, Tk * C)
     outs = []
     try:
+        ops.lib.ae_set_attention_tc(0)                          # this test is about the mma.sync kernel's key split
         for ns in (1, split, split):
             ops.lib.ae_set_attention_split(ns)
             o = torch.zeros(B * Tq, C, device="cuda", dtype=BF)
@@ -510,12 +511,58 @@ def test_attention_split_kv(ops, d, heads, Tq, Tk, split):
             outs.append(o)
     finally:
         ops.lib.ae_set_attention_split(0)
+        ops.lib.ae_set_attention_tc(1)
     assert torch.equal(outs[1], outs[2])                       # same call twice: same bits (and the counters were re-armed)
     qh, kh, vh = (t.float().view(B, -1, heads, d).transpose(1, 2) for t in (q, k, v))
     ref = (qh @ kh.transpose(-1, -2) * d ** -0.5).softmax(-1) @ vh
     ref = ref.transpose(1, 2).reshape(B * Tq, C)
     assert relerr(outs[1], ref) < 1e-2 and relerr(outs[0], ref) < 1e-2
     assert relerr(outs[1], outs[0]) < 4e-3                     # bf16 output rounding of slightly different fp32 values
+
+
+@pytest.mark.parametrize("B,d,heads,Tq,Tk,bias", [
+    (2, 48, 8, 1024, 1024, False),     # AudioLDM2-large level 1, reverse step (NT = 1, DP = 64)
+    (2, 64, 5, 1024, 1024, False),     # TANGO head dim
+    (1, 32, 4, 256, 256, False),
+    (2, 72, 8, 256, 256, False),       # DP = 128 (d padded 72 -> 80 by TMA zero fill), BKEYS = 64
+    (2, 120, 8, 128, 192, False),      # d = 120 -> 128, partial last key block
+    (3, 48, 8, 1000, 1000, False),     # ragged query tile and ragged key block
+    (2, 48, 4, 384, 333, True),        # additive key bias (+ ragged keys)
+    (40, 48, 8, 128, 128, False),      # 320 tiles -> NT = 2 (two query tiles per CTA)
+    (20, 80, 8, 256, 256, True),       # NT = 2, DP = 128, bias
+])
+def test_attention_tcgen05(ops, B, d, heads, Tq, Tk, bias):
+    """tcgen05 / TMEM / TMA attention (csrc/attn_tc.cu) vs a plain PyTorch fp32 softmax attention on the same operand-
+    rounded inputs, and vs the mma.sync kernel (ae_set_attention_tc(0)); deterministic (same call twice: same bits)."""
+    C = heads * d
+    q = rnd((B, Tq, 3 * C), 1, dtype=BF)                       # q | k | v packed like the fused qkv projection's output
+    kk = q if Tk == Tq else rnd((B, Tk, 3 * C), 2, dtype=BF)
+    kb = None
+    if bias:
+        kb = torch.zeros(B, Tk, device="cuda")
+        kb[:, Tk - 7:] = -10000.0
+        kb[0, 3] = -2.5
+    args = (heads, d, d ** -0.5, Tq, Tk, B, 3 * C, Tq * 3 * C, 3 * C, Tk * 3 * C, 3 * C, Tk * 3 * C)
+    outs = []
+    try:
+        for tc in (1, 1, 0):
+            ops.lib.ae_set_attention_tc(tc)
+            o = torch.zeros(B * Tq, C, device="cuda", dtype=BF)
+            ops.attention(q, kk[..., C:], kk[..., 2 * C:], o, *args, bias=kb)
+            outs.append(o)
+    finally:
+        ops.lib.ae_set_attention_tc(1)
+    assert torch.equal(outs[0], outs[1])
+    qh = q[..., :C].float().view(B, Tq, heads, d).transpose(1, 2)
+    kh = kk[..., C:2 * C].float().view(B, Tk, heads, d).transpose(1, 2)
+    vh = kk[..., 2 * C:].float().view(B, Tk, heads, d).transpose(1, 2)
+    sc = qh @ kh.transpose(-1, -2) * d ** -0.5
+    if kb is not None:
+        sc = sc + kb[:, None, None, :]
+    ref = (sc.softmax(-1) @ vh).transpose(1, 2).reshape(B * Tq, C)
+    e_tc, e_old = relerr(outs[0], ref), relerr(outs[2], ref)
+    print(f"B={B} d={d} T={Tq}/{Tk}: rel err tcgen05 {e_tc:.2e}  mma.sync {e_old:.2e}")
+    assert e_tc < 1e-2 and relerr(outs[0], outs[2]) < 1e-2
 
 
 def test_attention_cross_masked(ops):

@@ -397,3 +397,52 @@ def test_multi_clip_batched_matches_single_clip_calls():
         r_z, r_x, r_w = _rel(zs_b[k], zs.cpu()), _rel(xts_b[k], xts.cpu()), _rel(w_b[k:k + 1], w.cpu())
         print(f"clip {k}: batched vs single rel-L2 zs {r_z:.2e} xts {r_x:.2e} edit {r_w:.2e}")
         assert r_x < 1e-6 and r_z < 5e-3 and r_w < 3e-2
+
+
+def test_clip_queue_pipelined_matches_one_at_a_time():
+    """edit_clips_pipelined: (group=1) forward(i+1) enqueued ahead of reverse(i) on the two lanes == the drop-in functions
+    called one clip at a time, BIT FOR BIT; (group=2) batched groups with the next group's forward process overlapped
+    == the batched entry points run back to back on one stream, bit for bit."""
+    from audioeditingcode_b200.ddm_inversion import inversion_utils as IU
+    g = load_golden("loop_eps_single.npz")
+    N, ts, n = 10, 6, 4
+    m = _wrapper(N)
+    ys = {"": g["uncond"], "src": g["src"], "tgt": g["tgt"]}
+
+    class Txt:
+        def __call__(self, prompts, **kw):
+            return None, torch.cat([ys[p] for p in prompts]).cuda(), None
+    m.encode_text = Txt()
+    gen = torch.Generator().manual_seed(12)
+    clips = [(0.5 * torch.randn(1, 8, 16, 16, generator=gen)).cuda() for _ in range(n)]
+    noises = [torch.randn(N, 8, 16, 16, generator=gen).cuda() for _ in range(n)]
+    ref = []
+    for i in range(n):
+        _, zs, xts, _ = IU.inversion_forward_process(m, clips[i], etas=1.0, prompts=["src"], cfg_scales=[3.0],
+                                                     num_inference_steps=N, numerical_fix=True, forward_batch=4,
+                                                     reverse_hint=ts, noise=noises[i])
+        w, _ = IU.inversion_reverse_process(m, xT=xts, tstart=torch.tensor([ts], dtype=torch.int), etas=1.0,
+                                            prompts=["tgt"], neg_prompts=[""], cfg_scales=[5.0], zs=zs[:ts])
+        ref.append(w.clone())
+    got = IU.edit_clips_pipelined(m, clips, ["src"], ["tgt"], ts, cfg_src=3.0, cfg_tar=5.0, num_inference_steps=N,
+                                  forward_batch=4, noises=noises)
+    torch.cuda.synchronize()
+    for a, b in zip(got, ref):
+        assert torch.equal(a, b)
+    # groups of 2
+    x = torch.cat(clips[:2]), torch.cat(clips[2:])
+    refb = []
+    for k, xs in enumerate(x):
+        _, zs, xts = IU.inversion_forward_process_batched(m, xs, etas=1.0, prompts=["src"], cfg_scales=[3.0],
+                                                          num_inference_steps=N, forward_batch=4,
+                                                          noise=torch.stack(noises[2 * k:2 * k + 2]))
+        w, _ = IU.inversion_reverse_process_batched(m, xts, ts, etas=1.0, prompts=["tgt"], neg_prompts=[""],
+                                                    cfg_scales=[5.0], zs=zs[:, :ts])
+        refb += [w[0:1].clone(), w[1:2].clone()]
+    seen = []
+    gotb = IU.edit_clips_pipelined(m, clips, ["src"], ["tgt"], ts, cfg_src=3.0, cfg_tar=5.0, num_inference_steps=N,
+                                   forward_batch=4, noises=noises, group=2, on_result=lambda i, w: seen.append(i))
+    torch.cuda.synchronize()
+    assert seen == [0, 1, 2, 3]
+    for a, b in zip(gotb, refb):
+        assert torch.equal(a, b)

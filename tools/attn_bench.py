@@ -1,4 +1,7 @@
-"""Isolated timing of the attention kernel (CUDA graph of 20 back-to-back launches) per split-KV setting."""
+"""Isolated timing of the attention kernels (CUDA graph of 20 back-to-back launches): the tcgen05 / TMEM / TMA kernel
+(csrc/attn_tc.cu) vs the mma.sync kernel (csrc/attn_kernels.cu, ae_set_attention_tc(0)) on the self-attention shapes of
+the benchmarked U-Nets (AudioLDM2-large levels 1-2, TANGO level 0-1, the 30 s clip) at reverse-step and forward-chunk
+batch sizes."""
 import os
 import sys
 
@@ -6,25 +9,29 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from audioeditingcode_b200.ops import CudaOps  # noqa: E402
+from audioeditingcode_b200._lib import operand_torch_dtype  # noqa: E402
 
 ops = CudaOps()
-from audioeditingcode_b200._lib import operand_torch_dtype
-BF = operand_torch_dtype()        # the library build's 16-bit operand type (fp16 default, bf16 with AEDIT_OPERANDS=bf16)
-for (B, heads, d, T) in [(2, 8, 48, 1024), (2, 8, 72, 256), (2, 8, 120, 64), (100, 8, 48, 1024)]:
+BF = operand_torch_dtype()
+SHAPES = [(2, 8, 48, 1024), (8, 8, 48, 1024), (100, 8, 48, 1024), (2, 8, 72, 256), (100, 8, 72, 256), (2, 5, 64, 4096),
+          (20, 5, 64, 4096), (100, 10, 64, 1024), (2, 8, 32, 3072)]
+for (B, heads, d, T) in SHAPES:
     C = heads * d
     qkv = torch.randn(B * T, 3 * C, device="cuda").to(BF)
     out = torch.empty(B * T, C, device="cuda", dtype=BF)
-    for ns in ([1, 2, 3, 4, 8] if B == 2 else [1]):
-        ops.lib.ae_set_attention_split(ns)
+    res = {}
+    for tc in (1, 0):
+        ops.lib.ae_set_attention_tc(tc)
 
         def run():
             ops.attention(qkv, qkv[:, C:], qkv[:, 2 * C:], out, heads, d, d ** -0.5, T, T, B, 3 * C, T * 3 * C, 3 * C,
                           T * 3 * C, 3 * C, T * 3 * C)
         run()
         torch.cuda.synchronize()
+        n = 20 if B * T <= 32768 else 4
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
-            for _ in range(20):
+            for _ in range(n):
                 run()
         g.replay()
         torch.cuda.synchronize()
@@ -34,7 +41,8 @@ for (B, heads, d, T) in [(2, 8, 48, 1024), (2, 8, 72, 256), (2, 8, 120, 64), (10
             g.replay()
         e.record()
         torch.cuda.synchronize()
-        us = s.elapsed_time(e) * 1e3 / 100
-        fl = 4.0 * B * heads * T * T * d
-        print(f"attention B={B} heads={heads} d={d} T={T} split={ns}: {us:8.2f} us  {fl / us / 1e6:7.1f} TFLOP/s", flush=True)
-ops.lib.ae_set_attention_split(1)
+        res[tc] = s.elapsed_time(e) * 1e3 / (5 * n)
+    fl = 4.0 * B * heads * T * T * d
+    print(f"attention B={B:3d} heads={heads:2d} d={d:3d} T={T:4d}: tcgen05 {res[1]:9.2f} us {fl / res[1] / 1e6:7.1f} TFLOP/s | "
+          f"mma.sync {res[0]:9.2f} us {fl / res[0] / 1e6:7.1f} TFLOP/s | speed-up {res[0] / res[1]:.2f}x", flush=True)
+ops.lib.ae_set_attention_tc(1)
