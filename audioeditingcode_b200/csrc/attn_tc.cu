@@ -18,10 +18,9 @@
 //                  be rescaled — the reference maximum m_ref of a row is raised only when the block maximum exceeds it by
 //                  more than 8 (in log2 units; P then stays <= 256, exact enough in fp16 / bf16 with fp32 accumulation),
 //                  in which case the warp rescales its O rows in place (tcgen05.ld / tcgen05.st) before the next P.V.
-// NT = 2 / 4 query tiles per CTA (8 / 16 softmax warps = 2 / 4 per SM sub-partition, 64-key blocks so a row of S fits the
-// register budget) when the grid fills the machine anyway: MUFU, TMEM reads and FMA work only overlap ACROSS warps, and the
-// tiles share each K / V block; NT = 1 (double-buffered S, 128-key blocks) for small grids (reverse process at batch 2).
-// A row's arithmetic depends on the key-block size only through fp32 summation order.
+// NT = 2 query tiles per CTA (8 softmax warps = 2 per SM sub-partition) when the grid fills the machine anyway: MUFU, TMEM
+// reads and FMA work only overlap ACROSS warps, and the tiles share each K / V block; NT = 1 (double-buffered S) for small
+// grids (reverse process at batch 2).  A row's arithmetic does not depend on NT: same bits.
 #include <cuda.h>
 
 #include "common.cuh"
@@ -384,10 +383,13 @@ int attention_tc_try(const void* q, int64_t ld_q, int64_t q_bs, const void* k, i
     return 0;
   const int DP = d <= 64 ? 64 : 128;
   const long long tiles = (long long)B * heads * ((Tq + kQT - 1) / kQT);
-  // query tiles per CTA: as many softmax warps per SM sub-partition as the grid affords (the kernel is bound by the
-  // softmax warps: MUFU, TMEM reads and FMA work only overlap ACROSS warps); small grids keep one tile per CTA
-  const int NT = DP == 64 ? (tiles >= 6 * 148 ? 4 : (tiles >= 2 * 148 ? 2 : 1)) : (tiles >= 2 * 148 ? 2 : 1);
-  const int BKEYS = (DP == 64 && NT == 1) ? 128 : 64;
+  // Two query tiles per CTA (two softmax warps per SM sub-partition, shared K / V blocks) when the grid fills the machine
+  // anyway, one (double-buffered S) for small grids.  Measured and rejected (profiles/r02_attn_bench_v4.log): four tiles
+  // per CTA with 64-key blocks (16 softmax warps under a 96-register cap) — 6-28 % SLOWER: the kernel is bound by the
+  // per-block barrier round trips (S ready -> softmax -> P ready -> P.V -> next S), which twice as many, half as large
+  // key blocks double.
+  const int NT = tiles >= 2 * 148 ? 2 : 1;
+  const int BKEYS = DP == 64 ? 128 : 64;
   CUtensorMap tq, tk, tv;
   auto mk = [&](CUtensorMap* tm, const void* base, int64_t ld, int64_t bs, int T, int nb, int rows) {
     const uint64_t dims[4] = {(uint64_t)d, (uint64_t)heads, (uint64_t)T, (uint64_t)nb};
@@ -413,13 +415,10 @@ int attention_tc_try(const void* q, int64_t ld_q, int64_t q_bs, const void* k, i
   a.out = reinterpret_cast<op_t*>(out);
   a.ld_o = ld_o;
   a.bs_o = o_bs;
-  if (DP == 64) {
-    if (NT == 4) *rc = launch_tc<64, 64, 4>(tq, tk, tv, a, B, heads, st);
-    else if (NT == 2) *rc = launch_tc<64, 64, 2>(tq, tk, tv, a, B, heads, st);
-    else *rc = launch_tc<64, 128, 1>(tq, tk, tv, a, B, heads, st);
-  } else {
+  if (DP == 64)
+    *rc = NT == 2 ? launch_tc<64, 128, 2>(tq, tk, tv, a, B, heads, st) : launch_tc<64, 128, 1>(tq, tk, tv, a, B, heads, st);
+  else
     *rc = NT == 2 ? launch_tc<128, 64, 2>(tq, tk, tv, a, B, heads, st) : launch_tc<128, 64, 1>(tq, tk, tv, a, B, heads, st);
-  }
   return 1;
 }
 

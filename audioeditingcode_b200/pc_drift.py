@@ -112,13 +112,25 @@ def get_eigenvectors(ldm_stable, xt: torch.Tensor, text_emb: PromptEmbeddings, u
                      latents: torch.Tensor, mask: torch.Tensor, t: torch.Tensor, x0_pred: torch.Tensor,
                      pc_mode: PCStreamChoice = PCStreamChoice.BOTH, const: float = 1e-3, cfg_tar: float = 3,
                      iters: int = 50, double_precision: bool = False, eta: float = 1, n_ev: int = 1, group=None,
-                     init_eigvecs: Optional[torch.Tensor] = None
+                     init_eigvecs: Optional[torch.Tensor] = None, fd_const: Optional[float] = None
                      ) -> Tuple[torch.Tensor, torch.Tensor, List[torch.Tensor], List[torch.Tensor],
                                 Dict[int, torch.Tensor], Dict[int, torch.Tensor]]:
     """Subspace (power) iteration on the Jacobian of the posterior mean (pc_drift.py:96-198).
     `group` (extension; None = the reference's single-process behaviour): process group over which the n_ev directions
     are sharded, see the module docstring.  `init_eigvecs` (extension): explicit start `[n_ev, C, H, W]` used instead of
-    the `randn_like(xt) * mask * const` draw of :130 (seed-independent comparisons against the reference)."""
+    the `randn_like(xt) * mask * const` draw of :130 (seed-independent comparisons against the reference).
+    `fd_const` (extension; default None = `const`, the reference's behaviour; env AEDIT_PC_FD_CONST): the step of the
+    finite difference actually taken.  The iteration only uses Ab / const (direction and eigenvalue), which is independent
+    of the step to first order, but the reference default 1e-3 spreads a perturbation of 1e-3 / sqrt(D) per element — below
+    the resolution of 16-bit tensor-core operands (it sits at the rounding level of the reference's own fp32 evaluation,
+    DESIGN.md §2).  A step of ~0.3-1 resolves the Jacobian-vector products through the real U-Net
+    (tests/test_gpu_pc_drift.py::test_unet_jvp_resolves_with_fd_const)."""
+    import os as _os
+    if fd_const is None and _os.environ.get("AEDIT_PC_FD_CONST"):
+        fd_const = float(_os.environ["AEDIT_PC_FD_CONST"])
+    const_ret = const
+    if fd_const is not None:
+        const = float(fd_const)
     from . import parallel as _par
     lib = _lib.load()
     dev = ldm_stable.device
@@ -174,7 +186,7 @@ def get_eigenvectors(ldm_stable, xt: torch.Tensor, text_emb: PromptEmbeddings, u
             if not (i % 10) and i > 15:
                 # the reference stores the tensor it then scales IN PLACE by `const` (:188-193): the stored
                 # intermediate directions carry that factor
-                interm_eigvecs[i] = new_scaled
+                interm_eigvecs[i] = new_scaled if const == const_ret else new_scaled * (const_ret / const)
                 interm_eigvals[i] = norm_of_Ab / const * sigma2
             prev, cur = cur, prev
             scaled = new_scaled

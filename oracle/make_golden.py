@@ -443,6 +443,43 @@ def golden_pc_drift():
     save("pc_drift.npz", n_steps=N, shape=np.asarray([C_, H_, W_]), **out)
 
 
+def golden_pc_unet():
+    """Reference get_eigenvectors (unmodified, const = 1e-3, fp32 CPU) through the vendored tiny U-Net: the finite
+    differences it forms per iteration (perturbation in, posterior mean out) — the yardstick for the device path's
+    Jacobian-vector products through the real network (tests/test_gpu_pc_drift.py::test_unet_jvp_resolves_with_fd_const)."""
+    ref = ref_import.load()
+    PC = ref.pc_drift
+    cfg = C.preset("tiny-audioldm")
+    w = U.synthetic_weights(cfg, seed=0)
+    N, n_ev, iters = 20, 2, 6
+    model = make_fake_wrapper(ref, cfg, w, N)
+    g = torch.Generator().manual_seed(81)
+    xt = torch.randn(1, 8, 16, 16, generator=g)
+    lat = torch.randn(1, 8, 16, 16, generator=g)
+    mask = torch.ones(1, 8, 16, 16)
+    t = model.model.scheduler.timesteps[8]
+    unc = PC.PromptEmbeddings(None, prompt_vector(""), None)
+    txt = PC.PromptEmbeddings(None, prompt_vector("a dog barking"), None)
+    with torch.no_grad():
+        _, x0_pred = PC.forward_directional(model, xt, t, lat, unc, txt, 3.0, eta=1)
+    rec = []
+    orig = PC.forward_directional
+
+    def spy(*a, **k):
+        r = orig(*a, **k)
+        rec.append((k["eigvecs"].clone(), r[1].clone()))
+        return r
+    PC.forward_directional = spy
+    try:
+        torch.manual_seed(82)
+        PC.get_eigenvectors(model, xt, txt, unc, lat, mask, t, x0_pred, PC.PCStreamChoice.BOTH, 1e-3, 3.0, iters, False, 1,
+                            n_ev)
+    finally:
+        PC.forward_directional = orig
+    save("pc_unet.npz", n_steps=N, t=int(t), xt=xt, lat=lat, x0_pred=x0_pred, uncond=prompt_vector(""),
+         cond=prompt_vector("a dog barking"), scaled_in=torch.stack([r[0] for r in rec]), x0p=torch.stack([r[1] for r in rec]))
+
+
 def golden_sdedit():
     """SDEdit flow of code/main_run_sdedit.py:78-100 (pre-drawn latents, add_noise at timesteps[skip], forward_directional
     loop), reference pc_drift.forward_directional unmodified on the fake AudioLDM wrapper (vendored UNetModel); the
@@ -477,6 +514,8 @@ if __name__ == "__main__":
         golden_pc_drift()
     if what in ("all", "sdedit"):
         golden_sdedit()
+    if what in ("all", "pcunet"):
+        golden_pc_unet()
     if what in ("all", "ddim"):
         golden_ddim()
     if what in ("all", "loops"):

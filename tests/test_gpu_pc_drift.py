@@ -220,3 +220,51 @@ def test_sdedit_flow_vs_reference_golden():
     r = ((xt.cpu() - g["w_edit"]).norm() / g["w_edit"].norm()).item()
     print(f"sdedit {tstart} steps cfg {float(g['cfg_tar'])}: rel-L2 vs reference {r:.2e}")
     assert r < 5e-2
+
+
+def test_unet_jvp_resolves_with_fd_const():
+    """Jacobian-vector products THROUGH THE REAL (tiny) U-Net on the CUDA path.  Yardstick: the finite differences the
+    unmodified reference forms at its default const = 1e-3 in fp32 on the CPU (vendored UNetModel, golden pc_unet.npz:
+    perturbation in, posterior mean out, for every iteration of its get_eigenvectors run).  The device path evaluates the
+    same directions with a finite-difference step `fd_const` that 16-bit tensor-core operands can resolve and must
+    reproduce the reference's Ab / const (direction and length); at const = 1e-3 itself the perturbation
+    (1e-3 / sqrt(D) per element) is below operand resolution, which is also asserted, so the limitation stays visible."""
+    from oracle import unet_torch as U
+    from audioeditingcode_b200 import models, pc_drift as PC, unet_config as UC
+    g = load_golden("pc_unet.npz")
+    N = int(g["n_steps"])
+    cfg = UC.preset("tiny-audioldm")
+    m = models.load_model("synthetic/audioldm-tiny", torch.device("cuda"), N, weights=U.synthetic_weights(cfg, seed=0),
+                          config=cfg)
+    unc = PC.PromptEmbeddings(None, g["uncond"].cuda(), None)
+    txt = PC.PromptEmbeddings(None, g["cond"].cuda(), None)
+    t = torch.tensor(int(g["t"]))
+    xt, lat = g["xt"].cuda(), g["lat"].cuda()
+    _, x0_ref = PC.forward_directional(m, xt, t, lat, unc, txt, 3.0, eta=1)
+    assert ((x0_ref.cpu() - g["x0_pred"]).norm() / g["x0_pred"].norm()).item() < 1e-2
+    n_ev = g["scaled_in"].shape[1]
+    res = {}
+    for step in (1e-3, 0.05, 0.2, 0.5, 1.0):
+        cos_min, ratio = 1.0, []
+        for i in range(1, g["scaled_in"].shape[0]):                  # iteration 0 starts from white noise; skip it
+            v_unit = (g["scaled_in"][i] / 1e-3).cuda()               # the reference's unit directions of this iteration
+            ab_ref = (g["x0p"][i] - g["x0_pred"]) / 1e-3              # its finite difference per unit step (fp32, CPU)
+            _, x0p = PC.forward_directional(m, xt.expand(n_ev, -1, -1, -1), t, lat, unc, txt, 3.0, eta=1,
+                                            eigvecs=v_unit * step, amount=1)
+            ab = ((x0p - x0_ref) / step).cpu()
+            for k in range(n_ev):
+                a, b = ab[k].reshape(-1), ab_ref[k].reshape(-1)
+                cos_min = min(cos_min, float(a @ b / (a.norm() * b.norm())))
+                ratio.append(float(a.norm() / b.norm()))
+        res[step] = (cos_min, min(ratio), max(ratio))
+        print(f"fd step {step}: min cos(Ab_ours, Ab_reference) {cos_min:.4f}, |Ab| ratio {min(ratio):.3f}..{max(ratio):.3f}")
+    # a resolvable step reproduces the reference's finite differences (which carry ~3 % rounding noise of their own at
+    # const = 1e-3 in fp32; the larger step adds second-order terms of the network): direction and length
+    best = max(res[s][0] for s in (0.2, 0.5, 1.0))
+    assert best > 0.9 and res[0.5][0] > 0.9 and 0.9 < res[0.5][1] and res[0.5][2] < 1.1
+    assert res[1e-3][0] < 0.5                  # the reference's own step is NOT resolvable through 16-bit operands
+    # and get_eigenvectors runs end to end with it
+    ev, eigval, in_corr, in_norm, _, _ = PC.get_eigenvectors(m, xt, txt, unc, lat, torch.ones_like(xt), t, x0_ref,
+                                                            PC.PCStreamChoice.BOTH, 1e-3, 3.0, 8, False, 1, n_ev, fd_const=0.5)
+    E = ev.reshape(n_ev, -1)
+    assert (E @ E.T - torch.eye(n_ev, device="cuda")).abs().max().item() < 1e-5 and torch.isfinite(eigval).all()
