@@ -42,7 +42,7 @@ struct AttnTcArgs {
   long long ld_o, bs_o;
 };
 
-template <int DP, int BKEYS, int NT>
+template <int DP, int BKEYS, int NT, int SP>
 struct TcCfg {
   static constexpr int kStages = 2;
   static constexpr int kDBlocks = DP / 64;                 // 64-column d blocks (one TMA box each)
@@ -54,9 +54,10 @@ struct TcCfg {
   static constexpr int kOffV = kOffK + kStages * kKVBlockBytes;
   static constexpr int kOffP = kOffV + kStages * kKVBlockBytes;
   static constexpr int kOffBias = kOffP + NT * kPTileBytes;
-  static constexpr int kOffBar = kOffBias + NT * 4 * BKEYS * 4;
+  static constexpr int kOffX = kOffBias + NT * 4 * BKEYS * 4;        // row-statistics exchange between the SP column halves
+  static constexpr int kOffBar = kOffX + NT * 3 * 2 * kQT * 4;
   static constexpr int kTotal = kOffBar + 256 + 1024;      // + manual 1024-byte alignment slack
-  static constexpr int kThreads = (4 * NT + 2) * 32;
+  static constexpr int kThreads = (4 * NT * SP + 2) * 32;
   static constexpr uint32_t kTmemCols = 512;
   static_assert(NT * BKEYS <= 256 && (NT == 1 ? 2 * BKEYS <= 256 : true) && NT * DP <= 256, "TMEM column plan");
   static constexpr int kColS(int buf) { return buf * BKEYS; }    // S tiles (NT = 1: two buffers) in columns [0, 256)
@@ -69,11 +70,11 @@ __device__ __forceinline__ float ex2f(float x) {
   return y;
 }
 
-template <int DP, int BKEYS, int NT>
-__global__ void __launch_bounds__(TcCfg<DP, BKEYS, NT>::kThreads, 1)
+template <int DP, int BKEYS, int NT, int SP>
+__global__ void __launch_bounds__(TcCfg<DP, BKEYS, NT, SP>::kThreads, 1)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                const __grid_constant__ CUtensorMap tmV, AttnTcArgs a) {
-  using C = TcCfg<DP, BKEYS, NT>;
+  using C = TcCfg<DP, BKEYS, NT, SP>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kOffBar);
@@ -88,7 +89,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int head = blockIdx.y, b = blockIdx.z;
   const int q0 = blockIdx.x * (kQT * NT);
-  constexpr int kSoftmaxWarps = 4 * NT;
+  constexpr int kSoftmaxWarps = 4 * NT * SP;
 
   if (threadIdx.x == 0) {
     ptx::mbar_init(q_full, 1);
@@ -98,7 +99,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     }
     for (int i = 0; i < 4; ++i) {
       ptx::mbar_init(s_full + i, 1);
-      ptx::mbar_init(p_full + i, kQT);
+      ptx::mbar_init(p_full + i, kQT * SP);
       ptx::mbar_init(o_full + i, 1);
     }
     ptx::fence_mbar_init();
@@ -207,14 +208,24 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     }
   } else {
     // ================================================================= softmax warps (thread = query row)
-    const int t = warp >> 2;                                // tile
+    // SP = 2: a query row is shared by TWO threads (warps w and w + 4 of the tile own the same 32 TMEM lanes), each
+    // handling half of the key columns of every block and half of the output columns: the per-block critical path of a
+    // row (TMEM read -> max -> exp2 -> pack -> store) halves, at the price of one maximum exchange per block.
+    const int t = warp / (4 * SP);                          // tile
+    const int half = (warp >> 2) % SP;                      // column half owned by this warp
     const int row = (warp & 3) * 32 + lane;                 // TMEM lane / row of the tile
     const int q = q0 + t * kQT + row;
+    constexpr int KC = BKEYS / SP;                          // key columns per thread and block
     const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16);
-    float* sbias = reinterpret_cast<float*>(smem + C::kOffBias) + warp * BKEYS;      // this warp's private copy
+    float* sbias = reinterpret_cast<float*>(smem + C::kOffBias) + (t * 4 * SP + (warp & 3) * SP + half) * KC;  // per warp
+    float* xch = reinterpret_cast<float*>(smem + C::kOffX) + t * (3 * 2 * kQT);       // [2 parities + final][2 halves][128]
     uint8_t* p_row = smem + C::kOffP + t * C::kPTileBytes + row * 128;
     const int kvb = a.kv_map ? a.kv_map[b] : b;
     const float* bias_row = a.key_bias ? a.key_bias + (long long)kvb * a.ld_bias : nullptr;
+    const int oc0 = half * (a.d16 / SP), oc1 = oc0 + a.d16 / SP;                      // output columns of this thread
+    auto tile_sync = [&]() {
+      if (SP > 1) asm volatile("bar.sync %0, %1;" ::"r"(1 + t), "r"(kQT * SP) : "memory");
+    };
     float m_ref = -1.0e30f, l_run = 0.f;       // m_ref: the maximum the row's P values / O accumulator refer to (log2 units)
     constexpr float kLog2e = 1.4426950408889634f;
     constexpr float kRescaleGap = 8.0f;        // raise m_ref only when a block maximum exceeds it by more than 2^8
@@ -225,8 +236,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       const uint32_t s_addr = lane_addr + C::kColS(sbuf);
       if (a.need_mask) {                                    // additive key bias / out-of-range keys of this block
         __syncwarp();
-        for (int i = lane; i < BKEYS; i += 32) {
-          const int key = j * BKEYS + i;
+        for (int i = lane; i < KC; i += 32) {
+          const int key = j * BKEYS + half * KC + i;
           sbias[i] = key < a.Tk ? (bias_row ? bias_row[key] * kLog2e : 0.f) : -1.0e30f;
         }
         __syncwarp();
@@ -234,24 +245,31 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       ptx::mbar_wait(s_full + ((NT == 1) ? (j & 1) : t), (NT == 1) ? ((j >> 1) & 1) : (j & 1));
       ptx::tcgen05_fence_after();
       // ---- the S row, read from TMEM exactly once
-      uint32_t v[BKEYS];
+      uint32_t v[KC];
 #pragma unroll
-      for (int c = 0; c < BKEYS / 32; ++c) ptx::tmem_ld_32x32b_x32(s_addr + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&v[c * 32]));
+      for (int c = 0; c < KC / 32; ++c)
+        ptx::tmem_ld_32x32b_x32(s_addr + half * KC + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&v[c * 32]));
       ptx::tmem_ld_wait();
       float mx4[4] = {-1.0e30f, -1.0e30f, -1.0e30f, -1.0e30f};     // four independent chains (one warp per sub-partition: ILP)
       if (a.need_mask) {
 #pragma unroll
-        for (int i = 0; i < BKEYS; ++i) {
+        for (int i = 0; i < KC; ++i) {
           const float x = fmaf(__uint_as_float(v[i]), a.scale_log2, sbias[i]);
           v[i] = __float_as_uint(x);
           mx4[i & 3] = fmaxf(mx4[i & 3], x);
         }
       } else {
 #pragma unroll
-        for (int i = 0; i < BKEYS; ++i) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(v[i]));
+        for (int i = 0; i < KC; ++i) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(v[i]));
       }
       float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
       if (!a.need_mask) mx *= a.scale_log2;                 // scale > 0: max commutes with the scaling
+      if (SP > 1) {                                         // block maximum of the whole row: exchange the two halves
+        float* x2 = xch + (j & 1) * (2 * kQT);
+        x2[half * kQT + row] = mx;
+        tile_sync();
+        mx = fmaxf(mx, x2[(half ^ 1) * kQT + row]);
+      }
       // ---- reference maximum: first block sets it; later blocks raise it (and rescale O, l) only past the gap
       if (j == 0) {
         m_ref = mx;
@@ -263,7 +281,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
           const float m_new = raise ? mx : m_ref;
           const float alpha = ex2f(m_ref - m_new);
 #pragma unroll 1
-          for (int c = 0; c < a.d16; c += 8) {              // rare path: 8 columns at a time keeps the register peak low
+          for (int c = oc0; c < oc1; c += 8) {              // rare path: 8 columns at a time keeps the register peak low
             uint32_t o[8];
             ptx::tmem_ld_32x32b_x8(lane_addr + C::kColO(t) + c, o);
             ptx::tmem_ld_wait();
@@ -285,16 +303,17 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       }
       float ls4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-      for (int c8 = 0; c8 < BKEYS / 8; ++c8) {
+      for (int c8l = 0; c8l < KC / 8; ++c8l) {
+        const int c8 = half * (KC / 8) + c8l;               // 16-byte chunk of the row's BKEYS keys
         float pv[8];
         if (a.need_mask) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) pv[i] = ex2f(__uint_as_float(v[c8 * 8 + i]) - m_ref);
+          for (int i = 0; i < 8; ++i) pv[i] = ex2f(__uint_as_float(v[c8l * 8 + i]) - m_ref);
         } else {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) pv[i] = ex2f(fmaf(__uint_as_float(v[c8 * 8 + i]), a.scale_log2, -m_ref));
+          for (int i = 0; i < 8; ++i) pv[i] = ex2f(fmaf(__uint_as_float(v[c8l * 8 + i]), a.scale_log2, -m_ref));
         }
-        ls4[c8 & 3] += ((pv[0] + pv[1]) + (pv[2] + pv[3])) + ((pv[4] + pv[5]) + (pv[6] + pv[7]));
+        ls4[c8l & 3] += ((pv[0] + pv[1]) + (pv[2] + pv[3])) + ((pv[4] + pv[5]) + (pv[6] + pv[7]));
         op2_t h0 = ff2op2(pv[0], pv[1]), h1 = ff2op2(pv[2], pv[3]), h2 = ff2op2(pv[4], pv[5]), h3 = ff2op2(pv[6], pv[7]);
         uint4 pk;
         pk.x = *reinterpret_cast<uint32_t*>(&h0);
@@ -309,35 +328,33 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       ptx::tcgen05_fence_before();            // this thread's TMEM accesses (S read, O rescale) are complete
       ptx::mbar_arrive(p_full + t);
     }
-    // ---- normalise and store
+    // ---- normalise and store (this thread's output columns)
+    if (SP > 1) {                                           // row sum = the two halves' partial sums (same m_ref)
+      float* x2 = xch + 2 * (2 * kQT);
+      x2[half * kQT + row] = l_run;
+      tile_sync();
+      l_run += x2[(half ^ 1) * kQT + row];
+    }
     ptx::mbar_wait(o_full + t, (nblk - 1) & 1);
     ptx::tcgen05_fence_after();
     const float inv = l_run > 0.f ? 1.0f / l_run : 0.f;
     op_t* dst = a.out + (long long)b * a.bs_o + (long long)q * a.ld_o + (long long)head * a.d;
+#pragma unroll 1
+    for (int c = oc0; c < oc1; c += 8) {
+      uint32_t o[8];
+      ptx::tmem_ld_32x32b_x8(lane_addr + C::kColO(t) + c, o);
+      ptx::tmem_ld_wait();
+      if (q < a.Tq && c < a.d) {
+        float f[8];
 #pragma unroll
-    for (int c = 0; c < DP / 32; ++c) {
-      if (c * 32 < a.d16) {
-        uint32_t o[32];
-        ptx::tmem_ld_32x32b_x32(lane_addr + C::kColO(t) + c * 32, o);
-        ptx::tmem_ld_wait();
-        if (q < a.Tq) {
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const int col = c * 32 + g * 8;
-            if (col < a.d) {
-              float f[8];
-#pragma unroll
-              for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(o[g * 8 + i]) * inv;
-              op2_t h0 = ff2op2(f[0], f[1]), h1 = ff2op2(f[2], f[3]), h2 = ff2op2(f[4], f[5]), h3 = ff2op2(f[6], f[7]);
-              uint4 pk;
-              pk.x = *reinterpret_cast<uint32_t*>(&h0);
-              pk.y = *reinterpret_cast<uint32_t*>(&h1);
-              pk.z = *reinterpret_cast<uint32_t*>(&h2);
-              pk.w = *reinterpret_cast<uint32_t*>(&h3);
-              *reinterpret_cast<uint4*>(dst + col) = pk;
-            }
-          }
-        }
+        for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(o[i]) * inv;
+        op2_t h0 = ff2op2(f[0], f[1]), h1 = ff2op2(f[2], f[3]), h2 = ff2op2(f[4], f[5]), h3 = ff2op2(f[6], f[7]);
+        uint4 pk;
+        pk.x = *reinterpret_cast<uint32_t*>(&h0);
+        pk.y = *reinterpret_cast<uint32_t*>(&h1);
+        pk.z = *reinterpret_cast<uint32_t*>(&h2);
+        pk.w = *reinterpret_cast<uint32_t*>(&h3);
+        *reinterpret_cast<uint4*>(dst + c) = pk;
       }
     }
     ptx::tcgen05_fence_before();
@@ -349,18 +366,18 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   }
 }
 
-template <int DP, int BKEYS, int NT>
+template <int DP, int BKEYS, int NT, int SP>
 int launch_tc(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnTcArgs& a, int B, int heads,
               cudaStream_t st) {
-  using C = TcCfg<DP, BKEYS, NT>;
+  using C = TcCfg<DP, BKEYS, NT, SP>;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(attn_tc_kernel<DP, BKEYS, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kTotal);
+    cudaError_t e = cudaFuncSetAttribute(attn_tc_kernel<DP, BKEYS, NT, SP>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kTotal);
     if (e != cudaSuccess) return fail(AE_ECUDA, "attn_tc smem attribute (%d bytes): %s", C::kTotal, cudaGetErrorString(e));
     attr_set = true;
   }
   dim3 grid((a.Tq + kQT * NT - 1) / (kQT * NT), heads, B);
-  launch_kernel_family(8, attn_tc_kernel<DP, BKEYS, NT>, grid, dim3(C::kThreads), (size_t)C::kTotal, st, tq, tk, tv, a);
+  launch_kernel_family(8, attn_tc_kernel<DP, BKEYS, NT, SP>, grid, dim3(C::kThreads), (size_t)C::kTotal, st, tq, tk, tv, a);
   return launched("ae_attention(tcgen05)");
 }
 
@@ -388,7 +405,11 @@ int attention_tc_try(const void* q, int64_t ld_q, int64_t q_bs, const void* k, i
   // per CTA with 64-key blocks (16 softmax warps under a 96-register cap) — 6-28 % SLOWER: the kernel is bound by the
   // per-block barrier round trips (S ready -> softmax -> P ready -> P.V -> next S), which twice as many, half as large
   // key blocks double.
-  const int NT = tiles >= 2 * 148 ? 2 : 1;
+  // g_attn_tc: 1 auto; 2 / 3 / 4 force (NT 1, SP 2) / (NT 2, SP 1) / (NT 1, SP 1) — A/B measurements
+  int NT = tiles >= 2 * 148 ? 2 : 1, SP = NT == 1 ? 2 : 1;
+  if (g_attn_tc == 2) { NT = 1; SP = 2; }
+  if (g_attn_tc == 3) { NT = 2; SP = 1; }
+  if (g_attn_tc == 4) { NT = 1; SP = 1; }
   const int BKEYS = DP == 64 ? 128 : 64;
   CUtensorMap tq, tk, tv;
   auto mk = [&](CUtensorMap* tm, const void* base, int64_t ld, int64_t bs, int T, int nb, int rows) {
@@ -415,13 +436,18 @@ int attention_tc_try(const void* q, int64_t ld_q, int64_t q_bs, const void* k, i
   a.out = reinterpret_cast<op_t*>(out);
   a.ld_o = ld_o;
   a.bs_o = o_bs;
-  if (DP == 64)
-    *rc = NT == 2 ? launch_tc<64, 128, 2>(tq, tk, tv, a, B, heads, st) : launch_tc<64, 128, 1>(tq, tk, tv, a, B, heads, st);
-  else
-    *rc = NT == 2 ? launch_tc<128, 64, 2>(tq, tk, tv, a, B, heads, st) : launch_tc<128, 64, 1>(tq, tk, tv, a, B, heads, st);
+  if (DP == 64) {
+    if (NT == 2) *rc = launch_tc<64, 128, 2, 1>(tq, tk, tv, a, B, heads, st);
+    else if (SP == 2) *rc = launch_tc<64, 128, 1, 2>(tq, tk, tv, a, B, heads, st);
+    else *rc = launch_tc<64, 128, 1, 1>(tq, tk, tv, a, B, heads, st);
+  } else {
+    if (NT == 2) *rc = launch_tc<128, 64, 2, 1>(tq, tk, tv, a, B, heads, st);
+    else if (SP == 2) *rc = launch_tc<128, 64, 1, 2>(tq, tk, tv, a, B, heads, st);
+    else *rc = launch_tc<128, 64, 1, 1>(tq, tk, tv, a, B, heads, st);
+  }
   return 1;
 }
 
 }  // namespace aedit
 
-extern "C" void ae_set_attention_tc(int on) { aedit::g_attn_tc = on ? 1 : 0; }
+extern "C" void ae_set_attention_tc(int on) { aedit::g_attn_tc = (on >= 0 && on <= 4) ? on : 1; }

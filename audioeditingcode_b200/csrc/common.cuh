@@ -143,7 +143,9 @@ int make_operand_tmap(void* tm, const void* base, int rank, const uint64_t* dims
 
 inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
-__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
+// x * sigmoid(x); __fdividef = one MUFU.RCP + a multiply (2 ulp) instead of the IEEE division sequence: the result is rounded
+// to a 16-bit operand right after, and every kernel shares this definition (stream / non-stream GroupNorm: same bits)
+__device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 
 __device__ __forceinline__ float op_round(float x) { return op2f(f2op(x)); }
 

@@ -331,6 +331,29 @@ __global__ void __launch_bounds__(kGNThreads) gn_apply_stream_kernel(GNArgs a, i
   float* s_mean = s_B + a.C;
   float* s_rstd = s_mean + a.G;
   const int b = blockIdx.y;
+  const int vec_per_row = a.C >> 2;
+  const long long p0 = (long long)blockIdx.x * rows_per_cta;
+  const long long p1 = min(a.HW, p0 + (long long)rows_per_cta);
+  const int n_items = (int)((p1 - p0) * vec_per_row);
+  const long long row0 = (long long)b * a.HW + p0;
+  // software pipeline: the loads of batch i+1 are in flight while batch i is normalised — and the loads of batch 0
+  // while the CTA derives its affine table from the column statistics (a chain of dependent global loads that would
+  // otherwise leave the CTA without a byte in flight for a third of its life: 3.2 -> see profiles/r02_hbm_kernels_*)
+  float4 nxt[kGNStreamItems];
+  auto issue = [&](int i0) {
+#pragma unroll
+    for (int k = 0; k < kGNStreamItems; ++k) {
+      const int idx = i0 + k * kGNThreads;
+      if (idx < n_items) {
+        const int pr = idx / vec_per_row;
+        const int cc = (idx - pr * vec_per_row) << 2;
+        const long long row = row0 + pr;
+        nxt[k] = cc < a.C1 ? __ldcs(reinterpret_cast<const float4*>(a.x1 + row * a.C1 + cc))
+                           : __ldcs(reinterpret_cast<const float4*>(a.x2 + row * a.C2 + (cc - a.C1)));
+      }
+    }
+  };
+  issue(threadIdx.x);
   if (a.cs1) {
     gn_stats_from_colsums(a, b, s_mean, s_rstd);
     __syncthreads();
@@ -344,30 +367,17 @@ __global__ void __launch_bounds__(kGNThreads) gn_apply_stream_kernel(GNArgs a, i
     s_B[c] = __ldg(a.beta + c) - mr.x * A;
   }
   __syncthreads();
-  const int vec_per_row = a.C >> 2;
-  const long long p0 = (long long)blockIdx.x * rows_per_cta;
-  const long long p1 = min(a.HW, p0 + (long long)rows_per_cta);
-  const int n_items = (int)((p1 - p0) * vec_per_row);
-  const long long row0 = (long long)b * a.HW + p0;
   for (int i0 = threadIdx.x; i0 < n_items; i0 += kGNThreads * kGNStreamItems) {
     float4 v[kGNStreamItems];
-    int pr[kGNStreamItems], cc[kGNStreamItems];
 #pragma unroll
-    for (int k = 0; k < kGNStreamItems; ++k) {
-      const int idx = i0 + k * kGNThreads;
-      if (idx < n_items) {
-        pr[k] = idx / vec_per_row;
-        cc[k] = (idx - pr[k] * vec_per_row) << 2;
-        const long long row = row0 + pr[k];
-        v[k] = cc[k] < a.C1 ? __ldcs(reinterpret_cast<const float4*>(a.x1 + row * a.C1 + cc[k]))
-                            : __ldcs(reinterpret_cast<const float4*>(a.x2 + row * a.C2 + (cc[k] - a.C1)));
-      }
-    }
+    for (int k = 0; k < kGNStreamItems; ++k) v[k] = nxt[k];
+    issue(i0 + kGNThreads * kGNStreamItems);
 #pragma unroll
     for (int k = 0; k < kGNStreamItems; ++k) {
       const int idx = i0 + k * kGNThreads;
       if (idx >= n_items) continue;
-      const int c = cc[k];
+      const int pr = idx / vec_per_row;
+      const int c = (idx - pr * vec_per_row) << 2;
       const float in[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
       const float4 A4 = *reinterpret_cast<const float4*>(s_A + c);
       const float4 B4 = *reinterpret_cast<const float4*>(s_B + c);
@@ -376,7 +386,7 @@ __global__ void __launch_bounds__(kGNThreads) gn_apply_stream_kernel(GNArgs a, i
 #pragma unroll
         for (int e = 0; e < 4; ++e) o[e] = silu_f(o[e]);
       }
-      const long long off = (row0 + pr[k]) * a.C + c;
+      const long long off = (row0 + pr) * a.C + c;
       op2_t h0 = ff2op2(o[0], o[1]);
       op2_t h1 = ff2op2(o[2], o[3]);
       uint2 pk;

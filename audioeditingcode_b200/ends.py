@@ -138,6 +138,53 @@ def _load_state(path: str) -> Dict[str, torch.Tensor]:
     raise FileNotFoundError(path)
 
 
+def ldm_vae_to_canonical(sd: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+    """State dict of the ORIGINAL AudioLDM `AutoencoderKL` (what a TANGO snapshot's pytorch_model_vae.bin holds,
+    models.py:410-421; in-tree module: code/audioldm/variational_autoencoder/modules.py:419-683, autoencoder.py:9-103)
+    -> the diffusers names this package uses.  LDM `down.{i}.block.{j}` / `up.{level}.block.{j}` (level counted from the
+    full resolution, the decoder walks it downwards) / `mid.block_1|attn_1|block_2` / `nin_shortcut` / 1x1-conv attention
+    projections `q k v proj_out` -> `down_blocks` / `up_blocks.{n-1-level}` / `mid_block.resnets|attentions` /
+    `conv_shortcut` / Linear `to_q to_k to_v to_out.0`."""
+    n = len(VAE_MULT)
+    out: Dict[str, torch.Tensor] = {}
+
+    def res_names(dst, src):
+        return [(f"{src}.{b}", f"{dst}.{a}") for a, b in (("norm1", "norm1"), ("conv1", "conv1"), ("norm2", "norm2"),
+                                                          ("conv2", "conv2"), ("conv_shortcut", "nin_shortcut"))]
+    pairs = []
+    for side in ("encoder", "decoder"):
+        pairs += [(f"{side}.conv_in", f"{side}.conv_in"), (f"{side}.norm_out", f"{side}.conv_norm_out"),
+                  (f"{side}.conv_out", f"{side}.conv_out")]
+        pairs += res_names(f"{side}.mid_block.resnets.0", f"{side}.mid.block_1")
+        pairs += res_names(f"{side}.mid_block.resnets.1", f"{side}.mid.block_2")
+        pairs += [(f"{side}.mid.attn_1.norm", f"{side}.mid_block.attentions.0.group_norm")]
+        pairs += [(f"{side}.mid.attn_1.{b}", f"{side}.mid_block.attentions.0.{a}")
+                  for a, b in (("to_q", "q"), ("to_k", "k"), ("to_v", "v"), ("to_out.0", "proj_out"))]
+    for i in range(n):
+        for j in range(VAE_RES):
+            pairs += res_names(f"encoder.down_blocks.{i}.resnets.{j}", f"encoder.down.{i}.block.{j}")
+        pairs.append((f"encoder.down.{i}.downsample.conv", f"encoder.down_blocks.{i}.downsamplers.0.conv"))
+        for j in range(VAE_RES + 1):
+            pairs += res_names(f"decoder.up_blocks.{i}.resnets.{j}", f"decoder.up.{n - 1 - i}.block.{j}")
+        pairs.append((f"decoder.up.{n - 1 - i}.upsample.conv", f"decoder.up_blocks.{i}.upsamplers.0.conv"))
+    pairs += [("quant_conv", "quant_conv"), ("post_quant_conv", "post_quant_conv")]
+    for src, dst in pairs:
+        for suf in (".weight", ".bias"):
+            t = sd.get(src + suf)
+            if t is None:
+                continue
+            if ".attentions.0.to_" in dst and suf == ".weight" and t.dim() == 4:
+                t = t[:, :, 0, 0]                                   # 1x1 conv -> Linear
+            out[dst + suf] = t.float()
+    return out
+
+
+def ldm_hifigan_to_canonical(sd: Dict[str, torch.Tensor], prefix: str = "vocoder.") -> Dict[str, torch.Tensor]:
+    """`vocoder.*` entries of the same checkpoint (code/audioldm/hifigan/models.py:112-165, weight norm already removed by
+    get_vocoder, utilities.py:67-72) -> transformers SpeechT5HifiGan names (`ups.` -> `upsampler.`)."""
+    return {k[len(prefix):].replace("ups.", "upsampler."): v.float() for k, v in sd.items() if k.startswith(prefix)}
+
+
 # ------------------------------------------------------------------------------------------------- shared helpers
 class _Net:
     def __init__(self, device, ops: Optional[CudaOps] = None):
@@ -371,83 +418,88 @@ class HiFiGANEngine(_Net):
             self.up.append(dict(u=u, k=k, pad=(k - u) // 2, nt=nt, cin=cin, cout=cout, phases=phases,
                                 bias=self._to(w[f"upsampler.{i}.bias"], F32)))
 
-    def _conv1d(self, a_bf16, T, C, name, k, dil, out, residual=None):
-        """'same' dilated conv over time on a channels-last bf16 operand [1, T, C] (batch 1)."""
+    def _conv1d(self, a_bf16, B, T, C, name, k, dil, out, residual=None):
+        """'same' dilated conv over time on a channels-last operand [B, T, C] (zero padding per clip: the implicit-conv
+        TMA box never crosses the batch axis)."""
         ops = self.ops
         Wt, bias = self.w[name + ".weight"], self.w[name + ".bias"]
-        if ops.conv_supported(1, 1, T, C):
-            ops.gemm(a_bf16, Wt, out_f32=out, bias=bias, residual=residual, conv=(1, 1, T, C, 1, k, 1, dil))
+        if ops.conv_supported(B, 1, T, C):
+            ops.gemm(a_bf16, Wt, out_f32=out, bias=bias, residual=residual, conv=(B, 1, T, C, 1, k, 1, dil))
         else:
             K = k * C
-            col = ops.empty((T, (K + 7) // 8 * 8), self.adt, self.device)
-            ops.im2col(a_bf16, 1, 1, T, C, 1, k, 1, dil, 0, dil * (k - 1) // 2, 1, T, col)
+            col = ops.empty((B * T, (K + 7) // 8 * 8), self.adt, self.device)
+            ops.im2col(a_bf16, B, 1, T, C, 1, k, 1, dil, 0, dil * (k - 1) // 2, 1, T, col)
             ops.gemm(col, Wt, out_f32=out, bias=bias, residual=residual, K=K)
 
-    def _one(self, mel: torch.Tensor) -> torch.Tensor:
-        """mel: [T, 64] log-mel -> waveform [T_out] (hifigan/models.py:147-165)."""
+    def _many(self, mel: torch.Tensor) -> torch.Tensor:
+        """mel: [B, T, 64] log-mel -> waveforms [B, T_out] (hifigan/models.py:147-165), the B clips in ONE launch sequence
+        (main_run.py:184-185 vocodes the edited and the original spectrogram: decode_to_mel on a 2-row batch halves the
+        launches and doubles every GEMM's M)."""
         ops = self.ops
-        T = mel.shape[0]
+        B, T = mel.shape[0], mel.shape[1]
         x0 = mel.to(self.device, F32).contiguous()
         if self.normalize_before:
             x0 = ((x0 - self.mean) / self.scale).contiguous()
-        xb = ops.empty((T, HIFI_MELS), self.adt, self.device)
+        xb = ops.empty((B, T, HIFI_MELS), self.adt, self.device)
         ops.cast_bf16(x0, xb)
-        x = ops.empty((T, HIFI_INIT), F32, self.device)
-        self._conv1d(xb, T, HIFI_MELS, "conv_pre", 7, 1, x)
+        x = ops.empty((B * T, HIFI_INIT), F32, self.device)
+        self._conv1d(xb, B, T, HIFI_MELS, "conv_pre", 7, 1, x)
         scale = 1.0
         for i, st in enumerate(self.up):
             u, pad, nt, cin, cout = st["u"], st["pad"], st["nt"], st["cin"], st["cout"]
-            a = ops.empty((T, cin), self.adt, self.device)
+            a = ops.empty((B, T, cin), self.adt, self.device)
             ops.leaky_relu_bf16(x, 0.1, a, scale=scale)            # scale: the /3 of the previous MRF average
             T_out = (T - 1) * u - 2 * pad + st["k"]
             Q = (T_out - 1 + pad) // u + 1
-            col = ops.empty((Q, nt * cin), self.adt, self.device)
-            ops.im2col(a, 1, 1, T, cin, 1, nt, 1, 1, 0, nt - 1, 1, Q, col)
-            y = ops.empty((T_out, cout), F32, self.device)
+            col2 = ops.empty((B * Q, nt * cin), self.adt, self.device)     # 2-D: im2col takes the ROW pitch from stride(0)
+            ops.im2col(a, B, 1, T, cin, 1, nt, 1, 1, 0, nt - 1, 1, Q, col2)
+            col = col2.view(B, Q, nt * cin)
+            y = ops.empty((B, T_out, cout), F32, self.device)
             for r in range(u):
                 t0 = (r - pad) % u                                  # first output index of this phase
                 q0 = (t0 + pad) // u
                 cnt = (T_out - t0 + u - 1) // u
                 if cnt <= 0:
                     continue
-                ops.gemm(col[q0:q0 + cnt], st["phases"][r], out_f32=y[t0:], bias=st["bias"], M=cnt,
-                         ld_out_f32=u * cout)
+                for b in range(B):                                  # phase GEMMs interleave rows in time: one per clip
+                    ops.gemm(col[b, q0:q0 + cnt], st["phases"][r], out_f32=y[b, t0:], bias=st["bias"], M=cnt,
+                             ld_out_f32=u * cout)
             T = T_out
             xs = None
             for j, (rk, rd) in enumerate(zip(HIFI_RES_K, HIFI_RES_D)):
                 p = f"resblocks.{i * 3 + j}"
-                cur = y
+                cur = y.view(B * T, cout)
                 for d, dil in enumerate(rd):                        # hifigan/models.py:96-103
-                    a1 = ops.empty((T, cout), self.adt, self.device)
+                    a1 = ops.empty((B, T, cout), self.adt, self.device)
                     ops.leaky_relu_bf16(cur, 0.1, a1)
-                    h = ops.empty((T, cout), F32, self.device)
-                    self._conv1d(a1, T, cout, f"{p}.convs1.{d}", rk, dil, h)
-                    a2 = ops.empty((T, cout), self.adt, self.device)
+                    h = ops.empty((B * T, cout), F32, self.device)
+                    self._conv1d(a1, B, T, cout, f"{p}.convs1.{d}", rk, dil, h)
+                    a2 = ops.empty((B, T, cout), self.adt, self.device)
                     ops.leaky_relu_bf16(h, 0.1, a2)
-                    nxt = ops.empty((T, cout), F32, self.device)
-                    self._conv1d(a2, T, cout, f"{p}.convs2.{d}", rk, 1, nxt, residual=cur)
+                    nxt = ops.empty((B * T, cout), F32, self.device)
+                    self._conv1d(a2, B, T, cout, f"{p}.convs2.{d}", rk, 1, nxt, residual=cur)
                     cur = nxt
                 if xs is None:
                     xs = cur
                 else:
-                    acc = ops.empty((T, cout), F32, self.device)
+                    acc = ops.empty((B * T, cout), F32, self.device)
                     ops.add(xs, cur, acc)
                     xs = acc
             x = xs
             scale = 1.0 / len(HIFI_RES_K)
-        a = ops.empty((T, x.shape[-1]), self.adt, self.device)
+        a = ops.empty((B, T, x.shape[-1]), self.adt, self.device)
         ops.leaky_relu_bf16(x, 0.01, a, scale=scale)                # F.leaky_relu default slope (models.py:161)
-        o = ops.empty((T, 1), F32, self.device)
-        self._conv1d(a, T, x.shape[-1], "conv_post", 7, 1, o)
-        wav = ops.empty((T,), F32, self.device)
+        o = ops.empty((B * T, 1), F32, self.device)
+        self._conv1d(a, B, T, x.shape[-1], "conv_post", 7, 1, o)
+        wav = ops.empty((B, T), F32, self.device)
         ops.tanh(o.reshape(-1), wav)
         return wav
 
     def __call__(self, mel: torch.Tensor) -> torch.Tensor:
         """mel: [T, 64] or [B, T, 64] -> waveform [T_out] or [B, T_out] (SpeechT5HifiGan convention)."""
         if mel.dim() == 2:
-            return self._one(mel)
-        return torch.stack([self._one(m) for m in mel])
+            return self._many(mel[None])[0]
+        return self._many(mel)
 
 
 # ------------------------------------------------------------------------------------------------- facade
@@ -471,10 +523,32 @@ class AudioEnds:
                 "(allow_synthetic=True / AEDIT_ALLOW_SYNTHETIC=1)")
         return False
 
+    def _tango_state(self):
+        """TANGO snapshot (models.py:402-421): VAE + vocoder live in pytorch_model_vae.bin at the snapshot root under the
+        original AudioLDM names; vae_config.json may carry the latent scale factor."""
+        p = os.path.join(self.ckpt_dir, "pytorch_model_vae.bin") if self.ckpt_dir else None
+        if not p or not os.path.exists(p):
+            return None
+        if getattr(self, "_tango_sd", None) is None:
+            self._tango_sd = torch.load(p, map_location="cpu", weights_only=True)
+        return self._tango_sd
+
     def vae(self) -> VAEEngine:
         if self._vae is None:
             w, sf = None, VAE_SCALING
-            if self._require("vae"):
+            tango = self._tango_state()
+            if tango is not None:
+                import json
+                w = ldm_vae_to_canonical(tango)
+                missing = [k for k in vae_weight_shapes() if k not in w]
+                if missing:
+                    raise KeyError(f"pytorch_model_vae.bin lacks {len(missing)} VAE tensors, e.g. {missing[:3]}")
+                cfgp = os.path.join(self.ckpt_dir, "vae_config.json")
+                if os.path.exists(cfgp):
+                    sf = float(json.load(open(cfgp)).get("scale_factor", 1.0))
+                else:
+                    sf = 1.0
+            elif self._require("vae"):
                 import json
                 w = _load_state(os.path.join(self.ckpt_dir, "vae"))
                 cfgp = os.path.join(self.ckpt_dir, "vae", "config.json")
@@ -486,7 +560,10 @@ class AudioEnds:
     def voc(self) -> HiFiGANEngine:
         if self._voc is None:
             w, nb = None, False
-            if self._require("vocoder"):
+            tango = self._tango_state()
+            if tango is not None and any(k.startswith("vocoder.") for k in tango):
+                w = ldm_hifigan_to_canonical(tango)
+            elif self._require("vocoder"):
                 import json
                 w = _load_state(os.path.join(self.ckpt_dir, "vocoder"))
                 cfgp = os.path.join(self.ckpt_dir, "vocoder", "config.json")

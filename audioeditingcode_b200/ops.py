@@ -152,7 +152,7 @@ class CudaOps:
 
     def im2col(self, x, B, H, W, C_, kh, kw, stride, dil, pad_t, pad_l, Ho, Wo, out):
         check(self.lib.ae_im2col(_p(x), 0 if x.dtype == F32 else 1, B, H, W, C_, kh, kw, stride, dil, pad_t, pad_l,
-                                 Ho, Wo, _p(out), out.stride(0), _stream()), "ae_im2col")
+                                 Ho, Wo, _p(out), out.stride(-2), _stream()), "ae_im2col")
 
     # ---------------------------------------------------------------- norms / activations
     def _gn_workspace(self, B, groups, device):

@@ -60,6 +60,16 @@ def test_hifigan_vs_vendored_generator():
     print(f"hifigan rel-L2 {r:.2e} (torch-bf16 {float(g['bf16_autocast_err']):.2e})")
     assert r < 2e-2
     assert (wav.cpu() - g["wav"][0]).abs().max().item() < 0.05 * g["wav"].abs().max().item() + 1e-4
+    # batch axis (the edited / original pair of main_run.py:184-185 in one launch sequence): each clip's waveform equals
+    # its single-clip result (per-clip zero padding; a different M may pick another tile / split-K plan, so the
+    # comparison is to fp32 summation order, not bits)
+    mel2 = torch.stack([g["mel"][0], g["mel"][0].flip(0) * 0.5 - 1.0]).cuda()
+    w2 = voc(mel2)
+    assert w2.shape == (2, wav.shape[0])
+    r0, r1 = _rel(w2[0], wav), _rel(w2[1], voc(mel2[1]))
+    print(f"batched vocoder vs single calls: rel-L2 {r0:.2e} {r1:.2e}")
+    assert r0 < 2e-3 and r1 < 2e-3
+    assert _rel(w2[0], g["wav"][0]) < 2e-2
 
 
 def test_wrapper_ends_roundtrip_shapes():
@@ -74,3 +84,29 @@ def test_wrapper_ends_roundtrip_shapes():
     assert xd.shape == (1, 1, 128, 64)
     wav = m.decode_to_mel(xd)
     assert wav.dim() == 2 and wav.shape[0] == 1 and abs(wav.shape[1] - 128 * 160) <= 64
+
+
+def test_tango_posterior_sample_encode():
+    """TangoWrapper.vae_encode = get_first_stage_encoding(encode_first_stage(x)) = posterior.sample() * scale_factor
+    (models.py:439-447; DiagonalGaussianDistribution, distributions.py:24-73: logvar clamped to [-30, 20],
+    sample = mean + std * randn): with the generator seeded identically the sample is mean + exp(logvar / 2) * eps of the
+    moments the vendored-Encoder golden pins, and its front padding / length limit behave like the reference's."""
+    from audioeditingcode_b200 import models, unet_config as C
+    g = load_golden("vae_ends.npz")
+    m = models.load_model("synthetic/tango-tiny", torch.device("cuda"), 10, config=C.preset("tiny-tango"))
+    x = g["x"].cuda()
+    ends = m._ends()
+    mom = ends.vae().encode_moments(x)
+    mean, logvar = mom[:, :8], torch.clamp(mom[:, 8:], -30.0, 20.0)
+    torch.manual_seed(5)
+    z = m.vae_encode(x)
+    torch.manual_seed(5)
+    eps = torch.randn_like(mean)
+    want = (mean + torch.exp(0.5 * logvar) * eps) * ends.vae().scaling
+    assert torch.allclose(z, want, atol=1e-6, rtol=1e-6)
+    torch.manual_seed(6)
+    assert not torch.equal(m.vae_encode(x), z)
+    with pytest.raises(RuntimeWarning):                       # models.py:444-445
+        m.vae_encode(torch.zeros(1, 1, 1704, 64, device="cuda"))
+    xp = m.vae_encode(x[:, :, :x.shape[2] - 2])               # T % 4 != 0 -> front-padded to a multiple of 4 (:441-442)
+    assert xp.shape[2] == (x.shape[2] - 2 + 3) // 4

@@ -545,7 +545,7 @@ def test_attention_tcgen05(ops, B, d, heads, Tq, Tk, bias):
     args = (heads, d, d ** -0.5, Tq, Tk, B, 3 * C, Tq * 3 * C, 3 * C, Tk * 3 * C, 3 * C, Tk * 3 * C)
     outs = []
     try:
-        for tc in (1, 1, 0):
+        for tc in (1, 1, 0, 2, 3, 4):     # auto twice, mma.sync, then the forced variants (row split / two tiles / plain)
             ops.lib.ae_set_attention_tc(tc)
             o = torch.zeros(B * Tq, C, device="cuda", dtype=BF)
             ops.attention(q, kk[..., C:], kk[..., 2 * C:], o, *args, bias=kb)
@@ -553,6 +553,7 @@ def test_attention_tcgen05(ops, B, d, heads, Tq, Tk, bias):
     finally:
         ops.lib.ae_set_attention_tc(1)
     assert torch.equal(outs[0], outs[1])
+    assert torch.equal(outs[4], outs[5])                      # one or two query tiles per CTA: same bits per row
     qh = q[..., :C].float().view(B, Tq, heads, d).transpose(1, 2)
     kh = kk[..., C:2 * C].float().view(B, Tk, heads, d).transpose(1, 2)
     vh = kk[..., 2 * C:].float().view(B, Tk, heads, d).transpose(1, 2)
@@ -563,6 +564,8 @@ def test_attention_tcgen05(ops, B, d, heads, Tq, Tk, bias):
     e_tc, e_old = relerr(outs[0], ref), relerr(outs[2], ref)
     print(f"B={B} d={d} T={Tq}/{Tk}: rel err tcgen05 {e_tc:.2e}  mma.sync {e_old:.2e}")
     assert e_tc < 1e-2 and relerr(outs[0], outs[2]) < 1e-2
+    for o in outs[3:]:
+        assert relerr(o, ref) < 1e-2
 
 
 def test_attention_cross_masked(ops):

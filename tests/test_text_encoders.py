@@ -186,3 +186,29 @@ def test_reference_encode_text_methods_agree(ckpts):
     got2 = m2.encode_text(PROMPTS)
     for a, b in zip(ref2, got2):
         assert torch.equal(a, b)
+
+
+def test_tango_vae_checkpoint_names_roundtrip(tmp_path):
+    """A TANGO snapshot keeps VAE + vocoder in pytorch_model_vae.bin under the ORIGINAL AudioLDM names (models.py:410-421).
+    ends.ldm_vae_to_canonical / ldm_hifigan_to_canonical must map them onto the names the engines consume: a seeded
+    canonical state dict converted to the vendored naming by the ORACLE's converter (validated against the vendored
+    modules by the golden tests) and back by the product's loader must be the identity."""
+    from oracle import ends_torch as E
+    from audioeditingcode_b200 import ends
+    w = ends.synthetic(ends.vae_weight_shapes(), 3)
+    ldm = E.vae_to_ldm(w)
+    assert any(".nin_shortcut." in k for k in ldm) and any(k.startswith("decoder.up.2.") for k in ldm)
+    back = ends.ldm_vae_to_canonical(ldm)
+    assert set(back) == set(w)
+    for k in w:
+        assert torch.equal(back[k], w[k]), k
+    hv = ends.synthetic(ends.hifigan_weight_shapes(), 4)
+    sd = {"vocoder." + k: v for k, v in E.hifigan_to_ldm(hv).items()}
+    sd.update(ldm)
+    hb = ends.ldm_hifigan_to_canonical(sd)
+    assert set(hb) == set(hv) and all(torch.equal(hb[k], hv[k]) for k in hv)
+    # through the facade: a snapshot directory with only pytorch_model_vae.bin
+    torch.save(sd, tmp_path / "pytorch_model_vae.bin")
+    ae = ends.AudioEnds(torch.device("cpu"), str(tmp_path), allow_synthetic=False)
+    st = ae._tango_state()
+    assert st is not None and "encoder.down.0.block.0.norm1.weight" in st
