@@ -405,11 +405,15 @@ int attention_tc_try(const void* q, int64_t ld_q, int64_t q_bs, const void* k, i
   // per CTA with 64-key blocks (16 softmax warps under a 96-register cap) — 6-28 % SLOWER: the kernel is bound by the
   // per-block barrier round trips (S ready -> softmax -> P ready -> P.V -> next S), which twice as many, half as large
   // key blocks double.
-  // g_attn_tc: 1 auto; 2 / 3 / 4 force (NT 1, SP 2) / (NT 2, SP 1) / (NT 1, SP 1) — A/B measurements
-  int NT = tiles >= 2 * 148 ? 2 : 1, SP = NT == 1 ? 2 : 1;
+  // g_attn_tc: 1 auto; 2 / 3 / 4 / 5 force (NT 1, SP 2) / (NT 2, SP 1) / (NT 1, SP 1) / (NT 2, SP 2) — A/B measurements.
+  // Auto (profiles/r02_attn_bench_v5.log): a row split over two threads halves the per-block critical path of the softmax
+  // warps and wins while the grid is below ~3 waves of CTAs; beyond that two query tiles per CTA (shared K / V blocks)
+  // win — with the row split on top for d <= 64 (16 softmax warps; for d > 64 the extra warps gain nothing).
+  int NT = tiles >= 3 * 148 ? 2 : 1, SP = (NT == 1 || DP == 64) ? 2 : 1;
   if (g_attn_tc == 2) { NT = 1; SP = 2; }
   if (g_attn_tc == 3) { NT = 2; SP = 1; }
   if (g_attn_tc == 4) { NT = 1; SP = 1; }
+  if (g_attn_tc == 5) { NT = 2; SP = 2; }
   const int BKEYS = DP == 64 ? 128 : 64;
   CUtensorMap tq, tk, tv;
   auto mk = [&](CUtensorMap* tm, const void* base, int64_t ld, int64_t bs, int T, int nb, int rows) {
@@ -437,11 +441,13 @@ int attention_tc_try(const void* q, int64_t ld_q, int64_t q_bs, const void* k, i
   a.ld_o = ld_o;
   a.bs_o = o_bs;
   if (DP == 64) {
-    if (NT == 2) *rc = launch_tc<64, 128, 2, 1>(tq, tk, tv, a, B, heads, st);
+    if (NT == 2 && SP == 2) *rc = launch_tc<64, 128, 2, 2>(tq, tk, tv, a, B, heads, st);
+    else if (NT == 2) *rc = launch_tc<64, 128, 2, 1>(tq, tk, tv, a, B, heads, st);
     else if (SP == 2) *rc = launch_tc<64, 128, 1, 2>(tq, tk, tv, a, B, heads, st);
     else *rc = launch_tc<64, 128, 1, 1>(tq, tk, tv, a, B, heads, st);
   } else {
-    if (NT == 2) *rc = launch_tc<128, 64, 2, 1>(tq, tk, tv, a, B, heads, st);
+    if (NT == 2 && SP == 2) *rc = launch_tc<128, 64, 2, 2>(tq, tk, tv, a, B, heads, st);
+    else if (NT == 2) *rc = launch_tc<128, 64, 2, 1>(tq, tk, tv, a, B, heads, st);
     else if (SP == 2) *rc = launch_tc<128, 64, 1, 2>(tq, tk, tv, a, B, heads, st);
     else *rc = launch_tc<128, 64, 1, 1>(tq, tk, tv, a, B, heads, st);
   }
@@ -450,4 +456,4 @@ int attention_tc_try(const void* q, int64_t ld_q, int64_t q_bs, const void* k, i
 
 }  // namespace aedit
 
-extern "C" void ae_set_attention_tc(int on) { aedit::g_attn_tc = (on >= 0 && on <= 4) ? on : 1; }
+extern "C" void ae_set_attention_tc(int on) { aedit::g_attn_tc = (on >= 0 && on <= 5) ? on : 1; }

@@ -733,8 +733,15 @@ struct PersistLayout {
   static constexpr int kTotal = kRingBytes + kStripBytes + kBarBytes + kEpiBytes + 1024;
 };
 
+// Epilogue warps of the persistent kernel: the row-per-thread epilogue (bf16 / GEGLU outputs) is ALU- and latency-bound
+// — the GEGLU layers execute ~20 instructions per accumulator on ONE warp per SM sub-partition (ncu r01 v35: 9 % of the
+// warp slots) — so it runs on EIGHT warps: warps 2..5 and 6..9 share the four TMEM lane quadrants and split the tile's
+// columns in halves.  The staged epilogue (fp32 outputs) keeps four.
+template <bool STAGED>
+constexpr int persist_threads() { return STAGED ? kThreads : kThreads + 128; }
+
 template <int BN, int STAGES, bool STAGED>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(persist_threads<STAGED>(), 1)
 gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmDev p,
                        int tiles_n, int n_tiles) {
   using L = PersistLayout<BN, STAGES, STAGED>;
@@ -766,7 +773,7 @@ gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     }
     for (int s = 0; s < 2; ++s) {
       ptx::mbar_init(&tmem_full_bar[s], 1);
-      ptx::mbar_init(&tmem_empty_bar[s], 4);   // one arrival per epilogue warp
+      ptx::mbar_init(&tmem_empty_bar[s], STAGED ? 4 : 8);   // one arrival per epilogue warp
     }
     ptx::fence_mbar_init();
   }
@@ -866,9 +873,12 @@ gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       pdl_trigger();
     }
   } else {
-    // ===================== epilogue (warps 2..5 -> TMEM lane quadrants 2,3,0,1) =====================
+    // ===================== epilogue (warps 2..5 [6..9] -> TMEM lane quadrants 2,3,0,1) =====================
     const int quad = warp & 3;
     const int etid = (int)threadIdx.x - 64;
+    constexpr int kEpiThreads = persist_threads<STAGED>() - 64;
+    constexpr int kChunksPerWarp = (BN / 32) / (kEpiThreads / 128);      // column chunks of 32 per epilogue warp
+    const int c_first = ((warp - 2) >> 2) * kChunksPerWarp;
     pdl_wait();
     int i = 0;
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++i) {
@@ -895,7 +905,7 @@ gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         float* sb = s_bias + acc * BN;
         float* srb = s_rowb + acc * BN;
         if (stage_b || stage_rb) {
-          for (int c = etid; c < BN; c += 128) {
+          for (int c = etid; c < BN; c += kEpiThreads) {
             const bool ok = n0 + c < p.N;
             if (stage_b) sb[c] = ok ? __ldg(p.bias + n0 + c) : 0.f;
             if (stage_rb) srb[c] = ok ? __ldg(p.rowbias + (m0 / p.rows_per_group) * p.ld_rowbias + n0 + c) : 0.f;
@@ -903,15 +913,15 @@ gemm_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         }
         // also orders the epilogue warps tile by tile: buffer `acc` of sb / srb is rewritten two tiles later, after
         // every warp has passed the barrier of the tile in between
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
         ptx::mbar_wait(&tmem_full_bar[acc], par);
         ptx::tcgen05_fence_after();
 #pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
+        for (int c = c_first; c < c_first + kChunksPerWarp; ++c) {
           uint32_t v[32];
           ptx::tmem_ld_32x32b_x32(tmem_q + c * 32, v);
           ptx::tmem_ld_wait();
-          if (c == BN / 32 - 1) {
+          if (c == c_first + kChunksPerWarp - 1) {
             // last read of this accumulator buffer: hand it back before the global stores of the chunk
             ptx::tcgen05_fence_before();
             __syncwarp();
@@ -1216,8 +1226,9 @@ int launch_persistent(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gemm
   const int tiles_n = (p.N + BN - 1) / BN;
   const long long n_tiles = tiles_m * tiles_n;
   const unsigned grid = (unsigned)(n_tiles < n_sm ? n_tiles : n_sm);
-  cudaError_t e = launch_kernel_early(gemm_persistent_kernel<BN, STAGES, STAGED>, dim3(grid), dim3(kThreads),
-                                      (size_t)L::kTotal, st, tmA, tmB, p, tiles_n, (int)n_tiles);
+  cudaError_t e = launch_kernel_early(gemm_persistent_kernel<BN, STAGES, STAGED>, dim3(grid),
+                                      dim3(persist_threads<STAGED>()), (size_t)L::kTotal, st, tmA, tmB, p, tiles_n,
+                                      (int)n_tiles);
   if (e != cudaSuccess) return fail(AE_ECUDA, "ae_gemm persistent launch: %s", cudaGetErrorString(e));
   return launched("ae_gemm(persistent)");
 }

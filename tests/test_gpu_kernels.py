@@ -545,7 +545,7 @@ def test_attention_tcgen05(ops, B, d, heads, Tq, Tk, bias):
     args = (heads, d, d ** -0.5, Tq, Tk, B, 3 * C, Tq * 3 * C, 3 * C, Tk * 3 * C, 3 * C, Tk * 3 * C)
     outs = []
     try:
-        for tc in (1, 1, 0, 2, 3, 4):     # auto twice, mma.sync, then the forced variants (row split / two tiles / plain)
+        for tc in (1, 1, 0, 2, 3, 4, 5):  # auto twice, mma.sync, then the forced variants (row split / two tiles / plain / both)
             ops.lib.ae_set_attention_tc(tc)
             o = torch.zeros(B * Tq, C, device="cuda", dtype=BF)
             ops.attention(q, kk[..., C:], kk[..., 2 * C:], o, *args, bias=kb)

@@ -20,7 +20,7 @@ for (B, heads, d, T) in SHAPES:
     qkv = torch.randn(B * T, 3 * C, device="cuda").to(BF)
     out = torch.empty(B * T, C, device="cuda", dtype=BF)
     res = {}
-    for tc in (1, 0, 2, 3, 4):
+    for tc in (1, 0, 2, 3, 4, 5):
         ops.lib.ae_set_attention_tc(tc)
 
         def run():
@@ -45,5 +45,5 @@ for (B, heads, d, T) in SHAPES:
     fl = 4.0 * B * heads * T * T * d
     print(f"attention B={B:3d} heads={heads:2d} d={d:3d} T={T:4d}: tcgen05 {res[1]:9.2f} us {fl / res[1] / 1e6:7.1f} TFLOP/s | "
           f"mma.sync {res[0]:9.2f} us {fl / res[0] / 1e6:7.1f} TFLOP/s | speed-up {res[0] / res[1]:.2f}x | forced variants: "
-          f"row-split {res[2]:.1f} us, two-tiles {res[3]:.1f} us, plain {res[4]:.1f} us", flush=True)
+          f"row-split {res[2]:.1f} us, two-tiles {res[3]:.1f} us, plain {res[4]:.1f} us, two-tiles+row-split {res[5]:.1f} us", flush=True)
 ops.lib.ae_set_attention_tc(1)
