@@ -53,6 +53,11 @@ def _stream():
 
 class PipelineWrapper(torch.nn.Module):
     family = "audioldm"
+    # Finite-difference step pc_drift.get_eigenvectors takes through THIS evaluator when the caller does not pass
+    # `fd_const`: the U-Net here runs on 16-bit tensor-core operands, which cannot resolve the
+    # reference's const = 1e-3 (1e-3 / sqrt(D) per element); results are returned in units of the caller's `const`.
+    # None = take the caller's `const` literally.
+    pc_fd_const: Optional[float] = 1.0
 
     def __init__(self, model_id: str, device: torch.device, double_precision: bool = False,
                  token: Optional[str] = None, *args, weights: Optional[Dict[str, torch.Tensor]] = None,

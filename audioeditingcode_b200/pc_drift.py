@@ -119,15 +119,21 @@ def get_eigenvectors(ldm_stable, xt: torch.Tensor, text_emb: PromptEmbeddings, u
     `group` (extension; None = the reference's single-process behaviour): process group over which the n_ev directions
     are sharded, see the module docstring.  `init_eigvecs` (extension): explicit start `[n_ev, C, H, W]` used instead of
     the `randn_like(xt) * mask * const` draw of :130 (seed-independent comparisons against the reference).
-    `fd_const` (extension; default None = `const`, the reference's behaviour; env AEDIT_PC_FD_CONST): the step of the
-    finite difference actually taken.  The iteration only uses Ab / const (direction and eigenvalue), which is independent
-    of the step to first order, but the reference default 1e-3 spreads a perturbation of 1e-3 / sqrt(D) per element — below
-    the resolution of 16-bit tensor-core operands (it sits at the rounding level of the reference's own fp32 evaluation,
-    DESIGN.md §2).  A step of ~0.3-1 resolves the Jacobian-vector products through the real U-Net
+    `fd_const` (extension): the step of the finite difference actually taken.  The iteration only uses Ab / const
+    (direction and eigenvalue), which is independent of the step to first order, but the reference default 1e-3 spreads a
+    perturbation of 1e-3 / sqrt(D) per element — below the resolution of 16-bit tensor-core operands (and of the TF32
+    matmuls the reference itself enables on a GPU, utils.py:116; its CPU fp32 run is the one that resolves it, DESIGN.md
+    §2).  Resolution order: the argument; env AEDIT_PC_FD_CONST (a number, or "reference" for the caller's `const`);
+    the evaluator's own `ldm_stable.pc_fd_const` (1.0 for the wrappers of models.py, absent = `const` for any other
+    evaluator).  All outputs stay in units of the caller's `const`
     (tests/test_gpu_pc_drift.py::test_unet_jvp_resolves_with_fd_const)."""
     import os as _os
-    if fd_const is None and _os.environ.get("AEDIT_PC_FD_CONST"):
-        fd_const = float(_os.environ["AEDIT_PC_FD_CONST"])
+    if fd_const is None:
+        env = _os.environ.get("AEDIT_PC_FD_CONST", "")
+        if env:
+            fd_const = None if env.lower() in ("reference", "const") else float(env)
+        else:
+            fd_const = getattr(ldm_stable, "pc_fd_const", None)
     const_ret = const
     if fd_const is not None:
         const = float(fd_const)
