@@ -32,9 +32,9 @@ class AeGemmArgs(C.Structure):
                 ("out_f32", vp), ("ld_out_f32", i64), ("out_bf16", vp), ("ld_out_bf16", i64), ("act", i32),
                 ("alpha", f32), ("conv", i32), ("B", i32), ("H", i32), ("W_", i32), ("C", i32), ("kh", i32),
                 ("kw", i32), ("dil_h", i32), ("dil_w", i32), ("force_bn", i32), ("splitk_ws", vp), ("splitk_ws_bytes", i64),
-                ("force_split", i32), ("force_csplit", i32), ("w_dynamic", i32), ("force_stages", i32),
+                ("force_split", i32), ("w_dynamic", i32), ("force_stages", i32),
                 ("colstats", vp), ("cs_rows_per_sample", i32), ("force_persistent", i32),
-                ("force_multicast", i32), ("sm_L", i32), ("sm_block", i32), ("sm_rows", i32), ("sm_slot", vp),
+                ("sm_L", i32), ("sm_block", i32), ("sm_rows", i32), ("sm_slot", vp),
                 ("sm_bias", vp)]
 
 
@@ -49,7 +49,6 @@ _SIGS = {
     "ae_greatest_priority": (i32, []),
     "ae_set_shared_sm": (None, [i32]),
     "ae_set_skip_mask": (None, [i32]),
-    "ae_set_multicast": (None, [i32]),
     "ae_set_tile_model_reduce": (None, [i32, i32]),
     "ae_set_persistent_min_tiles": (None, [i32]),
     "ae_set_headroom": (None, [i32]),

@@ -295,10 +295,11 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         }
       }
       // ---- P = exp2(x - m_ref) -> operand type -> shared memory (K-major, 128-byte swizzle), row sum
-      if (NT == 1 && j > 0) {
+      if (j > 0) {
         // single query tile: S(j) was issued ahead of P.V(j-1) (double-buffered S), so that product may still be READING
-        // the P tile this block is about to overwrite — wait for it (with two tiles S_t(j) is issued after P.V_t(j-1) and
-        // tensor-core work completes in order, so seeing S_t(j) already implies it)
+        // the P tile this block is about to overwrite — wait for it.  With two tiles S_t(j) is issued after P.V_t(j-1) and
+        // tensor-core work completes in order, so seeing S_t(j) already implies it and the wait returns at once; it is
+        // kept so that every phase of o_full is observed before the next commit arrives on it (synccheck: missing wait)
         ptx::mbar_wait(o_full + t, (j - 1) & 1);
       }
       float ls4[4] = {0.f, 0.f, 0.f, 0.f};

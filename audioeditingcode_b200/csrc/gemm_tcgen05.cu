@@ -45,8 +45,6 @@ struct GemmDev {
   int num_kblocks;
   int kb_per_split;  // == num_kblocks when not split
   int split;         // 1: blockIdx.z is a K split (partials to out_f32 + z*stride_out), else a batch index
-  int csplit;        // >1: blockIdx.z is the rank in a thread-block cluster of that many CTAs sharing one output
-                     //     tile; partial accumulators are reduced through distributed shared memory (no workspace)
   // implicit conv
   int conv, H, W, HW, cblocks, kw, dil_h, dil_w, pad_h, pad_w;
   // epilogue
@@ -464,15 +462,7 @@ __device__ __forceinline__ void epilogue_strip(const GemmDev& p, float* strip, u
   }
 }
 
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.aligned;\n\tbarrier.cluster.wait.aligned;" ::: "memory");
-}
-
-// MC = 2: the two CTAs of a cluster (adjacent N tiles of one M tile) share the A tile — each fetches half of its rows
-// and TMA-multicasts them into both CTAs' rings, so a CTA pulls half of the A panel through L2 (the sub-wave layers of
-// the reverse process are bound by exactly that: ~70 KB/us per SM).  A ring slot is free once BOTH MMA warps are done
-// with it (empty barrier counts 2, each commit is multicast to both CTAs).  Linear (non-conv) operands only.
-template <int BN, int STAGES, int MC = 1>
+template <int BN, int STAGES>
 __global__ void __launch_bounds__(kThreads)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmDev p) {
   using L = SmemLayout<BN, STAGES>;
@@ -501,30 +491,27 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const int z = blockIdx.z;
   const int m0 = tile_m * BM;
   const int n0 = tile_n * BN;
-  const bool ksplit = p.split || p.csplit > 1;
+  const bool ksplit = p.split != 0;
   const int zb = ksplit ? 0 : z;  // batch coordinate of the tensor maps
   const int kb0 = ksplit ? z * p.kb_per_split : 0;
   const int kb1 = ksplit ? min(p.num_kblocks, kb0 + p.kb_per_split) : p.num_kblocks;
-  const int zo = p.csplit > 1 ? 0 : z;  // output / residual batch-or-partial index
+  const int zo = z;  // output / residual batch-or-partial index
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&tmA);
     ptx::prefetch_tensormap(&tmB);
     for (int s = 0; s < STAGES; ++s) {
       ptx::mbar_init(&full_bar[s], 1);
-      ptx::mbar_init(&empty_bar[s], MC);
+      ptx::mbar_init(&empty_bar[s], 1);
     }
     ptx::mbar_init(tmem_full_bar, 1);
     ptx::fence_mbar_init();
   }
-  uint32_t crank = 0;
-  if constexpr (MC == 2) crank = ptx::cluster_ctarank();
   if (warp == 1) ptx::tmem_alloc<TMEM_COLS>(tmem_slot);
   if (p.colstats && warp >= 2)
     for (int i = (int)threadIdx.x - 64; i < 2 * BN + 1; i += kThreads - 64) s_cs[i] = 0ull;
   ptx::tcgen05_fence_before();
   __syncthreads();
-  if constexpr (MC == 2) cluster_sync_all();   // the peer's barriers exist before anything is multicast to them
   ptx::tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   // Everything above overlapped the previous kernel (programmatic dependent launch).  The weight operand W never
@@ -561,10 +548,6 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           const int j = tap - i * p.kw;
           ptx::tma_load_4d(&tmA, &full_bar[stage], sA + stage * kATileBytes, cb * BK, w0 + j * p.dil_w - p.pad_w,
                            h0 + i * p.dil_h - p.pad_h, b0);
-        } else if constexpr (MC == 2) {
-          // my half of the A tile's rows (tmA's box is 64 rows here), delivered to both CTAs of the pair
-          ptx::tma_load_3d_multicast(&tmA, &full_bar[stage], sA + stage * kATileBytes + crank * (kATileBytes / 2),
-                                     kb * BK, m0 + (int)crank * (BM / 2), zb, (uint16_t)0x3);
         } else {
           ptx::tma_load_3d(&tmA, &full_bar[stage], sA + stage * kATileBytes, kb * BK, m0, zb);
         }
@@ -593,9 +576,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           const uint64_t db = ptx::umma_desc_k_sw128(b_addr + k * 32);
           ptx::umma_bf16_ss(tmem_base, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
         }
-        // frees the smem slot when these MMAs retire (pair: in both CTAs — either producer may refill either ring)
-        if constexpr (MC == 2) ptx::umma_commit_multicast(&empty_bar[stage], (uint16_t)0x3);
-        else ptx::umma_commit(&empty_bar[stage]);
+        // frees the smem slot when these MMAs retire
+        ptx::umma_commit(&empty_bar[stage]);
         if (++stage == STAGES) {
           stage = 0;
           phase ^= 1;
@@ -621,7 +603,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       ptx::tcgen05_fence_before();
     } else {
     const bool row_ok = m < p.M;
-    if (p.residual && row_ok && p.csplit <= 1) {
+    if (p.residual && row_ok) {
       // pull this row's residual segment towards L2 while the main loop runs (BN*4 bytes = up to 4 lines)
       const char* rp = reinterpret_cast<const char*>(p.residual + (long long)zo * p.stride_res + m * p.ld_res + n0);
 #pragma unroll
@@ -630,9 +612,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     // bias / row bias of the tile -> shared memory, one coalesced fetch per CTA while the main loop runs (the row bias
     // only when the whole tile lies in one row group, which is the rule for the time-embedding bias of the ResBlocks)
     const int etid = (int)threadIdx.x - 64;
-    const bool stage_b = p.bias != nullptr && p.csplit <= 1;
+    const bool stage_b = p.bias != nullptr;
     const long long mlast = min((long long)m0 + BM - 1, (long long)p.M - 1);
-    const bool stage_rb = p.rowbias != nullptr && p.csplit <= 1 && (m0 / p.rows_per_group) == (mlast / p.rows_per_group);
+    const bool stage_rb = p.rowbias != nullptr && (m0 / p.rows_per_group) == (mlast / p.rows_per_group);
     if (stage_b || stage_rb) {
       for (int i = etid; i < BN; i += 128) {
         const bool ok = n0 + i < p.N;
@@ -643,71 +625,19 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     ptx::mbar_wait(tmem_full_bar, 0);
     ptx::tcgen05_fence_after();
-    // cluster split-K: raw fp32 partial tile into this CTA's shared memory (the stage ring is idle once the
-    // accumulator is complete); row pitch BN+4 floats keeps the 16-byte row-owner stores conflict-free
-    float* red = reinterpret_cast<float*>(smem);
 #pragma unroll 1
     for (int c = 0; c < BN / 32; ++c) {
       uint32_t v[32];
       ptx::tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + c * 32, v);
       ptx::tmem_ld_wait();
-      if (p.csplit > 1) {
-        float4* dst = reinterpret_cast<float4*>(red + row * (BN + 4) + c * 32);
+      float acc[32];
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          dst[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
-                               __uint_as_float(v[4 * j + 3]));
-      } else {
-        float acc[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) acc[j] = __uint_as_float(v[j]) * p.alpha;
-        epilogue_chunk(p, acc, m, n0 + c * 32, zo, stage_b ? s_bias + c * 32 : nullptr, stage_rb ? s_rowb + c * 32 : nullptr);
-      }
+      for (int j = 0; j < 32; ++j) acc[j] = __uint_as_float(v[j]) * p.alpha;
+      epilogue_chunk(p, acc, m, n0 + c * 32, zo, stage_b ? s_bias + c * 32 : nullptr, stage_rb ? s_rowb + c * 32 : nullptr);
     }
     ptx::tcgen05_fence_before();
     }
   }
-  if (p.csplit > 1) {
-    // ---- distributed-shared-memory reduction: CTA `z` of the cluster finalises rows [z*R, (z+1)*R), R = 128/csplit,
-    //      summing the csplit partial tiles in rank order (fixed order -> deterministic), then runs the epilogue
-    cluster_sync_all();
-    if (warp >= 2) {
-      const int S = p.csplit;
-      const int R = BM / S;
-      constexpr int CH = BN / 32;
-      const uint32_t red_local = ptx::smem_u32(smem);
-      for (int item = threadIdx.x - 64; item < R * CH; item += kThreads - 64) {
-        const int lr = item / CH, c = item - lr * CH;
-        const int rrow = z * R + lr;
-        float acc[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) acc[j] = 0.f;
-        const uint32_t off = static_cast<uint32_t>((rrow * (BN + 4) + c * 32) * 4);
-        for (int s = 0; s < S; ++s) {
-          uint32_t raddr;
-          asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(red_local + off), "r"(s));
-          float4 t[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j)
-            asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];"
-                         : "=f"(t[j].x), "=f"(t[j].y), "=f"(t[j].z), "=f"(t[j].w)
-                         : "r"(raddr + j * 16));
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            acc[4 * j + 0] += t[j].x;
-            acc[4 * j + 1] += t[j].y;
-            acc[4 * j + 2] += t[j].z;
-            acc[4 * j + 3] += t[j].w;
-          }
-        }
-#pragma unroll
-        for (int j = 0; j < 32; ++j) acc[j] *= p.alpha;
-        epilogue_chunk(p, acc, (long long)m0 + rrow, n0 + c * 32, 0);
-      }
-    }
-    cluster_sync_all();  // nobody leaves while a peer may still read its partial tile
-  }
-  if constexpr (MC == 2) cluster_sync_all();   // the peer's last commits still arrive on this CTA's barriers
   __syncthreads();
   if (warp == 1) {
     ptx::tcgen05_fence_after();
@@ -1236,13 +1166,13 @@ int launch_persistent(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gemm
 constexpr int kHeadroomSmem = 116 * 1024;
 thread_local int g_headroom = 0;
 
-template <int BN, int STAGES, int MC = 1>
+template <int BN, int STAGES>
 int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmDev& p, int gz, cudaStream_t st) {
   using L = SmemLayout<BN, STAGES>;
   static bool attr_set = false;
   constexpr int kMaxDyn = L::kTotal > kHeadroomSmem ? L::kTotal : kHeadroomSmem;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, STAGES, MC>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDyn);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDyn);
     if (e != cudaSuccess) return fail(AE_ECUDA, "cudaFuncSetAttribute(smem=%d): %s", kMaxDyn, cudaGetErrorString(e));
     attr_set = true;
   }
@@ -1252,54 +1182,7 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmDev& p, int
   if (g_skip_mask & 1) return AE_OK;
   const unsigned tm = (unsigned)((p.M + BM - 1) / BM), tn = (unsigned)((p.N + BN - 1) / BN);
   dim3 grid = p.m_in_x ? dim3(tm, tn, gz) : dim3(tn, tm, gz);
-  cudaError_t e;
-  if constexpr (MC == 2) {
-    // CTA pairs along the N tiles (blockIdx.x): TMA multicast of the shared A tile
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = grid;
-    cfg.blockDim = dim3(kThreads);
-    cfg.dynamicSmemBytes = dyn_smem;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[3];
-    int na = 0;
-    attr[na].id = cudaLaunchAttributeClusterDimension;
-    attr[na].val.clusterDim.x = 2;
-    attr[na].val.clusterDim.y = 1;
-    attr[na].val.clusterDim.z = 1;
-    ++na;
-    if (g_use_pdl) {
-      attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-      attr[na].val.programmaticStreamSerializationAllowed = 1;
-      ++na;
-    }
-    if (g_launch_priority != 0) {
-      attr[na].id = cudaLaunchAttributePriority;
-      attr[na].val.priority = g_launch_priority;
-      ++na;
-    }
-    cfg.attrs = attr;
-    cfg.numAttrs = na;
-    e = cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<BN, STAGES, MC>, tmA, tmB, p);
-  } else if (p.csplit > 1) {
-    // thread-block cluster (1,1,csplit): the K slices of one output tile are co-scheduled and reduce through DSMEM
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = grid;
-    cfg.blockDim = dim3(kThreads);
-    cfg.dynamicSmemBytes = dyn_smem;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[2];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 1;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = (unsigned)p.csplit;
-    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[1].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = g_use_pdl ? 2 : 1;
-    e = cudaLaunchKernelEx(&cfg, gemm_tcgen05_kernel<BN, STAGES, MC>, tmA, tmB, p);
-  } else {
-    e = launch_kernel_early(gemm_tcgen05_kernel<BN, STAGES, MC>, grid, dim3(kThreads), dyn_smem, st, tmA, tmB, p);
-  }
+  cudaError_t e = launch_kernel_early(gemm_tcgen05_kernel<BN, STAGES>, grid, dim3(kThreads), dyn_smem, st, tmA, tmB, p);
   if (e != cudaSuccess) return fail(AE_ECUDA, "ae_gemm launch: %s", cudaGetErrorString(e));
   return launched("ae_gemm");
 }
@@ -1338,8 +1221,7 @@ extern "C" void ae_set_tile_model_reduce(int launch_ns, int bytes_per_us) {
   g_reduce_us = launch_ns * 1e-3;
   g_reduce_bw = bytes_per_us;
 }
-static thread_local int g_multicast = 0;   // measured slower at batch 2 (+5..+21 % per shape, profiles/r01_gemm_table_v33_B2_multicast.log): opt-in
-extern "C" void ae_set_multicast(int on) { g_multicast = on ? 1 : 0; }
+
 static thread_local int g_shallow_kb = 0;
 extern "C" void ae_set_shallow_kblocks(int kb) { g_shallow_kb = kb; }
 static thread_local int g_shared_sm = 0;
@@ -1384,7 +1266,6 @@ extern "C" int ae_gemm(const ae_gemm_args* a, ae_stream stream) {
   p.dil_h = p.dil_w = 1;
   p.pad_h = p.pad_w = 0;
   p.split = 0;
-  p.csplit = 0;
   p.fast_epi = 0;
   p.m_in_x = (a->M + BM - 1) / BM > 65535 ? 1 : 0;
   p.sm_L = p.sm_block = p.sm_rows = 0;
@@ -1405,8 +1286,8 @@ extern "C" int ae_gemm(const ae_gemm_args* a, ae_stream stream) {
   p.colstats = nullptr;
   p.cs_rows = 1;
   if (a->colstats) {
-    AE_CHECK_ARG(batch == 1 && a->act != 2 && a->N % 4 == 0 && a->out_f32 && a->force_csplit <= 1,
-                 "ae_gemm: colstats needs batch 1, a plain fp32 output with N %% 4 == 0 and no cluster split");
+    AE_CHECK_ARG(batch == 1 && a->act != 2 && a->N % 4 == 0 && a->out_f32,
+                 "ae_gemm: colstats needs batch 1 and a plain fp32 output with N %% 4 == 0");
     AE_CHECK_ARG(a->cs_rows_per_sample > 0 && a->cs_rows_per_sample % 32 == 0 && a->M % a->cs_rows_per_sample == 0,
                  "ae_gemm: colstats needs rows per sample (%d) to be a multiple of 32 dividing M", a->cs_rows_per_sample);
     AE_CHECK_ARG(a->ld_out_f32 % 4 == 0 && (reinterpret_cast<uintptr_t>(a->out_f32) & 15) == 0,
@@ -1460,7 +1341,7 @@ extern "C" int ae_gemm(const ae_gemm_args* a, ae_stream stream) {
   //      the K split are chosen together to minimise the operand bytes per SM, charging a split for its reduce launch.
   const long long tiles_m = (a->M + BM - 1) / BM;
   const bool may_split = batch == 1 && a->act != 2 && a->act != 3 && a->splitk_ws && a->N % 4 == 0 &&
-                         a->force_split != 1 && a->force_csplit <= 1;
+                         a->force_split != 1;
   int bn = a->force_bn;
   int S_model = 0;   // 0: no model decision (forced / large grid)
   if (bn == 0) {
@@ -1509,19 +1390,9 @@ extern "C" int ae_gemm(const ae_gemm_args* a, ae_stream stream) {
   AE_CHECK_ARG(bn == 32 || bn == 64 || bn == 128, "ae_gemm: force_bn must be 32, 64 or 128");
   const long long tiles = tiles_m * ((a->N + bn - 1) / bn);
 
-  // ---- cluster split-K (opt-in, force_csplit = 2 / 4 / 8): the K slices of a tile form a thread-block cluster and
-  //      reduce through DSMEM in one launch.  Measured slower than the workspace variant on B200 (cluster launch +
-  //      two cluster barriers cost ~7 us, profiles/r01_microbench_v8.log), so it is never chosen automatically.
-  int CS = 1;
-  if (batch == 1 && a->force_csplit > 1) {
-    CS = a->force_csplit;
-    AE_CHECK_ARG(CS == 2 || CS == 4 || CS == 8, "ae_gemm: force_csplit must be 1, 2, 4 or 8");
-    // every rank needs at least one K block (an idle rank would publish an unwritten accumulator)
-    while (CS > 1 && (long long)(CS - 1) * ((p.num_kblocks + CS - 1) / CS) >= p.num_kblocks) CS >>= 1;
-  }
   // ---- workspace split-K (two launches): partial tiles to an fp32 workspace, fixed-order reduce + epilogue kernel
   int S = 1;
-  if (CS == 1 && batch == 1 && a->act != 2 && a->act != 3 && a->splitk_ws && a->N % 4 == 0 && a->force_split != 1) {
+  if (batch == 1 && a->act != 2 && a->act != 3 && a->splitk_ws && a->N % 4 == 0 && a->force_split != 1) {
     if (a->force_split > 1)
       S = a->force_split;
     else if (S_model > 0)
@@ -1546,11 +1417,6 @@ extern "C" int ae_gemm(const ae_gemm_args* a, ae_stream stream) {
   cudaStream_t st = as_stream(stream);
   int gz = batch;
   GemmDev q = p;
-  if (CS > 1) {
-    q.csplit = CS;
-    q.kb_per_split = (p.num_kblocks + CS - 1) / CS;
-    gz = CS;
-  }
   if (S > 1) {
     q.split = 1;
     q.kb_per_split = (p.num_kblocks + S - 1) / S;
@@ -1572,7 +1438,7 @@ extern "C" int ae_gemm(const ae_gemm_args* a, ae_stream stream) {
     // half of that for the GEGLU output whose lanes own 2 columns)
     auto al = [](const void* ptr, uintptr_t b) { return (reinterpret_cast<uintptr_t>(ptr) & (b - 1)) == 0; };
     const bool g = q.act == 2;
-    bool ok = CS == 1 && g_fast_epi && q.act != 3 && (g ? (a->N % 32 == 0 && !q.residual && !q.rowbias) : (a->N % 4 == 0));
+    bool ok = g_fast_epi && q.act != 3 && (g ? (a->N % 32 == 0 && !q.residual && !q.rowbias) : (a->N % 4 == 0));
     ok = ok && (!q.bias || al(q.bias, 16));
     ok = ok && (!q.rowbias || (al(q.rowbias, 16) && q.ld_rowbias % 4 == 0));
     ok = ok && (!q.residual || (al(q.residual, 16) && q.ld_res % 4 == 0 && q.stride_res % 4 == 0));
@@ -1590,25 +1456,13 @@ extern "C" int ae_gemm(const ae_gemm_args* a, ae_stream stream) {
                                    "ae_set_fast_epilogue != 0)");
   }
   const long long ctas = tiles * gz;
-  const bool deep = a->force_stages ? (a->force_stages > 3) : (ctas <= 160 || CS > 1);
+  const bool deep = a->force_stages ? (a->force_stages > 3) : (ctas <= 160);
   // g_shared_sm (ae_set_shared_sm): this launch will share the SMs with a throughput-bound grid of another stream
   // whose CTAs hold ~100 KB of shared memory each (two per SM).  A 6-stage ring (120-192 KB) would only fit after BOTH
   // of them have retired with no successor taking the slot, i.e. practically never; the deepest ring that fits beside
   // ONE such CTA (<= ~103 KB: 3 / 4 / 5 stages at BN = 128 / 64 / 32) gets the next free slot.  Same bits either way:
   // the ring depth changes the buffering, not the order of the accumulation.
-  const bool shared_sm = g_shared_sm && CS == 1 && !a->force_stages;
-  // A-tile multicast across a pair of N tiles: sub-wave (deep) linear grids with an even number of N tiles
-  const long long tiles_n_ll = (a->N + bn - 1) / bn;
-  const bool mc = deep && CS == 1 && !p.conv && batch == 1 && !q.m_in_x && tiles_n_ll % 2 == 0 && !a->force_stages &&
-                  (a->force_multicast > 0 || (a->force_multicast == 0 && g_multicast));
-  CUtensorMap tmA_mc;
-  if (mc) {
-    uint64_t dims[3] = {(uint64_t)a->K, (uint64_t)a->M, 1};
-    uint64_t str[2] = {(uint64_t)a->lda * 2, (uint64_t)((int64_t)a->M * a->lda) * 2};
-    uint32_t box[3] = {BK, BM / 2, 1};
-    rc = make_tmap(&tmA_mc, a->A, 3, dims, str, box);
-    if (rc) return rc;
-  }
+  const bool shared_sm = g_shared_sm && !a->force_stages;
   // multi-wave grids with a short K loop: a 2-stage ring lets three CTAs share an SM (the CTA's fixed costs — launch,
   // TMEM allocation, pipeline ramp, epilogue — dominate its lifetime, so residency buys more than ring depth)
   // multi-wave grids: persistent CTAs with a double-buffered TMEM accumulator (gemm_persistent_kernel)
@@ -1622,7 +1476,7 @@ extern "C" int ae_gemm(const ae_gemm_args* a, ae_stream stream) {
   // on the machine meanwhile (whole job: 836 -> 862 ms with every shape persistent, profiles/r01_lanes_ab6.log).
   const bool persist_auto = g_persist_min_tiles > 0 && tiles >= g_persist_min_tiles && !p.conv && !q.fast_epi &&
                             (!q.out_f32 || q.act == 2 || p.num_kblocks >= 9);
-  const bool persist = CS == 1 && S == 1 && batch == 1 && !a->force_stages && (bn == 128 || bn == 64) &&
+  const bool persist = S == 1 && batch == 1 && !a->force_stages && (bn == 128 || bn == 64) &&
                        (a->force_persistent > 0 || (a->force_persistent == 0 && persist_auto)) &&
                        tiles * 1ll < 2147483647ll;
   if (persist) {
@@ -1632,22 +1486,9 @@ extern "C" int ae_gemm(const ae_gemm_args* a, ae_stream stream) {
     else
       rc = q.fast_epi ? launch_persistent<64, 6, true>(tmA, tmB, q, tiles_m, st)
                       : launch_persistent<64, 4, false>(tmA, tmB, q, tiles_m, st);
-  } else if (!deep && bn == 128 && CS == 1 && (a->force_stages == 2 || (!a->force_stages && p.num_kblocks <= g_shallow_kb)))
+  } else if (!deep && bn == 128 && (a->force_stages == 2 || (!a->force_stages && p.num_kblocks <= g_shallow_kb)))
     rc = launch<128, 2>(tmA, tmB, q, gz, st);
   else
-  if (mc) {
-    switch (bn) {
-      case 32:
-        rc = shared_sm ? launch<32, 5, 2>(tmA_mc, tmB, q, gz, st) : launch<32, 6, 2>(tmA_mc, tmB, q, gz, st);
-        break;
-      case 64:
-        rc = shared_sm ? launch<64, 4, 2>(tmA_mc, tmB, q, gz, st) : launch<64, 6, 2>(tmA_mc, tmB, q, gz, st);
-        break;
-      default:
-        rc = shared_sm ? launch<128, 3, 2>(tmA_mc, tmB, q, gz, st) : launch<128, 6, 2>(tmA_mc, tmB, q, gz, st);
-        break;
-    }
-  } else
   switch (bn) {
     case 32:
       rc = deep ? (shared_sm ? launch<32, 5>(tmA, tmB, q, gz, st) : launch<32, 6>(tmA, tmB, q, gz, st))

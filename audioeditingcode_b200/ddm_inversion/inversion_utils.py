@@ -259,8 +259,8 @@ def inversion_forward_process(model: PipelineWrapper,
     use (default N // 2, the ratio of main_run.py's own defaults 200 / 100); it only orders the chunk launches so the
     reverse process can start early (see _PendingForward), never changes a result — and `group` — a torch.distributed process group over which the
     timestep chunks of ONE clip are sharded: chunk k runs on group rank k % world, `xts` is
-    broadcast from rank 0 once, and `zs` / `xts` are merged by one sum-all-reduce each at the end (every row is owned
-    by exactly one rank, the others contribute zeros, so the merge is exact and every rank returns the full tensors)."""
+    broadcast from rank 0 once, and `zs` / `xts` are merged at the end by one all-gather of each rank's owned rows
+    (parallel.merge_owned_rows_: every row is owned by exactly one rank, every rank returns the full tensors)."""
     if len(prompts) > 1 and extract_h_space:
         raise NotImplementedError("How do you split cfg_scales for hspace? TODO")
     if extract_h_space or extract_skipconns:

@@ -52,8 +52,6 @@ class CudaOps:
             self.lib.ae_set_gn_stream_min_bytes(int(os.environ["AEDIT_GN_STREAM_MIN_BYTES"]))
         if "AEDIT_PERSIST_MIN_TILES" in os.environ:
             self.lib.ae_set_persistent_min_tiles(int(os.environ["AEDIT_PERSIST_MIN_TILES"]))
-        if "AEDIT_GEMM_MULTICAST" in os.environ:
-            self.lib.ae_set_multicast(int(os.environ["AEDIT_GEMM_MULTICAST"]))
         if "AEDIT_ATTN_SPLIT" in os.environ:
             self.lib.ae_set_attention_split(int(os.environ["AEDIT_ATTN_SPLIT"]))
         if "AEDIT_SHALLOW_KB" in os.environ:
@@ -85,7 +83,7 @@ class CudaOps:
     def gemm(self, A, W, *, out_f32=None, out_bf16=None, bias=None, rowbias=None, rows_per_group=1, residual=None,
              act=0, alpha=1.0, conv=None, M=None, K=None, force_bn=0, batch=1, strideA=0, strideW=0, stride_out=0,
              stride_res=0, lda=None, ldw=None, force_split=0, ld_out_f32=None, ld_out_bf16=None, force_stages=0,
-             w_dynamic=False, force_csplit=0, colstats=None, cs_rows=0, force_persistent=0, force_multicast=0, softmax=None):
+             w_dynamic=False, colstats=None, cs_rows=0, force_persistent=0, softmax=None):
         """D = alpha*A@W^T (+bias)(+rowbias[row//rows_per_group])(+residual) -> act.  conv=(B,H,W,C,kh,kw,dh,dw)
         turns A (channels-last image) into an implicit-GEMM operand."""
         a = AeGemmArgs()
@@ -128,9 +126,7 @@ class CudaOps:
         a.force_split = force_split
         a.force_stages = force_stages
         a.w_dynamic = 1 if w_dynamic else 0
-        a.force_csplit = force_csplit
         a.force_persistent = force_persistent
-        a.force_multicast = force_multicast
         if softmax is not None:             # act 3: (keys per group, columns per text row, slot map, rows per sample, bias)
             L_, block, slot, rows, sbias = softmax
             a.act = 3

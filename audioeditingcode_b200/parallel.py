@@ -85,14 +85,32 @@ def edit_clips(edit_fn: Callable[[torch.Tensor], torch.Tensor], clips: Sequence[
 
 
 def merge_owned_rows_(t: torch.Tensor, owned: Sequence[int], group=None) -> torch.Tensor:
-    """In place: rows of `t` (dim 0) not in `owned` are zeroed, then one SUM all-reduce — afterwards every rank holds
-    every row from its owner, bit-exactly (x + 0 + ... + 0).  Rows must be owned by exactly one rank."""
-    keep = torch.zeros(t.shape[0], dtype=torch.bool, device=t.device)
+    """In place: afterwards every rank holds every row of `t` (dim 0) from the rank that owns it, bit-exactly.  Rows must
+    be owned by exactly one rank; ownership is arbitrary (the timestep chunks of the sharded forward process), so the
+    ranks first exchange their index lists (n_rows int64 each), then ONE all-gather of max-owned-count rows per rank —
+    1/world of the bytes of a zero-padded sum-all-reduce of the full tensor."""
+    if not (dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1):
+        return t
+    ws = dist.get_world_size(group)
+    n = t.shape[0]
+    idx = torch.full((n,), -1, dtype=torch.int64, device=t.device)
     if len(owned):
-        keep[torch.as_tensor(list(owned), device=t.device)] = True
-    t[~keep] = 0
-    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+        idx[:len(owned)] = torch.as_tensor(list(owned), dtype=torch.int64, device=t.device)
+    all_idx = torch.empty((ws * n,), dtype=torch.int64, device=t.device)      # concatenated layout (gloo and nccl)
+    dist.all_gather_into_tensor(all_idx, idx, group=group)
+    all_idx = all_idx.view(ws, n)
+    counts = (all_idx >= 0).sum(1)
+    per = int(counts.max().item())
+    if int(counts.sum().item()) != n or per == 0:
+        raise ValueError(f"merge_owned_rows_: {int(counts.sum().item())} owned rows over the group for a tensor of {n} rows")
+    send = torch.zeros((per, *t.shape[1:]), dtype=t.dtype, device=t.device)
+    if len(owned):
+        send[:len(owned)] = t[idx[:len(owned)]]
+    recv = torch.empty((ws * per, *t.shape[1:]), dtype=t.dtype, device=t.device)
+    dist.all_gather_into_tensor(recv, send, group=group)
+    recv = recv.view(ws, per, *t.shape[1:])
+    valid = all_idx[:, :per] >= 0
+    t[all_idx[:, :per][valid]] = recv[valid]
     return t
 
 

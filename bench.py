@@ -140,7 +140,7 @@ def build_model(spec, device):
     return m, cfg
 
 
-def run_job(m, spec, x0_dev, forward_batch):
+def run_job(m, spec, x0_dev, forward_batch, fwd_group=None):
     """One bench step.  mode "edit" (default): inversion + edit of the clip(s) in x0_dev ([K,C,H,W]; K > 1 -> the
     multi-clip entry points, B = K*(1+P) rows per launch); "sdedit": add_noise + tstart forward_directional steps;
     "pc": one get_eigenvectors call (n_ev directions, `iters` subspace iterations)."""
@@ -150,7 +150,8 @@ def run_job(m, spec, x0_dev, forward_batch):
     src, tgt = "a recording of a dog barking", "a recording of a cat meowing"
     if mode == "edit" and x0_dev.shape[0] == 1:
         _, zs, xts, _ = IU.inversion_forward_process(m, x0_dev, etas=1.0, prompts=[src], cfg_scales=[spec["cfg_src"]],
-                                                     num_inference_steps=N, numerical_fix=True, forward_batch=forward_batch)
+                                                     num_inference_steps=N, numerical_fix=True, forward_batch=forward_batch,
+                                                     group=fwd_group)
         w, _ = IU.inversion_reverse_process(m, xT=xts, tstart=torch.tensor([ts], dtype=torch.int), etas=1.0,
                                             prompts=[tgt], neg_prompts=[""], cfg_scales=[spec["cfg_tar"]], zs=zs[:ts])
         return w
@@ -402,6 +403,10 @@ def main():
     ap.add_argument("--cpu-steps", type=int, default=0, help="CFG steps of the cpu_baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ends", action="store_true", help="skip the STFT / VAE / vocoder timing")
+    ap.add_argument("--shard-forward", action="store_true",
+                    help="N > 1: strong scaling of ONE clip — the timestep chunks of its forward process are sharded over "
+                         "the ranks (all-gather of the owned zs / xts rows), every rank then runs the sequential reverse "
+                         "process (replicas); default is one clip job per rank (weak)")
     args = ap.parse_args()
     spec = CONFIGS[args.config]
     mode = spec.get("mode", "edit")
@@ -457,7 +462,9 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     m, cfg = build_model(spec, dev)
     ops = m.engine.ops
-    g = torch.Generator().manual_seed(1 + rank)
+    shard_fwd = args.shard_forward and world > 1 and mode == "edit" and K == 1
+    fwd_group = dist.group.WORLD if shard_fwd else None
+    g = torch.Generator().manual_seed(1 if shard_fwd else 1 + rank)       # sharded: every rank holds the same clip
     x0_host = (0.5 * torch.randn(K, cfg.in_channels, spec["H"], spec["W"], generator=g)).pin_memory()
     x0_dev = x0_host.to(dev)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > L2 (126 MB)
@@ -484,14 +491,14 @@ def main():
         return ms
 
     def job_resident():
-        run_job(m, spec, x0_dev, args.forward_batch)
+        run_job(m, spec, x0_dev, args.forward_batch, fwd_group)
 
     out_rows = spec["n_ev"] if mode == "pc" else K
     e2e_out = torch.empty(out_rows, cfg.in_channels, spec["H"], spec["W"]).pin_memory()
 
     def job_e2e():
         x = x0_host.to(dev, non_blocking=True)
-        w = run_job(m, spec, x, args.forward_batch)
+        w = run_job(m, spec, x, args.forward_batch, fwd_group)
         e2e_out.copy_(w, non_blocking=True)
         torch.cuda.current_stream().synchronize()
 
@@ -504,7 +511,7 @@ def main():
     clocks = cs.summary()
     ms_e2e = timed_loop(job_e2e, args.steps)
     # pc under torchrun shards ONE extraction over the ranks (strong scaling); everything else is one job per rank (weak)
-    strong = mode == "pc" and world > 1
+    strong = (mode == "pc" and world > 1) or shard_fwd
     total_steps = steps_per_job * args.steps * (1 if strong else world)
     from audioeditingcode_b200 import _lib as _aelib
     op_dtype = "fp16" if _aelib.load().ae_operand_dtype() == 1 else "bf16"
@@ -520,7 +527,8 @@ def main():
                         "precision": f"{op_dtype} tensor-core operands (AEDIT_OPERANDS), fp32 accumulate / residual stream / "
                                      "scheduler state",
                         "denoising_steps_per_bench_step": steps_per_job, "forward_batch_timesteps": args.forward_batch,
-                        "parallelism": (f"pc-directions-sharded-{world}" if strong else f"clip-dp{world}"),
+                        "parallelism": (f"forward-timesteps-sharded-{world}+reverse-replicated" if shard_fwd else
+                                        f"pc-directions-sharded-{world}" if strong else f"clip-dp{world}"),
                         "l2": "256 MiB flush between jobs; weights (1.5 GB) >> L2",
                         "lanes": ("forward chunks and reverse steps of the clip on two streams (reverse lane high priority), "
                                   f"fast path taken {getattr(m, 'overlap_hits', 0)}x") if getattr(m, "overlap_hits", 0)

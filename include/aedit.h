@@ -77,9 +77,6 @@ void ae_set_headroom(int on);
 void ae_set_persistent_min_tiles(int tiles);
 /* Tile model constants: what a split-K reduce pass is charged (launch nanoseconds, bytes per microsecond). */
 void ae_set_tile_model_reduce(int launch_ns, int bytes_per_us);
-/* 1: sub-wave linear GEMM grids with an even number of N tiles run as CTA pairs (thread-block clusters of 2 along N)
- * that share the A tile by TMA multicast: each CTA pulls half of the A panel through L2.  Same bits. */
-void ae_set_multicast(int on);
 /* DIAGNOSTIC ONLY: drop the launches of kernel families (1 GEMM, 2 split-K reduce, 4 GroupNorm statistics,
  * 8 GroupNorm apply, 16 LayerNorm, 32 attention) to measure a family's marginal cost inside a captured graph
  * (tools/kernel_share.py).  Outputs are meaningless while the mask is non-zero. */
@@ -252,8 +249,6 @@ typedef struct {
   float* splitk_ws;
   int64_t splitk_ws_bytes;
   int32_t force_split;
-  int32_t force_csplit; /* cluster split-K (K slices of a tile in one thread-block cluster, DSMEM reduction, single
-                           launch): 0 auto, 1 never, 2/4/8 exactly that cluster size */
   int32_t w_dynamic;    /* 1 if W is written by a preceding kernel on the stream (e.g. K or V^T of an unfused attention):
                            disables the early W prefetch that otherwise overlaps the previous kernel's tail */
   int32_t force_stages; /* 0 auto (deep 6-stage ring for grids <= 160 CTAs, else 3 stages x 2-3 CTAs/SM), 3 or 6 */
@@ -266,7 +261,6 @@ typedef struct {
   int64_t* colstats;
   int32_t cs_rows_per_sample;
   int32_t force_persistent; /* 0 auto (ae_set_persistent_min_tiles), 1 persistent kernel, -1 one CTA per tile */
-  int32_t force_multicast;  /* 0 auto (ae_set_multicast), 1 pair the N tiles and TMA-multicast the A tile, -1 never */
   /* act == 3 — grouped softmax epilogue.  Cross-attention against FROZEN text (attention.py:234-262 with context =
    * the prompt embedding, constant over all denoising steps) folds into two small GEMMs:
    *   scores[m, (r,h,l)] = LN(x)[m,:] . KW[(r,h,l),:],  KW[(r,h,l), c] = scale * sum_j K_r[l, h*d+j] * Wq[h*d+j, c]

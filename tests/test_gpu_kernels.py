@@ -171,57 +171,6 @@ def test_groupnorm_from_column_statistics(ops, B, HW, C1, C2, silu, stream):
     assert torch.equal(raw, x.to(BF))
 
 
-@pytest.mark.parametrize("M,N,K,CS", [(128, 960, 960, 2), (128, 960, 960, 4), (128, 960, 8640, 8), (512, 576, 576, 2),
-                                      (100, 200, 1000, 4), (2048, 384, 384, 2), (128, 7680, 960, 0), (256, 64, 4096, 8)])
-def test_gemm_cluster_splitk(ops, M, N, K, CS):
-    """cluster split-K: the K slices of one tile run as a thread-block cluster and reduce through distributed
-    shared memory in rank order; every epilogue term applied once; bit-reproducible."""
-    A = rnd((M, K), 1, dtype=BF)
-    W = rnd((N, K), 2, 1 / math.sqrt(K), dtype=BF)
-    bias, res = rnd((N,), 3), rnd((M, N), 4)
-    rowbias = rnd(((M + 63) // 64, N), 5)
-    o32 = torch.empty(M, N, device="cuda")
-    o16 = torch.empty(M, N, device="cuda", dtype=BF)
-    kw = dict(bias=bias, rowbias=rowbias, rows_per_group=64, residual=res, act=1, alpha=0.5)
-    ops.gemm(A, W, out_f32=o32, out_bf16=o16, force_csplit=CS, **kw)
-    ref = F.silu(0.5 * (A.float() @ W.float().t()) + bias + res + rowbias.repeat_interleave(64, 0)[:M])
-    assert relerr(o32, ref) < 2e-5
-    assert relerr(o16, ref) < 4e-3
-    o_b = torch.empty_like(o32)
-    ops.gemm(A, W, out_f32=o_b, force_csplit=CS, **kw)
-    assert torch.equal(o32, o_b)
-    # in-place residual (out == residual) as used by the transformer blocks
-    hs = res.clone()
-    ops.gemm(A, W, out_f32=hs, bias=bias, residual=hs, force_csplit=CS)
-    assert relerr(hs, A.float() @ W.float().t() + bias + res) < 2e-5
-
-
-def test_gemm_cluster_splitk_conv_and_geglu(ops):
-    B, H, Wd, C, Co = 2, 32, 2, 960, 960
-    x = rnd((B, H, Wd, C), 1, dtype=BF)
-    wt = rnd((Co, C, 3, 3), 2, 1 / math.sqrt(C * 9), dtype=BF)
-    bias = rnd((Co,), 3)
-    Wp = wt.permute(0, 2, 3, 1).reshape(Co, -1).contiguous()
-    out = torch.empty(B * H * Wd, Co, device="cuda")
-    for cs in (0, 2, 4, 8):
-        ops.gemm(x, Wp, out_f32=out, bias=bias, conv=(B, H, Wd, C, 3, 3, 1, 1), force_csplit=cs)
-        ref = F.conv2d(x.float().permute(0, 3, 1, 2), wt.float(), bias, padding=1).permute(0, 2, 3, 1).reshape(-1, Co)
-        assert relerr(out, ref) < 2e-5, cs
-    # GEGLU epilogue through the cluster reduction
-    M, Cc = 128, 960
-    inner = 4 * Cc
-    xx = rnd((M, Cc), 4, dtype=BF)
-    Wf = rnd((2 * inner, Cc), 5, 1 / math.sqrt(Cc), dtype=BF)
-    bf = rnd((2 * inner,), 6)
-    idx = torch.arange(inner).view(-1, 16)
-    perm = torch.cat([idx, idx + inner], 1).reshape(-1).cuda()
-    o = torch.empty(M, inner, device="cuda", dtype=BF)
-    ops.gemm(xx, Wf[perm].contiguous(), out_bf16=o, bias=bf[perm].contiguous(), act=2, force_csplit=2)
-    h = xx.float() @ Wf.float().t() + bf
-    a, gt = h.chunk(2, -1)
-    assert relerr(o, a * F.gelu(gt)) < 4e-3
-
-
 @pytest.mark.parametrize("M,N,K,kind", [
     (128 * 160 + 37, 384, 384, "res"),        # > one tile per SM, ragged M tail, residual + bias + fp32/bf16 out (staged)
     (128 * 300, 192, 1728, "rowbias"),        # BN = 64 tiles, time-embedding row bias (staged, multi-wave fp32 out)
@@ -272,26 +221,7 @@ def test_gemm_persistent_same_bits(ops, M, N, K, kind):
         assert relerr(outs[1][0], ref) < 2e-5
 
 
-@pytest.mark.parametrize("M,N,K,S,bn", [(128, 960, 960, 1, 0), (128, 960, 960, 1, 64), (512, 576, 576, 1, 0),
-                                        (128, 960, 3840, 0, 0), (128, 960, 3840, 3, 32), (100, 960, 960, 1, 0),
-                                        (128, 7680, 960, 1, 128), (256, 2880, 960, 1, 0), (128, 64, 4096, 8, 32)])
-def test_gemm_multicast_pairs_same_bits(ops, M, N, K, S, bn):
-    """CTA pairs that share the A tile by TMA multicast (sub-wave linear grids) produce the bits of the unpaired
-    kernel, with and without split-K, ragged M included."""
-    A = rnd((M, K), 1, dtype=BF)
-    W = rnd((N, K), 2, 1 / math.sqrt(K), dtype=BF)
-    bias, res = rnd((N,), 3), rnd((M, N), 4)
-    outs = []
-    for mc in (-1, 1, 1):
-        o32 = torch.zeros(M, N, device="cuda")
-        o16 = torch.zeros(M, N, device="cuda", dtype=BF)
-        ops.gemm(A, W, out_f32=o32, out_bf16=o16, bias=bias, residual=res, force_split=S, force_bn=bn,
-                 force_multicast=mc)
-        outs.append((o32, o16))
-    for a, b, c in zip(*outs):
-        assert torch.equal(a, b) and torch.equal(b, c)
-    ref = A.float() @ W.float().t() + bias + res
-    assert relerr(outs[1][0], ref) < 2e-5
+
 
 
 def test_gemm_persistent_implicit_conv(ops):

@@ -87,7 +87,7 @@ def test_subspace_step_open_loop_vs_reference(key):
             assert torch.allclose(corr.cpu(), g[f"{key}_in_corr"][i - 1], atol=2e-4), f"iter {i} corr"
         # orthonormality (CholeskyQR2): |Q Q^T - I| at rounding level
         if n > 1:
-            gram = eig @ eig.T
+            gram = eig.double() @ eig.double().T           # fp64: independent of torch's TF32 matmul switch
             assert (gram - torch.eye(n, device="cuda")).abs().max().item() < 2e-6
         prev = ref_unit.contiguous()        # open loop: the reference's own previous iterate
 

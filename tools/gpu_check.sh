@@ -1,5 +1,5 @@
 #!/bin/bash
-# The GPU validation sequence of this repo, for `gpurun -- 'bash tools/gpu_check.sh [quick|full|ncu|sanitize]'`.
+# The GPU validation sequence of this repo, for `gpurun -- 'bash tools/gpu_check.sh [quick|full|ncu|sanitize|synccheck]'`.
 # Everything it writes goes to gpurun_out/ (scratch); copy what should be kept into profiles/.
 set -u
 mode=${1:-quick}
@@ -15,9 +15,14 @@ if [ "$mode" = full ]; then
   python tools/attn_bench.py > gpurun_out/attn_bench.log 2>&1
   python tools/hbm_kernels.py --json gpurun_out/hbm_kernels.json > gpurun_out/hbm_kernels.log 2>&1
 fi
+if [ "$mode" = synccheck ]; then tools="synccheck"; mode=sanitize; else tools="memcheck racecheck synccheck"; fi
 if [ "$mode" = sanitize ]; then
-  for tool in memcheck racecheck synccheck; do
-    timeout 1200 compute-sanitizer --tool $tool --error-exitcode 9 python -m pytest tests/test_gpu_kernels.py tests/test_gpu_pc_drift.py -x -q -k "not large" > gpurun_out/sanitizer_$tool.log 2>&1; echo "$tool rc=$?"; tail -3 gpurun_out/sanitizer_$tool.log
+  for tool in $tools; do
+    timeout 1200 compute-sanitizer --tool $tool --error-exitcode 9 --print-limit 100000 python -m pytest tests/test_gpu_kernels.py tests/test_gpu_pc_drift.py -x -q -k "not large" > gpurun_out/sanitizer_$tool.full 2>&1; echo "$tool rc=$?"
+    # keep the summary lines and one line per distinct error site (kernel + source line), not every thread's report
+    grep -E "passed|failed|SUMMARY" gpurun_out/sanitizer_$tool.full > gpurun_out/sanitizer_$tool.log
+    grep "=========     at " gpurun_out/sanitizer_$tool.full | sed 's/+0x[0-9a-f]* in / in /' | sort | uniq -c >> gpurun_out/sanitizer_$tool.log
+    rm -f gpurun_out/sanitizer_$tool.full; tail -6 gpurun_out/sanitizer_$tool.log
   done
 fi
 if [ "$mode" = ncu ]; then

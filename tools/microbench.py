@@ -37,7 +37,7 @@ def bench(name, fn, R=100, reps=5, flops=0.0, launches_per_call=1):
     return us
 
 
-def gemm_case(M, N, K, bn, conv=None, res=False, split=0, csplit=0):
+def gemm_case(M, N, K, bn, conv=None, res=False, split=0):
     if conv is not None:
         B, H, W, C = conv
         A = torch.randn(B, H, W, C, device=dev).to(BF)
@@ -50,7 +50,7 @@ def gemm_case(M, N, K, bn, conv=None, res=False, split=0, csplit=0):
     r = torch.randn(M, N, device=dev) if res else None
 
     def fn():
-        ops.gemm(A, Wt, out_f32=out, bias=bias, residual=r, force_bn=bn, force_split=split, force_csplit=csplit,
+        ops.gemm(A, Wt, out_f32=out, bias=bias, residual=r, force_bn=bn, force_split=split,
                  conv=None if conv is None else (*conv, 3, 3, 1, 1))
     return fn, 2.0 * M * N * K
 
@@ -82,23 +82,11 @@ for (B, HW, C) in [(2, 64, 960), (2, 4096, 192), (1, 4096, 192), (2, 4096, 384),
     ops.lib.ae_set_gn_fused(1)
 
 for bn in (32, 64, 128):
-    fn, fl = gemm_case(128, 960, 960, bn, csplit=1)
+    fn, fl = gemm_case(128, 960, 960, bn, split=1)
     bench(f"gemm M=128 N=960 K=960 bn={bn} (no split)", fn, flops=fl)
 for bn in (32, 64, 128):
-    fn, fl = gemm_case(128, 960, 8640, bn, split=1, csplit=1)
+    fn, fl = gemm_case(128, 960, 8640, bn, split=1)
     bench(f"gemm M=128 N=960 K=8640 bn={bn} (no split)", fn, flops=fl)
-for cs in (1, 2, 4, 8):
-    fn, fl = gemm_case(128, 960, 960, 128, csplit=cs)
-    bench(f"gemm M=128 N=960 K=960 bn=128 cluster-split={cs}", fn, flops=fl)
-for cs in (1, 2, 4, 8):
-    fn, fl = gemm_case(128, 960, 8640, 128, csplit=cs)
-    bench(f"gemm M=128 N=960 K=8640 bn=128 cluster-split={cs}", fn, flops=fl)
-for cs in (1, 2, 4):
-    fn, fl = gemm_case(2048, 384, 384, 128, csplit=cs)
-    bench(f"gemm M=2048 N=384 K=384 bn=128 cluster-split={cs}", fn, flops=fl)
-for cs in (1, 2, 4):
-    fn, fl = gemm_case(512, 576, 2304, 128, csplit=cs)
-    bench(f"gemm M=512 N=576 K=2304 bn=128 cluster-split={cs}", fn, flops=fl)
 for sp in (4, 9, 18):
     fn, fl = gemm_case(128, 960, 8640, 128, split=sp)
     bench(f"gemm M=128 N=960 K=8640 bn=128 ws-split={sp} (2 launches)", fn, flops=fl)
