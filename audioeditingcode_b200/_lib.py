@@ -51,14 +51,12 @@ _SIGS = {
     "ae_set_skip_mask": (None, [i32]),
     "ae_set_tile_model_reduce": (None, [i32, i32]),
     "ae_set_persistent_min_tiles": (None, [i32]),
-    "ae_set_headroom": (None, [i32]),
     "ae_set_shallow_kblocks": (None, [i32]),
     "ae_set_pdl_extra": (None, [i32]),
     "ae_set_gn_stream_min_bytes": (None, [i64]),
     "ae_set_splitk_ctas": (None, [i32]),
     "ae_set_fast_epilogue": (None, [i32]),
     "ae_set_tile_model": (None, [i32]),
-    "ae_set_gn_fused": (None, [i32]),
     "ae_sched_create": (i32, [vp, i32, f32, vp, i32, i32, C.POINTER(vp)]),
     "ae_sched_create_from_rows": (i32, [C.POINTER(AeSchedRow), i32, i32, i32, C.POINTER(vp)]),
     "ae_sched_set_eta": (i32, [vp, vp, vp]),
@@ -84,10 +82,6 @@ _SIGS = {
     "ae_geglu": (i32, [vp, i64, i32, vp, vp]),
     "ae_attention": (i32, [vp, i64, i64, vp, i64, i64, vp, i64, i64, vp, vp, i64, i32, i32, i32, i32, i32, f32, vp,
                            i64, i64, vp]),
-    "ae_attention_ws": (i32, [vp, i64, i64, vp, i64, i64, vp, i64, i64, vp, vp, i64, i32, i32, i32, i32, i32, f32, vp,
-                              i64, i64, vp, i64, vp]),
-    "ae_attention_workspace_bytes": (i64, [i32, i32, i32, i32]),
-    "ae_set_attention_split": (None, [i32]),
     "ae_set_attention_tc": (None, [i32]),
     "ae_timestep_embedding": (i32, [vp, i32, i32, vp, vp]),
     "ae_upsample_nearest": (i32, [vp, i32, i32, i32, i32, i32, i32, vp, vp]),

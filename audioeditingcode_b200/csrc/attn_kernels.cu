@@ -32,13 +32,6 @@ struct AttnArgs {
   long long ld_bias;
   int Tq, Tk;
   float scale_log2;  // scale * log2(e)
-  // split-KV (small grids: the reverse process at batch 2): blockIdx.x = q_tile * nsplit + split; every split walks
-  // its share of the key tiles and parks its un-normalised accumulator fragments + row statistics in `ws`; the last
-  // split of a (batch, head, q tile) to arrive (ticket counter) merges them in split order 0..nsplit-1 — fixed order,
-  // so the result does not depend on which CTA happens to be last — and writes the output.
-  int nsplit;
-  float* ws;               // [slots][nsplit][128 threads][NB*4 + 4] fp32
-  unsigned int* counters;  // [slots], zero between launches (the merging CTA re-arms its counter)
 };
 
 __device__ __forceinline__ float fast_exp2(float x) {
@@ -86,9 +79,7 @@ __global__ void __launch_bounds__(kAttnThreads) attention_kernel(AttnArgs a) {
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t4 = lane & 3;
-  const int nsplit = a.nsplit;
-  const int qt = blockIdx.x / nsplit, split = blockIdx.x - qt * nsplit;
-  const int q0 = qt * BQ;
+  const int q0 = blockIdx.x * BQ;
   const int head = blockIdx.y;
   const int b = blockIdx.z;
   const int bkv = a.kv_map ? a.kv_map[b] : b;
@@ -97,10 +88,8 @@ __global__ void __launch_bounds__(kAttnThreads) attention_kernel(AttnArgs a) {
   const op_t* vp = a.v + (long long)bkv * a.bs_v + (long long)head * D;
   const float* biasp = a.bias ? a.bias + (long long)bkv * a.ld_bias : nullptr;
 
-  const int ntiles_all = (a.Tk + BKV - 1) / BKV;
-  const int tps = (ntiles_all + nsplit - 1) / nsplit;          // key tiles per split
-  const int tile0 = split * tps;
-  const int ntiles = max(0, min(ntiles_all, tile0 + tps) - tile0);   // this CTA's tiles: tile0 .. tile0 + ntiles - 1
+  constexpr int tile0 = 0;
+  const int ntiles = (a.Tk + BKV - 1) / BKV;
   // prologue: Q and the first NS-1 key/value tiles, one commit group per tile (empty groups keep the count uniform)
   load_tile<D>(sQ, qp, a.ld_q, q0, a.Tq, tid);
 #pragma unroll
@@ -252,57 +241,6 @@ __global__ void __launch_bounds__(kAttnThreads) attention_kernel(AttnArgs a) {
   }
 
   pdl_trigger();   // key/value loop done: the normalise + store tail may overlap the next launch
-  if (nsplit > 1) {
-    constexpr int FR = NB * 4 + 4;     // floats per thread: accumulator fragments, m_run[2], l_run[2]
-    const long long slot = ((long long)b * gridDim.y + head) * (gridDim.x / nsplit) + qt;
-    float* mine = a.ws + ((slot * nsplit + split) * kAttnThreads + tid) * FR;
-#pragma unroll
-    for (int n = 0; n < NB; ++n)
-      __stcg(reinterpret_cast<float4*>(mine) + n, make_float4(o_acc[n][0], o_acc[n][1], o_acc[n][2], o_acc[n][3]));
-    __stcg(reinterpret_cast<float4*>(mine) + NB, make_float4(m_run[0], m_run[1], l_run[0], l_run[1]));
-    __shared__ int s_last;
-    __threadfence();
-    __syncthreads();
-    if (tid == 0) s_last = (atomicAdd(a.counters + slot, 1u) == (unsigned)nsplit - 1u) ? 1 : 0;
-    __syncthreads();
-    if (!s_last) return;
-    __threadfence();
-    // merge in split order (all loads of a split are independent; nsplit <= 8)
-    float mm[2] = {-INFINITY, -INFINITY};
-    float4 st[8];
-#pragma unroll
-    for (int sp = 0; sp < 8; ++sp) {
-      if (sp < nsplit) {
-        st[sp] = __ldcg(reinterpret_cast<const float4*>(a.ws + ((slot * nsplit + sp) * kAttnThreads + tid) * FR) + NB);
-        mm[0] = fmaxf(mm[0], st[sp].x);
-        mm[1] = fmaxf(mm[1], st[sp].y);
-      }
-    }
-    l_run[0] = l_run[1] = 0.f;
-#pragma unroll
-    for (int n = 0; n < NB; ++n)
-#pragma unroll
-      for (int k = 0; k < 4; ++k) o_acc[n][k] = 0.f;
-#pragma unroll
-    for (int sp = 0; sp < 8; ++sp) {
-      if (sp < nsplit) {
-        const float w0 = st[sp].x == -INFINITY ? 0.f : fast_exp2((st[sp].x - mm[0]) * a.scale_log2);
-        const float w1 = st[sp].y == -INFINITY ? 0.f : fast_exp2((st[sp].y - mm[1]) * a.scale_log2);
-        l_run[0] = fmaf(st[sp].z, w0, l_run[0]);
-        l_run[1] = fmaf(st[sp].w, w1, l_run[1]);
-        const float4* src = reinterpret_cast<const float4*>(a.ws + ((slot * nsplit + sp) * kAttnThreads + tid) * FR);
-#pragma unroll
-        for (int n = 0; n < NB; ++n) {
-          const float4 v = __ldcg(src + n);
-          o_acc[n][0] = fmaf(v.x, w0, o_acc[n][0]);
-          o_acc[n][1] = fmaf(v.y, w0, o_acc[n][1]);
-          o_acc[n][2] = fmaf(v.z, w1, o_acc[n][2]);
-          o_acc[n][3] = fmaf(v.w, w1, o_acc[n][3]);
-        }
-      }
-    }
-    if (tid == 0) a.counters[slot] = 0u;   // re-arm for the next launch (stream-ordered after this kernel)
-  }
   // ---- normalise and store (bf16 pairs)
   const int r0 = q0 + warp * 16 + g;
   const float inv0 = l_run[0] > 0.f ? 1.f / l_run[0] : 0.f;
@@ -332,7 +270,7 @@ int launch_attn(const AttnArgs& a, int B, int heads, cudaStream_t st) {
     if (e != cudaSuccess) return fail(AE_ECUDA, "attention smem attribute: %s", cudaGetErrorString(e));
     attr_set = true;
   }
-  dim3 grid(((a.Tq + BQ - 1) / BQ) * a.nsplit, heads, B);
+  dim3 grid((a.Tq + BQ - 1) / BQ, heads, B);
   launch_kernel_family(8, attention_kernel<D>, dim3(grid), dim3(kAttnThreads), (size_t)(C::kSmemBytes), st, a);
   return launched("ae_attention");
 }
@@ -350,19 +288,10 @@ int attention_tc_try(const void* q, int64_t ld_q, int64_t q_bs, const void* k, i
 
 using namespace aedit;
 
-static thread_local int g_attn_split = 1;   // 0 auto, 1 never (default: measured slower), n > 1: that many key splits
-extern "C" void ae_set_attention_split(int n) { g_attn_split = n; }
-
-extern "C" int64_t ae_attention_workspace_bytes(int B, int heads, int Tq, int d) {
-  const int64_t slots = (int64_t)B * heads * ((Tq + BQ - 1) / BQ);
-  const int64_t fr = (int64_t)((d + 15) / 16 * 16 / 8) * 4 + 4;
-  return slots * 4 + 256 + slots * 8 * kAttnThreads * fr * 4;   // counters, then up to 8 splits of fragments
-}
-
 static int attention_impl(const void* q, int64_t ld_q, int64_t q_bs, const void* k, int64_t ld_k, int64_t k_bs,
                           const void* v, int64_t ld_v, int64_t v_bs, const int32_t* kv_batch_map, const float* key_bias,
                           int64_t ld_bias, int B, int heads, int d, int Tq, int Tk, float scale, void* out, int64_t ld_o,
-                          int64_t o_bs, void* workspace, int64_t workspace_bytes, ae_stream stream) {
+                          int64_t o_bs, ae_stream stream) {
 
   AE_CHECK_ARG(q && k && v && out && B > 0 && heads > 0 && Tq > 0 && Tk > 0, "ae_attention: bad argument");
   AE_CHECK_ARG(ld_q % 8 == 0 && ld_k % 8 == 0 && ld_v % 8 == 0 && ld_o % 2 == 0,
@@ -386,31 +315,6 @@ static int attention_impl(const void* q, int64_t ld_q, int64_t q_bs, const void*
   a.Tq = Tq;
   a.Tk = Tk;
   a.scale_log2 = scale * 1.4426950408889634f;
-  a.nsplit = 1;
-  a.ws = nullptr;
-  a.counters = nullptr;
-  {
-    // split the keys when the grid cannot fill the machine (reverse process at batch 2: 256 CTAs of a 16-tile chain at
-    // T = 1024) — ~6 CTAs of this kernel fit on an SM
-    const long long qtiles = (Tq + BQ - 1) / BQ, base = qtiles * heads * B;
-    const int ntiles = (Tk + BKV - 1) / BKV;
-    int ns = 1;
-    if (workspace && g_attn_split != 1 && ntiles >= 4) {
-      if (g_attn_split > 1)
-        ns = g_attn_split;
-      else if (base < 444)
-        ns = (int)((888 + base / 2) / base);
-      if (ns > ntiles / 2) ns = ntiles / 2;
-      if (ns > 8) ns = 8;
-      while (ns > 1 && (ns - 1) * ((ntiles + ns - 1) / ns) >= ntiles) --ns;   // no empty split
-      if (ns > 1 && ae_attention_workspace_bytes(B, heads, Tq, d) > workspace_bytes) ns = 1;
-    }
-    if (ns > 1) {
-      a.nsplit = ns;
-      a.counters = reinterpret_cast<unsigned int*>(workspace);
-      a.ws = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + ((base * 4 + 255) / 256) * 256);
-    }
-  }
   cudaStream_t st = as_stream(stream);
   if (g_skip_mask & 32) return AE_OK;
   {
@@ -440,14 +344,5 @@ extern "C" int ae_attention(const void* q, int64_t ld_q, int64_t q_bs, const voi
                             int64_t ld_bias, int B, int heads, int d, int Tq, int Tk, float scale, void* out, int64_t ld_o,
                             int64_t o_bs, ae_stream stream) {
   return attention_impl(q, ld_q, q_bs, k, ld_k, k_bs, v, ld_v, v_bs, kv_batch_map, key_bias, ld_bias, B, heads, d, Tq, Tk,
-                        scale, out, ld_o, o_bs, nullptr, 0, stream);
-}
-
-extern "C" int ae_attention_ws(const void* q, int64_t ld_q, int64_t q_bs, const void* k, int64_t ld_k, int64_t k_bs,
-                               const void* v, int64_t ld_v, int64_t v_bs, const int32_t* kv_batch_map,
-                               const float* key_bias, int64_t ld_bias, int B, int heads, int d, int Tq, int Tk, float scale,
-                               void* out, int64_t ld_o, int64_t o_bs, void* workspace, int64_t workspace_bytes,
-                               ae_stream stream) {
-  return attention_impl(q, ld_q, q_bs, k, ld_k, k_bs, v, ld_v, v_bs, kv_batch_map, key_bias, ld_bias, B, heads, d, Tq, Tk,
-                        scale, out, ld_o, o_bs, workspace, workspace_bytes, stream);
+                        scale, out, ld_o, o_bs, stream);
 }

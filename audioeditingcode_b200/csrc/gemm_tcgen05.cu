@@ -1163,22 +1163,17 @@ int launch_persistent(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gemm
   return launched("ae_gemm(persistent)");
 }
 
-constexpr int kHeadroomSmem = 116 * 1024;
-thread_local int g_headroom = 0;
-
 template <int BN, int STAGES>
 int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmDev& p, int gz, cudaStream_t st) {
   using L = SmemLayout<BN, STAGES>;
   static bool attr_set = false;
-  constexpr int kMaxDyn = L::kTotal > kHeadroomSmem ? L::kTotal : kHeadroomSmem;
+  constexpr int kMaxDyn = L::kTotal;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDyn);
     if (e != cudaSuccess) return fail(AE_ECUDA, "cudaFuncSetAttribute(smem=%d): %s", kMaxDyn, cudaGetErrorString(e));
     attr_set = true;
   }
-  // g_headroom (ae_set_headroom): request at least half of the SM's shared memory, i.e. ONE CTA of this grid per SM —
-  // the other half stays free for the sub-wave kernels of a latency-bound chain running on another stream
-  const size_t dyn_smem = (g_headroom && L::kTotal < kHeadroomSmem) ? (size_t)kHeadroomSmem : (size_t)L::kTotal;
+  const size_t dyn_smem = (size_t)L::kTotal;
   if (g_skip_mask & 1) return AE_OK;
   const unsigned tm = (unsigned)((p.M + BM - 1) / BM), tn = (unsigned)((p.N + BN - 1) / BN);
   dim3 grid = p.m_in_x ? dim3(tm, tn, gz) : dim3(tn, tm, gz);
@@ -1201,7 +1196,6 @@ using namespace aedit;
 extern "C" void ae_set_pdl(int mode) { g_use_pdl = (mode == 1 || mode == 2) ? mode : 0; }
 extern "C" void ae_set_launch_priority(int prio) { g_launch_priority = prio; }
 extern "C" void ae_set_skip_mask(int mask) { g_skip_mask = mask; }
-extern "C" void ae_set_headroom(int on) { g_headroom = on ? 1 : 0; }
 extern "C" void ae_set_pdl_extra(int mask) { g_pdl_extra = mask; }
 extern "C" int ae_greatest_priority(void) {
   int least = 0, greatest = 0;

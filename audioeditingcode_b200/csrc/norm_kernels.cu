@@ -407,200 +407,6 @@ __global__ void __launch_bounds__(kGNThreads) gn_apply_stream_kernel(GNArgs a, i
   pdl_trigger();
 }
 
-// ---- small-batch path: ONE launch per GroupNorm.  grid (S, B) with S*B <= #SMs, so every CTA is resident at the
-// same time (one per SM).  The S CTAs of a sample each own HW/S positions: (1) read them once into shared memory,
-// (2) reduce them to per-group partial sums (double) published to the workspace, (3) rendezvous on the sample's
-// arrival counter (release / acquire at gpu scope; a lost peer traps instead of hanging), (4) every CTA reduces the S
-// partials of its sample in a fixed shape (same bits in every CTA, independent of what else is in the batch) and
-// (5) normalises its shared-memory slice.  One launch instead of stats + apply, and the tensor is read once.
-// Only used when the whole grid fits on the machine; callers that run several such grids CONCURRENTLY (two streams)
-// must disable it (ae_set_gn_fused(0)), because waiting CTAs of two grids could starve each other of SMs.
-__global__ void __launch_bounds__(512) gn_resident_kernel(GNArgs a) {
-  pdl_trigger();
-  pdl_wait();
-  extern __shared__ __align__(16) float sm[];
-  // layout: mean[G] rstd[G] | A[C] B[C] | red[TY][2C] | stage[chunk][C]
-  const int TX = blockDim.x, TY = blockDim.y;
-  float* s_mean = sm;
-  float* s_rstd = s_mean + a.G;
-  float* s_A = s_rstd + a.G;
-  float* s_B = s_A + a.C;
-  float* s_red = s_B + a.C;
-  float* s_stage = s_red + (size_t)TY * 2 * a.C;
-  const int s = blockIdx.x, b = blockIdx.y;
-  const int tx = threadIdx.x, ty = threadIdx.y;
-  const int tid = ty * TX + tx, nthr = TX * TY;
-  const int lane = tid & 31, wid = tid >> 5, nw = nthr >> 5;
-  const long long p0 = (long long)s * a.chunk;
-  const long long p1 = min(a.HW, p0 + a.chunk);
-  const int nq = a.C >> 2;
-  float su[kGNMaxQuadsPerThread][4], sq[kGNMaxQuadsPerThread][4];
-#pragma unroll
-  for (int k = 0; k < kGNMaxQuadsPerThread; ++k)
-#pragma unroll
-    for (int e = 0; e < 4; ++e) su[k][e] = sq[k][e] = 0.f;
-  for (long long pb = p0 + ty; pb < p1; pb += (long long)TY * kGNUnroll) {
-    float4 v[kGNUnroll][kGNMaxQuadsPerThread];
-#pragma unroll
-    for (int u = 0; u < kGNUnroll; ++u) {
-      const long long p = pb + (long long)u * TY;
-      const long long row = (long long)b * a.HW + p;
-#pragma unroll
-      for (int k = 0; k < kGNMaxQuadsPerThread; ++k) {
-        const int qd = tx + k * TX;
-        if (p < p1 && qd < nq) {
-          const int c = qd << 2;
-          v[u][k] = c < a.C1 ? *reinterpret_cast<const float4*>(a.x1 + row * a.C1 + c)
-                             : *reinterpret_cast<const float4*>(a.x2 + row * a.C2 + (c - a.C1));
-        } else {
-          v[u][k] = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < kGNUnroll; ++u) {
-      const long long p = pb + (long long)u * TY;
-#pragma unroll
-      for (int k = 0; k < kGNMaxQuadsPerThread; ++k) {
-        su[k][0] += v[u][k].x; sq[k][0] += v[u][k].x * v[u][k].x;
-        su[k][1] += v[u][k].y; sq[k][1] += v[u][k].y * v[u][k].y;
-        su[k][2] += v[u][k].z; sq[k][2] += v[u][k].z * v[u][k].z;
-        su[k][3] += v[u][k].w; sq[k][3] += v[u][k].w * v[u][k].w;
-        const int qd = tx + k * TX;
-        if (p < p1 && qd < nq) *reinterpret_cast<float4*>(s_stage + (size_t)(p - p0) * a.C + (qd << 2)) = v[u][k];
-      }
-    }
-  }
-  {
-    float* mysum = s_red + (size_t)ty * 2 * a.C;
-#pragma unroll
-    for (int k = 0; k < kGNMaxQuadsPerThread; ++k) {
-      const int qd = tx + k * TX;
-      if (qd < nq) {
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          mysum[(qd << 2) + e] = su[k][e];
-          mysum[a.C + (qd << 2) + e] = sq[k][e];
-        }
-      }
-    }
-  }
-  __syncthreads();
-  {
-    const int per = TY * a.cpg;
-    for (int g = wid; g < a.G; g += nw) {
-      double dsu = 0.0, dsq = 0.0;
-      for (int e = lane; e < per; e += 32) {
-        const int y = e / a.cpg, c = g * a.cpg + (e - y * a.cpg);
-        const float* r = s_red + (size_t)y * 2 * a.C;
-        dsu += (double)r[c];
-        dsq += (double)r[a.C + c];
-      }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        dsu += __shfl_down_sync(0xffffffffu, dsu, o);
-        dsq += __shfl_down_sync(0xffffffffu, dsq, o);
-      }
-      if (lane == 0) {
-        double* dst = a.partial + (((long long)b * a.S + s) * a.G + g) * 2;
-        __stcg(dst, dsu);
-        __stcg(dst + 1, dsq);
-      }
-    }
-  }
-  // ---- rendezvous of the S resident CTAs of sample b
-  __threadfence();
-  __syncthreads();
-  unsigned int* ctr = a.counters + b;
-  if (tid == 0) {
-    atomicAdd(ctr, 1u);
-    unsigned int seen = 0, spins = 0;
-    do {
-      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(ctr) : "memory");
-      if (seen < (unsigned)a.S && ++spins > (1u << 26)) __trap();
-    } while (seen < (unsigned)a.S);
-  }
-  __syncthreads();
-  __threadfence();
-  {
-    // one warp per group: lane l sums partials l, l+32, l+64 (S <= 64 -> at most 2 per lane) in that order, then a
-    // fixed-shape shuffle tree
-    for (int g = wid; g < a.G; g += nw) {
-      const double* src = a.partial + ((long long)b * a.S * a.G + g) * 2;
-      const long long st = (long long)a.G * 2;
-      double p0s = 0.0, q0s = 0.0, p1s = 0.0, q1s = 0.0;
-      if (lane < a.S) {
-        p0s = __ldcg(src + lane * st);
-        q0s = __ldcg(src + lane * st + 1);
-      }
-      if (lane + 32 < a.S) {
-        p1s = __ldcg(src + (lane + 32) * st);
-        q1s = __ldcg(src + (lane + 32) * st + 1);
-      }
-      double dsu = p0s + p1s, dsq = q0s + q1s;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        dsu += __shfl_down_sync(0xffffffffu, dsu, o);
-        dsq += __shfl_down_sync(0xffffffffu, dsq, o);
-      }
-      if (lane == 0) {
-        const double inv_n = 1.0 / ((double)a.HW * a.cpg);
-        const double mean = dsu * inv_n;
-        double var = dsq * inv_n - mean * mean;
-        if (var < 0.0) var = 0.0;
-        s_mean[g] = (float)mean;
-        s_rstd[g] = rsqrtf((float)var + a.eps);
-      }
-    }
-  }
-  __syncthreads();
-  if (tid == 0) {   // departure: the last CTA of the sample re-arms the counter for the next launch
-    const unsigned int old = atomicAdd(ctr, 1u);
-    if (old == 2u * (unsigned)a.S - 1u) atomicExch(ctr, 0u);
-  }
-  for (int c = tid; c < a.C; c += nthr) {
-    const int g = c / a.cpg;
-    const float A = s_rstd[g] * __ldg(a.gamma + c);
-    s_A[c] = A;
-    s_B[c] = __ldg(a.beta + c) - s_mean[g] * A;
-  }
-  __syncthreads();
-  for (long long p = p0 + ty; p < p1; p += TY) {
-    const long long row = (long long)b * a.HW + p;
-#pragma unroll
-    for (int k = 0; k < kGNMaxQuadsPerThread; ++k) {
-      const int qd = tx + k * TX;
-      if (qd >= nq) continue;
-      const int c = qd << 2;
-      const float4 v = *reinterpret_cast<const float4*>(s_stage + (size_t)(p - p0) * a.C + c);
-      const float in[4] = {v.x, v.y, v.z, v.w};
-      const float4 A4 = *reinterpret_cast<const float4*>(s_A + c);
-      const float4 B4 = *reinterpret_cast<const float4*>(s_B + c);
-      float o[4] = {fmaf(in[0], A4.x, B4.x), fmaf(in[1], A4.y, B4.y), fmaf(in[2], A4.z, B4.z), fmaf(in[3], A4.w, B4.w)};
-      if (a.silu) {
-#pragma unroll
-        for (int e = 0; e < 4; ++e) o[e] = silu_f(o[e]);
-      }
-      const long long off = row * a.C + c;
-      op2_t h0 = ff2op2(o[0], o[1]);
-      op2_t h1 = ff2op2(o[2], o[3]);
-      uint2 pk;
-      pk.x = *reinterpret_cast<uint32_t*>(&h0);
-      pk.y = *reinterpret_cast<uint32_t*>(&h1);
-      *reinterpret_cast<uint2*>(a.out + off) = pk;
-      if (a.raw_out) {
-        op2_t r0 = ff2op2(in[0], in[1]);
-        op2_t r1 = ff2op2(in[2], in[3]);
-        uint2 rk;
-        rk.x = *reinterpret_cast<uint32_t*>(&r0);
-        rk.y = *reinterpret_cast<uint32_t*>(&r1);
-        *reinterpret_cast<uint2*>(a.raw_out + off) = rk;
-      }
-      if (a.cat_out) *reinterpret_cast<float4*>(a.cat_out + off) = v;
-    }
-  }
-}
-
 // one warp per row; the row is read once into registers: NV float4 per lane (C <= 128*NV), NV a template constant
 template <int NV>
 __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict__ x, long long rows, int C, float eps,
@@ -680,8 +486,6 @@ using namespace aedit;
 
 static thread_local long long g_gn_stream_min_bytes = 8ll << 20;
 extern "C" void ae_set_gn_stream_min_bytes(int64_t bytes) { g_gn_stream_min_bytes = bytes; }
-static thread_local int g_gn_fused = 0;  // measured no faster than stats + apply (profiles/r01_microbench_v15_gn_resident.log): opt-in
-extern "C" void ae_set_gn_fused(int on) { g_gn_fused = on ? 1 : 0; }
 
 extern "C" int64_t ae_groupnorm_workspace_bytes(int B, int groups) {
   // partial sums [B, kMaxSplits, G, 2] double + stats [B, G, 2] float + counters [B] u32 (must start zeroed)
@@ -730,30 +534,6 @@ static int groupnorm_impl(const float* x1, int C1, const float* x2, int C2, int 
   a.partial = reinterpret_cast<double*>(wsb);
   a.stats = reinterpret_cast<float*>(wsb + (size_t)B * kMaxSplits * groups * 2 * 8);
   a.counters = reinterpret_cast<unsigned int*>(wsb + (size_t)B * kMaxSplits * groups * 2 * 8 + (size_t)B * groups * 2 * 4);
-  if (g_gn_fused && groups % 2 == 0 && !cs1) {
-    // single resident launch (see gn_resident_kernel): the whole grid must fit on the machine, one CTA per SM
-    static int n_sm = 0;
-    if (n_sm == 0) {
-      int dev = 0;
-      cudaGetDevice(&dev);
-      if (cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n_sm <= 0) n_sm = 1;
-      cudaFuncSetAttribute(gn_resident_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-      cudaGetLastError();
-    }
-    // slices per sample depend on the geometry only (never on B), so a sample's statistics have the same bits in
-    // every batch this path serves
-    int S = kMaxSplits;
-    if (S > HW / 2) S = (int)(HW / 2);
-    if (S >= 2) {
-      a.chunk = ceil_div64(HW, S);
-      a.S = (int)ceil_div64(HW, a.chunk);
-      const size_t smem = (size_t)(2 * groups + 2 * C + TY * 2 * C) * sizeof(float) + (size_t)a.chunk * C * sizeof(float);
-      if (smem <= 200 * 1024 && (long long)a.S * B <= n_sm) {
-        launch_kernel(gn_resident_kernel, dim3(a.S, B), dim3(TX, TY), smem, as_stream(stream), a);
-        return launched("ae_groupnorm(resident)");
-      }
-    }
-  }
   // position splits: enough CTAs to cover the machine at small batch, never more than kMaxSplits per sample
   int S = (int)ceil_div64(HW, 4 * TY);
   const int want = (296 + B - 1) / B;

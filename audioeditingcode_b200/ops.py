@@ -41,7 +41,6 @@ class CudaOps:
         self.act_dtype = _lib.operand_torch_dtype()      # fp16 (default build) or bf16 (AEDIT_OPERANDS=bf16)
         self._gn_ws = {}
         self._splitk_ws = {}
-        self._attn_ws = {}
         import os
         # programmatic dependent launch: GEMM-only mode (weight prefetch ahead of the dependency wait) measured +2-4 %
         # end to end on B200, all-kernel mode measured slower (profiles/r01_bench_v7_*, r01_bench_v8_*)
@@ -52,16 +51,12 @@ class CudaOps:
             self.lib.ae_set_gn_stream_min_bytes(int(os.environ["AEDIT_GN_STREAM_MIN_BYTES"]))
         if "AEDIT_PERSIST_MIN_TILES" in os.environ:
             self.lib.ae_set_persistent_min_tiles(int(os.environ["AEDIT_PERSIST_MIN_TILES"]))
-        if "AEDIT_ATTN_SPLIT" in os.environ:
-            self.lib.ae_set_attention_split(int(os.environ["AEDIT_ATTN_SPLIT"]))
         if "AEDIT_SHALLOW_KB" in os.environ:
             self.lib.ae_set_shallow_kblocks(int(os.environ["AEDIT_SHALLOW_KB"]))
         if "AEDIT_TILE_MODEL" in os.environ:
             self.lib.ae_set_tile_model(int(os.environ["AEDIT_TILE_MODEL"]))
         if "AEDIT_FAST_EPILOGUE" in os.environ:
             self.lib.ae_set_fast_epilogue(int(os.environ["AEDIT_FAST_EPILOGUE"]))
-        if "AEDIT_GN_FUSED" in os.environ:
-            self.lib.ae_set_gn_fused(int(os.environ["AEDIT_GN_FUSED"]))
         if "AEDIT_SPLITK_CTAS" in os.environ:
             self.lib.ae_set_splitk_ctas(int(os.environ["AEDIT_SPLITK_CTAS"]))
 
@@ -186,32 +181,11 @@ class CudaOps:
         inner = out.shape[-1]
         check(self.lib.ae_geglu(_p(h), out.numel() // inner, inner, _p(out), _stream()), "ae_geglu")
 
-    ATTN_WS_MAX_BYTES = 64 << 20
-
-    def _attn_workspace(self, B, heads, Tq, d, device):
-        """Split-KV workspace for small grids (ae_attention_ws); None when it would be large (big batches never split)."""
-        n = int(self.lib.ae_attention_workspace_bytes(B, heads, Tq, d))
-        if n > self.ATTN_WS_MAX_BYTES:
-            return None
-        key = (B, heads, Tq, d, str(device))
-        ws = self._attn_ws.get(key)
-        if ws is None:
-            ws = torch.zeros((n + 3) // 4, dtype=torch.float32, device=device)
-            self._attn_ws[key] = ws
-        return ws
-
     def attention(self, q, k, v, out, heads, d, scale, Tq, Tk, B, ld_q, bs_q, ld_k, bs_k, ld_v, bs_v, kv_map=None,
                   bias=None):
-        ws = self._attn_workspace(B, heads, Tq, d, q.device) if Tk >= 256 else None
-        if ws is None:
-            check(self.lib.ae_attention(_p(q), ld_q, bs_q, _p(k), ld_k, bs_k, _p(v), ld_v, bs_v, _p(kv_map), _p(bias),
-                                        0 if bias is None else bias.stride(0), B, heads, d, Tq, Tk, scale, _p(out),
-                                        out.stride(-2), Tq * out.stride(-2), _stream()), "ae_attention")
-        else:
-            check(self.lib.ae_attention_ws(_p(q), ld_q, bs_q, _p(k), ld_k, bs_k, _p(v), ld_v, bs_v, _p(kv_map), _p(bias),
-                                           0 if bias is None else bias.stride(0), B, heads, d, Tq, Tk, scale, _p(out),
-                                           out.stride(-2), Tq * out.stride(-2), _p(ws), ws.numel() * 4, _stream()),
-                  "ae_attention_ws")
+        check(self.lib.ae_attention(_p(q), ld_q, bs_q, _p(k), ld_k, bs_k, _p(v), ld_v, bs_v, _p(kv_map), _p(bias),
+                                    0 if bias is None else bias.stride(0), B, heads, d, Tq, Tk, scale, _p(out),
+                                    out.stride(-2), Tq * out.stride(-2), _stream()), "ae_attention")
 
     def timestep_embedding(self, t, dim, out):
         check(self.lib.ae_timestep_embedding(_p(t), t.shape[0], dim, _p(out), _stream()), "ae_timestep_embedding")

@@ -73,8 +73,6 @@ class GraphedForward:
         # batch is cut in two halves captured on two forked streams of the same graph, so the two dependency chains
         # interleave on the SMs.  Each chain owns its workspaces (second CudaOps instance).
         self.dual = engine.dual_stream and B % 2 == 0 and B <= engine.dual_stream_max_b and lane == 0
-        if self.dual:
-            engine.ops.lib.ae_set_gn_fused(0)     # two concurrent resident GroupNorm grids could starve each other
         cur = torch.cuda.current_stream()
         side = capture_stream if capture_stream is not None else torch.cuda.Stream(priority=-1 if lane >= 1 else 0)
         self._side2 = torch.cuda.Stream() if self.dual else None
@@ -83,7 +81,6 @@ class GraphedForward:
         pdlx = int(os.environ.get(("AEDIT_PDLX_FWD", "AEDIT_PDLX_SOLO", "AEDIT_PDLX_SHARED")[lane],
                                   os.environ.get("AEDIT_PDL_EXTRA", str(engine.pdl_extra[lane]))))
         engine.ops.lib.ae_set_pdl_extra(pdlx)
-        engine.ops.lib.ae_set_headroom(1 if (lane == 0 and engine.fwd_headroom and B > 8) else 0)
         if lane >= 1:
             engine.ops = engine.ops_b()
             if os.environ.get("AEDIT_REV_PRIORITY", "1") != "0":
@@ -105,7 +102,6 @@ class GraphedForward:
                 engine.ops.lib.ae_set_shared_sm(0)
             engine.ops = main_ops
             engine.ops.lib.ae_set_pdl_extra(int(os.environ.get("AEDIT_PDL_EXTRA", "0")))
-            engine.ops.lib.ae_set_headroom(0)
 
     def _run(self, engine):
         if not self.dual:
@@ -159,7 +155,6 @@ class UNetEngine:
         self.dual_stream = os.environ.get("AEDIT_DUAL_STREAM", "0") != "0"
         self.dual_stream_max_b = int(os.environ.get("AEDIT_DUAL_STREAM_MAX_B", "4"))
         self._ops_b = None
-        self.fwd_headroom = os.environ.get("AEDIT_FWD_HEADROOM", "0") != "0"
         self.fold_cross_attn = os.environ.get("AEDIT_FOLD_CROSS_ATTN", "1") != "0" and hasattr(ops, "lib")
         self.graph_placement_tries = int(os.environ.get("AEDIT_GRAPH_PLACEMENT_TRIES", "4"))
         self.shared_sm_rings = os.environ.get("AEDIT_SHARED_SM_RINGS", "1") != "0"

@@ -66,10 +66,6 @@ void ae_set_gn_stream_min_bytes(int64_t bytes);
 /* Multi-wave 128-wide GEMM grids whose K loop has at most this many 64-wide blocks use a 2-stage operand ring (three
  * CTAs per SM instead of two).  0 = never.  Same bits. */
 void ae_set_shallow_kblocks(int kb);
-/* 1: GEMM grids launched (captured) from now on keep ONE CTA per SM (they request at least half of the SM's shared
- * memory), leaving the other half to the sub-wave kernels of a latency-bound chain on another stream — the
- * forward-process chunks are captured this way when they overlap the reverse process.  0 (default): 2-3 CTAs per SM. */
-void ae_set_headroom(int on);
 /* GEMM grids of at least this many 128 x BN output tiles (no K split, no batch) run as persistent CTAs, one per SM,
  * with the accumulator double-buffered in TMEM so that a tile's epilogue overlaps the next tile's main loop — for the
  * shapes where that measured faster (linears with a bf16 / GEGLU output or >= 9 K blocks).  Default 296; 0 = never.
@@ -102,11 +98,6 @@ void ae_set_fast_epilogue(int mode);
 void ae_set_tile_model(int on);
 
 
-/* GroupNorm as ONE launch whenever the grid (<= 64 position slices per sample x B) fits on the machine with one CTA
- * per SM and a slice fits in shared memory: the CTAs of a sample rendezvous on an arrival counter between the
- * statistics and the normalisation.  Default OFF: measured 18.6 us vs 2 x 9.0 us for [2,4096,192] — no gain.  Turn it off when several GroupNorm grids may run CONCURRENTLY
- * (two streams): CTAs of one grid waiting for peers that cannot be scheduled would hang (the kernel traps then). */
-void ae_set_gn_fused(int on);
 
 /* ------------------------------------------------------------------------------------------------
  * Scheduler table  (code/models.py:85-158, :539-549; integer index math of
@@ -319,19 +310,6 @@ int ae_attention(const void* q, int64_t ld_q, int64_t q_batch_stride, const void
  * strides run on the tcgen05 kernel (csrc/attn_tc.cu: S and the per-block P.V product in TMEM, Q / K / V by TMA, online
  * softmax from tcgen05.ld); the rest on the mma.sync kernel.  ae_set_attention_tc(0) forces the mma.sync kernel (A/B). */
 void ae_set_attention_tc(int on);
-
-/* Same, with a workspace that lets the kernel split the KEYS of small grids over several CTAs (split-KV; the partial
- * accumulators are merged in split order by the last CTA of a query tile to arrive, so the result is deterministic).
- * workspace: ae_attention_workspace_bytes(B, heads, Tq, d) bytes, its first B*heads*ceil(Tq/64)*4 bytes ZERO-initialised
- * once by the caller (arrival counters, re-armed by the kernel).  ae_set_attention_split: 0 auto, 1 never (the default:
- * at batch 2 the split measured slower, 6.04 -> 6.14-6.37 ms per evaluation), n forced. */
-int64_t ae_attention_workspace_bytes(int B, int heads, int Tq, int d);
-void ae_set_attention_split(int n);
-int ae_attention_ws(const void* q, int64_t ld_q, int64_t q_batch_stride, const void* k, int64_t ld_k,
-                    int64_t k_batch_stride, const void* v, int64_t ld_v, int64_t v_batch_stride,
-                    const int32_t* kv_batch_map, const float* key_bias, int64_t ld_bias, int B, int heads, int d, int Tq,
-                    int Tk, float scale, void* out, int64_t ld_o, int64_t o_batch_stride, void* workspace,
-                    int64_t workspace_bytes, ae_stream stream);
 
 /* Sinusoidal timestep embedding [cos | sin] (util.py:173-197), bf16 out [B, dim]; t: int64 [B] */
 int ae_timestep_embedding(const int64_t* t, int B, int dim, void* out_bf16, ae_stream stream);

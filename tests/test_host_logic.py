@@ -219,4 +219,3 @@ def test_c_abi_argument_errors_without_a_device():
     rc = lib.ae_groupnorm(dummy, 60, None, 0, 1, 64, 32, 1e-5, dummy, dummy, 1, dummy, None, None, dummy, None)
     assert rc == -1 and b"divisible" in lib.ae_last_error()
     assert lib.ae_layernorm(dummy, 4, 4096, 1e-5, dummy, dummy, dummy, None) == -1
-    assert lib.ae_attention_workspace_bytes(2, 8, 1024, 48) > 0

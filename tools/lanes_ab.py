@@ -11,7 +11,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench as B  # noqa: E402
 from audioeditingcode_b200.ddm_inversion import inversion_utils as IU  # noqa: E402
 
-DEFAULTS = dict(overlap=1, fb=50, head=10, rev="adaptive", pdlx=0, gnstream=1, pf=0, ps=0, pc=15, skb=0, hr=0, pmt=296, gpt=4, rep=0, ssm=1)
+DEFAULTS = dict(overlap=1, fb=50, head=10, rev="adaptive", pdlx=0, gnstream=1, pf=0, ps=0, pc=15, skb=0, pmt=296, gpt=4, rep=0, ssm=1)
 
 
 def timed(fn, reps, flush):
@@ -48,13 +48,12 @@ def main():
         for kv in v.split(","):
             k, val = kv.split("=")
             o[k] = val if k == "rev" else int(val)
-        key = (o["pdlx"], o["gnstream"], o["pf"], o["ps"], o["pc"], o["skb"], o["hr"], o["pmt"], o["gpt"], o["rep"], o["ssm"])
+        key = (o["pdlx"], o["gnstream"], o["pf"], o["ps"], o["pc"], o["skb"], o["pmt"], o["gpt"], o["rep"], o["ssm"])
         if key != last:
             torch.cuda.synchronize()
             m.engine._graphs.clear()
             m.engine.pdl_extra = [o["pf"] or o["pdlx"], o["ps"] or o["pdlx"], o["pc"] or o["pdlx"]]
             lib.ae_set_shallow_kblocks(o["skb"])
-            m.engine.fwd_headroom = bool(o["hr"])
             lib.ae_set_persistent_min_tiles(o["pmt"])
             m.engine.graph_placement_tries = o["gpt"]
             m.engine.shared_sm_rings = bool(o["ssm"])

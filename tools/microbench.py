@@ -73,13 +73,8 @@ for (B, HW, C) in [(2, 64, 960), (2, 4096, 192), (1, 4096, 192), (2, 4096, 384),
     gx = torch.randn(B, HW, C, device=dev)
     gg, gb = torch.ones(C, device=dev), torch.zeros(C, device=dev)
     go = torch.empty(B, HW, C, device=dev, dtype=BF)
-    for fused in (0, 1):
-        if fused and B > 8:
-            continue
-        ops.lib.ae_set_gn_fused(fused)
-        bench(f"groupnorm B={B} HW={HW} C={C} " + ("(single resident launch)" if fused else "(stats + apply launches)"),
-              lambda: ops.groupnorm(gx, None, gg, gb, 1e-5, 32, True, go), launches_per_call=1 if fused else 2)
-    ops.lib.ae_set_gn_fused(1)
+    bench(f"groupnorm B={B} HW={HW} C={C} (stats + apply launches)",
+          lambda: ops.groupnorm(gx, None, gg, gb, 1e-5, 32, True, go), launches_per_call=2)
 
 for bn in (32, 64, 128):
     fn, fl = gemm_case(128, 960, 960, bn, split=1)
