@@ -1,12 +1,15 @@
 #!/bin/bash
-# The GPU validation sequence of this repo, for `gpurun -- 'bash tools/gpu_check.sh [quick|full|ncu|sanitize|synccheck]'`.
+# The GPU validation sequence of this repo, for `gpurun -- 'bash tools/gpu_check.sh [quick|full|ncu|sanitize|synccheck][-only]'`.
 # Everything it writes goes to gpurun_out/ (scratch); copy what should be kept into profiles/.
 set -u
 mode=${1:-quick}
 mkdir -p gpurun_out
-python -m pytest tests -m gpu -q -x > gpurun_out/pytest_gpu.log 2>&1; echo "pytest -m gpu rc=$?"; tail -2 gpurun_out/pytest_gpu.log
-python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?"; tail -1 gpurun_out/smoke.log
-timeout 1500 python bench.py --steps 5 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?"; tail -c 600 gpurun_out/bench.json
+if [ "${mode%-only}" = "$mode" ]; then     # "<mode>-only" skips the suite / smoke / bench preamble
+  python -m pytest tests -m gpu -q -x > gpurun_out/pytest_gpu.log 2>&1; echo "pytest -m gpu rc=$?"; tail -2 gpurun_out/pytest_gpu.log
+  python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?"; tail -1 gpurun_out/smoke.log
+  timeout 1500 python bench.py --steps 5 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?"; tail -c 600 gpurun_out/bench.json
+fi
+mode=${mode%-only}
 if [ "$mode" = full ]; then
   for c in tango-10s sdedit-30s pc-drift; do
     timeout 900 python bench.py --config $c --steps 3 --warmup 3 --no-cpu-baseline --no-ends --queue-group 0 > gpurun_out/bench_$c.json 2> gpurun_out/bench_$c.err; echo "$c rc=$?"
