@@ -56,8 +56,16 @@ class PipelineWrapper(torch.nn.Module):
     # Finite-difference step pc_drift.get_eigenvectors takes through THIS evaluator when the caller does not pass
     # `fd_const`: the U-Net here runs on 16-bit tensor-core operands, which cannot resolve the
     # reference's const = 1e-3 (1e-3 / sqrt(D) per element); results are returned in units of the caller's `const`.
-    # None = take the caller's `const` literally.
-    pc_fd_const: Optional[float] = 1.0
+    # None = take the caller's `const` literally.  1.0 resolves through fp16 operands (11 significand bits; min cos 0.96 vs the
+    # reference's fp32 finite differences through the tiny U-Net); the bf16 build (8 bits) needs 8x the step for the same
+    # resolution (measured 0.59 at 1.0, 0.93 at 4.0).
+    @property
+    def pc_fd_const(self) -> Optional[float]:
+        return getattr(self, "_pc_fd_const", 8.0 if _lib.operand_torch_dtype() == torch.bfloat16 else 1.0)
+
+    @pc_fd_const.setter
+    def pc_fd_const(self, value: Optional[float]) -> None:
+        self._pc_fd_const = value
 
     def __init__(self, model_id: str, device: torch.device, double_precision: bool = False,
                  token: Optional[str] = None, *args, weights: Optional[Dict[str, torch.Tensor]] = None,

@@ -124,8 +124,8 @@ def get_eigenvectors(ldm_stable, xt: torch.Tensor, text_emb: PromptEmbeddings, u
     perturbation of 1e-3 / sqrt(D) per element — below the resolution of 16-bit tensor-core operands (and of the TF32
     matmuls the reference itself enables on a GPU, utils.py:116; its CPU fp32 run is the one that resolves it, DESIGN.md
     §2).  Resolution order: the argument; env AEDIT_PC_FD_CONST (a number, or "reference" for the caller's `const`);
-    the evaluator's own `ldm_stable.pc_fd_const` (1.0 for the wrappers of models.py, absent = `const` for any other
-    evaluator).  All outputs stay in units of the caller's `const`
+    the evaluator's own `ldm_stable.pc_fd_const` (wrappers of models.py: 1.0 with fp16 operands, 8.0 with the bf16 build;
+    absent = `const` for any other evaluator).  All outputs stay in units of the caller's `const`
     (tests/test_gpu_pc_drift.py::test_unet_jvp_resolves_with_fd_const)."""
     import os as _os
     if fd_const is None:

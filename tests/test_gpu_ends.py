@@ -68,7 +68,9 @@ def test_hifigan_vs_vendored_generator():
     assert w2.shape == (2, wav.shape[0])
     r0, r1 = _rel(w2[0], wav), _rel(w2[1], voc(mel2[1]))
     print(f"batched vocoder vs single calls: rel-L2 {r0:.2e} {r1:.2e}")
-    assert r0 < 2e-3 and r1 < 2e-3
+    from audioeditingcode_b200 import _lib
+    tol = 8e-3 if _lib.load().ae_operand_dtype() == 0 else 2e-3          # bf16-operand build: 8x the operand rounding
+    assert r0 < tol and r1 < tol
     assert _rel(w2[0], g["wav"][0]) < 2e-2
 
 

@@ -396,7 +396,8 @@ def test_multi_clip_batched_matches_single_clip_calls():
                                             prompts=tgt[k], neg_prompts=[""], cfg_scales=[5.0], zs=zs[:ts])
         r_z, r_x, r_w = _rel(zs_b[k], zs.cpu()), _rel(xts_b[k], xts.cpu()), _rel(w_b[k:k + 1], w.cpu())
         print(f"clip {k}: batched vs single rel-L2 zs {r_z:.2e} xts {r_x:.2e} edit {r_w:.2e}")
-        assert r_x < 1e-6 and r_z < 5e-3 and r_w < 3e-2
+        tol_z, tol_w = (2e-2, 1e-1) if _bf16_build() else (5e-3, 3e-2)
+        assert r_x < 1e-6 and r_z < tol_z and r_w < tol_w
 
 
 def test_clip_queue_pipelined_matches_one_at_a_time():

@@ -245,7 +245,7 @@ def test_unet_jvp_resolves_with_fd_const():
     assert ((x0_ref.cpu() - g["x0_pred"]).norm() / g["x0_pred"].norm()).item() < 1e-2
     n_ev = g["scaled_in"].shape[1]
     res = {}
-    for step in (1e-3, 0.05, 0.2, 0.5, 1.0, 2.0, 4.0):
+    for step in (1e-3, 0.05, 0.2, 0.5, 1.0, 2.0, 4.0, 8.0):
         cos_min, ratio = 1.0, []
         for i in range(1, g["scaled_in"].shape[0]):                  # iteration 0 starts from white noise; skip it
             v_unit = (g["scaled_in"][i] / 1e-3).cuda()               # the reference's unit directions of this iteration
@@ -261,17 +261,23 @@ def test_unet_jvp_resolves_with_fd_const():
         print(f"fd step {step}: min cos(Ab_ours, Ab_reference) {cos_min:.4f}, |Ab| ratio {min(ratio):.3f}..{max(ratio):.3f}")
     # a resolvable step reproduces the reference's finite differences (which carry ~3 % rounding noise of their own at
     # const = 1e-3 in fp32; the larger step adds second-order terms of the network): direction and length
-    best = max(res[s][0] for s in (0.2, 0.5, 1.0))
-    assert best > 0.9 and res[0.5][0] > 0.9 and 0.9 < res[0.5][1] and res[0.5][2] < 1.1
-    assert res[1.0][0] > 0.93 and 0.9 < res[1.0][1] and res[1.0][2] < 1.1    # the wrappers' default step (pc_fd_const)
+    from audioeditingcode_b200 import _lib
+    default_step = m.pc_fd_const               # the wrappers' own step: 1.0 with fp16 operands, 8.0 with bf16 operands
+    if _lib.load().ae_operand_dtype() == 1:
+        assert default_step == 1.0
+        best = max(res[s][0] for s in (0.2, 0.5, 1.0))
+        assert best > 0.9 and res[0.5][0] > 0.9 and 0.9 < res[0.5][1] and res[0.5][2] < 1.1
+        assert res[1.0][0] > 0.93
+    else:
+        assert default_step == 8.0
+    assert res[default_step][0] > 0.9 and 0.9 < res[default_step][1] and res[default_step][2] < 1.1
     assert res[1e-3][0] < 0.5                  # the reference's own step is NOT resolvable through 16-bit operands
     # get_eigenvectors end to end: the wrapper's own default step (models.PipelineWrapper.pc_fd_const) is what runs when
     # the caller passes nothing, outputs in units of the caller's const; AEDIT_PC_FD_CONST=reference forces const itself
-    assert m.pc_fd_const == 1.0
     start = g["scaled_in"][1].reshape(n_ev, *xt.shape[1:]) / 1e-3
     args = (m, xt, txt, unc, lat, torch.ones_like(xt), t, x0_ref, PC.PCStreamChoice.BOTH, 1e-3, 3.0, 8, False, 1, n_ev)
     ev, eigval, in_corr, in_norm, _, _ = PC.get_eigenvectors(*args, init_eigvecs=start * 1.0)
-    ev1, eigval1, *_ = PC.get_eigenvectors(*args, init_eigvecs=start * 1.0, fd_const=1.0)
+    ev1, eigval1, *_ = PC.get_eigenvectors(*args, init_eigvecs=start * 1.0, fd_const=default_step)
     assert torch.equal(ev, ev1) and torch.equal(eigval, eigval1)
     E = ev.reshape(n_ev, -1)
     assert (E @ E.T - torch.eye(n_ev, device="cuda")).abs().max().item() < 1e-5 and torch.isfinite(eigval).all()
