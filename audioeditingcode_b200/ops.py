@@ -51,6 +51,8 @@ class CudaOps:
             self.lib.ae_set_gn_stream_min_bytes(int(os.environ["AEDIT_GN_STREAM_MIN_BYTES"]))
         if "AEDIT_PERSIST_MIN_TILES" in os.environ:
             self.lib.ae_set_persistent_min_tiles(int(os.environ["AEDIT_PERSIST_MIN_TILES"]))
+        if "AEDIT_ATTN_TC" in os.environ:
+            self.lib.ae_set_attention_tc(int(os.environ["AEDIT_ATTN_TC"]))      # 0: mma.sync kernel everywhere (A/B)
         if "AEDIT_SHALLOW_KB" in os.environ:
             self.lib.ae_set_shallow_kblocks(int(os.environ["AEDIT_SHALLOW_KB"]))
         if "AEDIT_TILE_MODEL" in os.environ:
