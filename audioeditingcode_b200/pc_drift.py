@@ -108,6 +108,20 @@ def forward_directional(ldm_stable, xt: torch.Tensor, timestep: torch.Tensor, la
     return prev, x0p
 
 
+def resolve_fd_const(ldm_stable, const: float, fd_const: Optional[float] = None) -> float:
+    """The finite-difference step get_eigenvectors actually takes (see its docstring): the `fd_const` argument, else env
+    AEDIT_PC_FD_CONST (a number, or "reference" / "const" for the caller's `const`), else the evaluator's own
+    `pc_fd_const` attribute, else `const` — the reference's behaviour (pc_drift.py:130,140)."""
+    import os as _os
+    if fd_const is None:
+        env = _os.environ.get("AEDIT_PC_FD_CONST", "")
+        if env:
+            fd_const = None if env.lower() in ("reference", "const") else float(env)
+        else:
+            fd_const = getattr(ldm_stable, "pc_fd_const", None)
+    return float(const if fd_const is None else fd_const)
+
+
 def get_eigenvectors(ldm_stable, xt: torch.Tensor, text_emb: PromptEmbeddings, uncond_emb: PromptEmbeddings,
                      latents: torch.Tensor, mask: torch.Tensor, t: torch.Tensor, x0_pred: torch.Tensor,
                      pc_mode: PCStreamChoice = PCStreamChoice.BOTH, const: float = 1e-3, cfg_tar: float = 3,
@@ -127,16 +141,8 @@ def get_eigenvectors(ldm_stable, xt: torch.Tensor, text_emb: PromptEmbeddings, u
     the evaluator's own `ldm_stable.pc_fd_const` (wrappers of models.py: 1.0 with fp16 operands, 8.0 with the bf16 build;
     absent = `const` for any other evaluator).  All outputs stay in units of the caller's `const`
     (tests/test_gpu_pc_drift.py::test_unet_jvp_resolves_with_fd_const)."""
-    import os as _os
-    if fd_const is None:
-        env = _os.environ.get("AEDIT_PC_FD_CONST", "")
-        if env:
-            fd_const = None if env.lower() in ("reference", "const") else float(env)
-        else:
-            fd_const = getattr(ldm_stable, "pc_fd_const", None)
     const_ret = const
-    if fd_const is not None:
-        const = float(fd_const)
+    const = resolve_fd_const(ldm_stable, const, fd_const)
     from . import parallel as _par
     lib = _lib.load()
     dev = ldm_stable.device

@@ -219,3 +219,26 @@ def test_c_abi_argument_errors_without_a_device():
     rc = lib.ae_groupnorm(dummy, 60, None, 0, 1, 64, 32, 1e-5, dummy, dummy, 1, dummy, None, None, dummy, None)
     assert rc == -1 and b"divisible" in lib.ae_last_error()
     assert lib.ae_layernorm(dummy, 4, 4096, 1e-5, dummy, dummy, dummy, None) == -1
+
+
+def test_pc_drift_finite_difference_step_resolution(monkeypatch):
+    """get_eigenvectors' step: argument > AEDIT_PC_FD_CONST > the evaluator's pc_fd_const > the caller's const (the
+    reference's behaviour, pc_drift.py:130,140); the wrappers' own step follows the operand type of the loaded library."""
+    import types
+    from audioeditingcode_b200 import pc_drift as PC, models, _lib
+    plain, tuned = types.SimpleNamespace(), types.SimpleNamespace(pc_fd_const=2.0)
+    monkeypatch.delenv("AEDIT_PC_FD_CONST", raising=False)
+    assert PC.resolve_fd_const(plain, 1e-3) == 1e-3
+    assert PC.resolve_fd_const(tuned, 1e-3) == 2.0
+    assert PC.resolve_fd_const(tuned, 1e-3, 0.5) == 0.5
+    monkeypatch.setenv("AEDIT_PC_FD_CONST", "reference")
+    assert PC.resolve_fd_const(tuned, 1e-3) == 1e-3
+    monkeypatch.setenv("AEDIT_PC_FD_CONST", "4")
+    assert PC.resolve_fd_const(tuned, 1e-3) == 4.0 and PC.resolve_fd_const(tuned, 1e-3, 0.5) == 0.5
+    monkeypatch.delenv("AEDIT_PC_FD_CONST")
+    want = 8.0 if _lib.load().ae_operand_dtype() == 0 else 1.0
+    w = models.PipelineWrapper.__new__(models.PipelineWrapper)      # the property needs no loaded model
+    torch.nn.Module.__init__(w)
+    assert w.pc_fd_const == want
+    w.pc_fd_const = None
+    assert w.pc_fd_const is None and PC.resolve_fd_const(w, 1e-3) == 1e-3
