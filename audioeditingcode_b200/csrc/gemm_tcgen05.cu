@@ -6,12 +6,12 @@
 // diffusers ResnetBlock2D + Transformer2DModel driven from code/models.py:293-388; in-tree twins
 // code/audioldm/latent_diffusion/openaimodel.py:213-244, attention.py:220-323).
 //
-// Tile: 128 (M) x BN (N) x 64 (K) bf16, fp32 accumulators in TMEM.  One CTA per output tile, 6 warps:
-//   warp 0  TMA producer   (cp.async.bulk.tensor, 128B-swizzled K-major tiles, 3-stage mbarrier ring; the ring is
-//           kept short so 2-3 CTAs are resident per SM and one CTA's epilogue overlaps another's main loop)
+// Tile: 128 (M) x BN (N) x 64 (K) of 16-bit operands (op_t: fp16; bf16 with -DAE_OPERAND_BF16), fp32 accumulators in TMEM.
+//   gemm_tcgen05_kernel: one CTA per output tile, 6 warps (gemm_persistent_kernel further down: one CTA per SM)
+//   warp 0  TMA producer (cp.async.bulk.tensor, 128B-swizzled K-major tiles, 2..6-stage mbarrier ring; short rings keep 2-3 CTAs per SM)
 //   warp 1  TMEM allocator + single-thread tcgen05.mma issuer (4 UMMAs of K=16 per stage) + tcgen05.commit
-//   warps 2-5  epilogue: tcgen05.ld 32 lanes x 32 columns per warp, fused bias / time-embedding row bias /
-//              residual / SiLU / GEGLU, direct vectorised global stores (each thread owns one output row segment)
+//   warps 2-5  epilogue: tcgen05.ld; fused bias / time-embedding row bias / residual / SiLU / GEGLU / GroupNorm column
+//              statistics; row-per-thread stores, or (fp32 outputs) a shared-memory transpose for row-contiguous accesses
 // Implicit convolution: the A operand is a channels-last image [B,H,W,C]; K-block kb = (tap, 64-channel slab);
 // the producer issues a 4-D TMA box {64 ch, Wb, Hb, Bb} at (c0, w0+dw, h0+dh, b0) — out-of-bounds rows/cols are
 // zero-filled by TMA, which is exactly the convolution's zero padding.  The 128 tile rows are the flattened
