@@ -4,14 +4,14 @@
 // short sequences (T < 128) and odd layouts.
 //
 // One CTA owns NT tiles of 128 queries of one (batch, head) and walks the keys in blocks of BKEYS:
-//   warp 4*NT      TMA producer: Q tile(s) once, then a 2-stage ring of K / V blocks (cp.async.bulk.tensor, 128-byte
+//   warp 4*NT*SP   TMA producer: Q tile(s) once, then a 2-stage ring of K / V blocks (cp.async.bulk.tensor, 128-byte
 //                  swizzle; the head's d columns are addressed through a 4-D tensor map {d, heads, T, batch}, so columns
 //                  beyond d and rows beyond T are zero-filled by the TMA unit = the padding to 64 / 128 columns)
-//   warp 4*NT+1    TMEM allocator + single-thread MMA issuer:
+//   warp 4*NT*SP+1 TMEM allocator + single-thread MMA issuer:
 //                    S = Q K^T      tcgen05.mma kind::f16, A = Q (K-major), B = K block (K-major), D = S in TMEM (fp32)
 //                    O_blk = P V    A = P (K-major, written to shared memory by the softmax warps),
 //                                   B = V block exactly as TMA delivers it = MN-major operand (ptx::umma_desc_mn_sw128)
-//   warps 0..4*NT-1  softmax: thread i of a tile's warpgroup owns query row i = TMEM lane i: tcgen05.ld of the S row,
+//   warps 0..4*NT*SP-1  softmax: query row i = TMEM lane i is owned by SP threads (SP = 2: half of the key columns each): S row,
 //                  scale / key bias, block maximum, P = exp2(s - m_ref) -> operand type -> shared memory in the swizzled
 //                  K-major layout, row sum.  The output accumulates IN TMEM across the key blocks (tcgen05.mma with the
 //                  accumulate flag): TMEM reads cost 64 B/clk, so S is read exactly once per block and O only when it must
